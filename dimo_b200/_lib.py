@@ -1,0 +1,87 @@
+"""ctypes binding of libdimo_b200.so (include/dimo_b200.h).  No CPU fallback: if the library is
+missing or a call fails this raises, it never routes around the CUDA path."""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libdimo_b200.so")
+
+_lib = None
+
+c_int, c_i64, c_f32, c_vp, c_sz = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
+
+# name -> (restype, argtypes); mirrors include/dimo_b200.h one to one
+_SIGS = {
+    "dimo_abi_version": (c_int, []),
+    "dimo_last_error": (ctypes.c_char_p, []),
+    "dimo_device_info": (c_int, [c_vp]),
+    "dimo_raster_scan_temp_bytes": (c_sz, [c_i64]),
+    "dimo_raster_sort_temp_bytes": (c_sz, [c_i64]),
+    "dimo_raster_preprocess": (c_int, [c_int] * 6 + [c_f32, c_vp] + [c_vp, c_i64] * 6 + [c_vp] * 4 + [c_vp, c_sz, c_vp, c_vp]),
+    "dimo_raster_bin": (c_int, [c_int] * 4 + [c_i64] + [c_vp] * 7 + [c_vp, c_sz, c_vp, c_vp, c_vp]),
+    "dimo_raster_blend_fwd": (c_int, [c_int] * 3 + [c_vp] * 10),
+    "dimo_raster_blend_bwd": (c_int, [c_int] * 4 + [c_vp] * 12),
+    "dimo_raster_preprocess_bwd": (c_int, [c_int] * 6 + [c_f32, c_vp] + [c_vp, c_i64] * 4 + [c_vp] * 10),
+    "dimo_knn": (c_int, [c_int] * 3 + [c_vp] * 5),
+    "dimo_dist3nn": (c_int, [c_int, c_vp, c_vp, c_vp]),
+    "dimo_linear_fwd": (c_int, [c_int] * 3 + [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_int, c_vp]),
+    "dimo_linear_bwd_data": (c_int, [c_int] * 3 + [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_vp]),
+    "dimo_linear_bwd_weight": (c_int, [c_int] * 3 + [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "dimo_timenet_embed_fwd": (c_int, [c_int] * 3 + [c_vp] * 4 + [c_i64, c_vp]),
+    "dimo_timenet_embed_bwd": (c_int, [c_int] * 3 + [c_vp] * 3 + [c_i64, c_vp, c_vp, c_vp]),
+    "dimo_lbs_fwd": (c_int, [c_int] * 4 + [c_vp] * 11),
+    "dimo_lbs_bwd": (c_int, [c_int] * 4 + [c_vp] * 17),
+    "dimo_ssim_fwd": (c_int, [c_int] * 4 + [c_vp] * 5),
+    "dimo_ssim_bwd": (c_int, [c_int] * 4 + [c_vp] * 3 + [c_f32] * 3 + [c_vp, c_vp]),
+}
+
+
+def exported_symbols():
+    return sorted(_SIGS)
+
+
+def lib():
+    """Loads the library (once).  Raises RuntimeError with build instructions if it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -m dimo_b200.build` "
+                "(dimo_b200 has no CPU or PyTorch fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name, None)    # a missing symbol fails loudly at call time (call())
+            if fn is not None:
+                fn.restype = res
+                fn.argtypes = args
+        if L.dimo_abi_version() != 1:
+            raise RuntimeError("libdimo_b200.so ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError("libdimo_b200: " + lib().dimo_last_error().decode())
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL).  Refuses CPU tensors: the product path is CUDA only."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("dimo_b200 ops need CUDA tensors (there is no CPU path)")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    fn = getattr(lib(), name, None)
+    if fn is None:
+        raise RuntimeError(f"libdimo_b200.so does not export {name}: rebuild with `python -m dimo_b200.build`")
+    check(fn(*args))

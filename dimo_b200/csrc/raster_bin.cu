@@ -1,0 +1,160 @@
+// Binning stage of the tile rasteriser: inclusive scan of per-splat tile counts, key emission,
+// (tile|depth) radix sort, packing of splat records into sorted order and per-tile ranges.
+//
+// Upstream shape (diff_gauss / diff_gaussian_rasterization, call site
+// renderer/latent_gs_renderer.py:1256-1277): InclusiveSum -> duplicateWithKeys -> SortPairs ->
+// identifyTileRanges.  B200 change: the sorted instance list is materialised as contiguous 64-byte
+// splat records ("packed") so the blend kernels stream each tile's list with 1-D bulk TMA
+// (cp.async.bulk) instead of gathering by index.  Scan and sort are CUB device primitives compiled
+// into this library (integer-only, HBM-bound).
+#include "common.cuh"
+#include <cub/cub.cuh>
+#include <stdarg.h>
+
+namespace dimo {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+// 4 lanes per instance: lane q copies float4 #q of the 64-byte record (reads: 64 B contiguous per
+// instance, writes: fully coalesced).  Lane 0 also writes the tile range boundaries.
+__global__ void __launch_bounds__(256) pack_ranges_kernel(int64_t R, const uint64_t* __restrict__ keys,
+                                                          const uint32_t* __restrict__ vals,
+                                                          const float4* __restrict__ splats,
+                                                          float4* __restrict__ packed, uint2* __restrict__ ranges) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t j = t >> 2;
+  const int qd = (int)(t & 3);
+  if (j >= R) return;
+  const uint32_t v = vals[j];
+  packed[4 * j + qd] = splats[4 * (int64_t)v + qd];
+  if (qd == 0) {
+    const uint32_t tile = (uint32_t)(keys[j] >> 32);
+    if (j == 0) {
+      ranges[tile].x = 0;
+    } else {
+      const uint32_t prev = (uint32_t)(keys[j - 1] >> 32);
+      if (prev != tile) {
+        ranges[prev].y = (uint32_t)j;
+        ranges[tile].x = (uint32_t)j;
+      }
+    }
+    if (j == R - 1) ranges[tile].y = (uint32_t)R;
+  }
+}
+
+static inline int key_bits(int B, int W, int H) {
+  const int64_t tiles = (int64_t)B * ((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+  int bits = 1;
+  while (((int64_t)1 << bits) < tiles) ++bits;
+  return 32 + bits;
+}
+
+}  // namespace dimo
+
+using namespace dimo;
+
+namespace dimo {
+int preprocess_launch(int B, int N, int W, int H, int sh_degree, int sh_coeffs, float scale_modifier,
+                      const float* cams, const float* means3D, int64_t means3D_bstride, const float* scales,
+                      int64_t scales_bstride, const float* rotations, int64_t rotations_bstride,
+                      const float* opacities, int64_t opacities_bstride, const float* shs, int64_t shs_bstride,
+                      const float* colors_precomp, int64_t colors_bstride, float* splats, int32_t* radii,
+                      uint32_t* tiles_touched, cudaStream_t st);
+int emit_keys_launch(int B, int N, int W, int H, int64_t R, const float* splats, const int32_t* radii,
+                     const uint32_t* offsets, uint64_t* keys, uint32_t* vals, cudaStream_t st);
+}  // namespace dimo
+
+extern "C" {
+
+int dimo_abi_version(void) { return DIMO_ABI_VERSION; }
+const char* dimo_last_error(void) { return dimo::get_error(); }
+
+int dimo_device_info(int* out3_host) {
+  int dev = 0;
+  DIMO_CHECK_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  DIMO_CHECK_CUDA(cudaGetDeviceProperties(&p, dev));
+  out3_host[0] = p.multiProcessorCount;
+  out3_host[1] = (int)p.sharedMemPerBlockOptin;
+  out3_host[2] = p.major * 10 + p.minor;
+  return 0;
+}
+
+size_t dimo_raster_scan_temp_bytes(int64_t BN) {
+  size_t bytes = 0;
+  cub::DeviceScan::InclusiveSum(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)BN);
+  return bytes + 256;
+}
+
+size_t dimo_raster_sort_temp_bytes(int64_t R) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
+                                  (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)R, 0, 64);
+  return bytes + 256;
+}
+
+int dimo_raster_preprocess(int B, int N, int W, int H, int sh_degree, int sh_coeffs, float scale_modifier,
+                           const float* cams, const float* means3D, int64_t means3D_bstride, const float* scales,
+                           int64_t scales_bstride, const float* rotations, int64_t rotations_bstride,
+                           const float* opacities, int64_t opacities_bstride, const float* shs,
+                           int64_t shs_bstride, const float* colors_precomp, int64_t colors_bstride,
+                           float* splats, int32_t* radii, uint32_t* tiles_touched, uint32_t* offsets,
+                           void* scan_temp, size_t scan_temp_bytes, int64_t* R_host, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t BN = (int64_t)B * N;
+  DIMO_REQUIRE(B >= 0 && N >= 0 && W > 0 && H > 0, "bad sizes");
+  DIMO_REQUIRE(BN < ((int64_t)1 << 31), "B*N must fit int32");
+  DIMO_REQUIRE(sh_degree >= 0 && sh_degree <= 3, "sh_degree must be 0..3");
+  DIMO_REQUIRE((shs != nullptr) != (colors_precomp != nullptr), "exactly one of shs / colors_precomp");
+  DIMO_REQUIRE(shs == nullptr || sh_coeffs >= (sh_degree + 1) * (sh_degree + 1), "sh_coeffs < (deg+1)^2");
+  if (BN == 0) {
+    if (R_host) *R_host = 0;
+    return 0;
+  }
+  int rc = preprocess_launch(B, N, W, H, sh_degree, sh_coeffs, scale_modifier, cams, means3D,
+                                         means3D_bstride, scales, scales_bstride, rotations, rotations_bstride,
+                                         opacities, opacities_bstride, shs, shs_bstride, colors_precomp,
+                                         colors_bstride, splats, radii, tiles_touched, st);
+  if (rc) return rc;
+  size_t need = scan_temp_bytes;
+  DIMO_CHECK_CUDA(cub::DeviceScan::InclusiveSum(scan_temp, need, tiles_touched, offsets, (int)BN, st));
+  if (R_host) {
+    uint32_t last = 0;
+    DIMO_CHECK_CUDA(cudaMemcpyAsync(&last, offsets + (BN - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    DIMO_CHECK_CUDA(cudaStreamSynchronize(st));
+    *R_host = (int64_t)last;
+  }
+  return 0;
+}
+
+int dimo_raster_bin(int B, int N, int W, int H, int64_t R, const float* splats, const int32_t* radii,
+                    const uint32_t* offsets, uint64_t* keys_unsorted, uint32_t* vals_unsorted,
+                    uint64_t* keys_sorted, uint32_t* vals_sorted, void* sort_temp, size_t sort_temp_bytes,
+                    float* packed, uint32_t* ranges, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+  const int64_t ntiles = (int64_t)B * gx * gy;
+  DIMO_REQUIRE(R < ((int64_t)1 << 31), "instance count must fit int32");
+  DIMO_CHECK_CUDA(cudaMemsetAsync(ranges, 0, sizeof(uint32_t) * 2 * ntiles, st));
+  if (R == 0) return 0;
+  int rc = emit_keys_launch(B, N, W, H, R, splats, radii, offsets, keys_unsorted, vals_unsorted, st);
+  if (rc) return rc;
+  size_t need = sort_temp_bytes;
+  DIMO_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(sort_temp, need, keys_unsorted, keys_sorted, vals_unsorted,
+                                                  vals_sorted, (int)R, 0, key_bits(B, W, H), st));
+  pack_ranges_kernel<<<ceil_div(R * 4, 256), 256, 0, st>>>(R, keys_sorted, vals_sorted,
+                                                           reinterpret_cast<const float4*>(splats),
+                                                           reinterpret_cast<float4*>(packed),
+                                                           reinterpret_cast<uint2*>(ranges));
+  DIMO_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,189 @@
+"""Host side of the tile rasteriser: torch owns the memory, libdimo_b200 does the work.
+
+`rasterize_batch` renders B frames that share the image size in one set of kernel launches
+(preprocess -> scan -> key emission -> radix sort -> pack -> blend) and is differentiable through
+`_Rasterize` (blend backward -> preprocess backward).  The single-frame reference API
+(diff_gauss / diff_gaussian_rasterization GaussianRasterizer, renderer/latent_gs_renderer.py:1147,
+1256-1277) is B=1 of the same path (dimo_b200/shims).
+"""
+import torch
+
+from . import _lib
+
+CAM_FLOATS = 40
+SPLAT_FLOATS = 16
+TILE = 16
+
+
+def pack_cameras(viewmatrix, projmatrix, campos, tanfovx, tanfovy, bg):
+    """[B?,4,4],[B?,4,4],[B?,3], python floats or [B] tensors, [B?,3] -> [B,40] device block
+    (layout: include/dimo_b200.h DIMO_CAM_FLOATS).  No host sync."""
+    dev = viewmatrix.device
+    V = viewmatrix.reshape(-1, 16).float()
+    B = V.shape[0]
+    P = projmatrix.reshape(-1, 16).float().expand(B, 16)
+    C = campos.reshape(-1, 3).float().expand(B, 3)
+    if not torch.is_tensor(tanfovx):
+        tan = torch.tensor([[float(tanfovx), float(tanfovy)]], dtype=torch.float32).to(dev, non_blocking=True).expand(B, 2)
+    else:
+        tan = torch.stack([tanfovx.float().reshape(-1), tanfovy.float().reshape(-1)], dim=1).to(dev).expand(B, 2)
+    G = bg.reshape(-1, 3).float().to(dev).expand(B, 3)
+    return torch.cat([V, P, C, tan, G], dim=1).contiguous()
+
+
+def _bstride(t, B, per_frame_numel):
+    """element stride between frames: 0 if the tensor is shared by all frames"""
+    if t is None:
+        return 0
+    if t.numel() == per_frame_numel:
+        return 0
+    assert t.numel() == B * per_frame_numel, "batched argument has wrong size"
+    return per_frame_numel
+
+
+class RasterState:
+    """Buffers kept from forward for backward / inspection (all torch-owned)."""
+    __slots__ = ("B", "N", "W", "H", "R", "cams", "splats", "radii", "tiles_touched", "offsets", "keys_sorted",
+                 "vals_sorted", "packed", "ranges", "final_T", "n_contrib", "sh_degree", "sh_coeffs",
+                 "scale_modifier")
+
+
+def _forward_impl(cams, means3D, scales, rotations, opacities, shs, colors_precomp, B, N, W, H, sh_degree,
+                  scale_modifier):
+    dev = means3D.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    st = RasterState()
+    st.B, st.N, st.W, st.H = B, N, W, H
+    st.cams = cams
+    st.sh_degree = int(sh_degree)
+    st.sh_coeffs = 0 if shs is None else int(shs.shape[-2])
+    st.scale_modifier = float(scale_modifier)
+    BN = B * N
+    st.splats = torch.empty(BN, SPLAT_FLOATS, **f32)
+    st.radii = torch.empty(BN, dtype=torch.int32, device=dev)
+    st.tiles_touched = torch.empty(BN, dtype=torch.int32, device=dev)
+    st.offsets = torch.empty(BN, dtype=torch.int32, device=dev)
+    L = _lib.lib()
+    scan_bytes = L.dimo_raster_scan_temp_bytes(BN)
+    scan_temp = torch.empty(scan_bytes, dtype=torch.uint8, device=dev)
+    import ctypes
+    R_host = ctypes.c_int64(0)
+    s = _lib.stream()
+    _lib.call("dimo_raster_preprocess", B, N, W, H, st.sh_degree, st.sh_coeffs, st.scale_modifier, _lib.ptr(cams),
+              _lib.ptr(means3D), _bstride(means3D, B, N * 3),
+              _lib.ptr(scales), _bstride(scales, B, N * 3),
+              _lib.ptr(rotations), _bstride(rotations, B, N * 4),
+              _lib.ptr(opacities), _bstride(opacities, B, N),
+              _lib.ptr(shs), _bstride(shs, B, N * st.sh_coeffs * 3),
+              _lib.ptr(colors_precomp), _bstride(colors_precomp, B, N * 3),
+              _lib.ptr(st.splats), _lib.ptr(st.radii), _lib.ptr(st.tiles_touched), _lib.ptr(st.offsets),
+              _lib.ptr(scan_temp), scan_bytes, ctypes.addressof(R_host), s)
+    R = int(R_host.value)
+    st.R = R
+    gx, gy = (W + TILE - 1) // TILE, (H + TILE - 1) // TILE
+    Ra = max(R, 1)
+    keys_u = torch.empty(Ra, dtype=torch.int64, device=dev)
+    vals_u = torch.empty(Ra, dtype=torch.int32, device=dev)
+    st.keys_sorted = torch.empty(Ra, dtype=torch.int64, device=dev)
+    st.vals_sorted = torch.empty(Ra, dtype=torch.int32, device=dev)
+    st.packed = torch.empty(Ra, SPLAT_FLOATS, **f32)
+    st.ranges = torch.empty(B * gx * gy, 2, dtype=torch.int32, device=dev)
+    sort_bytes = L.dimo_raster_sort_temp_bytes(Ra)
+    sort_temp = torch.empty(sort_bytes, dtype=torch.uint8, device=dev)
+    _lib.call("dimo_raster_bin", B, N, W, H, R, _lib.ptr(st.splats), _lib.ptr(st.radii), _lib.ptr(st.offsets),
+              _lib.ptr(keys_u), _lib.ptr(vals_u), _lib.ptr(st.keys_sorted), _lib.ptr(st.vals_sorted),
+              _lib.ptr(sort_temp), sort_bytes, _lib.ptr(st.packed), _lib.ptr(st.ranges), s)
+    color = torch.empty(B, 3, H, W, **f32)
+    depth = torch.empty(B, 1, H, W, **f32)
+    normal = torch.empty(B, 3, H, W, **f32)
+    alpha = torch.empty(B, 1, H, W, **f32)
+    st.final_T = torch.empty(B, H, W, **f32)
+    st.n_contrib = torch.empty(B, H, W, dtype=torch.int32, device=dev)
+    _lib.call("dimo_raster_blend_fwd", B, W, H, _lib.ptr(cams), _lib.ptr(st.packed), _lib.ptr(st.ranges),
+              _lib.ptr(color), _lib.ptr(depth), _lib.ptr(normal), _lib.ptr(alpha), _lib.ptr(st.final_T),
+              _lib.ptr(st.n_contrib), s)
+    return color, depth, normal, alpha, st
+
+
+class _Rasterize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, scales, rotations, opacities, shs, colors_precomp, cams, B, N, W, H,
+                sh_degree, scale_modifier, state_out):
+        color, depth, normal, alpha, st = _forward_impl(cams, means3D, scales, rotations, opacities, shs,
+                                                        colors_precomp, B, N, W, H, sh_degree, scale_modifier)
+        ctx.st = st
+        ctx.save_for_backward(means3D, scales, rotations, shs)
+        ctx.shapes = (means3D.shape, None if means2D is None else means2D.shape, scales.shape, rotations.shape,
+                      opacities.shape, None if shs is None else shs.shape,
+                      None if colors_precomp is None else colors_precomp.shape)
+        if state_out is not None:
+            state_out.append(st)
+        radii = st.radii.view(B, N)
+        ctx.mark_non_differentiable(radii)
+        return color, depth, normal, alpha, radii
+
+    @staticmethod
+    def backward(ctx, g_color, g_depth, g_normal, g_alpha, _g_radii):
+        st = ctx.st
+        means3D, scales, rotations, shs = ctx.saved_tensors
+        B, N, W, H = st.B, st.N, st.W, st.H
+        dev = means3D.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        zeros = lambda *s: torch.zeros(*s, **f32)
+        g_color = g_color.contiguous() if g_color is not None else zeros(B, 3, H, W)
+        g_depth = g_depth.contiguous() if g_depth is not None else zeros(B, 1, H, W)
+        g_normal = g_normal.contiguous() if g_normal is not None else zeros(B, 3, H, W)
+        g_alpha = g_alpha.contiguous() if g_alpha is not None else zeros(B, 1, H, W)
+        s = _lib.stream()
+        dsplats = torch.empty(B * N, SPLAT_FLOATS, **f32)
+        _lib.call("dimo_raster_blend_bwd", B, N, W, H, _lib.ptr(st.cams), _lib.ptr(st.packed), _lib.ptr(st.ranges),
+                  _lib.ptr(st.vals_sorted), _lib.ptr(st.final_T), _lib.ptr(st.n_contrib), _lib.ptr(g_color),
+                  _lib.ptr(g_depth), _lib.ptr(g_normal), _lib.ptr(g_alpha), _lib.ptr(dsplats), s)
+        d_means3D = torch.empty(B, N, 3, **f32)
+        d_means2D = torch.empty(B, N, 3, **f32)
+        d_scales = torch.empty(B, N, 3, **f32)
+        d_rot = torch.empty(B, N, 4, **f32)
+        d_op = torch.empty(B, N, **f32)
+        use_sh = shs is not None
+        d_shs = torch.empty(B, N, st.sh_coeffs, 3, **f32) if use_sh else None
+        d_col = None if use_sh else torch.empty(B, N, 3, **f32)
+        _lib.call("dimo_raster_preprocess_bwd", B, N, W, H, st.sh_degree, st.sh_coeffs, st.scale_modifier,
+                  _lib.ptr(st.cams),
+                  _lib.ptr(means3D), _bstride(means3D, B, N * 3),
+                  _lib.ptr(scales), _bstride(scales, B, N * 3),
+                  _lib.ptr(rotations), _bstride(rotations, B, N * 4),
+                  _lib.ptr(shs), _bstride(shs, B, N * st.sh_coeffs * 3) if use_sh else 0,
+                  _lib.ptr(st.radii), _lib.ptr(dsplats), _lib.ptr(d_means3D), _lib.ptr(d_means2D),
+                  _lib.ptr(d_scales), _lib.ptr(d_rot), _lib.ptr(d_op), _lib.ptr(d_shs), _lib.ptr(d_col), s)
+        sh_m3, sh_m2, sh_sc, sh_rot, sh_op, sh_shs, sh_col = ctx.shapes
+
+        def fit(g, shape, per_frame):
+            """[B, ...per-frame] -> the input's own shape (sum over frames when the input was shared)"""
+            if shape is None or g is None:
+                return None
+            numel = 1
+            for d in shape:
+                numel *= d
+            if numel == per_frame and B > 1:
+                g = g.sum(dim=0)
+            return g.reshape(shape)
+
+        return (fit(d_means3D, sh_m3, N * 3), fit(d_means2D, sh_m2, N * 3) if ctx.needs_input_grad[1] else None,
+                fit(d_scales, sh_sc, N * 3), fit(d_rot, sh_rot, N * 4), fit(d_op, sh_op, N),
+                fit(d_shs, sh_shs, N * st.sh_coeffs * 3) if use_sh else None,
+                fit(d_col, sh_col, N * 3) if not use_sh else None,
+                None, None, None, None, None, None, None, None)
+
+
+def rasterize_batch(cams, means3D, scales, rotations, opacities, W, H, shs=None, colors_precomp=None,
+                    sh_degree=0, scale_modifier=1.0, means2D=None, state_out=None):
+    """cams [B,40]; means3D [B,N,3] or [N,3]; scales [N,3]; rotations [B,N,4] or [N,4]; opacities [N,1]/[N];
+    shs [N,K,3] xor colors_precomp [B?,N,3].  Returns color [B,3,H,W], depth [B,1,H,W], normal [B,3,H,W],
+    alpha [B,1,H,W], radii [B,N] int32."""
+    if (shs is None) == (colors_precomp is None):
+        raise ValueError("Please provide exactly one of either SHs or precomputed colors!")
+    B = cams.shape[0]
+    N = scales.shape[-2]
+    c = lambda t: None if t is None else t.contiguous().float()
+    return _Rasterize.apply(c(means3D), means2D, c(scales), c(rotations), c(opacities), c(shs), c(colors_precomp),
+                            cams.contiguous(), B, N, int(W), int(H), int(sh_degree), float(scale_modifier), state_out)

@@ -1,0 +1,182 @@
+/* libdimo_b200.so -- C ABI of the B200-native DIMO deform -> raster -> loss hot path.
+ *
+ * The reference has no C ABI: its boundary for this path is five Python extension modules
+ * (pybind11 / torch extensions) plus PyTorch glue.  Each entry point below names the
+ * reference interface it replaces (file:line relative to the reference tree); the Python
+ * shims in dimo_b200/shims/ bind these with ctypes and re-expose the reference's own module
+ * names and call signatures.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in _host;
+ *  - the caller owns every buffer (inputs, outputs, workspace, saved-for-backward); the
+ *    library never allocates device memory and never touches the default stream;
+ *  - `stream` is a cudaStream_t passed as void*;
+ *  - return 0 on success, <0 on error (message via dimo_last_error(), thread-local);
+ *  - fp32 everywhere unless noted; integers called out per argument;
+ *  - `*_bstride` is the element stride between consecutive frames of a batched argument;
+ *    0 means "shared by all B frames".
+ */
+#ifndef DIMO_B200_H
+#define DIMO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DIMO_ABI_VERSION 1
+
+/* Per-frame camera block, DIMO_CAM_FLOATS floats on the device:
+ *   [0:16)  viewmatrix   (world_view_transform, row-vector convention)   renderer/latent_gs_renderer.py:960
+ *   [16:32) projmatrix   (full_proj_transform)                            :969
+ *   [32:35) campos       (camera_center)                                  :970
+ *   [35]    tanfovx  [36] tanfovy                                         :1129-1130
+ *   [37:40) bg colour                                                     :1139
+ * i.e. the fields of GaussianRasterizationSettings (:1133-1146) that vary per frame. */
+#define DIMO_CAM_FLOATS 40
+
+/* Per-Gaussian projected record ("splat"), DIMO_SPLAT_FLOATS floats (64 B, TMA-bulk friendly):
+ *   x, y (pixel centre), conic_a, conic_b | conic_c, opacity, r, g | b, depth, nx, ny | nz, 0,0,0 */
+#define DIMO_SPLAT_FLOATS 16
+
+int         dimo_abi_version(void);
+const char* dimo_last_error(void);
+/* device properties the host side sizes grids with: out[0]=SM count, out[1]=max smem/block optin,
+ * out[2]=compute capability major*10+minor */
+int         dimo_device_info(int* out3_host);
+
+/* ---------------------------------------------------------------------------------------------
+ * Rasteriser  (replaces diff_gauss.GaussianRasterizer.forward/backward, call site
+ * renderer/latent_gs_renderer.py:1147,1256-1266, and diff_gaussian_rasterization
+ * .GaussianRasterizer, :1163,1268-1277).  Batched over B frames that share W,H.
+ * ------------------------------------------------------------------------------------------- */
+
+/* temp bytes for the scan over B*N counters / the radix sort of R (key,value) pairs */
+size_t dimo_raster_scan_temp_bytes(int64_t BN);
+size_t dimo_raster_sort_temp_bytes(int64_t R);
+
+/* Stage 1: per-Gaussian projection + tile counting + inclusive scan.
+ *   splats [B*N,16] f32, radii [B*N] i32, tiles_touched [B*N] u32, offsets [B*N] u32 (inclusive scan).
+ *   shs [N,sh_coeffs,3] (or NULL) / colors_precomp [N,3] (or NULL): exactly one non-NULL.
+ *   R_host: if non-NULL the stream is synchronised and the total instance count is stored there. */
+int dimo_raster_preprocess(
+    int B, int N, int W, int H, int sh_degree, int sh_coeffs, float scale_modifier,
+    const float* cams,
+    const float* means3D, int64_t means3D_bstride,
+    const float* scales, int64_t scales_bstride,
+    const float* rotations, int64_t rotations_bstride,
+    const float* opacities, int64_t opacities_bstride,
+    const float* shs, int64_t shs_bstride,
+    const float* colors_precomp, int64_t colors_bstride,
+    float* splats, int32_t* radii, uint32_t* tiles_touched, uint32_t* offsets,
+    void* scan_temp, size_t scan_temp_bytes,
+    int64_t* R_host, void* stream);
+
+/* Stage 2: emit (tile|depth) keys, sort, pack splats in sorted order, per-tile ranges.
+ *   keys_* [R] u64, vals_* [R] u32 (index into B*N), packed [R,16] f32, ranges [B*tiles,2] u32. */
+int dimo_raster_bin(
+    int B, int N, int W, int H, int64_t R,
+    const float* splats, const int32_t* radii, const uint32_t* offsets,
+    uint64_t* keys_unsorted, uint32_t* vals_unsorted, uint64_t* keys_sorted, uint32_t* vals_sorted,
+    void* sort_temp, size_t sort_temp_bytes,
+    float* packed, uint32_t* ranges, void* stream);
+
+/* Stage 3: per-tile front-to-back blend.
+ *   out_color [B,3,H,W], out_depth [B,1,H,W], out_normal [B,3,H,W], out_alpha [B,1,H,W],
+ *   final_T [B,H,W] f32, n_contrib [B,H,W] i32. */
+int dimo_raster_blend_fwd(
+    int B, int W, int H, const float* cams, const float* packed, const uint32_t* ranges,
+    float* out_color, float* out_depth, float* out_normal, float* out_alpha,
+    float* final_T, int32_t* n_contrib, void* stream);
+
+/* Backward of stage 3: dL_dsplats [B*N,16] (zeroed here, then accumulated), same field layout as a splat. */
+int dimo_raster_blend_bwd(
+    int B, int N, int W, int H, const float* cams, const float* packed, const uint32_t* ranges,
+    const uint32_t* vals_sorted, const float* final_T, const int32_t* n_contrib,
+    const float* dL_dcolor, const float* dL_ddepth, const float* dL_dnormal, const float* dL_dalpha,
+    float* dL_dsplats, void* stream);
+
+/* Backward of stage 1: per-frame gradients (dense, no atomics):
+ *   dL_dmeans3D [B,N,3], dL_dmeans2D [B,N,3] (NDC units, z=0), dL_dscales [B,N,3],
+ *   dL_drotations [B,N,4], dL_dopacities [B,N], dL_dshs [B,N,sh_coeffs,3] or dL_dcolors [B,N,3]. */
+int dimo_raster_preprocess_bwd(
+    int B, int N, int W, int H, int sh_degree, int sh_coeffs, float scale_modifier,
+    const float* cams,
+    const float* means3D, int64_t means3D_bstride,
+    const float* scales, int64_t scales_bstride,
+    const float* rotations, int64_t rotations_bstride,
+    const float* shs, int64_t shs_bstride,
+    const int32_t* radii, const float* dL_dsplats,
+    float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dscales, float* dL_drotations,
+    float* dL_dopacities, float* dL_dshs, float* dL_dcolors, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Nearest neighbours (replaces knn_cuda.KNN(k, transpose_mode=True), main_train_dimo.py:505-506,
+ * and simple_knn._C.distCUDA2, renderer/latent_gs_renderer.py:426).
+ * ------------------------------------------------------------------------------------------- */
+/* ref [M,3], query [N,3] -> dist [N,k] f32 (Euclidean, ascending), idx [N,k] i64.  k <= 8. */
+int dimo_knn(int M, int N, int k, const float* ref, const float* query,
+             float* dist, int64_t* idx, void* stream);
+/* points [N,3] -> mean squared distance to the 3 nearest other points, [N]. */
+int dimo_dist3nn(int N, const float* points, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Deformation: positional encoding + TimeNet MLP (renderer/latent_gs_renderer.py:184-235,
+ * src/pos_enc.py:6-54) and K-neighbour linear-blend skinning (:1191-1219).
+ * ------------------------------------------------------------------------------------------- */
+
+/* Generic fused linear layer, the building block of TimeNet:
+ *   Y[R,No] = act( X[R,K] * W[No,K]^T + bias[No] ),  row strides ldx/ldy in floats, relu 0/1. */
+int dimo_linear_fwd(int R, int K, int No, const float* X, int64_t ldx, const float* Wt,
+                    const float* bias, float* Y, int64_t ldy, int relu, void* stream);
+/* dX[R,K] (=|+=) (dY*[Y>0]) * W ; accumulate 0/1 ; Y==NULL -> no relu mask. dYm [R,No] receives the masked dY
+ * (may alias dY). */
+int dimo_linear_bwd_data(int R, int K, int No, const float* dY, int64_t lddy, const float* Y, int64_t ldy,
+                         const float* Wt, float* dYm, int64_t lddym, float* dX, int64_t lddx,
+                         int accumulate, void* stream);
+/* dW[No,K] += dYm^T * X ; db[No] += sum_rows dYm   (dYm already relu-masked) */
+int dimo_linear_bwd_weight(int R, int K, int No, const float* dYm, int64_t lddym, const float* X, int64_t ldx,
+                           float* dW, float* db, void* stream);
+
+/* TimeNet input embedding h0[R,104] = [posenc(x,10) | posenc(t,6) | latent]  (pos_enc.py:35-36,
+ * latent_gs_renderer.py:223-225).  Row r belongs to group g = r / rows_per_group and reads
+ * times[g], latents[g*L..].  pts [rows_per_group,3] shared by all groups. */
+int dimo_timenet_embed_fwd(int G, int rows_per_group, int L, const float* pts, const float* times,
+                           const float* latents, float* h0, int64_t ldh, void* stream);
+/* backward of the embedding: dpts [rows_per_group,3] += , dlatents [G,L] += */
+int dimo_timenet_embed_bwd(int G, int rows_per_group, int L, const float* pts, const float* times,
+                           const float* dh0, int64_t ldh, float* dpts, float* dlatents, void* stream);
+
+/* LBS skinning + activations for B (motion,t) frames over N Gaussians with K neighbours.
+ *   xyz [N,3], rot [N,4], idx [N,K] i64, dist [N,K], c_xyz [M,3], c_radius_raw [M] (log-radius),
+ *   dxyz [B,M,3], dquat [B,M,4]  ->  means3D [B,N,3], rotations [B,N,4] (normalised). */
+int dimo_lbs_fwd(int B, int N, int M, int K, const float* xyz, const float* rot, const int64_t* idx,
+                 const float* dist, const float* c_xyz, const float* c_radius_raw,
+                 const float* dxyz, const float* dquat, float* means3D, float* rotations, void* stream);
+/* backward: accumulates (+=) into dxyz_c [N,3], drot_c [N,4], dc_xyz [M,3], dc_radius_raw [M],
+ * ddxyz [B,M,3], ddquat [B,M,4].  All outputs must be zeroed (or hold prior grads) by the caller. */
+int dimo_lbs_bwd(int B, int N, int M, int K, const float* xyz, const float* rot, const int64_t* idx,
+                 const float* dist, const float* c_xyz, const float* c_radius_raw,
+                 const float* dxyz, const float* dquat, const float* dL_dmeans3D, const float* dL_drotations,
+                 float* dxyz_c, float* drot_c, float* dc_xyz, float* dc_radius_raw,
+                 float* ddxyz, float* ddquat, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Image loss (replaces fused_ssim.fused_ssim, main_test_dimo.py:979, and src/loss.py:144-178 ssim /
+ * l1_loss + F.mse_loss, main_train_dimo.py:333-344).
+ *   img1,img2 [B,C,H,W]; sums[3] (f32, zeroed by callee) = { sum ssim_map, sum |a-b|, sum (a-b)^2 }.
+ *   dm [3,B,C,H,W]: the three partial-derivative maps kept for backward (may be NULL for eval).
+ * ------------------------------------------------------------------------------------------- */
+int dimo_ssim_fwd(int B, int C, int H, int W, const float* img1, const float* img2,
+                  float* sums, float* dm, void* stream);
+/* dL_dimg1 [B,C,H,W] = w_ssim * d(sum ssim_map)/dimg1 + w_l1 * d(sum|a-b|)/dimg1 + w_mse * d(sum (a-b)^2)/dimg1.
+ * Weights are DEVICE scalars-by-value (host floats): caller folds 1/numel and upstream grads in. */
+int dimo_ssim_bwd(int B, int C, int H, int W, const float* img1, const float* img2, const float* dm,
+                  float w_ssim, float w_l1, float w_mse, float* dL_dimg1, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIMO_B200_H */

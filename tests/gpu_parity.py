@@ -1,0 +1,117 @@
+"""Shared CUDA-vs-oracle comparison helpers (used by the -m gpu tests and __graft_entry__.smoke)."""
+import math
+
+import torch
+
+import dimo_b200
+from dimo_b200 import raster as draster, synthetic
+from dimo_b200.camera import orbit_minicam
+from oracle import raster as oraster, camera as ocamera, deform as odeform
+
+PIX_TOL = 1e-4      # north_star: within 1e-4 rel on pixel values and gradients
+GRAD_TOL = 1e-4
+
+
+def rel_err(a, ref):
+    """max |a-ref| relative to the tensor's scale max|ref| (per-element relative error is meaningless for
+    the near-zero entries every gradient tensor has)."""
+    a = a.detach().double().cpu()
+    ref = ref.detach().double().cpu()
+    scale = max(ref.abs().max().item(), 1e-30)
+    return (a - ref).abs().max().item() / scale
+
+
+def outlier_frac(a, ref, tol):
+    a = a.detach().double().cpu(); ref = ref.detach().double().cpu()
+    scale = max(ref.abs().max().item(), 1e-30)
+    return ((a - ref).abs() > tol * scale).double().mean().item()
+
+
+def scene_inputs(N, seed=0, sh_coeffs=1, scale_boost=0.0):
+    sc = synthetic.make_scene(N, n_ctrl=min(512, N), seed=seed, sh_coeffs=sh_coeffs)
+    xyz = sc["_xyz"]
+    scales = torch.exp(sc["_scaling"] + scale_boost)
+    rot = torch.nn.functional.normalize(sc["_rotation"])
+    op = torch.sigmoid(sc["_opacity"])
+    shs = torch.cat([sc["_features_dc"], sc["_features_rest"]], dim=1)
+    return xyz, scales, rot, op, shs
+
+
+def loss_weights(H, W, seed=1):
+    g = torch.Generator().manual_seed(seed)
+    return dict(c=torch.rand(3, H, W, generator=g), d=torch.rand(1, H, W, generator=g) * 0.3,
+                n=torch.rand(3, H, W, generator=g) - 0.5, a=torch.rand(1, H, W, generator=g))
+
+
+def weighted_loss(img, depth, normal, alpha, w):
+    return (img * w["c"]).sum() + (depth * w["d"]).sum() + (normal * w["n"]).sum() + (alpha * w["a"]).sum()
+
+
+def run_raster_pair(N, W, H, view=1, nviews=8, sh_degree=0, seed=0, scale_boost=0.0, bg=(1.0, 1.0, 1.0),
+                    device="cuda"):
+    """Runs the oracle (CPU fp32 + autograd) and the CUDA path on identical inputs; returns both result dicts."""
+    K = (sh_degree + 1) ** 2
+    xyz, scales, rot, op, shs = scene_inputs(N, seed, K, scale_boost)
+    bg_t = torch.tensor(bg, dtype=torch.float32)
+    w = loss_weights(H, W)
+
+    # ---- oracle ----
+    ocam = ocamera.orbit_cam(view, nviews, W, H)
+    leaves = [t.clone().requires_grad_(True) for t in (xyz, scales, rot, op, shs)]
+    m2d = torch.zeros(N, 3, requires_grad=True)
+    o = oraster.rasterize(leaves[0], leaves[1], leaves[2], leaves[3], ocam.world_view_transform,
+                          ocam.full_proj_transform, ocam.camera_center, ocam.tanfovx, ocam.tanfovy, W, H, bg_t,
+                          shs=leaves[4], sh_degree=sh_degree, means2D=m2d)
+    weighted_loss(o["image"], o["depth"], o["normal"], o["alpha"], w).backward()
+    o["grads"] = dict(means3D=leaves[0].grad, scales=leaves[1].grad, rotations=leaves[2].grad,
+                      opacities=leaves[3].grad, shs=leaves[4].grad, means2D=m2d.grad)
+
+    # ---- CUDA ----
+    cam = orbit_minicam(view, nviews, W, H, device=device)
+    assert torch.equal(cam.world_view_transform.cpu(), ocam.world_view_transform)
+    assert torch.equal(cam.full_proj_transform.cpu(), ocam.full_proj_transform)
+    cams = draster.pack_cameras(cam.world_view_transform, cam.full_proj_transform, cam.camera_center,
+                                math.tan(cam.FoVx * 0.5), math.tan(cam.FoVy * 0.5), bg_t.to(device))
+    cl = [t.clone().to(device).requires_grad_(True) for t in (xyz, scales, rot, op, shs)]
+    cm2d = torch.zeros(N, 3, device=device, requires_grad=True)
+    state = []
+    color, depth, normal, alpha, radii = draster.rasterize_batch(
+        cams, cl[0], cl[1], cl[2], cl[3], W, H, shs=cl[4], sh_degree=sh_degree, means2D=cm2d, state_out=state)
+    wd = {k: v.to(device) for k, v in w.items()}
+    weighted_loss(color[0], depth[0], normal[0], alpha[0], wd).backward()
+    torch.cuda.synchronize()
+    st = state[0]
+    c = dict(image=color[0], depth=depth[0], normal=normal[0], alpha=alpha[0], radii=radii[0],
+             tiles_touched=st.tiles_touched, keys=st.keys_sorted[:st.R], ids=st.vals_sorted[:st.R],
+             ranges=st.ranges, n_contrib=st.n_contrib[0], final_T=st.final_T[0], R=st.R,
+             grads=dict(means3D=cl[0].grad, scales=cl[1].grad, rotations=cl[2].grad, opacities=cl[3].grad,
+                        shs=cl[4].grad, means2D=cm2d.grad))
+    return o, c
+
+
+def compare_raster(o, c, verbose=True):
+    """Returns (int_mismatches: dict name->count, float_errs: dict name->rel_err)."""
+    ints = {}
+    ints["radii"] = int((o["radii"] != c["radii"].cpu()).sum())
+    ints["tiles_touched"] = int((o["tiles_touched"] != c["tiles_touched"].cpu()).sum())
+    ints["R"] = abs(int(o["keys"].numel()) - int(c["R"]))
+    if ints["R"] == 0:
+        ints["keys"] = int((o["keys"] != c["keys"].cpu()).sum())
+        ints["ids"] = int((o["ids"] != c["ids"].cpu().long()).sum())
+        ints["ranges"] = int((o["ranges"] != c["ranges"].cpu().long()).sum())
+    flo = {k: rel_err(c[k], o[k]) for k in ("image", "depth", "normal", "alpha", "final_T")}
+    flo["n_contrib_mismatch_frac"] = (o["n_contrib"] != c["n_contrib"].cpu()).double().mean().item()
+    gr = {k: rel_err(c["grads"][k], o["grads"][k]) for k in o["grads"]}
+    if verbose:
+        print("ints", ints)
+        print("pix ", {k: f"{v:.2e}" for k, v in flo.items()})
+        print("grad", {k: f"{v:.2e}" for k, v in gr.items()})
+    return ints, flo, gr
+
+
+def smoke():
+    o, c = run_raster_pair(800, 64, 64)
+    ints, flo, gr = compare_raster(o, c)
+    assert all(v == 0 for v in ints.values()), ints
+    assert all(flo[k] < PIX_TOL for k in ("image", "depth", "normal", "alpha")), flo
+    assert all(v < 5 * GRAD_TOL for v in gr.values()), gr
