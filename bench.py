@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- train frames/s of the DIMO deform -> raster -> loss step on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's algorithm on the host CPU (oracle port)
+
+One "step" = one optimisation step over S frames per GPU: find_knn -> TimeNet over the unique (motion,t)
+pairs -> LBS -> batched rasterisation -> {MSE, SSIM, mask-MSE} -> backward -> [all-reduce] -> Adam.
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n_gaussians, n_ctrl, H, W, motions/step/GPU, views/step, frames/step, total motions/GPU, total frames, total views)
+    "c3": dict(N=100_000, M=512, H=512, W=512, bm=4, bv=2, bf=2, motions_per_gpu=16, frames=32, views=8,
+               desc="c3 shard: 100k synthetic Gaussians, 512 control points, 512x512, 16 motions x 32 frames per GPU"),
+    "c2": dict(N=30_000, M=512, H=512, W=512, bm=4, bv=2, bf=2, motions_per_gpu=51, frames=20, views=9,
+               desc="c2 shape: 30k synthetic Gaussians, 512 control points, 512x512, 51 motions x 20 frames"),
+    "small": dict(N=5_000, M=128, H=128, W=128, bm=2, bv=2, bf=2, motions_per_gpu=4, frames=8, views=4,
+                  desc="small smoke workload"),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-frames", type=int, default=1, help="frames in the bounded CPU sample")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+def build_model(wl, rank, device, seed=0):
+    import torch
+    from dimo_b200 import synthetic
+    from dimo_b200.renderer import Renderer
+    sc = synthetic.make_scene(wl["N"], n_ctrl=wl["M"], n_motions=wl["motions_per_gpu"], seed=seed)
+    # each rank owns its own block of motions (latent codes): different seed stream for the latents only
+    g = torch.Generator().manual_seed(1000 + rank)
+    sc["_latent_codes"] = torch.randn(wl["motions_per_gpu"], 32, generator=g)
+    r = Renderer(sh_degree=0, white_background=True, num_latent_code=wl["motions_per_gpu"], add_normal=True,
+                 device=device)
+    r.gaussians.load_state(sc)
+    # xavier everywhere, the two head layers scaled x0.01 instead of the zero/identity init
+    tn = r.gaussians._timenet
+    gi = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for lin in (tn.pts_layers[-1], tn.rot_layers[-1]):
+            w = torch.empty_like(lin.weight, device="cpu")
+            torch.nn.init.xavier_uniform_(w, generator=gi)
+            lin.weight.copy_(0.01 * w)
+        tn.rot_layers[-1].bias.copy_(torch.tensor([1.0, 0, 0, 0]))
+    return r, sc
+
+
+def step_schedule(wl, step):
+    """Deterministic stand-in for the reference's random.sample (main_train_dimo.py:266-270):
+    bm motions x bv views x bf frames, motion-major."""
+    ms = [(step * wl["bm"] + i) % wl["motions_per_gpu"] for i in range(wl["bm"])]
+    vs = [(step * wl["bv"] + i) % wl["views"] for i in range(wl["bv"])]
+    fs = [(step * wl["bf"] + i) % wl["frames"] for i in range(wl["bf"])]
+    frames = [(m, v, f) for m in ms for v in vs for f in fs]
+    return frames
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                f = [x.strip() for x in out.split(",")]
+                self.samples.append(float(f[0])); self.max_mhz = float(f[1])
+                for n, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline(wl, n_frames, threads=None):
+    """Times the oracle (CPU restatement of the reference algorithm, autograd backward) on `n_frames` frames of the
+    same workload: deform (TimeNet+LBS) -> raster -> MSE+SSIM+mask loss -> backward.  Returns frames/s."""
+    import torch
+    from dimo_b200 import synthetic
+    from oracle import deform as od, raster as orast, camera as ocam, loss as oloss, knn as oknn
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    sc = synthetic.make_scene(wl["N"], n_ctrl=wl["M"], n_motions=wl["motions_per_gpu"], seed=0)
+    params = od.timenet_init(32, seed=0, final_scale=0.01)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sc.items()}
+    H, W = wl["H"], wl["W"]
+    g = torch.Generator().manual_seed(5)
+    t0 = time.perf_counter()
+    dist, idx = oknn.knn(sc["_c_xyz"], sc["_xyz"], 4)
+    done = 0
+    for (m, v, f) in step_schedule(wl, 0)[:n_frames]:
+        cam = ocam.orbit_cam(v, wl["views"], W, H)
+        t = f / wl["frames"]
+        dxyz, dquat = od.timenet_forward(params, leaves["_c_xyz"], t, leaves["_latent_codes"][m])
+        means, rots = od.lbs_deform(leaves["_xyz"], leaves["_rotation"], leaves["_c_xyz"],
+                                    torch.exp(leaves["_c_radius"]), dxyz, dquat, idx, dist)
+        out = orast.rasterize(means, torch.exp(leaves["_scaling"]), rots, torch.sigmoid(leaves["_opacity"]),
+                              cam.world_view_transform, cam.full_proj_transform, cam.camera_center, cam.tanfovx,
+                              cam.tanfovy, W, H, torch.ones(3),
+                              shs=torch.cat([leaves["_features_dc"], leaves["_features_rest"]], 1), sh_degree=0)
+        gt = torch.rand(1, 3, H, W, generator=g); mk = torch.rand(1, 1, H, W, generator=g)
+        img = out["image"].clamp(0, 1)[None]
+        loss = 5000.0 * oloss.mse_loss(img, gt) + 500.0 * (1 - oloss.ssim(img, gt)) + \
+            500.0 * oloss.mse_loss(out["alpha"][None], mk)
+        loss.backward()
+        done += 1
+    dt = time.perf_counter() - t0
+    return done / dt, dt, threads
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    budget_s = 150.0                      # keep the whole arm within a few minutes
+    t_start = time.perf_counter()
+    for _ in range(max(1, args.steps)):
+        fps, dt, threads = cpu_baseline(wl, args.cpu_frames)
+        vals.append((fps, dt))
+        if time.perf_counter() - t_start + dt > budget_s:
+            break
+    fps = sorted(v[0] for v in vals)[len(vals) // 2]
+    sample = f"{args.cpu_frames} frame(s) of the {args.workload} workload (of {wl['bm'] * wl['bv'] * wl['bf']} per step), " \
+             f"deform+raster+loss fwd+bwd, oracle port (PyTorch CPU + autograd)"
+    line = {"impl": "reference", "metric": "train frames/s (deform+raster+SSIM fwd+bwd)", "value": fps,
+            "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 / fps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": wl["desc"], "H": wl["H"], "W": wl["W"],
+                                                          "gaussians": wl["N"]},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ge.ensure_built()
+    from dimo_b200 import _lib, trainstep
+    from dimo_b200.camera import orbit_minicam
+
+    r, _ = build_model(wl, rank, dev)
+    ts = trainstep.TrainStep(r, lr=1e-5, world=world)
+    H, W = wl["H"], wl["W"]
+    S = wl["bm"] * wl["bv"] * wl["bf"]
+    cams_all = [orbit_minicam(v, wl["views"], W, H, device=dev) for v in range(wl["views"])]
+
+    # ground truth: U(0,1) images + masks for a pool of steps, in pinned host memory (e2e) and resident in HBM (value)
+    pool = min(4, args.steps + args.warmup)
+    g = torch.Generator().manual_seed(1234 + rank)
+    gt_host = [torch.rand(S, 3, H, W, generator=g).pin_memory() for _ in range(pool)]
+    mk_host = [torch.rand(S, 1, H, W, generator=g).pin_memory() for _ in range(pool)]
+    gt_dev = [t.to(dev) for t in gt_host]
+    mk_dev = [t.to(dev) for t in mk_host]
+
+    def one_step(i, e2e):
+        frames = step_schedule(wl, i)
+        cams = [cams_all[v] for (_, v, _) in frames]
+        times = [f / wl["frames"] for (_, _, f) in frames]
+        lat = [m for (m, _, _) in frames]
+        if e2e:
+            gt = gt_host[i % pool].to(dev, non_blocking=True)
+            mk = mk_host[i % pool].to(dev, non_blocking=True)
+        else:
+            gt, mk = gt_dev[i % pool], mk_dev[i % pool]
+        loss = ts.run(cams, times, lat, gt, mk, wl["bm"])
+        if e2e:
+            return loss.item()          # device -> host read of the step's result
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(e2e, steps, warmup, profile=False):
+        for i in range(warmup):
+            one_step(i, e2e)
+        barrier()
+        if profile:
+            _lib.PROFILE.reset(enabled=True)
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(warmup, warmup + steps):
+            one_step(i, e2e)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if profile:
+            _lib.PROFILE.enabled = False
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms = timed(False, args.steps, args.warmup, profile=True)
+    prof = _lib.PROFILE.summary()
+    clocks = sampler.stop() if sampler else None
+    frames_total = world * S * args.steps
+    value = frames_total / (ms / 1000.0)
+
+    e2e = None
+    if not args.no_e2e:
+        ms_e = timed(True, args.steps, 1)
+        cam_bytes = S * 40 * 4
+        e2e = {"value": world * S * args.steps / (ms_e / 1000.0), "unit": "frames/s",
+               "h2d_bytes_per_step": S * 4 * H * W * 4 + cam_bytes, "d2h_bytes_per_step": 4}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # roofline for the dominant kernel group of the step (measured live above with CUDA events per C-ABI call)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    roof = None
+    if prof:
+        top = max(prof.items(), key=lambda kv: kv[1]["ms"])
+        name, rec = top
+        st = r_state_stats(_lib)
+        alg = algorithmic_bytes(name, wl, S, st)
+        dur_s = rec["ms"] / rec["calls"] / 1000.0
+        roof = {"kernel": name, "bound": "hbm", "achieved": alg / dur_s / 1e9 if alg else None, "peak": hbm_peak,
+                "unit": "GB/s", "frac": (alg / dur_s / 1e9 / hbm_peak) if alg else None, "traffic": None,
+                "peak_source": peak_src, "avg_launch_ms": rec["ms"] / rec["calls"],
+                "share_of_step": rec["ms"] / ms,
+                "note": "blend kernels are FP32-FMA/MUFU-issue bound by design (DESIGN.md K5/K6); HBM fraction is reported as the contract asks",
+                "breakdown_ms_per_step": {k: round(v["ms"] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
+                "instances_R_per_step": st.get("R"), "pairs_note": "R = tile instances of the last step"}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        fps, dt, threads = cpu_baseline(wl, args.cpu_frames)
+        cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+               "sample": f"{args.cpu_frames} frame(s) of the same workload ({dt:.1f} s), oracle port of deform+raster+loss fwd+bwd"}
+
+    line = {"metric": "train frames/s (deform+raster+SSIM fwd+bwd)", "value": value, "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "frames_per_step_per_gpu": S, "H": H, "W": W, "gaussians": wl["N"],
+                       "parallelism": f"motion-sharded dp{world}, one flat NCCL all-reduce/step" if world > 1 else "single GPU",
+                       "optimizer": "torch fused Adam (plumbing; hand-written fused Adam is SURVEY 8f N1)",
+                       "l2": "per-step working set (GT 64 MiB + splat/instance buffers > 200 MiB) exceeds the 126 MB L2; no explicit flush",
+                       "raster_MPix_per_s_fwd_bwd": value * H * W / 1e6},
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": _lib.PROFILE.kernel_launches_per_step(args.steps)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def r_state_stats(_lib):
+    return dict(_lib.PROFILE.extra)
+
+
+def algorithmic_bytes(name, wl, S, st):
+    """Algorithmic HBM bytes per launch (DESIGN.md 'Kernels')."""
+    P = wl["H"] * wl["W"] * S
+    R = st.get("R") or 0
+    BN = wl["N"] * S
+    table = {
+        "dimo_raster_blend_fwd": 64 * R + 40 * P,
+        "dimo_raster_blend_bwd": 64 * R + 4 * R + 72 * P + 2 * 52 * R,
+        "dimo_raster_preprocess": 56 * BN + 72 * BN,
+        "dimo_raster_bin": 12 * R + 6 * 24 * R + 2 * 64 * R,
+        "dimo_raster_preprocess_bwd": 64 * BN + 44 * BN + 60 * BN,
+        "dimo_ssim_fwd": 8 * 3 * P + 36 * P,
+        "dimo_ssim_bwd": 60 * P + 12 * P,
+    }
+    return table.get(name)
+
+
+def main():
+    args = parse()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -27,14 +27,14 @@ _SIGS = {
     "dimo_knn": (c_int, [c_int] * 3 + [c_vp] * 5),
     "dimo_dist3nn": (c_int, [c_int, c_vp, c_vp, c_vp]),
     "dimo_linear_fwd": (c_int, [c_int] * 3 + [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_int, c_vp]),
-    "dimo_linear_bwd_data": (c_int, [c_int] * 3 + [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_vp]),
-    "dimo_linear_bwd_weight": (c_int, [c_int] * 3 + [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "dimo_linear_bwd_data": (c_int, [c_int] * 3 + [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_vp]),
+    "dimo_linear_bwd_weight": (c_int, [c_int] * 3 + [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "dimo_timenet_embed_fwd": (c_int, [c_int] * 3 + [c_vp] * 4 + [c_i64, c_vp]),
     "dimo_timenet_embed_bwd": (c_int, [c_int] * 3 + [c_vp] * 3 + [c_i64, c_vp, c_vp, c_vp]),
     "dimo_lbs_fwd": (c_int, [c_int] * 4 + [c_vp] * 11),
     "dimo_lbs_bwd": (c_int, [c_int] * 4 + [c_vp] * 17),
-    "dimo_ssim_fwd": (c_int, [c_int] * 4 + [c_vp] * 5),
-    "dimo_ssim_bwd": (c_int, [c_int] * 4 + [c_vp] * 3 + [c_f32] * 3 + [c_vp, c_vp]),
+    "dimo_ssim_fwd": (c_int, [c_int] * 5 + [c_vp] * 5),
+    "dimo_ssim_bwd": (c_int, [c_int] * 5 + [c_vp] * 3 + [c_f32] * 3 + [c_vp, c_vp]),
 }
 
 
@@ -80,8 +80,55 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# hand-written kernels launched per C-ABI call (CUB scan/sort launches are listed separately)
+_OWN_LAUNCHES = {
+    "dimo_raster_preprocess": 1, "dimo_raster_bin": 2, "dimo_raster_blend_fwd": 1, "dimo_raster_blend_bwd": 1,
+    "dimo_raster_preprocess_bwd": 1, "dimo_knn": 1, "dimo_dist3nn": 1, "dimo_linear_fwd": 1,
+    "dimo_linear_bwd_data": 1, "dimo_linear_bwd_weight": 1, "dimo_timenet_embed_fwd": 1,
+    "dimo_timenet_embed_bwd": 1, "dimo_lbs_fwd": 1, "dimo_lbs_bwd": 1, "dimo_ssim_fwd": 1, "dimo_ssim_bwd": 1,
+}
+
+
+class _Profile:
+    """Optional per-call CUDA-event timing on the launching stream (bench.py's live roofline numbers)."""
+
+    def __init__(self):
+        self.reset(False)
+
+    def reset(self, enabled=False):
+        self.enabled = enabled
+        self.events = []          # (name, start, end)
+        self.counts = {}
+        self.extra = getattr(self, "extra", {})
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1 in self.events:
+            rec = out.setdefault(name, {"ms": 0.0, "calls": 0})
+            rec["ms"] += e0.elapsed_time(e1)
+            rec["calls"] += 1
+        return out
+
+    def kernel_launches_per_step(self, steps):
+        n = sum(_OWN_LAUNCHES.get(k, 0) * v for k, v in self.counts.items())
+        return n // max(steps, 1)
+
+
+PROFILE = _Profile()
+
+
 def call(name, *args):
     fn = getattr(lib(), name, None)
     if fn is None:
         raise RuntimeError(f"libdimo_b200.so does not export {name}: rebuild with `python -m dimo_b200.build`")
-    check(fn(*args))
+    if PROFILE.enabled:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(fn(*args))
+        e1.record()
+        PROFILE.events.append((name, e0, e1))
+        PROFILE.counts[name] = PROFILE.counts.get(name, 0) + 1
+    else:
+        check(fn(*args))

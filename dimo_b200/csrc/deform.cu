@@ -1,0 +1,302 @@
+// K-neighbour linear-blend skinning of the canonical Gaussians by the deformed control points,
+// fused with the rotation activation -- the stage-s2 block of Renderer.render
+// (renderer/latent_gs_renderer.py:1191-1209, :1219; helpers build_rotation_3d :112-133,
+// quat_mul :135-147, get_c_radius :403-407).
+//
+// The reference runs ~40 elementwise/gather launches with [N,4,3,3] temporaries per render; here one
+// kernel per direction handles all B (motion,t) frames of a step.  HBM-bound: fwd reads
+// xyz 12 + rot 16 + idx 32 + dist 16 B per Gaussian once per block column and writes 28 B per
+// (frame, Gaussian); the M x 11-float control tables stay in L1/L2.
+//
+// Backward accumulates control-point gradients in a shared-memory table (M x 11 floats) per CTA and
+// flushes once, instead of N*K*11 contended global atomics on 512 addresses.
+#include "common.cuh"
+
+namespace dimo {
+
+constexpr float LBS_EPS = 1e-7f;        // renderer/latent_gs_renderer.py:1192
+constexpr float NORM_EPS = 1e-12f;      // F.normalize default eps
+constexpr int LBS_MAXK = 8;
+
+struct Quat { float r, x, y, z; };
+
+__device__ __forceinline__ void rot_from_unit(const Quat& q, float R[3][3]) {
+  const float r = q.r, x = q.x, y = q.y, z = q.z;
+  R[0][0] = 1.f - 2.f * (y * y + z * z); R[0][1] = 2.f * (x * y - r * z); R[0][2] = 2.f * (x * z + r * y);
+  R[1][0] = 2.f * (x * y + r * z); R[1][1] = 1.f - 2.f * (x * x + z * z); R[1][2] = 2.f * (y * z - r * x);
+  R[2][0] = 2.f * (x * z - r * y); R[2][1] = 2.f * (y * z + r * x); R[2][2] = 1.f - 2.f * (x * x + y * y);
+}
+
+__device__ __forceinline__ Quat quat_mul(const Quat& a, const Quat& b) {
+  Quat o;
+  o.r = a.r * b.r - a.x * b.x - a.y * b.y - a.z * b.z;
+  o.x = a.r * b.x + a.x * b.r + a.y * b.z - a.z * b.y;
+  o.y = a.r * b.y - a.x * b.z + a.y * b.r + a.z * b.x;
+  o.z = a.r * b.z + a.x * b.y - a.y * b.x + a.z * b.r;
+  return o;
+}
+
+// skinning weights for one Gaussian: w_k = exp(-d^2 / (2 r^2)) + eps, L1-normalised
+template <int K>
+__device__ __forceinline__ float lbs_weights(const float* dist_i, const int64_t* idx_i,
+                                             const float* __restrict__ c_radius_raw, float* w, float* e,
+                                             float* rad, int* nb) {
+  float S = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    nb[k] = (int)idx_i[k];
+    rad[k] = expf(c_radius_raw[nb[k]]);
+    const float d = dist_i[k];
+    e[k] = expf(-1.0f * (d * d) / (2.0f * (rad[k] * rad[k])));
+    w[k] = e[k] + LBS_EPS;
+    S += fabsf(w[k]);
+  }
+  return fmaxf(S, NORM_EPS);
+}
+
+template <int K>
+__global__ void __launch_bounds__(256) lbs_fwd_kernel(
+    int N, int M, const float* __restrict__ xyz, const float* __restrict__ rot, const int64_t* __restrict__ idx,
+    const float* __restrict__ dist, const float* __restrict__ c_xyz, const float* __restrict__ c_radius_raw,
+    const float* __restrict__ dxyz, const float* __restrict__ dquat, float* __restrict__ means3D,
+    float4* __restrict__ rotations) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (i >= N) return;
+  float w[K], e[K], rad[K];
+  int nb[K];
+  const float S = lbs_weights<K>(dist + (int64_t)i * K, idx + (int64_t)i * K, c_radius_raw, w, e, rad, nb);
+  const float px = xyz[3 * (int64_t)i], py = xyz[3 * (int64_t)i + 1], pz = xyz[3 * (int64_t)i + 2];
+  const float* dx_b = dxyz + (int64_t)b * M * 3;
+  const float* dq_b = dquat + (int64_t)b * M * 4;
+  float ox = 0.f, oy = 0.f, oz = 0.f;
+  Quat qb = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int j = nb[k];
+    const float wn = w[k] / S;
+    const float4 dq = *reinterpret_cast<const float4*>(dq_b + 4 * (int64_t)j);
+    const float nrm = sqrtf(dq.x * dq.x + dq.y * dq.y + dq.z * dq.z + dq.w * dq.w);
+    const Quat qn = {dq.x / nrm, dq.y / nrm, dq.z / nrm, dq.w / nrm};
+    float R[3][3];
+    rot_from_unit(qn, R);
+    const float cx = c_xyz[3 * j], cy = c_xyz[3 * j + 1], cz = c_xyz[3 * j + 2];
+    const float vx = px - cx, vy = py - cy, vz = pz - cz;
+    ox += wn * (R[0][0] * vx + R[0][1] * vy + R[0][2] * vz + cx + dx_b[3 * j]);
+    oy += wn * (R[1][0] * vx + R[1][1] * vy + R[1][2] * vz + cy + dx_b[3 * j + 1]);
+    oz += wn * (R[2][0] * vx + R[2][1] * vy + R[2][2] * vz + cz + dx_b[3 * j + 2]);
+    qb.r += wn * dq.x; qb.x += wn * dq.y; qb.y += wn * dq.z; qb.z += wn * dq.w;
+  }
+  const float4 rc4 = *reinterpret_cast<const float4*>(rot + 4 * (int64_t)i);
+  const Quat rc = {rc4.x, rc4.y, rc4.z, rc4.w};
+  const Quat u = quat_mul(qb, rc);
+  const float un = fmaxf(sqrtf(u.r * u.r + u.x * u.x + u.y * u.y + u.z * u.z), NORM_EPS);
+  const int64_t o = (int64_t)b * N + i;
+  means3D[3 * o] = ox; means3D[3 * o + 1] = oy; means3D[3 * o + 2] = oz;
+  rotations[o] = make_float4(u.r / un, u.x / un, u.y / un, u.z / un);
+}
+
+// control-table gradient slots: [0:3) ddxyz  [3:7) ddquat  [7:10) dc_xyz  [10] dc_radius_raw
+constexpr int CT = 11;
+
+template <int K>
+__global__ void __launch_bounds__(256) lbs_bwd_kernel(
+    int N, int M, int use_smem, const float* __restrict__ xyz, const float* __restrict__ rot,
+    const int64_t* __restrict__ idx, const float* __restrict__ dist, const float* __restrict__ c_xyz,
+    const float* __restrict__ c_radius_raw, const float* __restrict__ dxyz, const float* __restrict__ dquat,
+    const float* __restrict__ g_means3D, const float4* __restrict__ g_rotations, float* __restrict__ dxyz_c,
+    float* __restrict__ drot_c, float* __restrict__ dc_xyz, float* __restrict__ dc_radius_raw,
+    float* __restrict__ ddxyz, float* __restrict__ ddquat) {
+  extern __shared__ float tab[];   // [M][CT] when use_smem
+  const int b = blockIdx.y;
+  if (use_smem) {
+    for (int e = threadIdx.x; e < M * CT; e += blockDim.x) tab[e] = 0.f;
+    __syncthreads();
+  }
+  const float* dx_b = dxyz + (int64_t)b * M * 3;
+  const float* dq_b = dquat + (int64_t)b * M * 4;
+  float* ddx_b = ddxyz + (int64_t)b * M * 3;
+  float* ddq_b = ddquat + (int64_t)b * M * 4;
+
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    float w[K], e[K], rad[K];
+    int nb[K];
+    const float S = lbs_weights<K>(dist + (int64_t)i * K, idx + (int64_t)i * K, c_radius_raw, w, e, rad, nb);
+    const float px = xyz[3 * (int64_t)i], py = xyz[3 * (int64_t)i + 1], pz = xyz[3 * (int64_t)i + 2];
+    const int64_t o = (int64_t)b * N + i;
+    const float gx = g_means3D[3 * o], gy = g_means3D[3 * o + 1], gz = g_means3D[3 * o + 2];
+    const float4 gr4 = g_rotations[o];
+
+    // recompute blended quaternion and product (cheap) for the normalisation backward
+    Quat qb = {0.f, 0.f, 0.f, 0.f};
+    float4 dqv[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      dqv[k] = *reinterpret_cast<const float4*>(dq_b + 4 * (int64_t)nb[k]);
+      const float wn = w[k] / S;
+      qb.r += wn * dqv[k].x; qb.x += wn * dqv[k].y; qb.y += wn * dqv[k].z; qb.z += wn * dqv[k].w;
+    }
+    const float4 rc4 = *reinterpret_cast<const float4*>(rot + 4 * (int64_t)i);
+    const Quat rc = {rc4.x, rc4.y, rc4.z, rc4.w};
+    const Quat u = quat_mul(qb, rc);
+    const float un_raw = sqrtf(u.r * u.r + u.x * u.x + u.y * u.y + u.z * u.z);
+    const float un = fmaxf(un_raw, NORM_EPS);
+    const float y0 = u.r / un, y1 = u.x / un, y2 = u.y / un, y3 = u.z / un;
+    float g0 = gr4.x, g1 = gr4.y, g2 = gr4.z, g3 = gr4.w;
+    if (un_raw > NORM_EPS) {
+      const float dotyg = y0 * g0 + y1 * g1 + y2 * g2 + y3 * g3;
+      g0 = (g0 - y0 * dotyg) / un; g1 = (g1 - y1 * dotyg) / un; g2 = (g2 - y2 * dotyg) / un; g3 = (g3 - y3 * dotyg) / un;
+    } else {
+      g0 /= un; g1 /= un; g2 /= un; g3 /= un;
+    }
+    // u = qb (x) rc
+    const float gq_r = g0 * rc.r + g1 * rc.x + g2 * rc.y + g3 * rc.z;
+    const float gq_x = -g0 * rc.x + g1 * rc.r - g2 * rc.z + g3 * rc.y;
+    const float gq_y = -g0 * rc.y + g1 * rc.z + g2 * rc.r - g3 * rc.x;
+    const float gq_z = -g0 * rc.z - g1 * rc.y + g2 * rc.x + g3 * rc.r;
+    const float gc_r = g0 * qb.r + g1 * qb.x + g2 * qb.y + g3 * qb.z;
+    const float gc_x = -g0 * qb.x + g1 * qb.r + g2 * qb.z - g3 * qb.y;
+    const float gc_y = -g0 * qb.y - g1 * qb.z + g2 * qb.r + g3 * qb.x;
+    const float gc_z = -g0 * qb.z + g1 * qb.y - g2 * qb.x + g3 * qb.r;
+    atomicAdd(&drot_c[4 * (int64_t)i + 0], gc_r);
+    atomicAdd(&drot_c[4 * (int64_t)i + 1], gc_x);
+    atomicAdd(&drot_c[4 * (int64_t)i + 2], gc_y);
+    atomicAdd(&drot_c[4 * (int64_t)i + 3], gc_z);
+
+    float gwn[K];
+    float gxyz[3] = {0.f, 0.f, 0.f};
+    float dotw = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int j = nb[k];
+      const float wn = w[k] / S;
+      const float4 dq = dqv[k];
+      const float nrm = sqrtf(dq.x * dq.x + dq.y * dq.y + dq.z * dq.z + dq.w * dq.w);
+      const Quat qn = {dq.x / nrm, dq.y / nrm, dq.z / nrm, dq.w / nrm};
+      float R[3][3];
+      rot_from_unit(qn, R);
+      const float cx = c_xyz[3 * j], cy = c_xyz[3 * j + 1], cz = c_xyz[3 * j + 2];
+      const float v[3] = {px - cx, py - cy, pz - cz};
+      const float tx = R[0][0] * v[0] + R[0][1] * v[1] + R[0][2] * v[2] + cx + dx_b[3 * j];
+      const float ty = R[1][0] * v[0] + R[1][1] * v[1] + R[1][2] * v[2] + cy + dx_b[3 * j + 1];
+      const float tz = R[2][0] * v[0] + R[2][1] * v[1] + R[2][2] * v[2] + cz + dx_b[3 * j + 2];
+      gwn[k] = gx * tx + gy * ty + gz * tz + gq_r * dq.x + gq_x * dq.y + gq_y * dq.z + gq_z * dq.w;
+      dotw += gwn[k] * wn;
+      // R^T g
+      const float rtg[3] = {R[0][0] * gx + R[1][0] * gy + R[2][0] * gz, R[0][1] * gx + R[1][1] * gy + R[2][1] * gz,
+                            R[0][2] * gx + R[1][2] * gy + R[2][2] * gz};
+      gxyz[0] += wn * rtg[0]; gxyz[1] += wn * rtg[1]; gxyz[2] += wn * rtg[2];
+      // dL/dR = wn * g v^T  ->  unit quaternion  ->  raw dquat (through normalisation)
+      const float gvec[3] = {gx, gy, gz};
+      float dR[3][3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) dR[a][c] = wn * gvec[a] * v[c];
+      const float r = qn.r, x = qn.x, y = qn.y, z = qn.z;
+      float gn0 = 2.f * (-z * dR[0][1] + y * dR[0][2] + z * dR[1][0] - x * dR[1][2] - y * dR[2][0] + x * dR[2][1]);
+      float gn1 = 2.f * (y * dR[0][1] + z * dR[0][2] + y * dR[1][0] - 2.f * x * dR[1][1] - r * dR[1][2] + z * dR[2][0] +
+                         r * dR[2][1] - 2.f * x * dR[2][2]);
+      float gn2 = 2.f * (-2.f * y * dR[0][0] + x * dR[0][1] + r * dR[0][2] + x * dR[1][0] + z * dR[1][2] - r * dR[2][0] +
+                         z * dR[2][1] - 2.f * y * dR[2][2]);
+      float gn3 = 2.f * (-2.f * z * dR[0][0] - r * dR[0][1] + x * dR[0][2] + r * dR[1][0] - 2.f * z * dR[1][1] +
+                         y * dR[1][2] + x * dR[2][0] + y * dR[2][1]);
+      const float dotn = r * gn0 + x * gn1 + y * gn2 + z * gn3;
+      const float gdq0 = (gn0 - r * dotn) / nrm + wn * gq_r;
+      const float gdq1 = (gn1 - x * dotn) / nrm + wn * gq_x;
+      const float gdq2 = (gn2 - y * dotn) / nrm + wn * gq_y;
+      const float gdq3 = (gn3 - z * dotn) / nrm + wn * gq_z;
+      if (use_smem) {
+        float* tj = tab + j * CT;
+        atomicAdd(tj + 0, wn * gx); atomicAdd(tj + 1, wn * gy); atomicAdd(tj + 2, wn * gz);
+        atomicAdd(tj + 3, gdq0); atomicAdd(tj + 4, gdq1); atomicAdd(tj + 5, gdq2); atomicAdd(tj + 6, gdq3);
+        atomicAdd(tj + 7, wn * (gx - rtg[0])); atomicAdd(tj + 8, wn * (gy - rtg[1])); atomicAdd(tj + 9, wn * (gz - rtg[2]));
+      } else {
+        atomicAdd(ddx_b + 3 * j + 0, wn * gx); atomicAdd(ddx_b + 3 * j + 1, wn * gy); atomicAdd(ddx_b + 3 * j + 2, wn * gz);
+        atomicAdd(ddq_b + 4 * j + 0, gdq0); atomicAdd(ddq_b + 4 * j + 1, gdq1);
+        atomicAdd(ddq_b + 4 * j + 2, gdq2); atomicAdd(ddq_b + 4 * j + 3, gdq3);
+        atomicAdd(dc_xyz + 3 * j + 0, wn * (gx - rtg[0])); atomicAdd(dc_xyz + 3 * j + 1, wn * (gy - rtg[1]));
+        atomicAdd(dc_xyz + 3 * j + 2, wn * (gz - rtg[2]));
+      }
+    }
+    atomicAdd(&dxyz_c[3 * (int64_t)i + 0], gxyz[0]);
+    atomicAdd(&dxyz_c[3 * (int64_t)i + 1], gxyz[1]);
+    atomicAdd(&dxyz_c[3 * (int64_t)i + 2], gxyz[2]);
+    // weights: wn = w / S ; w = exp(-d^2 / (2 r^2)) + eps ; r = exp(raw)
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const float gw = (gwn[k] - dotw) / S;
+      const float d = dist[(int64_t)i * K + k];
+      const float graw = gw * e[k] * (d * d) / (rad[k] * rad[k]);   // dw/dr * r = e * d^2 / r^2
+      if (use_smem) atomicAdd(tab + nb[k] * CT + 10, graw);
+      else atomicAdd(dc_radius_raw + nb[k], graw);
+    }
+  }
+  if (use_smem) {
+    __syncthreads();
+    for (int e2 = threadIdx.x; e2 < M * CT; e2 += blockDim.x) {
+      const float val = tab[e2];
+      if (val == 0.f) continue;
+      const int j = e2 / CT, q = e2 - j * CT;
+      if (q < 3) atomicAdd(ddx_b + 3 * j + q, val);
+      else if (q < 7) atomicAdd(ddq_b + 4 * j + (q - 3), val);
+      else if (q < 10) atomicAdd(dc_xyz + 3 * j + (q - 7), val);
+      else atomicAdd(dc_radius_raw + j, val);
+    }
+  }
+}
+
+}  // namespace dimo
+
+using namespace dimo;
+
+extern "C" int dimo_lbs_fwd(int B, int N, int M, int K, const float* xyz, const float* rot, const int64_t* idx,
+                            const float* dist, const float* c_xyz, const float* c_radius_raw, const float* dxyz,
+                            const float* dquat, float* means3D, float* rotations, void* stream) {
+  DIMO_REQUIRE(K >= 1 && K <= LBS_MAXK, "K must be 1..8");
+  if (B == 0 || N == 0) return 0;
+  dim3 grid(ceil_div(N, 256), B);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (K) {
+#define DIMO_LBS_CASE(KK)                                                                                         \
+  case KK:                                                                                                        \
+    lbs_fwd_kernel<KK><<<grid, 256, 0, st>>>(N, M, xyz, rot, idx, dist, c_xyz, c_radius_raw, dxyz, dquat, means3D, \
+                                             reinterpret_cast<float4*>(rotations));                               \
+    break;
+    DIMO_LBS_CASE(1) DIMO_LBS_CASE(2) DIMO_LBS_CASE(3) DIMO_LBS_CASE(4)
+    DIMO_LBS_CASE(5) DIMO_LBS_CASE(6) DIMO_LBS_CASE(7) DIMO_LBS_CASE(8)
+#undef DIMO_LBS_CASE
+  }
+  DIMO_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dimo_lbs_bwd(int B, int N, int M, int K, const float* xyz, const float* rot, const int64_t* idx,
+                            const float* dist, const float* c_xyz, const float* c_radius_raw, const float* dxyz,
+                            const float* dquat, const float* dL_dmeans3D, const float* dL_drotations, float* dxyz_c,
+                            float* drot_c, float* dc_xyz, float* dc_radius_raw, float* ddxyz, float* ddquat,
+                            void* stream) {
+  DIMO_REQUIRE(K >= 1 && K <= LBS_MAXK, "K must be 1..8");
+  if (B == 0 || N == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = (size_t)M * CT * sizeof(float);
+  const int use_smem = smem <= 160 * 1024 ? 1 : 0;
+  // few, fat CTAs per frame so each shared-memory table is flushed once: ~2 waves over 148 SMs in total
+  int per_frame = max(1, min(ceil_div(N, 256), ceil_div(296, B)));
+  dim3 grid(per_frame, B);
+  switch (K) {
+#define DIMO_LBS_CASE(KK)                                                                                          \
+  case KK: {                                                                                                       \
+    if (use_smem && smem > 48 * 1024)                                                                              \
+      DIMO_CHECK_CUDA(cudaFuncSetAttribute(lbs_bwd_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    lbs_bwd_kernel<KK><<<grid, 256, use_smem ? smem : 0, st>>>(                                                    \
+        N, M, use_smem, xyz, rot, idx, dist, c_xyz, c_radius_raw, dxyz, dquat, dL_dmeans3D,                        \
+        reinterpret_cast<const float4*>(dL_drotations), dxyz_c, drot_c, dc_xyz, dc_radius_raw, ddxyz, ddquat);     \
+  } break;
+    DIMO_LBS_CASE(1) DIMO_LBS_CASE(2) DIMO_LBS_CASE(3) DIMO_LBS_CASE(4)
+    DIMO_LBS_CASE(5) DIMO_LBS_CASE(6) DIMO_LBS_CASE(7) DIMO_LBS_CASE(8)
+#undef DIMO_LBS_CASE
+  }
+  DIMO_CHECK_LAUNCH();
+  return 0;
+}

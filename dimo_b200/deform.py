@@ -1,0 +1,249 @@
+"""Deformation ops (host side): TimeNet (positional encoding + 12 fused Linear layers) and K-neighbour
+linear-blend skinning, batched over the G unique (motion, t) pairs of a step.
+
+`TimeNet` keeps the reference module's structure and parameter names (renderer/latent_gs_renderer.py:
+184-203: deformnet.{0..7}, pts_layers.{0,2}, rot_layers.{0,2}) so released `timenet.pth` checkpoints
+load unchanged; its forward runs libdimo_b200 kernels through `_TimeNetFn` instead of F.linear.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.init as init
+
+from . import _lib
+
+PTS_FREQS, TIME_FREQS, HIDDEN, DEPTH, SKIP_AFTER = 10, 6, 256, 8, 4
+
+
+def _linear_fwd(R, K, No, X, ldx, W, b, Y, ldy, relu, s):
+    _lib.call("dimo_linear_fwd", R, K, No, X, ldx, _lib.ptr(W), _lib.ptr(b), Y, ldy, int(relu), s)
+
+
+class _TimeNetFn(torch.autograd.Function):
+    """(pts [M,3], times [G], latents [G,L], 24 params) -> dxyz [G,M,3], dquat [G,M,4]."""
+
+    @staticmethod
+    def forward(ctx, pts, times, latents, *params):
+        dev = pts.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        pts = pts.contiguous().float()
+        times = times.contiguous().float()
+        latents = latents.contiguous().float()
+        params = [p.contiguous().float() for p in params]
+        Ws, bs = params[0::2], params[1::2]
+        M, G, L = pts.shape[0], times.shape[0], latents.shape[1]
+        R = G * M
+        E = 3 * 2 * PTS_FREQS + 2 * TIME_FREQS + L           # 104
+        CAT = E + HIDDEN                                       # 360
+        s = _lib.stream()
+        # activations: cat = [h0 | out of layer 4]; acts[i] = out of layer i (i != 4)
+        cat = torch.empty(R, CAT, **f32)
+        _lib.call("dimo_timenet_embed_fwd", G, M, L, _lib.ptr(pts), _lib.ptr(times), _lib.ptr(latents),
+                  _lib.ptr(cat), CAT, s)
+        acts = []
+        x_ptr, x_ld, x_k = cat.data_ptr(), CAT, E
+        for i in range(DEPTH):
+            if i == SKIP_AFTER:
+                y = None
+                y_ptr, y_ld = cat.data_ptr() + 4 * E, CAT
+            else:
+                y = torch.empty(R, HIDDEN, **f32)
+                y_ptr, y_ld = y.data_ptr(), HIDDEN
+            _linear_fwd(R, x_k, HIDDEN, x_ptr, x_ld, Ws[i], bs[i], y_ptr, y_ld, True, s)
+            acts.append(y)
+            if i == SKIP_AFTER:
+                x_ptr, x_ld, x_k = cat.data_ptr(), CAT, CAT
+            else:
+                x_ptr, x_ld, x_k = y_ptr, y_ld, HIDDEN
+        h = acts[DEPTH - 1]
+        hp = torch.empty(R, HIDDEN, **f32)
+        hr = torch.empty(R, HIDDEN, **f32)
+        dxyz = torch.empty(G, M, 3, **f32)
+        dquat = torch.empty(G, M, 4, **f32)
+        _linear_fwd(R, HIDDEN, HIDDEN, h.data_ptr(), HIDDEN, Ws[8], bs[8], hp.data_ptr(), HIDDEN, True, s)
+        _linear_fwd(R, HIDDEN, 3, hp.data_ptr(), HIDDEN, Ws[9], bs[9], dxyz.data_ptr(), 3, False, s)
+        _linear_fwd(R, HIDDEN, HIDDEN, h.data_ptr(), HIDDEN, Ws[10], bs[10], hr.data_ptr(), HIDDEN, True, s)
+        _linear_fwd(R, HIDDEN, 4, hr.data_ptr(), HIDDEN, Ws[11], bs[11], dquat.data_ptr(), 4, False, s)
+        ctx.save_for_backward(pts, times, latents, cat, hp, hr, *[a for a in acts if a is not None], *Ws)
+        ctx.dims = (M, G, L, E, CAT)
+        return dxyz, dquat
+
+    @staticmethod
+    def backward(ctx, g_dxyz, g_dquat):
+        M, G, L, E, CAT = ctx.dims
+        R = G * M
+        saved = ctx.saved_tensors
+        pts, times, latents, cat, hp, hr = saved[:6]
+        acts_list = list(saved[6:6 + DEPTH - 1])
+        Ws = list(saved[6 + DEPTH - 1:])
+        acts = acts_list[:SKIP_AFTER] + [None] + acts_list[SKIP_AFTER:]
+        dev = pts.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        s = _lib.stream()
+        g_dxyz = g_dxyz.contiguous().float()
+        g_dquat = g_dquat.contiguous().float()
+        dWs = [torch.zeros_like(W) for W in Ws]
+        dbs = [torch.zeros(W.shape[0], **f32) for W in Ws]
+
+        def bwd_layer(li, K, No, dY_ptr, lddy, Y_ptr, ldy, X_ptr, ldx, dX_ptr, lddx, accumulate):
+            _lib.call("dimo_linear_bwd_weight", R, K, No, dY_ptr, lddy, Y_ptr, ldy, X_ptr, ldx,
+                      _lib.ptr(dWs[li]), _lib.ptr(dbs[li]), s)
+            if dX_ptr is not None:
+                _lib.call("dimo_linear_bwd_data", R, K, No, dY_ptr, lddy, Y_ptr, ldy, _lib.ptr(Ws[li]), dX_ptr, lddx,
+                          int(accumulate), s)
+
+        h = acts[DEPTH - 1]
+        dhp = torch.empty(R, HIDDEN, **f32)
+        dhr = torch.empty(R, HIDDEN, **f32)
+        dh = torch.empty(R, HIDDEN, **f32)
+        # heads (no ReLU on the outputs)
+        bwd_layer(9, HIDDEN, 3, g_dxyz.data_ptr(), 3, None, 0, hp.data_ptr(), HIDDEN, dhp.data_ptr(), HIDDEN, False)
+        bwd_layer(11, HIDDEN, 4, g_dquat.data_ptr(), 4, None, 0, hr.data_ptr(), HIDDEN, dhr.data_ptr(), HIDDEN, False)
+        bwd_layer(8, HIDDEN, HIDDEN, dhp.data_ptr(), HIDDEN, hp.data_ptr(), HIDDEN, h.data_ptr(), HIDDEN,
+                  dh.data_ptr(), HIDDEN, False)
+        bwd_layer(10, HIDDEN, HIDDEN, dhr.data_ptr(), HIDDEN, hr.data_ptr(), HIDDEN, h.data_ptr(), HIDDEN,
+                  dh.data_ptr(), HIDDEN, True)
+        # trunk, layers 7..0 ; dcat collects the skip-concatenated gradient [dh0 | d(out of layer 4)]
+        dcat = torch.empty(R, CAT, **f32)
+        dY_ptr, lddy = dh.data_ptr(), HIDDEN
+        bufs = [dh, torch.empty(R, HIDDEN, **f32)]
+        cur = 0
+        for i in range(DEPTH - 1, -1, -1):
+            if i == SKIP_AFTER:
+                Y_ptr, ldy = cat.data_ptr() + 4 * E, CAT
+            else:
+                Y_ptr, ldy = acts[i].data_ptr(), HIDDEN
+            if i == 0:
+                X_ptr, ldx, K = cat.data_ptr(), CAT, E
+                dX_ptr, lddx, accumulate = dcat.data_ptr(), CAT, True     # += the skip branch's dh0
+            elif i == SKIP_AFTER + 1:
+                X_ptr, ldx, K = cat.data_ptr(), CAT, CAT
+                dX_ptr, lddx, accumulate = dcat.data_ptr(), CAT, False
+            else:
+                prev = acts[i - 1]
+                if i - 1 == SKIP_AFTER:
+                    X_ptr, ldx = cat.data_ptr() + 4 * E, CAT
+                else:
+                    X_ptr, ldx = prev.data_ptr(), HIDDEN
+                K = HIDDEN
+                cur ^= 1
+                dX_ptr, lddx, accumulate = bufs[cur].data_ptr(), HIDDEN, False
+            bwd_layer(i, K, HIDDEN, dY_ptr, lddy, Y_ptr, ldy, X_ptr, ldx, dX_ptr, lddx, accumulate)
+            if i == SKIP_AFTER + 1:
+                dY_ptr, lddy = dcat.data_ptr() + 4 * E, CAT
+            else:
+                dY_ptr, lddy = dX_ptr, lddx
+        need_pts, need_lat = ctx.needs_input_grad[0], ctx.needs_input_grad[2]
+        dpts = torch.zeros(M, 3, **f32) if need_pts else None
+        dlat = torch.zeros(G, L, **f32) if need_lat else None
+        if need_pts or need_lat:
+            _lib.call("dimo_timenet_embed_bwd", G, M, L, _lib.ptr(pts), _lib.ptr(times), _lib.ptr(dcat), CAT,
+                      _lib.ptr(dpts), _lib.ptr(dlat), s)
+        grads = []
+        for W, b in zip(dWs, dbs):
+            grads += [W, b]
+        return (dpts, None, dlat, *grads)
+
+
+def _xavier(m):
+    # renderer/latent_gs_renderer.py:166-170 (the bias branch re-initialises the weight; bias keeps nn.Linear's default)
+    if isinstance(m, nn.Linear):
+        init.xavier_uniform_(m.weight, gain=1)
+
+
+class TimeNet(nn.Module):
+    """Same constructor, parameters and outputs as the reference TimeNet (:184-235)."""
+
+    def __init__(self, D=8, W=256, skips=[4], latent_code_dim=32, device="cuda"):
+        super().__init__()
+        if D != DEPTH or W != HIDDEN or list(skips) != [SKIP_AFTER]:
+            raise NotImplementedError("dimo_b200 TimeNet is specialised to D=8, W=256, skips=[4] (the reference's only use)")
+        self.pts_ch, self.times_ch = PTS_FREQS, TIME_FREQS
+        self.input_ch = 3 * 2 * PTS_FREQS + 2 * TIME_FREQS + latent_code_dim
+        self.skips = skips
+        self.deformnet = nn.ModuleList(
+            [nn.Linear(self.input_ch, W)] +
+            [nn.Linear(W, W) if i not in self.skips else nn.Linear(W + self.input_ch, W) for i in range(D - 1)])
+        self.pts_layers = nn.Sequential(nn.Linear(W, W), nn.ReLU(), nn.Linear(W, 3))
+        self.rot_layers = nn.Sequential(nn.Linear(W, W), nn.ReLU(), nn.Linear(W, 4))
+        self.device = device
+        self.deformnet.apply(_xavier); self.pts_layers.apply(_xavier); self.rot_layers.apply(_xavier)
+        init.constant_(self.pts_layers[-1].weight, 0); init.constant_(self.pts_layers[-1].bias, 0)
+        init.constant_(self.rot_layers[-1].weight, 0)
+        self.rot_layers[-1].bias.data = torch.tensor([1., 0., 0., 0.])
+
+    def flat_params(self):
+        ps = []
+        for l in self.deformnet:
+            ps += [l.weight, l.bias]
+        for l in (self.pts_layers[0], self.pts_layers[2], self.rot_layers[0], self.rot_layers[2]):
+            ps += [l.weight, l.bias]
+        return ps
+
+    def forward_batched(self, pts, times, latents):
+        """pts [M,3]; times [G]; latents [G,L] -> dxyz [G,M,3], dquat [G,M,4] (one launch set for all G)."""
+        return _TimeNetFn.apply(pts, times, latents, *self.flat_params())
+
+    def forward(self, pts, t, latent_code, nobatch=False, t_apply=False):
+        """Reference call forms: (pts [M,3], float t, latent [L]) and the t_apply form
+        (pts [1,M,3], t [T,M,1], latent [L]) used by arap_loss_v2 (:1081-1094)."""
+        if t_apply:
+            p = pts[0] if pts.dim() == 3 else pts
+            times = t[:, 0, 0]
+            lat = latent_code[None, :].expand(times.shape[0], -1)
+            return self.forward_batched(p, times, lat)
+        squeeze = pts.dim() == 2
+        p = pts if squeeze else pts[0]
+        times = torch.tensor([float(t)], dtype=torch.float32).to(p.device, non_blocking=True)
+        dxyz, dquat = self.forward_batched(p, times, latent_code[None, :])
+        return (dxyz[0], dquat[0]) if squeeze else (dxyz, dquat)
+
+    def get_mlp_parameters(self):
+        a, r = [], []
+        for name, p in self.named_parameters():
+            (r if name.split('.')[0] == "rot_layers" else a).append(p)
+        return a, r
+
+
+class _LBSFn(torch.autograd.Function):
+    """(xyz [N,3], rot [N,4], c_xyz [M,3], c_radius_raw [M,1], dxyz [G,M,3], dquat [G,M,4], idx, dist)
+    -> means3D [G,N,3], rotations [G,N,4] (normalised).  renderer/latent_gs_renderer.py:1191-1219."""
+
+    @staticmethod
+    def forward(ctx, xyz, rot, c_xyz, c_radius_raw, dxyz, dquat, idx, dist):
+        c = lambda t: t.contiguous().float()
+        xyz, rot, c_xyz, c_radius_raw, dxyz, dquat, dist = map(c, (xyz, rot, c_xyz, c_radius_raw, dxyz, dquat, dist))
+        idx = idx.contiguous()
+        assert idx.dtype == torch.int64
+        G, M = dxyz.shape[0], c_xyz.shape[0]
+        N, K = idx.shape
+        means3D = torch.empty(G, N, 3, dtype=torch.float32, device=xyz.device)
+        rotations = torch.empty(G, N, 4, dtype=torch.float32, device=xyz.device)
+        _lib.call("dimo_lbs_fwd", G, N, M, K, _lib.ptr(xyz), _lib.ptr(rot), _lib.ptr(idx), _lib.ptr(dist),
+                  _lib.ptr(c_xyz), _lib.ptr(c_radius_raw), _lib.ptr(dxyz), _lib.ptr(dquat), _lib.ptr(means3D),
+                  _lib.ptr(rotations), _lib.stream())
+        ctx.save_for_backward(xyz, rot, c_xyz, c_radius_raw, dxyz, dquat, idx, dist)
+        return means3D, rotations
+
+    @staticmethod
+    def backward(ctx, g_means3D, g_rot):
+        xyz, rot, c_xyz, c_radius_raw, dxyz, dquat, idx, dist = ctx.saved_tensors
+        G, M = dxyz.shape[0], c_xyz.shape[0]
+        N, K = idx.shape
+        z = lambda t: torch.zeros_like(t)
+        d_xyz, d_rot, d_cxyz, d_crad, d_dxyz, d_dquat = z(xyz), z(rot), z(c_xyz), z(c_radius_raw), z(dxyz), z(dquat)
+        g_means3D = g_means3D.contiguous().float() if g_means3D is not None else torch.zeros(G, N, 3, device=xyz.device)
+        g_rot = g_rot.contiguous().float() if g_rot is not None else torch.zeros(G, N, 4, device=xyz.device)
+        _lib.call("dimo_lbs_bwd", G, N, M, K, _lib.ptr(xyz), _lib.ptr(rot), _lib.ptr(idx), _lib.ptr(dist),
+                  _lib.ptr(c_xyz), _lib.ptr(c_radius_raw), _lib.ptr(dxyz), _lib.ptr(dquat), _lib.ptr(g_means3D),
+                  _lib.ptr(g_rot), _lib.ptr(d_xyz), _lib.ptr(d_rot), _lib.ptr(d_cxyz), _lib.ptr(d_crad),
+                  _lib.ptr(d_dxyz), _lib.ptr(d_dquat), _lib.stream())
+        return d_xyz, d_rot, d_cxyz, d_crad, d_dxyz, d_dquat, None, None
+
+
+def lbs_deform(xyz, rot, c_xyz, c_radius_raw, dxyz, dquat, neighbor_indices, neighbor_dists):
+    """Batched stage-s2 skinning; dxyz/dquat may be [M,*] (one frame) or [G,M,*]."""
+    single = dxyz.dim() == 2
+    if single:
+        dxyz, dquat = dxyz[None], dquat[None]
+    m, r = _LBSFn.apply(xyz, rot, c_xyz, c_radius_raw, dxyz, dquat, neighbor_indices, neighbor_dists)
+    return (m[0], r[0]) if single else (m, r)

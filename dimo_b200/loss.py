@@ -1,0 +1,67 @@
+"""Fused image losses (host side): SSIM + L1 + MSE in one forward and one backward kernel.
+ssim() == src/loss.py:144 ssim(img1, img2) == fused_ssim.fused_ssim(img1, img2) (main_test_dimo.py:979);
+l1 == src/loss.py:178; mse == F.mse_loss (main_train_dimo.py:333)."""
+import torch
+
+from . import _lib
+
+
+class _ImageLoss(torch.autograd.Function):
+    """returns the three means [ssim, l1, mse] as a [3] tensor; differentiable w.r.t. img1 only
+    (the reference's second argument is ground truth)."""
+
+    @staticmethod
+    def forward(ctx, img1, img2, need_ssim_grad, clamp01=False):
+        img1 = img1.contiguous().float()
+        img2 = img2.contiguous().float()
+        if img1.dim() == 3:
+            img1 = img1[None]; img2 = img2[None]
+        B, C, H, W = img1.shape
+        dev = img1.device
+        sums = torch.empty(3, dtype=torch.float32, device=dev)
+        keep = bool(need_ssim_grad) and img1.requires_grad
+        dm = torch.empty(3, B, C, H, W, dtype=torch.float32, device=dev) if keep else None
+        _lib.call("dimo_ssim_fwd", B, C, H, W, int(clamp01), _lib.ptr(img1), _lib.ptr(img2), _lib.ptr(sums), _lib.ptr(dm),
+                  _lib.stream())
+        ctx.save_for_backward(img1, img2, dm)
+        ctx.dims = (B, C, H, W)
+        ctx.clamp01 = int(clamp01)
+        return sums / float(B * C * H * W)
+
+    @staticmethod
+    def backward(ctx, g):
+        img1, img2, dm = ctx.saved_tensors
+        B, C, H, W = ctx.dims
+        # weights are host scalars in the C ABI; one small D2H read of the three upstream grads
+        gw = (g.float() / float(B * C * H * W)).tolist()
+        if dm is None and gw[0] != 0.0:
+            raise RuntimeError("ssim gradient requested but the derivative maps were not kept")
+        out = torch.empty_like(img1)
+        _lib.call("dimo_ssim_bwd", B, C, H, W, ctx.clamp01, _lib.ptr(img1), _lib.ptr(img2), _lib.ptr(dm), gw[0], gw[1], gw[2],
+                  _lib.ptr(out), _lib.stream())
+        return out, None, None, None
+
+
+def image_losses(img1, img2, need_ssim_grad=True, clamp01=False):
+    """-> tensor [3] = (mean ssim map, mean |a-b|, mean (a-b)^2); clamp01 clamps img1 to [0,1] on load"""
+    return _ImageLoss.apply(img1, img2, need_ssim_grad, clamp01)
+
+
+def ssim(img1, img2, window_size=11, size_average=True):
+    if window_size != 11 or not size_average:
+        raise NotImplementedError("dimo_b200 ssim: window 11 / size_average=True only (what the reference calls)")
+    return image_losses(img1, img2)[0]
+
+
+def fused_ssim(img1, img2, padding="same", train=True):
+    if padding != "same":
+        raise NotImplementedError("dimo_b200 fused_ssim: 'same' (zero) padding only")
+    return image_losses(img1, img2, need_ssim_grad=train)[0]
+
+
+def l1_loss(a, b):
+    return image_losses(a, b, need_ssim_grad=False)[1]
+
+
+def mse_loss(a, b):
+    return image_losses(a, b, need_ssim_grad=False)[2]

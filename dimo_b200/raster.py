@@ -80,6 +80,7 @@ def _forward_impl(cams, means3D, scales, rotations, opacities, shs, colors_preco
               _lib.ptr(scan_temp), scan_bytes, ctypes.addressof(R_host), s)
     R = int(R_host.value)
     st.R = R
+    _lib.PROFILE.extra["R"] = R
     gx, gy = (W + TILE - 1) // TILE, (H + TILE - 1) // TILE
     Ra = max(R, 1)
     keys_u = torch.empty(Ra, dtype=torch.int64, device=dev)

@@ -1,0 +1,229 @@
+"""Host-side mirror of the reference renderer classes for the hot path
+(renderer/latent_gs_renderer.py: GaussianModel :248-415 [parameters + activations only], Renderer.render
+:1096-1293) on top of the libdimo_b200 kernels.
+
+`Renderer.render(...)` keeps the reference signature and result dict (one frame per call);
+`Renderer.render_batch(...)` is the B200 fast path: all S frames of an optimisation step in ONE launch
+set -- TimeNet once per unique (motion, t) pair (its output is view-independent), LBS once per pair,
+rasterisation batched over all frames.
+
+Out of scope here: densify/prune, PLY/.pth I/O, optimizer surgery.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import deform as _deform
+from . import knn as _knn
+from . import raster as _raster
+from .camera import MiniCam  # noqa: F401  (re-export: the reference imports MiniCam from the renderer module)
+
+C0 = 0.28209479177387814
+
+
+def inverse_sigmoid(x):
+    return torch.log(x / (1 - x))
+
+
+class GaussianModel:
+    """Parameters + activations of the reference GaussianModel, same attribute names."""
+
+    def __init__(self, sh_degree: int, num_latent_code: int = 1, latent_code_dim: int = 32, device="cuda"):
+        self.active_sh_degree = 0
+        self.max_sh_degree = sh_degree
+        self.num_latent_code = num_latent_code
+        self.latent_code_dim = latent_code_dim
+        self.device = device
+        e = torch.empty(0, device=device)
+        self._xyz = self._features_dc = self._features_rest = self._scaling = self._rotation = self._opacity = e
+        self._c_xyz = self._c_radius = self._r = e
+        self.max_radii2D = e
+        self.optimizer = None
+        self._latent_codes = nn.Parameter(torch.randn(num_latent_code, latent_code_dim, device=device))
+        self._timenet = _deform.TimeNet(latent_code_dim=latent_code_dim).to(device)
+        self.neighbor_dists = None
+        self.neighbor_indices = None
+
+    # -- construction from tensors (synthetic scenes, checkpoints) --------------------------------
+    def load_state(self, state: dict):
+        for k in ("_xyz", "_features_dc", "_features_rest", "_scaling", "_rotation", "_opacity", "_c_xyz", "_c_radius"):
+            setattr(self, k, nn.Parameter(state[k].to(self.device).float().contiguous()))
+        if "_latent_codes" in state:
+            self._latent_codes = nn.Parameter(state["_latent_codes"].to(self.device).float().contiguous())
+            self.num_latent_code = self._latent_codes.shape[0]
+        self._r = torch.empty(0, device=self.device)
+        self.max_radii2D = torch.zeros(self._xyz.shape[0], device=self.device)
+
+    # -- activations: renderer/latent_gs_renderer.py:257-265, 340-407 ---------------------------
+    @property
+    def get_scaling(self):
+        if len(self._r) == 0:
+            return torch.exp(self._scaling)
+        elif self._r.shape[0] != self._xyz.shape[0]:
+            return torch.exp(self._r.repeat(self._xyz.shape[0], 3))
+        elif self._r.shape[1] == 1:
+            return torch.exp(self._r.repeat(1, 3))
+        elif self._r.shape == self._xyz.shape:
+            return torch.exp(self._r)
+        raise ValueError("Shape of _r is not supported.")
+
+    @property
+    def get_rotation(self):
+        return F.normalize(self._rotation)
+
+    @property
+    def get_xyz(self):
+        return self._xyz
+
+    @property
+    def get_c_xyz(self):
+        return self._c_xyz
+
+    @property
+    def get_features(self):
+        return torch.cat((self._features_dc, self._features_rest), dim=1)
+
+    @property
+    def get_opacity(self):
+        return torch.sigmoid(self._opacity)
+
+    @property
+    def get_latent_codes(self):
+        return self._latent_codes
+
+    def get_c_radius(self, stage="s2"):
+        if stage < "s2":
+            return torch.exp(self._r.repeat(self._xyz.shape[0], 1))
+        return torch.exp(self._c_radius)
+
+    def parameters(self):
+        return [self._xyz, self._features_dc, self._features_rest, self._opacity, self._scaling, self._rotation,
+                self._c_xyz, self._c_radius, self._latent_codes] + list(self._timenet.parameters())
+
+    def find_knn(self, k=4):
+        """main_train_dimo.py:502-509 (GUI.find_knn): once per optimisation step."""
+        self.neighbor_dists, self.neighbor_indices = _knn.knn(self._c_xyz, self._xyz, k)
+
+
+class Renderer:
+    def __init__(self, sh_degree=3, white_background=True, radius=1, delta_t=1 / 32, num_latent_code=1,
+                 latent_code_dim=32, add_normal=False, device="cuda"):
+        self.sh_degree = sh_degree
+        self.white_background = white_background
+        self.radius = radius
+        self.gaussians = GaussianModel(sh_degree, num_latent_code, latent_code_dim, device=device)
+        self.bg_color = torch.tensor([1, 1, 1] if white_background else [0, 0, 0], dtype=torch.float32, device=device)
+        self.delta_t = delta_t
+        self.add_normal = add_normal
+
+    # ------------------------------------------------------------------------------------------
+    def render_batch(self, cameras, times, latent_indices, stage="s2", scaling_modifier=1.0, bg_color=None,
+                     override_color=None, xyz_detach=False, clamp=True):
+        """cameras: list of S MiniCam (same W,H); times: list of S floats; latent_indices: list of S ints.
+        Returns a dict of batched tensors: image [S,3,H,W] (clamped), depth, normal, alpha, radii [S,N],
+        visibility_filter, pts_t [S,N,3], cpts_t [U,M,3] + `pair_of_frame` (frame -> unique (motion,t) index)."""
+        g = self.gaussians
+        dev = g._xyz.device
+        S = len(cameras)
+        W, H = int(cameras[0].image_width), int(cameras[0].image_height)
+        # unique (motion, t) pairs: the deformation is view-independent
+        pairs, pair_of_frame = {}, []
+        for t, li in zip(times, latent_indices):
+            key = (int(li), float(t))
+            pair_of_frame.append(pairs.setdefault(key, len(pairs)))
+        keys = list(pairs.keys())
+        U = len(keys)
+        t_host = torch.tensor([k[1] for k in keys], dtype=torch.float32)
+        li_host = torch.tensor([k[0] for k in keys], dtype=torch.int64)
+        pf_host = torch.tensor(pair_of_frame, dtype=torch.int64)
+        t_dev = t_host.to(dev, non_blocking=True)
+        li_dev = li_host.to(dev, non_blocking=True)
+        pf_dev = pf_host.to(dev, non_blocking=True)
+        latents = g._latent_codes[li_dev]                                   # [U,L]
+
+        if stage >= "s2":
+            dxyz, dquat = g._timenet.forward_batched(g._c_xyz, t_dev, latents)   # [U,M,3],[U,M,4]
+            cpts_t = g._c_xyz[None] + dxyz
+            means3D_u, rot_u = _deform.lbs_deform(g._xyz, g._rotation, g._c_xyz, g._c_radius, dxyz, dquat,
+                                                  g.neighbor_indices, g.neighbor_dists)
+        elif stage == "s1":
+            dxyz, dquat = g._timenet.forward_batched(g._xyz, t_dev, latents)
+            cpts_t = g._xyz[None] + dxyz
+            means3D_u = cpts_t
+            rot_u = F.normalize(g._rotation)[None].expand(U, -1, -1)
+        else:
+            raise ValueError("Nonexistent stage!!!")
+        if xyz_detach:
+            means3D_u = means3D_u.detach()
+        means3D = means3D_u[pf_dev] if U != S or pair_of_frame != list(range(S)) else means3D_u
+        rotations = rot_u[pf_dev] if U != S or pair_of_frame != list(range(S)) else rot_u
+
+        bg = self.bg_color if bg_color is None else bg_color
+        V = torch.stack([c.world_view_transform for c in cameras])
+        P = torch.stack([c.full_proj_transform for c in cameras])
+        C = torch.stack([c.camera_center for c in cameras]).float()
+        tan = torch.tensor([[math.tan(c.FoVx * 0.5), math.tan(c.FoVy * 0.5)] for c in cameras], dtype=torch.float32)
+        tan = tan.to(dev, non_blocking=True)
+        cams = _raster.pack_cameras(V, P, C, tan[:, 0], tan[:, 1], bg)
+
+        shs = colors = None
+        if override_color is None:
+            shs = g.get_features
+        else:
+            colors = override_color
+        color, depth, normal, alpha, radii = _raster.rasterize_batch(
+            cams, means3D, g.get_scaling, rotations, g.get_opacity, W, H, shs=shs, colors_precomp=colors,
+            sh_degree=g.active_sh_degree, scale_modifier=scaling_modifier)
+        return {"image": color.clamp(0, 1) if clamp else None, "image_raw": color, "depth": depth, "normal": normal,
+                "alpha": alpha, "radii": radii, "visibility_filter": radii > 0, "pts_t": means3D, "cpts_t": cpts_t, "pair_of_frame": pair_of_frame}
+
+    # ------------------------------------------------------------------------------------------
+    def render(self, viewpoint_camera, scaling_modifier=1.0, bg_color=None, override_color=None,
+               compute_cov3D_python=False, convert_SHs_python=False, time=0.0, stage="s1", rot_as_res=True,
+               xyz_detach=False, local_frame=True, direct_deform=False, vertices_deform=None, latent_index=0):
+        """Reference signature and result dict (renderer/latent_gs_renderer.py:1096-1293), one frame."""
+        if compute_cov3D_python or convert_SHs_python or not local_frame:
+            raise NotImplementedError("dimo_b200 render(): python-side cov3D / SH conversion and local_frame=False "
+                                      "are off the reference's default path")
+        g = self.gaussians
+        dev = g._xyz.device
+        screenspace_points = torch.zeros_like(g._xyz, requires_grad=True) + 0
+        try:
+            screenspace_points.retain_grad()
+        except Exception:
+            pass
+        t_dev = torch.tensor([float(time)], dtype=torch.float32).to(dev, non_blocking=True)
+        latents = g._latent_codes[latent_index][None]
+        if stage >= "s2":
+            dxyz, dquat = g._timenet.forward_batched(g._c_xyz, t_dev, latents)
+            cpts_t = g._c_xyz + dxyz[0]
+            means3D, rotations = _deform.lbs_deform(g._xyz, g._rotation, g._c_xyz, g._c_radius, dxyz[0], dquat[0],
+                                                    g.neighbor_indices, g.neighbor_dists)
+        elif stage == "s1":
+            dxyz, dquat = g._timenet.forward_batched(g._xyz, t_dev, latents)
+            cpts_t = g._xyz + dxyz[0]
+            means3D = cpts_t
+            rotations = F.normalize(g._rotation)
+        else:
+            raise ValueError("Nonexistent stage!!!")
+        if xyz_detach:
+            means3D = means3D.detach()
+        bg = self.bg_color if bg_color is None else bg_color
+        cams = _raster.pack_cameras(viewpoint_camera.world_view_transform, viewpoint_camera.full_proj_transform,
+                                    viewpoint_camera.camera_center, math.tan(viewpoint_camera.FoVx * 0.5),
+                                    math.tan(viewpoint_camera.FoVy * 0.5), bg)
+        shs = colors = None
+        if override_color is None:
+            shs = g.get_features
+        else:
+            colors = override_color
+        color, depth, normal, alpha, radii = _raster.rasterize_batch(
+            cams, means3D, g.get_scaling, rotations, g.get_opacity, int(viewpoint_camera.image_width),
+            int(viewpoint_camera.image_height), shs=shs, colors_precomp=colors, sh_degree=g.active_sh_degree,
+            scale_modifier=scaling_modifier, means2D=screenspace_points)
+        radii = radii[0]
+        return {"image": color[0].clamp(0, 1), "depth": depth[0], "normal": normal[0], "alpha": alpha[0],
+                "viewspace_points": screenspace_points, "visibility_filter": radii > 0, "radii": radii,
+                "pts_t": means3D, "cpts_t": cpts_t}

@@ -1,0 +1,111 @@
+"""One optimisation step of the DIMO inner loop on the B200 fast path.
+
+Workload definition = the hot loop of GUI.train_step (main_train_dimo.py:253-417) restricted to the
+north_star terms: find_knn -> S x [deform -> rasterise] -> {MSE per frame, SSIM per motion, mask MSE on
+alpha} -> backward -> (one gradient all-reduce) -> Adam.  All S frames of the step go through ONE
+launch set (Renderer.render_batch).  LPIPS and the ARAP/chamfer/smoothness regularisers are
+SURVEY.md 8f "next" rows and are not part of this step.
+"""
+import torch
+
+from . import _lib
+from .renderer import Renderer
+
+
+class StepLossWeights:
+    # configs/train_config.yaml:34-38
+    lambda_mse = 5000.0
+    lambda_ssim = 500.0
+    lambda_mask = 500.0
+
+
+class _StepLoss(torch.autograd.Function):
+    """loss = l_mse * sum_f MSE(clamp(img_f), gt_f) + l_ssim * sum_m (1 - SSIM(clamp(img_m), gt_m))
+            + l_mask * sum_m MSE(alpha_m, mask_m)
+    over S frames grouped in n_motions equal groups (main_train_dimo.py:328-351; the reference's 0.5 factor on
+    non-reference views is taken as 1).  One fused forward kernel per tensor pair, one fused backward; no host sync."""
+
+    @staticmethod
+    def forward(ctx, image, alpha, gt, mask, n_motions, l_mse, l_ssim, l_mask):
+        S, _, H, W = image.shape
+        dev = image.device
+        image = image.contiguous(); alpha = alpha.contiguous(); gt = gt.contiguous(); mask = mask.contiguous()
+        sums_i = torch.empty(3, dtype=torch.float32, device=dev)
+        sums_a = torch.empty(3, dtype=torch.float32, device=dev)
+        dm = torch.empty(3, S, 3, H, W, dtype=torch.float32, device=dev)
+        s = _lib.stream()
+        _lib.call("dimo_ssim_fwd", S, 3, H, W, 1, _lib.ptr(image), _lib.ptr(gt), _lib.ptr(sums_i), _lib.ptr(dm), s)
+        _lib.call("dimo_ssim_fwd", S, 1, H, W, 0, _lib.ptr(alpha), _lib.ptr(mask), _lib.ptr(sums_a), None, s)
+        n_img = float(3 * H * W)
+        per_motion = S // n_motions
+        # sum_f MSE_f = sums_i[2] / n_img ; sum_m (1 - ssim_m) = n_motions - sums_i[0] / (per_motion * n_img)
+        loss = (l_mse / n_img) * sums_i[2] + l_ssim * (n_motions - sums_i[0] / (per_motion * n_img)) \
+            + (l_mask / (per_motion * H * W)) * sums_a[2]
+        ctx.save_for_backward(image, alpha, gt, mask, dm)
+        ctx.w = (-l_ssim / (per_motion * n_img), l_mse / n_img, l_mask / (per_motion * H * W))
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        image, alpha, gt, mask, dm = ctx.saved_tensors
+        S, _, H, W = image.shape
+        w_ssim, w_mse, w_mask = ctx.w
+        s = _lib.stream()
+        d_img = torch.empty_like(image)
+        d_alpha = torch.empty_like(alpha)
+        _lib.call("dimo_ssim_bwd", S, 3, H, W, 1, _lib.ptr(image), _lib.ptr(gt), _lib.ptr(dm), w_ssim, 0.0, w_mse,
+                  _lib.ptr(d_img), s)
+        _lib.call("dimo_ssim_bwd", S, 1, H, W, 0, _lib.ptr(alpha), _lib.ptr(mask), None, 0.0, 0.0, w_mask,
+                  _lib.ptr(d_alpha), s)
+        return d_img * g, d_alpha * g, None, None, None, None, None, None
+
+
+def step_loss(image, alpha, gt, mask, n_motions, weights=StepLossWeights):
+    return _StepLoss.apply(image, alpha, gt, mask, n_motions, weights.lambda_mse, weights.lambda_ssim,
+                           weights.lambda_mask)
+
+
+class TrainStep:
+    """Holds the model + optimizer and runs steps.  `world` > 1: one flat fp32 all-reduce (sum) of every
+    gradient per step over NCCL (the only exchange on the path; frames are sharded by motion)."""
+
+    def __init__(self, renderer: Renderer, lr=1e-4, world=1, stage="s2"):
+        self.r = renderer
+        self.g = renderer.gaussians
+        self.stage = stage
+        self.world = world
+        self.params = [p for p in self.g.parameters() if p.numel() > 0]
+        self.opt = torch.optim.Adam(self.params, lr=lr, eps=1e-15, fused=True)
+        self._flat = None
+
+    def allreduce_grads(self):
+        import torch.distributed as dist
+        grads = [p.grad for p in self.params if p.grad is not None]
+        n = sum(g.numel() for g in grads)
+        if self._flat is None or self._flat.numel() != n:
+            self._flat = torch.empty(n, dtype=torch.float32, device=grads[0].device)
+        o = 0
+        views = []
+        for g in grads:
+            v = self._flat[o:o + g.numel()].view_as(g)
+            views.append(v)
+            o += g.numel()
+        torch._foreach_copy_(views, grads)
+        dist.all_reduce(self._flat, op=dist.ReduceOp.SUM)
+        torch._foreach_copy_(grads, views)
+
+    def run(self, cameras, times, latent_indices, gt, mask, n_motions, optimize=True):
+        """cameras/times/latent_indices: length-S lists ordered motion-major; gt [S,3,H,W], mask [S,1,H,W] on device.
+        Returns the (device) loss tensor."""
+        if self.stage >= "s2":
+            self.g.find_knn(4)
+        # the loss kernel clamps the render to [0,1] on load (and masks the gradient), so skip the separate clamp pass
+        out = self.r.render_batch(cameras, times, latent_indices, stage=self.stage, clamp=False)
+        loss = step_loss(out["image_raw"], out["alpha"], gt, mask, n_motions)
+        loss.backward()
+        if self.world > 1:
+            self.allreduce_grads()
+        if optimize:
+            self.opt.step()
+        self.opt.zero_grad(set_to_none=False)
+        return loss

@@ -131,14 +131,13 @@ int dimo_dist3nn(int N, const float* points, float* out, void* stream);
  *   Y[R,No] = act( X[R,K] * W[No,K]^T + bias[No] ),  row strides ldx/ldy in floats, relu 0/1. */
 int dimo_linear_fwd(int R, int K, int No, const float* X, int64_t ldx, const float* Wt,
                     const float* bias, float* Y, int64_t ldy, int relu, void* stream);
-/* dX[R,K] (=|+=) (dY*[Y>0]) * W ; accumulate 0/1 ; Y==NULL -> no relu mask. dYm [R,No] receives the masked dY
- * (may alias dY). */
+/* dX[R,K] (=|+=) (dY * [Y>0]) * W ; accumulate 0/1 ; Y == NULL -> no ReLU mask (head layers). */
 int dimo_linear_bwd_data(int R, int K, int No, const float* dY, int64_t lddy, const float* Y, int64_t ldy,
-                         const float* Wt, float* dYm, int64_t lddym, float* dX, int64_t lddx,
-                         int accumulate, void* stream);
-/* dW[No,K] += dYm^T * X ; db[No] += sum_rows dYm   (dYm already relu-masked) */
-int dimo_linear_bwd_weight(int R, int K, int No, const float* dYm, int64_t lddym, const float* X, int64_t ldx,
-                           float* dW, float* db, void* stream);
+                         const float* Wt, float* dX, int64_t lddx, int accumulate, void* stream);
+/* dW[No,K] += (dY * [Y>0])^T * X ; db[No] += column sums of (dY * [Y>0]).  dW/db must be zeroed (or hold
+ * prior gradients) by the caller. */
+int dimo_linear_bwd_weight(int R, int K, int No, const float* dY, int64_t lddy, const float* Y, int64_t ldy,
+                           const float* X, int64_t ldx, float* dW, float* db, void* stream);
 
 /* TimeNet input embedding h0[R,104] = [posenc(x,10) | posenc(t,6) | latent]  (pos_enc.py:35-36,
  * latent_gs_renderer.py:223-225).  Row r belongs to group g = r / rows_per_group and reads
@@ -168,12 +167,14 @@ int dimo_lbs_bwd(int B, int N, int M, int K, const float* xyz, const float* rot,
  * l1_loss + F.mse_loss, main_train_dimo.py:333-344).
  *   img1,img2 [B,C,H,W]; sums[3] (f32, zeroed by callee) = { sum ssim_map, sum |a-b|, sum (a-b)^2 }.
  *   dm [3,B,C,H,W]: the three partial-derivative maps kept for backward (may be NULL for eval).
+ *   clamp01: img1 is clamped to [0,1] on load (the reference clamps the render before the losses,
+ *   renderer/latent_gs_renderer.py:1279) and the backward zeroes the gradient outside [0,1].
  * ------------------------------------------------------------------------------------------- */
-int dimo_ssim_fwd(int B, int C, int H, int W, const float* img1, const float* img2,
+int dimo_ssim_fwd(int B, int C, int H, int W, int clamp01, const float* img1, const float* img2,
                   float* sums, float* dm, void* stream);
 /* dL_dimg1 [B,C,H,W] = w_ssim * d(sum ssim_map)/dimg1 + w_l1 * d(sum|a-b|)/dimg1 + w_mse * d(sum (a-b)^2)/dimg1.
- * Weights are DEVICE scalars-by-value (host floats): caller folds 1/numel and upstream grads in. */
-int dimo_ssim_bwd(int B, int C, int H, int W, const float* img1, const float* img2, const float* dm,
+ * Weights are host floats: the caller folds 1/numel and the loss weights in. */
+int dimo_ssim_bwd(int B, int C, int H, int W, int clamp01, const float* img1, const float* img2, const float* dm,
                   float w_ssim, float w_l1, float w_mse, float* dL_dimg1, void* stream);
 
 #ifdef __cplusplus

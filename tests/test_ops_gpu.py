@@ -1,0 +1,152 @@
+"""-m gpu: KNN / dist3nn / TimeNet / LBS / image-loss kernels vs the CPU oracle (through the C ABI)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, ref):
+    import gpu_parity as gp
+    return gp.rel_err(a, ref)
+
+
+@pytest.mark.parametrize("M,N,k", [(512, 5000, 4), (37, 300, 4), (2500, 1000, 8), (4, 10, 1)])
+def test_knn_bit_exact(cuda, M, N, k):
+    from dimo_b200 import knn as dknn
+    from oracle import knn as oknn
+    g = torch.Generator().manual_seed(M + N)
+    ref = torch.rand(M, 3, generator=g) - 0.5
+    q = torch.rand(N, 3, generator=g) - 0.5
+    q[:3] = ref[:3]                       # exact hits (distance 0)
+    if M > 8:
+        ref[5] = ref[6]                   # duplicate reference point -> tie, lower index first
+    od, oi = oknn.knn(ref, q, k)
+    d, i = dknn.knn(ref.cuda(), q.cuda(), k)
+    assert i.dtype == torch.int64 and tuple(i.shape) == (N, k)
+    assert torch.equal(i.cpu(), oi), "neighbour indices differ"
+    assert torch.equal(d.cpu(), od), "distances differ (should be bit-exact: same fp32 op sequence)"
+
+
+def test_knn_shim_shapes(cuda):
+    import dimo_b200; dimo_b200.install_shims()
+    from knn_cuda import KNN
+    ref = torch.rand(1, 64, 3, device="cuda"); q = torch.rand(1, 500, 3, device="cuda")
+    d, i = KNN(k=4, transpose_mode=True)(ref, q)
+    assert tuple(d.shape) == (1, 500, 4) and tuple(i.shape) == (1, 500, 4) and i.dtype == torch.int64
+
+
+@pytest.mark.parametrize("N", [5, 1000, 5000])
+def test_dist3nn(cuda, N):
+    import dimo_b200; dimo_b200.install_shims()
+    from simple_knn._C import distCUDA2
+    from oracle import knn as oknn
+    pts = torch.rand(N, 3, generator=torch.Generator().manual_seed(N))
+    assert torch.equal(distCUDA2(pts.cuda()).cpu(), oknn.dist3nn(pts))
+
+
+def _timenet_pair(M, G, L=32, seed=0, final_scale=0.01):
+    from dimo_b200.deform import TimeNet
+    from oracle import deform as od
+    params = od.timenet_init(L, seed=seed, final_scale=final_scale)
+    net = TimeNet(latent_code_dim=L).cuda()
+    with torch.no_grad():
+        for p, (W, b) in zip(zip(net.flat_params()[0::2], net.flat_params()[1::2]), params):
+            p[0].copy_(W); p[1].copy_(b)
+    g = torch.Generator().manual_seed(seed + 1)
+    pts = (torch.rand(M, 3, generator=g) - 0.5)
+    times = torch.rand(G, generator=g)
+    lat = torch.randn(G, L, generator=g)
+    return net, params, pts, times, lat
+
+
+@pytest.mark.parametrize("M,G", [(512, 3), (100, 1), (33, 5)])
+def test_timenet_fwd_bwd(cuda, M, G):
+    from oracle import deform as od
+    net, params, pts, times, lat = _timenet_pair(M, G)
+    # oracle
+    op = [(W.clone().requires_grad_(True), b.clone().requires_grad_(True)) for W, b in params]
+    opts = pts.clone().requires_grad_(True); olat = lat.clone().requires_grad_(True)
+    rows_pts = opts[None].expand(G, M, 3).reshape(-1, 3)
+    rows_t = times[:, None, None].expand(G, M, 1).reshape(-1, 1)
+    rows_lat = olat[:, None, :].expand(G, M, -1).reshape(G * M, -1)
+    odx, odq = od.timenet_forward(op, rows_pts, rows_t, rows_lat)
+    g = torch.Generator().manual_seed(7)
+    wx = torch.randn(G * M, 3, generator=g); wq = torch.randn(G * M, 4, generator=g)
+    ((odx * wx).sum() + (odq * wq).sum()).backward()
+    # cuda
+    cpts = pts.cuda().requires_grad_(True); clat = lat.cuda().requires_grad_(True)
+    dx, dq = net.forward_batched(cpts, times.cuda(), clat)
+    ((dx.reshape(-1, 3) * wx.cuda()).sum() + (dq.reshape(-1, 4) * wq.cuda()).sum()).backward()
+    assert _rel(dx.reshape(-1, 3), odx) < 1e-4 and _rel(dq.reshape(-1, 4), odq) < 1e-4
+    assert _rel(cpts.grad, opts.grad) < 1e-4, f"dpts {_rel(cpts.grad, opts.grad):.2e}"
+    assert _rel(clat.grad, olat.grad) < 1e-4
+    for li, (p_w, p_b) in enumerate(zip(net.flat_params()[0::2], net.flat_params()[1::2])):
+        assert _rel(p_w.grad, op[li][0].grad) < 1e-4, f"dW[{li}] {_rel(p_w.grad, op[li][0].grad):.2e}"
+        assert _rel(p_b.grad, op[li][1].grad) < 1e-4, f"db[{li}] {_rel(p_b.grad, op[li][1].grad):.2e}"
+
+
+def test_timenet_reference_call_forms(cuda):
+    """single-frame call (pts, float t, latent[L]) and identity init (zero heads)"""
+    from dimo_b200.deform import TimeNet
+    net = TimeNet().cuda()
+    pts = torch.rand(50, 3, device="cuda")
+    dx, dq = net(pts, 0.3, torch.randn(32, device="cuda"))
+    assert tuple(dx.shape) == (50, 3) and tuple(dq.shape) == (50, 4)
+    assert float(dx.abs().max()) == 0.0
+    assert torch.equal(dq.cpu(), torch.tensor([1., 0, 0, 0]).repeat(50, 1))
+
+
+@pytest.mark.parametrize("N,M,G", [(3000, 512, 2), (200, 16, 3)])
+def test_lbs_fwd_bwd(cuda, N, M, G):
+    from dimo_b200 import deform as dd, knn as dknn
+    from oracle import deform as od, knn as oknn
+    g = torch.Generator().manual_seed(N)
+    xyz = torch.rand(N, 3, generator=g) - 0.5
+    rot = torch.randn(N, 4, generator=g)
+    c_xyz = xyz[torch.randperm(N, generator=g)[:M]].clone()
+    c_rad = torch.log(torch.full((M, 1), 0.08)) + 0.1 * torch.randn(M, 1, generator=g)
+    dxyz = 0.05 * torch.randn(G, M, 3, generator=g)
+    dquat = torch.tensor([1., 0, 0, 0]) + 0.2 * torch.randn(G, M, 4, generator=g)
+    dist, idx = oknn.knn(c_xyz, xyz, 4)
+    leaves = [t.clone().requires_grad_(True) for t in (xyz, rot, c_xyz, c_rad, dxyz, dquat)]
+    wm = torch.randn(G, N, 3, generator=g); wr = torch.randn(G, N, 4, generator=g)
+    loss = 0
+    om, orr = [], []
+    for b in range(G):
+        m, r = od.lbs_deform(leaves[0], leaves[1], leaves[2], torch.exp(leaves[3]), leaves[4][b], leaves[5][b], idx, dist)
+        om.append(m); orr.append(r)
+        loss = loss + (m * wm[b]).sum() + (r * wr[b]).sum()
+    loss.backward()
+    cl = [t.clone().cuda().requires_grad_(True) for t in (xyz, rot, c_xyz, c_rad, dxyz, dquat)]
+    cd, ci = dknn.knn(c_xyz.cuda(), xyz.cuda(), 4)
+    assert torch.equal(ci.cpu(), idx)
+    m, r = dd.lbs_deform(cl[0], cl[1], cl[2], cl[3], cl[4], cl[5], ci, cd)
+    ((m * wm.cuda()).sum() + (r * wr.cuda()).sum()).backward()
+    assert _rel(m, torch.stack(om)) < 1e-4 and _rel(r, torch.stack(orr)) < 1e-4
+    for name, a, b in zip(("xyz", "rot", "c_xyz", "c_radius", "dxyz", "dquat"), cl, leaves):
+        assert _rel(a.grad, b.grad) < 1e-4, f"d{name}: {_rel(a.grad, b.grad):.2e}"
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 3, 64, 64), (1, 3, 50, 70), (4, 1, 33, 17)])
+def test_image_losses(cuda, B, C, H, W):
+    from dimo_b200 import loss as dl
+    from oracle import loss as ol
+    g = torch.Generator().manual_seed(H * W)
+    a = torch.rand(B, C, H, W, generator=g); b = (a + 0.2 * torch.randn(B, C, H, W, generator=g)).clamp(0, 1)
+    oa = a.clone().requires_grad_(True)
+    o = 0.7 * (1 - ol.ssim(oa, b)) + 1.3 * ol.l1_loss(oa, b) + 2.1 * ol.mse_loss(oa, b)
+    o.backward()
+    ca = a.cuda().requires_grad_(True)
+    v = dl.image_losses(ca, b.cuda())
+    c = 0.7 * (1 - v[0]) + 1.3 * v[1] + 2.1 * v[2]
+    c.backward()
+    assert abs(float(v[0]) - float(ol.ssim(a, b))) < 1e-5
+    assert abs(float(c) - float(o)) < 1e-4 * abs(float(o))
+    assert _rel(ca.grad, oa.grad) < 1e-4, f"{_rel(ca.grad, oa.grad):.2e}"
+
+
+def test_fused_ssim_shim_identity(cuda):
+    import dimo_b200; dimo_b200.install_shims()
+    from fused_ssim import fused_ssim
+    a = torch.rand(1, 3, 40, 40, device="cuda")
+    assert abs(float(fused_ssim(a, a)) - 1.0) < 1e-6
