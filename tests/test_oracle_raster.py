@@ -1,0 +1,122 @@
+"""CPU: self-consistency and known-answer tests of the rasteriser oracle (parity unpinned upstream, so the
+oracle is pinned analytically instead: closed forms, ordering, tile geometry, fp64 gradcheck)."""
+import math
+
+import pytest
+import torch
+
+from oracle import camera as ocam, raster as orast, sh as osh, knn as oknn
+
+
+def _cam(W=64, H=64, view=0):
+    return ocam.orbit_cam(view, 8, W, H)
+
+
+def _raster(cam, xyz, scales, rot, op, rgb, W, H, bg=(0., 0., 0.), dtype=torch.float32, **kw):
+    return orast.rasterize(xyz.to(dtype), scales.to(dtype), rot.to(dtype), op.to(dtype), cam.world_view_transform,
+                           cam.full_proj_transform, cam.camera_center, cam.tanfovx, cam.tanfovy, W, H,
+                           torch.tensor(bg, dtype=dtype), colors_precomp=rgb.to(dtype), **kw)
+
+
+def test_single_isotropic_gaussian_closed_form():
+    W = H = 64
+    cam = _cam(W, H)
+    s = 0.05
+    xyz = torch.zeros(1, 3); scales = torch.full((1, 3), s); rot = torch.tensor([[1., 0, 0, 0]])
+    op = torch.tensor([[0.8]]); rgb = torch.tensor([[0.2, 0.5, 0.9]])
+    r = _raster(cam, xyz, scales, rot, op, rgb, W, H)
+    # camera at distance 2 on +z looking at the origin: depth 2, centre pixel (W-1)/2
+    fx = W / (2 * cam.tanfovx)
+    var = (fx * s / 2.0) ** 2 + orast.DILATION
+    assert abs(r["pre"]["cov2d"][0, 0].item() - var) < 1e-3 * var
+    assert abs(r["pre"]["xy"][0, 0].item() - (W - 1) / 2) < 1e-3
+    assert r["radii"][0].item() == math.ceil(3 * math.sqrt(var))
+    px, py = 31, 31
+    d2 = (px - (W - 1) / 2) ** 2 + (py - (H - 1) / 2) ** 2
+    alpha = 0.8 * math.exp(-0.5 * d2 / var)
+    assert abs(r["alpha"][0, py, px].item() - alpha) < 1e-5
+    assert torch.allclose(r["image"][:, py, px], alpha * rgb[0], atol=1e-5)
+    assert abs(r["depth"][0, py, px].item() - alpha * 2.0) < 1e-4
+    assert r["n_contrib"][py, px].item() == 1
+
+
+def test_front_to_back_order_and_background():
+    W = H = 32
+    cam = _cam(W, H)
+    xyz = torch.tensor([[0., 0, 0.3], [0., 0, -0.3]])      # first is nearer to the camera (z=+2)
+    scales = torch.full((2, 3), 0.2); rot = torch.tensor([[1., 0, 0, 0]] * 2)
+    op = torch.tensor([[0.6], [0.7]]); rgb = torch.tensor([[1., 0, 0], [0, 1., 0]])
+    bg = (0.1, 0.2, 0.3)
+    r = _raster(cam, xyz, scales, rot, op, rgb, W, H, bg=bg)
+    assert r["ids"][r["ranges"][0, 0]:r["ranges"][0, 1]].tolist()[0] == 0       # nearer first
+    c = 15
+    pre = r["pre"]
+    def a(i):
+        dx = pre["xy"][i, 0] - c; dy = pre["xy"][i, 1] - c
+        p = -0.5 * (pre["conic"][i, 0] * dx * dx + pre["conic"][i, 2] * dy * dy) - pre["conic"][i, 1] * dx * dy
+        return min(0.99, (pre["opacity"][i] * torch.exp(p)).item())
+    a0, a1 = a(0), a(1)
+    T = (1 - a0) * (1 - a1)
+    want = torch.tensor([a0 * 1.0 + T * bg[0], (1 - a0) * a1 + T * bg[1], T * bg[2]])
+    assert torch.allclose(r["image"][:, c, c], want, atol=1e-5)
+    assert abs(r["alpha"][0, c, c].item() - (1 - T)) < 1e-6
+
+
+def test_tile_rect_and_keys():
+    W, H = 64, 48
+    cam = _cam(W, H)
+    xyz = torch.tensor([[0.0, 0.0, 0.0]]); scales = torch.full((1, 3), 0.02)
+    r = _raster(cam, xyz, scales, torch.tensor([[1., 0, 0, 0]]), torch.tensor([[0.5]]), torch.ones(1, 3), W, H)
+    x, y = r["pre"]["xy"][0].tolist(); rad = r["radii"][0].item()
+    gx, gy = 4, 3
+    x0 = min(gx, max(0, int((x - rad) / 16))); x1 = min(gx, max(0, int((x + rad + 15) / 16)))
+    y0 = min(gy, max(0, int((y - rad) / 16))); y1 = min(gy, max(0, int((y + rad + 15) / 16)))
+    assert r["pre"]["rect"][0].tolist() == [x0, y0, x1, y1]
+    assert r["tiles_touched"][0].item() == (x1 - x0) * (y1 - y0) == r["keys"].numel()
+    tiles = sorted(ty * gx + tx for ty in range(y0, y1) for tx in range(x0, x1))
+    assert (r["keys"] >> 32).tolist() == tiles
+    depth_bits = torch.tensor([2.0]).view(torch.int32).item()
+    assert all((k & 0xFFFFFFFF) == depth_bits for k in r["keys"].tolist())
+
+
+def test_culling():
+    W = H = 32
+    cam = _cam(W, H)
+    xyz = torch.tensor([[0., 0, 1.9], [0., 0, 5.0], [50., 0, 0]])   # z_view = 0.1 (near-culled), behind, far off-screen
+    r = _raster(cam, xyz, torch.full((3, 3), 0.01), torch.tensor([[1., 0, 0, 0]] * 3), torch.full((3, 1), 0.5),
+                torch.ones(3, 3), W, H, bg=(1., 1., 1.))
+    assert r["radii"].tolist() == [0, 0, 0] and r["keys"].numel() == 0
+    assert torch.equal(r["image"], torch.ones(3, H, W)) and float(r["alpha"].abs().max()) == 0
+
+
+def test_gradcheck_fp64():
+    """autograd through the oracle agrees with finite differences (fp64), i.e. the gradient oracle is sound"""
+    torch.manual_seed(0)
+    W = H = 16
+    cam = _cam(W, H)
+    N = 6
+    xyz = ((torch.rand(N, 3) - 0.5) * 0.4).double().requires_grad_(True)
+    scales = (0.05 + 0.1 * torch.rand(N, 3)).double().requires_grad_(True)
+    rot = torch.nn.functional.normalize(torch.randn(N, 4)).double().requires_grad_(True)
+    op = (0.3 + 0.5 * torch.rand(N, 1)).double().requires_grad_(True)
+    shs = torch.randn(N, 4, 3).double().requires_grad_(True)
+    wts = torch.rand(8, H, W).double()
+
+    def f(xyz, scales, rot, op, shs):
+        r = orast.rasterize(xyz, scales, rot, op, cam.world_view_transform, cam.full_proj_transform,
+                            cam.camera_center, cam.tanfovx, cam.tanfovy, W, H, torch.tensor([0.3, 0.6, 0.9]).double(),
+                            shs=shs, sh_degree=1)
+        out = torch.cat([r["image"], r["depth"], r["normal"], r["alpha"]], 0)
+        return (out * wts).sum()
+
+    assert torch.autograd.gradcheck(f, (xyz, scales, rot, op, shs), eps=1e-6, atol=1e-5, rtol=1e-3, nondet_tol=0)
+
+
+def test_knn_oracle_basic():
+    ref = torch.tensor([[0., 0, 0], [1, 0, 0], [0, 2, 0], [0, 0, 3], [1, 0, 0]])
+    q = torch.tensor([[0.9, 0, 0]])
+    d, i = oknn.knn(ref, q, 4)
+    assert i.tolist() == [[1, 4, 0, 2]]          # tie between 1 and 4 -> lower index first
+    assert torch.allclose(d[0], torch.tensor([0.1, 0.1, 0.9, math.sqrt(0.81 + 4)]))
+    pts = torch.tensor([[0., 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [5, 5, 5]])
+    assert torch.allclose(oknn.dist3nn(pts)[0], torch.tensor(1.0))
