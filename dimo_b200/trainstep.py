@@ -9,6 +9,7 @@ SURVEY.md 8f "next" rows and are not part of this step.
 import torch
 
 from . import _lib
+from .dist import FlatGradReducer
 from .renderer import Renderer
 
 
@@ -76,23 +77,10 @@ class TrainStep:
         self.world = world
         self.params = [p for p in self.g.parameters() if p.numel() > 0]
         self.opt = torch.optim.Adam(self.params, lr=lr, eps=1e-15, fused=True)
-        self._flat = None
+        self.reducer = FlatGradReducer(self.params) if world > 1 else None
 
     def allreduce_grads(self):
-        import torch.distributed as dist
-        grads = [p.grad for p in self.params if p.grad is not None]
-        n = sum(g.numel() for g in grads)
-        if self._flat is None or self._flat.numel() != n:
-            self._flat = torch.empty(n, dtype=torch.float32, device=grads[0].device)
-        o = 0
-        views = []
-        for g in grads:
-            v = self._flat[o:o + g.numel()].view_as(g)
-            views.append(v)
-            o += g.numel()
-        torch._foreach_copy_(views, grads)
-        dist.all_reduce(self._flat, op=dist.ReduceOp.SUM)
-        torch._foreach_copy_(grads, views)
+        self.reducer.reduce()
 
     def run(self, cameras, times, latent_indices, gt, mask, n_motions, optimize=True):
         """cameras/times/latent_indices: length-S lists ordered motion-major; gt [S,3,H,W], mask [S,1,H,W] on device.

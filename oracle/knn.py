@@ -22,13 +22,18 @@ def _sqdist(q, r):
     return (dx * dx + dy * dy) + dz * dz
 
 
+def _sqrt_rn(x):
+    """correctly rounded fp32 sqrt (torch.sqrt on CPU is not; see oracle/raster.py::_sqrt_rn)"""
+    return x.double().sqrt().float() if x.dtype == torch.float32 else torch.sqrt(x)
+
+
 def knn(ref, query, k=4, chunk=8192):
     """ref [M,3], query [N,3] -> dist [N,k] (Euclidean), idx [N,k] int64."""
     ds, ix = [], []
     for s in range(0, query.shape[0], chunk):
         d2 = _sqdist(query[s:s + chunk], ref)
         order = torch.sort(d2, dim=1, stable=True)
-        ds.append(torch.sqrt(order.values[:, :k]))
+        ds.append(_sqrt_rn(order.values[:, :k]))
         ix.append(order.indices[:, :k])
     return torch.cat(ds), torch.cat(ix)
 

@@ -42,6 +42,15 @@ def _f32(x):
     return torch.tensor(x, dtype=torch.float32).item()
 
 
+def _sqrt_rn(x):
+    """Correctly rounded fp32 square root.  torch.sqrt on CPU (SLEEF) is off by 1 ulp for ~0.6 % of inputs, the
+    CUDA sqrtf (default -prec-sqrt=true) is IEEE; sqrt in fp64 followed by rounding to fp32 is exact-rounded
+    (53 >= 2*24+2 bits), so this is the same function the kernel computes."""
+    if x.dtype == torch.float32:
+        return x.double().sqrt().float()
+    return torch.sqrt(x)
+
+
 def _dot3(a0, a1, a2, b0, b1, b2):
     return (a0 * b0 + a1 * b1) + a2 * b2
 
@@ -117,9 +126,9 @@ def preprocess(means3D, scales, rotations, opacities, view, proj, campos, tanfov
     conic_b = -cb * det_inv
     conic_c = ca * det_inv
     mid = 0.5 * (ca + cc)
-    root = torch.sqrt(torch.clamp_min(mid * mid - det, LAMBDA_FLOOR))
+    root = _sqrt_rn(torch.clamp_min(mid * mid - det, LAMBDA_FLOOR))
     lam = torch.maximum(mid + root, mid - root)
-    radius_f = torch.ceil(RADIUS_SIGMAS * torch.sqrt(lam))
+    radius_f = torch.ceil(RADIUS_SIGMAS * _sqrt_rn(lam))
     pix_x = ((ndc_x + 1.0) * W - 1.0) * 0.5
     pix_y = ((ndc_y + 1.0) * H - 1.0) * 0.5
 
