@@ -117,7 +117,9 @@ def cpu_baseline(wl, n_frames, threads=None):
     import torch
     from dimo_b200 import synthetic
     from oracle import deform as od, raster as orast, camera as ocam, loss as oloss, knn as oknn
-    threads = threads or os.cpu_count()
+    # the oracle's per-tile blend is a stream of small tensor ops: beyond ~16 threads the intra-op pool only
+    # adds contention (measured: 8 threads 40 s/frame, 128 threads 657 s/frame on the B200 host) -> cap at 16
+    threads = threads or min(os.cpu_count(), 16)
     torch.set_num_threads(threads)
     sc = synthetic.make_scene(wl["N"], n_ctrl=wl["M"], n_motions=wl["motions_per_gpu"], seed=0)
     params = od.timenet_init(32, seed=0, final_scale=0.01)

@@ -33,7 +33,27 @@ __global__ void __launch_bounds__(256) pack_ranges_kernel(int64_t R, const uint6
   const int qd = (int)(t & 3);
   if (j >= R) return;
   const uint32_t v = vals[j];
-  packed[4 * j + qd] = splats[4 * (int64_t)v + qd];
+  // splat record  x,y,ca,cb | cc,op,r,g | b,depth,nx,ny | nz,-,-,-   ->   blend record (raster_blend.cu)
+  //               x,y,a2,b2 | c2,op,pthr2,r | g,b,depth,nx | ny,nz,gid,0
+  const float4* sp = splats + 4 * (int64_t)v;
+  constexpr float LOG2E = 1.4426950408889634f;
+  float4 o;
+  if (qd == 0) {
+    const float4 s0 = sp[0];
+    o = make_float4(s0.x, s0.y, (-0.5f * LOG2E) * s0.z, -LOG2E * s0.w);
+  } else if (qd == 1) {
+    const float4 s1 = sp[1];
+    // pairs with p2 < pthr2 cannot reach alpha >= 1/255 (0.01 in log2 units = 0.7 % safety margin on alpha)
+    const float pthr2 = -log2f(255.0f * s1.y) - 0.01f;
+    o = make_float4((-0.5f * LOG2E) * s1.x, s1.y, pthr2, s1.z);
+  } else if (qd == 2) {
+    const float4 s1 = sp[1], s2 = sp[2];
+    o = make_float4(s1.w, s2.x, s2.y, s2.z);
+  } else {
+    const float4 s2 = sp[2], s3 = sp[3];
+    o = make_float4(s2.w, s3.x, __uint_as_float(v), 0.f);
+  }
+  packed[4 * j + qd] = o;
   if (qd == 0) {
     const uint32_t tile = (uint32_t)(keys[j] >> 32);
     if (j == 0) {

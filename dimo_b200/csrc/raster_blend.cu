@@ -1,23 +1,38 @@
 // Per-tile alpha blending, forward and backward (the "renderCUDA" stage of diff_gauss /
 // diff_gaussian_rasterization; call site renderer/latent_gs_renderer.py:1256-1277).
 //
-// B200 design: one CTA per 16x16 tile per frame.  The tile's depth-sorted splat list is a
-// contiguous run of 64-byte records (raster_bin.cu packs it), streamed into shared memory by
-// 1-D bulk TMA (cp.async.bulk -> mbarrier complete_tx), double-buffered, 256 records (16 KB) per
-// stage; every thread then reads records as broadcast LDS.128.  Bound: FP32 FMA + MUFU.EX2 issue
-// and shared-memory broadcast bandwidth, HBM secondary.
-//
-// Backward: back-to-front replay from the tile's deepest contributor; per-splat gradients are
-// reduced over the 32 pixels of a warp with shuffles, over the 8 warps in shared memory, and
-// flushed with one global atomicAdd per (tile, splat, field) -- ~256x fewer global atomics than a
-// per-pixel scheme.
+// B200 design
+//  * one CTA (64 threads = 2 warps) per 16x16 tile per frame; every thread owns 4 horizontally
+//    adjacent pixels, so the per-splat shared-memory reads (broadcast LDS.128) and the row-dependent
+//    part of the quadratic form are amortised over 4 pixels and outputs leave as 128-bit stores;
+//  * the tile's depth-sorted splat list is a contiguous run of 64-byte "blend records"
+//    (raster_bin.cu packs them), streamed into shared memory by 1-D bulk TMA
+//    (cp.async.bulk -> mbarrier complete_tx), double-buffered, 128 records (8 KB) per stage;
+//  * records carry the conic pre-multiplied by -0.5*log2(e) (resp. -log2(e)), so
+//    alpha = opacity * ex2(p2) is one MUFU.EX2 without the extra multiply, and a conservative
+//    threshold p2 >= -log2(255*opacity) - margin that skips the MUFU for pairs that cannot reach
+//    alpha >= 1/255 (the exact test still follows, so results are unchanged);
+//  * backward: back-to-front replay from the tile's deepest contributor; per-splat gradients are
+//    summed over a thread's 4 pixels, reduced over the warp with shuffles, over the 2 warps in shared
+//    memory, and flushed with one global atomicAdd per (tile, splat, field).
+// Bound: FP32 FMA + MUFU.EX2 issue; HBM is secondary.
 #include "common.cuh"
 
 namespace dimo {
 
-constexpr int CHUNK = 256;                      // splat records per smem stage
+constexpr int CHUNK = 128;                      // blend records per smem stage
 constexpr int REC_F4 = DIMO_SPLAT_FLOATS / 4;   // float4 per record
 constexpr int NGRAD = 13;                       // gradient fields per splat (x,y,ca,cb,cc,op,r,g,b,depth,nx,ny,nz)
+constexpr int PPT = 4;                          // pixels per thread
+constexpr int BLEND_THREADS = TILE_PIX / PPT;   // 64
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+
+// blend record layout (written by pack_ranges_kernel, raster_bin.cu):
+//   f4#0: x, y, a2 = -0.5*log2e*conic_a, b2 = -log2e*conic_b
+//   f4#1: c2 = -0.5*log2e*conic_c, opacity, pthr2, r
+//   f4#2: g, b, depth, nx
+//   f4#3: ny, nz, gid (int bits), 0
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -51,8 +66,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
-__global__ void __launch_bounds__(TILE_PIX) blend_fwd_kernel(
+__global__ void __launch_bounds__(BLEND_THREADS) blend_fwd_kernel(
     int W, int H, int gx, int tiles_per_frame, const float* __restrict__ cams, const float4* __restrict__ packed,
     const uint2* __restrict__ ranges, float* __restrict__ out_color, float* __restrict__ out_depth,
     float* __restrict__ out_normal, float* __restrict__ out_alpha, float* __restrict__ final_T,
@@ -64,10 +84,9 @@ __global__ void __launch_bounds__(TILE_PIX) blend_fwd_kernel(
   const int b = tile / tiles_per_frame;
   const int t = tile - b * tiles_per_frame;
   const int ty = t / gx, tx = t - ty * gx;
-  const int tid = threadIdx.y * TILE + threadIdx.x;
-  const int pxi = tx * TILE + threadIdx.x, pyi = ty * TILE + threadIdx.y;
-  const bool inside = pxi < W && pyi < H;
-  const float pxf = (float)pxi, pyf = (float)pyi;
+  const int tid = threadIdx.x;
+  const int px0 = tx * TILE + (tid & 3) * PPT, pyi = ty * TILE + (tid >> 2);
+  const float pxf0 = (float)px0, pyf = (float)pyi;
 
   const uint2 rng = ranges[tile];
   const int n = (int)(rng.y - rng.x);
@@ -88,44 +107,68 @@ __global__ void __launch_bounds__(TILE_PIX) blend_fwd_kernel(
     }
   }
 
-  float T = 1.0f;
-  float Cr = 0.f, Cg = 0.f, Cb = 0.f, D = 0.f, Nx = 0.f, Ny = 0.f, Nz = 0.f;
-  int contributor = 0, last = 0;
-  bool done = !inside;
+  float T[PPT], Cr[PPT], Cg[PPT], Cb[PPT], D[PPT], Nx[PPT], Ny[PPT], Nz[PPT];
+  int last[PPT];
+  unsigned alive = 0;
+#pragma unroll
+  for (int i = 0; i < PPT; ++i) {
+    T[i] = 1.f; Cr[i] = Cg[i] = Cb[i] = D[i] = Nx[i] = Ny[i] = Nz[i] = 0.f; last[i] = 0;
+    if (px0 + i < W && pyi < H) alive |= 1u << i;
+  }
 
   int c = 0;
   for (; c < nchunks; ++c) {
     const int stage = c & 1;
     mbar_wait(&bar[stage], (c >> 1) & 1);
     const int cnt = min(CHUNK, n - c * CHUNK);
-    if (!done) {
+    // The loop is kept WARP-UNIFORM (votes decide every branch that is not a plain predicated region): a
+    // per-thread `continue`/`break` loop de-converges the warp for good -- the first version of this kernel ran
+    // at 1.65 active threads per instruction (profiles/r1_blend_v1_*.csv).
+    if (__any_sync(0xffffffffu, alive != 0)) {
       const float4* s = &sm[stage][0];
+      const int base = c * CHUNK;
       for (int j = 0; j < cnt; ++j) {
-        ++contributor;
-        const float4 a = s[j * REC_F4 + 0];   // x, y, conic_a, conic_b
-        const float4 bq = s[j * REC_F4 + 1];  // conic_c, opacity, r, g
-        const float dx = a.x - pxf, dy = a.y - pyf;
-        const float power = -0.5f * (a.z * dx * dx + bq.x * dy * dy) - a.w * dx * dy;
-        if (power > 0.0f) continue;
-        const float alpha = fminf(ALPHA_MAX, bq.y * __expf(power));
-        if (alpha < ALPHA_MIN) continue;
-        const float test_T = T * (1.0f - alpha);
-        if (test_T < T_MIN) {
-          done = true;
-          break;
+        const float4 a = s[j * REC_F4 + 0];   // x, y, a2, b2
+        const float4 bq = s[j * REC_F4 + 1];  // c2, opacity, pthr2, r
+        const float dy = a.y - pyf, dx0 = a.x - pxf0;
+        const float by = a.w * dy, cy = bq.x * dy * dy;
+        float p[PPT];
+        unsigned hit = 0;
+#pragma unroll
+        for (int i = 0; i < PPT; ++i) {
+          const float dx = dx0 - (float)i;
+          p[i] = fmaf(fmaf(a.z, dx, by), dx, cy);
+          if (p[i] <= 0.f && p[i] >= bq.z) hit |= 1u << i;
         }
-        const float4 cq = s[j * REC_F4 + 2];  // b, depth, nx, ny
-        const float nzv = s[j * REC_F4 + 3].x;
-        const float w = alpha * T;
-        Cr += bq.z * w; Cg += bq.w * w; Cb += cq.x * w;
-        D += cq.y * w;
-        Nx += cq.z * w; Ny += cq.w * w; Nz += nzv * w;
-        T = test_T;
-        last = contributor;
+        hit &= alive;
+        if (__any_sync(0xffffffffu, hit != 0)) {
+          const float4 cq = s[j * REC_F4 + 2];  // g, b, depth, nx
+          const float4 dq = s[j * REC_F4 + 3];  // ny, nz, gid, -
+#pragma unroll
+          for (int i = 0; i < PPT; ++i) {
+            if (hit & (1u << i)) {
+              const float alpha = fminf(ALPHA_MAX, bq.y * ex2_approx(p[i]));
+              if (alpha >= ALPHA_MIN) {
+                const float test_T = T[i] * (1.0f - alpha);
+                if (test_T < T_MIN) {
+                  alive &= ~(1u << i);
+                } else {
+                  const float w = alpha * T[i];
+                  Cr[i] = fmaf(bq.w, w, Cr[i]); Cg[i] = fmaf(cq.x, w, Cg[i]); Cb[i] = fmaf(cq.y, w, Cb[i]);
+                  D[i] = fmaf(cq.z, w, D[i]);
+                  Nx[i] = fmaf(cq.w, w, Nx[i]); Ny[i] = fmaf(dq.x, w, Ny[i]); Nz[i] = fmaf(dq.y, w, Nz[i]);
+                  T[i] = test_T;
+                  last[i] = base + j + 1;
+                }
+              }
+            }
+          }
+          if (!__any_sync(0xffffffffu, alive != 0)) break;   // whole warp saturated
+        }
       }
     }
-    const int num_done = __syncthreads_count(done);
-    if (num_done == TILE_PIX) break;
+    const int num_alive = __syncthreads_count(alive != 0);
+    if (num_alive == 0) break;
     if (tid == 0 && c + 2 < nchunks) {
       const int cnt2 = min(CHUNK, n - (c + 2) * CHUNK);
       mbar_expect_tx(&bar[stage], cnt2 * 64);
@@ -135,20 +178,39 @@ __global__ void __launch_bounds__(TILE_PIX) blend_fwd_kernel(
   // an early break can leave chunk c+1 in flight: it must land before this CTA's smem is released
   if (c < nchunks && c + 1 < nchunks) mbar_wait(&bar[(c + 1) & 1], ((c + 1) >> 1) & 1);
 
-  if (inside) {
-    const float* bg = cams + (int64_t)b * DIMO_CAM_FLOATS + CAM_BG;
-    const int64_t hw = (int64_t)H * W;
-    const int64_t pix = (int64_t)pyi * W + pxi;
-    out_color[((int64_t)b * 3 + 0) * hw + pix] = Cr + T * bg[0];
-    out_color[((int64_t)b * 3 + 1) * hw + pix] = Cg + T * bg[1];
-    out_color[((int64_t)b * 3 + 2) * hw + pix] = Cb + T * bg[2];
-    out_depth[(int64_t)b * hw + pix] = D;
-    out_normal[((int64_t)b * 3 + 0) * hw + pix] = Nx;
-    out_normal[((int64_t)b * 3 + 1) * hw + pix] = Ny;
-    out_normal[((int64_t)b * 3 + 2) * hw + pix] = Nz;
-    out_alpha[(int64_t)b * hw + pix] = 1.0f - T;
-    final_T[(int64_t)b * hw + pix] = T;
-    n_contrib[(int64_t)b * hw + pix] = last;
+  if (pyi >= H || px0 >= W) return;
+  const float* bg = cams + (int64_t)b * DIMO_CAM_FLOATS + CAM_BG;
+  const float bg0 = bg[0], bg1 = bg[1], bg2 = bg[2];
+  const int64_t hw = (int64_t)H * W;
+  const int64_t pix = (int64_t)pyi * W + px0;
+  float* oc = out_color + (int64_t)b * 3 * hw + pix;
+  float* od = out_depth + (int64_t)b * hw + pix;
+  float* on = out_normal + (int64_t)b * 3 * hw + pix;
+  float* oa = out_alpha + (int64_t)b * hw + pix;
+  float* oT = final_T + (int64_t)b * hw + pix;
+  int32_t* oN = n_contrib + (int64_t)b * hw + pix;
+  if ((W & 3) == 0 && px0 + PPT <= W) {
+    // W % 4 == 0 and px0 % 4 == 0: 16-byte aligned rows -> 128-bit stores
+    *reinterpret_cast<float4*>(oc) = make_float4(Cr[0] + T[0] * bg0, Cr[1] + T[1] * bg0, Cr[2] + T[2] * bg0, Cr[3] + T[3] * bg0);
+    *reinterpret_cast<float4*>(oc + hw) = make_float4(Cg[0] + T[0] * bg1, Cg[1] + T[1] * bg1, Cg[2] + T[2] * bg1, Cg[3] + T[3] * bg1);
+    *reinterpret_cast<float4*>(oc + 2 * hw) = make_float4(Cb[0] + T[0] * bg2, Cb[1] + T[1] * bg2, Cb[2] + T[2] * bg2, Cb[3] + T[3] * bg2);
+    *reinterpret_cast<float4*>(od) = make_float4(D[0], D[1], D[2], D[3]);
+    *reinterpret_cast<float4*>(on) = make_float4(Nx[0], Nx[1], Nx[2], Nx[3]);
+    *reinterpret_cast<float4*>(on + hw) = make_float4(Ny[0], Ny[1], Ny[2], Ny[3]);
+    *reinterpret_cast<float4*>(on + 2 * hw) = make_float4(Nz[0], Nz[1], Nz[2], Nz[3]);
+    *reinterpret_cast<float4*>(oa) = make_float4(1.f - T[0], 1.f - T[1], 1.f - T[2], 1.f - T[3]);
+    *reinterpret_cast<float4*>(oT) = make_float4(T[0], T[1], T[2], T[3]);
+    *reinterpret_cast<int4*>(oN) = make_int4(last[0], last[1], last[2], last[3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+      if (px0 + i < W) {
+        oc[i] = Cr[i] + T[i] * bg0; oc[hw + i] = Cg[i] + T[i] * bg1; oc[2 * hw + i] = Cb[i] + T[i] * bg2;
+        od[i] = D[i];
+        on[i] = Nx[i]; on[hw + i] = Ny[i]; on[2 * hw + i] = Nz[i];
+        oa[i] = 1.f - T[i]; oT[i] = T[i]; oN[i] = last[i];
+      }
+    }
   }
 }
 
@@ -158,11 +220,11 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-__global__ void __launch_bounds__(TILE_PIX) blend_bwd_kernel(
+__global__ void __launch_bounds__(BLEND_THREADS) blend_bwd_kernel(
     int W, int H, int gx, int tiles_per_frame, const float* __restrict__ cams, const float4* __restrict__ packed,
-    const uint2* __restrict__ ranges, const uint32_t* __restrict__ vals_sorted, const float* __restrict__ final_T,
-    const int32_t* __restrict__ n_contrib, const float* __restrict__ dL_dcolor, const float* __restrict__ dL_ddepth,
-    const float* __restrict__ dL_dnormal, const float* __restrict__ dL_dalpha, float* __restrict__ dL_dsplats) {
+    const uint2* __restrict__ ranges, const float* __restrict__ final_T, const int32_t* __restrict__ n_contrib,
+    const float* __restrict__ dL_dcolor, const float* __restrict__ dL_ddepth, const float* __restrict__ dL_dnormal,
+    const float* __restrict__ dL_dalpha, float* __restrict__ dL_dsplats) {
   __shared__ __align__(128) float4 sm[2][CHUNK * REC_F4];
   __shared__ float acc[CHUNK * NGRAD];
   __shared__ __align__(8) uint64_t bar[2];
@@ -172,34 +234,39 @@ __global__ void __launch_bounds__(TILE_PIX) blend_bwd_kernel(
   const int b = tile / tiles_per_frame;
   const int t = tile - b * tiles_per_frame;
   const int ty = t / gx, tx = t - ty * gx;
-  const int tid = threadIdx.y * TILE + threadIdx.x;
+  const int tid = threadIdx.x;
   const int lane = tid & 31;
-  const int pxi = tx * TILE + threadIdx.x, pyi = ty * TILE + threadIdx.y;
-  const bool inside = pxi < W && pyi < H;
-  const float pxf = (float)pxi, pyf = (float)pyi;
+  const int px0 = tx * TILE + (tid & 3) * PPT, pyi = ty * TILE + (tid >> 2);
+  const float pxf0 = (float)px0, pyf = (float)pyi;
   const uint2 rng = ranges[tile];
   if (rng.y <= rng.x) return;
 
   const int64_t hw = (int64_t)H * W;
-  const int64_t pix = (int64_t)pyi * W + pxi;
-  float gc0 = 0.f, gc1 = 0.f, gc2 = 0.f, gd = 0.f, gn0 = 0.f, gn1 = 0.f, gn2 = 0.f, ga = 0.f, Tf = 1.f;
-  int last = 0;
-  if (inside) {
-    gc0 = dL_dcolor[((int64_t)b * 3 + 0) * hw + pix];
-    gc1 = dL_dcolor[((int64_t)b * 3 + 1) * hw + pix];
-    gc2 = dL_dcolor[((int64_t)b * 3 + 2) * hw + pix];
-    gd = dL_ddepth[(int64_t)b * hw + pix];
-    gn0 = dL_dnormal[((int64_t)b * 3 + 0) * hw + pix];
-    gn1 = dL_dnormal[((int64_t)b * 3 + 1) * hw + pix];
-    gn2 = dL_dnormal[((int64_t)b * 3 + 2) * hw + pix];
-    ga = dL_dalpha[(int64_t)b * hw + pix];
-    Tf = final_T[(int64_t)b * hw + pix];
-    last = n_contrib[(int64_t)b * hw + pix];
-  }
   const float* bg = cams + (int64_t)b * DIMO_CAM_FLOATS + CAM_BG;
-  // Qp = sum_{j>i} (g.f_j) alpha_j T_j  -  (ga - g_rgb.bg) * T_final
-  float Qp = -(ga - (gc0 * bg[0] + gc1 * bg[1] + gc2 * bg[2])) * Tf;
-  float T = Tf;
+  const float bg0 = bg[0], bg1 = bg[1], bg2 = bg[2];
+  float gc0[PPT], gc1[PPT], gc2[PPT], gd[PPT], gn0[PPT], gn1[PPT], gn2[PPT], T[PPT], Qp[PPT];
+  int last[PPT];
+  int lmax = 0;
+#pragma unroll
+  for (int i = 0; i < PPT; ++i) {
+    gc0[i] = gc1[i] = gc2[i] = gd[i] = gn0[i] = gn1[i] = gn2[i] = 0.f; T[i] = 1.f; Qp[i] = 0.f; last[i] = 0;
+    if (px0 + i < W && pyi < H) {
+      const int64_t pix = (int64_t)pyi * W + px0 + i;
+      gc0[i] = dL_dcolor[((int64_t)b * 3 + 0) * hw + pix];
+      gc1[i] = dL_dcolor[((int64_t)b * 3 + 1) * hw + pix];
+      gc2[i] = dL_dcolor[((int64_t)b * 3 + 2) * hw + pix];
+      gd[i] = dL_ddepth[(int64_t)b * hw + pix];
+      gn0[i] = dL_dnormal[((int64_t)b * 3 + 0) * hw + pix];
+      gn1[i] = dL_dnormal[((int64_t)b * 3 + 1) * hw + pix];
+      gn2[i] = dL_dnormal[((int64_t)b * 3 + 2) * hw + pix];
+      const float ga = dL_dalpha[(int64_t)b * hw + pix];
+      T[i] = final_T[(int64_t)b * hw + pix];
+      last[i] = n_contrib[(int64_t)b * hw + pix];
+      // Qp = sum_{j>i} (g.f_j) alpha_j T_j  -  (ga - g_rgb.bg) * T_final
+      Qp[i] = -(ga - (gc0[i] * bg0 + gc1[i] * bg1 + gc2[i] * bg2)) * T[i];
+      lmax = max(lmax, last[i]);
+    }
+  }
 
   if (tid == 0) {
     s_max = 0;
@@ -207,10 +274,10 @@ __global__ void __launch_bounds__(TILE_PIX) blend_bwd_kernel(
     mbar_init(&bar[1], 1);
     fence_mbar_init();
   }
-  for (int k = tid; k < CHUNK * NGRAD; k += TILE_PIX) acc[k] = 0.f;
+  for (int k = tid; k < CHUNK * NGRAD; k += BLEND_THREADS) acc[k] = 0.f;
   __syncthreads();
   {
-    int m = last;
+    int m = lmax;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
     if (lane == 0 && m > 0) atomicMax(&s_max, m);
@@ -239,47 +306,57 @@ __global__ void __launch_bounds__(TILE_PIX) blend_bwd_kernel(
     const float4* s = &sm[stage][0];
     for (int j = cnt - 1; j >= 0; --j) {
       const int pos = cc * CHUNK + j;
-      bool active = pos < last;
-      float dx = 0.f, dy = 0.f, G = 0.f, alpha = 0.f;
+      unsigned hit = 0;
+      float p[PPT];
       float4 a, bq;
-      if (__any_sync(0xffffffffu, active)) {
+      float dy = 0.f, dx0 = 0.f;
+      if (__any_sync(0xffffffffu, pos < lmax)) {
         a = s[j * REC_F4 + 0];
         bq = s[j * REC_F4 + 1];
-        if (active) {
-          dx = a.x - pxf; dy = a.y - pyf;
-          const float power = -0.5f * (a.z * dx * dx + bq.x * dy * dy) - a.w * dx * dy;
-          if (power > 0.0f) {
-            active = false;
-          } else {
-            G = __expf(power);
-            alpha = fminf(ALPHA_MAX, bq.y * G);
-            if (alpha < ALPHA_MIN) active = false;
-          }
+        dy = a.y - pyf; dx0 = a.x - pxf0;
+        const float by = a.w * dy, cy = bq.x * dy * dy;
+#pragma unroll
+        for (int i = 0; i < PPT; ++i) {
+          const float dx = dx0 - (float)i;
+          p[i] = fmaf(fmaf(a.z, dx, by), dx, cy);
+          if (pos < last[i] && p[i] <= 0.f && p[i] >= bq.z) hit |= 1u << i;
         }
       }
-      if (!__any_sync(0xffffffffu, active)) continue;
+      if (!__any_sync(0xffffffffu, hit != 0)) continue;
       float v[NGRAD];
 #pragma unroll
       for (int q = 0; q < NGRAD; ++q) v[q] = 0.f;
-      if (active) {
-        const float4 cq = s[j * REC_F4 + 2];
-        const float nzv = s[j * REC_F4 + 3].x;
-        const float inv = 1.0f / (1.0f - alpha);
-        T = T * inv;
-        const float w = alpha * T;
-        const float dotf = gc0 * bq.z + gc1 * bq.w + gc2 * cq.x + gd * cq.y + gn0 * cq.z + gn1 * cq.w + gn2 * nzv;
-        const float dLa = T * dotf - Qp * inv;
-        Qp += dotf * w;
-        const float gp = dLa * bq.y * G;
-        v[0] = -(a.z * dx + a.w * dy) * gp;
-        v[1] = -(bq.x * dy + a.w * dx) * gp;
-        v[2] = -0.5f * dx * dx * gp;
-        v[3] = -dx * dy * gp;
-        v[4] = -0.5f * dy * dy * gp;
-        v[5] = G * dLa;
-        v[6] = gc0 * w; v[7] = gc1 * w; v[8] = gc2 * w;
-        v[9] = gd * w;
-        v[10] = gn0 * w; v[11] = gn1 * w; v[12] = gn2 * w;
+      if (hit) {
+        const float4 cq = s[j * REC_F4 + 2];  // g, b, depth, nx
+        const float4 dq = s[j * REC_F4 + 3];  // ny, nz, gid, -
+#pragma unroll
+        for (int i = 0; i < PPT; ++i) {
+          if (hit & (1u << i)) {
+            const float G = ex2_approx(p[i]);
+            const float alpha = fminf(ALPHA_MAX, bq.y * G);
+            if (alpha >= ALPHA_MIN) {
+              const float dx = dx0 - (float)i;
+              const float inv = 1.0f / (1.0f - alpha);
+              T[i] = T[i] * inv;
+              const float w = alpha * T[i];
+              const float dotf = gc0[i] * bq.w + gc1[i] * cq.x + gc2[i] * cq.y + gd[i] * cq.z + gn0[i] * cq.w +
+                                 gn1[i] * dq.x + gn2[i] * dq.y;
+              const float dLa = T[i] * dotf - Qp[i] * inv;
+              Qp[i] = fmaf(dotf, w, Qp[i]);
+              // alpha = op * 2^p2 ; p2 = a2 dx^2 + b2 dx dy + c2 dy^2
+              const float gp2 = dLa * bq.y * G * LN2;
+              v[0] += (2.f * a.z * dx + a.w * dy) * gp2;     // d/dx
+              v[1] += (2.f * bq.x * dy + a.w * dx) * gp2;    // d/dy
+              v[2] += dx * dx * gp2;                         // d/da2
+              v[3] += dx * dy * gp2;                         // d/db2
+              v[4] += dy * dy * gp2;                         // d/dc2
+              v[5] += G * dLa;
+              v[6] += gc0[i] * w; v[7] += gc1[i] * w; v[8] += gc2[i] * w;
+              v[9] += gd[i] * w;
+              v[10] += gn0[i] * w; v[11] += gn1[i] * w; v[12] += gn2[i] * w;
+            }
+          }
+        }
       }
 #pragma unroll
       for (int q = 0; q < NGRAD; ++q) v[q] = warp_sum(v[q]);
@@ -288,24 +365,26 @@ __global__ void __launch_bounds__(TILE_PIX) blend_bwd_kernel(
         for (int q = 0; q < NGRAD; ++q) atomicAdd(&acc[j * NGRAD + q], v[q]);
       }
     }
-    __syncthreads();   // all reads of sm[stage] and all smem atomics of this chunk are done
+    __syncthreads();   // all reads of sm[stage] (except gid below) and all smem atomics of this chunk are done
+    // flush this chunk's accumulators: one global atomic per (splat, field); conic grads back to natural units
+    for (int e = tid; e < cnt * NGRAD; e += BLEND_THREADS) {
+      const int j = e / NGRAD, q = e - j * NGRAD;
+      float val = acc[e];
+      acc[e] = 0.f;
+      if (val != 0.f) {
+        const uint32_t gid = __float_as_uint(s[j * REC_F4 + 3].z);
+        if (q == 2 || q == 4) val *= -0.5f * LOG2E;
+        else if (q == 3) val *= -LOG2E;
+        atomicAdd(&dL_dsplats[(int64_t)gid * DIMO_SPLAT_FLOATS + q], val);
+      }
+    }
+    __syncthreads();
     if (tid == 0 && k + 2 < nchunks) {
       const int c2 = nchunks - 1 - (k + 2);
       const int cnt2 = min(CHUNK, nproc - c2 * CHUNK);
       mbar_expect_tx(&bar[stage], cnt2 * 64);
       bulk_g2s(&sm[stage][0], src + (int64_t)c2 * CHUNK * REC_F4, cnt2 * 64, &bar[stage]);
     }
-    // flush this chunk's accumulators: one global atomic per (splat, field)
-    for (int e = tid; e < cnt * NGRAD; e += TILE_PIX) {
-      const int j = e / NGRAD, q = e - j * NGRAD;
-      const float val = acc[e];
-      acc[e] = 0.f;
-      if (val != 0.f) {
-        const uint32_t gid = vals_sorted[(int64_t)rng.x + cc * CHUNK + j];
-        atomicAdd(&dL_dsplats[(int64_t)gid * DIMO_SPLAT_FLOATS + q], val);
-      }
-    }
-    __syncthreads();
   }
 }
 
@@ -319,8 +398,7 @@ extern "C" int dimo_raster_blend_fwd(int B, int W, int H, const float* cams, con
   DIMO_REQUIRE(B >= 0 && W > 0 && H > 0, "bad sizes");
   if (B == 0) return 0;
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
-  dim3 block(TILE, TILE);
-  blend_fwd_kernel<<<B * gx * gy, block, 0, (cudaStream_t)stream>>>(
+  blend_fwd_kernel<<<B * gx * gy, BLEND_THREADS, 0, (cudaStream_t)stream>>>(
       W, H, gx, gx * gy, cams, reinterpret_cast<const float4*>(packed), reinterpret_cast<const uint2*>(ranges),
       out_color, out_depth, out_normal, out_alpha, final_T, n_contrib);
   DIMO_CHECK_LAUNCH();
@@ -332,15 +410,15 @@ extern "C" int dimo_raster_blend_bwd(int B, int N, int W, int H, const float* ca
                                      const int32_t* n_contrib, const float* dL_dcolor, const float* dL_ddepth,
                                      const float* dL_dnormal, const float* dL_dalpha, float* dL_dsplats,
                                      void* stream) {
+  (void)vals_sorted;   // the Gaussian id travels inside the blend record
   DIMO_REQUIRE(B >= 0 && W > 0 && H > 0, "bad sizes");
   cudaStream_t st = (cudaStream_t)stream;
   if (B == 0 || N == 0) return 0;
   DIMO_CHECK_CUDA(cudaMemsetAsync(dL_dsplats, 0, sizeof(float) * DIMO_SPLAT_FLOATS * (size_t)B * N, st));
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
-  dim3 block(TILE, TILE);
-  blend_bwd_kernel<<<B * gx * gy, block, 0, st>>>(
+  blend_bwd_kernel<<<B * gx * gy, BLEND_THREADS, 0, st>>>(
       W, H, gx, gx * gy, cams, reinterpret_cast<const float4*>(packed), reinterpret_cast<const uint2*>(ranges),
-      vals_sorted, final_T, n_contrib, dL_dcolor, dL_ddepth, dL_dnormal, dL_dalpha, dL_dsplats);
+      final_T, n_contrib, dL_dcolor, dL_ddepth, dL_dnormal, dL_dalpha, dL_dsplats);
   DIMO_CHECK_LAUNCH();
   return 0;
 }
