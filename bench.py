@@ -206,20 +206,43 @@ def run_ours(args, wl):
     gt_dev = [t.to(dev) for t in gt_host]
     mk_dev = [t.to(dev) for t in mk_host]
 
+    # e2e: ground truth travels host(pinned) -> device EVERY step, on a copy stream, double-buffered, so the
+    # copy of step i+1 overlaps the compute of step i (the reference uploads per render on the default stream,
+    # main_train_dimo.py:283-284)
+    copy_stream = torch.cuda.Stream(device=dev)
+    gt_buf = [torch.empty(S, 3, H, W, device=dev) for _ in range(2)]
+    mk_buf = [torch.empty(S, 1, H, W, device=dev) for _ in range(2)]
+    ready_ev, free_ev, staged = [None, None], [None, None], {}
+
+    def stage(i):
+        slot = i % 2
+        with torch.cuda.stream(copy_stream):
+            if free_ev[slot] is not None:
+                copy_stream.wait_event(free_ev[slot])
+            gt_buf[slot].copy_(gt_host[i % pool], non_blocking=True)
+            mk_buf[slot].copy_(mk_host[i % pool], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        ready_ev[slot] = ev
+        staged[i] = slot
+
     def one_step(i, e2e):
         frames = step_schedule(wl, i)
         cams = [cams_all[v] for (_, v, _) in frames]
         times = [f / wl["frames"] for (_, _, f) in frames]
         lat = [m for (m, _, _) in frames]
         if e2e:
-            gt = gt_host[i % pool].to(dev, non_blocking=True)
-            mk = mk_host[i % pool].to(dev, non_blocking=True)
-        else:
-            gt, mk = gt_dev[i % pool], mk_dev[i % pool]
-        loss = ts.run(cams, times, lat, gt, mk, wl["bm"])
-        if e2e:
+            if i not in staged:
+                stage(i)
+            slot = staged.pop(i)
+            torch.cuda.current_stream().wait_event(ready_ev[slot])
+            stage(i + 1)
+            loss = ts.run(cams, times, lat, gt_buf[slot], mk_buf[slot], wl["bm"])
+            ev = torch.cuda.Event()
+            ev.record()
+            free_ev[slot] = ev
             return loss.item()          # device -> host read of the step's result
-        return loss
+        return ts.run(cams, times, lat, gt_dev[i % pool], mk_dev[i % pool], wl["bm"])
 
     def barrier():
         if world > 1:

@@ -19,8 +19,8 @@ _SIGS = {
     "dimo_device_info": (c_int, [c_vp]),
     "dimo_raster_scan_temp_bytes": (c_sz, [c_i64]),
     "dimo_raster_sort_temp_bytes": (c_sz, [c_i64]),
-    "dimo_raster_preprocess": (c_int, [c_int] * 6 + [c_f32, c_vp] + [c_vp, c_i64] * 6 + [c_vp] * 4 + [c_vp, c_sz, c_vp, c_vp]),
-    "dimo_raster_bin": (c_int, [c_int] * 4 + [c_i64] + [c_vp] * 7 + [c_vp, c_sz, c_vp, c_vp, c_vp]),
+    "dimo_raster_preprocess": (c_int, [c_int] * 6 + [c_f32, c_vp] + [c_vp, c_i64] * 6 + [c_vp] * 6 + [c_vp, c_sz, c_vp, c_vp]),
+    "dimo_raster_bin": (c_int, [c_int] * 4 + [c_i64] + [c_vp] * 8 + [c_vp, c_sz, c_vp, c_vp, c_vp]),
     "dimo_raster_blend_fwd": (c_int, [c_int] * 3 + [c_vp] * 10),
     "dimo_raster_blend_bwd": (c_int, [c_int] * 4 + [c_vp] * 12),
     "dimo_raster_preprocess_bwd": (c_int, [c_int] * 6 + [c_f32, c_vp] + [c_vp, c_i64] * 4 + [c_vp] * 10),
@@ -82,7 +82,7 @@ def stream():
 
 # hand-written kernels launched per C-ABI call (CUB scan/sort launches are listed separately)
 _OWN_LAUNCHES = {
-    "dimo_raster_preprocess": 1, "dimo_raster_bin": 2, "dimo_raster_blend_fwd": 1, "dimo_raster_blend_bwd": 1,
+    "dimo_raster_preprocess": 2, "dimo_raster_bin": 2, "dimo_raster_blend_fwd": 1, "dimo_raster_blend_bwd": 1,
     "dimo_raster_preprocess_bwd": 1, "dimo_knn": 1, "dimo_dist3nn": 1, "dimo_linear_fwd": 1,
     "dimo_linear_bwd_data": 1, "dimo_linear_bwd_weight": 1, "dimo_timenet_embed_fwd": 1,
     "dimo_timenet_embed_bwd": 1, "dimo_lbs_fwd": 1, "dimo_lbs_bwd": 1, "dimo_ssim_fwd": 1, "dimo_ssim_bwd": 1,

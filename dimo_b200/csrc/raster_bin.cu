@@ -2,11 +2,19 @@
 // (tile|depth) radix sort, packing of splat records into sorted order and per-tile ranges.
 //
 // Upstream shape (diff_gauss / diff_gaussian_rasterization, call site
-// renderer/latent_gs_renderer.py:1256-1277): InclusiveSum -> duplicateWithKeys -> SortPairs ->
-// identifyTileRanges.  B200 change: the sorted instance list is materialised as contiguous 64-byte
-// splat records ("packed") so the blend kernels stream each tile's list with 1-D bulk TMA
-// (cp.async.bulk) instead of gathering by index.  Scan and sort are CUB device primitives compiled
-// into this library (integer-only, HBM-bound).
+// renderer/latent_gs_renderer.py:1256-1277): InclusiveSum -> duplicateWithKeys -> SortPairs over
+// 64-bit (tile | depth) keys (6 radix passes at 512^2 x 16 frames = 144 B per instance) -> identifyTileRanges.
+//
+// Here the same total order is produced with ~4.5x less traffic:
+//   1. the B*N splats are sorted ONCE by (frame, depth) -- 64-bit keys, but only B*N of them;
+//   2. tile counts are scanned in that order and instances are emitted front-to-back;
+//   3. the R instances are STABLE-sorted by the tile id alone: 32-bit keys, ceil(log2(B*tiles)) bits
+//      (14 bits = 2 passes at 512^2 x 16 frames, 32 B per instance).
+// A stable sort keeps the emission order inside a tile, i.e. ascending depth with ties in ascending Gaussian
+// index -- bit-for-bit the order of the 64-bit sort (tests compare against the oracle's stable 64-bit sort).
+// The sorted instance list is then materialised as contiguous 64-byte blend records ("packed") so the blend
+// kernels stream each tile's list with 1-D bulk TMA instead of gathering by index.  Scan and sorts are CUB
+// device primitives compiled into this library (integer-only, HBM-bound).
 #include "common.cuh"
 #include <cub/cub.cuh>
 #include <stdarg.h>
@@ -24,7 +32,7 @@ const char* get_error() { return g_err; }
 
 // 4 lanes per instance: lane q copies float4 #q of the 64-byte record (reads: 64 B contiguous per
 // instance, writes: fully coalesced).  Lane 0 also writes the tile range boundaries.
-__global__ void __launch_bounds__(256) pack_ranges_kernel(int64_t R, const uint64_t* __restrict__ keys,
+__global__ void __launch_bounds__(256) pack_ranges_kernel(int64_t R, const uint32_t* __restrict__ keys,
                                                           const uint32_t* __restrict__ vals,
                                                           const float4* __restrict__ splats,
                                                           float4* __restrict__ packed, uint2* __restrict__ ranges) {
@@ -55,11 +63,11 @@ __global__ void __launch_bounds__(256) pack_ranges_kernel(int64_t R, const uint6
   }
   packed[4 * j + qd] = o;
   if (qd == 0) {
-    const uint32_t tile = (uint32_t)(keys[j] >> 32);
+    const uint32_t tile = keys[j];
     if (j == 0) {
       ranges[tile].x = 0;
     } else {
-      const uint32_t prev = (uint32_t)(keys[j - 1] >> 32);
+      const uint32_t prev = keys[j - 1];
       if (prev != tile) {
         ranges[prev].y = (uint32_t)j;
         ranges[tile].x = (uint32_t)j;
@@ -69,12 +77,18 @@ __global__ void __launch_bounds__(256) pack_ranges_kernel(int64_t R, const uint6
   }
 }
 
-static inline int key_bits(int B, int W, int H) {
-  const int64_t tiles = (int64_t)B * ((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+static inline int bits_for(int64_t n) {
   int bits = 1;
-  while (((int64_t)1 << bits) < tiles) ++bits;
-  return 32 + bits;
+  while (((int64_t)1 << bits) < n) ++bits;
+  return bits;
 }
+
+// gathers tile counts in depth-sorted order for the scan
+struct PermutedCount {
+  const uint32_t* counts;
+  const uint32_t* perm;
+  __host__ __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return counts[perm[i]]; }
+};
 
 }  // namespace dimo
 
@@ -86,9 +100,10 @@ int preprocess_launch(int B, int N, int W, int H, int sh_degree, int sh_coeffs, 
                       int64_t scales_bstride, const float* rotations, int64_t rotations_bstride,
                       const float* opacities, int64_t opacities_bstride, const float* shs, int64_t shs_bstride,
                       const float* colors_precomp, int64_t colors_bstride, float* splats, int32_t* radii,
-                      uint32_t* tiles_touched, cudaStream_t st);
+                      uint32_t* tiles_touched, uint64_t* depth_keys, uint32_t* iota, cudaStream_t st);
 int emit_keys_launch(int B, int N, int W, int H, int64_t R, const float* splats, const int32_t* radii,
-                     const uint32_t* offsets, uint64_t* keys, uint32_t* vals, cudaStream_t st);
+                     const uint32_t* perm, const uint32_t* offsets, uint32_t* tile_keys, uint32_t* vals,
+                     cudaStream_t st);
 }  // namespace dimo
 
 extern "C" {
@@ -108,15 +123,17 @@ int dimo_device_info(int* out3_host) {
 }
 
 size_t dimo_raster_scan_temp_bytes(int64_t BN) {
-  size_t bytes = 0;
-  cub::DeviceScan::InclusiveSum(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)BN);
-  return bytes + 256;
+  size_t scan = 0, sort = 0;
+  cub::DeviceScan::InclusiveSum(nullptr, scan, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)BN);
+  cub::DeviceRadixSort::SortPairs(nullptr, sort, (const uint64_t*)nullptr, (uint64_t*)nullptr,
+                                  (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)BN, 0, 64);
+  return (scan > sort ? scan : sort) + 256;
 }
 
 size_t dimo_raster_sort_temp_bytes(int64_t R) {
   size_t bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
-                                  (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)R, 0, 64);
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                  (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)R, 0, 32);
   return bytes + 256;
 }
 
@@ -126,7 +143,8 @@ int dimo_raster_preprocess(int B, int N, int W, int H, int sh_degree, int sh_coe
                            const float* opacities, int64_t opacities_bstride, const float* shs,
                            int64_t shs_bstride, const float* colors_precomp, int64_t colors_bstride,
                            float* splats, int32_t* radii, uint32_t* tiles_touched, uint32_t* offsets,
-                           void* scan_temp, size_t scan_temp_bytes, int64_t* R_host, void* stream) {
+                           uint64_t* depth_keys, uint32_t* perm, void* scan_temp, size_t scan_temp_bytes,
+                           int64_t* R_host, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t BN = (int64_t)B * N;
   DIMO_REQUIRE(B >= 0 && N >= 0 && W > 0 && H > 0, "bad sizes");
@@ -138,13 +156,19 @@ int dimo_raster_preprocess(int B, int N, int W, int H, int sh_degree, int sh_coe
     if (R_host) *R_host = 0;
     return 0;
   }
-  int rc = preprocess_launch(B, N, W, H, sh_degree, sh_coeffs, scale_modifier, cams, means3D,
-                                         means3D_bstride, scales, scales_bstride, rotations, rotations_bstride,
-                                         opacities, opacities_bstride, shs, shs_bstride, colors_precomp,
-                                         colors_bstride, splats, radii, tiles_touched, st);
+  // depth_keys: [2*BN] (unsorted | sorted), perm: [2*BN] (iota | sorted permutation = perm + BN)
+  int rc = preprocess_launch(B, N, W, H, sh_degree, sh_coeffs, scale_modifier, cams, means3D, means3D_bstride, scales,
+                             scales_bstride, rotations, rotations_bstride, opacities, opacities_bstride, shs,
+                             shs_bstride, colors_precomp, colors_bstride, splats, radii, tiles_touched, depth_keys,
+                             perm, st);
   if (rc) return rc;
   size_t need = scan_temp_bytes;
-  DIMO_CHECK_CUDA(cub::DeviceScan::InclusiveSum(scan_temp, need, tiles_touched, offsets, (int)BN, st));
+  DIMO_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(scan_temp, need, depth_keys, depth_keys + BN, perm, perm + BN,
+                                                  (int)BN, 0, 32 + bits_for(B), st));
+  need = scan_temp_bytes;
+  cub::TransformInputIterator<uint32_t, PermutedCount, cub::CountingInputIterator<uint32_t>> counts_sorted(
+      cub::CountingInputIterator<uint32_t>(0), PermutedCount{tiles_touched, perm + BN});
+  DIMO_CHECK_CUDA(cub::DeviceScan::InclusiveSum(scan_temp, need, counts_sorted, offsets, (int)BN, st));
   if (R_host) {
     uint32_t last = 0;
     DIMO_CHECK_CUDA(cudaMemcpyAsync(&last, offsets + (BN - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -155,20 +179,21 @@ int dimo_raster_preprocess(int B, int N, int W, int H, int sh_degree, int sh_coe
 }
 
 int dimo_raster_bin(int B, int N, int W, int H, int64_t R, const float* splats, const int32_t* radii,
-                    const uint32_t* offsets, uint64_t* keys_unsorted, uint32_t* vals_unsorted,
-                    uint64_t* keys_sorted, uint32_t* vals_sorted, void* sort_temp, size_t sort_temp_bytes,
-                    float* packed, uint32_t* ranges, void* stream) {
+                    const uint32_t* perm_sorted, const uint32_t* offsets, uint32_t* keys_unsorted,
+                    uint32_t* vals_unsorted, uint32_t* keys_sorted, uint32_t* vals_sorted, void* sort_temp,
+                    size_t sort_temp_bytes, float* packed, uint32_t* ranges, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
   const int64_t ntiles = (int64_t)B * gx * gy;
   DIMO_REQUIRE(R < ((int64_t)1 << 31), "instance count must fit int32");
+  DIMO_REQUIRE(ntiles < ((int64_t)1 << 31), "B*tiles must fit int32");
   DIMO_CHECK_CUDA(cudaMemsetAsync(ranges, 0, sizeof(uint32_t) * 2 * ntiles, st));
   if (R == 0) return 0;
-  int rc = emit_keys_launch(B, N, W, H, R, splats, radii, offsets, keys_unsorted, vals_unsorted, st);
+  int rc = emit_keys_launch(B, N, W, H, R, splats, radii, perm_sorted, offsets, keys_unsorted, vals_unsorted, st);
   if (rc) return rc;
   size_t need = sort_temp_bytes;
   DIMO_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(sort_temp, need, keys_unsorted, keys_sorted, vals_unsorted,
-                                                  vals_sorted, (int)R, 0, key_bits(B, W, H), st));
+                                                  vals_sorted, (int)R, 0, bits_for(ntiles), st));
   pack_ranges_kernel<<<ceil_div(R * 4, 256), 256, 0, st>>>(R, keys_sorted, vals_sorted,
                                                            reinterpret_cast<const float4*>(splats),
                                                            reinterpret_cast<float4*>(packed),

@@ -358,11 +358,27 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_bwd_kernel(
           }
         }
       }
+      // Transposed butterfly: 16 value slots (13 used) reduced over 32 lanes with 8+4+2+1 exchange steps plus one
+      // final pair step = 16 shuffles (a plain per-value butterfly needs 13*5 = 65).  After it, lane l holds the
+      // warp total of slot (l >> 1) -> even lanes issue ONE vector shared-memory atomic.
+      {
+        float w16[16];
 #pragma unroll
-      for (int q = 0; q < NGRAD; ++q) v[q] = warp_sum(v[q]);
-      if (lane == 0) {
+        for (int q = 0; q < 16; ++q) w16[q] = q < NGRAD ? v[q] : 0.f;
 #pragma unroll
-        for (int q = 0; q < NGRAD; ++q) atomicAdd(&acc[j * NGRAD + q], v[q]);
+        for (int half = 8, m = 16; half >= 1; half >>= 1, m >>= 1) {
+          const bool upper = (lane & m) != 0;
+#pragma unroll
+          for (int q = 0; q < half; ++q) {
+            const float keep = upper ? w16[q + half] : w16[q];
+            const float send = upper ? w16[q] : w16[q + half];
+            w16[q] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+          }
+        }
+        // now w16[0] on lane l is the partial over lanes with equal bits 4..1 of slot ((l>>1)&15); fold bit 0
+        const float tot = w16[0] + __shfl_xor_sync(0xffffffffu, w16[0], 1);
+        const int slot = lane >> 1;
+        if ((lane & 1) == 0 && slot < NGRAD) atomicAdd(&acc[j * NGRAD + slot], tot);
       }
     }
     __syncthreads();   // all reads of sm[stage] (except gid below) and all smem atomics of this chunk are done

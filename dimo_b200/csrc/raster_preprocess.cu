@@ -195,7 +195,8 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
     const float* __restrict__ opacities, int64_t op_bs,
     const float* __restrict__ shs, int64_t shs_bs,
     const float* __restrict__ colors, int64_t col_bs,
-    float4* __restrict__ splats, int32_t* __restrict__ radii, uint32_t* __restrict__ tiles_touched) {
+    float4* __restrict__ splats, int32_t* __restrict__ radii, uint32_t* __restrict__ tiles_touched,
+    uint64_t* __restrict__ depth_keys) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)B * N) return;
   const int b = (int)(idx / N);
@@ -223,6 +224,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
   if (!visible) {
     radii[idx] = 0;
     tiles_touched[idx] = 0;
+    depth_keys[idx] = ~0ull;                 // culled splats sort to the end and emit nothing
     const float4 zz = make_float4(0.f, 0.f, 0.f, 0.f);
     out[0] = zz; out[1] = zz; out[2] = zz; out[3] = zz;
     return;
@@ -261,6 +263,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
 
   radii[idx] = (int)g.radius_f;
   tiles_touched[idx] = (uint32_t)ntiles;
+  depth_keys[idx] = ((uint64_t)b << 32) | (uint64_t)__float_as_uint(g.tvz);   // view depth > 0.2: bits order as uints
   out[0] = make_float4(g.pix_x, g.pix_y, g.conic_a, g.conic_b);
   out[1] = make_float4(g.conic_c, op, rgb[0], rgb[1]);
   out[2] = make_float4(rgb[2], g.tvz, nx, ny);
@@ -433,31 +436,39 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
   dL_dop[idx] = g_op;
 }
 
-// Emits, for every visible splat, one (tile | depth) key and its B*N index per covered tile.
-// Upstream shape: "duplicateWithKeys".  key = (frame*tiles + ty*gx + tx) << 32 | float_bits(depth).
+// Emits, for every visible splat, one (frame*tiles + tile) key and its B*N index per covered tile.
+// Upstream shape: "duplicateWithKeys", with one change: thread i handles the i-th splat of the (frame, depth,
+// index)-sorted order (`perm`), and `offsets` is the inclusive scan of tile counts in that order.  Instances
+// are therefore emitted front-to-back, and a STABLE sort by the tile id alone (raster_bin.cu) yields exactly
+// the order of a full (tile | depth) 64-bit sort -- ties in depth keep ascending Gaussian index.
 __global__ void __launch_bounds__(256) emit_keys_kernel(
     int64_t BN, int N, int W, int H, const float4* __restrict__ splats, const int32_t* __restrict__ radii,
-    const uint32_t* __restrict__ offsets, int64_t R, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= BN) return;
+    const uint32_t* __restrict__ perm, const uint32_t* __restrict__ offsets, int64_t R,
+    uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ vals) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= BN) return;
+  const uint32_t idx = perm[i];
   const int rad = radii[idx];
   if (rad <= 0) return;
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
-  const float4 s0 = splats[4 * idx + 0];
-  const float depth = splats[4 * idx + 2].y;
+  const float4 s0 = splats[4 * (int64_t)idx + 0];
   int x0, y0, x1, y1;
   tile_rect(s0.x, s0.y, (float)rad, gx, gy, x0, y0, x1, y1);
-  uint64_t off = idx == 0 ? 0 : offsets[idx - 1];
-  const uint64_t frame_base = (uint64_t)(idx / N) * (uint64_t)(gx * gy);
-  const uint32_t dbits = __float_as_uint(depth);
+  uint64_t off = i == 0 ? 0 : offsets[i - 1];
+  const uint32_t frame_base = (uint32_t)(idx / (uint32_t)N) * (uint32_t)(gx * gy);
   for (int ty = y0; ty < y1; ++ty)
     for (int tx = x0; tx < x1; ++tx) {
       if ((int64_t)off < R) {
-        keys[off] = ((frame_base + (uint64_t)(ty * gx + tx)) << 32) | dbits;
-        vals[off] = (uint32_t)idx;
+        tile_keys[off] = frame_base + (uint32_t)(ty * gx + tx);
+        vals[off] = idx;
       }
       ++off;
     }
+}
+
+__global__ void __launch_bounds__(256) iota_kernel(int64_t n, uint32_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (uint32_t)i;
 }
 
 }  // namespace dimo
@@ -469,23 +480,26 @@ int preprocess_launch(
     const float* means3D, int64_t means3D_bstride, const float* scales, int64_t scales_bstride,
     const float* rotations, int64_t rotations_bstride, const float* opacities, int64_t opacities_bstride,
     const float* shs, int64_t shs_bstride, const float* colors_precomp, int64_t colors_bstride,
-    float* splats, int32_t* radii, uint32_t* tiles_touched, cudaStream_t st) {
+    float* splats, int32_t* radii, uint32_t* tiles_touched, uint64_t* depth_keys, uint32_t* iota,
+    cudaStream_t st) {
   const int64_t BN = (int64_t)B * N;
   if (BN == 0) return 0;
+  iota_kernel<<<ceil_div(BN, 256), 256, 0, st>>>(BN, iota);
   preprocess_fwd_kernel<<<ceil_div(BN, 256), 256, 0, st>>>(
       B, N, W, H, sh_degree, sh_coeffs, scale_modifier, cams, means3D, means3D_bstride, scales, scales_bstride,
       rotations, rotations_bstride, opacities, opacities_bstride, shs, shs_bstride, colors_precomp, colors_bstride,
-      reinterpret_cast<float4*>(splats), radii, tiles_touched);
+      reinterpret_cast<float4*>(splats), radii, tiles_touched, depth_keys);
   DIMO_CHECK_LAUNCH();
   return 0;
 }
 
 int emit_keys_launch(int B, int N, int W, int H, int64_t R, const float* splats, const int32_t* radii,
-                     const uint32_t* offsets, uint64_t* keys, uint32_t* vals, cudaStream_t st) {
+                     const uint32_t* perm, const uint32_t* offsets, uint32_t* tile_keys, uint32_t* vals,
+                     cudaStream_t st) {
   const int64_t BN = (int64_t)B * N;
   if (BN == 0 || R == 0) return 0;
   emit_keys_kernel<<<ceil_div(BN, 256), 256, 0, st>>>(BN, N, W, H, reinterpret_cast<const float4*>(splats), radii,
-                                                      offsets, R, keys, vals);
+                                                      perm, offsets, R, tile_keys, vals);
   DIMO_CHECK_LAUNCH();
   return 0;
 }

@@ -43,7 +43,7 @@ def _bstride(t, B, per_frame_numel):
 
 class RasterState:
     """Buffers kept from forward for backward / inspection (all torch-owned)."""
-    __slots__ = ("B", "N", "W", "H", "R", "cams", "splats", "radii", "tiles_touched", "offsets", "keys_sorted",
+    __slots__ = ("B", "N", "W", "H", "R", "cams", "splats", "radii", "tiles_touched", "offsets", "perm", "keys_sorted",
                  "vals_sorted", "packed", "ranges", "final_T", "n_contrib", "sh_degree", "sh_coeffs",
                  "scale_modifier")
 
@@ -64,6 +64,9 @@ def _forward_impl(cams, means3D, scales, rotations, opacities, shs, colors_preco
     st.tiles_touched = torch.empty(BN, dtype=torch.int32, device=dev)
     st.offsets = torch.empty(BN, dtype=torch.int32, device=dev)
     L = _lib.lib()
+    depth_keys = torch.empty(2 * BN, dtype=torch.int64, device=dev)
+    perm2 = torch.empty(2 * BN, dtype=torch.int32, device=dev)
+    st.perm = perm2[BN:]
     scan_bytes = L.dimo_raster_scan_temp_bytes(BN)
     scan_temp = torch.empty(scan_bytes, dtype=torch.uint8, device=dev)
     import ctypes
@@ -77,21 +80,22 @@ def _forward_impl(cams, means3D, scales, rotations, opacities, shs, colors_preco
               _lib.ptr(shs), _bstride(shs, B, N * st.sh_coeffs * 3),
               _lib.ptr(colors_precomp), _bstride(colors_precomp, B, N * 3),
               _lib.ptr(st.splats), _lib.ptr(st.radii), _lib.ptr(st.tiles_touched), _lib.ptr(st.offsets),
-              _lib.ptr(scan_temp), scan_bytes, ctypes.addressof(R_host), s)
+              _lib.ptr(depth_keys), _lib.ptr(perm2), _lib.ptr(scan_temp), scan_bytes, ctypes.addressof(R_host), s)
     R = int(R_host.value)
     st.R = R
     _lib.PROFILE.extra["R"] = R
     gx, gy = (W + TILE - 1) // TILE, (H + TILE - 1) // TILE
     Ra = max(R, 1)
-    keys_u = torch.empty(Ra, dtype=torch.int64, device=dev)
+    keys_u = torch.empty(Ra, dtype=torch.int32, device=dev)
     vals_u = torch.empty(Ra, dtype=torch.int32, device=dev)
-    st.keys_sorted = torch.empty(Ra, dtype=torch.int64, device=dev)
+    st.keys_sorted = torch.empty(Ra, dtype=torch.int32, device=dev)        # frame*tiles + tile, sorted
     st.vals_sorted = torch.empty(Ra, dtype=torch.int32, device=dev)
     st.packed = torch.empty(Ra, SPLAT_FLOATS, **f32)
     st.ranges = torch.empty(B * gx * gy, 2, dtype=torch.int32, device=dev)
     sort_bytes = L.dimo_raster_sort_temp_bytes(Ra)
     sort_temp = torch.empty(sort_bytes, dtype=torch.uint8, device=dev)
-    _lib.call("dimo_raster_bin", B, N, W, H, R, _lib.ptr(st.splats), _lib.ptr(st.radii), _lib.ptr(st.offsets),
+    _lib.call("dimo_raster_bin", B, N, W, H, R, _lib.ptr(st.splats), _lib.ptr(st.radii), _lib.ptr(st.perm),
+              _lib.ptr(st.offsets),
               _lib.ptr(keys_u), _lib.ptr(vals_u), _lib.ptr(st.keys_sorted), _lib.ptr(st.vals_sorted),
               _lib.ptr(sort_temp), sort_bytes, _lib.ptr(st.packed), _lib.ptr(st.ranges), s)
     color = torch.empty(B, 3, H, W, **f32)

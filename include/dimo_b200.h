@@ -57,9 +57,13 @@ int         dimo_device_info(int* out3_host);
 size_t dimo_raster_scan_temp_bytes(int64_t BN);
 size_t dimo_raster_sort_temp_bytes(int64_t R);
 
-/* Stage 1: per-Gaussian projection + tile counting + inclusive scan.
- *   splats [B*N,16] f32, radii [B*N] i32, tiles_touched [B*N] u32, offsets [B*N] u32 (inclusive scan).
+/* Stage 1: per-Gaussian projection + tile counting, depth sort of the B*N splats, inclusive scan of the tile
+ * counts in (frame, depth, index) order.
+ *   splats [B*N,16] f32, radii [B*N] i32, tiles_touched [B*N] u32 (Gaussian order),
+ *   depth_keys [2*B*N] u64 scratch (unsorted | sorted), perm [2*B*N] u32 scratch: perm + B*N is the sorted
+ *   permutation (input of stage 2), offsets [B*N] u32 = inclusive scan in sorted order.
  *   shs [N,sh_coeffs,3] (or NULL) / colors_precomp [N,3] (or NULL): exactly one non-NULL.
+ *   temp: dimo_raster_scan_temp_bytes(B*N) bytes.
  *   R_host: if non-NULL the stream is synchronised and the total instance count is stored there. */
 int dimo_raster_preprocess(
     int B, int N, int W, int H, int sh_degree, int sh_coeffs, float scale_modifier,
@@ -71,15 +75,18 @@ int dimo_raster_preprocess(
     const float* shs, int64_t shs_bstride,
     const float* colors_precomp, int64_t colors_bstride,
     float* splats, int32_t* radii, uint32_t* tiles_touched, uint32_t* offsets,
+    uint64_t* depth_keys, uint32_t* perm,
     void* scan_temp, size_t scan_temp_bytes,
     int64_t* R_host, void* stream);
 
-/* Stage 2: emit (tile|depth) keys, sort, pack splats in sorted order, per-tile ranges.
- *   keys_* [R] u64, vals_* [R] u32 (index into B*N), packed [R,16] f32, ranges [B*tiles,2] u32. */
+/* Stage 2: emit (frame*tiles + tile) keys front-to-back, stable-sort by tile, pack blend records in sorted
+ * order, per-tile ranges.
+ *   perm_sorted [B*N] u32 (= perm + B*N of stage 1), keys_* [R] u32, vals_* [R] u32 (index into B*N),
+ *   packed [R,16] f32, ranges [B*tiles,2] u32; temp: dimo_raster_sort_temp_bytes(R) bytes. */
 int dimo_raster_bin(
     int B, int N, int W, int H, int64_t R,
-    const float* splats, const int32_t* radii, const uint32_t* offsets,
-    uint64_t* keys_unsorted, uint32_t* vals_unsorted, uint64_t* keys_sorted, uint32_t* vals_sorted,
+    const float* splats, const int32_t* radii, const uint32_t* perm_sorted, const uint32_t* offsets,
+    uint32_t* keys_unsorted, uint32_t* vals_unsorted, uint32_t* keys_sorted, uint32_t* vals_sorted,
     void* sort_temp, size_t sort_temp_bytes,
     float* packed, uint32_t* ranges, void* stream);
 

@@ -103,13 +103,15 @@ def test_raster_properties_full_size(cuda):
     s = st[0]
     R = s.R
     assert R == int(s.offsets[-1]) and R == int(s.tiles_touched.sum())
-    keys = s.keys_sorted[:R]
-    assert bool((keys[1:] >= keys[:-1]).all()), "keys not sorted"
+    keys = s.keys_sorted[:R].long()                    # frame*tiles + tile
+    assert bool((keys[1:] >= keys[:-1]).all()), "tile keys not sorted"
+    perm = s.perm.long()
+    assert torch.equal(torch.sort(perm).values, torch.arange(2 * N, device="cuda")), "perm is not a permutation"
     rng = s.ranges.long()
     nonempty = rng[:, 1] > rng[:, 0]
     starts, ends = rng[nonempty, 0], rng[nonempty, 1]
     assert int(starts[0]) == 0 and int(ends[-1]) == R and bool((starts[1:] == ends[:-1]).all())
-    tile_of_key = (keys >> 32)
+    tile_of_key = keys
     counts = torch.bincount(tile_of_key, minlength=rng.shape[0])
     assert torch.equal(counts, (rng[:, 1] - rng[:, 0]))
     depth_rec = s.packed[:R, 10]                       # blend record: depth
