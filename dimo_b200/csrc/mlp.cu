@@ -35,8 +35,10 @@ struct GemmArgs {
 // A_LC: A's contiguous dimension is l (else i).  B_LC: B's contiguous dimension is l (else j).
 template <bool A_LC, bool B_LC>
 __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs p) {
-  __shared__ float As[BK][BM + 4];
-  __shared__ float Bs[BK][BN + 4];
+  // double-buffered smem tiles; the next k-tile is prefetched from global into registers while the current one
+  // is consumed (one __syncthreads per k-tile)
+  __shared__ float As[2][BK][BM + 4];
+  __shared__ float Bs[2][BK][BN + 4];
   const int tid = threadIdx.x;
   const int i0 = blockIdx.x * BM, j0 = blockIdx.y * BN;
   const int l_begin = blockIdx.z * p.l_per_split;
@@ -50,37 +52,50 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs p) {
   float rsum[4] = {0.f, 0.f, 0.f, 0.f};
   const bool do_rowsum = p.rowsum != nullptr && blockIdx.y == 0;
 
-  for (int l0 = l_begin; l0 < l_end; l0 += BK) {
-    // ---- load A tile (BM x BK) ----
+  // per-thread element coordinates inside a tile (4 A elements + 4 B elements)
+  int a_ii[4], a_ll[4], b_jj[4], b_ll[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int lin = tid + e * 256;
+    if (A_LC) { a_ii[e] = lin / BK; a_ll[e] = lin % BK; } else { a_ll[e] = lin / BM; a_ii[e] = lin % BM; }
+    if (B_LC) { b_jj[e] = lin / BK; b_ll[e] = lin % BK; } else { b_ll[e] = lin / BN; b_jj[e] = lin % BN; }
+  }
+  float ra[4], rb[4];
+  auto fetch = [&](int l0) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const int lin = tid + e * 256;
-      int ii, ll;
-      if (A_LC) { ii = lin / BK; ll = lin % BK; } else { ll = lin / BM; ii = lin % BM; }
-      const int gi = i0 + ii, gl = l0 + ll;
+      const int gi = i0 + a_ii[e], gl = l0 + a_ll[e];
       float v = 0.f;
       if (gi < p.I && gl < l_end) {
         v = p.A[gi * p.sAi + gl * p.sAl];
         if (p.mask != nullptr && !(p.mask[gi * p.sMi + gl * p.sMl] > 0.f)) v = 0.f;
       }
-      As[ll][ii] = v;
+      ra[e] = v;
+      const int gj = j0 + b_jj[e], gl2 = l0 + b_ll[e];
+      rb[e] = (gj < p.J && gl2 < l_end) ? p.Bm[gl2 * p.sBl + gj * p.sBj] : 0.f;
     }
-    // ---- load B tile (BK x BN) ----
+  };
+  auto stash = [&](int buf) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const int lin = tid + e * 256;
-      int jj, ll;
-      if (B_LC) { jj = lin / BK; ll = lin % BK; } else { ll = lin / BN; jj = lin % BN; }
-      const int gj = j0 + jj, gl = l0 + ll;
-      float v = 0.f;
-      if (gj < p.J && gl < l_end) v = p.Bm[gl * p.sBl + gj * p.sBj];
-      Bs[ll][jj] = v;
+      As[buf][a_ll[e]][a_ii[e]] = ra[e];
+      Bs[buf][b_ll[e]][b_jj[e]] = rb[e];
     }
-    __syncthreads();
+  };
+
+  if (l_begin < l_end) {
+    fetch(l_begin);
+    stash(0);
+  }
+  __syncthreads();
+  int buf = 0;
+  for (int l0 = l_begin; l0 < l_end; l0 += BK) {
+    const bool more = l0 + BK < l_end;
+    if (more) fetch(l0 + BK);
 #pragma unroll
     for (int l = 0; l < BK; ++l) {
-      const float4 a4 = *reinterpret_cast<const float4*>(&As[l][ty * 4]);
-      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[l][tx * 4]);
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[buf][l][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][l][tx * 4]);
       const float a[4] = {a4.x, a4.y, a4.z, a4.w};
       const float b[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
@@ -92,7 +107,9 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs p) {
         for (int u = 0; u < 4; ++u) rsum[u] += a[u];
       }
     }
+    if (more) stash(buf ^ 1);
     __syncthreads();
+    buf ^= 1;
   }
 
 #pragma unroll
