@@ -29,6 +29,7 @@ SOURCES = {
     "knn.cu": ["-fmad=false"],
     "deform.cu": [],
     "mlp.cu": [],
+    "mlp_tc.cu": [],
     "ssim.cu": [],
 }
 

@@ -1,0 +1,282 @@
+// TimeNet linear layer on the 5th-generation tensor cores: Y = act(X * W^T + b) as a tcgen05 GEMM with
+// 3xTF32 error compensation (renderer/latent_gs_renderer.py:223-232 runs these layers as cuBLAS FP32 SGEMM; the
+// 1e-4 parity bound rules out plain TF32/BF16).
+//
+//   x = hi + lo  with hi = tf32(x), lo = tf32(x - hi)     (22 mantissa bits kept)
+//   X*W^T ~= Xhi*Whi^T + Xhi*Wlo^T + Xlo*Whi^T            (three kind::tf32 MMAs per k-step, FP32 accumulate in TMEM)
+//
+// One CTA (128 threads) owns a 128-row x 128-column output tile:
+//   * operands are split into hi/lo on the fly while they are copied global -> shared memory in the canonical
+//     K-major no-swizzle UMMA layout (8-row x 16-byte core matrices, 128 B each; LBO = 128 B between the K-chunks of
+//     a core-matrix row, SBO = 1024 B between 8-row groups);
+//   * two shared-memory stages of 32 K-elements; one elected thread issues 4 k-steps x 3 tcgen05.mma (M=128, N=128,
+//     K=8) per stage and commits them to an mbarrier, the other threads are already filling the next stage;
+//   * the accumulator lives in 128 TMEM columns; the epilogue reads it with tcgen05.ld (32 lanes x 32 columns per
+//     warp), adds the bias, applies ReLU / the accumulate option and writes rows with 128-bit stores.
+// The ReLU mask of the backward data-gradient (dX = (dY * [Y>0]) * W) is applied while loading the A operand.
+#include "common.cuh"
+
+namespace dimo {
+
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32;
+constexpr int TC_THREADS = 128;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;        // 16 KB (one of hi / lo)
+constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;        // 16 KB
+constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // 64 KB
+constexpr int TC_SMEM_BYTES = 2 * TC_STAGE_BYTES + 1024;          // + alignment slack
+
+// debug knobs (dimo_tc_debug_set): 0 = swap LBO/SBO in the shared-memory descriptors, 1 = single-pass TF32 (no compensation)
+static int h_tc_knob[4] = {0, 0, 0, 0};
+
+struct TcArgs {
+  int R, K, No;
+  const float* X; int64_t ldx;
+  const float* mask; int64_t ldm;     // optional: X(r,k) *= [mask(r,k) > 0]
+  const float* Wt;                    // [No, K] row-major (K contiguous)
+  const float* bias;
+  float* Y; int64_t ldy;
+  int relu, accumulate;
+  int swap_lbo_sbo, single_pass;
+};
+
+__device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+
+// byte offset of (row, 16-byte chunk) inside a [rows x 32 floats] canonical K-major tile
+__device__ __forceinline__ uint32_t canon_off(int row, int chunk) {
+  return (uint32_t)((((row >> 3) * (TC_BK / 4) + chunk) << 7) + ((row & 7) << 4));
+}
+
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);               // start address, bits [0,14)
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;     // leading dimension byte offset, bits [16,30)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;     // stride dimension byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                               // descriptor version 1 (Blackwell), bits [46,48)
+  // base_offset [49,52) = 0, lbo_mode [52] = 0, layout_type [61,64) = 0 (SWIZZLE_NONE)
+  return d;
+}
+
+// instruction descriptor for kind::tf32, FP32 accumulate, both operands K-major
+__device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(tc_smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
+      "%24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(TcArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t mma_bar[2];
+  __shared__ uint32_t tmem_slot;
+  // 1024-byte aligned operand area
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * TC_BN;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_slot)),
+                 "r"((uint32_t)TC_BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(&mma_bar[0])) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(&mma_bar[1])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = tmem_slot;
+
+  const uint32_t idesc = make_idesc_tf32(TC_BM, TC_BN);
+  const uint32_t lbo = p.swap_lbo_sbo ? 1024u : 128u, sbo = p.swap_lbo_sbo ? 128u : 1024u;
+  const int nk = (p.K + TC_BK - 1) / TC_BK;
+
+  for (int kt = 0; kt < nk; ++kt) {
+    const int s = kt & 1;
+    uint8_t* stage = smem + s * TC_STAGE_BYTES;
+    uint8_t* a_hi = stage, *a_lo = stage + TC_A_BYTES, *b_hi = stage + 2 * TC_A_BYTES,
+             *b_lo = stage + 2 * TC_A_BYTES + TC_B_BYTES;
+    if (kt >= 2) tc_mbar_wait(&mma_bar[s], (uint32_t)(((kt >> 1) - 1) & 1));   // MMAs of tile kt-2 have read this stage
+    const int k0 = kt * TC_BK;
+    // ---- fill: 128 rows x 8 chunks for A and for B; 8 consecutive threads read one 128-byte row segment ----
+#pragma unroll 4
+    for (int e = tid; e < TC_BM * (TC_BK / 4); e += TC_THREADS) {
+      const int row = e >> 3, chunk = e & 7;
+      const int gr = m0 + row, gk = k0 + chunk * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gr < p.R && gk < p.K) {
+        v = *reinterpret_cast<const float4*>(p.X + gr * p.ldx + gk);
+        if (p.mask != nullptr) {
+          const float4 m = *reinterpret_cast<const float4*>(p.mask + gr * p.ldm + gk);
+          if (!(m.x > 0.f)) v.x = 0.f;
+          if (!(m.y > 0.f)) v.y = 0.f;
+          if (!(m.z > 0.f)) v.z = 0.f;
+          if (!(m.w > 0.f)) v.w = 0.f;
+        }
+      }
+      uint4 hi = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+      uint4 lo = make_uint4(to_tf32(v.x - __uint_as_float(hi.x)), to_tf32(v.y - __uint_as_float(hi.y)),
+                            to_tf32(v.z - __uint_as_float(hi.z)), to_tf32(v.w - __uint_as_float(hi.w)));
+      const uint32_t off = canon_off(row, chunk);
+      *reinterpret_cast<uint4*>(a_hi + off) = hi;
+      *reinterpret_cast<uint4*>(a_lo + off) = lo;
+    }
+#pragma unroll 4
+    for (int e = tid; e < TC_BN * (TC_BK / 4); e += TC_THREADS) {
+      const int row = e >> 3, chunk = e & 7;
+      const int gn = n0 + row, gk = k0 + chunk * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gn < p.No && gk < p.K) v = *reinterpret_cast<const float4*>(p.Wt + (int64_t)gn * p.K + gk);
+      uint4 hi = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+      uint4 lo = make_uint4(to_tf32(v.x - __uint_as_float(hi.x)), to_tf32(v.y - __uint_as_float(hi.y)),
+                            to_tf32(v.z - __uint_as_float(hi.z)), to_tf32(v.w - __uint_as_float(hi.w)));
+      const uint32_t off = canon_off(row, chunk);
+      *reinterpret_cast<uint4*>(b_hi + off) = hi;
+      *reinterpret_cast<uint4*>(b_lo + off) = lo;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async-proxy (MMA) reads
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t sa_hi = tc_smem_u32(a_hi), sa_lo = tc_smem_u32(a_lo), sb_hi = tc_smem_u32(b_hi),
+                     sb_lo = tc_smem_u32(b_lo);
+#pragma unroll
+      for (int ks = 0; ks < TC_BK / 8; ++ks) {
+        const uint32_t koff = (uint32_t)ks * 256u;     // 8 tf32 = two 16-byte chunks = two 128-byte core-matrix blocks
+        const uint64_t dah = make_smem_desc(sa_hi + koff, lbo, sbo), dal = make_smem_desc(sa_lo + koff, lbo, sbo);
+        const uint64_t dbh = make_smem_desc(sb_hi + koff, lbo, sbo), dbl = make_smem_desc(sb_lo + koff, lbo, sbo);
+        tc_mma(tmem_d, dah, dbh, idesc, (kt > 0 || ks > 0) ? 1u : 0u);
+        if (!p.single_pass) {
+          tc_mma(tmem_d, dah, dbl, idesc, 1u);
+          tc_mma(tmem_d, dal, dbh, idesc, 1u);
+        }
+      }
+      tc_commit(&mma_bar[s]);
+    }
+  }
+  // all MMAs done <=> the last commit has arrived
+  {
+    const int last = nk - 1;
+    tc_mbar_wait(&mma_bar[last & 1], (uint32_t)((last >> 1) & 1));
+  }
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  // ---- epilogue: warp w owns TMEM lanes [32w, 32w+32) = output rows m0 + 32w + lane ----
+  const int row = m0 + warp * 32 + lane;
+#pragma unroll 1
+  for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+    uint32_t v[32];
+    tc_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+    if (row < p.R) {
+      float* yrow = p.Y + row * p.ldy + n0 + c0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const int gn = n0 + c0 + j;
+        if (gn >= p.No) break;
+        float o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float val = __uint_as_float(v[j + q]);
+          if (p.bias != nullptr && gn + q < p.No) val += p.bias[gn + q];
+          if (p.relu) val = fmaxf(val, 0.f);
+          o[q] = val;
+        }
+        const bool vec = (gn + 3 < p.No) && ((reinterpret_cast<uintptr_t>(yrow + j) & 15) == 0);
+        if (vec) {
+          float4 prev = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.accumulate) prev = *reinterpret_cast<float4*>(yrow + j);
+          *reinterpret_cast<float4*>(yrow + j) = make_float4(o[0] + prev.x, o[1] + prev.y, o[2] + prev.z, o[3] + prev.w);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (gn + q < p.No) yrow[j + q] = o[q] + (p.accumulate ? yrow[j + q] : 0.f);
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)TC_BN) : "memory");
+  }
+}
+
+}  // namespace dimo
+
+using namespace dimo;
+
+extern "C" int dimo_tc_debug_set(int key, int value) {
+  if (key < 0 || key >= 4) return -2;
+  h_tc_knob[key] = value;
+  return 0;
+}
+
+extern "C" int dimo_linear_tc(int R, int K, int No, const float* X, int64_t ldx, const float* mask, int64_t ldm,
+                              const float* Wt, const float* bias, float* Y, int64_t ldy, int relu, int accumulate,
+                              void* stream) {
+  if (R == 0 || No == 0) return 0;
+  DIMO_REQUIRE(K % 4 == 0 && ldx % 4 == 0, "tensor-core linear: K and ldx must be multiples of 4 floats");
+  DIMO_REQUIRE((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(Wt) & 15) == 0,
+               "tensor-core linear: X and W must be 16-byte aligned");
+  DIMO_REQUIRE(mask == nullptr || (ldm % 4 == 0 && (reinterpret_cast<uintptr_t>(mask) & 15) == 0),
+               "tensor-core linear: mask must be 16-byte aligned");
+  static bool attr_set = false;
+  if (!attr_set) {
+    DIMO_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    attr_set = true;
+  }
+  TcArgs p{};
+  p.R = R; p.K = K; p.No = No; p.X = X; p.ldx = ldx; p.mask = mask; p.ldm = ldm; p.Wt = Wt; p.bias = bias;
+  p.Y = Y; p.ldy = ldy; p.relu = relu; p.accumulate = accumulate;
+  p.swap_lbo_sbo = h_tc_knob[0]; p.single_pass = h_tc_knob[1];
+  dim3 grid(ceil_div(R, TC_BM), ceil_div(No, TC_BN));
+  linear_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(p);
+  DIMO_CHECK_LAUNCH();
+  return 0;
+}

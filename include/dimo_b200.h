@@ -146,6 +146,16 @@ int dimo_linear_bwd_data(int R, int K, int No, const float* dY, int64_t lddy, co
 int dimo_linear_bwd_weight(int R, int K, int No, const float* dY, int64_t lddy, const float* Y, int64_t ldy,
                            const float* X, int64_t ldx, float* dW, float* db, void* stream);
 
+/* Tensor-core (tcgen05, 3xTF32-compensated) variant of the fused linear layer:
+ *   Y[R,No] (=|+=) act( (X * [mask>0]) * W[No,K]^T + bias ).  mask may be NULL (same shape/stride rules as X, ldm);
+ *   K, ldx (and ldm) multiples of 4 floats, X/W/mask 16-byte aligned.  Used for TimeNet forward and, with the
+ *   transposed weights, for the data gradient. */
+int dimo_linear_tc(int R, int K, int No, const float* X, int64_t ldx, const float* mask, int64_t ldm,
+                   const float* Wt, const float* bias, float* Y, int64_t ldy, int relu, int accumulate,
+                   void* stream);
+/* bring-up knobs for the kernel above (0: swap LBO/SBO, 1: single-pass TF32); not part of the stable ABI */
+int dimo_tc_debug_set(int key, int value);
+
 /* TimeNet input embedding h0[R,104] = [posenc(x,10) | posenc(t,6) | latent]  (pos_enc.py:35-36,
  * latent_gs_renderer.py:223-225).  Row r belongs to group g = r / rows_per_group and reads
  * times[g], latents[g*L..].  pts [rows_per_group,3] shared by all groups. */

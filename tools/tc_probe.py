@@ -1,0 +1,60 @@
+#!/usr/bin/env python
+"""Bring-up probe for the tcgen05 linear kernel (csrc/mlp_tc.cu): runs on the GPU box, prints for each knob setting
+the error of random problems and where one-hot inputs land in the output (reveals descriptor/layout mistakes)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from dimo_b200 import _lib  # noqa: E402
+
+
+def linear_tc(X, W, b=None, relu=False, mask=None, acc=None):
+    R, K = X.shape
+    No = W.shape[0]
+    Y = torch.zeros(R, No, device="cuda") if acc is None else acc.clone()
+    _lib.call("dimo_linear_tc", R, K, No, _lib.ptr(X), X.stride(0), _lib.ptr(mask), 0 if mask is None else mask.stride(0),
+              _lib.ptr(W), _lib.ptr(b), _lib.ptr(Y), Y.stride(0), int(relu), int(acc is not None), _lib.stream())
+    torch.cuda.synchronize()
+    return Y
+
+
+def main():
+    torch.manual_seed(0)
+    for swap in (0, 1):
+        _lib.call("dimo_tc_debug_set", 0, swap)
+        for single in (0, 1):
+            _lib.call("dimo_tc_debug_set", 1, single)
+            for (R, K, No) in [(128, 32, 128), (128, 64, 128), (4096, 256, 256), (300, 104, 256)]:
+                X = torch.randn(R, K, device="cuda"); W = torch.randn(No, K, device="cuda") / K ** 0.5
+                Y = linear_tc(X, W)
+                ref = (X.double() @ W.double().t())
+                err = ((Y.double() - ref).abs().max() / ref.abs().max()).item()
+                print(f"swap={swap} single={single} R={R} K={K} No={No} rel_err={err:.3e} finite={bool(torch.isfinite(Y).all())}")
+        # one-hot placement probe, K = 32
+        _lib.call("dimo_tc_debug_set", 1, 1)
+        for (r0, k0, n0) in [(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1), (9, 5, 17), (100, 31, 127), (37, 12, 64)]:
+            X = torch.zeros(128, 32, device="cuda"); W = torch.zeros(128, 32, device="cuda")
+            X[r0, k0] = 1.0; W[n0, k0] = 2.0
+            Y = linear_tc(X, W)
+            nz = torch.nonzero(Y.abs() > 1e-3)
+            print(f"swap={swap} onehot r0={r0} k0={k0} n0={n0} -> nonzeros={nz[:6].tolist()} vals={[round(Y[i,j].item(),3) for i,j in nz[:6].tolist()]}")
+    _lib.call("dimo_tc_debug_set", 0, 0); _lib.call("dimo_tc_debug_set", 1, 0)
+    # epilogue options with the default knobs
+    X = torch.randn(1000, 256, device="cuda"); W = torch.randn(256, 256, device="cuda") / 16; b = torch.randn(256, device="cuda")
+    Ym = torch.randn(1000, 256, device="cuda")
+    Y = linear_tc(X, W, b, relu=True)
+    ref = torch.relu(X.double() @ W.double().t() + b.double())
+    print("bias+relu err", ((Y.double() - ref).abs().max() / ref.abs().max()).item())
+    acc0 = torch.randn(1000, 256, device="cuda")
+    Y = linear_tc(X, W, mask=Ym, acc=acc0)
+    ref = acc0.double() + (X.double() * (Ym > 0)) @ W.double().t()
+    print("mask+accumulate err", ((Y.double() - ref).abs().max() / ref.abs().max()).item())
+    Wh = torch.randn(3, 256, device="cuda")
+    Y = linear_tc(X, Wh)
+    print("No=3 err", ((Y.double() - X.double() @ Wh.double().t()).abs().max()).item())
+
+
+if __name__ == "__main__":
+    main()
