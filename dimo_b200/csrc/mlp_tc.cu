@@ -144,10 +144,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(TcArgs p) {
              *b_lo = stage + 2 * TC_A_BYTES + TC_B_BYTES;
     if (kt >= 2) tc_mbar_wait(&mma_bar[s], (uint32_t)(((kt >> 1) - 1) & 1));   // MMAs of tile kt-2 have read this stage
     const int k0 = kt * TC_BK;
-    // ---- fill: 128 rows x 8 chunks for A and for B; 8 consecutive threads read one 128-byte row segment ----
+    // ---- fill: 128 rows x 8 chunks for A and for B.  Lane mapping: each quarter-warp writes the 8 rows of ONE core
+    // matrix (128 contiguous bytes -> conflict-free STS.128); quarters 0/1 (2/3) take the two adjacent 16-byte chunks
+    // of the same rows, so every global request still covers full 32-byte sectors. ----
 #pragma unroll 4
     for (int e = tid; e < TC_BM * (TC_BK / 4); e += TC_THREADS) {
-      const int row = e >> 3, chunk = e & 7;
+      const int row = (((e >> 4) & 15) << 3) | (e & 7), chunk = ((e >> 8) << 1) | ((e >> 3) & 1);
       const int gr = m0 + row, gk = k0 + chunk * 4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (gr < p.R && gk < p.K) {
@@ -169,7 +171,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(TcArgs p) {
     }
 #pragma unroll 4
     for (int e = tid; e < TC_BN * (TC_BK / 4); e += TC_THREADS) {
-      const int row = e >> 3, chunk = e & 7;
+      const int row = (((e >> 4) & 15) << 3) | (e & 7), chunk = ((e >> 8) << 1) | ((e >> 3) & 1);
       const int gn = n0 + row, gk = k0 + chunk * 4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (gn < p.No && gk < p.K) v = *reinterpret_cast<const float4*>(p.Wt + (int64_t)gn * p.K + gk);
@@ -247,6 +249,167 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(TcArgs p) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Weight gradient  dW[n,k] += sum_r (dY[r,n] * [Y[r,n] > 0]) * X[r,k],  db[n] += sum_r dY[r,n] * [Y[r,n] > 0]
+// as D[M = n, N = k] with the reduction over rows r.  Both operands are MN-major (the non-reduction index is the
+// contiguous one in memory), canonical no-swizzle layout: core matrix = 8 reduction steps x 16 bytes (4 MN elements);
+// SBO = 128 B between the 16-byte column groups, one 8-step group per MMA (LBO unused within an instruction).
+// grid = (ceil(No/128), ceil(K/128), row splits); partial tiles are added to dW with fp32 atomics.
+// ---------------------------------------------------------------------------------------------------------------
+struct TcWgradArgs {
+  int R, K, No;
+  const float* dY; int64_t lddy;
+  const float* mask; int64_t ldm;
+  const float* X; int64_t ldx;
+  float* dW;   // [No, K]
+  float* db;   // [No] or NULL
+  int rows_per_split;
+  int single_pass;
+};
+
+__device__ __forceinline__ uint32_t make_idesc_tf32_mn(int M, int N) {
+  return make_idesc_tf32(M, N) | (1u << 15) | (1u << 16);   // a_major = b_major = MN
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(TcWgradArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t mma_bar[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float s_db[TC_BM];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.x * TC_BM, k0 = blockIdx.y * TC_BN;
+  const int r_begin = blockIdx.z * p.rows_per_split;
+  const int r_end = min(p.R, r_begin + p.rows_per_split);
+  const bool do_db = p.db != nullptr && blockIdx.y == 0;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_slot)),
+                 "r"((uint32_t)TC_BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(&mma_bar[0])) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(&mma_bar[1])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  s_db[tid] = 0.f;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = tmem_slot;
+  const uint32_t idesc = make_idesc_tf32_mn(TC_BM, TC_BN);
+  const int nrows = max(0, r_end - r_begin);
+  const int nk = (nrows + TC_BK - 1) / TC_BK;
+
+  float4 dbacc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dbacc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  for (int kt = 0; kt < nk; ++kt) {
+    const int s = kt & 1;
+    uint8_t* stage = smem + s * TC_STAGE_BYTES;
+    uint8_t* a_hi = stage, *a_lo = stage + TC_A_BYTES, *b_hi = stage + 2 * TC_A_BYTES,
+             *b_lo = stage + 2 * TC_A_BYTES + TC_B_BYTES;
+    if (kt >= 2) tc_mbar_wait(&mma_bar[s], (uint32_t)(((kt >> 1) - 1) & 1));
+    const int r0 = r_begin + kt * TC_BK;
+    // tile layout: k-group g (8 rows) at g*4096 B, 16-byte column group u at u*128 B, row (r & 7) at 16 B
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int e = tid + it * TC_THREADS;
+      const int rl = e & 7, u = (((e >> 6)) << 1) | ((e >> 3) & 1), g = (e >> 4) & 3;
+      const int gr = r0 + g * 8 + rl;
+      const uint32_t off = (uint32_t)(g * 4096 + u * 128 + rl * 16);
+      {   // A' = masked dY, columns n0 + 4u .. +3
+        const int gn = n0 + 4 * u;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gr < r_end && gn < p.No) {
+          v = *reinterpret_cast<const float4*>(p.dY + gr * p.lddy + gn);
+          if (p.mask != nullptr) {
+            const float4 m = *reinterpret_cast<const float4*>(p.mask + gr * p.ldm + gn);
+            if (!(m.x > 0.f)) v.x = 0.f;
+            if (!(m.y > 0.f)) v.y = 0.f;
+            if (!(m.z > 0.f)) v.z = 0.f;
+            if (!(m.w > 0.f)) v.w = 0.f;
+          }
+        }
+        dbacc[it].x += v.x; dbacc[it].y += v.y; dbacc[it].z += v.z; dbacc[it].w += v.w;
+        const uint4 hi = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+        const uint4 lo = make_uint4(to_tf32(v.x - __uint_as_float(hi.x)), to_tf32(v.y - __uint_as_float(hi.y)),
+                                    to_tf32(v.z - __uint_as_float(hi.z)), to_tf32(v.w - __uint_as_float(hi.w)));
+        *reinterpret_cast<uint4*>(a_hi + off) = hi;
+        *reinterpret_cast<uint4*>(a_lo + off) = lo;
+      }
+      {   // B' = X, columns k0 + 4u .. +3
+        const int gk = k0 + 4 * u;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gr < r_end && gk < p.K) v = *reinterpret_cast<const float4*>(p.X + gr * p.ldx + gk);
+        const uint4 hi = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+        const uint4 lo = make_uint4(to_tf32(v.x - __uint_as_float(hi.x)), to_tf32(v.y - __uint_as_float(hi.y)),
+                                    to_tf32(v.z - __uint_as_float(hi.z)), to_tf32(v.w - __uint_as_float(hi.w)));
+        *reinterpret_cast<uint4*>(b_hi + off) = hi;
+        *reinterpret_cast<uint4*>(b_lo + off) = lo;
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t sa_hi = tc_smem_u32(a_hi), sa_lo = tc_smem_u32(a_lo), sb_hi = tc_smem_u32(b_hi),
+                     sb_lo = tc_smem_u32(b_lo);
+#pragma unroll
+      for (int ks = 0; ks < TC_BK / 8; ++ks) {
+        const uint32_t koff = (uint32_t)ks * 4096u;
+        const uint64_t dah = make_smem_desc(sa_hi + koff, 4096u, 128u), dal = make_smem_desc(sa_lo + koff, 4096u, 128u);
+        const uint64_t dbh = make_smem_desc(sb_hi + koff, 4096u, 128u), dbl = make_smem_desc(sb_lo + koff, 4096u, 128u);
+        tc_mma(tmem_d, dah, dbh, idesc, (kt > 0 || ks > 0) ? 1u : 0u);
+        if (!p.single_pass) {
+          tc_mma(tmem_d, dah, dbl, idesc, 1u);
+          tc_mma(tmem_d, dal, dbh, idesc, 1u);
+        }
+      }
+      tc_commit(&mma_bar[s]);
+    }
+  }
+  if (nk > 0) {
+    const int last = nk - 1;
+    tc_mbar_wait(&mma_bar[last & 1], (uint32_t)((last >> 1) & 1));
+  }
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  if (nk > 0) {
+    const int nrow = n0 + warp * 32 + lane;          // output row = weight row n
+#pragma unroll 1
+    for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+      uint32_t v[32];
+      tc_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      if (nrow < p.No) {
+        float* wrow = p.dW + (int64_t)nrow * p.K + k0 + c0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (k0 + c0 + j < p.K) atomicAdd(wrow + j, __uint_as_float(v[j]));
+      }
+    }
+    if (do_db) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int e = tid + it * TC_THREADS;
+        const int u = (((e >> 6)) << 1) | ((e >> 3) & 1);
+        atomicAdd(&s_db[4 * u + 0], dbacc[it].x); atomicAdd(&s_db[4 * u + 1], dbacc[it].y);
+        atomicAdd(&s_db[4 * u + 2], dbacc[it].z); atomicAdd(&s_db[4 * u + 3], dbacc[it].w);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (do_db && nk > 0 && n0 + tid < p.No) atomicAdd(p.db + n0 + tid, s_db[tid]);
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)TC_BN) : "memory");
+  }
+}
+
 }  // namespace dimo
 
 using namespace dimo;
@@ -277,6 +440,33 @@ extern "C" int dimo_linear_tc(int R, int K, int No, const float* X, int64_t ldx,
   p.swap_lbo_sbo = h_tc_knob[0]; p.single_pass = h_tc_knob[1];
   dim3 grid(ceil_div(R, TC_BM), ceil_div(No, TC_BN));
   linear_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(p);
+  DIMO_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dimo_linear_wgrad_tc(int R, int K, int No, const float* dY, int64_t lddy, const float* mask, int64_t ldm,
+                                    const float* X, int64_t ldx, float* dW, float* db, void* stream) {
+  if (R == 0 || No == 0 || K == 0) return 0;
+  DIMO_REQUIRE(No % 4 == 0 && K % 4 == 0 && lddy % 4 == 0 && ldx % 4 == 0,
+               "tensor-core wgrad: No, K, lddy, ldx must be multiples of 4 floats");
+  DIMO_REQUIRE((reinterpret_cast<uintptr_t>(dY) & 15) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0,
+               "tensor-core wgrad: dY and X must be 16-byte aligned");
+  DIMO_REQUIRE(mask == nullptr || (ldm % 4 == 0 && (reinterpret_cast<uintptr_t>(mask) & 15) == 0),
+               "tensor-core wgrad: mask must be 16-byte aligned");
+  static bool attr_set = false;
+  if (!attr_set) {
+    DIMO_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    attr_set = true;
+  }
+  TcWgradArgs p{};
+  p.R = R; p.K = K; p.No = No; p.dY = dY; p.lddy = lddy; p.mask = mask; p.ldm = ldm; p.X = X; p.ldx = ldx;
+  p.dW = dW; p.db = db; p.single_pass = h_tc_knob[1];
+  const int tiles = ceil_div(No, TC_BM) * ceil_div(K, TC_BN);
+  int splits = max(1, min(ceil_div(R, 2 * TC_BK), ceil_div(148, tiles)));
+  p.rows_per_split = ceil_div(ceil_div(R, splits), TC_BK) * TC_BK;
+  splits = ceil_div(R, p.rows_per_split);
+  dim3 grid(ceil_div(No, TC_BM), ceil_div(K, TC_BN), splits);
+  wgrad_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(p);
   DIMO_CHECK_LAUNCH();
   return 0;
 }

@@ -5,6 +5,8 @@ linear-blend skinning, batched over the G unique (motion, t) pairs of a step.
 184-203: deformnet.{0..7}, pts_layers.{0,2}, rot_layers.{0,2}) so released `timenet.pth` checkpoints
 load unchanged; its forward runs libdimo_b200 kernels through `_TimeNetFn` instead of F.linear.
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.init as init
@@ -13,9 +15,16 @@ from . import _lib
 
 PTS_FREQS, TIME_FREQS, HIDDEN, DEPTH, SKIP_AFTER = 10, 6, 256, 8, 4
 
+# TimeNet GEMMs run on the tcgen05 tensor cores (3xTF32-compensated, csrc/mlp_tc.cu); DIMO_TC=0 selects the FP32
+# SIMT kernels (csrc/mlp.cu) for A/B comparison.  Both are hand-written kernels of this library.
+USE_TC = os.environ.get("DIMO_TC", "1") != "0"
+
 
 def _linear_fwd(R, K, No, X, ldx, W, b, Y, ldy, relu, s):
-    _lib.call("dimo_linear_fwd", R, K, No, X, ldx, _lib.ptr(W), _lib.ptr(b), Y, ldy, int(relu), s)
+    if USE_TC and K % 4 == 0 and ldx % 4 == 0:
+        _lib.call("dimo_linear_tc", R, K, No, X, ldx, None, 0, _lib.ptr(W), _lib.ptr(b), Y, ldy, int(relu), 0, s)
+    else:
+        _lib.call("dimo_linear_fwd", R, K, No, X, ldx, _lib.ptr(W), _lib.ptr(b), Y, ldy, int(relu), s)
 
 
 class _TimeNetFn(torch.autograd.Function):
@@ -84,12 +93,27 @@ class _TimeNetFn(torch.autograd.Function):
         dWs = [torch.zeros_like(W) for W in Ws]
         dbs = [torch.zeros(W.shape[0], **f32) for W in Ws]
 
+        keep = []    # transposed weights must outlive the asynchronous launches that read them
+
         def bwd_layer(li, K, No, dY_ptr, lddy, Y_ptr, ldy, X_ptr, ldx, dX_ptr, lddx, accumulate):
-            _lib.call("dimo_linear_bwd_weight", R, K, No, dY_ptr, lddy, Y_ptr, ldy, X_ptr, ldx,
-                      _lib.ptr(dWs[li]), _lib.ptr(dbs[li]), s)
+            if USE_TC and No % 4 == 0 and K % 4 == 0 and lddy % 4 == 0 and ldx % 4 == 0 and \
+                    (Y_ptr is None or ldy % 4 == 0):
+                _lib.call("dimo_linear_wgrad_tc", R, K, No, dY_ptr, lddy, Y_ptr, ldy if Y_ptr is not None else 0,
+                          X_ptr, ldx, _lib.ptr(dWs[li]), _lib.ptr(dbs[li]), s)
+            else:
+                _lib.call("dimo_linear_bwd_weight", R, K, No, dY_ptr, lddy, Y_ptr, ldy, X_ptr, ldx,
+                          _lib.ptr(dWs[li]), _lib.ptr(dbs[li]), s)
             if dX_ptr is not None:
-                _lib.call("dimo_linear_bwd_data", R, K, No, dY_ptr, lddy, Y_ptr, ldy, _lib.ptr(Ws[li]), dX_ptr, lddx,
-                          int(accumulate), s)
+                if USE_TC and No % 4 == 0 and lddy % 4 == 0 and (Y_ptr is None or ldy % 4 == 0):
+                    # dX[R,K] = (dY * [Y>0]) [R,No] * W[No,K]: same kernel with the transposed weight as the
+                    # "[N_out, K_red]" operand (reduction over No)
+                    Wt = Ws[li].t().contiguous()
+                    keep.append(Wt)
+                    _lib.call("dimo_linear_tc", R, No, K, dY_ptr, lddy, Y_ptr, ldy if Y_ptr is not None else 0,
+                              _lib.ptr(Wt), None, dX_ptr, lddx, 0, int(accumulate), s)
+                else:
+                    _lib.call("dimo_linear_bwd_data", R, K, No, dY_ptr, lddy, Y_ptr, ldy, _lib.ptr(Ws[li]), dX_ptr,
+                              lddx, int(accumulate), s)
 
         h = acts[DEPTH - 1]
         dhp = torch.empty(R, HIDDEN, **f32)

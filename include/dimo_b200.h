@@ -153,7 +153,11 @@ int dimo_linear_bwd_weight(int R, int K, int No, const float* dY, int64_t lddy, 
 int dimo_linear_tc(int R, int K, int No, const float* X, int64_t ldx, const float* mask, int64_t ldm,
                    const float* Wt, const float* bias, float* Y, int64_t ldy, int relu, int accumulate,
                    void* stream);
-/* bring-up knobs for the kernel above (0: swap LBO/SBO, 1: single-pass TF32); not part of the stable ABI */
+/* Tensor-core weight gradient: dW[No,K] += (dY * [mask>0])^T * X, db[No] += column sums of (dY * [mask>0]);
+ *   No, K, lddy, ldx (ldm) multiples of 4 floats; 16-byte aligned operands.  dW/db accumulate (caller zeroes). */
+int dimo_linear_wgrad_tc(int R, int K, int No, const float* dY, int64_t lddy, const float* mask, int64_t ldm,
+                         const float* X, int64_t ldx, float* dW, float* db, void* stream);
+/* bring-up knobs for the kernels above (0: swap LBO/SBO, 1: single-pass TF32); not part of the stable ABI */
 int dimo_tc_debug_set(int key, int value);
 
 /* TimeNet input embedding h0[R,104] = [posenc(x,10) | posenc(t,6) | latent]  (pos_enc.py:35-36,

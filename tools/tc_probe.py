@@ -51,6 +51,17 @@ def main():
     Y = linear_tc(X, W, mask=Ym, acc=acc0)
     ref = acc0.double() + (X.double() * (Ym > 0)) @ W.double().t()
     print("mask+accumulate err", ((Y.double() - ref).abs().max() / ref.abs().max()).item())
+    # weight gradient (MN-major operands)
+    for (R, K, No) in [(128, 128, 128), (4096, 256, 256), (4096, 360, 256), (4096, 104, 256), (1000, 256, 256)]:
+        dY = torch.randn(R, No, device="cuda"); Yk = torch.randn(R, No, device="cuda"); Xk = torch.randn(R, K, device="cuda")
+        dW = torch.zeros(No, K, device="cuda"); db = torch.zeros(No, device="cuda")
+        _lib.call("dimo_linear_wgrad_tc", R, K, No, _lib.ptr(dY), No, _lib.ptr(Yk), No, _lib.ptr(Xk), K, _lib.ptr(dW),
+                  _lib.ptr(db), _lib.stream())
+        torch.cuda.synchronize()
+        dYm = dY.double() * (Yk > 0)
+        rW = dYm.t() @ Xk.double(); rb = dYm.sum(0)
+        print(f"wgrad R={R} K={K} No={No} dW err {((dW.double()-rW).abs().max()/rW.abs().max()).item():.3e} "
+              f"db err {((db.double()-rb).abs().max()/rb.abs().max()).item():.3e}")
     Wh = torch.randn(3, 256, device="cuda")
     Y = linear_tc(X, Wh)
     print("No=3 err", ((Y.double() - X.double() @ Wh.double().t()).abs().max()).item())
