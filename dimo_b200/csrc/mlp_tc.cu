@@ -146,41 +146,55 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(TcArgs p) {
     const int k0 = kt * TC_BK;
     // ---- fill: 128 rows x 8 chunks for A and for B.  Lane mapping: each quarter-warp writes the 8 rows of ONE core
     // matrix (128 contiguous bytes -> conflict-free STS.128); quarters 0/1 (2/3) take the two adjacent 16-byte chunks
-    // of the same rows, so every global request still covers full 32-byte sectors. ----
-#pragma unroll 4
-    for (int e = tid; e < TC_BM * (TC_BK / 4); e += TC_THREADS) {
+    // of the same rows, so every global request still covers full 32-byte sectors.  All 16 loads of the stage are
+    // issued before any conversion so that each thread keeps 16 x 16 B in flight (the tiles come from L2). ----
+    float4 va[8], vb[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int e = tid + it * TC_THREADS;
       const int row = (((e >> 4) & 15) << 3) | (e & 7), chunk = ((e >> 8) << 1) | ((e >> 3) & 1);
-      const int gr = m0 + row, gk = k0 + chunk * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (gr < p.R && gk < p.K) {
-        v = *reinterpret_cast<const float4*>(p.X + gr * p.ldx + gk);
-        if (p.mask != nullptr) {
+      const int gr = m0 + row, gn = n0 + row, gk = k0 + chunk * 4;
+      va[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      vb[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gr < p.R && gk < p.K) va[it] = *reinterpret_cast<const float4*>(p.X + gr * p.ldx + gk);
+      if (gn < p.No && gk < p.K) vb[it] = *reinterpret_cast<const float4*>(p.Wt + (int64_t)gn * p.K + gk);
+    }
+    if (p.mask != nullptr) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int e = tid + it * TC_THREADS;
+        const int row = (((e >> 4) & 15) << 3) | (e & 7), chunk = ((e >> 8) << 1) | ((e >> 3) & 1);
+        const int gr = m0 + row, gk = k0 + chunk * 4;
+        if (gr < p.R && gk < p.K) {
           const float4 m = *reinterpret_cast<const float4*>(p.mask + gr * p.ldm + gk);
-          if (!(m.x > 0.f)) v.x = 0.f;
-          if (!(m.y > 0.f)) v.y = 0.f;
-          if (!(m.z > 0.f)) v.z = 0.f;
-          if (!(m.w > 0.f)) v.w = 0.f;
+          if (!(m.x > 0.f)) va[it].x = 0.f;
+          if (!(m.y > 0.f)) va[it].y = 0.f;
+          if (!(m.z > 0.f)) va[it].z = 0.f;
+          if (!(m.w > 0.f)) va[it].w = 0.f;
         }
       }
-      uint4 hi = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
-      uint4 lo = make_uint4(to_tf32(v.x - __uint_as_float(hi.x)), to_tf32(v.y - __uint_as_float(hi.y)),
-                            to_tf32(v.z - __uint_as_float(hi.z)), to_tf32(v.w - __uint_as_float(hi.w)));
-      const uint32_t off = canon_off(row, chunk);
-      *reinterpret_cast<uint4*>(a_hi + off) = hi;
-      *reinterpret_cast<uint4*>(a_lo + off) = lo;
     }
-#pragma unroll 4
-    for (int e = tid; e < TC_BN * (TC_BK / 4); e += TC_THREADS) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int e = tid + it * TC_THREADS;
       const int row = (((e >> 4) & 15) << 3) | (e & 7), chunk = ((e >> 8) << 1) | ((e >> 3) & 1);
-      const int gn = n0 + row, gk = k0 + chunk * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (gn < p.No && gk < p.K) v = *reinterpret_cast<const float4*>(p.Wt + (int64_t)gn * p.K + gk);
-      uint4 hi = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
-      uint4 lo = make_uint4(to_tf32(v.x - __uint_as_float(hi.x)), to_tf32(v.y - __uint_as_float(hi.y)),
-                            to_tf32(v.z - __uint_as_float(hi.z)), to_tf32(v.w - __uint_as_float(hi.w)));
       const uint32_t off = canon_off(row, chunk);
-      *reinterpret_cast<uint4*>(b_hi + off) = hi;
-      *reinterpret_cast<uint4*>(b_lo + off) = lo;
+      {
+        const float4 v = va[it];
+        const uint4 hi = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+        const uint4 lo = make_uint4(to_tf32(v.x - __uint_as_float(hi.x)), to_tf32(v.y - __uint_as_float(hi.y)),
+                                    to_tf32(v.z - __uint_as_float(hi.z)), to_tf32(v.w - __uint_as_float(hi.w)));
+        *reinterpret_cast<uint4*>(a_hi + off) = hi;
+        *reinterpret_cast<uint4*>(a_lo + off) = lo;
+      }
+      {
+        const float4 v = vb[it];
+        const uint4 hi = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+        const uint4 lo = make_uint4(to_tf32(v.x - __uint_as_float(hi.x)), to_tf32(v.y - __uint_as_float(hi.y)),
+                                    to_tf32(v.z - __uint_as_float(hi.z)), to_tf32(v.w - __uint_as_float(hi.w)));
+        *reinterpret_cast<uint4*>(b_hi + off) = hi;
+        *reinterpret_cast<uint4*>(b_lo + off) = lo;
+      }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async-proxy (MMA) reads
     __syncthreads();
@@ -252,9 +266,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(TcArgs p) {
 
 // ---------------------------------------------------------------------------------------------------------------
 // Weight gradient  dW[n,k] += sum_r (dY[r,n] * [Y[r,n] > 0]) * X[r,k],  db[n] += sum_r dY[r,n] * [Y[r,n] > 0]
-// as D[M = n, N = k] with the reduction over rows r.  Both operands are MN-major (the non-reduction index is the
-// contiguous one in memory), canonical no-swizzle layout: core matrix = 8 reduction steps x 16 bytes (4 MN elements);
-// SBO = 128 B between the 16-byte column groups, one 8-step group per MMA (LBO unused within an instruction).
+// as D[M = n, N = k] with the reduction over rows r.  In memory both operands have the NON-reduction index
+// contiguous (dY[r][n], X[r][k]); every thread transposes 4x4 blocks in registers while filling shared memory, so the
+// tensor core sees the same K-major canonical layout as the forward kernel (reduction index r = UMMA K).
 // grid = (ceil(No/128), ceil(K/128), row splits); partial tiles are added to dW with fp32 atomics.
 // ---------------------------------------------------------------------------------------------------------------
 struct TcWgradArgs {
@@ -267,10 +281,6 @@ struct TcWgradArgs {
   int rows_per_split;
   int single_pass;
 };
-
-__device__ __forceinline__ uint32_t make_idesc_tf32_mn(int M, int N) {
-  return make_idesc_tf32(M, N) | (1u << 15) | (1u << 16);   // a_major = b_major = MN
-}
 
 __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(TcWgradArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -300,13 +310,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(TcWgradArgs p) 
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = tmem_slot;
-  const uint32_t idesc = make_idesc_tf32_mn(TC_BM, TC_BN);
+  const uint32_t idesc = make_idesc_tf32(TC_BM, TC_BN);
   const int nrows = max(0, r_end - r_begin);
   const int nk = (nrows + TC_BK - 1) / TC_BK;
 
-  float4 dbacc[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) dbacc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 dbacc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const uint32_t lbo = 128u, sbo = 1024u;
 
   for (int kt = 0; kt < nk; ++kt) {
     const int s = kt & 1;
@@ -315,42 +324,68 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(TcWgradArgs p) 
              *b_lo = stage + 2 * TC_A_BYTES + TC_B_BYTES;
     if (kt >= 2) tc_mbar_wait(&mma_bar[s], (uint32_t)(((kt >> 1) - 1) & 1));
     const int r0 = r_begin + kt * TC_BK;
-    // tile layout: k-group g (8 rows) at g*4096 B, 16-byte column group u at u*128 B, row (r & 7) at 16 B
+    // item = (column group u of 4 columns, row chunk c of 4 rows): 32 x 8 items, 2 per thread (same u, c and c+4)
+    const int u = tid & 31;
+    float4 va[2][4], vb[2][4];
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int e = tid + it * TC_THREADS;
-      const int rl = e & 7, u = (((e >> 6)) << 1) | ((e >> 3) & 1), g = (e >> 4) & 3;
-      const int gr = r0 + g * 8 + rl;
-      const uint32_t off = (uint32_t)(g * 4096 + u * 128 + rl * 16);
-      {   // A' = masked dY, columns n0 + 4u .. +3
-        const int gn = n0 + 4 * u;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gr < r_end && gn < p.No) {
-          v = *reinterpret_cast<const float4*>(p.dY + gr * p.lddy + gn);
-          if (p.mask != nullptr) {
+    for (int it = 0; it < 2; ++it) {
+      const int c = (tid >> 5) + 4 * it;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int gr = r0 + 4 * c + j;
+        const int gn = n0 + 4 * u, gk = k0 + 4 * u;
+        va[it][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        vb[it][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gr < r_end && gn < p.No) va[it][j] = *reinterpret_cast<const float4*>(p.dY + gr * p.lddy + gn);
+        if (gr < r_end && gk < p.K) vb[it][j] = *reinterpret_cast<const float4*>(p.X + gr * p.ldx + gk);
+      }
+    }
+    if (p.mask != nullptr) {
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int c = (tid >> 5) + 4 * it;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int gr = r0 + 4 * c + j, gn = n0 + 4 * u;
+          if (gr < r_end && gn < p.No) {
             const float4 m = *reinterpret_cast<const float4*>(p.mask + gr * p.ldm + gn);
-            if (!(m.x > 0.f)) v.x = 0.f;
-            if (!(m.y > 0.f)) v.y = 0.f;
-            if (!(m.z > 0.f)) v.z = 0.f;
-            if (!(m.w > 0.f)) v.w = 0.f;
+            if (!(m.x > 0.f)) va[it][j].x = 0.f;
+            if (!(m.y > 0.f)) va[it][j].y = 0.f;
+            if (!(m.z > 0.f)) va[it][j].z = 0.f;
+            if (!(m.w > 0.f)) va[it][j].w = 0.f;
           }
         }
-        dbacc[it].x += v.x; dbacc[it].y += v.y; dbacc[it].z += v.z; dbacc[it].w += v.w;
-        const uint4 hi = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
-        const uint4 lo = make_uint4(to_tf32(v.x - __uint_as_float(hi.x)), to_tf32(v.y - __uint_as_float(hi.y)),
-                                    to_tf32(v.z - __uint_as_float(hi.z)), to_tf32(v.w - __uint_as_float(hi.w)));
-        *reinterpret_cast<uint4*>(a_hi + off) = hi;
-        *reinterpret_cast<uint4*>(a_lo + off) = lo;
       }
-      {   // B' = X, columns k0 + 4u .. +3
-        const int gk = k0 + 4 * u;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gr < r_end && gk < p.K) v = *reinterpret_cast<const float4*>(p.X + gr * p.ldx + gk);
-        const uint4 hi = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
-        const uint4 lo = make_uint4(to_tf32(v.x - __uint_as_float(hi.x)), to_tf32(v.y - __uint_as_float(hi.y)),
-                                    to_tf32(v.z - __uint_as_float(hi.z)), to_tf32(v.w - __uint_as_float(hi.w)));
-        *reinterpret_cast<uint4*>(b_hi + off) = hi;
-        *reinterpret_cast<uint4*>(b_lo + off) = lo;
+    }
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int c = (tid >> 5) + 4 * it;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        dbacc.x += va[it][j].x; dbacc.y += va[it][j].y; dbacc.z += va[it][j].z; dbacc.w += va[it][j].w;
+      }
+      // transposed 4x4 blocks: output row (4u + i) holds rows r..r+3 of column i
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float a0 = i == 0 ? va[it][0].x : i == 1 ? va[it][0].y : i == 2 ? va[it][0].z : va[it][0].w;
+        const float a1 = i == 0 ? va[it][1].x : i == 1 ? va[it][1].y : i == 2 ? va[it][1].z : va[it][1].w;
+        const float a2 = i == 0 ? va[it][2].x : i == 1 ? va[it][2].y : i == 2 ? va[it][2].z : va[it][2].w;
+        const float a3 = i == 0 ? va[it][3].x : i == 1 ? va[it][3].y : i == 2 ? va[it][3].z : va[it][3].w;
+        const float b0 = i == 0 ? vb[it][0].x : i == 1 ? vb[it][0].y : i == 2 ? vb[it][0].z : vb[it][0].w;
+        const float b1 = i == 0 ? vb[it][1].x : i == 1 ? vb[it][1].y : i == 2 ? vb[it][1].z : vb[it][1].w;
+        const float b2 = i == 0 ? vb[it][2].x : i == 1 ? vb[it][2].y : i == 2 ? vb[it][2].z : vb[it][2].w;
+        const float b3 = i == 0 ? vb[it][3].x : i == 1 ? vb[it][3].y : i == 2 ? vb[it][3].z : vb[it][3].w;
+        const uint32_t off = canon_off(4 * u + i, c);
+        const uint4 ah = make_uint4(to_tf32(a0), to_tf32(a1), to_tf32(a2), to_tf32(a3));
+        const uint4 al = make_uint4(to_tf32(a0 - __uint_as_float(ah.x)), to_tf32(a1 - __uint_as_float(ah.y)),
+                                    to_tf32(a2 - __uint_as_float(ah.z)), to_tf32(a3 - __uint_as_float(ah.w)));
+        const uint4 bh = make_uint4(to_tf32(b0), to_tf32(b1), to_tf32(b2), to_tf32(b3));
+        const uint4 bl = make_uint4(to_tf32(b0 - __uint_as_float(bh.x)), to_tf32(b1 - __uint_as_float(bh.y)),
+                                    to_tf32(b2 - __uint_as_float(bh.z)), to_tf32(b3 - __uint_as_float(bh.w)));
+        *reinterpret_cast<uint4*>(a_hi + off) = ah;
+        *reinterpret_cast<uint4*>(a_lo + off) = al;
+        *reinterpret_cast<uint4*>(b_hi + off) = bh;
+        *reinterpret_cast<uint4*>(b_lo + off) = bl;
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -361,9 +396,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(TcWgradArgs p) 
                      sb_lo = tc_smem_u32(b_lo);
 #pragma unroll
       for (int ks = 0; ks < TC_BK / 8; ++ks) {
-        const uint32_t koff = (uint32_t)ks * 4096u;
-        const uint64_t dah = make_smem_desc(sa_hi + koff, 4096u, 128u), dal = make_smem_desc(sa_lo + koff, 4096u, 128u);
-        const uint64_t dbh = make_smem_desc(sb_hi + koff, 4096u, 128u), dbl = make_smem_desc(sb_lo + koff, 4096u, 128u);
+        const uint32_t koff = (uint32_t)ks * 256u;
+        const uint64_t dah = make_smem_desc(sa_hi + koff, lbo, sbo), dal = make_smem_desc(sa_lo + koff, lbo, sbo);
+        const uint64_t dbh = make_smem_desc(sb_hi + koff, lbo, sbo), dbl = make_smem_desc(sb_lo + koff, lbo, sbo);
         tc_mma(tmem_d, dah, dbh, idesc, (kt > 0 || ks > 0) ? 1u : 0u);
         if (!p.single_pass) {
           tc_mma(tmem_d, dah, dbl, idesc, 1u);
@@ -393,13 +428,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(TcWgradArgs p) 
       }
     }
     if (do_db) {
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int e = tid + it * TC_THREADS;
-        const int u = (((e >> 6)) << 1) | ((e >> 3) & 1);
-        atomicAdd(&s_db[4 * u + 0], dbacc[it].x); atomicAdd(&s_db[4 * u + 1], dbacc[it].y);
-        atomicAdd(&s_db[4 * u + 2], dbacc[it].z); atomicAdd(&s_db[4 * u + 3], dbacc[it].w);
-      }
+      const int u = tid & 31;
+      atomicAdd(&s_db[4 * u + 0], dbacc.x); atomicAdd(&s_db[4 * u + 1], dbacc.y);
+      atomicAdd(&s_db[4 * u + 2], dbacc.z); atomicAdd(&s_db[4 * u + 3], dbacc.w);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
