@@ -51,6 +51,55 @@ def main():
     Y = linear_tc(X, W, mask=Ym, acc=acc0)
     ref = acc0.double() + (X.double() * (Ym > 0)) @ W.double().t()
     print("mask+accumulate err", ((Y.double() - ref).abs().max() / ref.abs().max()).item())
+    # exact call shapes of the TimeNet data-gradient (strided views into the [R,360] concat buffers)
+    def call_tc(R, Kred, Nout, A, lda, mask, ldm, Wt, Y, ldy, acc):
+        _lib.call("dimo_linear_tc", R, Kred, Nout, A, lda, mask, ldm, _lib.ptr(Wt), None, Y, ldy, 0, int(acc), _lib.stream())
+        torch.cuda.synchronize()
+    for R in (1536, 1000, 4096):
+        E, CAT, Hd = 104, 360, 256
+        dY = torch.randn(R, Hd, device="cuda"); Ym = torch.randn(R, Hd, device="cuda")
+        W5 = torch.randn(Hd, CAT, device="cuda") / 16; W0 = torch.randn(Hd, E, device="cuda") / 16
+        dcat = torch.full((R, CAT), 7.0, device="cuda")
+        call_tc(R, Hd, CAT, dY.data_ptr(), Hd, Ym.data_ptr(), Hd, W5.t().contiguous(), dcat.data_ptr(), CAT, False)
+        ref5 = (dY.double() * (Ym > 0)) @ W5.double()
+        e5 = ((dcat.double() - ref5).abs().max() / ref5.abs().max()).item()
+        dY0 = torch.randn(R, Hd, device="cuda"); Y0 = torch.randn(R, Hd, device="cuda")
+        call_tc(R, Hd, E, dY0.data_ptr(), Hd, Y0.data_ptr(), Hd, W0.t().contiguous(), dcat.data_ptr(), CAT, True)
+        ref = ref5.clone(); ref[:, :E] += (dY0.double() * (Y0 > 0)) @ W0.double()
+        e0 = ((dcat.double() - ref).abs().max() / ref.abs().max()).item()
+        # layer 4: dY and mask are column-offset views (ld 360) of the concat buffers
+        catY = torch.randn(R, CAT, device="cuda"); W4 = torch.randn(Hd, Hd, device="cuda") / 16
+        out = torch.zeros(R, Hd, device="cuda")
+        call_tc(R, Hd, Hd, dcat.data_ptr() + 4 * E, CAT, catY.data_ptr() + 4 * E, CAT, W4.t().contiguous(), out.data_ptr(), Hd, False)
+        ref4 = (dcat[:, E:].double() * (catY[:, E:] > 0)) @ W4.double()
+        e4 = ((out.double() - ref4).abs().max() / ref4.abs().max()).item()
+        print(f"dgrad shapes R={R}: layer5 {e5:.2e} layer0(acc) {e0:.2e} layer4(views) {e4:.2e}")
+    # full TimeNet backward: tensor-core vs SIMT kernels on identical inputs
+    import importlib
+    from dimo_b200 import deform as dd
+    for (M, G) in [(512, 3), (512, 8), (100, 1)]:
+        res = {}
+        for tc in (False, True):
+            dd.USE_TC = tc
+            torch.manual_seed(1)
+            net = dd.TimeNet().cuda()
+            with torch.no_grad():
+                for q in net.parameters():
+                    q.copy_(torch.randn_like(q) * 0.05)
+            pts = (torch.rand(M, 3, device="cuda") - 0.5).requires_grad_(True)
+            lat = torch.randn(G, 32, device="cuda").requires_grad_(True)
+            tms = torch.rand(G, device="cuda")
+            dx, dq = net.forward_batched(pts, tms, lat)
+            w1 = torch.randn_like(dx); w2 = torch.randn_like(dq)
+            ((dx * w1).sum() + (dq * w2).sum()).backward()
+            torch.cuda.synchronize()
+            res[tc] = [dx.detach(), dq.detach(), pts.grad, lat.grad] + [q.grad for q in net.parameters()]
+        names = ["dx", "dq", "dpts", "dlat"] + [n for n, _ in net.named_parameters()]
+        errs = {n: ((a.double() - b.double()).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+                for n, a, b in zip(names, res[True], res[False])}
+        bad = {k: f"{v:.1e}" for k, v in errs.items() if v > 2e-5}
+        print(f"TimeNet TC vs SIMT M={M} G={G}: max {max(errs.values()):.2e} bad={bad}")
+    dd.USE_TC = True
     # weight gradient (MN-major operands)
     for (R, K, No) in [(128, 128, 128), (4096, 256, 256), (4096, 360, 256), (4096, 104, 256), (1000, 256, 256)]:
         dY = torch.randn(R, No, device="cuda"); Yk = torch.randn(R, No, device="cuda"); Xk = torch.randn(R, K, device="cuda")
