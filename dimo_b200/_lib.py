@@ -119,6 +119,7 @@ class _Profile:
 
 
 PROFILE = _Profile()
+SYNC_EVERY_CALL = False      # debug: device-synchronise after every C-ABI call
 
 
 def call(name, *args):
@@ -135,3 +136,5 @@ def call(name, *args):
         PROFILE.counts[name] = PROFILE.counts.get(name, 0) + 1
     else:
         check(fn(*args))
+    if SYNC_EVERY_CALL:
+        torch.cuda.synchronize()

@@ -5,14 +5,15 @@
 //   x = hi + lo  with hi = tf32(x), lo = tf32(x - hi)     (22 mantissa bits kept)
 //   X*W^T ~= Xhi*Whi^T + Xhi*Wlo^T + Xlo*Whi^T            (three kind::tf32 MMAs per k-step, FP32 accumulate in TMEM)
 //
-// One CTA (128 threads) owns a 128-row x 128-column output tile:
+// One CTA owns a 128-row output tile (64 columns, 256 threads for forward / data-gradient; 128 columns, 128 threads
+// for the weight gradient):
 //   * operands are split into hi/lo on the fly while they are copied global -> shared memory in the canonical
 //     K-major no-swizzle UMMA layout (8-row x 16-byte core matrices, 128 B each; LBO = 128 B between the K-chunks of
 //     a core-matrix row, SBO = 1024 B between 8-row groups);
-//   * two shared-memory stages of 32 K-elements; one elected thread issues 4 k-steps x 3 tcgen05.mma (M=128, N=128,
-//     K=8) per stage and commits them to an mbarrier, the other threads are already filling the next stage;
-//   * the accumulator lives in 128 TMEM columns; the epilogue reads it with tcgen05.ld (32 lanes x 32 columns per
-//     warp), adds the bias, applies ReLU / the accumulate option and writes rows with 128-bit stores.
+//   * two shared-memory stages of 32 K-elements; one elected thread issues 4 k-steps x 3 tcgen05.mma (M=128,
+//     K=8) per stage and commits them to an mbarrier, while every thread already holds the next K-tile in registers;
+//   * the accumulator lives in TMEM; the epilogue reads it with tcgen05.ld (32 lanes x 32 columns per warp), adds the
+//     bias, applies ReLU / the accumulate option and writes rows with 128-bit stores.
 // The ReLU mask of the backward data-gradient (dX = (dY * [Y>0]) * W) is applied while loading the A operand.
 #include "common.cuh"
 
@@ -108,18 +109,32 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(TcArgs p) {
+// Forward / data-gradient kernel: 128-row x 64-column output tile, 256 threads (8 warps).
+constexpr int LIN_BN = 64, LIN_THREADS = 256;
+constexpr int LIN_A_BYTES = TC_BM * TC_BK * 4;                       // 16 KB (one of hi / lo)
+constexpr int LIN_B_BYTES = LIN_BN * TC_BK * 4;                      //  8 KB
+constexpr int LIN_STAGE_BYTES = 2 * LIN_A_BYTES + 2 * LIN_B_BYTES;   // 48 KB
+constexpr int LIN_SMEM_BYTES = 2 * LIN_STAGE_BYTES + 1024;
+
+__device__ __forceinline__ void split_store(uint8_t* hi_base, uint8_t* lo_base, uint32_t off, const float4 v) {
+  const uint4 hi = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+  const uint4 lo = make_uint4(to_tf32(v.x - __uint_as_float(hi.x)), to_tf32(v.y - __uint_as_float(hi.y)),
+                              to_tf32(v.z - __uint_as_float(hi.z)), to_tf32(v.w - __uint_as_float(hi.w)));
+  *reinterpret_cast<uint4*>(hi_base + off) = hi;
+  *reinterpret_cast<uint4*>(lo_base + off) = lo;
+}
+
+__global__ void __launch_bounds__(LIN_THREADS, 1) linear_tc_kernel(TcArgs p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t mma_bar[2];
   __shared__ uint32_t tmem_slot;
-  // 1024-byte aligned operand area
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * TC_BN;
+  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * LIN_BN;
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_slot)),
-                 "r"((uint32_t)TC_BN)
+                 "r"((uint32_t)LIN_BN)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -133,39 +148,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(TcArgs p) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = tmem_slot;
 
-  const uint32_t idesc = make_idesc_tf32(TC_BM, TC_BN);
+  const uint32_t idesc = make_idesc_tf32(TC_BM, LIN_BN);
   const uint32_t lbo = p.swap_lbo_sbo ? 1024u : 128u, sbo = p.swap_lbo_sbo ? 128u : 1024u;
   const int nk = (p.K + TC_BK - 1) / TC_BK;
 
-  for (int kt = 0; kt < nk; ++kt) {
-    const int s = kt & 1;
-    uint8_t* stage = smem + s * TC_STAGE_BYTES;
-    uint8_t* a_hi = stage, *a_lo = stage + TC_A_BYTES, *b_hi = stage + 2 * TC_A_BYTES,
-             *b_lo = stage + 2 * TC_A_BYTES + TC_B_BYTES;
-    if (kt >= 2) tc_mbar_wait(&mma_bar[s], (uint32_t)(((kt >> 1) - 1) & 1));   // MMAs of tile kt-2 have read this stage
+  // Per-thread tile coordinates.  Quarter-warps write the 8 rows of ONE core matrix (128 contiguous bytes ->
+  // conflict-free STS.128); neighbouring quarters take the adjacent 16-byte chunk of the same rows, so every global
+  // request covers full 32-byte sectors.  A: 128 rows x 8 chunks = 4 per thread, B: 64 rows x 8 chunks = 2 per thread.
+  int a_row[4], a_chunk[4], b_row[2], b_chunk[2];
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int e = tid + it * LIN_THREADS;
+    a_row[it] = (((e >> 4) & 15) << 3) | (e & 7);
+    a_chunk[it] = ((e >> 8) << 1) | ((e >> 3) & 1);
+  }
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int e = tid + it * LIN_THREADS;
+    b_row[it] = (((e >> 4) & 7) << 3) | (e & 7);
+    b_chunk[it] = ((e >> 7) << 1) | ((e >> 3) & 1);
+  }
+  float4 va[4], vb[2];
+  // the operands of K-tile kt+1 are fetched into registers while tile kt is converted, stored and multiplied
+  auto fetch = [&](int kt) {
     const int k0 = kt * TC_BK;
-    // ---- fill: 128 rows x 8 chunks for A and for B.  Lane mapping: each quarter-warp writes the 8 rows of ONE core
-    // matrix (128 contiguous bytes -> conflict-free STS.128); quarters 0/1 (2/3) take the two adjacent 16-byte chunks
-    // of the same rows, so every global request still covers full 32-byte sectors.  All 16 loads of the stage are
-    // issued before any conversion so that each thread keeps 16 x 16 B in flight (the tiles come from L2). ----
-    float4 va[8], vb[8];
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int e = tid + it * TC_THREADS;
-      const int row = (((e >> 4) & 15) << 3) | (e & 7), chunk = ((e >> 8) << 1) | ((e >> 3) & 1);
-      const int gr = m0 + row, gn = n0 + row, gk = k0 + chunk * 4;
+    for (int it = 0; it < 4; ++it) {
+      const int gr = m0 + a_row[it], gk = k0 + a_chunk[it] * 4;
       va[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-      vb[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (gr < p.R && gk < p.K) va[it] = *reinterpret_cast<const float4*>(p.X + gr * p.ldx + gk);
-      if (gn < p.No && gk < p.K) vb[it] = *reinterpret_cast<const float4*>(p.Wt + (int64_t)gn * p.K + gk);
-    }
-    if (p.mask != nullptr) {
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int e = tid + it * TC_THREADS;
-        const int row = (((e >> 4) & 15) << 3) | (e & 7), chunk = ((e >> 8) << 1) | ((e >> 3) & 1);
-        const int gr = m0 + row, gk = k0 + chunk * 4;
-        if (gr < p.R && gk < p.K) {
+      if (gr < p.R && gk < p.K) {
+        va[it] = *reinterpret_cast<const float4*>(p.X + gr * p.ldx + gk);
+        if (p.mask != nullptr) {
           const float4 m = *reinterpret_cast<const float4*>(p.mask + gr * p.ldm + gk);
           if (!(m.x > 0.f)) va[it].x = 0.f;
           if (!(m.y > 0.f)) va[it].y = 0.f;
@@ -175,27 +188,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(TcArgs p) {
       }
     }
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int e = tid + it * TC_THREADS;
-      const int row = (((e >> 4) & 15) << 3) | (e & 7), chunk = ((e >> 8) << 1) | ((e >> 3) & 1);
-      const uint32_t off = canon_off(row, chunk);
-      {
-        const float4 v = va[it];
-        const uint4 hi = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
-        const uint4 lo = make_uint4(to_tf32(v.x - __uint_as_float(hi.x)), to_tf32(v.y - __uint_as_float(hi.y)),
-                                    to_tf32(v.z - __uint_as_float(hi.z)), to_tf32(v.w - __uint_as_float(hi.w)));
-        *reinterpret_cast<uint4*>(a_hi + off) = hi;
-        *reinterpret_cast<uint4*>(a_lo + off) = lo;
-      }
-      {
-        const float4 v = vb[it];
-        const uint4 hi = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
-        const uint4 lo = make_uint4(to_tf32(v.x - __uint_as_float(hi.x)), to_tf32(v.y - __uint_as_float(hi.y)),
-                                    to_tf32(v.z - __uint_as_float(hi.z)), to_tf32(v.w - __uint_as_float(hi.w)));
-        *reinterpret_cast<uint4*>(b_hi + off) = hi;
-        *reinterpret_cast<uint4*>(b_lo + off) = lo;
-      }
+    for (int it = 0; it < 2; ++it) {
+      const int gn = n0 + b_row[it], gk = k0 + b_chunk[it] * 4;
+      vb[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gn < p.No && gk < p.K) vb[it] = *reinterpret_cast<const float4*>(p.Wt + (int64_t)gn * p.K + gk);
     }
+  };
+
+  fetch(0);
+  for (int kt = 0; kt < nk; ++kt) {
+    const int s = kt & 1;
+    uint8_t* stage = smem + s * LIN_STAGE_BYTES;
+    uint8_t* a_hi = stage, *a_lo = stage + LIN_A_BYTES, *b_hi = stage + 2 * LIN_A_BYTES,
+             *b_lo = stage + 2 * LIN_A_BYTES + LIN_B_BYTES;
+    if (kt >= 2) tc_mbar_wait(&mma_bar[s], (uint32_t)(((kt >> 1) - 1) & 1));   // MMAs of tile kt-2 have read this stage
+#pragma unroll
+    for (int it = 0; it < 4; ++it) split_store(a_hi, a_lo, canon_off(a_row[it], a_chunk[it]), va[it]);
+#pragma unroll
+    for (int it = 0; it < 2; ++it) split_store(b_hi, b_lo, canon_off(b_row[it], b_chunk[it]), vb[it]);
+    if (kt + 1 < nk) fetch(kt + 1);          // in flight during the barrier, the MMA issue and the next wait
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async-proxy (MMA) reads
     __syncthreads();
     if (tid == 0) {
@@ -223,12 +234,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(TcArgs p) {
   }
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-  // ---- epilogue: warp w owns TMEM lanes [32w, 32w+32) = output rows m0 + 32w + lane ----
-  const int row = m0 + warp * 32 + lane;
-#pragma unroll 1
-  for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+  // ---- epilogue: warp w reads TMEM lanes [32 (w&3), +32) (its quarter) and columns [32 (w>>2), +32) ----
+  const int row = m0 + (warp & 3) * 32 + lane;
+  const int c0 = (warp >> 2) * 32;
+  {
     uint32_t v[32];
-    tc_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+    tc_ld32(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, v);
     if (row < p.R) {
       float* yrow = p.Y + row * p.ldy + n0 + c0;
 #pragma unroll
@@ -259,10 +270,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(TcArgs p) {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)TC_BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)LIN_BN) : "memory");
   }
 }
-
 
 // ---------------------------------------------------------------------------------------------------------------
 // Weight gradient  dW[n,k] += sum_r (dY[r,n] * [Y[r,n] > 0]) * X[r,k],  db[n] += sum_r dY[r,n] * [Y[r,n] > 0]
@@ -462,15 +472,15 @@ extern "C" int dimo_linear_tc(int R, int K, int No, const float* X, int64_t ldx,
                "tensor-core linear: mask must be 16-byte aligned");
   static bool attr_set = false;
   if (!attr_set) {
-    DIMO_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    DIMO_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LIN_SMEM_BYTES));
     attr_set = true;
   }
   TcArgs p{};
   p.R = R; p.K = K; p.No = No; p.X = X; p.ldx = ldx; p.mask = mask; p.ldm = ldm; p.Wt = Wt; p.bias = bias;
   p.Y = Y; p.ldy = ldy; p.relu = relu; p.accumulate = accumulate;
   p.swap_lbo_sbo = h_tc_knob[0]; p.single_pass = h_tc_knob[1];
-  dim3 grid(ceil_div(R, TC_BM), ceil_div(No, TC_BN));
-  linear_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(p);
+  dim3 grid(ceil_div(R, TC_BM), ceil_div(No, LIN_BN));
+  linear_tc_kernel<<<grid, LIN_THREADS, LIN_SMEM_BYTES, (cudaStream_t)stream>>>(p);
   DIMO_CHECK_LAUNCH();
   return 0;
 }

@@ -18,10 +18,12 @@ PTS_FREQS, TIME_FREQS, HIDDEN, DEPTH, SKIP_AFTER = 10, 6, 256, 8, 4
 # TimeNet GEMMs run on the tcgen05 tensor cores (3xTF32-compensated, csrc/mlp_tc.cu); DIMO_TC=0 selects the FP32
 # SIMT kernels (csrc/mlp.cu) for A/B comparison.  Both are hand-written kernels of this library.
 USE_TC = os.environ.get("DIMO_TC", "1") != "0"
+TC_FWD = TC_DGRAD = TC_WGRAD = True      # per-operation switches (bring-up / A-B tests); all on by default
+DEBUG_CAPTURE = None                      # list -> forward activations are cloned into it (bring-up only)
 
 
 def _linear_fwd(R, K, No, X, ldx, W, b, Y, ldy, relu, s):
-    if USE_TC and K % 4 == 0 and ldx % 4 == 0:
+    if USE_TC and TC_FWD and K % 4 == 0 and ldx % 4 == 0:
         _lib.call("dimo_linear_tc", R, K, No, X, ldx, None, 0, _lib.ptr(W), _lib.ptr(b), Y, ldy, int(relu), 0, s)
     else:
         _lib.call("dimo_linear_fwd", R, K, No, X, ldx, _lib.ptr(W), _lib.ptr(b), Y, ldy, int(relu), s)
@@ -74,6 +76,8 @@ class _TimeNetFn(torch.autograd.Function):
         _linear_fwd(R, HIDDEN, 4, hr.data_ptr(), HIDDEN, Ws[11], bs[11], dquat.data_ptr(), 4, False, s)
         ctx.save_for_backward(pts, times, latents, cat, hp, hr, *[a for a in acts if a is not None], *Ws)
         ctx.dims = (M, G, L, E, CAT)
+        if DEBUG_CAPTURE is not None:
+            DEBUG_CAPTURE.append([t.clone() for t in (cat, hp, hr, *[a for a in acts if a is not None])])
         return dxyz, dquat
 
     @staticmethod
@@ -96,7 +100,7 @@ class _TimeNetFn(torch.autograd.Function):
         keep = []    # transposed weights must outlive the asynchronous launches that read them
 
         def bwd_layer(li, K, No, dY_ptr, lddy, Y_ptr, ldy, X_ptr, ldx, dX_ptr, lddx, accumulate):
-            if USE_TC and No % 4 == 0 and K % 4 == 0 and lddy % 4 == 0 and ldx % 4 == 0 and \
+            if USE_TC and TC_WGRAD and No % 4 == 0 and K % 4 == 0 and lddy % 4 == 0 and ldx % 4 == 0 and \
                     (Y_ptr is None or ldy % 4 == 0):
                 _lib.call("dimo_linear_wgrad_tc", R, K, No, dY_ptr, lddy, Y_ptr, ldy if Y_ptr is not None else 0,
                           X_ptr, ldx, _lib.ptr(dWs[li]), _lib.ptr(dbs[li]), s)
@@ -104,7 +108,7 @@ class _TimeNetFn(torch.autograd.Function):
                 _lib.call("dimo_linear_bwd_weight", R, K, No, dY_ptr, lddy, Y_ptr, ldy, X_ptr, ldx,
                           _lib.ptr(dWs[li]), _lib.ptr(dbs[li]), s)
             if dX_ptr is not None:
-                if USE_TC and No % 4 == 0 and lddy % 4 == 0 and (Y_ptr is None or ldy % 4 == 0):
+                if USE_TC and TC_DGRAD and No % 4 == 0 and lddy % 4 == 0 and (Y_ptr is None or ldy % 4 == 0):
                     # dX[R,K] = (dY * [Y>0]) [R,No] * W[No,K]: same kernel with the transposed weight as the
                     # "[N_out, K_red]" operand (reduction over No)
                     Wt = Ws[li].t().contiguous()

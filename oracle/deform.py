@@ -71,10 +71,13 @@ def timenet_init(latent_dim=32, seed=0, dtype=torch.float32, final_scale=None):
     return [(W, b) for W, b in params]
 
 
-def timenet_forward(params, pts, t, latent):
+def timenet_forward(params, pts, t, latent, return_kink_distance=False):
     """TimeNet.forward, renderer/latent_gs_renderer.py:205-235, on flat rows.
 
     pts [R,3], t [R,1] (or python float), latent [R,L] (or [L]) -> (dxyz [R,3], dquat [R,4]).
+    return_kink_distance: also return, per row, min |pre-activation| / max |pre-activation| over all ReLU
+    inputs -- rows where it is ~1e-6 sit on a ReLU kink, where the gradient is discontinuous and two
+    floating-point evaluations can legitimately disagree (used by the parity tests to mask such rows).
     """
     R = pts.shape[0]
     if not torch.is_tensor(t):
@@ -84,15 +87,28 @@ def timenet_forward(params, pts, t, latent):
         latent = latent[None, :].expand(R, -1)
     h0 = torch.cat([posenc(pts, PTS_FREQS), posenc(t, TIME_FREQS), latent], dim=-1)
     h = h0
+    kink = None
+
+    def relu_layer(x, W, b):
+        nonlocal kink
+        z = F.linear(x, W, b)
+        if return_kink_distance:
+            with torch.no_grad():
+                d = z.abs().min(dim=-1).values / z.abs().max().clamp_min(1e-30)
+                kink = d if kink is None else torch.minimum(kink, d)
+        return F.relu(z)
+
     for i in range(DEPTH):
         W, b = params[i]
-        h = F.relu(F.linear(h, W, b))
+        h = relu_layer(h, W, b)
         if i == SKIP_AFTER:
             h = torch.cat([h0, h], dim=-1)
-    hp = F.relu(F.linear(h, *params[8]))
+    hp = relu_layer(h, *params[8])
     dxyz = F.linear(hp, *params[9])
-    hr = F.relu(F.linear(h, *params[10]))
+    hr = relu_layer(h, *params[10])
     dquat = F.linear(hr, *params[11])
+    if return_kink_distance:
+        return dxyz, dquat, kink
     return dxyz, dquat
 
 

@@ -69,9 +69,15 @@ def test_timenet_fwd_bwd(cuda, M, G):
     rows_pts = opts[None].expand(G, M, 3).reshape(-1, 3)
     rows_t = times[:, None, None].expand(G, M, 1).reshape(-1, 1)
     rows_lat = olat[:, None, :].expand(G, M, -1).reshape(G * M, -1)
-    odx, odq = od.timenet_forward(op, rows_pts, rows_t, rows_lat)
+    odx, odq, kink = od.timenet_forward(op, rows_pts, rows_t, rows_lat, return_kink_distance=True)
     g = torch.Generator().manual_seed(7)
     wx = torch.randn(G * M, 3, generator=g); wq = torch.randn(G * M, 4, generator=g)
+    # Rows whose forward pass sits within 2e-5 (relative) of a ReLU kink get zero loss weight: the gradient is
+    # discontinuous there, so two correct floating-point evaluations (FP32 FMA order, 3xTF32 tensor cores) can pick
+    # different sides and differ by a whole row contribution (~1/sqrt(R) of an entry).  Typically 0-10 rows of 1536.
+    safe = (kink > 2e-5).float()[:, None]
+    assert float(safe.mean()) > 0.95
+    wx = wx * safe; wq = wq * safe
     ((odx * wx).sum() + (odq * wq).sum()).backward()
     # cuda
     cpts = pts.cuda().requires_grad_(True); clat = lat.cuda().requires_grad_(True)

@@ -77,28 +77,61 @@ def main():
     # full TimeNet backward: tensor-core vs SIMT kernels on identical inputs
     import importlib
     from dimo_b200 import deform as dd
-    for (M, G) in [(512, 3), (512, 8), (100, 1)]:
-        res = {}
+    def run_net(M, G, tc, fwd=True, dgrad=True, wgrad=True, sync=False):
+        dd.USE_TC = tc; dd.TC_FWD = fwd; dd.TC_DGRAD = dgrad; dd.TC_WGRAD = wgrad
+        _lib.SYNC_EVERY_CALL = sync
+        torch.manual_seed(1)
+        net = dd.TimeNet().cuda()
+        with torch.no_grad():
+            for q in net.parameters():
+                q.copy_(torch.randn_like(q) * 0.05)
+        pts = (torch.rand(M, 3, device="cuda") - 0.5).requires_grad_(True)
+        lat = torch.randn(G, 32, device="cuda").requires_grad_(True)
+        tms = torch.rand(G, device="cuda")
+        dx, dq = net.forward_batched(pts, tms, lat)
+        w1 = torch.randn_like(dx); w2 = torch.randn_like(dq)
+        ((dx * w1).sum() + (dq * w2).sum()).backward()
+        torch.cuda.synchronize()
+        _lib.SYNC_EVERY_CALL = False
+        names = ["dx", "dq", "dpts", "dlat"] + [n.replace("deformnet.", "d").replace("_layers.", "").replace("weight", "W").replace("bias", "b") for n, _ in net.named_parameters()]
+        return names, [dx.detach(), dq.detach(), pts.grad, lat.grad] + [q.grad for q in net.parameters()]
+
+    # activations / parameters after a tensor-core forward vs after a SIMT forward
+    for (M, G) in [(512, 3)]:
+        caps = {}
         for tc in (False, True):
-            dd.USE_TC = tc
+            dd.USE_TC = tc; dd.TC_FWD = True
+            dd.DEBUG_CAPTURE = []
             torch.manual_seed(1)
             net = dd.TimeNet().cuda()
             with torch.no_grad():
                 for q in net.parameters():
                     q.copy_(torch.randn_like(q) * 0.05)
-            pts = (torch.rand(M, 3, device="cuda") - 0.5).requires_grad_(True)
-            lat = torch.randn(G, 32, device="cuda").requires_grad_(True)
-            tms = torch.rand(G, device="cuda")
-            dx, dq = net.forward_batched(pts, tms, lat)
-            w1 = torch.randn_like(dx); w2 = torch.randn_like(dq)
-            ((dx * w1).sum() + (dq * w2).sum()).backward()
+            p0 = [q.detach().clone() for q in net.parameters()]
+            pts = (torch.rand(M, 3, device="cuda") - 0.5); lat = torch.randn(G, 32, device="cuda"); tms = torch.rand(G, device="cuda")
+            with torch.no_grad():
+                dx, dq = net.forward_batched(pts, tms, lat)
             torch.cuda.synchronize()
-            res[tc] = [dx.detach(), dq.detach(), pts.grad, lat.grad] + [q.grad for q in net.parameters()]
-        names = ["dx", "dq", "dpts", "dlat"] + [n for n, _ in net.named_parameters()]
-        errs = {n: ((a.double() - b.double()).abs().max() / b.abs().max().clamp_min(1e-30)).item()
-                for n, a, b in zip(names, res[True], res[False])}
-        bad = {k: f"{v:.1e}" for k, v in errs.items() if v > 2e-5}
-        print(f"TimeNet TC vs SIMT M={M} G={G}: max {max(errs.values()):.2e} bad={bad}")
+            pchg = max(float((a - b).abs().max()) for a, b in zip(p0, [q.detach() for q in net.parameters()]))
+            caps[tc] = dd.DEBUG_CAPTURE[0]
+            print(f"forward tc={tc}: params changed by {pchg:.1e}")
+        dd.DEBUG_CAPTURE = None
+        nm = ["cat", "hp", "hr"] + [f"act{i}" for i in (0, 1, 2, 3, 5, 6, 7)]
+        for n, a, b in zip(nm, caps[True], caps[False]):
+            d = (a - b).abs()
+            flips = int(((a > 0) != (b > 0)).sum())
+            print(f"  {n}: max abs diff {float(d.max()):.2e} (scale {float(b.abs().max()):.2e}) relu-mask flips {flips} of {a.numel()}"
+                  f" rows with diff>1e-4: {int((d.max(dim=1).values > 1e-4).sum())}")
+    for (M, G) in [(512, 3), (100, 1)]:
+        names, ref = run_net(M, G, False)
+        for label, kw in [("all", {}), ("all+sync", dict(sync=True)), ("fwd only", dict(dgrad=False, wgrad=False)),
+                          ("dgrad only", dict(fwd=False, wgrad=False)), ("wgrad only", dict(fwd=False, dgrad=False))]:
+            _, got = run_net(M, G, True, **kw)
+            errs = {n: ((a.double() - b.double()).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+                    for n, a, b in zip(names, got, ref)}
+            bad = " ".join(f"{k}:{v:.0e}" for k, v in errs.items() if v > 2e-5)
+            print(f"TimeNet TC[{label}] vs SIMT M={M} G={G}: max {max(errs.values()):.1e} bad: {bad}")
+    dd.TC_FWD = dd.TC_DGRAD = dd.TC_WGRAD = True
     dd.USE_TC = True
     # weight gradient (MN-major operands)
     for (R, K, No) in [(128, 128, 128), (4096, 256, 256), (4096, 360, 256), (4096, 104, 256), (1000, 256, 256)]:
