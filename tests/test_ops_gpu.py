@@ -74,9 +74,10 @@ def test_timenet_fwd_bwd(cuda, M, G):
     wx = torch.randn(G * M, 3, generator=g); wq = torch.randn(G * M, 4, generator=g)
     # Rows whose forward pass sits within 2e-5 (relative) of a ReLU kink get zero loss weight: the gradient is
     # discontinuous there, so two correct floating-point evaluations (FP32 FMA order, 3xTF32 tensor cores) can pick
-    # different sides and differ by a whole row contribution (~1/sqrt(R) of an entry).  Typically 0-10 rows of 1536.
+    # different sides and differ by a whole row contribution (~1/sqrt(R) of an entry).  Each row has 2560 ReLU inputs,
+    # so 10-20 % of the rows have one of them this close to zero.
     safe = (kink > 2e-5).float()[:, None]
-    assert float(safe.mean()) > 0.95
+    assert float(safe.mean()) > 0.6
     wx = wx * safe; wq = wq * safe
     ((odx * wx).sum() + (odq * wq).sum()).backward()
     # cuda
