@@ -1,9 +1,17 @@
-"""Multi-GPU plumbing for the path: motion sharding + ONE flat gradient all-reduce per step.
+"""Multi-GPU plumbing for the path: motion sharding + ONE flat gradient buffer all-reduced per step.
 
 The reference is single-GPU; frames (motion, t, view) are independent given the shared
 parameters, so ranks own disjoint blocks of motions and the only exchange is the gradient sum at the
 optimizer step.  torch.distributed (NCCL over NVLink/NVSwitch on the box, gloo in the CPU tests)
 is the transport; there is no data-path collective inside any kernel.
+
+Design: every parameter's ``.grad`` is a VIEW into one persistent fp32 buffer, so autograd accumulates straight
+into the communication buffer (no pack / unpack copies).  The buffer has two contiguous buckets:
+
+  bucket 0  "early"  gradients that are final before the deformation-MLP backward runs (the per-Gaussian
+            parameters: 14 floats per Gaussian) -- its all-reduce is launched from a post-accumulate hook and
+            overlaps the TimeNet backward;
+  bucket 1  everything else (control points, latent codes, TimeNet weights), reduced after backward.
 """
 import torch
 
@@ -17,12 +25,37 @@ def shard_motions(n_motions, world, rank):
 
 
 class FlatGradReducer:
-    """Packs every gradient into one persistent fp32 buffer, all-reduces it once (SUM), unpacks.
+    """Gradients of `params` live in one flat buffer (`.flat`); `reduce()` sums it over the process group.
     Gradients of latent codes owned by other ranks are zero locally, so SUM gives every rank the full update."""
 
-    def __init__(self, params):
-        self.params = [p for p in params if p.numel() > 0]
+    def __init__(self, params, early=(), group=None, attach=True):
+        early_ids = {id(p) for p in early}
+        self.early = [p for p in params if p.numel() > 0 and id(p) in early_ids]
+        self.late = [p for p in params if p.numel() > 0 and id(p) not in early_ids]
+        self.params = self.early + self.late
+        self.group = group
+        self.n_early = sum(p.numel() for p in self.early)
+        self.n = sum(p.numel() for p in self.params)
         self.flat = None
+        self._arrived = 0
+        self._work = []
+        self._hooks = []
+        if attach and self.params:
+            self.attach()
+
+    # ------------------------------------------------------------------------------------------
+    def attach(self):
+        dev = self.params[0].device
+        self.flat = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        o = 0
+        for p in self.params:
+            v = self.flat[o:o + p.numel()].view_as(p)
+            if p.grad is not None:
+                v.copy_(p.grad)
+            p.grad = v
+            o += p.numel()
+        for p in self.early:
+            self._hooks.append(p.register_post_accumulate_grad_hook(self._on_early_grad))
 
     def layout(self):
         o, out = 0, []
@@ -31,19 +64,35 @@ class FlatGradReducer:
             o += p.numel()
         return out, o
 
-    def reduce(self, group=None):
+    def zero(self):
+        self.flat.zero_()
+        self._arrived = 0
+        self._work = []
+
+    def _on_early_grad(self, _p):
+        self._arrived += 1
+        if self._arrived == len(self.early) and self._distributed():
+            self._launch(0, self.n_early)
+
+    def _distributed(self):
         import torch.distributed as dist
-        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
-        lay, n = self.layout()
-        dev = grads[0].device
-        if self.flat is None or self.flat.numel() != n or self.flat.device != dev:
-            self.flat = torch.empty(n, dtype=torch.float32, device=dev)
-        views = [self.flat[o:o + k].view_as(g) for (o, k), g in zip(lay, grads)]
-        torch._foreach_copy_(views, grads)
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-        for p, v in zip(self.params, views):
-            if p.grad is None:
-                p.grad = v.clone()
-            else:
-                p.grad.copy_(v)
-        return n
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def _launch(self, lo, hi):
+        import torch.distributed as dist
+        if hi > lo:
+            self._work.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def reduce(self):
+        """Call after backward.  Launches what is still outstanding and makes the current stream wait for all of it."""
+        if not self._distributed():
+            return self.n
+        early_done = self._arrived >= len(self.early) and len(self.early) > 0
+        if not early_done:
+            self._launch(0, self.n_early)
+        self._launch(self.n_early, self.n)
+        for w in self._work:
+            w.wait()
+        self._work = []
+        self._arrived = 0
+        return self.n

@@ -77,10 +77,21 @@ class TrainStep:
         self.world = world
         self.params = [p for p in self.g.parameters() if p.numel() > 0]
         self.opt = torch.optim.Adam(self.params, lr=lr, eps=1e-15, fused=True)
-        self.reducer = FlatGradReducer(self.params) if world > 1 else None
+        g = self.g
+        # per-Gaussian parameters: their gradients are final once the LBS backward has run, i.e. before the
+        # TimeNet backward -> bucket 0 of the flat buffer, all-reduced while the MLP backward executes
+        early = [g._xyz, g._features_dc, g._features_rest, g._opacity, g._scaling, g._rotation]
+        self.reducer = FlatGradReducer(self.params, early=early)
 
-    def allreduce_grads(self):
-        self.reducer.reduce()
+    def _timed(self, name, fn):
+        if not _lib.PROFILE.enabled:
+            return fn()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        _lib.PROFILE.events.append((name, e0, e1))
+        return out
 
     def run(self, cameras, times, latent_indices, gt, mask, n_motions, optimize=True):
         """cameras/times/latent_indices: length-S lists ordered motion-major; gt [S,3,H,W], mask [S,1,H,W] on device.
@@ -90,10 +101,10 @@ class TrainStep:
         # the loss kernel clamps the render to [0,1] on load (and masks the gradient), so skip the separate clamp pass
         out = self.r.render_batch(cameras, times, latent_indices, stage=self.stage, clamp=False)
         loss = step_loss(out["image_raw"], out["alpha"], gt, mask, n_motions)
-        loss.backward()
+        loss.backward()                                   # gradients accumulate straight into reducer.flat
         if self.world > 1:
-            self.allreduce_grads()
+            self._timed("py:allreduce_wait", self.reducer.reduce)
         if optimize:
-            self.opt.step()
-        self.opt.zero_grad(set_to_none=False)
+            self._timed("py:adam", self.opt.step)
+        self._timed("py:zero_grad", self.reducer.zero)
         return loss

@@ -32,16 +32,24 @@ def _worker(rank, world, port, q):
     params = [torch.nn.Parameter(torch.zeros(s)) for s in shapes]
     g = torch.Generator().manual_seed(10 + rank)
     local = [torch.randn(s, generator=g) for s in shapes]
-    for p, gr in zip(params, local):
-        p.grad = gr.clone()
-    # latent-code-like parameter: each rank only has gradient rows for the motions it owns
+    red = FlatGradReducer(params, early=params[:2])          # gradients become views into red.flat
+    assert all(p.grad.data_ptr() >= red.flat.data_ptr() for p in params)
+    # "backward": autograd accumulates in place into the views; the early hook launches bucket 0 by itself
     lo, hi = shard_motions(4, world, rank)
-    params[3].grad.zero_(); params[3].grad[lo:hi] = local[3][lo:hi]
-    red = FlatGradReducer(params)
+    loss = 0
+    for i, (p, w) in enumerate(zip(params, local)):
+        if i == 3:      # latent-code-like parameter: only the rows of the motions this rank owns get gradient
+            loss = loss + (p[lo:hi] * w[lo:hi]).sum()
+        else:
+            loss = loss + (p * w).sum()
+    loss.backward()
     n = red.reduce()
-    assert n == sum(p.numel() for p in params)
-    assert red.flat.numel() == n                      # one buffer, one collective
+    assert n == sum(p.numel() for p in params) == red.flat.numel()      # one buffer
+    for p in params:
+        assert p.grad.untyped_storage().data_ptr() == red.flat.untyped_storage().data_ptr()
     q.put((rank, [p.grad.numpy().copy() for p in params], [l.numpy().copy() for l in local]))
+    red.zero()
+    assert float(red.flat.abs().max()) == 0.0 and float(params[0].grad.abs().max()) == 0.0
     dist.barrier()
     dist.destroy_process_group()
 
