@@ -20,7 +20,7 @@ _SIGS = {
     "dimo_raster_scan_temp_bytes": (c_sz, [c_i64]),
     "dimo_raster_sort_temp_bytes": (c_sz, [c_i64]),
     "dimo_raster_preprocess": (c_int, [c_int] * 6 + [c_f32, c_vp] + [c_vp, c_i64] * 6 + [c_vp] * 6 + [c_vp, c_sz, c_vp, c_vp]),
-    "dimo_raster_bin": (c_int, [c_int] * 4 + [c_i64] + [c_vp] * 8 + [c_vp, c_sz, c_vp, c_vp, c_vp]),
+    "dimo_raster_bin": (c_int, [c_int] * 4 + [c_i64] + [c_vp] * 8 + [c_vp, c_sz, c_vp, c_vp, c_vp, c_vp]),
     "dimo_raster_blend_fwd": (c_int, [c_int] * 3 + [c_vp] * 10),
     "dimo_raster_blend_bwd": (c_int, [c_int] * 4 + [c_vp] * 12),
     "dimo_raster_preprocess_bwd": (c_int, [c_int] * 6 + [c_f32, c_vp] + [c_vp, c_i64] * 4 + [c_vp] * 10),
@@ -126,7 +126,7 @@ def call(name, *args):
     fn = getattr(lib(), name, None)
     if fn is None:
         raise RuntimeError(f"libdimo_b200.so does not export {name}: rebuild with `python -m dimo_b200.build`")
-    if PROFILE.enabled:
+    if PROFILE.enabled and not torch.cuda.is_current_stream_capturing():
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()

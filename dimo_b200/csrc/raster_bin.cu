@@ -32,7 +32,10 @@ const char* get_error() { return g_err; }
 
 // 4 lanes per instance: lane q copies float4 #q of the 64-byte record (reads: 64 B contiguous per
 // instance, writes: fully coalesced).  Lane 0 also writes the tile range boundaries.
-__global__ void __launch_bounds__(256) pack_ranges_kernel(int64_t R, const uint32_t* __restrict__ keys,
+//
+// `R` is the number of SLOTS: with an exact instance count every slot is valid; in capacity mode (no host
+// read-back of the count) the unused tail carries sentinel keys (>= ntiles) which sort last and are skipped here.
+__global__ void __launch_bounds__(256) pack_ranges_kernel(int64_t R, uint32_t ntiles, const uint32_t* __restrict__ keys,
                                                           const uint32_t* __restrict__ vals,
                                                           const float4* __restrict__ splats,
                                                           float4* __restrict__ packed, uint2* __restrict__ ranges) {
@@ -40,6 +43,8 @@ __global__ void __launch_bounds__(256) pack_ranges_kernel(int64_t R, const uint3
   const int64_t j = t >> 2;
   const int qd = (int)(t & 3);
   if (j >= R) return;
+  const uint32_t tile = keys[j];
+  if (tile >= ntiles) return;                 // sentinel slot
   const uint32_t v = vals[j];
   // splat record  x,y,ca,cb | cc,op,r,g | b,depth,nx,ny | nz,-,-,-   ->   blend record (raster_blend.cu)
   //               x,y,a2,b2 | c2,op,pthr2,r | g,b,depth,nx | ny,nz,gid,0
@@ -63,17 +68,18 @@ __global__ void __launch_bounds__(256) pack_ranges_kernel(int64_t R, const uint3
   }
   packed[4 * j + qd] = o;
   if (qd == 0) {
-    const uint32_t tile = keys[j];
-    if (j == 0) {
-      ranges[tile].x = 0;
-    } else {
-      const uint32_t prev = keys[j - 1];
-      if (prev != tile) {
-        ranges[prev].y = (uint32_t)j;
-        ranges[tile].x = (uint32_t)j;
-      }
-    }
-    if (j == R - 1) ranges[tile].y = (uint32_t)R;
+    if (j == 0 || keys[j - 1] != tile) ranges[tile].x = (uint32_t)j;
+    if (j == R - 1 || keys[j + 1] != tile) ranges[tile].y = (uint32_t)(j + 1);
+  }
+}
+
+// capacity mode: flags an instance count larger than the number of slots (the surplus instances were dropped)
+__global__ void overflow_check_kernel(const uint32_t* __restrict__ offsets, int64_t BN, int64_t slots,
+                                      int32_t* __restrict__ flag) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const uint32_t total = offsets[BN - 1];
+    flag[0] = (int32_t)total;
+    if ((int64_t)total > slots) flag[1] = 1;
   }
 }
 
@@ -181,20 +187,28 @@ int dimo_raster_preprocess(int B, int N, int W, int H, int sh_degree, int sh_coe
 int dimo_raster_bin(int B, int N, int W, int H, int64_t R, const float* splats, const int32_t* radii,
                     const uint32_t* perm_sorted, const uint32_t* offsets, uint32_t* keys_unsorted,
                     uint32_t* vals_unsorted, uint32_t* keys_sorted, uint32_t* vals_sorted, void* sort_temp,
-                    size_t sort_temp_bytes, float* packed, uint32_t* ranges, void* stream) {
+                    size_t sort_temp_bytes, float* packed, uint32_t* ranges, int32_t* count_overflow, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
   const int64_t ntiles = (int64_t)B * gx * gy;
+  const int64_t BN = (int64_t)B * N;
   DIMO_REQUIRE(R < ((int64_t)1 << 31), "instance count must fit int32");
-  DIMO_REQUIRE(ntiles < ((int64_t)1 << 31), "B*tiles must fit int32");
+  DIMO_REQUIRE(ntiles < ((int64_t)1 << 31) - 1, "B*tiles must fit int32");
   DIMO_CHECK_CUDA(cudaMemsetAsync(ranges, 0, sizeof(uint32_t) * 2 * ntiles, st));
-  if (R == 0) return 0;
+  if (R == 0 || BN == 0) return 0;
+  if (count_overflow != nullptr) {
+    // capacity mode: R is a slot count chosen by the caller; unused slots keep the all-ones sentinel key
+    DIMO_CHECK_CUDA(cudaMemsetAsync(keys_unsorted, 0xFF, sizeof(uint32_t) * (size_t)R, st));
+    overflow_check_kernel<<<1, 32, 0, st>>>(offsets, BN, R, count_overflow);
+    DIMO_CHECK_LAUNCH();
+  }
   int rc = emit_keys_launch(B, N, W, H, R, splats, radii, perm_sorted, offsets, keys_unsorted, vals_unsorted, st);
   if (rc) return rc;
   size_t need = sort_temp_bytes;
+  // one spare code above the last tile id so that the sentinel sorts behind every real key
   DIMO_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(sort_temp, need, keys_unsorted, keys_sorted, vals_unsorted,
-                                                  vals_sorted, (int)R, 0, bits_for(ntiles), st));
-  pack_ranges_kernel<<<ceil_div(R * 4, 256), 256, 0, st>>>(R, keys_sorted, vals_sorted,
+                                                  vals_sorted, (int)R, 0, bits_for(ntiles + 1), st));
+  pack_ranges_kernel<<<ceil_div(R * 4, 256), 256, 0, st>>>(R, (uint32_t)ntiles, keys_sorted, vals_sorted,
                                                            reinterpret_cast<const float4*>(splats),
                                                            reinterpret_cast<float4*>(packed),
                                                            reinterpret_cast<uint2*>(ranges));

@@ -43,15 +43,21 @@ def _bstride(t, B, per_frame_numel):
 
 class RasterState:
     """Buffers kept from forward for backward / inspection (all torch-owned)."""
-    __slots__ = ("B", "N", "W", "H", "R", "cams", "splats", "radii", "tiles_touched", "offsets", "perm", "keys_sorted",
+    __slots__ = ("B", "N", "W", "H", "R", "count_overflow", "cams", "splats", "radii", "tiles_touched", "offsets", "perm",
+                 "keys_sorted",
                  "vals_sorted", "packed", "ranges", "final_T", "n_contrib", "sh_degree", "sh_coeffs",
                  "scale_modifier")
 
 
 def _forward_impl(cams, means3D, scales, rotations, opacities, shs, colors_precomp, B, N, W, H, sh_degree,
-                  scale_modifier):
+                  scale_modifier, capacity=None):
+    """capacity=None: exact mode -- the instance count R is read back from the device once (a host sync, like the
+    upstream rasterisers) and buffers are sized to it.  capacity=int: sync-free mode for CUDA graphs -- buffers hold
+    `capacity` instance slots, `st.count_overflow` (device i32[2]) receives the true count and an overflow flag."""
+    import ctypes
     dev = means3D.device
     f32 = dict(dtype=torch.float32, device=dev)
+    i32 = dict(dtype=torch.int32, device=dev)
     st = RasterState()
     st.B, st.N, st.W, st.H = B, N, W, H
     st.cams = cams
@@ -60,16 +66,15 @@ def _forward_impl(cams, means3D, scales, rotations, opacities, shs, colors_preco
     st.scale_modifier = float(scale_modifier)
     BN = B * N
     st.splats = torch.empty(BN, SPLAT_FLOATS, **f32)
-    st.radii = torch.empty(BN, dtype=torch.int32, device=dev)
-    st.tiles_touched = torch.empty(BN, dtype=torch.int32, device=dev)
-    st.offsets = torch.empty(BN, dtype=torch.int32, device=dev)
+    st.radii = torch.empty(BN, **i32)
+    st.tiles_touched = torch.empty(BN, **i32)
+    st.offsets = torch.empty(BN, **i32)
     L = _lib.lib()
     depth_keys = torch.empty(2 * BN, dtype=torch.int64, device=dev)
-    perm2 = torch.empty(2 * BN, dtype=torch.int32, device=dev)
+    perm2 = torch.empty(2 * BN, **i32)
     st.perm = perm2[BN:]
     scan_bytes = L.dimo_raster_scan_temp_bytes(BN)
     scan_temp = torch.empty(scan_bytes, dtype=torch.uint8, device=dev)
-    import ctypes
     R_host = ctypes.c_int64(0)
     s = _lib.stream()
     _lib.call("dimo_raster_preprocess", B, N, W, H, st.sh_degree, st.sh_coeffs, st.scale_modifier, _lib.ptr(cams),
@@ -80,30 +85,38 @@ def _forward_impl(cams, means3D, scales, rotations, opacities, shs, colors_preco
               _lib.ptr(shs), _bstride(shs, B, N * st.sh_coeffs * 3),
               _lib.ptr(colors_precomp), _bstride(colors_precomp, B, N * 3),
               _lib.ptr(st.splats), _lib.ptr(st.radii), _lib.ptr(st.tiles_touched), _lib.ptr(st.offsets),
-              _lib.ptr(depth_keys), _lib.ptr(perm2), _lib.ptr(scan_temp), scan_bytes, ctypes.addressof(R_host), s)
-    R = int(R_host.value)
-    st.R = R
-    _lib.PROFILE.extra["R"] = R
+              _lib.ptr(depth_keys), _lib.ptr(perm2), _lib.ptr(scan_temp), scan_bytes,
+              ctypes.addressof(R_host) if capacity is None else None, s)
+    if capacity is None:
+        R = int(R_host.value)
+        st.R = R
+        st.count_overflow = None
+        _lib.PROFILE.extra["R"] = R
+    else:
+        R = int(capacity)
+        st.R = None                                  # true count lives on the device: st.count_overflow[0]
+        st.count_overflow = torch.zeros(2, **i32)
     gx, gy = (W + TILE - 1) // TILE, (H + TILE - 1) // TILE
     Ra = max(R, 1)
-    keys_u = torch.empty(Ra, dtype=torch.int32, device=dev)
-    vals_u = torch.empty(Ra, dtype=torch.int32, device=dev)
-    st.keys_sorted = torch.empty(Ra, dtype=torch.int32, device=dev)        # frame*tiles + tile, sorted
-    st.vals_sorted = torch.empty(Ra, dtype=torch.int32, device=dev)
+    keys_u = torch.empty(Ra, **i32)
+    vals_u = torch.empty(Ra, **i32)
+    st.keys_sorted = torch.empty(Ra, **i32)          # frame*tiles + tile, sorted (sentinel in unused slots)
+    st.vals_sorted = torch.empty(Ra, **i32)
     st.packed = torch.empty(Ra, SPLAT_FLOATS, **f32)
-    st.ranges = torch.empty(B * gx * gy, 2, dtype=torch.int32, device=dev)
+    st.ranges = torch.empty(B * gx * gy, 2, **i32)
     sort_bytes = L.dimo_raster_sort_temp_bytes(Ra)
     sort_temp = torch.empty(sort_bytes, dtype=torch.uint8, device=dev)
     _lib.call("dimo_raster_bin", B, N, W, H, R, _lib.ptr(st.splats), _lib.ptr(st.radii), _lib.ptr(st.perm),
               _lib.ptr(st.offsets),
               _lib.ptr(keys_u), _lib.ptr(vals_u), _lib.ptr(st.keys_sorted), _lib.ptr(st.vals_sorted),
-              _lib.ptr(sort_temp), sort_bytes, _lib.ptr(st.packed), _lib.ptr(st.ranges), s)
+              _lib.ptr(sort_temp), sort_bytes, _lib.ptr(st.packed), _lib.ptr(st.ranges),
+              _lib.ptr(st.count_overflow), s)
     color = torch.empty(B, 3, H, W, **f32)
     depth = torch.empty(B, 1, H, W, **f32)
     normal = torch.empty(B, 3, H, W, **f32)
     alpha = torch.empty(B, 1, H, W, **f32)
     st.final_T = torch.empty(B, H, W, **f32)
-    st.n_contrib = torch.empty(B, H, W, dtype=torch.int32, device=dev)
+    st.n_contrib = torch.empty(B, H, W, **i32)
     _lib.call("dimo_raster_blend_fwd", B, W, H, _lib.ptr(cams), _lib.ptr(st.packed), _lib.ptr(st.ranges),
               _lib.ptr(color), _lib.ptr(depth), _lib.ptr(normal), _lib.ptr(alpha), _lib.ptr(st.final_T),
               _lib.ptr(st.n_contrib), s)
@@ -113,9 +126,10 @@ def _forward_impl(cams, means3D, scales, rotations, opacities, shs, colors_preco
 class _Rasterize(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, scales, rotations, opacities, shs, colors_precomp, cams, B, N, W, H,
-                sh_degree, scale_modifier, state_out):
+                sh_degree, scale_modifier, state_out, capacity):
         color, depth, normal, alpha, st = _forward_impl(cams, means3D, scales, rotations, opacities, shs,
-                                                        colors_precomp, B, N, W, H, sh_degree, scale_modifier)
+                                                        colors_precomp, B, N, W, H, sh_degree, scale_modifier,
+                                                        capacity)
         ctx.st = st
         ctx.save_for_backward(means3D, scales, rotations, shs)
         ctx.shapes = (means3D.shape, None if means2D is None else means2D.shape, scales.shape, rotations.shape,
@@ -177,11 +191,11 @@ class _Rasterize(torch.autograd.Function):
                 fit(d_scales, sh_sc, N * 3), fit(d_rot, sh_rot, N * 4), fit(d_op, sh_op, N),
                 fit(d_shs, sh_shs, N * st.sh_coeffs * 3) if use_sh else None,
                 fit(d_col, sh_col, N * 3) if not use_sh else None,
-                None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None)
 
 
 def rasterize_batch(cams, means3D, scales, rotations, opacities, W, H, shs=None, colors_precomp=None,
-                    sh_degree=0, scale_modifier=1.0, means2D=None, state_out=None):
+                    sh_degree=0, scale_modifier=1.0, means2D=None, state_out=None, capacity=None):
     """cams [B,40]; means3D [B,N,3] or [N,3]; scales [N,3]; rotations [B,N,4] or [N,4]; opacities [N,1]/[N];
     shs [N,K,3] xor colors_precomp [B?,N,3].  Returns color [B,3,H,W], depth [B,1,H,W], normal [B,3,H,W],
     alpha [B,1,H,W], radii [B,N] int32."""
@@ -191,4 +205,5 @@ def rasterize_batch(cams, means3D, scales, rotations, opacities, W, H, shs=None,
     N = scales.shape[-2]
     c = lambda t: None if t is None else t.contiguous().float()
     return _Rasterize.apply(c(means3D), means2D, c(scales), c(rotations), c(opacities), c(shs), c(colors_precomp),
-                            cams.contiguous(), B, N, int(W), int(H), int(sh_degree), float(scale_modifier), state_out)
+                            cams.contiguous(), B, N, int(W), int(H), int(sh_degree), float(scale_modifier), state_out,
+                            capacity)

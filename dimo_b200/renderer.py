@@ -119,30 +119,52 @@ class Renderer:
         self.add_normal = add_normal
 
     # ------------------------------------------------------------------------------------------
-    def render_batch(self, cameras, times, latent_indices, stage="s2", scaling_modifier=1.0, bg_color=None,
-                     override_color=None, xyz_detach=False, clamp=True):
-        """cameras: list of S MiniCam (same W,H); times: list of S floats; latent_indices: list of S ints.
-        Returns a dict of batched tensors: image [S,3,H,W] (clamped), depth, normal, alpha, radii [S,N],
-        visibility_filter, pts_t [S,N,3], cpts_t [U,M,3] + `pair_of_frame` (frame -> unique (motion,t) index)."""
-        g = self.gaussians
-        dev = g._xyz.device
-        S = len(cameras)
-        W, H = int(cameras[0].image_width), int(cameras[0].image_height)
-        # unique (motion, t) pairs: the deformation is view-independent (SURVEY.md F5)
+    def prepare_step(self, cameras, times, latent_indices, bg_color=None, out=None):
+        """Host-side packing of one step's frame list into device tensors (no kernels of ours, no host sync):
+        cams [S,40], t [U], li [U] i64, pf [S] i64 where U = unique (motion, t) pairs (the deformation is
+        view-independent) and pf maps frame -> pair.  `out`: an earlier result whose tensors are
+        overwritten in place (static buffers for CUDA-graph replay; U and S must not change)."""
+        dev = self.gaussians._xyz.device
         pairs, pair_of_frame = {}, []
         for t, li in zip(times, latent_indices):
-            key = (int(li), float(t))
-            pair_of_frame.append(pairs.setdefault(key, len(pairs)))
+            pair_of_frame.append(pairs.setdefault((int(li), float(t)), len(pairs)))
         keys = list(pairs.keys())
-        U = len(keys)
-        t_host = torch.tensor([k[1] for k in keys], dtype=torch.float32)
-        li_host = torch.tensor([k[0] for k in keys], dtype=torch.int64)
-        pf_host = torch.tensor(pair_of_frame, dtype=torch.int64)
-        t_dev = t_host.to(dev, non_blocking=True)
-        li_dev = li_host.to(dev, non_blocking=True)
-        pf_dev = pf_host.to(dev, non_blocking=True)
-        latents = g._latent_codes[li_dev]                                   # [U,L]
+        bg = self.bg_color if bg_color is None else bg_color
+        V = torch.stack([c.world_view_transform for c in cameras]).reshape(-1, 16).float()
+        P = torch.stack([c.full_proj_transform for c in cameras]).reshape(-1, 16).float()
+        C = torch.stack([c.camera_center for c in cameras]).float()
+        S = len(cameras)
+        host = torch.empty(S, 3, dtype=torch.float32)                  # tanfovx, tanfovy, pair index
+        for i, c in enumerate(cameras):
+            host[i, 0] = math.tan(c.FoVx * 0.5); host[i, 1] = math.tan(c.FoVy * 0.5)
+        host[:, 2] = torch.tensor(pair_of_frame, dtype=torch.float32)
+        small = host.to(dev, non_blocking=True)
+        bgd = bg.to(dev).float().reshape(1, 3).expand(S, 3)
+        cams = torch.cat([V, P, C, small[:, 0:2], bgd], dim=1)
+        th = torch.tensor([[k[1], float(k[0])] for k in keys], dtype=torch.float32).to(dev, non_blocking=True)
+        prep = {"cams": cams, "t": th[:, 0].contiguous(), "li": th[:, 1].long(), "pf": small[:, 2].long(),
+                "S": S, "U": len(keys), "W": int(cameras[0].image_width), "H": int(cameras[0].image_height),
+                "pair_of_frame": pair_of_frame, "expand": pair_of_frame != list(range(S))}
+        if out is not None:
+            assert out["S"] == prep["S"] and out["U"] == prep["U"] and out["expand"] == prep["expand"]
+            for k in ("cams", "t", "li", "pf"):
+                out[k].copy_(prep[k])
+            out["pair_of_frame"] = pair_of_frame
+            return out
+        return prep
 
+    def render_batch(self, cameras=None, times=None, latent_indices=None, stage="s2", scaling_modifier=1.0,
+                     bg_color=None, override_color=None, xyz_detach=False, clamp=True, prepared=None, capacity=None):
+        """All S frames of a step in ONE launch set.  cameras: list of S MiniCam (same W,H); times: list of S floats;
+        latent_indices: list of S ints -- or `prepared` = the result of prepare_step().  capacity: instance-slot
+        capacity for the sync-free rasteriser mode (None = exact mode with one host read-back).
+        Returns a dict of batched tensors: image [S,3,H,W] (clamped), image_raw, depth, normal, alpha, radii [S,N],
+        visibility_filter, pts_t [S,N,3], cpts_t [U,M,3] + `pair_of_frame` (frame -> unique (motion,t) index)."""
+        g = self.gaussians
+        prep = prepared if prepared is not None else self.prepare_step(cameras, times, latent_indices, bg_color)
+        W, H = prep["W"], prep["H"]
+        latents = g._latent_codes[prep["li"]]                               # [U,L]
+        t_dev = prep["t"]
         if stage >= "s2":
             dxyz, dquat = g._timenet.forward_batched(g._c_xyz, t_dev, latents)   # [U,M,3],[U,M,4]
             cpts_t = g._c_xyz[None] + dxyz
@@ -152,32 +174,26 @@ class Renderer:
             dxyz, dquat = g._timenet.forward_batched(g._xyz, t_dev, latents)
             cpts_t = g._xyz[None] + dxyz
             means3D_u = cpts_t
-            rot_u = F.normalize(g._rotation)[None].expand(U, -1, -1)
+            rot_u = F.normalize(g._rotation)[None].expand(prep["U"], -1, -1)
         else:
             raise ValueError("Nonexistent stage!!!")
         if xyz_detach:
             means3D_u = means3D_u.detach()
-        means3D = means3D_u[pf_dev] if U != S or pair_of_frame != list(range(S)) else means3D_u
-        rotations = rot_u[pf_dev] if U != S or pair_of_frame != list(range(S)) else rot_u
-
-        bg = self.bg_color if bg_color is None else bg_color
-        V = torch.stack([c.world_view_transform for c in cameras])
-        P = torch.stack([c.full_proj_transform for c in cameras])
-        C = torch.stack([c.camera_center for c in cameras]).float()
-        tan = torch.tensor([[math.tan(c.FoVx * 0.5), math.tan(c.FoVy * 0.5)] for c in cameras], dtype=torch.float32)
-        tan = tan.to(dev, non_blocking=True)
-        cams = _raster.pack_cameras(V, P, C, tan[:, 0], tan[:, 1], bg)
+        means3D = means3D_u[prep["pf"]] if prep["expand"] else means3D_u
+        rotations = rot_u[prep["pf"]] if prep["expand"] else rot_u
 
         shs = colors = None
         if override_color is None:
             shs = g.get_features
         else:
             colors = override_color
+        state = []
         color, depth, normal, alpha, radii = _raster.rasterize_batch(
-            cams, means3D, g.get_scaling, rotations, g.get_opacity, W, H, shs=shs, colors_precomp=colors,
-            sh_degree=g.active_sh_degree, scale_modifier=scaling_modifier)
+            prep["cams"], means3D, g.get_scaling, rotations, g.get_opacity, W, H, shs=shs, colors_precomp=colors,
+            sh_degree=g.active_sh_degree, scale_modifier=scaling_modifier, state_out=state, capacity=capacity)
         return {"image": color.clamp(0, 1) if clamp else None, "image_raw": color, "depth": depth, "normal": normal,
-                "alpha": alpha, "radii": radii, "visibility_filter": radii > 0, "pts_t": means3D, "cpts_t": cpts_t, "pair_of_frame": pair_of_frame}
+                "alpha": alpha, "radii": radii, "visibility_filter": radii > 0, "pts_t": means3D, "cpts_t": cpts_t,
+                "pair_of_frame": prep["pair_of_frame"], "raster_state": state[0]}
 
     # ------------------------------------------------------------------------------------------
     def render(self, viewpoint_camera, scaling_modifier=1.0, bg_color=None, override_color=None,

@@ -5,6 +5,13 @@ north_star terms: find_knn -> S x [deform -> rasterise] -> {MSE per frame, SSIM 
 alpha} -> backward -> (one gradient all-reduce) -> Adam.  All S frames of the step go through ONE
 launch set (Renderer.render_batch).  LPIPS and the ARAP/chamfer/smoothness regularisers are
 SURVEY.md 8f "next" rows and are not part of this step.
+
+Two execution modes, same kernels, same results:
+  eager   every kernel is launched from Python each step; the rasteriser reads the instance count back once
+          per step to size its buffers (the only host sync on the path);
+  graph   the rasteriser runs in capacity mode (no read-back, overflow flag on the device) and the WHOLE step --
+          forward, loss, backward, all-reduce, Adam -- is captured once in a CUDA graph and replayed; only the
+          step's inputs (cameras, times, latent indices, ground truth) are copied into static buffers.
 """
 import torch
 
@@ -67,24 +74,35 @@ def step_loss(image, alpha, gt, mask, n_motions, weights=StepLossWeights):
 
 
 class TrainStep:
-    """Holds the model + optimizer and runs steps.  `world` > 1: one flat fp32 all-reduce (sum) of every
-    gradient per step over NCCL (the only exchange on the path; frames are sharded by motion)."""
+    """Holds the model + optimizer and runs steps.  `world` > 1: the flat gradient buffer is summed over the
+    process group once per step (the only exchange on the path; frames are sharded by motion)."""
 
-    def __init__(self, renderer: Renderer, lr=1e-4, world=1, stage="s2"):
+    def __init__(self, renderer: Renderer, lr=1e-4, world=1, stage="s2", graph=False, probe_steps=3,
+                 capacity_margin=1.4):
         self.r = renderer
         self.g = renderer.gaussians
         self.stage = stage
         self.world = world
         self.params = [p for p in self.g.parameters() if p.numel() > 0]
-        self.opt = torch.optim.Adam(self.params, lr=lr, eps=1e-15, fused=True)
+        self.opt = torch.optim.Adam(self.params, lr=lr, eps=1e-15, fused=True, capturable=bool(graph))
         g = self.g
         # per-Gaussian parameters: their gradients are final once the LBS backward has run, i.e. before the
         # TimeNet backward -> bucket 0 of the flat buffer, all-reduced while the MLP backward executes
         early = [g._xyz, g._features_dc, g._features_rest, g._opacity, g._scaling, g._rotation]
         self.reducer = FlatGradReducer(self.params, early=early)
+        # graph mode state
+        self.use_graph = bool(graph)
+        self.probe_steps = int(probe_steps)
+        self.capacity_margin = float(capacity_margin)
+        self.graph = None
+        self.capacity = None
+        self._seen = 0
+        self._max_R = 0
+        self._static = None
+        self.graph_error = None
 
     def _timed(self, name, fn):
-        if not _lib.PROFILE.enabled:
+        if not _lib.PROFILE.enabled or torch.cuda.is_current_stream_capturing():
             return fn()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -93,13 +111,17 @@ class TrainStep:
         _lib.PROFILE.events.append((name, e0, e1))
         return out
 
-    def run(self, cameras, times, latent_indices, gt, mask, n_motions, optimize=True):
-        """cameras/times/latent_indices: length-S lists ordered motion-major; gt [S,3,H,W], mask [S,1,H,W] on device.
-        Returns the (device) loss tensor."""
+    # ------------------------------------------------------------------------------------------
+    def _body(self, prep, gt, mask, n_motions, optimize=True, capacity=None, overflow_acc=None):
         if self.stage >= "s2":
             self.g.find_knn(4)
         # the loss kernel clamps the render to [0,1] on load (and masks the gradient), so skip the separate clamp pass
-        out = self.r.render_batch(cameras, times, latent_indices, stage=self.stage, clamp=False)
+        out = self.r.render_batch(prepared=prep, stage=self.stage, clamp=False, capacity=capacity)
+        st = out["raster_state"]
+        if capacity is None:
+            self._max_R = max(self._max_R, st.R)
+        elif overflow_acc is not None:
+            overflow_acc.copy_(torch.maximum(overflow_acc, st.count_overflow))
         loss = step_loss(out["image_raw"], out["alpha"], gt, mask, n_motions)
         loss.backward()                                   # gradients accumulate straight into reducer.flat
         if self.world > 1:
@@ -108,3 +130,56 @@ class TrainStep:
             self._timed("py:adam", self.opt.step)
         self._timed("py:zero_grad", self.reducer.zero)
         return loss
+
+    def _capture(self, prep, gt, mask, n_motions, optimize):
+        dev = gt.device
+        self.capacity = int(self._max_R * self.capacity_margin) + 1024
+        self._static = {"prep": {k: (v.clone() if torch.is_tensor(v) else v) for k, v in prep.items()},
+                        "gt": gt.clone(), "mask": mask.clone(),
+                        "overflow": torch.zeros(2, dtype=torch.int32, device=dev), "n_motions": n_motions,
+                        "optimize": optimize}
+        st = self._static
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                      # warm-up in capacity mode (allocator, lazy inits)
+            for _ in range(2):
+                self._body(st["prep"], st["gt"], st["mask"], n_motions, optimize, self.capacity, st["overflow"])
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            st["loss"] = self._body(st["prep"], st["gt"], st["mask"], n_motions, optimize, self.capacity, st["overflow"])
+        self.graph = graph
+
+    def overflowed(self):
+        """graph mode: (max instance count seen, capacity, overflow flag) -- one small device read."""
+        if self._static is None:
+            return self._max_R, None, False
+        cnt, flag = self._static["overflow"].tolist()
+        return cnt, self.capacity, bool(flag)
+
+    # ------------------------------------------------------------------------------------------
+    def run(self, cameras, times, latent_indices, gt, mask, n_motions, optimize=True):
+        """cameras/times/latent_indices: length-S lists ordered motion-major; gt [S,3,H,W], mask [S,1,H,W] on device.
+        Returns the (device) loss tensor."""
+        if not self.use_graph or self.graph_error is not None:
+            prep = self.r.prepare_step(cameras, times, latent_indices)
+            return self._body(prep, gt, mask, n_motions, optimize)
+        if self.graph is None:
+            prep = self.r.prepare_step(cameras, times, latent_indices)
+            if self._seen < self.probe_steps:              # eager probe steps: learn the instance count
+                self._seen += 1
+                return self._body(prep, gt, mask, n_motions, optimize)
+            try:
+                self._capture(prep, gt, mask, n_motions, optimize)
+            except Exception as e:                         # stay correct: fall back to eager and say so
+                self.graph_error = f"{type(e).__name__}: {e}"
+                self.graph = None
+                torch.cuda.synchronize()
+                return self._body(prep, gt, mask, n_motions, optimize)
+        st = self._static
+        self.r.prepare_step(cameras, times, latent_indices, out=st["prep"])
+        st["gt"].copy_(gt, non_blocking=True)
+        st["mask"].copy_(mask, non_blocking=True)
+        self.graph.replay()
+        return st["loss"]

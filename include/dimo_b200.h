@@ -82,13 +82,18 @@ int dimo_raster_preprocess(
 /* Stage 2: emit (frame*tiles + tile) keys front-to-back, stable-sort by tile, pack blend records in sorted
  * order, per-tile ranges.
  *   perm_sorted [B*N] u32 (= perm + B*N of stage 1), keys_* [R] u32, vals_* [R] u32 (index into B*N),
- *   packed [R,16] f32, ranges [B*tiles,2] u32; temp: dimo_raster_sort_temp_bytes(R) bytes. */
+ *   packed [R,16] f32, ranges [B*tiles,2] u32; temp: dimo_raster_sort_temp_bytes(R) bytes.
+ *   R is the number of instance SLOTS.  count_overflow == NULL: R is the exact count read back from stage 1.
+ *   count_overflow != NULL (i32[2], device, [1] zeroed by the caller once): "capacity mode" for sync-free /
+ *   CUDA-graph use -- R is a capacity, unused slots carry a sentinel key that sorts last, [0] receives the true
+ *   count and [1] is set to 1 if it exceeded R (the surplus instances were dropped: the caller must re-run with a
+ *   larger capacity). */
 int dimo_raster_bin(
     int B, int N, int W, int H, int64_t R,
     const float* splats, const int32_t* radii, const uint32_t* perm_sorted, const uint32_t* offsets,
     uint32_t* keys_unsorted, uint32_t* vals_unsorted, uint32_t* keys_sorted, uint32_t* vals_sorted,
     void* sort_temp, size_t sort_temp_bytes,
-    float* packed, uint32_t* ranges, void* stream);
+    float* packed, uint32_t* ranges, int32_t* count_overflow, void* stream);
 
 /* Stage 3: per-tile front-to-back blend.
  *   out_color [B,3,H,W], out_depth [B,1,H,W], out_normal [B,3,H,W], out_alpha [B,1,H,W],

@@ -1,0 +1,93 @@
+"""-m gpu: the sync-free (capacity) rasteriser mode and the whole-step CUDA graph reproduce the eager path."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _cams(views, W, H):
+    from dimo_b200 import raster as draster
+    from dimo_b200.camera import orbit_minicam
+    out = []
+    for v in views:
+        cam = orbit_minicam(v, 8, W, H)
+        out.append(draster.pack_cameras(cam.world_view_transform, cam.full_proj_transform, cam.camera_center,
+                                        math.tan(cam.FoVx / 2), math.tan(cam.FoVy / 2), torch.ones(3, device="cuda")))
+    return torch.cat(out)
+
+
+def test_capacity_mode_equals_exact(cuda):
+    import gpu_parity as gp
+    from dimo_b200 import raster as draster
+    N, W, H = 5000, 96, 80
+    xyz, scales, rot, op, shs = [t.cuda() for t in gp.scene_inputs(N, scale_boost=0.3)]
+    cams = _cams((0, 3), W, H)
+    st = []
+    exact = draster.rasterize_batch(cams, xyz, scales, rot, op, W, H, shs=shs, state_out=st)
+    R = st[0].R
+    stc = []
+    capped = draster.rasterize_batch(cams, xyz, scales, rot, op, W, H, shs=shs, state_out=stc, capacity=R + 777)
+    for a, b in zip(exact, capped):
+        assert torch.equal(a, b)
+    assert stc[0].count_overflow.tolist() == [R, 0]
+    assert torch.equal(stc[0].ranges, st[0].ranges)
+    assert torch.equal(stc[0].keys_sorted[:R], st[0].keys_sorted[:R])
+    assert bool((stc[0].keys_sorted[R:].long() & 0xFFFFFFFF >= cams.shape[0] * 6 * 5).all()), "tail must hold sentinels"
+    # backward through the capped path
+    leaves = [t.clone().requires_grad_(True) for t in (xyz, scales, rot, op, shs)]
+    o1 = draster.rasterize_batch(cams, *leaves[:4], W, H, shs=leaves[4])
+    (o1[0].sum() + o1[3].sum()).backward()
+    g1 = [l.grad.clone() for l in leaves]
+    leaves2 = [t.clone().requires_grad_(True) for t in (xyz, scales, rot, op, shs)]
+    o2 = draster.rasterize_batch(cams, *leaves2[:4], W, H, shs=leaves2[4], capacity=R + 5)
+    (o2[0].sum() + o2[3].sum()).backward()
+    for a, b in zip(g1, [l.grad for l in leaves2]):
+        assert gp.rel_err(b, a) < 1e-5
+    # too small a capacity is detected (and does not crash)
+    sto = []
+    draster.rasterize_batch(cams, xyz, scales, rot, op, W, H, shs=shs, state_out=sto, capacity=max(R // 2, 1))
+    cnt, flag = sto[0].count_overflow.tolist()
+    assert cnt == R and flag == 1
+
+
+def _make_step(graph):
+    from dimo_b200 import synthetic, trainstep
+    from dimo_b200.renderer import Renderer
+    sc = synthetic.make_scene(4000, n_ctrl=64, n_motions=4, seed=3)
+    r = Renderer(sh_degree=0, num_latent_code=4, add_normal=True, device="cuda")
+    r.gaussians.load_state(sc)
+    torch.manual_seed(0)
+    with torch.no_grad():
+        tn = r.gaussians._timenet
+        for lin in (tn.pts_layers[-1], tn.rot_layers[-1]):
+            lin.weight.copy_(0.01 * torch.randn_like(lin.weight))
+    return trainstep.TrainStep(r, lr=1e-4, graph=graph, probe_steps=2)
+
+
+def test_trainstep_graph_matches_eager(cuda):
+    from dimo_b200.camera import orbit_minicam
+    W = H = 64
+    cams_all = [orbit_minicam(v, 4, W, H) for v in range(4)]
+    g = torch.Generator().manual_seed(1)
+    gts = [torch.rand(8, 3, H, W, generator=g).cuda() for _ in range(3)]
+    mks = [torch.rand(8, 1, H, W, generator=g).cuda() for _ in range(3)]
+    losses = {}
+    for mode in (False, True):
+        ts = _make_step(mode)
+        ls = []
+        for i in range(7):
+            frames = [(m, v, f) for m in ((i) % 4, (i + 1) % 4) for v in ((i) % 4, (i + 2) % 4) for f in (i % 5, (i + 3) % 5)]
+            cams = [cams_all[v] for (_, v, _) in frames]
+            times = [f / 5 for (_, _, f) in frames]
+            lat = [m for (m, _, _) in frames]
+            ls.append(float(ts.run(cams, times, lat, gts[i % 3], mks[i % 3], 2)))
+        losses[mode] = ls
+        if mode:
+            assert ts.graph_error is None, ts.graph_error
+            assert ts.graph is not None, "graph was never captured"
+            cnt, cap, flag = ts.overflowed()
+            assert not flag and cnt <= cap
+    for a, b in zip(losses[False], losses[True]):
+        assert abs(a - b) <= 2e-3 * abs(a), (losses[False], losses[True])
