@@ -78,7 +78,7 @@ class TrainStep:
     process group once per step (the only exchange on the path; frames are sharded by motion)."""
 
     def __init__(self, renderer: Renderer, lr=1e-4, world=1, stage="s2", graph=False, probe_steps=3,
-                 capacity_margin=1.4):
+                 capacity_margin=1.25):
         self.r = renderer
         self.g = renderer.gaussians
         self.stage = stage
@@ -141,9 +141,9 @@ class TrainStep:
         st = self._static
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):                      # warm-up in capacity mode (allocator, lazy inits)
-            for _ in range(2):
-                self._body(st["prep"], st["gt"], st["mask"], n_motions, optimize, self.capacity, st["overflow"])
+        with torch.cuda.stream(side):                      # warm-up in capacity mode (allocator, lazy inits);
+            for _ in range(2):                             # no optimizer update: the step sequence stays unchanged
+                self._body(st["prep"], st["gt"], st["mask"], n_motions, False, self.capacity, st["overflow"])
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
