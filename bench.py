@@ -53,6 +53,7 @@ def build_model(wl, rank, device, seed=0):
     import torch
     from dimo_b200 import synthetic
     from dimo_b200.renderer import Renderer
+    torch.manual_seed(seed)               # TimeNet's xavier init (replicated on every rank) draws from the global RNG
     sc = synthetic.make_scene(wl["N"], n_ctrl=wl["M"], n_motions=wl["motions_per_gpu"], seed=seed)
     # each rank owns its own block of motions (latent codes): different seed stream for the latents only
     g = torch.Generator().manual_seed(1000 + rank)
@@ -314,9 +315,17 @@ def run_ours(args, wl):
     for rec in prof.values():
         rec["ms_per_step"] = rec["ms"] / prof_steps
 
-    if rank != 0:
+    def finish():
+        """Multi-rank teardown.  A captured CUDA graph keeps references into the NCCL communicator and
+        destroy_process_group() can block on it, so: drain the device, meet at a barrier, flush, and leave."""
         if world > 1:
-            dist.destroy_process_group()
+            torch.cuda.synchronize()
+            dist.barrier()
+            sys.stdout.flush(); sys.stderr.flush()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
 
     # roofline for the dominant kernel group of the step (measured live above with CUDA events per C-ABI call)
@@ -366,8 +375,7 @@ def run_ours(args, wl):
     if overflow:
         line["invalid"] = "instance capacity overflow during the timed region"
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)

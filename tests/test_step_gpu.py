@@ -56,9 +56,9 @@ def _make_step(graph):
     from dimo_b200 import synthetic, trainstep
     from dimo_b200.renderer import Renderer
     sc = synthetic.make_scene(4000, n_ctrl=64, n_motions=4, seed=3)
+    torch.manual_seed(0)                  # TimeNet's xavier init draws from the global RNG: same net in both modes
     r = Renderer(sh_degree=0, num_latent_code=4, add_normal=True, device="cuda")
     r.gaussians.load_state(sc)
-    torch.manual_seed(0)
     with torch.no_grad():
         tn = r.gaussians._timenet
         for lin in (tn.pts_layers[-1], tn.rot_layers[-1]):
