@@ -110,11 +110,16 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 
 // Forward / data-gradient kernel: 128-row x 64-column output tile, 256 threads (8 warps).
-constexpr int LIN_BN = 64, LIN_THREADS = 256;
-constexpr int LIN_A_BYTES = TC_BM * TC_BK * 4;                       // 16 KB (one of hi / lo)
-constexpr int LIN_B_BYTES = LIN_BN * TC_BK * 4;                      //  8 KB
+constexpr int LIN_BN = 64, LIN_BK = 64, LIN_THREADS = 256;     // 64 K-elements per stage: 8 k-steps, half the barrier rounds
+constexpr int LIN_A_BYTES = TC_BM * LIN_BK * 4;                       // 16 KB (one of hi / lo)
+constexpr int LIN_B_BYTES = LIN_BN * LIN_BK * 4;                      //  8 KB
 constexpr int LIN_STAGE_BYTES = 2 * LIN_A_BYTES + 2 * LIN_B_BYTES;   // 48 KB
 constexpr int LIN_SMEM_BYTES = 2 * LIN_STAGE_BYTES + 1024;
+constexpr int LIN_NA = TC_BM * (LIN_BK / 4) / LIN_THREADS, LIN_NB = LIN_BN * (LIN_BK / 4) / LIN_THREADS;   // 16-byte chunks per thread
+
+__device__ __forceinline__ uint32_t canon_off_n(int row, int chunk, int nchunks) {
+  return (uint32_t)((((row >> 3) * nchunks + chunk) << 7) + ((row & 7) << 4));
+}
 
 __device__ __forceinline__ void split_store(uint8_t* hi_base, uint8_t* lo_base, uint32_t off, const float4 v) {
   const uint4 hi = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
@@ -149,31 +154,32 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) linear_tc_kernel(TcArgs p) {
   const uint32_t tmem_d = tmem_slot;
 
   const uint32_t idesc = make_idesc_tf32(TC_BM, LIN_BN);
-  const uint32_t lbo = p.swap_lbo_sbo ? 1024u : 128u, sbo = p.swap_lbo_sbo ? 128u : 1024u;
-  const int nk = (p.K + TC_BK - 1) / TC_BK;
+  constexpr uint32_t LIN_SBO = (LIN_BK / 4) * 128;    // 8-row groups are LIN_BK/4 core matrices apart
+  const uint32_t lbo = p.swap_lbo_sbo ? LIN_SBO : 128u, sbo = p.swap_lbo_sbo ? 128u : LIN_SBO;
+  const int nk = (p.K + LIN_BK - 1) / LIN_BK;
 
   // Per-thread tile coordinates.  Quarter-warps write the 8 rows of ONE core matrix (128 contiguous bytes ->
   // conflict-free STS.128); neighbouring quarters take the adjacent 16-byte chunk of the same rows, so every global
-  // request covers full 32-byte sectors.  A: 128 rows x 8 chunks = 4 per thread, B: 64 rows x 8 chunks = 2 per thread.
-  int a_row[4], a_chunk[4], b_row[2], b_chunk[2];
+  // request covers full 32-byte sectors.  A: 128 rows x 16 chunks = 8 per thread, B: 64 rows x 16 chunks = 4 per thread.
+  int a_row[LIN_NA], a_chunk[LIN_NA], b_row[LIN_NB], b_chunk[LIN_NB];
 #pragma unroll
-  for (int it = 0; it < 4; ++it) {
+  for (int it = 0; it < LIN_NA; ++it) {
     const int e = tid + it * LIN_THREADS;
     a_row[it] = (((e >> 4) & 15) << 3) | (e & 7);
     a_chunk[it] = ((e >> 8) << 1) | ((e >> 3) & 1);
   }
 #pragma unroll
-  for (int it = 0; it < 2; ++it) {
+  for (int it = 0; it < LIN_NB; ++it) {
     const int e = tid + it * LIN_THREADS;
     b_row[it] = (((e >> 4) & 7) << 3) | (e & 7);
     b_chunk[it] = ((e >> 7) << 1) | ((e >> 3) & 1);
   }
-  float4 va[4], vb[2];
+  float4 va[LIN_NA], vb[LIN_NB];
   // the operands of K-tile kt+1 are fetched into registers while tile kt is converted, stored and multiplied
   auto fetch = [&](int kt) {
-    const int k0 = kt * TC_BK;
+    const int k0 = kt * LIN_BK;
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
+    for (int it = 0; it < LIN_NA; ++it) {
       const int gr = m0 + a_row[it], gk = k0 + a_chunk[it] * 4;
       va[it] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (gr < p.R && gk < p.K) {
@@ -188,7 +194,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) linear_tc_kernel(TcArgs p) {
       }
     }
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
+    for (int it = 0; it < LIN_NB; ++it) {
       const int gn = n0 + b_row[it], gk = k0 + b_chunk[it] * 4;
       vb[it] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (gn < p.No && gk < p.K) vb[it] = *reinterpret_cast<const float4*>(p.Wt + (int64_t)gn * p.K + gk);
@@ -203,9 +209,9 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) linear_tc_kernel(TcArgs p) {
              *b_lo = stage + 2 * LIN_A_BYTES + LIN_B_BYTES;
     if (kt >= 2) tc_mbar_wait(&mma_bar[s], (uint32_t)(((kt >> 1) - 1) & 1));   // MMAs of tile kt-2 have read this stage
 #pragma unroll
-    for (int it = 0; it < 4; ++it) split_store(a_hi, a_lo, canon_off(a_row[it], a_chunk[it]), va[it]);
+    for (int it = 0; it < LIN_NA; ++it) split_store(a_hi, a_lo, canon_off_n(a_row[it], a_chunk[it], LIN_BK / 4), va[it]);
 #pragma unroll
-    for (int it = 0; it < 2; ++it) split_store(b_hi, b_lo, canon_off(b_row[it], b_chunk[it]), vb[it]);
+    for (int it = 0; it < LIN_NB; ++it) split_store(b_hi, b_lo, canon_off_n(b_row[it], b_chunk[it], LIN_BK / 4), vb[it]);
     if (kt + 1 < nk) fetch(kt + 1);          // in flight during the barrier, the MMA issue and the next wait
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async-proxy (MMA) reads
     __syncthreads();
@@ -214,7 +220,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) linear_tc_kernel(TcArgs p) {
       const uint32_t sa_hi = tc_smem_u32(a_hi), sa_lo = tc_smem_u32(a_lo), sb_hi = tc_smem_u32(b_hi),
                      sb_lo = tc_smem_u32(b_lo);
 #pragma unroll
-      for (int ks = 0; ks < TC_BK / 8; ++ks) {
+      for (int ks = 0; ks < LIN_BK / 8; ++ks) {
         const uint32_t koff = (uint32_t)ks * 256u;     // 8 tf32 = two 16-byte chunks = two 128-byte core-matrix blocks
         const uint64_t dah = make_smem_desc(sa_hi + koff, lbo, sbo), dal = make_smem_desc(sa_lo + koff, lbo, sbo);
         const uint64_t dbh = make_smem_desc(sb_hi + koff, lbo, sbo), dbl = make_smem_desc(sb_lo + koff, lbo, sbo);
@@ -503,7 +509,8 @@ extern "C" int dimo_linear_wgrad_tc(int R, int K, int No, const float* dY, int64
   p.R = R; p.K = K; p.No = No; p.dY = dY; p.lddy = lddy; p.mask = mask; p.ldm = ldm; p.X = X; p.ldx = ldx;
   p.dW = dW; p.db = db; p.single_pass = h_tc_knob[1];
   const int tiles = ceil_div(No, TC_BM) * ceil_div(K, TC_BN);
-  int splits = max(1, min(ceil_div(R, 2 * TC_BK), ceil_div(148, tiles)));
+  const int target_ctas = h_tc_knob[2] > 0 ? h_tc_knob[2] : 148;     // knob 2: CTA budget for the row split (tuning)
+  int splits = max(1, min(ceil_div(R, 2 * TC_BK), ceil_div(target_ctas, tiles)));
   p.rows_per_split = ceil_div(ceil_div(R, splits), TC_BK) * TC_BK;
   splits = ceil_div(R, p.rows_per_split);
   dim3 grid(ceil_div(No, TC_BM), ceil_div(K, TC_BN), splits);

@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_bwd_kernel(
             const float alpha = fminf(ALPHA_MAX, bq.y * G);
             if (alpha >= ALPHA_MIN) {
               const float dx = dx0 - (float)i;
-              const float inv = 1.0f / (1.0f - alpha);
+              const float inv = __fdividef(1.0f, 1.0f - alpha);   // alpha <= 0.99: MUFU.RCP (1 ulp) is ample for the 1e-4 bound
               T[i] = T[i] * inv;
               const float w = alpha * T[i];
               const float dotf = gc0[i] * bq.w + gc1[i] * cq.x + gc2[i] * cq.y + gd[i] * cq.z + gn0[i] * cq.w +
