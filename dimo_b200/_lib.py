@@ -31,6 +31,7 @@ _SIGS = {
     "dimo_linear_bwd_weight": (c_int, [c_int] * 3 + [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "dimo_linear_tc": (c_int, [c_int] * 3 + [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_vp]),
     "dimo_linear_wgrad_tc": (c_int, [c_int] * 3 + [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "dimo_linear_wgrad_tc_grouped": (c_int, [c_int, c_int] + [c_vp] * 10 + [c_vp]),
     "dimo_tc_debug_set": (c_int, [c_int, c_int]),
     "dimo_timenet_embed_fwd": (c_int, [c_int] * 3 + [c_vp] * 4 + [c_i64, c_vp]),
     "dimo_timenet_embed_bwd": (c_int, [c_int] * 3 + [c_vp] * 3 + [c_i64, c_vp, c_vp, c_vp]),
@@ -87,7 +88,7 @@ def stream():
 _OWN_LAUNCHES = {
     "dimo_raster_preprocess": 2, "dimo_raster_bin": 2, "dimo_raster_blend_fwd": 1, "dimo_raster_blend_bwd": 1,
     "dimo_raster_preprocess_bwd": 1, "dimo_knn": 1, "dimo_dist3nn": 1, "dimo_linear_fwd": 1,
-    "dimo_linear_bwd_data": 1, "dimo_linear_tc": 1, "dimo_linear_wgrad_tc": 1, "dimo_linear_bwd_weight": 1, "dimo_timenet_embed_fwd": 1,
+    "dimo_linear_bwd_data": 1, "dimo_linear_tc": 1, "dimo_linear_wgrad_tc": 1, "dimo_linear_wgrad_tc_grouped": 1, "dimo_linear_bwd_weight": 1, "dimo_timenet_embed_fwd": 1,
     "dimo_timenet_embed_bwd": 1, "dimo_lbs_fwd": 1, "dimo_lbs_bwd": 1, "dimo_ssim_fwd": 1, "dimo_ssim_bwd": 1,
 }
 

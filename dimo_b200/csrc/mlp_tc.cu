@@ -296,19 +296,35 @@ struct TcWgradArgs {
   float* db;   // [No] or NULL
   int rows_per_split;
   int single_pass;
+  int gx, gy;          // tiles along No and K
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(TcWgradArgs p) {
+// Grouped launch: the weight gradients of all TimeNet layers are independent once the data-gradient chain has
+// produced every dY, so they run as ONE launch (1-D grid over [problem][split][k-tile][n-tile]) instead of twelve
+// sub-wave launches of ~128 CTAs each.
+constexpr int TC_MAX_GROUP = 12;
+struct TcWgradGroup {
+  int n;
+  int cta_start[TC_MAX_GROUP + 1];
+  TcWgradArgs p[TC_MAX_GROUP];
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ TcWgradGroup grp) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t mma_bar[2];
   __shared__ uint32_t tmem_slot;
   __shared__ float s_db[TC_BM];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n0 = blockIdx.x * TC_BM, k0 = blockIdx.y * TC_BN;
-  const int r_begin = blockIdx.z * p.rows_per_split;
+  int gi = 0;
+  while (gi + 1 < grp.n && (int)blockIdx.x >= grp.cta_start[gi + 1]) ++gi;
+  const TcWgradArgs& p = grp.p[gi];
+  const int local = (int)blockIdx.x - grp.cta_start[gi];
+  const int bx = local % p.gx, by = (local / p.gx) % p.gy, bz = local / (p.gx * p.gy);
+  const int n0 = bx * TC_BM, k0 = by * TC_BN;
+  const int r_begin = bz * p.rows_per_split;
   const int r_end = min(p.R, r_begin + p.rows_per_split);
-  const bool do_db = p.db != nullptr && blockIdx.y == 0;
+  const bool do_db = p.db != nullptr && by == 0;
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_slot)),
@@ -491,30 +507,68 @@ extern "C" int dimo_linear_tc(int R, int K, int No, const float* X, int64_t ldx,
   return 0;
 }
 
-extern "C" int dimo_linear_wgrad_tc(int R, int K, int No, const float* dY, int64_t lddy, const float* mask, int64_t ldm,
-                                    const float* X, int64_t ldx, float* dW, float* db, void* stream) {
-  if (R == 0 || No == 0 || K == 0) return 0;
+static int wgrad_fill(TcWgradArgs& p, int R, int K, int No, const float* dY, int64_t lddy, const float* mask,
+                      int64_t ldm, const float* X, int64_t ldx, float* dW, float* db, int target_ctas) {
   DIMO_REQUIRE(No % 4 == 0 && K % 4 == 0 && lddy % 4 == 0 && ldx % 4 == 0,
                "tensor-core wgrad: No, K, lddy, ldx must be multiples of 4 floats");
   DIMO_REQUIRE((reinterpret_cast<uintptr_t>(dY) & 15) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0,
                "tensor-core wgrad: dY and X must be 16-byte aligned");
   DIMO_REQUIRE(mask == nullptr || (ldm % 4 == 0 && (reinterpret_cast<uintptr_t>(mask) & 15) == 0),
                "tensor-core wgrad: mask must be 16-byte aligned");
+  p = TcWgradArgs{};
+  p.R = R; p.K = K; p.No = No; p.dY = dY; p.lddy = lddy; p.mask = mask; p.ldm = ldm; p.X = X; p.ldx = ldx;
+  p.dW = dW; p.db = db; p.single_pass = h_tc_knob[1];
+  p.gx = ceil_div(No, TC_BM); p.gy = ceil_div(K, TC_BN);
+  const int tiles = p.gx * p.gy;
+  int splits = max(1, min(ceil_div(R, 2 * TC_BK), ceil_div(target_ctas, tiles)));
+  p.rows_per_split = ceil_div(ceil_div(R, splits), TC_BK) * TC_BK;
+  splits = ceil_div(R, p.rows_per_split);
+  return tiles * splits;       // CTAs of this problem
+}
+
+static int wgrad_launch(const TcWgradGroup& grp, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     DIMO_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     attr_set = true;
   }
-  TcWgradArgs p{};
-  p.R = R; p.K = K; p.No = No; p.dY = dY; p.lddy = lddy; p.mask = mask; p.ldm = ldm; p.X = X; p.ldx = ldx;
-  p.dW = dW; p.db = db; p.single_pass = h_tc_knob[1];
-  const int tiles = ceil_div(No, TC_BM) * ceil_div(K, TC_BN);
-  const int target_ctas = h_tc_knob[2] > 0 ? h_tc_knob[2] : 148;     // knob 2: CTA budget for the row split (tuning)
-  int splits = max(1, min(ceil_div(R, 2 * TC_BK), ceil_div(target_ctas, tiles)));
-  p.rows_per_split = ceil_div(ceil_div(R, splits), TC_BK) * TC_BK;
-  splits = ceil_div(R, p.rows_per_split);
-  dim3 grid(ceil_div(No, TC_BM), ceil_div(K, TC_BN), splits);
-  wgrad_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(p);
+  const int total = grp.cta_start[grp.n];
+  if (total == 0) return 0;
+  wgrad_tc_kernel<<<total, TC_THREADS, TC_SMEM_BYTES, st>>>(grp);
   DIMO_CHECK_LAUNCH();
   return 0;
+}
+
+extern "C" int dimo_linear_wgrad_tc(int R, int K, int No, const float* dY, int64_t lddy, const float* mask, int64_t ldm,
+                                    const float* X, int64_t ldx, float* dW, float* db, void* stream) {
+  if (R == 0 || No == 0 || K == 0) return 0;
+  TcWgradGroup grp{};
+  grp.n = 1;
+  const int target_ctas = h_tc_knob[2] > 0 ? h_tc_knob[2] : 148;     // knob 2: CTA budget for the row split (tuning)
+  const int ctas = wgrad_fill(grp.p[0], R, K, No, dY, lddy, mask, ldm, X, ldx, dW, db, target_ctas);
+  if (ctas < 0) return ctas;
+  grp.cta_start[0] = 0; grp.cta_start[1] = ctas;
+  return wgrad_launch(grp, (cudaStream_t)stream);
+}
+
+extern "C" int dimo_linear_wgrad_tc_grouped(int n, int R, const int* K, const int* No, const float* const* dY,
+                                            const int64_t* lddy, const float* const* mask, const int64_t* ldm,
+                                            const float* const* X, const int64_t* ldx, float* const* dW,
+                                            float* const* db, void* stream) {
+  DIMO_REQUIRE(n >= 0 && n <= TC_MAX_GROUP, "at most 12 problems per grouped weight-gradient launch");
+  if (n == 0 || R == 0) return 0;
+  TcWgradGroup grp{};
+  grp.n = n;
+  // every problem gets enough row splits to keep ~2 waves of CTAs in flight over the whole group
+  const int target_ctas = h_tc_knob[2] > 0 ? h_tc_knob[2] : max(32, 2 * 148 / n);
+  int start = 0;
+  for (int i = 0; i < n; ++i) {
+    grp.cta_start[i] = start;
+    const int ctas = wgrad_fill(grp.p[i], R, K[i], No[i], dY[i], lddy[i], mask[i], ldm[i], X[i], ldx[i], dW[i], db[i],
+                                target_ctas);
+    if (ctas < 0) return ctas;
+    start += ctas;
+  }
+  grp.cta_start[n] = start;
+  return wgrad_launch(grp, (cudaStream_t)stream);
 }

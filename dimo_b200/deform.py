@@ -5,6 +5,7 @@ linear-blend skinning, batched over the G unique (motion, t) pairs of a step.
 184-203: deformnet.{0..7}, pts_layers.{0,2}, rot_layers.{0,2}) so released `timenet.pth` checkpoints
 load unchanged; its forward runs libdimo_b200 kernels through `_TimeNetFn` instead of F.linear.
 """
+import ctypes
 import os
 
 import torch
@@ -98,12 +99,12 @@ class _TimeNetFn(torch.autograd.Function):
         dbs = [torch.zeros(W.shape[0], **f32) for W in Ws]
 
         keep = []    # transposed weights must outlive the asynchronous launches that read them
+        deferred = []   # tensor-core weight gradients: independent of each other -> ONE grouped launch at the end
 
         def bwd_layer(li, K, No, dY_ptr, lddy, Y_ptr, ldy, X_ptr, ldx, dX_ptr, lddx, accumulate):
             if USE_TC and TC_WGRAD and No % 4 == 0 and K % 4 == 0 and lddy % 4 == 0 and ldx % 4 == 0 and \
                     (Y_ptr is None or ldy % 4 == 0):
-                _lib.call("dimo_linear_wgrad_tc", R, K, No, dY_ptr, lddy, Y_ptr, ldy if Y_ptr is not None else 0,
-                          X_ptr, ldx, _lib.ptr(dWs[li]), _lib.ptr(dbs[li]), s)
+                deferred.append((li, K, No, dY_ptr, lddy, Y_ptr, ldy if Y_ptr is not None else 0, X_ptr, ldx))
             else:
                 _lib.call("dimo_linear_bwd_weight", R, K, No, dY_ptr, lddy, Y_ptr, ldy, X_ptr, ldx,
                           _lib.ptr(dWs[li]), _lib.ptr(dbs[li]), s)
@@ -130,11 +131,11 @@ class _TimeNetFn(torch.autograd.Function):
                   dh.data_ptr(), HIDDEN, False)
         bwd_layer(10, HIDDEN, HIDDEN, dhr.data_ptr(), HIDDEN, hr.data_ptr(), HIDDEN, h.data_ptr(), HIDDEN,
                   dh.data_ptr(), HIDDEN, True)
-        # trunk, layers 7..0 ; dcat collects the skip-concatenated gradient [dh0 | d(out of layer 4)]
+        # trunk, layers 7..0 ; dcat collects the skip-concatenated gradient [dh0 | d(out of layer 4)].  Every layer's
+        # incoming gradient keeps its own buffer (no ping-pong) because the weight gradients read them at the end.
         dcat = torch.empty(R, CAT, **f32)
         dY_ptr, lddy = dh.data_ptr(), HIDDEN
-        bufs = [dh, torch.empty(R, HIDDEN, **f32)]
-        cur = 0
+        grads_alive = [dh]
         for i in range(DEPTH - 1, -1, -1):
             if i == SKIP_AFTER:
                 Y_ptr, ldy = cat.data_ptr() + 4 * E, CAT
@@ -153,13 +154,23 @@ class _TimeNetFn(torch.autograd.Function):
                 else:
                     X_ptr, ldx = prev.data_ptr(), HIDDEN
                 K = HIDDEN
-                cur ^= 1
-                dX_ptr, lddx, accumulate = bufs[cur].data_ptr(), HIDDEN, False
+                buf = torch.empty(R, HIDDEN, **f32)
+                grads_alive.append(buf)
+                dX_ptr, lddx, accumulate = buf.data_ptr(), HIDDEN, False
             bwd_layer(i, K, HIDDEN, dY_ptr, lddy, Y_ptr, ldy, X_ptr, ldx, dX_ptr, lddx, accumulate)
             if i == SKIP_AFTER + 1:
                 dY_ptr, lddy = dcat.data_ptr() + 4 * E, CAT
             else:
                 dY_ptr, lddy = dX_ptr, lddx
+        if deferred:
+            n = len(deferred)
+            ia = lambda vals: (ctypes.c_int * n)(*vals)
+            la = lambda vals: (ctypes.c_int64 * n)(*vals)
+            pa = lambda vals: (ctypes.c_void_p * n)(*vals)
+            _lib.call("dimo_linear_wgrad_tc_grouped", n, R, ia([d[1] for d in deferred]), ia([d[2] for d in deferred]),
+                      pa([d[3] for d in deferred]), la([d[4] for d in deferred]), pa([d[5] for d in deferred]),
+                      la([d[6] for d in deferred]), pa([d[7] for d in deferred]), la([d[8] for d in deferred]),
+                      pa([dWs[d[0]].data_ptr() for d in deferred]), pa([dbs[d[0]].data_ptr() for d in deferred]), s)
         need_pts, need_lat = ctx.needs_input_grad[0], ctx.needs_input_grad[2]
         dpts = torch.zeros(M, 3, **f32) if need_pts else None
         dlat = torch.zeros(G, L, **f32) if need_lat else None

@@ -162,6 +162,11 @@ int dimo_linear_tc(int R, int K, int No, const float* X, int64_t ldx, const floa
  *   No, K, lddy, ldx (ldm) multiples of 4 floats; 16-byte aligned operands.  dW/db accumulate (caller zeroes). */
 int dimo_linear_wgrad_tc(int R, int K, int No, const float* dY, int64_t lddy, const float* mask, int64_t ldm,
                          const float* X, int64_t ldx, float* dW, float* db, void* stream);
+/* The same for n <= 12 independent layers (same R) in ONE launch: every argument is a host array of length n. */
+int dimo_linear_wgrad_tc_grouped(int n, int R, const int* K, const int* No, const float* const* dY,
+                                 const int64_t* lddy, const float* const* mask, const int64_t* ldm,
+                                 const float* const* X, const int64_t* ldx, float* const* dW, float* const* db,
+                                 void* stream);
 /* bring-up knobs for the kernels above (0: swap LBO/SBO, 1: single-pass TF32); not part of the stable ABI */
 int dimo_tc_debug_set(int key, int value);
 
