@@ -199,7 +199,7 @@ def run_ours(args, wl):
     from dimo_b200.camera import orbit_minicam
 
     r, _ = build_model(wl, rank, dev)
-    ts = trainstep.TrainStep(r, lr=1e-5, world=world, graph=not args.no_graph, probe_steps=6)
+    ts = trainstep.TrainStep(r, lr=1e-5, world=world, graph=not args.no_graph, probe_steps=6, capacity_margin=1.12)
     H, W = wl["H"], wl["W"]
     S = wl["bm"] * wl["bv"] * wl["bf"]
     cams_all = [orbit_minicam(v, wl["views"], W, H, device=dev) for v in range(wl["views"])]

@@ -34,7 +34,7 @@ _SIGS = {
     "dimo_linear_wgrad_tc_grouped": (c_int, [c_int, c_int] + [c_vp] * 10 + [c_vp]),
     "dimo_tc_debug_set": (c_int, [c_int, c_int]),
     "dimo_timenet_embed_fwd": (c_int, [c_int] * 3 + [c_vp] * 4 + [c_i64, c_vp]),
-    "dimo_timenet_embed_bwd": (c_int, [c_int] * 3 + [c_vp] * 3 + [c_i64, c_vp, c_vp, c_vp]),
+    "dimo_timenet_embed_bwd": (c_int, [c_int] * 3 + [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "dimo_lbs_fwd": (c_int, [c_int] * 4 + [c_vp] * 11),
     "dimo_lbs_bwd": (c_int, [c_int] * 4 + [c_vp] * 17),
     "dimo_ssim_fwd": (c_int, [c_int] * 5 + [c_vp] * 5),

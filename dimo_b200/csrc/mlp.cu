@@ -1,11 +1,10 @@
 // TimeNet (renderer/latent_gs_renderer.py:184-235) building blocks: positional-encoding embedding
 // (src/pos_enc.py:6-54) and fused Linear(+bias)(+ReLU) forward / data-grad / weight-grad.
 //
-// Round-1 implementation: FP32 SIMT tiled GEMM (64x64x16 tiles, 4x4 register micro-tiles) with the
+// FP32 SIMT tiled GEMM (64x64x16 tiles, 4x4 register micro-tiles, register prefetch + double-buffered smem) with the
 // epilogues fused (bias, ReLU, ReLU-mask on the incoming gradient, bias-gradient reduction, split-R
-// weight-gradient accumulation).  FP32 is what the 1e-4 parity bound needs (the reference runs cuBLAS
-// SGEMM with TF32 off); the tcgen05 3xTF32 variant of this same contraction is the next step for this
-// kernel.
+// weight-gradient accumulation).  It serves the 3- and 4-wide head layers and is the A/B reference (DIMO_TC=0) of
+// the tcgen05 3xTF32 kernels in mlp_tc.cu, which run everything else.
 //
 // One generic kernel computes  C[i,j] (=|+=|atomic+=) sum_l A(i,l) * B(l,j)  with arbitrary element
 // strides; the three layer operations pick strides so that global loads stay coalesced:
@@ -165,31 +164,62 @@ __global__ void __launch_bounds__(128) embed_fwd_kernel(int G, int Mrows, int L,
   }
 }
 
-// dpts[m,d] += sum_g sum_k 2^k (cos(2^k x) dh[6k+d] - sin(2^k x) dh[6k+3+d]) ; dlatents[g,l] += sum_m dh[72+l]
-__global__ void __launch_bounds__(256) embed_bwd_kernel(int G, int Mrows, int L, const float* __restrict__ pts,
+// dpts[m,d] += sum_g sum_k 2^k (cos(2^k x) dh[6k+d] - sin(2^k x) dh[6k+3+d]) ; dlatents[g,l] += sum_m dh[72+l].
+// One warp per row, EMB_ROWS_PER_WARP rows per warp: lanes read the row's 104 gradient values and the sin/cos
+// values the forward pass left in h0 (no transcendental is recomputed), fully coalesced.
+constexpr int EMB_ROWS_PER_WARP = 4;
+
+__global__ void __launch_bounds__(256) embed_bwd_kernel(int G, int Mrows, int L, const float* __restrict__ h0,
                                                         const float* __restrict__ dh0, int64_t ldh,
                                                         float* __restrict__ dpts, float* __restrict__ dlatents) {
-  const int g = blockIdx.y;
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
   extern __shared__ float slat[];   // [L] partial sums of this block
+  const int g = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int l = threadIdx.x; l < L; l += blockDim.x) slat[l] = 0.f;
   __syncthreads();
-  if (m < Mrows) {
+  const int row_base = (blockIdx.x * (blockDim.x >> 5) + warp) * EMB_ROWS_PER_WARP;
+  float lat_acc[4] = {0.f, 0.f, 0.f, 0.f};     // latent columns lane, lane+32, ... (L <= 128)
+  for (int rr = 0; rr < EMB_ROWS_PER_WARP; ++rr) {
+    const int m = row_base + rr;
+    if (m >= Mrows) break;
     const float* dh = dh0 + ((int64_t)g * Mrows + m) * ldh;
+    const float* hv = h0 + ((int64_t)g * Mrows + m) * ldh;
     if (dpts != nullptr) {
       float gp[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        const float x = pts[3 * m + d];
-        for (int k = 0; k < PTS_FREQS; ++k) {
-          const float f = (float)(1 << k), a = x * f;
-          gp[d] += f * (cosf(a) * dh[6 * k + d] - sinf(a) * dh[6 * k + 3 + d]);
+      for (int half = 0; half < 2; ++half) {
+        const int c = lane + 32 * half;
+        if (c < 60) {
+          const int k = c / 6, rem = c - 6 * k, d = rem % 3;
+          const float f = (float)(1 << k);
+          // column c holds sin(f x_d) if rem < 3 (its derivative uses the cos stored 3 columns later), else cos
+          const float term = rem < 3 ? f * hv[c + 3] * dh[c] : -f * hv[c - 3] * dh[c];
+          gp[0] += d == 0 ? term : 0.f;
+          gp[1] += d == 1 ? term : 0.f;
+          gp[2] += d == 2 ? term : 0.f;
         }
-        atomicAdd(&dpts[3 * m + d], gp[d]);
+      }
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) gp[d] += __shfl_xor_sync(0xffffffffu, gp[d], o);
+      }
+      if (lane < 3) atomicAdd(&dpts[3 * m + lane], lane == 0 ? gp[0] : (lane == 1 ? gp[1] : gp[2]));
+    }
+    if (dlatents != nullptr) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int l = lane + 32 * q;
+        if (l < L) lat_acc[q] += dh[EMB_XT + l];
       }
     }
-    if (dlatents != nullptr)
-      for (int l = 0; l < L; ++l) atomicAdd(&slat[l], dh[EMB_XT + l]);
+  }
+  if (dlatents != nullptr) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int l = lane + 32 * q;
+      if (l < L) atomicAdd(&slat[l], lat_acc[q]);
+    }
   }
   __syncthreads();
   if (dlatents != nullptr)
@@ -261,12 +291,12 @@ extern "C" int dimo_timenet_embed_fwd(int G, int rows_per_group, int L, const fl
   return 0;
 }
 
-extern "C" int dimo_timenet_embed_bwd(int G, int rows_per_group, int L, const float* pts, const float* times,
-                                      const float* dh0, int64_t ldh, float* dpts, float* dlatents, void* stream) {
-  (void)times;
+extern "C" int dimo_timenet_embed_bwd(int G, int rows_per_group, int L, const float* h0, const float* dh0,
+                                      int64_t ldh, float* dpts, float* dlatents, void* stream) {
   if (G == 0 || rows_per_group == 0) return 0;
-  dim3 grid(ceil_div(rows_per_group, 256), G);
-  embed_bwd_kernel<<<grid, 256, sizeof(float) * (size_t)max(L, 1), (cudaStream_t)stream>>>(G, rows_per_group, L, pts,
+  DIMO_REQUIRE(L <= 128, "latent dimension must be <= 128");
+  dim3 grid(ceil_div(rows_per_group, 8 * EMB_ROWS_PER_WARP), G);
+  embed_bwd_kernel<<<grid, 256, sizeof(float) * (size_t)max(L, 1), (cudaStream_t)stream>>>(G, rows_per_group, L, h0,
                                                                                           dh0, ldh, dpts, dlatents);
   DIMO_CHECK_LAUNCH();
   return 0;

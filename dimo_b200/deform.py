@@ -175,7 +175,7 @@ class _TimeNetFn(torch.autograd.Function):
         dpts = torch.zeros(M, 3, **f32) if need_pts else None
         dlat = torch.zeros(G, L, **f32) if need_lat else None
         if need_pts or need_lat:
-            _lib.call("dimo_timenet_embed_bwd", G, M, L, _lib.ptr(pts), _lib.ptr(times), _lib.ptr(dcat), CAT,
+            _lib.call("dimo_timenet_embed_bwd", G, M, L, _lib.ptr(cat), _lib.ptr(dcat), CAT,
                       _lib.ptr(dpts), _lib.ptr(dlat), s)
         grads = []
         for W, b in zip(dWs, dbs):

@@ -175,9 +175,10 @@ int dimo_tc_debug_set(int key, int value);
  * times[g], latents[g*L..].  pts [rows_per_group,3] shared by all groups. */
 int dimo_timenet_embed_fwd(int G, int rows_per_group, int L, const float* pts, const float* times,
                            const float* latents, float* h0, int64_t ldh, void* stream);
-/* backward of the embedding: dpts [rows_per_group,3] += , dlatents [G,L] += */
-int dimo_timenet_embed_bwd(int G, int rows_per_group, int L, const float* pts, const float* times,
-                           const float* dh0, int64_t ldh, float* dpts, float* dlatents, void* stream);
+/* backward of the embedding: dpts [rows_per_group,3] += , dlatents [G,L] += .  h0 is the forward output (its
+ * sin/cos columns are reused instead of being recomputed); h0 and dh0 share the row stride ldh. */
+int dimo_timenet_embed_bwd(int G, int rows_per_group, int L, const float* h0, const float* dh0, int64_t ldh,
+                           float* dpts, float* dlatents, void* stream);
 
 /* LBS skinning + activations for B (motion,t) frames over N Gaussians with K neighbours.
  *   xyz [N,3], rot [N,4], idx [N,K] i64, dist [N,K], c_xyz [M,3], c_radius_raw [M] (log-radius),
