@@ -117,9 +117,69 @@ def compare_raster(o, c, verbose=True):
     return ints, flo, gr
 
 
+def run_step_pair(N=1500, M=32, W=64, H=64, device="cuda"):
+    """One full deform -> raster -> loss step (4 frames: 2 motions x 1 view x 2 times) on the CUDA fast path and on the
+    oracle, same seeded inputs.  Returns (loss_cuda, loss_oracle, grads_cuda, grads_oracle) for a few parameters."""
+    from dimo_b200 import trainstep
+    from dimo_b200.renderer import Renderer
+    from oracle import loss as oloss, knn as oknn
+    sc = synthetic.make_scene(N, n_ctrl=M, n_motions=2, seed=11)
+    params = odeform.timenet_init(32, seed=5, final_scale=0.05)
+    frames = [(0, 1, 0.25), (0, 1, 0.75), (1, 1, 0.25), (1, 1, 0.75)]      # (motion, view, t), motion-major
+    g = torch.Generator().manual_seed(2)
+    gt = torch.rand(4, 3, H, W, generator=g); mk = torch.rand(4, 1, H, W, generator=g)
+    lw = trainstep.StepLossWeights
+
+    # ---- oracle ----
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sc.items()}
+    op = [(Wt.clone().requires_grad_(True), b.clone().requires_grad_(True)) for Wt, b in params]
+    dist, idx = oknn.knn(sc["_c_xyz"], sc["_xyz"], 4)
+    imgs, alphas = [], []
+    for (m, v, t) in frames:
+        cam = ocamera.orbit_cam(v, 4, W, H)
+        dxyz, dquat = odeform.timenet_forward(op, leaves["_c_xyz"], t, leaves["_latent_codes"][m])
+        means, rots = odeform.lbs_deform(leaves["_xyz"], leaves["_rotation"], leaves["_c_xyz"],
+                                         torch.exp(leaves["_c_radius"]), dxyz, dquat, idx, dist)
+        out = oraster.rasterize(means, torch.exp(leaves["_scaling"]), rots, torch.sigmoid(leaves["_opacity"]),
+                                cam.world_view_transform, cam.full_proj_transform, cam.camera_center, cam.tanfovx,
+                                cam.tanfovy, W, H, torch.ones(3), shs=torch.cat([leaves["_features_dc"], leaves["_features_rest"]], 1))
+        imgs.append(out["image"].clamp(0, 1)); alphas.append(out["alpha"])
+    img = torch.stack(imgs); alp = torch.stack(alphas)
+    lo = 0
+    for f in range(4):
+        lo = lo + lw.lambda_mse * oloss.mse_loss(img[f], gt[f])
+    for m in range(2):
+        sl = slice(2 * m, 2 * m + 2)
+        lo = lo + lw.lambda_ssim * (1 - oloss.ssim(img[sl], gt[sl])) + lw.lambda_mask * oloss.mse_loss(alp[sl], mk[sl])
+    lo.backward()
+
+    # ---- CUDA fast path (eager TrainStep, no optimizer update) ----
+    r = Renderer(sh_degree=0, num_latent_code=2, add_normal=True, device=device)
+    r.gaussians.load_state(sc)
+    with torch.no_grad():
+        for p_pair, (Wt, b) in zip(zip(r.gaussians._timenet.flat_params()[0::2], r.gaussians._timenet.flat_params()[1::2]), params):
+            p_pair[0].copy_(Wt); p_pair[1].copy_(b)
+    ts = trainstep.TrainStep(r, lr=0.0)
+    cams = [orbit_minicam(v, 4, W, H, device=device) for (_, v, _) in frames]
+    prep = r.prepare_step(cams, [t for (_, _, t) in frames], [m for (m, _, _) in frames])
+    ts.g.find_knn(4)
+    out = r.render_batch(prepared=prep, stage="s2", clamp=False)
+    lc = trainstep.step_loss(out["image_raw"], out["alpha"], gt.to(device), mk.to(device), 2)
+    lc.backward()
+    torch.cuda.synchronize()
+    gc = {"xyz": r.gaussians._xyz.grad, "opacity": r.gaussians._opacity.grad, "c_xyz": r.gaussians._c_xyz.grad,
+          "latents": r.gaussians._latent_codes.grad, "W0": r.gaussians._timenet.deformnet[0].weight.grad}
+    go = {"xyz": leaves["_xyz"].grad, "opacity": leaves["_opacity"].grad, "c_xyz": leaves["_c_xyz"].grad,
+          "latents": leaves["_latent_codes"].grad, "W0": op[0][0].grad}
+    return float(lc), float(lo), gc, go
+
+
 def smoke():
     o, c = run_raster_pair(800, 64, 64)
     ints, flo, gr = compare_raster(o, c)
     assert all(v == 0 for v in ints.values()), ints
     assert all(flo[k] < PIX_TOL for k in ("image", "depth", "normal", "alpha")), flo
     assert all(v < 5 * GRAD_TOL for v in gr.values()), gr
+    lc, lo, gc, go = run_step_pair()
+    print(f"full step: loss cuda {lc:.6f} oracle {lo:.6f}")
+    assert abs(lc - lo) <= 1e-4 * abs(lo), (lc, lo)
