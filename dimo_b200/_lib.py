@@ -20,8 +20,8 @@ _SIGS = {
     "dimo_raster_scan_temp_bytes": (c_sz, [c_i64]),
     "dimo_raster_sort_temp_bytes": (c_sz, [c_i64]),
     "dimo_raster_preprocess": (c_int, [c_int] * 6 + [c_f32, c_vp] + [c_vp, c_i64] * 6 + [c_vp] * 6 + [c_vp, c_sz, c_vp, c_vp]),
-    "dimo_raster_bin": (c_int, [c_int] * 4 + [c_i64] + [c_vp] * 8 + [c_vp, c_sz, c_vp, c_vp, c_vp, c_vp]),
-    "dimo_raster_blend_fwd": (c_int, [c_int] * 3 + [c_vp] * 10),
+    "dimo_raster_bin": (c_int, [c_int] * 4 + [c_i64] + [c_vp] * 8 + [c_vp, c_sz, c_vp, c_vp, c_vp]),
+    "dimo_raster_blend_fwd": (c_int, [c_int] * 3 + [c_vp] * 11),
     "dimo_raster_blend_bwd": (c_int, [c_int] * 4 + [c_vp] * 12),
     "dimo_raster_preprocess_bwd": (c_int, [c_int] * 6 + [c_f32, c_vp] + [c_vp, c_i64] * 4 + [c_vp] * 10),
     "dimo_knn": (c_int, [c_int] * 3 + [c_vp] * 5),
@@ -62,6 +62,11 @@ def lib():
                 fn.argtypes = args
         if L.dimo_abi_version() != 1:
             raise RuntimeError("libdimo_b200.so ABI version mismatch")
+        # bring-up knobs for A/B runs, e.g. DIMO_KNOBS="3=1,2=148" (see dimo_tc_debug_set in include/dimo_b200.h)
+        for kv in filter(None, os.environ.get("DIMO_KNOBS", "").split(",")):
+            k, v = kv.split("=")
+            if L.dimo_tc_debug_set(int(k), int(v)) != 0:
+                raise RuntimeError(f"bad DIMO_KNOBS entry {kv!r}")
         _lib = L
     return _lib
 

@@ -477,9 +477,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(const __grid_co
 
 using namespace dimo;
 
+namespace dimo { extern int g_blend_gather_mode; }   // raster_blend.cu
+
 extern "C" int dimo_tc_debug_set(int key, int value) {
   if (key < 0 || key >= 4) return -2;
   h_tc_knob[key] = value;
+  if (key == 3) dimo::g_blend_gather_mode = value != 0;
   return 0;
 }
 

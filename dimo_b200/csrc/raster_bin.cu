@@ -1,5 +1,5 @@
 // Binning stage of the tile rasteriser: inclusive scan of per-splat tile counts, key emission,
-// (tile|depth) radix sort, packing of splat records into sorted order and per-tile ranges.
+// stable radix sort by tile id, per-tile ranges.
 //
 // Upstream shape (diff_gauss / diff_gaussian_rasterization, call site
 // renderer/latent_gs_renderer.py:1256-1277): InclusiveSum -> duplicateWithKeys -> SortPairs over
@@ -12,9 +12,11 @@
 //      (14 bits = 2 passes at 512^2 x 16 frames, 32 B per instance).
 // A stable sort keeps the emission order inside a tile, i.e. ascending depth with ties in ascending Gaussian
 // index -- bit-for-bit the order of the 64-bit sort (tests compare against the oracle's stable 64-bit sort).
-// The sorted instance list is then materialised as contiguous 64-byte blend records ("packed") so the blend
-// kernels stream each tile's list with 1-D bulk TMA instead of gathering by index.  Scan and sorts are CUB
-// device primitives compiled into this library (integer-only, HBM-bound).
+// The blend kernels gather the 64-byte blend records of a tile's list by index (`vals_sorted` -> record table
+// written by the preprocess kernel): the table (B*N records) is far smaller than the instance list and mostly
+// L2-resident, and only the part of a list in front of the saturation depth is ever fetched -- materialising all R
+// records in sorted order (the first version of this file) cost more than both sorts together.  Scan and sorts
+// are CUB device primitives compiled into this library (integer-only, HBM-bound).
 #include "common.cuh"
 #include <cub/cub.cuh>
 #include <stdarg.h>
@@ -30,47 +32,18 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
-// 4 lanes per instance: lane q copies float4 #q of the 64-byte record (reads: 64 B contiguous per
-// instance, writes: fully coalesced).  Lane 0 also writes the tile range boundaries.
+// Per-tile [begin, end) ranges of the sorted instance list: one thread per slot compares its key with its neighbours.
 //
 // `R` is the number of SLOTS: with an exact instance count every slot is valid; in capacity mode (no host
 // read-back of the count) the unused tail carries sentinel keys (>= ntiles) which sort last and are skipped here.
-__global__ void __launch_bounds__(256) pack_ranges_kernel(int64_t R, uint32_t ntiles, const uint32_t* __restrict__ keys,
-                                                          const uint32_t* __restrict__ vals,
-                                                          const float4* __restrict__ splats,
-                                                          float4* __restrict__ packed, uint2* __restrict__ ranges) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t j = t >> 2;
-  const int qd = (int)(t & 3);
+__global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t R, uint32_t ntiles, const uint32_t* __restrict__ keys,
+                                                          uint2* __restrict__ ranges) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= R) return;
   const uint32_t tile = keys[j];
   if (tile >= ntiles) return;                 // sentinel slot
-  const uint32_t v = vals[j];
-  // splat record  x,y,ca,cb | cc,op,r,g | b,depth,nx,ny | nz,-,-,-   ->   blend record (raster_blend.cu)
-  //               x,y,a2,b2 | c2,op,pthr2,r | g,b,depth,nx | ny,nz,gid,0
-  const float4* sp = splats + 4 * (int64_t)v;
-  constexpr float LOG2E = 1.4426950408889634f;
-  float4 o;
-  if (qd == 0) {
-    const float4 s0 = sp[0];
-    o = make_float4(s0.x, s0.y, (-0.5f * LOG2E) * s0.z, -LOG2E * s0.w);
-  } else if (qd == 1) {
-    const float4 s1 = sp[1];
-    // pairs with p2 < pthr2 cannot reach alpha >= 1/255 (0.01 in log2 units = 0.7 % safety margin on alpha)
-    const float pthr2 = -log2f(255.0f * s1.y) - 0.01f;
-    o = make_float4((-0.5f * LOG2E) * s1.x, s1.y, pthr2, s1.z);
-  } else if (qd == 2) {
-    const float4 s1 = sp[1], s2 = sp[2];
-    o = make_float4(s1.w, s2.x, s2.y, s2.z);
-  } else {
-    const float4 s2 = sp[2], s3 = sp[3];
-    o = make_float4(s2.w, s3.x, __uint_as_float(v), 0.f);
-  }
-  packed[4 * j + qd] = o;
-  if (qd == 0) {
-    if (j == 0 || keys[j - 1] != tile) ranges[tile].x = (uint32_t)j;
-    if (j == R - 1 || keys[j + 1] != tile) ranges[tile].y = (uint32_t)(j + 1);
-  }
+  if (j == 0 || keys[j - 1] != tile) ranges[tile].x = (uint32_t)j;
+  if (j == R - 1 || keys[j + 1] != tile) ranges[tile].y = (uint32_t)(j + 1);
 }
 
 // capacity mode: flags an instance count larger than the number of slots (the surplus instances were dropped)
@@ -187,7 +160,7 @@ int dimo_raster_preprocess(int B, int N, int W, int H, int sh_degree, int sh_coe
 int dimo_raster_bin(int B, int N, int W, int H, int64_t R, const float* splats, const int32_t* radii,
                     const uint32_t* perm_sorted, const uint32_t* offsets, uint32_t* keys_unsorted,
                     uint32_t* vals_unsorted, uint32_t* keys_sorted, uint32_t* vals_sorted, void* sort_temp,
-                    size_t sort_temp_bytes, float* packed, uint32_t* ranges, int32_t* count_overflow, void* stream) {
+                    size_t sort_temp_bytes, uint32_t* ranges, int32_t* count_overflow, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
   const int64_t ntiles = (int64_t)B * gx * gy;
@@ -208,10 +181,8 @@ int dimo_raster_bin(int B, int N, int W, int H, int64_t R, const float* splats, 
   // one spare code above the last tile id so that the sentinel sorts behind every real key
   DIMO_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(sort_temp, need, keys_unsorted, keys_sorted, vals_unsorted,
                                                   vals_sorted, (int)R, 0, bits_for(ntiles + 1), st));
-  pack_ranges_kernel<<<ceil_div(R * 4, 256), 256, 0, st>>>(R, (uint32_t)ntiles, keys_sorted, vals_sorted,
-                                                           reinterpret_cast<const float4*>(splats),
-                                                           reinterpret_cast<float4*>(packed),
-                                                           reinterpret_cast<uint2*>(ranges));
+  tile_ranges_kernel<<<ceil_div(R, 256), 256, 0, st>>>(R, (uint32_t)ntiles, keys_sorted,
+                                                       reinterpret_cast<uint2*>(ranges));
   DIMO_CHECK_LAUNCH();
   return 0;
 }

@@ -5,9 +5,11 @@
 //  * one CTA (64 threads = 2 warps) per 16x16 tile per frame; every thread owns 4 horizontally
 //    adjacent pixels, so the per-splat shared-memory reads (broadcast LDS.128) and the row-dependent
 //    part of the quadratic form are amortised over 4 pixels and outputs leave as 128-bit stores;
-//  * the tile's depth-sorted splat list is a contiguous run of 64-byte "blend records"
-//    (raster_bin.cu packs them), streamed into shared memory by 1-D bulk TMA
-//    (cp.async.bulk -> mbarrier complete_tx), double-buffered, 128 records (8 KB) per stage;
+//  * the tile's depth-sorted list is a run of record indices (`vals_sorted`); the 64-byte "blend records"
+//    themselves live once per (frame, Gaussian) in the table the preprocess kernel writes.  Every thread
+//    gathers two records per stage into shared memory with 64-byte bulk async copies
+//    (cp.async.bulk -> mbarrier complete_tx; or 4 x 16-byte cp.async, DIMO knob 3), double-buffered,
+//    128 records (8 KB) per stage, indices prefetched one stage further ahead in registers;
 //  * records carry the conic pre-multiplied by -0.5*log2(e) (resp. -log2(e)), so
 //    alpha = opacity * ex2(p2) is one MUFU.EX2 without the extra multiply, and a conservative
 //    threshold p2 >= -log2(255*opacity) - margin that skips the MUFU for pairs that cannot reach
@@ -28,11 +30,14 @@ constexpr int BLEND_THREADS = TILE_PIX / PPT;   // 64
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 
-// blend record layout (written by pack_ranges_kernel, raster_bin.cu):
+// blend record layout (written by preprocess_fwd_kernel, raster_preprocess.cu):
 //   f4#0: x, y, a2 = -0.5*log2e*conic_a, b2 = -log2e*conic_b
 //   f4#1: c2 = -0.5*log2e*conic_c, opacity, pthr2, r
 //   f4#2: g, b, depth, nx
-//   f4#3: ny, nz, gid (int bits), 0
+//   f4#3: ny, nz, gid (own table index, int bits), 0
+
+// Gather mode (dimo_tc_debug_set key 3): 0 = one 64-byte bulk copy per record, 1 = four 16-byte cp.async per record.
+int g_blend_gather_mode = 0;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -66,17 +71,53 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Stage loader shared by both kernels.  `ids` = this tile's record indices; list positions [pos0, pos0 + cnt) go to
+// `dst`.  Thread t fetches records t and t + 64 of the stage; their indices were prefetched into id0/id1.
+//   MODE 0: bar expects 1 arrival (thread 0, with the stage's byte count) + the copies' complete_tx;
+//   MODE 1: bar expects BLEND_THREADS arrivals, each fired when that thread's cp.async group has landed.
+template <int MODE>
+__device__ __forceinline__ void stage_gather(float4* dst, const float4* __restrict__ table, uint32_t id0, uint32_t id1,
+                                             int cnt, int tid, uint64_t* bar) {
+  if (MODE == 0) {
+    if (tid == 0) mbar_expect_tx(bar, cnt * 64);
+    if (tid < cnt) bulk_g2s(dst + tid * REC_F4, table + (int64_t)id0 * REC_F4, 64, bar);
+    if (tid + 64 < cnt) bulk_g2s(dst + (tid + 64) * REC_F4, table + (int64_t)id1 * REC_F4, 64, bar);
+  } else {
+    if (tid < cnt) {
+      const float4* src = table + (int64_t)id0 * REC_F4;
+#pragma unroll
+      for (int q = 0; q < REC_F4; ++q) cp_async16(dst + tid * REC_F4 + q, src + q);
+    }
+    if (tid + 64 < cnt) {
+      const float4* src = table + (int64_t)id1 * REC_F4;
+#pragma unroll
+      for (int q = 0; q < REC_F4; ++q) cp_async16(dst + (tid + 64) * REC_F4 + q, src + q);
+    }
+    cp_async_arrive_noinc(bar);
+  }
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 
+static_assert(CHUNK == 2 * BLEND_THREADS, "stage_gather assigns two records per thread");
+
+template <int MODE>
 __global__ void __launch_bounds__(BLEND_THREADS) blend_fwd_kernel(
-    int W, int H, int gx, int tiles_per_frame, const float* __restrict__ cams, const float4* __restrict__ packed,
-    const uint2* __restrict__ ranges, float* __restrict__ out_color, float* __restrict__ out_depth,
-    float* __restrict__ out_normal, float* __restrict__ out_alpha, float* __restrict__ final_T,
-    int32_t* __restrict__ n_contrib) {
+    int W, int H, int gx, int tiles_per_frame, const float* __restrict__ cams, const float4* __restrict__ table,
+    const uint32_t* __restrict__ vals_sorted, const uint2* __restrict__ ranges, float* __restrict__ out_color,
+    float* __restrict__ out_depth, float* __restrict__ out_normal, float* __restrict__ out_alpha,
+    float* __restrict__ final_T, int32_t* __restrict__ n_contrib) {
   __shared__ __align__(128) float4 sm[2][CHUNK * REC_F4];
   __shared__ __align__(8) uint64_t bar[2];
 
@@ -91,21 +132,26 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_fwd_kernel(
   const uint2 rng = ranges[tile];
   const int n = (int)(rng.y - rng.x);
   const int nchunks = (n + CHUNK - 1) / CHUNK;
-  const float4* src = packed + (int64_t)rng.x * REC_F4;
+  const uint32_t* ids = vals_sorted + rng.x;
+  // record indices of list positions c*CHUNK + tid and + 64 (0 when past the end: never dereferenced)
+  auto load_ids = [&](int c, uint32_t& i0, uint32_t& i1) {
+    const int p0 = c * CHUNK + tid;
+    i0 = p0 < n ? ids[p0] : 0u;
+    i1 = p0 + 64 < n ? ids[p0 + 64] : 0u;
+  };
 
   if (tid == 0) {
-    mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
+    mbar_init(&bar[0], MODE == 0 ? 1 : BLEND_THREADS);
+    mbar_init(&bar[1], MODE == 0 ? 1 : BLEND_THREADS);
     fence_mbar_init();
   }
   __syncthreads();
-  if (tid == 0) {
-    for (int c = 0; c < 2 && c < nchunks; ++c) {
-      const int cnt = min(CHUNK, n - c * CHUNK);
-      mbar_expect_tx(&bar[c], cnt * 64);
-      bulk_g2s(&sm[c][0], src + (int64_t)c * CHUNK * REC_F4, cnt * 64, &bar[c]);
-    }
+  uint32_t nid0 = 0, nid1 = 0;   // indices of the next stage to be issued
+  for (int c = 0; c < 2 && c < nchunks; ++c) {
+    load_ids(c, nid0, nid1);
+    stage_gather<MODE>(&sm[c][0], table, nid0, nid1, min(CHUNK, n - c * CHUNK), tid, &bar[c]);
   }
+  if (nchunks > 2) load_ids(2, nid0, nid1);
 
   float T[PPT], Cr[PPT], Cg[PPT], Cb[PPT], D[PPT], Nx[PPT], Ny[PPT], Nz[PPT];
   int last[PPT];
@@ -169,10 +215,9 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_fwd_kernel(
     }
     const int num_alive = __syncthreads_count(alive != 0);
     if (num_alive == 0) break;
-    if (tid == 0 && c + 2 < nchunks) {
-      const int cnt2 = min(CHUNK, n - (c + 2) * CHUNK);
-      mbar_expect_tx(&bar[stage], cnt2 * 64);
-      bulk_g2s(&sm[stage][0], src + (int64_t)(c + 2) * CHUNK * REC_F4, cnt2 * 64, &bar[stage]);
+    if (c + 2 < nchunks) {
+      stage_gather<MODE>(&sm[stage][0], table, nid0, nid1, min(CHUNK, n - (c + 2) * CHUNK), tid, &bar[stage]);
+      if (c + 3 < nchunks) load_ids(c + 3, nid0, nid1);
     }
   }
   // an early break can leave chunk c+1 in flight: it must land before this CTA's smem is released
@@ -220,9 +265,11 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(BLEND_THREADS) blend_bwd_kernel(
-    int W, int H, int gx, int tiles_per_frame, const float* __restrict__ cams, const float4* __restrict__ packed,
-    const uint2* __restrict__ ranges, const float* __restrict__ final_T, const int32_t* __restrict__ n_contrib,
+    int W, int H, int gx, int tiles_per_frame, const float* __restrict__ cams, const float4* __restrict__ table,
+    const uint32_t* __restrict__ vals_sorted, const uint2* __restrict__ ranges, const float* __restrict__ final_T,
+    const int32_t* __restrict__ n_contrib,
     const float* __restrict__ dL_dcolor, const float* __restrict__ dL_ddepth, const float* __restrict__ dL_dnormal,
     const float* __restrict__ dL_dalpha, float* __restrict__ dL_dsplats) {
   __shared__ __align__(128) float4 sm[2][CHUNK * REC_F4];
@@ -270,8 +317,8 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_bwd_kernel(
 
   if (tid == 0) {
     s_max = 0;
-    mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
+    mbar_init(&bar[0], MODE == 0 ? 1 : BLEND_THREADS);
+    mbar_init(&bar[1], MODE == 0 ? 1 : BLEND_THREADS);
     fence_mbar_init();
   }
   for (int k = tid; k < CHUNK * NGRAD; k += BLEND_THREADS) acc[k] = 0.f;
@@ -286,17 +333,21 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_bwd_kernel(
   const int nproc = s_max;   // list positions [0, nproc) hold every contributor of this tile
   if (nproc == 0) return;
   const int nchunks = (nproc + CHUNK - 1) / CHUNK;
-  const float4* src = packed + (int64_t)rng.x * REC_F4;
+  const uint32_t* ids = vals_sorted + rng.x;
+  auto load_ids = [&](int cc, uint32_t& i0, uint32_t& i1) {
+    const int p0 = cc * CHUNK + tid;
+    i0 = p0 < nproc ? ids[p0] : 0u;
+    i1 = p0 + 64 < nproc ? ids[p0 + 64] : 0u;
+  };
 
   // chunk k of the descending walk is list chunk (nchunks-1-k); stage = k&1
-  if (tid == 0) {
-    for (int k = 0; k < 2 && k < nchunks; ++k) {
-      const int cc = nchunks - 1 - k;
-      const int cnt = min(CHUNK, nproc - cc * CHUNK);
-      mbar_expect_tx(&bar[k], cnt * 64);
-      bulk_g2s(&sm[k][0], src + (int64_t)cc * CHUNK * REC_F4, cnt * 64, &bar[k]);
-    }
+  uint32_t nid0 = 0, nid1 = 0;   // indices of the next stage to be issued
+  for (int k = 0; k < 2 && k < nchunks; ++k) {
+    const int cc = nchunks - 1 - k;
+    load_ids(cc, nid0, nid1);
+    stage_gather<MODE>(&sm[k][0], table, nid0, nid1, min(CHUNK, nproc - cc * CHUNK), tid, &bar[k]);
   }
+  if (nchunks > 2) load_ids(nchunks - 3, nid0, nid1);
 
   for (int k = 0; k < nchunks; ++k) {
     const int stage = k & 1;
@@ -395,11 +446,10 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_bwd_kernel(
       }
     }
     __syncthreads();
-    if (tid == 0 && k + 2 < nchunks) {
+    if (k + 2 < nchunks) {
       const int c2 = nchunks - 1 - (k + 2);
-      const int cnt2 = min(CHUNK, nproc - c2 * CHUNK);
-      mbar_expect_tx(&bar[stage], cnt2 * 64);
-      bulk_g2s(&sm[stage][0], src + (int64_t)c2 * CHUNK * REC_F4, cnt2 * 64, &bar[stage]);
+      stage_gather<MODE>(&sm[stage][0], table, nid0, nid1, min(CHUNK, nproc - c2 * CHUNK), tid, &bar[stage]);
+      if (k + 3 < nchunks) load_ids(c2 - 1, nid0, nid1);
     }
   }
 }
@@ -408,33 +458,36 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_bwd_kernel(
 
 using namespace dimo;
 
-extern "C" int dimo_raster_blend_fwd(int B, int W, int H, const float* cams, const float* packed,
-                                     const uint32_t* ranges, float* out_color, float* out_depth, float* out_normal,
-                                     float* out_alpha, float* final_T, int32_t* n_contrib, void* stream) {
+extern "C" int dimo_raster_blend_fwd(int B, int W, int H, const float* cams, const float* splats,
+                                     const uint32_t* vals_sorted, const uint32_t* ranges, float* out_color,
+                                     float* out_depth, float* out_normal, float* out_alpha, float* final_T,
+                                     int32_t* n_contrib, void* stream) {
   DIMO_REQUIRE(B >= 0 && W > 0 && H > 0, "bad sizes");
   if (B == 0) return 0;
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
-  blend_fwd_kernel<<<B * gx * gy, BLEND_THREADS, 0, (cudaStream_t)stream>>>(
-      W, H, gx, gx * gy, cams, reinterpret_cast<const float4*>(packed), reinterpret_cast<const uint2*>(ranges),
-      out_color, out_depth, out_normal, out_alpha, final_T, n_contrib);
+  auto kern = g_blend_gather_mode == 0 ? blend_fwd_kernel<0> : blend_fwd_kernel<1>;
+  kern<<<B * gx * gy, BLEND_THREADS, 0, (cudaStream_t)stream>>>(
+      W, H, gx, gx * gy, cams, reinterpret_cast<const float4*>(splats), vals_sorted,
+      reinterpret_cast<const uint2*>(ranges), out_color, out_depth, out_normal, out_alpha, final_T, n_contrib);
   DIMO_CHECK_LAUNCH();
   return 0;
 }
 
-extern "C" int dimo_raster_blend_bwd(int B, int N, int W, int H, const float* cams, const float* packed,
-                                     const uint32_t* ranges, const uint32_t* vals_sorted, const float* final_T,
+extern "C" int dimo_raster_blend_bwd(int B, int N, int W, int H, const float* cams, const float* splats,
+                                     const uint32_t* vals_sorted, const uint32_t* ranges, const float* final_T,
                                      const int32_t* n_contrib, const float* dL_dcolor, const float* dL_ddepth,
                                      const float* dL_dnormal, const float* dL_dalpha, float* dL_dsplats,
                                      void* stream) {
-  (void)vals_sorted;   // the Gaussian id travels inside the blend record
   DIMO_REQUIRE(B >= 0 && W > 0 && H > 0, "bad sizes");
   cudaStream_t st = (cudaStream_t)stream;
   if (B == 0 || N == 0) return 0;
   DIMO_CHECK_CUDA(cudaMemsetAsync(dL_dsplats, 0, sizeof(float) * DIMO_SPLAT_FLOATS * (size_t)B * N, st));
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
-  blend_bwd_kernel<<<B * gx * gy, BLEND_THREADS, 0, st>>>(
-      W, H, gx, gx * gy, cams, reinterpret_cast<const float4*>(packed), reinterpret_cast<const uint2*>(ranges),
-      final_T, n_contrib, dL_dcolor, dL_ddepth, dL_dnormal, dL_dalpha, dL_dsplats);
+  auto kern = g_blend_gather_mode == 0 ? blend_bwd_kernel<0> : blend_bwd_kernel<1>;
+  kern<<<B * gx * gy, BLEND_THREADS, 0, st>>>(
+      W, H, gx, gx * gy, cams, reinterpret_cast<const float4*>(splats), vals_sorted,
+      reinterpret_cast<const uint2*>(ranges), final_T, n_contrib, dL_dcolor, dL_ddepth, dL_dnormal, dL_dalpha,
+      dL_dsplats);
   DIMO_CHECK_LAUNCH();
   return 0;
 }

@@ -264,10 +264,16 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
   radii[idx] = (int)g.radius_f;
   tiles_touched[idx] = (uint32_t)ntiles;
   depth_keys[idx] = ((uint64_t)b << 32) | (uint64_t)__float_as_uint(g.tvz);   // view depth > 0.2: bits order as uints
-  out[0] = make_float4(g.pix_x, g.pix_y, g.conic_a, g.conic_b);
-  out[1] = make_float4(g.conic_c, op, rgb[0], rgb[1]);
-  out[2] = make_float4(rgb[2], g.tvz, nx, ny);
-  out[3] = make_float4(nz, 0.f, 0.f, 0.f);
+  // blend record (include/dimo_b200.h; consumed as-is by raster_blend.cu, gathered by index):
+  //   x, y, a2, b2 | c2, opacity, pthr2, r | g, b, depth, nx | ny, nz, own index, 0
+  // the conic is pre-multiplied into log2 units (alpha = opacity * 2^(a2 dx^2 + b2 dx dy + c2 dy^2));
+  // pairs with p2 < pthr2 cannot reach alpha >= 1/255 (0.01 in log2 units = 0.7 % safety margin on alpha)
+  constexpr float LOG2E = 1.4426950408889634f;
+  const float pthr2 = -log2f(255.0f * op) - 0.01f;
+  out[0] = make_float4(g.pix_x, g.pix_y, (-0.5f * LOG2E) * g.conic_a, -LOG2E * g.conic_b);
+  out[1] = make_float4((-0.5f * LOG2E) * g.conic_c, op, pthr2, rgb[0]);
+  out[2] = make_float4(rgb[1], rgb[2], g.tvz, nx);
+  out[3] = make_float4(ny, nz, __uint_as_float((uint32_t)idx), 0.f);
 }
 
 __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
@@ -445,25 +451,60 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(
     int64_t BN, int N, int W, int H, const float4* __restrict__ splats, const int32_t* __restrict__ radii,
     const uint32_t* __restrict__ perm, const uint32_t* __restrict__ offsets, int64_t R,
     uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ vals) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= BN) return;
-  const uint32_t idx = perm[i];
-  const int rad = radii[idx];
-  if (rad <= 0) return;
+  // Warp-cooperative: a warp owns 32 consecutive splats of the sorted order and walks their concatenated output
+  // slots 32 at a time, so the key/value stores are full 128-byte lines (one thread per splat writing its own
+  // run gave 4-byte scattered stores).  The owner of a slot is found by a 5-step shuffle search over the
+  // lanes' inclusive offsets.
+  const int lane = threadIdx.x & 31;
+  const int64_t first = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) - lane;   // this warp's first splat
+  if (first >= BN) return;
+  const int64_t i = first + lane;
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
-  const float4 s0 = splats[4 * (int64_t)idx + 0];
-  int x0, y0, x1, y1;
-  tile_rect(s0.x, s0.y, (float)rad, gx, gy, x0, y0, x1, y1);
-  uint64_t off = i == 0 ? 0 : offsets[i - 1];
-  const uint32_t frame_base = (uint32_t)(idx / (uint32_t)N) * (uint32_t)(gx * gy);
-  for (int ty = y0; ty < y1; ++ty)
-    for (int tx = x0; tx < x1; ++tx) {
-      if ((int64_t)off < R) {
-        tile_keys[off] = frame_base + (uint32_t)(ty * gx + tx);
-        vals[off] = idx;
-      }
-      ++off;
+  const uint32_t base = first == 0 ? 0u : offsets[first - 1];
+  uint32_t incl = 0, idx = 0, rect = 0, fbase = 0;
+  if (i < BN) {
+    incl = offsets[i] - base;
+    idx = perm[i];
+    const int rad = radii[idx];
+    if (rad > 0) {
+      const float4 s0 = splats[4 * (int64_t)idx + 0];
+      int x0, y0, x1, y1;
+      tile_rect(s0.x, s0.y, (float)rad, gx, gy, x0, y0, x1, y1);
+      rect = (uint32_t)x0 | ((uint32_t)y0 << 10) | ((uint32_t)(x1 - x0) << 20);   // gx, gy <= 1023 (checked by the host)
+      fbase = (uint32_t)(idx / (uint32_t)N) * (uint32_t)(gx * gy);
     }
+  }
+  // lanes past the end repeat the last valid inclusive offset (they own no slots)
+  {
+    const int last_valid = (int)min((int64_t)31, BN - 1 - first);
+    const uint32_t tail = __shfl_sync(0xffffffffu, incl, last_valid);
+    if (i >= BN) incl = tail;
+  }
+  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+  const uint32_t excl = __shfl_up_sync(0xffffffffu, incl, 1);
+  const uint32_t excl0 = lane == 0 ? 0u : excl;
+  for (uint32_t o0 = 0; o0 < total; o0 += 32) {
+    const uint32_t o = o0 + lane;
+    int s = 0;   // smallest lane with incl > o
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+      const uint32_t v = __shfl_sync(0xffffffffu, incl, s + step - 1);
+      if (v <= o) s += step;
+    }
+    s = min(s, 31);
+    const uint32_t o_excl = __shfl_sync(0xffffffffu, excl0, s);
+    const uint32_t o_rect = __shfl_sync(0xffffffffu, rect, s);
+    const uint32_t o_fb = __shfl_sync(0xffffffffu, fbase, s);
+    const uint32_t o_idx = __shfl_sync(0xffffffffu, idx, s);
+    const int64_t slot = (int64_t)base + o;
+    if (o < total && slot < R) {
+      const uint32_t k = o - o_excl;
+      const uint32_t w = o_rect >> 20, x0 = o_rect & 1023u, y0 = (o_rect >> 10) & 1023u;
+      const uint32_t row = k / w;
+      tile_keys[slot] = o_fb + (y0 + row) * (uint32_t)gx + x0 + (k - row * w);
+      vals[slot] = o_idx;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256) iota_kernel(int64_t n, uint32_t* __restrict__ out) {
@@ -498,6 +539,7 @@ int emit_keys_launch(int B, int N, int W, int H, int64_t R, const float* splats,
                      cudaStream_t st) {
   const int64_t BN = (int64_t)B * N;
   if (BN == 0 || R == 0) return 0;
+  DIMO_REQUIRE((W + TILE - 1) / TILE <= 1023 && (H + TILE - 1) / TILE <= 1023, "image larger than 1023 tiles per side");
   emit_keys_kernel<<<ceil_div(BN, 256), 256, 0, st>>>(BN, N, W, H, reinterpret_cast<const float4*>(splats), radii,
                                                       perm, offsets, R, tile_keys, vals);
   DIMO_CHECK_LAUNCH();

@@ -45,7 +45,7 @@ class RasterState:
     """Buffers kept from forward for backward / inspection (all torch-owned)."""
     __slots__ = ("B", "N", "W", "H", "R", "count_overflow", "cams", "splats", "radii", "tiles_touched", "offsets", "perm",
                  "keys_sorted",
-                 "vals_sorted", "packed", "ranges", "final_T", "n_contrib", "sh_degree", "sh_coeffs",
+                 "vals_sorted", "ranges", "final_T", "n_contrib", "sh_degree", "sh_coeffs",
                  "scale_modifier")
 
 
@@ -102,14 +102,13 @@ def _forward_impl(cams, means3D, scales, rotations, opacities, shs, colors_preco
     vals_u = torch.empty(Ra, **i32)
     st.keys_sorted = torch.empty(Ra, **i32)          # frame*tiles + tile, sorted (sentinel in unused slots)
     st.vals_sorted = torch.empty(Ra, **i32)
-    st.packed = torch.empty(Ra, SPLAT_FLOATS, **f32)
     st.ranges = torch.empty(B * gx * gy, 2, **i32)
     sort_bytes = L.dimo_raster_sort_temp_bytes(Ra)
     sort_temp = torch.empty(sort_bytes, dtype=torch.uint8, device=dev)
     _lib.call("dimo_raster_bin", B, N, W, H, R, _lib.ptr(st.splats), _lib.ptr(st.radii), _lib.ptr(st.perm),
               _lib.ptr(st.offsets),
               _lib.ptr(keys_u), _lib.ptr(vals_u), _lib.ptr(st.keys_sorted), _lib.ptr(st.vals_sorted),
-              _lib.ptr(sort_temp), sort_bytes, _lib.ptr(st.packed), _lib.ptr(st.ranges),
+              _lib.ptr(sort_temp), sort_bytes, _lib.ptr(st.ranges),
               _lib.ptr(st.count_overflow), s)
     color = torch.empty(B, 3, H, W, **f32)
     depth = torch.empty(B, 1, H, W, **f32)
@@ -117,7 +116,8 @@ def _forward_impl(cams, means3D, scales, rotations, opacities, shs, colors_preco
     alpha = torch.empty(B, 1, H, W, **f32)
     st.final_T = torch.empty(B, H, W, **f32)
     st.n_contrib = torch.empty(B, H, W, **i32)
-    _lib.call("dimo_raster_blend_fwd", B, W, H, _lib.ptr(cams), _lib.ptr(st.packed), _lib.ptr(st.ranges),
+    _lib.call("dimo_raster_blend_fwd", B, W, H, _lib.ptr(cams), _lib.ptr(st.splats), _lib.ptr(st.vals_sorted),
+              _lib.ptr(st.ranges),
               _lib.ptr(color), _lib.ptr(depth), _lib.ptr(normal), _lib.ptr(alpha), _lib.ptr(st.final_T),
               _lib.ptr(st.n_contrib), s)
     return color, depth, normal, alpha, st
@@ -155,8 +155,8 @@ class _Rasterize(torch.autograd.Function):
         g_alpha = g_alpha.contiguous() if g_alpha is not None else zeros(B, 1, H, W)
         s = _lib.stream()
         dsplats = torch.empty(B * N, SPLAT_FLOATS, **f32)
-        _lib.call("dimo_raster_blend_bwd", B, N, W, H, _lib.ptr(st.cams), _lib.ptr(st.packed), _lib.ptr(st.ranges),
-                  _lib.ptr(st.vals_sorted), _lib.ptr(st.final_T), _lib.ptr(st.n_contrib), _lib.ptr(g_color),
+        _lib.call("dimo_raster_blend_bwd", B, N, W, H, _lib.ptr(st.cams), _lib.ptr(st.splats),
+                  _lib.ptr(st.vals_sorted), _lib.ptr(st.ranges), _lib.ptr(st.final_T), _lib.ptr(st.n_contrib), _lib.ptr(g_color),
                   _lib.ptr(g_depth), _lib.ptr(g_normal), _lib.ptr(g_alpha), _lib.ptr(dsplats), s)
         d_means3D = torch.empty(B, N, 3, **f32)
         d_means2D = torch.empty(B, N, 3, **f32)

@@ -37,8 +37,12 @@ extern "C" {
  * i.e. the fields of GaussianRasterizationSettings (:1133-1146) that vary per frame. */
 #define DIMO_CAM_FLOATS 40
 
-/* Per-Gaussian projected record ("splat"), DIMO_SPLAT_FLOATS floats (64 B, TMA-bulk friendly):
- *   x, y (pixel centre), conic_a, conic_b | conic_c, opacity, r, g | b, depth, nx, ny | nz, 0,0,0 */
+/* Per-(frame, Gaussian) projected record ("splat" / blend record), DIMO_SPLAT_FLOATS floats (64 B = one bulk
+ * async copy into shared memory):
+ *   x, y (pixel centre), a2, b2 | c2, opacity, pthr2, r | g, b, depth, nx | ny, nz, own index (u32 bits), 0
+ * with a2 = -0.5*log2(e)*conic_a, b2 = -log2(e)*conic_b, c2 = -0.5*log2(e)*conic_c (alpha = opacity * 2^p2) and
+ * pthr2 = -log2(255*opacity) - 0.01 (pairs below it cannot reach alpha >= 1/255).
+ * Gradient records (dL_dsplats) use: x, y, conic_a, conic_b | conic_c, opacity, r, g | b, depth, nx, ny | nz,0,0,0 */
 #define DIMO_SPLAT_FLOATS 16
 
 int         dimo_abi_version(void);
@@ -79,10 +83,9 @@ int dimo_raster_preprocess(
     void* scan_temp, size_t scan_temp_bytes,
     int64_t* R_host, void* stream);
 
-/* Stage 2: emit (frame*tiles + tile) keys front-to-back, stable-sort by tile, pack blend records in sorted
- * order, per-tile ranges.
- *   perm_sorted [B*N] u32 (= perm + B*N of stage 1), keys_* [R] u32, vals_* [R] u32 (index into B*N),
- *   packed [R,16] f32, ranges [B*tiles,2] u32; temp: dimo_raster_sort_temp_bytes(R) bytes.
+/* Stage 2: emit (frame*tiles + tile) keys front-to-back, stable-sort by tile, per-tile ranges.
+ *   perm_sorted [B*N] u32 (= perm + B*N of stage 1), keys_* [R] u32, vals_* [R] u32 (index into the B*N splat
+ *   records), ranges [B*tiles,2] u32; temp: dimo_raster_sort_temp_bytes(R) bytes.
  *   R is the number of instance SLOTS.  count_overflow == NULL: R is the exact count read back from stage 1.
  *   count_overflow != NULL (i32[2], device, [1] zeroed by the caller once): "capacity mode" for sync-free /
  *   CUDA-graph use -- R is a capacity, unused slots carry a sentinel key that sorts last, [0] receives the true
@@ -93,20 +96,21 @@ int dimo_raster_bin(
     const float* splats, const int32_t* radii, const uint32_t* perm_sorted, const uint32_t* offsets,
     uint32_t* keys_unsorted, uint32_t* vals_unsorted, uint32_t* keys_sorted, uint32_t* vals_sorted,
     void* sort_temp, size_t sort_temp_bytes,
-    float* packed, uint32_t* ranges, int32_t* count_overflow, void* stream);
+    uint32_t* ranges, int32_t* count_overflow, void* stream);
 
-/* Stage 3: per-tile front-to-back blend.
+/* Stage 3: per-tile front-to-back blend; tile t walks vals_sorted[ranges[t].x .. ranges[t].y) and gathers the
+ * splat records by index.
  *   out_color [B,3,H,W], out_depth [B,1,H,W], out_normal [B,3,H,W], out_alpha [B,1,H,W],
  *   final_T [B,H,W] f32, n_contrib [B,H,W] i32. */
 int dimo_raster_blend_fwd(
-    int B, int W, int H, const float* cams, const float* packed, const uint32_t* ranges,
-    float* out_color, float* out_depth, float* out_normal, float* out_alpha,
+    int B, int W, int H, const float* cams, const float* splats, const uint32_t* vals_sorted,
+    const uint32_t* ranges, float* out_color, float* out_depth, float* out_normal, float* out_alpha,
     float* final_T, int32_t* n_contrib, void* stream);
 
-/* Backward of stage 3: dL_dsplats [B*N,16] (zeroed here, then accumulated), same field layout as a splat. */
+/* Backward of stage 3: dL_dsplats [B*N,16] (zeroed here, then accumulated), gradient-record layout above. */
 int dimo_raster_blend_bwd(
-    int B, int N, int W, int H, const float* cams, const float* packed, const uint32_t* ranges,
-    const uint32_t* vals_sorted, const float* final_T, const int32_t* n_contrib,
+    int B, int N, int W, int H, const float* cams, const float* splats, const uint32_t* vals_sorted,
+    const uint32_t* ranges, const float* final_T, const int32_t* n_contrib,
     const float* dL_dcolor, const float* dL_ddepth, const float* dL_dnormal, const float* dL_dalpha,
     float* dL_dsplats, void* stream);
 
@@ -167,7 +171,8 @@ int dimo_linear_wgrad_tc_grouped(int n, int R, const int* K, const int* No, cons
                                  const int64_t* lddy, const float* const* mask, const int64_t* ldm,
                                  const float* const* X, const int64_t* ldx, float* const* dW, float* const* db,
                                  void* stream);
-/* bring-up knobs for the kernels above (0: swap LBO/SBO, 1: single-pass TF32); not part of the stable ABI */
+/* bring-up knobs (0: swap LBO/SBO, 1: single-pass TF32, 2: wgrad CTA target, 3: blend gather via 16-byte
+ * cp.async instead of 64-byte bulk copies); not part of the stable ABI */
 int dimo_tc_debug_set(int key, int value);
 
 /* TimeNet input embedding h0[R,104] = [posenc(x,10) | posenc(t,6) | latent]  (pos_enc.py:35-36,

@@ -114,10 +114,13 @@ def test_raster_properties_full_size(cuda):
     tile_of_key = keys
     counts = torch.bincount(tile_of_key, minlength=rng.shape[0])
     assert torch.equal(counts, (rng[:, 1] - rng[:, 0]))
-    depth_rec = s.packed[:R, 10]                       # blend record: depth
+    vals = s.vals_sorted[:R].long()
+    depth_rec = s.splats[vals, 10]                     # blend record: depth
     same_tile = tile_of_key[1:] == tile_of_key[:-1]
     assert bool((depth_rec[1:][same_tile] >= depth_rec[:-1][same_tile]).all()), "tile lists not depth sorted"
-    assert torch.equal(s.packed[:R, 14].view(torch.int32), s.vals_sorted[:R]), "gid in record != sorted value"
+    vis = s.radii > 0
+    own = s.splats[:, 14].contiguous().view(torch.int32)
+    assert torch.equal(own[vis], torch.arange(2 * N, device="cuda", dtype=torch.int32)[vis]), "record index field"
     assert torch.allclose(alpha[:, 0], 1 - s.final_T, atol=1e-6)
     assert bool((alpha >= 0).all()) and bool((alpha <= 1).all())
     # linearity in colour: doubling every (unclamped) colour doubles the image (bg = 0)
