@@ -31,6 +31,7 @@ SOURCES = {
     "mlp.cu": [],
     "mlp_tc.cu": [],
     "ssim.cu": [],
+    "optim.cu": [],
 }
 
 

@@ -41,7 +41,10 @@ __device__ __forceinline__ float block_sum_128(float v, float* red) {
 __global__ void __launch_bounds__(SS_THREADS) ssim_fwd_kernel(int H, int W, const float* __restrict__ img1,
                                                               const float* __restrict__ img2,
                                                               float* __restrict__ sums, float* __restrict__ dm,
-                                                              int64_t plane_count, int clamp01) {
+                                                              int64_t plane_count, int clamp01, int C,
+                                                              const float* __restrict__ mse_frame_w,
+                                                              float* __restrict__ loss_acc, float lw_ssim, float lw_l1,
+                                                              float lw_mse) {
   __shared__ float s1[SS_HH][SS_HW + 1];
   __shared__ float s2[SS_HH][SS_HW + 1];
   __shared__ float hz[5][SS_HH][SS_TW + 1];
@@ -129,15 +132,53 @@ __global__ void __launch_bounds__(SS_THREADS) ssim_fwd_kernel(int H, int W, cons
   }
   const float t0 = block_sum_128(v_ssim, red);
   const float t1 = block_sum_128(v_l1, red);
-  const float t2 = block_sum_128(v_mse, red);
-  if (tid == 0) { atomicAdd(&sums[0], t0); atomicAdd(&sums[1], t1); atomicAdd(&sums[2], t2); }
+  float t2 = block_sum_128(v_mse, red);
+  if (tid == 0) {
+    if (mse_frame_w != nullptr) t2 *= mse_frame_w[plane / C];
+    atomicAdd(&sums[0], t0); atomicAdd(&sums[1], t1); atomicAdd(&sums[2], t2);
+    if (loss_acc != nullptr) atomicAdd(loss_acc, lw_ssim * t0 + lw_l1 * t1 + lw_mse * t2);
+  }
+}
+
+// sum (a-b)^2 over n floats: the mask term F.mse_loss(alpha, gt_mask) (main_train_dimo.py:350) needs no SSIM
+// moments.  128-bit loads over the first 4*n4 elements (n4 = 0 when a pointer is not 16-byte aligned), scalar loads for
+// the rest, one atomic per CTA.  HBM: 8 B per element.
+__global__ void __launch_bounds__(256) sqdiff_sum_kernel(int64_t n, int64_t n4, const float* __restrict__ a,
+                                                         const float* __restrict__ b, float* __restrict__ sum,
+                                                         float* __restrict__ loss_acc, float lw) {
+  __shared__ float red[8];
+  float v = 0.f;
+  const float4* a4 = reinterpret_cast<const float4*>(a);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+    const float4 x = a4[i], y = b4[i];
+    const float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
+    v += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+  }
+  for (int64_t i = 4 * n4 + (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const float d = a[i] - b[i];
+    v = fmaf(d, d, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w];
+    atomicAdd(sum, t);
+    if (loss_acc != nullptr) atomicAdd(loss_acc, lw * t);
+  }
 }
 
 __global__ void __launch_bounds__(SS_THREADS) ssim_bwd_kernel(int H, int W, const float* __restrict__ img1,
                                                               const float* __restrict__ img2,
                                                               const float* __restrict__ dm, float w_ssim, float w_l1,
                                                               float w_mse, float* __restrict__ dL_dimg1,
-                                                              int64_t plane_count, int clamp01) {
+                                                              int64_t plane_count, int clamp01, int C,
+                                                              const float* __restrict__ mse_frame_w,
+                                                              const float* __restrict__ g_dev) {
   __shared__ float sm[3][SS_HH][SS_HW + 1];
   __shared__ float hz[3][SS_HH][SS_TW + 1];
   const int plane = blockIdx.z;
@@ -192,6 +233,10 @@ __global__ void __launch_bounds__(SS_THREADS) ssim_bwd_kernel(int H, int W, cons
     }
   }
   const int gx = x0 + col;
+  // upstream gradient of the scalar loss (device scalar, so no host read and no extra elementwise pass)
+  const float gup = g_dev != nullptr ? g_dev[0] : 1.f;
+  w_ssim *= gup; w_l1 *= gup;
+  w_mse *= gup * (mse_frame_w != nullptr ? mse_frame_w[plane / C] : 1.f);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int gy = y0 + 4 * rg + j;
@@ -214,28 +259,45 @@ __global__ void __launch_bounds__(SS_THREADS) ssim_bwd_kernel(int H, int W, cons
 using namespace dimo;
 
 extern "C" int dimo_ssim_fwd(int B, int C, int H, int W, int clamp01, const float* img1, const float* img2,
-                             float* sums, float* dm, void* stream) {
+                             float* sums, float* dm, const float* mse_frame_w, float* loss_acc, float lw_ssim,
+                             float lw_l1, float lw_mse, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   DIMO_CHECK_CUDA(cudaMemsetAsync(sums, 0, 3 * sizeof(float), st));
   const int planes = B * C;
   if (planes == 0) return 0;
   DIMO_REQUIRE(planes <= 65535, "B*C must be <= 65535");
   dim3 grid(ceil_div(W, SS_TW), ceil_div(H, SS_TH), planes);
-  ssim_fwd_kernel<<<grid, SS_THREADS, 0, st>>>(H, W, img1, img2, sums, dm, (int64_t)planes, clamp01);
+  ssim_fwd_kernel<<<grid, SS_THREADS, 0, st>>>(H, W, img1, img2, sums, dm, (int64_t)planes, clamp01, C, mse_frame_w,
+                                               loss_acc, lw_ssim, lw_l1, lw_mse);
   DIMO_CHECK_LAUNCH();
   return 0;
 }
 
 extern "C" int dimo_ssim_bwd(int B, int C, int H, int W, int clamp01, const float* img1, const float* img2,
-                             const float* dm, float w_ssim, float w_l1, float w_mse, float* dL_dimg1,
-                             void* stream) {
+                             const float* dm, float w_ssim, float w_l1, float w_mse, const float* mse_frame_w,
+                             const float* g_dev, float* dL_dimg1, void* stream) {
   const int planes = B * C;
   if (planes == 0) return 0;
   DIMO_REQUIRE(planes <= 65535, "B*C must be <= 65535");
   DIMO_REQUIRE(w_ssim == 0.f || dm != nullptr, "dm maps required when w_ssim != 0");
   dim3 grid(ceil_div(W, SS_TW), ceil_div(H, SS_TH), planes);
   ssim_bwd_kernel<<<grid, SS_THREADS, 0, (cudaStream_t)stream>>>(H, W, img1, img2, dm, w_ssim, w_l1, w_mse, dL_dimg1,
-                                                                 (int64_t)planes, clamp01);
+                                                                 (int64_t)planes, clamp01, C, mse_frame_w, g_dev);
+  DIMO_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dimo_sqdiff_sum(int64_t n, const float* a, const float* b, float* sum, float* loss_acc, float lw,
+                               void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  DIMO_CHECK_CUDA(cudaMemsetAsync(sum, 0, sizeof(float), st));
+  if (n == 0) return 0;
+  DIMO_REQUIRE(n > 0, "n must not be negative");
+  const bool aligned = ((uintptr_t)a & 15) == 0 && ((uintptr_t)b & 15) == 0;
+  const int64_t n4 = aligned ? n / 4 : 0;
+  const int64_t want = ((aligned ? n4 + 3 : n) + 255) / 256;
+  const int grid = (int)(want < 148 * 8 ? (want > 0 ? want : 1) : 148 * 8);
+  sqdiff_sum_kernel<<<grid, 256, 0, st>>>(n, n4, a, b, sum, loss_acc, lw);
   DIMO_CHECK_LAUNCH();
   return 0;
 }

@@ -31,10 +31,14 @@ def _linear_fwd(R, K, No, X, ldx, W, b, Y, ldy, relu, s):
 
 
 class _TimeNetFn(torch.autograd.Function):
-    """(pts [M,3], times [G], latents [G,L], 24 params) -> dxyz [G,M,3], dquat [G,M,4]."""
+    """(pts [M,3], times [G], latents [G,L], sink, 24 params) -> dxyz [G,M,3], dquat [G,M,4].
+    `sink`: None, or the 24 gradient tensors of the parameters (views of the flat gradient buffer, dist.py): the
+    backward kernels then accumulate straight into them and autograd sees no parameter gradients (no temporaries,
+    no AccumulateGrad add per parameter -- 48 small launches per step)."""
 
     @staticmethod
-    def forward(ctx, pts, times, latents, *params):
+    def forward(ctx, pts, times, latents, sink, *params):
+        ctx.sink = sink
         dev = pts.device
         f32 = dict(dtype=torch.float32, device=dev)
         pts = pts.contiguous().float()
@@ -95,11 +99,28 @@ class _TimeNetFn(torch.autograd.Function):
         s = _lib.stream()
         g_dxyz = g_dxyz.contiguous().float()
         g_dquat = g_dquat.contiguous().float()
-        dWs = [torch.zeros_like(W) for W in Ws]
-        dbs = [torch.zeros(W.shape[0], **f32) for W in Ws]
+        sink = ctx.sink
+        if sink is not None:
+            dWs, dbs = list(sink[0::2]), list(sink[1::2])
+        else:
+            dWs = [torch.zeros_like(W) for W in Ws]
+            dbs = [torch.zeros(W.shape[0], **f32) for W in Ws]
 
-        keep = []    # transposed weights must outlive the asynchronous launches that read them
         deferred = []   # tensor-core weight gradients: independent of each other -> ONE grouped launch at the end
+        # W^T for the tensor-core data-gradient GEMMs: one grouped transpose launch into one buffer
+        Wts = {}
+        if USE_TC and TC_DGRAD:
+            tl = [li for li, W in enumerate(Ws) if W.shape[0] % 4 == 0]
+            tbuf = torch.empty(sum(Ws[li].numel() for li in tl), **f32)
+            o = 0
+            for li in tl:
+                Wts[li] = tbuf[o:o + Ws[li].numel()]
+                o += Ws[li].numel()
+            nt = len(tl)
+            _lib.call("dimo_transpose_grouped", nt, (ctypes.c_int * nt)(*[Ws[li].shape[0] for li in tl]),
+                      (ctypes.c_int * nt)(*[Ws[li].shape[1] for li in tl]),
+                      (ctypes.c_void_p * nt)(*[Ws[li].data_ptr() for li in tl]),
+                      (ctypes.c_void_p * nt)(*[Wts[li].data_ptr() for li in tl]), s)
 
         def bwd_layer(li, K, No, dY_ptr, lddy, Y_ptr, ldy, X_ptr, ldx, dX_ptr, lddx, accumulate):
             if USE_TC and TC_WGRAD and No % 4 == 0 and K % 4 == 0 and lddy % 4 == 0 and ldx % 4 == 0 and \
@@ -112,10 +133,8 @@ class _TimeNetFn(torch.autograd.Function):
                 if USE_TC and TC_DGRAD and No % 4 == 0 and lddy % 4 == 0 and (Y_ptr is None or ldy % 4 == 0):
                     # dX[R,K] = (dY * [Y>0]) [R,No] * W[No,K]: same kernel with the transposed weight as the
                     # "[N_out, K_red]" operand (reduction over No)
-                    Wt = Ws[li].t().contiguous()
-                    keep.append(Wt)
                     _lib.call("dimo_linear_tc", R, No, K, dY_ptr, lddy, Y_ptr, ldy if Y_ptr is not None else 0,
-                              _lib.ptr(Wt), None, dX_ptr, lddx, 0, int(accumulate), s)
+                              _lib.ptr(Wts[li]), None, dX_ptr, lddx, 0, int(accumulate), s)
                 else:
                     _lib.call("dimo_linear_bwd_data", R, K, No, dY_ptr, lddy, Y_ptr, ldy, _lib.ptr(Ws[li]), dX_ptr,
                               lddx, int(accumulate), s)
@@ -177,10 +196,12 @@ class _TimeNetFn(torch.autograd.Function):
         if need_pts or need_lat:
             _lib.call("dimo_timenet_embed_bwd", G, M, L, _lib.ptr(cat), _lib.ptr(dcat), CAT,
                       _lib.ptr(dpts), _lib.ptr(dlat), s)
+        if sink is not None:
+            return (dpts, None, dlat, None, *([None] * (2 * len(Ws))))
         grads = []
         for W, b in zip(dWs, dbs):
             grads += [W, b]
-        return (dpts, None, dlat, *grads)
+        return (dpts, None, dlat, None, *grads)
 
 
 def _xavier(m):
@@ -205,6 +226,10 @@ class TimeNet(nn.Module):
         self.pts_layers = nn.Sequential(nn.Linear(W, W), nn.ReLU(), nn.Linear(W, 3))
         self.rot_layers = nn.Sequential(nn.Linear(W, W), nn.ReLU(), nn.Linear(W, 4))
         self.device = device
+        # True: backward accumulates weight/bias gradients straight into the parameters' preallocated .grad tensors
+        # (set by trainstep.TrainStep, whose gradients are views of one flat buffer); autograd's own accumulation is
+        # bypassed for these parameters, so torch.autograd.grad() would not see them -- off by default
+        self.direct_grads = False
         self.deformnet.apply(_xavier); self.pts_layers.apply(_xavier); self.rot_layers.apply(_xavier)
         init.constant_(self.pts_layers[-1].weight, 0); init.constant_(self.pts_layers[-1].bias, 0)
         init.constant_(self.rot_layers[-1].weight, 0)
@@ -220,7 +245,13 @@ class TimeNet(nn.Module):
 
     def forward_batched(self, pts, times, latents):
         """pts [M,3]; times [G]; latents [G,L] -> dxyz [G,M,3], dquat [G,M,4] (one launch set for all G)."""
-        return _TimeNetFn.apply(pts, times, latents, *self.flat_params())
+        ps = self.flat_params()
+        sink = None
+        if self.direct_grads and torch.is_grad_enabled():
+            sink = [p.grad for p in ps]
+            if any(g is None or not g.is_contiguous() for g in sink):
+                raise RuntimeError("TimeNet.direct_grads needs every parameter's .grad preallocated (FlatGradReducer)")
+        return _TimeNetFn.apply(pts, times, latents, sink, *ps)
 
     def forward(self, pts, t, latent_code, nobatch=False, t_apply=False):
         """Reference call forms: (pts [M,3], float t, latent [L]) and the t_apply form

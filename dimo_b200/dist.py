@@ -15,6 +15,8 @@ into the communication buffer (no pack / unpack copies).  The buffer has two con
 """
 import torch
 
+ALIGN = 4      # floats
+
 
 def shard_motions(n_motions, world, rank):
     """Block partition of motion (latent) indices: rank r owns [lo, hi).  Sizes differ by at most one."""
@@ -34,8 +36,18 @@ class FlatGradReducer:
         self.late = [p for p in params if p.numel() > 0 and id(p) not in early_ids]
         self.params = self.early + self.late
         self.group = group
-        self.n_early = sum(p.numel() for p in self.early)
-        self.n = sum(p.numel() for p in self.params)
+        # every tensor starts on a 16-byte boundary (128-bit accesses in the fused optimizer, optim.FusedAdam);
+        # the padding floats stay zero and ride along in the all-reduce
+        al = lambda x: (x + ALIGN - 1) // ALIGN * ALIGN
+        self.offsets, o = [], 0
+        for i, p in enumerate(self.params):
+            self.offsets.append((o, p.numel()))
+            o = al(o + p.numel())
+            if i == len(self.early) - 1:
+                self.n_early = o
+        if not self.early:
+            self.n_early = 0
+        self.n = o
         self.flat = None
         self._arrived = 0
         self._work = []
@@ -47,25 +59,23 @@ class FlatGradReducer:
     def attach(self):
         dev = self.params[0].device
         self.flat = torch.zeros(self.n, dtype=torch.float32, device=dev)
-        o = 0
-        for p in self.params:
-            v = self.flat[o:o + p.numel()].view_as(p)
+        for p, (o, numel) in zip(self.params, self.offsets):
+            v = self.flat[o:o + numel].view_as(p)
             if p.grad is not None:
                 v.copy_(p.grad)
             p.grad = v
-            o += p.numel()
         for p in self.early:
             self._hooks.append(p.register_post_accumulate_grad_hook(self._on_early_grad))
 
     def layout(self):
-        o, out = 0, []
-        for p in self.params:
-            out.append((o, p.numel()))
-            o += p.numel()
-        return out, o
+        return list(self.offsets), self.n
 
     def zero(self):
         self.flat.zero_()
+        self.reset()
+
+    def reset(self):
+        """Per-step bookkeeping only (the fused optimizer clears the buffer itself)."""
         self._arrived = 0
         self._work = []
 

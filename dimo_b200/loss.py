@@ -22,7 +22,7 @@ class _ImageLoss(torch.autograd.Function):
         keep = bool(need_ssim_grad) and img1.requires_grad
         dm = torch.empty(3, B, C, H, W, dtype=torch.float32, device=dev) if keep else None
         _lib.call("dimo_ssim_fwd", B, C, H, W, int(clamp01), _lib.ptr(img1), _lib.ptr(img2), _lib.ptr(sums), _lib.ptr(dm),
-                  _lib.stream())
+                  None, None, 0.0, 0.0, 0.0, _lib.stream())
         ctx.save_for_backward(img1, img2, dm)
         ctx.dims = (B, C, H, W)
         ctx.clamp01 = int(clamp01)
@@ -38,7 +38,7 @@ class _ImageLoss(torch.autograd.Function):
             raise RuntimeError("ssim gradient requested but the derivative maps were not kept")
         out = torch.empty_like(img1)
         _lib.call("dimo_ssim_bwd", B, C, H, W, ctx.clamp01, _lib.ptr(img1), _lib.ptr(img2), _lib.ptr(dm), gw[0], gw[1], gw[2],
-                  _lib.ptr(out), _lib.stream())
+                  None, None, _lib.ptr(out), _lib.stream())
         return out, None, None, None
 
 

@@ -1,0 +1,102 @@
+"""Optimizer of the loop: torch.optim.Adam over GaussianModel.training_setup's parameter groups
+(renderer/latent_gs_renderer.py:453-476; stepped at main_train_dimo.py:416-417) as ONE kernel launch.
+
+All parameters are re-homed as views of one flat fp32 buffer whose layout equals that of the flat gradient
+buffer (`dist.FlatGradReducer`), so `dimo_adam_step` walks (param, grad, exp_avg, exp_avg_sq) with 128-bit
+accesses and clears the gradient in the same pass (optimizer.zero_grad() folded in).  Learning rates are per
+parameter group, live in a small device array and may change between steps (`update_learning_rate`, :502-520)
+without re-capturing a CUDA graph; the step counter is device-resident for the same reason.
+
+Same interface subset as torch.optim.Adam that the reference touches: `param_groups` (list of dicts with
+"params", "lr", "name"), `step()`, `zero_grad()`, `state_dict()` / `load_state_dict()`.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+class FusedAdam:
+    def __init__(self, param_groups, reducer, betas=(0.9, 0.999), eps=1e-15, lr=0.0, fold_zero_grad=True):
+        """param_groups: list of {"params": [...], "lr": float, "name": str} (or a flat list of tensors -> one group);
+        reducer: the FlatGradReducer that owns the flat gradient buffer (defines the layout)."""
+        if param_groups and not isinstance(param_groups[0], dict):
+            param_groups = [{"params": list(param_groups), "lr": lr, "name": "all"}]
+        self.param_groups = []
+        for g in param_groups:
+            ps = [p for p in g["params"] if p.numel() > 0]
+            self.param_groups.append({"params": ps, "lr": float(g.get("lr", lr)), "name": g.get("name", "")})
+        self.reducer = reducer
+        self.betas = (float(betas[0]), float(betas[1]))
+        self.eps = float(eps)
+        self.fold_zero_grad = bool(fold_zero_grad)
+        group_of = {}
+        for gi, g in enumerate(self.param_groups):
+            for p in g["params"]:
+                group_of[id(p)] = gi
+        dev = reducer.flat.device
+        n = reducer.flat.numel()
+        assert n % 4 == 0, "flat buffer must be padded to a multiple of 4 floats"
+        # parameters become views of one flat buffer laid out like the gradient buffer
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        begins, groups = [], []
+        for p, (off, numel) in zip(reducer.params, reducer.offsets):
+            if id(p) not in group_of:
+                raise ValueError("every parameter of the flat gradient buffer needs an optimizer group")
+            view = self.flat[off:off + numel].view_as(p)
+            view.copy_(p.data)
+            p.data = view
+            gi = group_of[id(p)]
+            if groups and groups[-1] == gi:
+                continue                      # same group as the previous tensor: extend the segment
+            begins.append(off)
+            groups.append(gi)
+        begins.append(n)
+        self._seg_group = groups
+        self._seg_begin = (ctypes.c_int64 * len(begins))(*begins)
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.state = torch.zeros(4, dtype=torch.int32, device=dev)     # [0] step count, [1] ticket
+        self._lr_host = torch.zeros(len(groups), dtype=torch.float32).pin_memory() if dev.type == "cuda" else \
+            torch.zeros(len(groups), dtype=torch.float32)
+        self._lr_dev = torch.zeros(len(groups), dtype=torch.float32, device=dev)
+        self._lr_sent = None
+        self.sync_lrs()
+
+    # ------------------------------------------------------------------------------------------
+    def sync_lrs(self):
+        """Uploads the groups' learning rates if they changed (call outside a graph capture / before a replay)."""
+        cur = tuple(self.param_groups[g]["lr"] for g in self._seg_group)
+        if cur != self._lr_sent:
+            for i, v in enumerate(cur):
+                self._lr_host[i] = v
+            self._lr_dev.copy_(self._lr_host, non_blocking=True)
+            self._lr_sent = cur
+
+    def step(self):
+        if not torch.cuda.is_current_stream_capturing():
+            self.sync_lrs()
+        _lib.call("dimo_adam_step", self.flat.numel(), _lib.ptr(self.flat), _lib.ptr(self.reducer.flat),
+                  _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), len(self._seg_group), self._seg_begin,
+                  _lib.ptr(self._lr_dev), self.betas[0], self.betas[1], self.eps, int(self.fold_zero_grad),
+                  _lib.ptr(self.state), _lib.stream())
+
+    def zero_grad(self, set_to_none=False):
+        """No kernel when the clear is folded into step(); the reducer's bookkeeping is reset either way."""
+        if self.fold_zero_grad:
+            self.reducer.reset()
+        else:
+            self.reducer.zero()
+
+    # ------------------------------------------------------------------------------------------
+    def state_dict(self):
+        return {"step": int(self.state[0].item()), "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
+                "lrs": [g["lr"] for g in self.param_groups], "names": [g["name"] for g in self.param_groups]}
+
+    def load_state_dict(self, sd):
+        self.exp_avg.copy_(sd["exp_avg"]); self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.state.zero_(); self.state[0] = int(sd["step"])
+        for g, lr in zip(self.param_groups, sd["lrs"]):
+            g["lr"] = float(lr)
+        self.sync_lrs()

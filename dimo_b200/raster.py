@@ -131,6 +131,7 @@ class _Rasterize(torch.autograd.Function):
                                                         colors_precomp, B, N, W, H, sh_degree, scale_modifier,
                                                         capacity)
         ctx.st = st
+        ctx.set_materialize_grads(False)     # unused outputs (depth / normal in the image-loss step) arrive as None
         ctx.save_for_backward(means3D, scales, rotations, shs)
         ctx.shapes = (means3D.shape, None if means2D is None else means2D.shape, scales.shape, rotations.shape,
                       opacities.shape, None if shs is None else shs.shape,
@@ -150,8 +151,11 @@ class _Rasterize(torch.autograd.Function):
         f32 = dict(dtype=torch.float32, device=dev)
         zeros = lambda *s: torch.zeros(*s, **f32)
         g_color = g_color.contiguous() if g_color is not None else zeros(B, 3, H, W)
-        g_depth = g_depth.contiguous() if g_depth is not None else zeros(B, 1, H, W)
-        g_normal = g_normal.contiguous() if g_normal is not None else zeros(B, 3, H, W)
+        if g_depth is None and g_normal is None:
+            pass        # NULL for both: the kernel drops the four channels (dimo_raster_blend_bwd, DN = false)
+        else:
+            g_depth = g_depth.contiguous() if g_depth is not None else zeros(B, 1, H, W)
+            g_normal = g_normal.contiguous() if g_normal is not None else zeros(B, 3, H, W)
         g_alpha = g_alpha.contiguous() if g_alpha is not None else zeros(B, 1, H, W)
         s = _lib.stream()
         dsplats = torch.empty(B * N, SPLAT_FLOATS, **f32)

@@ -102,6 +102,22 @@ class GaussianModel:
         return [self._xyz, self._features_dc, self._features_rest, self._opacity, self._scaling, self._rotation,
                 self._c_xyz, self._c_radius, self._latent_codes] + list(self._timenet.parameters())
 
+    # reference group names and order: GaussianModel.training_setup, renderer/latent_gs_renderer.py:460-473
+    GROUP_NAMES = ("xyz", "f_dc", "f_rest", "opacity", "scaling", "rotation", "latent_code", "deform", "deform_rot",
+                   "c_xyz", "c_radius", "r")
+
+    def param_groups(self, lr=0.0):
+        """The twelve optimizer groups of training_setup.  lr: float (every group) or {name: lr} (missing -> 0.0,
+        the reference constructs Adam with lr=0.0 and per-group values)."""
+        mlp, mlp_rot = self._timenet.get_mlp_parameters()
+        tensors = {"xyz": [self._xyz], "f_dc": [self._features_dc], "f_rest": [self._features_rest],
+                   "opacity": [self._opacity], "scaling": [self._scaling], "rotation": [self._rotation],
+                   "latent_code": [self._latent_codes], "deform": list(mlp), "deform_rot": list(mlp_rot),
+                   "c_xyz": [self._c_xyz], "c_radius": [self._c_radius], "r": [self._r]}
+        get = (lambda n: float(lr.get(n, 0.0))) if isinstance(lr, dict) else (lambda n: float(lr))
+        return [{"params": [p for p in tensors[n] if isinstance(p, nn.Parameter)], "lr": get(n), "name": n}
+                for n in self.GROUP_NAMES]
+
     def find_knn(self, k=4):
         """main_train_dimo.py:502-509 (GUI.find_knn): once per optimisation step."""
         self.neighbor_dists, self.neighbor_indices = _knn.knn(self._c_xyz, self._xyz, k)

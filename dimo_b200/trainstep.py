@@ -17,6 +17,7 @@ import torch
 
 from . import _lib
 from .dist import FlatGradReducer
+from .optim import FusedAdam
 from .renderer import Renderer
 
 
@@ -28,48 +29,53 @@ class StepLossWeights:
 
 
 class _StepLoss(torch.autograd.Function):
-    """loss = l_mse * sum_f MSE(clamp(img_f), gt_f) + l_ssim * sum_m (1 - SSIM(clamp(img_m), gt_m))
+    """loss = l_mse * sum_f w_f MSE(clamp(img_f), gt_f) + l_ssim * sum_m (1 - SSIM(clamp(img_m), gt_m))
             + l_mask * sum_m MSE(alpha_m, mask_m)
-    over S frames grouped in n_motions equal groups (main_train_dimo.py:328-351; the reference's 0.5 factor on
-    non-reference views is taken as 1).  One fused forward kernel per tensor pair, one fused backward; no host sync."""
+    over S frames grouped in n_motions equal groups (main_train_dimo.py:328-351).  w_f is the reference's 1 / 0.5
+    weighting of reference / non-reference (view, frame) pairs (:333-336; `frame_w` [S] on the device, None = all 1).
+    Launches: one fused SSIM+MSE forward over the images, one squared-difference reduction over the masks (both add
+    their weighted sums straight into the loss scalar), two gradient kernels that read the upstream gradient as a
+    device scalar.  No host sync, no elementwise glue."""
 
     @staticmethod
-    def forward(ctx, image, alpha, gt, mask, n_motions, l_mse, l_ssim, l_mask):
+    def forward(ctx, image, alpha, gt, mask, frame_w, n_motions, l_mse, l_ssim, l_mask):
         S, _, H, W = image.shape
         dev = image.device
         image = image.contiguous(); alpha = alpha.contiguous(); gt = gt.contiguous(); mask = mask.contiguous()
-        sums_i = torch.empty(3, dtype=torch.float32, device=dev)
-        sums_a = torch.empty(3, dtype=torch.float32, device=dev)
+        sums = torch.empty(4, dtype=torch.float32, device=dev)        # [ssim, l1, mse] of the images | mask sq. sum
         dm = torch.empty(3, S, 3, H, W, dtype=torch.float32, device=dev)
-        s = _lib.stream()
-        _lib.call("dimo_ssim_fwd", S, 3, H, W, 1, _lib.ptr(image), _lib.ptr(gt), _lib.ptr(sums_i), _lib.ptr(dm), s)
-        _lib.call("dimo_ssim_fwd", S, 1, H, W, 0, _lib.ptr(alpha), _lib.ptr(mask), _lib.ptr(sums_a), None, s)
         n_img = float(3 * H * W)
         per_motion = S // n_motions
-        # sum_f MSE_f = sums_i[2] / n_img ; sum_m (1 - ssim_m) = n_motions - sums_i[0] / (per_motion * n_img)
-        loss = (l_mse / n_img) * sums_i[2] + l_ssim * (n_motions - sums_i[0] / (per_motion * n_img)) \
-            + (l_mask / (per_motion * H * W)) * sums_a[2]
-        ctx.save_for_backward(image, alpha, gt, mask, dm)
-        ctx.w = (-l_ssim / (per_motion * n_img), l_mse / n_img, l_mask / (per_motion * H * W))
+        # sum_f w_f MSE_f = sums[2] / n_img ; sum_m (1 - ssim_m) = n_motions - sums[0] / (per_motion * n_img)
+        w_ssim, w_mse, w_mask = -l_ssim / (per_motion * n_img), l_mse / n_img, l_mask / (per_motion * H * W)
+        loss = torch.full((), l_ssim * n_motions, dtype=torch.float32, device=dev)
+        s = _lib.stream()
+        _lib.call("dimo_ssim_fwd", S, 3, H, W, 1, _lib.ptr(image), _lib.ptr(gt), _lib.ptr(sums), _lib.ptr(dm),
+                  _lib.ptr(frame_w), _lib.ptr(loss), w_ssim, 0.0, w_mse, s)
+        _lib.call("dimo_sqdiff_sum", S * H * W, _lib.ptr(alpha), _lib.ptr(mask), sums.data_ptr() + 12, _lib.ptr(loss),
+                  w_mask, s)
+        ctx.save_for_backward(image, alpha, gt, mask, dm, frame_w)
+        ctx.w = (w_ssim, w_mse, w_mask)
         return loss
 
     @staticmethod
     def backward(ctx, g):
-        image, alpha, gt, mask, dm = ctx.saved_tensors
+        image, alpha, gt, mask, dm, frame_w = ctx.saved_tensors
         S, _, H, W = image.shape
         w_ssim, w_mse, w_mask = ctx.w
         s = _lib.stream()
+        g = g.contiguous().float()
         d_img = torch.empty_like(image)
         d_alpha = torch.empty_like(alpha)
         _lib.call("dimo_ssim_bwd", S, 3, H, W, 1, _lib.ptr(image), _lib.ptr(gt), _lib.ptr(dm), w_ssim, 0.0, w_mse,
-                  _lib.ptr(d_img), s)
+                  _lib.ptr(frame_w), _lib.ptr(g), _lib.ptr(d_img), s)
         _lib.call("dimo_ssim_bwd", S, 1, H, W, 0, _lib.ptr(alpha), _lib.ptr(mask), None, 0.0, 0.0, w_mask,
-                  _lib.ptr(d_alpha), s)
-        return d_img * g, d_alpha * g, None, None, None, None, None, None
+                  None, _lib.ptr(g), _lib.ptr(d_alpha), s)
+        return d_img, d_alpha, None, None, None, None, None, None, None
 
 
-def step_loss(image, alpha, gt, mask, n_motions, weights=StepLossWeights):
-    return _StepLoss.apply(image, alpha, gt, mask, n_motions, weights.lambda_mse, weights.lambda_ssim,
+def step_loss(image, alpha, gt, mask, n_motions, weights=StepLossWeights, frame_w=None):
+    return _StepLoss.apply(image, alpha, gt, mask, frame_w, n_motions, weights.lambda_mse, weights.lambda_ssim,
                            weights.lambda_mask)
 
 
@@ -78,18 +84,32 @@ class TrainStep:
     process group once per step (the only exchange on the path; frames are sharded by motion)."""
 
     def __init__(self, renderer: Renderer, lr=1e-4, world=1, stage="s2", graph=False, probe_steps=3,
-                 capacity_margin=1.25):
+                 capacity_margin=1.25, optimizer="fused"):
+        """lr: one float for every group, or {group name: lr} with the reference's group names
+        (renderer/latent_gs_renderer.py:460-473).  optimizer: "fused" (dimo_adam_step, one launch incl. zero_grad) or
+        "torch" (torch.optim.Adam(fused=True), kept for A/B runs)."""
         self.r = renderer
         self.g = renderer.gaussians
         self.stage = stage
         self.world = world
         self.params = [p for p in self.g.parameters() if p.numel() > 0]
-        self.opt = torch.optim.Adam(self.params, lr=lr, eps=1e-15, fused=True, capturable=bool(graph))
         g = self.g
         # per-Gaussian parameters: their gradients are final once the LBS backward has run, i.e. before the
         # TimeNet backward -> bucket 0 of the flat buffer, all-reduced while the MLP backward executes
         early = [g._xyz, g._features_dc, g._features_rest, g._opacity, g._scaling, g._rotation]
         self.reducer = FlatGradReducer(self.params, early=early)
+        groups = g.param_groups(lr)
+        if optimizer == "fused":
+            self.opt = FusedAdam(groups, self.reducer, eps=1e-15)
+        else:
+            self.opt = torch.optim.Adam([{"params": [p for p in gr["params"] if p.numel() > 0], "lr": gr["lr"],
+                                          "name": gr["name"]} for gr in groups if any(p.numel() for p in gr["params"])],
+                                        lr=0.0, eps=1e-15, fused=True, capturable=bool(graph))
+        self.fused_opt = optimizer == "fused"
+        g.optimizer = self.opt
+        # TimeNet's weight gradients are accumulated by the kernels straight into the flat buffer
+        g._timenet.direct_grads = True
+        self.frame_w = None           # optional [S] device tensor: per-frame MSE weights (main_train_dimo.py:333-336)
         # graph mode state
         self.use_graph = bool(graph)
         self.probe_steps = int(probe_steps)
@@ -122,13 +142,17 @@ class TrainStep:
             self._max_R = max(self._max_R, st.R)
         elif overflow_acc is not None:
             overflow_acc.copy_(torch.maximum(overflow_acc, st.count_overflow))
-        loss = step_loss(out["image_raw"], out["alpha"], gt, mask, n_motions)
+        loss = step_loss(out["image_raw"], out["alpha"], gt, mask, n_motions, frame_w=self.frame_w)
         loss.backward()                                   # gradients accumulate straight into reducer.flat
         if self.world > 1:
             self._timed("py:allreduce_wait", self.reducer.reduce)
-        if optimize:
-            self._timed("py:adam", self.opt.step)
-        self._timed("py:zero_grad", self.reducer.zero)
+        if optimize and self.fused_opt:
+            self.opt.step()                               # dimo_adam_step: update + gradient clear in one launch
+            self.opt.zero_grad()
+        else:
+            if optimize:
+                self._timed("py:adam", self.opt.step)
+            self._timed("py:zero_grad", self.reducer.zero)
         return loss
 
     def _capture(self, prep, gt, mask, n_motions, optimize):
@@ -181,5 +205,7 @@ class TrainStep:
         self.r.prepare_step(cameras, times, latent_indices, out=st["prep"])
         st["gt"].copy_(gt, non_blocking=True)
         st["mask"].copy_(mask, non_blocking=True)
+        if self.fused_opt:
+            self.opt.sync_lrs()                            # learning-rate changes reach the replay through device memory
         self.graph.replay()
         return st["loss"]

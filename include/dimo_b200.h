@@ -107,7 +107,9 @@ int dimo_raster_blend_fwd(
     const uint32_t* ranges, float* out_color, float* out_depth, float* out_normal, float* out_alpha,
     float* final_T, int32_t* n_contrib, void* stream);
 
-/* Backward of stage 3: dL_dsplats [B*N,16] (zeroed here, then accumulated), gradient-record layout above. */
+/* Backward of stage 3: dL_dsplats [B*N,16] (zeroed here, then accumulated), gradient-record layout above.
+ * dL_ddepth and dL_dnormal may BOTH be NULL (no loss term reads depth / normal, e.g. the MSE + SSIM + mask step):
+ * the four channels are then compiled out of the pixel loop and of the warp reduction. */
 int dimo_raster_blend_bwd(
     int B, int N, int W, int H, const float* cams, const float* splats, const uint32_t* vals_sorted,
     const uint32_t* ranges, const float* final_T, const int32_t* n_contrib,
@@ -208,11 +210,43 @@ int dimo_lbs_bwd(int B, int N, int M, int K, const float* xyz, const float* rot,
  *   renderer/latent_gs_renderer.py:1279) and the backward zeroes the gradient outside [0,1].
  * ------------------------------------------------------------------------------------------- */
 int dimo_ssim_fwd(int B, int C, int H, int W, int clamp01, const float* img1, const float* img2,
-                  float* sums, float* dm, void* stream);
-/* dL_dimg1 [B,C,H,W] = w_ssim * d(sum ssim_map)/dimg1 + w_l1 * d(sum|a-b|)/dimg1 + w_mse * d(sum (a-b)^2)/dimg1.
- * Weights are host floats: the caller folds 1/numel and the loss weights in. */
+                  float* sums, float* dm, const float* mse_frame_w, float* loss_acc, float lw_ssim, float lw_l1,
+                  float lw_mse, void* stream);
+/*   mse_frame_w [B] (device, or NULL = 1): per-frame weight of the squared-error sum -- the reference weights the MSE
+ *   of non-reference views/frames by 0.5 (main_train_dimo.py:331-336); sums[2] is then the weighted sum.
+ *   loss_acc (device scalar, or NULL): loss_acc += lw_ssim*sums[0] + lw_l1*sums[1] + lw_mse*sums[2], accumulated by
+ *   the kernel itself so the step's scalar loss needs no elementwise launches; NOT zeroed by the callee. */
+
+/* dL_dimg1 [B,C,H,W] = g * (w_ssim * d(sum ssim_map)/dimg1 + w_l1 * d(sum|a-b|)/dimg1
+ *                           + w_mse * mse_frame_w[b] * d(sum (a-b)^2)/dimg1).
+ * Weights are host floats: the caller folds 1/numel and the loss weights in.  g = *g_dev, the upstream gradient of
+ * the scalar loss as a DEVICE scalar (NULL = 1).  w_ssim == 0 skips the convolutions (dm may then be NULL). */
 int dimo_ssim_bwd(int B, int C, int H, int W, int clamp01, const float* img1, const float* img2, const float* dm,
-                  float w_ssim, float w_l1, float w_mse, float* dL_dimg1, void* stream);
+                  float w_ssim, float w_l1, float w_mse, const float* mse_frame_w, const float* g_dev,
+                  float* dL_dimg1, void* stream);
+
+/* sum (a-b)^2 over n floats -> sum[0] (zeroed by the callee); optional
+ * loss_acc += lw * sum.  The mask term F.mse_loss(render_alpha, gt_mask), main_train_dimo.py:350; its gradient is
+ * dimo_ssim_bwd with w_ssim = 0. */
+int dimo_sqdiff_sum(int64_t n, const float* a, const float* b, float* sum, float* loss_acc, float lw, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Optimizer: torch.optim.Adam(groups, lr=0.0, eps=1e-15) of GaussianModel.training_setup
+ * (renderer/latent_gs_renderer.py:453-476), stepped + zero_grad'ed at main_train_dimo.py:416-417.
+ *   params / grads / exp_avg / exp_avg_sq: flat fp32 buffers of n floats (n % 4 == 0) with identical layout;
+ *   nseg learning-rate segments: seg_begin_host [nseg+1] (host array, element offsets, multiples of 4, covering
+ *   [0,n)), seg_lr [nseg] (DEVICE array, so learning-rate schedules work under CUDA-graph replay);
+ *   state [4] i32 (device): [0] = number of updates applied so far (bias correction uses state[0]+1 and the
+ *   kernel increments it), [1] scratch (must start 0);  zero_grads != 0: grads are cleared in the same pass.
+ * ------------------------------------------------------------------------------------------- */
+int dimo_adam_step(int64_t n, float* params, float* grads, float* exp_avg, float* exp_avg_sq, int nseg,
+                   const int64_t* seg_begin_host, const float* seg_lr, double beta1, double beta2, float eps,
+                   int zero_grads, int* state, void* stream);
+
+/* dst_k[c][r] = src_k[r][c] for n <= 16 row-major matrices in ONE launch (W^T operands of the tensor-core
+ * data-gradient GEMMs); all four arguments are host arrays of length n. */
+int dimo_transpose_grouped(int n, const int* rows_host, const int* cols_host, const float* const* src_host,
+                           float* const* dst_host, void* stream);
 
 #ifdef __cplusplus
 }

@@ -43,12 +43,16 @@ def loss_weights(H, W, seed=1):
                 n=torch.rand(3, H, W, generator=g) - 0.5, a=torch.rand(1, H, W, generator=g))
 
 
-def weighted_loss(img, depth, normal, alpha, w):
-    return (img * w["c"]).sum() + (depth * w["d"]).sum() + (normal * w["n"]).sum() + (alpha * w["a"]).sum()
+def weighted_loss(img, depth, normal, alpha, w, use_dn=True):
+    """use_dn=False: depth and normal stay out of the loss -> the CUDA backward runs its 9-field (DN = false) variant"""
+    l = (img * w["c"]).sum() + (alpha * w["a"]).sum()
+    if use_dn:
+        l = l + (depth * w["d"]).sum() + (normal * w["n"]).sum()
+    return l
 
 
 def run_raster_pair(N, W, H, view=1, nviews=8, sh_degree=0, seed=0, scale_boost=0.0, bg=(1.0, 1.0, 1.0),
-                    device="cuda"):
+                    device="cuda", use_dn=True):
     """Runs the oracle (CPU fp32 + autograd) and the CUDA path on identical inputs; returns both result dicts."""
     K = (sh_degree + 1) ** 2
     xyz, scales, rot, op, shs = scene_inputs(N, seed, K, scale_boost)
@@ -62,7 +66,7 @@ def run_raster_pair(N, W, H, view=1, nviews=8, sh_degree=0, seed=0, scale_boost=
     o = oraster.rasterize(leaves[0], leaves[1], leaves[2], leaves[3], ocam.world_view_transform,
                           ocam.full_proj_transform, ocam.camera_center, ocam.tanfovx, ocam.tanfovy, W, H, bg_t,
                           shs=leaves[4], sh_degree=sh_degree, means2D=m2d)
-    weighted_loss(o["image"], o["depth"], o["normal"], o["alpha"], w).backward()
+    weighted_loss(o["image"], o["depth"], o["normal"], o["alpha"], w, use_dn).backward()
     o["grads"] = dict(means3D=leaves[0].grad, scales=leaves[1].grad, rotations=leaves[2].grad,
                       opacities=leaves[3].grad, shs=leaves[4].grad, means2D=m2d.grad)
 
@@ -78,7 +82,7 @@ def run_raster_pair(N, W, H, view=1, nviews=8, sh_degree=0, seed=0, scale_boost=
     color, depth, normal, alpha, radii = draster.rasterize_batch(
         cams, cl[0], cl[1], cl[2], cl[3], W, H, shs=cl[4], sh_degree=sh_degree, means2D=cm2d, state_out=state)
     wd = {k: v.to(device) for k, v in w.items()}
-    weighted_loss(color[0], depth[0], normal[0], alpha[0], wd).backward()
+    weighted_loss(color[0], depth[0], normal[0], alpha[0], wd, use_dn).backward()
     torch.cuda.synchronize()
     st = state[0]
     # the library sorts 32-bit tile ids (emitted front-to-back); rebuild the reference-shaped 64-bit

@@ -44,7 +44,9 @@ def _worker(rank, world, port, q):
             loss = loss + (p * w).sum()
     loss.backward()
     n = red.reduce()
-    assert n == sum(p.numel() for p in params) == red.flat.numel()      # one buffer
+    total = sum(p.numel() for p in params)
+    assert n == red.flat.numel() and total <= n < total + 4 * len(params)      # one buffer (16-byte aligned tensors)
+    assert all(o % 4 == 0 for o, _ in red.offsets) and red.n_early % 4 == 0
     for p in params:
         assert p.grad.untyped_storage().data_ptr() == red.flat.untyped_storage().data_ptr()
     q.put((rank, [p.grad.numpy().copy() for p in params], [l.numpy().copy() for l in local]))

@@ -5,15 +5,17 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("N,W,H,deg,boost", [
-    (800, 64, 64, 0, 0.0),
-    (3000, 128, 96, 0, 0.5),      # non-square, bigger splats -> long tile lists
-    (1500, 70, 50, 3, 0.3),       # ragged image (partial tiles) + SH degree 3
-    (1, 32, 32, 0, 2.0),          # single Gaussian
+@pytest.mark.parametrize("N,W,H,deg,boost,use_dn", [
+    (800, 64, 64, 0, 0.0, True),
+    (3000, 128, 96, 0, 0.5, True),      # non-square, bigger splats -> long tile lists
+    (1500, 70, 50, 3, 0.3, True),       # ragged image (partial tiles) + SH degree 3
+    (1, 32, 32, 0, 2.0, True),          # single Gaussian
+    (3000, 128, 96, 0, 0.5, False),     # loss without depth / normal: 9-field backward variant
+    (1500, 70, 50, 3, 0.3, False),
 ])
-def test_raster_matches_oracle(cuda, N, W, H, deg, boost):
+def test_raster_matches_oracle(cuda, N, W, H, deg, boost, use_dn):
     import gpu_parity as gp
-    o, c = gp.run_raster_pair(N, W, H, sh_degree=deg, scale_boost=boost)
+    o, c = gp.run_raster_pair(N, W, H, sh_degree=deg, scale_boost=boost, use_dn=use_dn)
     ints, flo, gr = gp.compare_raster(o, c)
     assert all(v == 0 for v in ints.values()), f"integer outputs differ: {ints}"
     for k in ("image", "depth", "normal", "alpha", "final_T"):
