@@ -367,7 +367,7 @@ def run_ours(args, wl):
                        "execution": ("whole step replayed as one CUDA graph (rasteriser in capacity mode: "
                                      f"{capacity} instance slots, max count seen {count_seen}, overflow={overflow})")
                        if graph_used else ("eager launches" + (f" (graph capture failed: {ts.graph_error})" if ts.graph_error else "")),
-                       "optimizer": "torch fused Adam (plumbing; hand-written fused Adam is SURVEY 8f N1)",
+                       "optimizer": "dimo_adam_step: one launch over the flat parameter/gradient buffers, zero_grad folded in",
                        "l2": "per-step working set (GT 64 MiB + splat/instance buffers > 200 MiB) exceeds the 126 MB L2; no explicit flush",
                        "raster_MPix_per_s_fwd_bwd": value * H * W / 1e6},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
@@ -392,13 +392,15 @@ def algorithmic_bytes(name, wl, S, st):
     R = st.get("R") or 0
     BN = wl["N"] * S
     table = {
-        "dimo_raster_blend_fwd": 64 * R + 40 * P,
-        "dimo_raster_blend_bwd": 64 * R + 4 * R + 72 * P + 2 * 52 * R,
+        "dimo_raster_blend_fwd": 68 * R + 40 * P,                 # record gather + index, 10 output planes
+        # depth/normal carry no gradient in this step: 24 B/px in, 9 gradient fields (RMW) per (tile, splat)
+        "dimo_raster_blend_bwd": 68 * R + 24 * P + 2 * 36 * R,
         "dimo_raster_preprocess": 56 * BN + 72 * BN,
-        "dimo_raster_bin": 12 * R + 6 * 24 * R + 2 * 64 * R,
+        "dimo_raster_bin": 8 * R + 2 * 16 * R + 4 * R,             # emit, 2 radix passes over (key, value), ranges
         "dimo_raster_preprocess_bwd": 64 * BN + 44 * BN + 60 * BN,
         "dimo_ssim_fwd": 8 * 3 * P + 36 * P,
         "dimo_ssim_bwd": 60 * P + 12 * P,
+        "dimo_adam_step": 32 * st.get("n_params", 0),
     }
     return table.get(name)
 

@@ -58,8 +58,11 @@ class FusedAdam:
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.state = torch.zeros(4, dtype=torch.int32, device=dev)     # [0] step count, [1] ticket
-        self._lr_host = torch.zeros(len(groups), dtype=torch.float32).pin_memory() if dev.type == "cuda" else \
-            torch.zeros(len(groups), dtype=torch.float32)
+        # learning rates travel through a small ring of pinned staging buffers (asynchronous copies; a slot is
+        # reused only after its previous copy has completed)
+        self._lr_ring = [torch.zeros(len(groups), dtype=torch.float32).pin_memory() for _ in range(4)]
+        self._lr_events = [None] * 4
+        self._lr_slot = 0
         self._lr_dev = torch.zeros(len(groups), dtype=torch.float32, device=dev)
         self._lr_sent = None
         self.sync_lrs()
@@ -69,9 +72,17 @@ class FusedAdam:
         """Uploads the groups' learning rates if they changed (call outside a graph capture / before a replay)."""
         cur = tuple(self.param_groups[g]["lr"] for g in self._seg_group)
         if cur != self._lr_sent:
+            k = self._lr_slot
+            self._lr_slot = (k + 1) % len(self._lr_ring)
+            if self._lr_events[k] is not None:
+                self._lr_events[k].synchronize()
+            host = self._lr_ring[k]
             for i, v in enumerate(cur):
-                self._lr_host[i] = v
-            self._lr_dev.copy_(self._lr_host, non_blocking=True)
+                host[i] = v
+            self._lr_dev.copy_(host, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            self._lr_events[k] = ev
             self._lr_sent = cur
 
     def step(self):

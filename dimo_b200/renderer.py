@@ -179,7 +179,7 @@ class Renderer:
         g = self.gaussians
         prep = prepared if prepared is not None else self.prepare_step(cameras, times, latent_indices, bg_color)
         W, H = prep["W"], prep["H"]
-        latents = g._latent_codes[prep["li"]]                               # [U,L]
+        latents = g._latent_codes.index_select(0, prep["li"])               # [U,L]
         t_dev = prep["t"]
         if stage >= "s2":
             dxyz, dquat = g._timenet.forward_batched(g._c_xyz, t_dev, latents)   # [U,M,3],[U,M,4]
@@ -195,8 +195,10 @@ class Renderer:
             raise ValueError("Nonexistent stage!!!")
         if xyz_detach:
             means3D_u = means3D_u.detach()
-        means3D = means3D_u[prep["pf"]] if prep["expand"] else means3D_u
-        rotations = rot_u[prep["pf"]] if prep["expand"] else rot_u
+        # (motion, t) pair -> frames.  index_select: its backward is one index_add (advanced indexing would run a
+        # sort-based index_put with half a dozen helper launches per tensor)
+        means3D = means3D_u.index_select(0, prep["pf"]) if prep["expand"] else means3D_u
+        rotations = rot_u.index_select(0, prep["pf"]) if prep["expand"] else rot_u
 
         shs = colors = None
         if override_color is None:
