@@ -20,11 +20,11 @@ _SIGS = {
     "dimo_device_info": (c_int, [c_vp]),
     "dimo_raster_scan_temp_bytes": (c_sz, [c_i64]),
     "dimo_raster_sort_temp_bytes": (c_sz, [c_i64]),
-    "dimo_raster_preprocess": (c_int, [c_int] * 6 + [c_f32, c_vp] + [c_vp, c_i64] * 6 + [c_vp] * 6 + [c_vp, c_sz, c_vp, c_vp]),
+    "dimo_raster_preprocess": (c_int, [c_int] * 6 + [c_f32, c_vp, c_vp] + [c_vp, c_i64] * 6 + [c_vp] * 6 + [c_vp, c_sz, c_vp, c_vp]),
     "dimo_raster_bin": (c_int, [c_int] * 4 + [c_i64] + [c_vp] * 8 + [c_vp, c_sz, c_vp, c_vp, c_vp]),
     "dimo_raster_blend_fwd": (c_int, [c_int] * 3 + [c_vp] * 11),
     "dimo_raster_blend_bwd": (c_int, [c_int] * 4 + [c_vp] * 12),
-    "dimo_raster_preprocess_bwd": (c_int, [c_int] * 6 + [c_f32, c_vp] + [c_vp, c_i64] * 4 + [c_vp] * 10),
+    "dimo_raster_preprocess_bwd": (c_int, [c_int] * 6 + [c_f32, c_vp, c_vp] + [c_vp, c_i64] * 4 + [c_vp] * 10),
     "dimo_knn": (c_int, [c_int] * 3 + [c_vp] * 5),
     "dimo_dist3nn": (c_int, [c_int, c_vp, c_vp, c_vp]),
     "dimo_linear_fwd": (c_int, [c_int] * 3 + [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_int, c_vp]),
@@ -40,6 +40,7 @@ _SIGS = {
     "dimo_lbs_bwd": (c_int, [c_int] * 4 + [c_vp] * 17),
     "dimo_ssim_fwd": (c_int, [c_int] * 5 + [c_vp] * 6 + [c_f32] * 3 + [c_vp]),
     "dimo_ssim_bwd": (c_int, [c_int] * 5 + [c_vp] * 3 + [c_f32] * 3 + [c_vp] * 4),
+    "dimo_segment_sum": (c_int, [c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "dimo_sqdiff_sum": (c_int, [c_i64] + [c_vp] * 4 + [c_f32, c_vp]),
     "dimo_adam_step": (c_int, [c_i64] + [c_vp] * 4 + [c_int, c_vp, c_vp, c_f64, c_f64, c_f32, c_int, c_vp, c_vp]),
     "dimo_transpose_grouped": (c_int, [c_int] + [c_vp] * 5),
@@ -99,7 +100,7 @@ _OWN_LAUNCHES = {
     "dimo_raster_preprocess_bwd": 1, "dimo_knn": 1, "dimo_dist3nn": 1, "dimo_linear_fwd": 1,
     "dimo_linear_bwd_data": 1, "dimo_linear_tc": 1, "dimo_linear_wgrad_tc": 1, "dimo_linear_wgrad_tc_grouped": 1, "dimo_linear_bwd_weight": 1, "dimo_timenet_embed_fwd": 1,
     "dimo_timenet_embed_bwd": 1, "dimo_lbs_fwd": 1, "dimo_lbs_bwd": 1, "dimo_ssim_fwd": 1, "dimo_ssim_bwd": 1,
-    "dimo_sqdiff_sum": 1, "dimo_adam_step": 1, "dimo_transpose_grouped": 1,
+    "dimo_sqdiff_sum": 1, "dimo_segment_sum": 1, "dimo_adam_step": 1, "dimo_transpose_grouped": 1,
 }
 
 

@@ -90,7 +90,8 @@ using namespace dimo;
 
 namespace dimo {
 int preprocess_launch(int B, int N, int W, int H, int sh_degree, int sh_coeffs, float scale_modifier,
-                      const float* cams, const float* means3D, int64_t means3D_bstride, const float* scales,
+                      const float* cams, const int32_t* frame_src, const float* means3D, int64_t means3D_bstride,
+                      const float* scales,
                       int64_t scales_bstride, const float* rotations, int64_t rotations_bstride,
                       const float* opacities, int64_t opacities_bstride, const float* shs, int64_t shs_bstride,
                       const float* colors_precomp, int64_t colors_bstride, float* splats, int32_t* radii,
@@ -132,7 +133,8 @@ size_t dimo_raster_sort_temp_bytes(int64_t R) {
 }
 
 int dimo_raster_preprocess(int B, int N, int W, int H, int sh_degree, int sh_coeffs, float scale_modifier,
-                           const float* cams, const float* means3D, int64_t means3D_bstride, const float* scales,
+                           const float* cams, const int32_t* frame_src, const float* means3D,
+                           int64_t means3D_bstride, const float* scales,
                            int64_t scales_bstride, const float* rotations, int64_t rotations_bstride,
                            const float* opacities, int64_t opacities_bstride, const float* shs,
                            int64_t shs_bstride, const float* colors_precomp, int64_t colors_bstride,
@@ -151,7 +153,8 @@ int dimo_raster_preprocess(int B, int N, int W, int H, int sh_degree, int sh_coe
     return 0;
   }
   // depth_keys: [2*BN] (unsorted | sorted), perm: [2*BN] (iota | sorted permutation = perm + BN)
-  int rc = preprocess_launch(B, N, W, H, sh_degree, sh_coeffs, scale_modifier, cams, means3D, means3D_bstride, scales,
+  int rc = preprocess_launch(B, N, W, H, sh_degree, sh_coeffs, scale_modifier, cams, frame_src, means3D,
+                             means3D_bstride, scales,
                              scales_bstride, rotations, rotations_bstride, opacities, opacities_bstride, shs,
                              shs_bstride, colors_precomp, colors_bstride, splats, radii, tiles_touched, depth_keys,
                              perm, st);

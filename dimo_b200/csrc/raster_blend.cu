@@ -37,6 +37,9 @@ constexpr float LN2 = 0.6931471805599453f;
 
 // Gather mode (dimo_tc_debug_set key 3): 0 = one 64-byte bulk copy per record, 1 = four 16-byte cp.async per record.
 int g_blend_gather_mode = 0;
+// Records per shared-memory stage of the backward kernel (dimo_tc_debug_set key 4): 128, or 64 = half the shared memory
+// per CTA (12.7 KB instead of 25.6 KB) -> occupancy is no longer shared-memory bound, at twice the barrier rounds.
+int g_blend_bwd_chunk = 64;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -285,7 +288,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int MODE, bool DN>
+template <int MODE, bool DN, int CH>
 __global__ void __launch_bounds__(BLEND_THREADS) blend_bwd_kernel(
     int W, int H, int gx, int tiles_per_frame, const float* __restrict__ cams, const float4* __restrict__ table,
     const uint32_t* __restrict__ vals_sorted, const uint2* __restrict__ ranges, const float* __restrict__ final_T,
@@ -293,8 +296,8 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_bwd_kernel(
     const float* __restrict__ dL_dcolor, const float* __restrict__ dL_ddepth, const float* __restrict__ dL_dnormal,
     const float* __restrict__ dL_dalpha, float* __restrict__ dL_dsplats) {
   constexpr int NG = BwdFields<DN>::NG;
-  __shared__ __align__(128) float4 sm[2][CHUNK * REC_F4];
-  __shared__ float acc[2][CHUNK * NG];          // [warp][record][field]
+  __shared__ __align__(128) float4 sm[2][CH * REC_F4];
+  __shared__ float acc[2][CH * NG];          // [warp][record][field]
   __shared__ __align__(8) uint64_t bar[2];
   __shared__ int s_max;
 
@@ -346,7 +349,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_bwd_kernel(
     mbar_init(&bar[1], MODE == 0 ? 1 : BLEND_THREADS);
     fence_mbar_init();
   }
-  for (int k = tid; k < 2 * CHUNK * NG; k += BLEND_THREADS) (&acc[0][0])[k] = 0.f;
+  for (int k = tid; k < 2 * CH * NG; k += BLEND_THREADS) (&acc[0][0])[k] = 0.f;
   __syncthreads();
   {
     int m = lmax;
@@ -357,12 +360,12 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_bwd_kernel(
   __syncthreads();
   const int nproc = s_max;   // list positions [0, nproc) hold every contributor of this tile
   if (nproc == 0) return;
-  const int nchunks = (nproc + CHUNK - 1) / CHUNK;
+  const int nchunks = (nproc + CH - 1) / CH;
   const uint32_t* ids = vals_sorted + rng.x;
   auto load_ids = [&](int cc, uint32_t& i0, uint32_t& i1) {
-    const int p0 = cc * CHUNK + tid;
+    const int p0 = cc * CH + tid;
     i0 = p0 < nproc ? ids[p0] : 0u;
-    i1 = p0 + 64 < nproc ? ids[p0 + 64] : 0u;
+    i1 = (CH > BLEND_THREADS && p0 + 64 < nproc) ? ids[p0 + 64] : 0u;
   };
 
   // chunk k of the descending walk is list chunk (nchunks-1-k); stage = k&1
@@ -370,7 +373,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_bwd_kernel(
   for (int k = 0; k < 2 && k < nchunks; ++k) {
     const int cc = nchunks - 1 - k;
     load_ids(cc, nid0, nid1);
-    stage_gather<MODE>(&sm[k][0], table, nid0, nid1, min(CHUNK, nproc - cc * CHUNK), tid, &bar[k]);
+    stage_gather<MODE>(&sm[k][0], table, nid0, nid1, min(CH, nproc - cc * CH), tid, &bar[k]);
   }
   if (nchunks > 2) load_ids(nchunks - 3, nid0, nid1);
 
@@ -378,11 +381,11 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_bwd_kernel(
   for (int k = 0; k < nchunks; ++k) {
     const int stage = k & 1;
     const int cc = nchunks - 1 - k;
-    const int cnt = min(CHUNK, nproc - cc * CHUNK);
+    const int cnt = min(CH, nproc - cc * CH);
     mbar_wait(&bar[stage], (k >> 1) & 1);
     const float4* s = &sm[stage][0];
     for (int j = cnt - 1; j >= 0; --j) {
-      const int pos = cc * CHUNK + j;
+      const int pos = cc * CH + j;
       unsigned hit = 0;
       float p[PPT];
       float4 a, bq;
@@ -503,7 +506,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_bwd_kernel(
     __syncthreads();
     if (k + 2 < nchunks) {
       const int c2 = nchunks - 1 - (k + 2);
-      stage_gather<MODE>(&sm[stage][0], table, nid0, nid1, min(CHUNK, nproc - c2 * CHUNK), tid, &bar[stage]);
+      stage_gather<MODE>(&sm[stage][0], table, nid0, nid1, min(CH, nproc - c2 * CH), tid, &bar[stage]);
       if (k + 3 < nchunks) load_ids(c2 - 1, nid0, nid1);
     }
   }
@@ -542,8 +545,12 @@ extern "C" int dimo_raster_blend_bwd(int B, int N, int W, int H, const float* ca
   DIMO_REQUIRE((dL_ddepth == nullptr) == (dL_dnormal == nullptr), "dL_ddepth and dL_dnormal: pass both or neither");
   DIMO_REQUIRE(dL_dcolor != nullptr && dL_dalpha != nullptr, "dL_dcolor / dL_dalpha must not be NULL");
   const bool dn = dL_ddepth != nullptr;
-  auto kern = g_blend_gather_mode == 0 ? (dn ? blend_bwd_kernel<0, true> : blend_bwd_kernel<0, false>)
-                                       : (dn ? blend_bwd_kernel<1, true> : blend_bwd_kernel<1, false>);
+  const bool small = g_blend_bwd_chunk == 64;
+  auto kern = g_blend_gather_mode == 0
+                  ? (dn ? (small ? blend_bwd_kernel<0, true, 64> : blend_bwd_kernel<0, true, 128>)
+                        : (small ? blend_bwd_kernel<0, false, 64> : blend_bwd_kernel<0, false, 128>))
+                  : (dn ? (small ? blend_bwd_kernel<1, true, 64> : blend_bwd_kernel<1, true, 128>)
+                        : (small ? blend_bwd_kernel<1, false, 64> : blend_bwd_kernel<1, false, 128>));
   kern<<<B * gx * gy, BLEND_THREADS, 0, st>>>(
       W, H, gx, gx * gy, cams, reinterpret_cast<const float4*>(splats), vals_sorted,
       reinterpret_cast<const uint2*>(ranges), final_T, n_contrib, dL_dcolor, dL_ddepth, dL_dnormal, dL_dalpha,

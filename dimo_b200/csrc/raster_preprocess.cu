@@ -188,7 +188,7 @@ __device__ __forceinline__ void sh_basis_grad(int deg, float x, float y, float z
 
 __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
     int B, int N, int W, int H, int sh_degree, int sh_coeffs, float scale_modifier,
-    const float* __restrict__ cams,
+    const float* __restrict__ cams, const int32_t* __restrict__ frame_src,
     const float* __restrict__ means3D, int64_t means3D_bs,
     const float* __restrict__ scales, int64_t scales_bs,
     const float* __restrict__ rotations, int64_t rot_bs,
@@ -203,11 +203,12 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
   const int i = (int)(idx - (int64_t)b * N);
   const float* cam = cams + (int64_t)b * DIMO_CAM_FLOATS;
 
-  const float* pm = means3D + b * means3D_bs + 3 * (int64_t)i;
+  const int bsrc = frame_src != nullptr ? frame_src[b] : b;   // deformation block of this frame ((motion, t) pair)
+  const float* pm = means3D + bsrc * means3D_bs + 3 * (int64_t)i;
   const float px = pm[0], py = pm[1], pz = pm[2];
   const float* ps = scales + b * scales_bs + 3 * (int64_t)i;
   const float sc[3] = {ps[0], ps[1], ps[2]};
-  const float4 q4 = *reinterpret_cast<const float4*>(rotations + b * rot_bs + 4 * (int64_t)i);
+  const float4 q4 = *reinterpret_cast<const float4*>(rotations + bsrc * rot_bs + 4 * (int64_t)i);
   const float q[4] = {q4.x, q4.y, q4.z, q4.w};
 
   Geo g;
@@ -278,7 +279,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
 
 __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
     int B, int N, int W, int H, int sh_degree, int sh_coeffs, float scale_modifier,
-    const float* __restrict__ cams,
+    const float* __restrict__ cams, const int32_t* __restrict__ frame_src,
     const float* __restrict__ means3D, int64_t means3D_bs,
     const float* __restrict__ scales, int64_t scales_bs,
     const float* __restrict__ rotations, int64_t rot_bs,
@@ -307,11 +308,12 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
   const float* cam = cams + (int64_t)b * DIMO_CAM_FLOATS;
   const float* V = cam + CAM_VIEW;
   const float* P = cam + CAM_PROJ;
-  const float* pm = means3D + b * means3D_bs + 3 * (int64_t)i;
+  const int bsrc = frame_src != nullptr ? frame_src[b] : b;   // deformation block of this frame ((motion, t) pair)
+  const float* pm = means3D + bsrc * means3D_bs + 3 * (int64_t)i;
   const float px = pm[0], py = pm[1], pz = pm[2];
   const float* ps = scales + b * scales_bs + 3 * (int64_t)i;
   const float sc[3] = {ps[0], ps[1], ps[2]};
-  const float4 q4 = *reinterpret_cast<const float4*>(rotations + b * rot_bs + 4 * (int64_t)i);
+  const float4 q4 = *reinterpret_cast<const float4*>(rotations + bsrc * rot_bs + 4 * (int64_t)i);
   const float q[4] = {q4.x, q4.y, q4.z, q4.w};
   Geo g;
   project(cam, px, py, pz, sc, q, scale_modifier, W, H, g);
@@ -512,12 +514,45 @@ __global__ void __launch_bounds__(256) iota_kernel(int64_t n, uint32_t* __restri
   if (i < n) out[i] = (uint32_t)i;
 }
 
+// out[u, :] = sum over rows s with seg[s] == u of in[s, :]  (seg == NULL: every row belongs to segment 0), rows
+// added in ascending s (deterministic).  Folds the per-frame gradients of the rasteriser backward onto the inputs
+// they came from: a (motion, t) deformation shared by several views, or a parameter shared by all frames.
+// HBM: 4 B read per input element + 4 B written per output element.
+constexpr int SEG_MAX_ROWS = 1024;
+template <int VEC>
+__global__ void __launch_bounds__(256) segment_sum_kernel(int S, int64_t n, const int32_t* __restrict__ seg,
+                                                          const float* __restrict__ in, float* __restrict__ out) {
+  __shared__ int32_t s_seg[SEG_MAX_ROWS];
+  for (int k = threadIdx.x; k < S; k += blockDim.x) s_seg[k] = seg != nullptr ? seg[k] : 0;
+  __syncthreads();
+  const int u = blockIdx.y;
+  const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+  if (e >= n) return;
+  float acc[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+  for (int r = 0; r < S; ++r) {
+    if (s_seg[r] != u) continue;
+    const float* row = in + (int64_t)r * n + e;
+    if (VEC == 4) {
+      const float4 v = *reinterpret_cast<const float4*>(row);
+      acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+    } else {
+      acc[0] += row[0];
+    }
+  }
+  float* o = out + (int64_t)u * n + e;
+  if (VEC == 4) *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  else o[0] = acc[0];
+}
+
 }  // namespace dimo
 
 namespace dimo {
 
 int preprocess_launch(
     int B, int N, int W, int H, int sh_degree, int sh_coeffs, float scale_modifier, const float* cams,
+    const int32_t* frame_src,
     const float* means3D, int64_t means3D_bstride, const float* scales, int64_t scales_bstride,
     const float* rotations, int64_t rotations_bstride, const float* opacities, int64_t opacities_bstride,
     const float* shs, int64_t shs_bstride, const float* colors_precomp, int64_t colors_bstride,
@@ -527,9 +562,9 @@ int preprocess_launch(
   if (BN == 0) return 0;
   iota_kernel<<<ceil_div(BN, 256), 256, 0, st>>>(BN, iota);
   preprocess_fwd_kernel<<<ceil_div(BN, 256), 256, 0, st>>>(
-      B, N, W, H, sh_degree, sh_coeffs, scale_modifier, cams, means3D, means3D_bstride, scales, scales_bstride,
-      rotations, rotations_bstride, opacities, opacities_bstride, shs, shs_bstride, colors_precomp, colors_bstride,
-      reinterpret_cast<float4*>(splats), radii, tiles_touched, depth_keys);
+      B, N, W, H, sh_degree, sh_coeffs, scale_modifier, cams, frame_src, means3D, means3D_bstride, scales,
+      scales_bstride, rotations, rotations_bstride, opacities, opacities_bstride, shs, shs_bstride, colors_precomp,
+      colors_bstride, reinterpret_cast<float4*>(splats), radii, tiles_touched, depth_keys);
   DIMO_CHECK_LAUNCH();
   return 0;
 }
@@ -552,6 +587,7 @@ using namespace dimo;
 
 extern "C" int dimo_raster_preprocess_bwd(
     int B, int N, int W, int H, int sh_degree, int sh_coeffs, float scale_modifier, const float* cams,
+    const int32_t* frame_src,
     const float* means3D, int64_t means3D_bstride, const float* scales, int64_t scales_bstride,
     const float* rotations, int64_t rotations_bstride, const float* shs, int64_t shs_bstride,
     const int32_t* radii, const float* dL_dsplats, float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dscales,
@@ -562,10 +598,26 @@ extern "C" int dimo_raster_preprocess_bwd(
   DIMO_REQUIRE((dL_dshs != nullptr) != (dL_dcolors != nullptr), "exactly one of dL_dshs / dL_dcolors");
   DIMO_REQUIRE(dL_dcolors != nullptr || shs != nullptr, "shs required when colours come from SH");
   preprocess_bwd_kernel<<<ceil_div(BN, 256), 256, 0, (cudaStream_t)stream>>>(
-      B, N, W, H, sh_degree, sh_coeffs, scale_modifier, cams, means3D, means3D_bstride, scales, scales_bstride,
-      rotations, rotations_bstride, shs, shs_bstride, radii, reinterpret_cast<const float4*>(dL_dsplats),
+      B, N, W, H, sh_degree, sh_coeffs, scale_modifier, cams, frame_src, means3D, means3D_bstride, scales,
+      scales_bstride, rotations, rotations_bstride, shs, shs_bstride, radii, reinterpret_cast<const float4*>(dL_dsplats),
       dL_dmeans3D, dL_dmeans2D, dL_dscales, reinterpret_cast<float4*>(dL_drotations), dL_dopacities, dL_dshs,
       dL_dcolors);
+  DIMO_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dimo_segment_sum(int S, int U, int64_t n, const int32_t* seg, const float* in, float* out, void* stream) {
+  DIMO_REQUIRE(S >= 0 && S <= SEG_MAX_ROWS && U >= 0 && U <= 65535 && n >= 0, "segment_sum: S <= 1024, U <= 65535");
+  if (U == 0 || n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec = (n & 3) == 0 && ((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0;
+  if (vec) {
+    dim3 grid(ceil_div(n / 4, 256), U);
+    segment_sum_kernel<4><<<grid, 256, 0, st>>>(S, n, seg, in, out);
+  } else {
+    dim3 grid(ceil_div(n, 256), U);
+    segment_sum_kernel<1><<<grid, 256, 0, st>>>(S, n, seg, in, out);
+  }
   DIMO_CHECK_LAUNCH();
   return 0;
 }

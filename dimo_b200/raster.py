@@ -31,13 +31,14 @@ def pack_cameras(viewmatrix, projmatrix, campos, tanfovx, tanfovy, bg):
     return torch.cat([V, P, C, tan, G], dim=1).contiguous()
 
 
-def _bstride(t, B, per_frame_numel):
-    """element stride between frames: 0 if the tensor is shared by all frames"""
+def _bstride(t, B, per_frame_numel, blocks=None):
+    """element stride between frames: 0 if the tensor is shared by all frames.  blocks: number of blocks the
+    tensor may hold instead of B (inputs addressed through frame_src)."""
     if t is None:
         return 0
     if t.numel() == per_frame_numel:
         return 0
-    assert t.numel() == B * per_frame_numel, "batched argument has wrong size"
+    assert t.numel() == (B if blocks is None else blocks) * per_frame_numel, "batched argument has wrong size"
     return per_frame_numel
 
 
@@ -46,11 +47,11 @@ class RasterState:
     __slots__ = ("B", "N", "W", "H", "R", "count_overflow", "cams", "splats", "radii", "tiles_touched", "offsets", "perm",
                  "keys_sorted",
                  "vals_sorted", "ranges", "final_T", "n_contrib", "sh_degree", "sh_coeffs",
-                 "scale_modifier")
+                 "scale_modifier", "frame_src", "n_src")
 
 
 def _forward_impl(cams, means3D, scales, rotations, opacities, shs, colors_precomp, B, N, W, H, sh_degree,
-                  scale_modifier, capacity=None):
+                  scale_modifier, capacity=None, frame_src=None, n_src=None):
     """capacity=None: exact mode -- the instance count R is read back from the device once (a host sync, like the
     upstream rasterisers) and buffers are sized to it.  capacity=int: sync-free mode for CUDA graphs -- buffers hold
     `capacity` instance slots, `st.count_overflow` (device i32[2]) receives the true count and an overflow flag."""
@@ -64,6 +65,7 @@ def _forward_impl(cams, means3D, scales, rotations, opacities, shs, colors_preco
     st.sh_degree = int(sh_degree)
     st.sh_coeffs = 0 if shs is None else int(shs.shape[-2])
     st.scale_modifier = float(scale_modifier)
+    st.frame_src, st.n_src = frame_src, n_src
     BN = B * N
     st.splats = torch.empty(BN, SPLAT_FLOATS, **f32)
     st.radii = torch.empty(BN, **i32)
@@ -78,9 +80,10 @@ def _forward_impl(cams, means3D, scales, rotations, opacities, shs, colors_preco
     R_host = ctypes.c_int64(0)
     s = _lib.stream()
     _lib.call("dimo_raster_preprocess", B, N, W, H, st.sh_degree, st.sh_coeffs, st.scale_modifier, _lib.ptr(cams),
-              _lib.ptr(means3D), _bstride(means3D, B, N * 3),
+              _lib.ptr(frame_src),
+              _lib.ptr(means3D), _bstride(means3D, B, N * 3, n_src),
               _lib.ptr(scales), _bstride(scales, B, N * 3),
-              _lib.ptr(rotations), _bstride(rotations, B, N * 4),
+              _lib.ptr(rotations), _bstride(rotations, B, N * 4, n_src),
               _lib.ptr(opacities), _bstride(opacities, B, N),
               _lib.ptr(shs), _bstride(shs, B, N * st.sh_coeffs * 3),
               _lib.ptr(colors_precomp), _bstride(colors_precomp, B, N * 3),
@@ -126,10 +129,10 @@ def _forward_impl(cams, means3D, scales, rotations, opacities, shs, colors_preco
 class _Rasterize(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, scales, rotations, opacities, shs, colors_precomp, cams, B, N, W, H,
-                sh_degree, scale_modifier, state_out, capacity):
+                sh_degree, scale_modifier, state_out, capacity, frame_src, n_src):
         color, depth, normal, alpha, st = _forward_impl(cams, means3D, scales, rotations, opacities, shs,
                                                         colors_precomp, B, N, W, H, sh_degree, scale_modifier,
-                                                        capacity)
+                                                        capacity, frame_src, n_src)
         ctx.st = st
         ctx.set_materialize_grads(False)     # unused outputs (depth / normal in the image-loss step) arrive as None
         ctx.save_for_backward(means3D, scales, rotations, shs)
@@ -171,43 +174,58 @@ class _Rasterize(torch.autograd.Function):
         d_shs = torch.empty(B, N, st.sh_coeffs, 3, **f32) if use_sh else None
         d_col = None if use_sh else torch.empty(B, N, 3, **f32)
         _lib.call("dimo_raster_preprocess_bwd", B, N, W, H, st.sh_degree, st.sh_coeffs, st.scale_modifier,
-                  _lib.ptr(st.cams),
-                  _lib.ptr(means3D), _bstride(means3D, B, N * 3),
+                  _lib.ptr(st.cams), _lib.ptr(st.frame_src),
+                  _lib.ptr(means3D), _bstride(means3D, B, N * 3, st.n_src),
                   _lib.ptr(scales), _bstride(scales, B, N * 3),
-                  _lib.ptr(rotations), _bstride(rotations, B, N * 4),
+                  _lib.ptr(rotations), _bstride(rotations, B, N * 4, st.n_src),
                   _lib.ptr(shs), _bstride(shs, B, N * st.sh_coeffs * 3) if use_sh else 0,
                   _lib.ptr(st.radii), _lib.ptr(dsplats), _lib.ptr(d_means3D), _lib.ptr(d_means2D),
                   _lib.ptr(d_scales), _lib.ptr(d_rot), _lib.ptr(d_op), _lib.ptr(d_shs), _lib.ptr(d_col), s)
         sh_m3, sh_m2, sh_sc, sh_rot, sh_op, sh_shs, sh_col = ctx.shapes
 
-        def fit(g, shape, per_frame):
-            """[B, ...per-frame] -> the input's own shape (sum over frames when the input was shared)"""
+        def fit(g, shape, per_frame, mapped=False):
+            """[B, ...per-frame] -> the input's own shape: summed over all frames when the input was shared, over the
+            frames of each block when it was addressed through frame_src (one dimo_segment_sum launch either way)"""
             if shape is None or g is None:
                 return None
             numel = 1
             for d in shape:
                 numel *= d
-            if numel == per_frame and B > 1:
-                g = g.sum(dim=0)
-            return g.reshape(shape)
+            if numel == B * per_frame and not (mapped and st.frame_src is not None):
+                return g.reshape(shape)
+            U = numel // per_frame
+            if B > 1024:                       # beyond the kernel's row table: plain torch reduction (shared inputs only)
+                assert U == 1
+                return g.reshape(B, per_frame).sum(dim=0).reshape(shape)
+            out = torch.empty(U, per_frame, **f32)
+            _lib.call("dimo_segment_sum", B, U, per_frame, _lib.ptr(st.frame_src) if U > 1 else None, _lib.ptr(g),
+                      _lib.ptr(out), s)
+            return out.reshape(shape)
 
-        return (fit(d_means3D, sh_m3, N * 3), fit(d_means2D, sh_m2, N * 3) if ctx.needs_input_grad[1] else None,
-                fit(d_scales, sh_sc, N * 3), fit(d_rot, sh_rot, N * 4), fit(d_op, sh_op, N),
+        return (fit(d_means3D, sh_m3, N * 3, True), fit(d_means2D, sh_m2, N * 3) if ctx.needs_input_grad[1] else None,
+                fit(d_scales, sh_sc, N * 3), fit(d_rot, sh_rot, N * 4, True), fit(d_op, sh_op, N),
                 fit(d_shs, sh_shs, N * st.sh_coeffs * 3) if use_sh else None,
                 fit(d_col, sh_col, N * 3) if not use_sh else None,
-                None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None, None)
 
 
 def rasterize_batch(cams, means3D, scales, rotations, opacities, W, H, shs=None, colors_precomp=None,
-                    sh_degree=0, scale_modifier=1.0, means2D=None, state_out=None, capacity=None):
+                    sh_degree=0, scale_modifier=1.0, means2D=None, state_out=None, capacity=None, frame_src=None):
     """cams [B,40]; means3D [B,N,3] or [N,3]; scales [N,3]; rotations [B,N,4] or [N,4]; opacities [N,1]/[N];
-    shs [N,K,3] xor colors_precomp [B?,N,3].  Returns color [B,3,H,W], depth [B,1,H,W], normal [B,3,H,W],
-    alpha [B,1,H,W], radii [B,N] int32."""
+    shs [N,K,3] xor colors_precomp [B?,N,3].  frame_src [B] int32 (device): means3D / rotations are [U,N,*] and
+    frame b uses block frame_src[b] (frames that differ only in the view share one deformation).
+    Returns color [B,3,H,W], depth [B,1,H,W], normal [B,3,H,W], alpha [B,1,H,W], radii [B,N] int32."""
     if (shs is None) == (colors_precomp is None):
         raise ValueError("Please provide exactly one of either SHs or precomputed colors!")
     B = cams.shape[0]
     N = scales.shape[-2]
     c = lambda t: None if t is None else t.contiguous().float()
+    n_src = None
+    if frame_src is not None:
+        assert frame_src.dtype == torch.int32 and frame_src.numel() == B and means3D.dim() == 3
+        n_src = int(means3D.shape[0])
+        if B > 1024:
+            raise ValueError("frame_src supports at most 1024 frames per launch set")
     return _Rasterize.apply(c(means3D), means2D, c(scales), c(rotations), c(opacities), c(shs), c(colors_precomp),
                             cams.contiguous(), B, N, int(W), int(H), int(sh_degree), float(scale_modifier), state_out,
-                            capacity)
+                            capacity, frame_src, n_src)

@@ -159,23 +159,26 @@ class Renderer:
         cams = torch.cat([V, P, C, small[:, 0:2], bgd], dim=1)
         th = torch.tensor([[k[1], float(k[0])] for k in keys], dtype=torch.float32).to(dev, non_blocking=True)
         prep = {"cams": cams, "t": th[:, 0].contiguous(), "li": th[:, 1].long(), "pf": small[:, 2].long(),
+                "pf32": small[:, 2].int(),
                 "S": S, "U": len(keys), "W": int(cameras[0].image_width), "H": int(cameras[0].image_height),
                 "pair_of_frame": pair_of_frame, "expand": pair_of_frame != list(range(S))}
         if out is not None:
             assert out["S"] == prep["S"] and out["U"] == prep["U"] and out["expand"] == prep["expand"]
-            for k in ("cams", "t", "li", "pf"):
+            for k in ("cams", "t", "li", "pf", "pf32"):
                 out[k].copy_(prep[k])
             out["pair_of_frame"] = pair_of_frame
             return out
         return prep
 
     def render_batch(self, cameras=None, times=None, latent_indices=None, stage="s2", scaling_modifier=1.0,
-                     bg_color=None, override_color=None, xyz_detach=False, clamp=True, prepared=None, capacity=None):
+                     bg_color=None, override_color=None, xyz_detach=False, clamp=True, prepared=None, capacity=None,
+                     with_visibility=True):
         """All S frames of a step in ONE launch set.  cameras: list of S MiniCam (same W,H); times: list of S floats;
         latent_indices: list of S ints -- or `prepared` = the result of prepare_step().  capacity: instance-slot
         capacity for the sync-free rasteriser mode (None = exact mode with one host read-back).
         Returns a dict of batched tensors: image [S,3,H,W] (clamped), image_raw, depth, normal, alpha, radii [S,N],
-        visibility_filter, pts_t [S,N,3], cpts_t [U,M,3] + `pair_of_frame` (frame -> unique (motion,t) index)."""
+        visibility_filter, pts_t [U,N,3] (one block per unique (motion,t); frame f uses block pair_of_frame[f]),
+        cpts_t [U,M,3] + `pair_of_frame`."""
         g = self.gaussians
         prep = prepared if prepared is not None else self.prepare_step(cameras, times, latent_indices, bg_color)
         W, H = prep["W"], prep["H"]
@@ -195,23 +198,25 @@ class Renderer:
             raise ValueError("Nonexistent stage!!!")
         if xyz_detach:
             means3D_u = means3D_u.detach()
-        # (motion, t) pair -> frames.  index_select: its backward is one index_add (advanced indexing would run a
-        # sort-based index_put with half a dozen helper launches per tensor)
-        means3D = means3D_u.index_select(0, prep["pf"]) if prep["expand"] else means3D_u
-        rotations = rot_u.index_select(0, prep["pf"]) if prep["expand"] else rot_u
+        # (motion, t) pair -> frames: the rasteriser reads block pf[b] for frame b (no [S,N,*] copies) and its
+        # backward folds the per-frame gradients back onto the U blocks with one segment-sum launch per tensor
+        frame_src = prep["pf32"] if prep["expand"] else None
+        means3D, rotations = means3D_u, rot_u
 
         shs = colors = None
         if override_color is None:
-            shs = g.get_features
+            # no higher-order coefficients (sh_degree 0): the DC tensor IS the feature tensor, skip the concatenation
+            shs = g._features_dc if g._features_rest.shape[1] == 0 else g.get_features
         else:
             colors = override_color
         state = []
         color, depth, normal, alpha, radii = _raster.rasterize_batch(
             prep["cams"], means3D, g.get_scaling, rotations, g.get_opacity, W, H, shs=shs, colors_precomp=colors,
-            sh_degree=g.active_sh_degree, scale_modifier=scaling_modifier, state_out=state, capacity=capacity)
+            sh_degree=g.active_sh_degree, scale_modifier=scaling_modifier, state_out=state, capacity=capacity,
+            frame_src=frame_src)
         return {"image": color.clamp(0, 1) if clamp else None, "image_raw": color, "depth": depth, "normal": normal,
-                "alpha": alpha, "radii": radii, "visibility_filter": radii > 0, "pts_t": means3D, "cpts_t": cpts_t,
-                "pair_of_frame": prep["pair_of_frame"], "raster_state": state[0]}
+                "alpha": alpha, "radii": radii, "visibility_filter": (radii > 0) if with_visibility else None,
+                "pts_t": means3D, "cpts_t": cpts_t, "pair_of_frame": prep["pair_of_frame"], "raster_state": state[0]}
 
     # ------------------------------------------------------------------------------------------
     def render(self, viewpoint_camera, scaling_modifier=1.0, bg_color=None, override_color=None,

@@ -136,7 +136,8 @@ class TrainStep:
         if self.stage >= "s2":
             self.g.find_knn(4)
         # the loss kernel clamps the render to [0,1] on load (and masks the gradient), so skip the separate clamp pass
-        out = self.r.render_batch(prepared=prep, stage=self.stage, clamp=False, capacity=capacity)
+        out = self.r.render_batch(prepared=prep, stage=self.stage, clamp=False, capacity=capacity,
+                                  with_visibility=False)
         st = out["raster_state"]
         if capacity is None:
             self._max_R = max(self._max_R, st.R)

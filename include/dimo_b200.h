@@ -68,10 +68,13 @@ size_t dimo_raster_sort_temp_bytes(int64_t R);
  *   permutation (input of stage 2), offsets [B*N] u32 = inclusive scan in sorted order.
  *   shs [N,sh_coeffs,3] (or NULL) / colors_precomp [N,3] (or NULL): exactly one non-NULL.
  *   temp: dimo_raster_scan_temp_bytes(B*N) bytes.
- *   R_host: if non-NULL the stream is synchronised and the total instance count is stored there. */
+ *   R_host: if non-NULL the stream is synchronised and the total instance count is stored there.
+ *   frame_src [B] i32 (device, or NULL = identity): frame b reads means3D / rotations block frame_src[b] -- the
+ *   deformation depends on (motion, t) only, so the frames of a step that differ in the view alone share one
+ *   block (renderer/latent_gs_renderer.py:1191-1219 is recomputed per render upstream). */
 int dimo_raster_preprocess(
     int B, int N, int W, int H, int sh_degree, int sh_coeffs, float scale_modifier,
-    const float* cams,
+    const float* cams, const int32_t* frame_src,
     const float* means3D, int64_t means3D_bstride,
     const float* scales, int64_t scales_bstride,
     const float* rotations, int64_t rotations_bstride,
@@ -121,7 +124,7 @@ int dimo_raster_blend_bwd(
  *   dL_drotations [B,N,4], dL_dopacities [B,N], dL_dshs [B,N,sh_coeffs,3] or dL_dcolors [B,N,3]. */
 int dimo_raster_preprocess_bwd(
     int B, int N, int W, int H, int sh_degree, int sh_coeffs, float scale_modifier,
-    const float* cams,
+    const float* cams, const int32_t* frame_src,
     const float* means3D, int64_t means3D_bstride,
     const float* scales, int64_t scales_bstride,
     const float* rotations, int64_t rotations_bstride,
@@ -174,7 +177,8 @@ int dimo_linear_wgrad_tc_grouped(int n, int R, const int* K, const int* No, cons
                                  const float* const* X, const int64_t* ldx, float* const* dW, float* const* db,
                                  void* stream);
 /* bring-up knobs (0: swap LBO/SBO, 1: single-pass TF32, 2: wgrad CTA target, 3: blend gather via 16-byte
- * cp.async instead of 64-byte bulk copies); not part of the stable ABI */
+ * cp.async instead of 64-byte bulk copies, 4: records per stage of the blend backward, 64 or 128); not part of the
+ * stable ABI */
 int dimo_tc_debug_set(int key, int value);
 
 /* TimeNet input embedding h0[R,104] = [posenc(x,10) | posenc(t,6) | latent]  (pos_enc.py:35-36,
@@ -224,6 +228,11 @@ int dimo_ssim_fwd(int B, int C, int H, int W, int clamp01, const float* img1, co
 int dimo_ssim_bwd(int B, int C, int H, int W, int clamp01, const float* img1, const float* img2, const float* dm,
                   float w_ssim, float w_l1, float w_mse, const float* mse_frame_w, const float* g_dev,
                   float* dL_dimg1, void* stream);
+
+/* out[u,:] = sum of the rows s of in [S,n] with seg[s] == u (seg [S] i32 device; NULL: all rows -> segment 0), u < U,
+ * rows added in ascending order.  Folds per-frame gradients ([B,N,*], dimo_raster_preprocess_bwd) onto shared inputs:
+ * the (motion, t) block named by frame_src, or a per-Gaussian parameter shared by all frames.  S <= 1024. */
+int dimo_segment_sum(int S, int U, int64_t n, const int32_t* seg, const float* in, float* out, void* stream);
 
 /* sum (a-b)^2 over n floats -> sum[0] (zeroed by the callee); optional
  * loss_acc += lw * sum.  The mask term F.mse_loss(render_alpha, gt_mask), main_train_dimo.py:350; its gradient is

@@ -66,6 +66,43 @@ def test_batched_equals_single(cuda):
             assert torch.equal(a[v], b[0])
 
 
+def test_frame_src_equals_expanded_inputs(cuda):
+    """frames addressed through frame_src (one deformation block per (motion, t) pair, shared by the views) ==
+    the same frames with the blocks materialised per frame: forward bit-identical, gradients folded per block."""
+    import math
+    import gpu_parity as gp
+    from dimo_b200 import raster as draster
+    from dimo_b200.camera import orbit_minicam
+    N, W, H = 2000, 96, 80
+    xyz, scales, rot, op, shs = [t.cuda() for t in gp.scene_inputs(N, scale_boost=0.3)]
+    g = torch.Generator().manual_seed(3)
+    U = 3
+    means_u = (xyz[None] + 0.02 * torch.randn(U, N, 3, generator=g).cuda())
+    rot_u = torch.nn.functional.normalize(rot[None] + 0.1 * torch.randn(U, N, 4, generator=g).cuda(), dim=-1)
+    pf = torch.tensor([0, 1, 0, 1, 2, 2, 1], dtype=torch.int64, device="cuda")      # 7 frames over 3 blocks
+    cams = []
+    for v in range(7):
+        cam = orbit_minicam(v, 7, W, H)
+        cams.append(draster.pack_cameras(cam.world_view_transform, cam.full_proj_transform, cam.camera_center,
+                                         math.tan(cam.FoVx / 2), math.tan(cam.FoVy / 2), torch.ones(3, device="cuda")))
+    cams = torch.cat(cams)
+    wc = torch.rand(7, 3, H, W, device="cuda"); wa = torch.rand(7, 1, H, W, device="cuda")
+    res = []
+    for mapped in (False, True):
+        leaves = [t.clone().requires_grad_(True) for t in (means_u, rot_u, scales, op, shs)]
+        if mapped:
+            out = draster.rasterize_batch(cams, leaves[0], leaves[2], leaves[1], leaves[3], W, H, shs=leaves[4],
+                                          frame_src=pf.int())
+        else:
+            out = draster.rasterize_batch(cams, leaves[0][pf], leaves[2], leaves[1][pf], leaves[3], W, H, shs=leaves[4])
+        ((out[0] * wc).sum() + (out[3] * wa).sum()).backward()
+        res.append((out, [l.grad.clone() for l in leaves]))
+    for a, b in zip(res[0][0], res[1][0]):
+        assert torch.equal(a, b)
+    for a, b in zip(res[0][1], res[1][1]):
+        assert gp.rel_err(b, a) < 1e-6
+
+
 def test_raster_full_size_c2_shape(cuda):
     """BASELINE config-2 shape: 30k Gaussians, 512x512, vs the oracle.  Integers must be bit-exact.  Pixels: the
     alpha>=1/255 and T>=1e-4 decisions can flip between two exp implementations at a handful of (pixel, splat)
