@@ -45,6 +45,9 @@ def parse():
                     help="item: loss.item() every step (host sync); async: non_blocking D2H into pinned memory, one sync at the end")
     ap.add_argument("--cpu-frames", type=int, default=1, help="frames in the bounded CPU sample")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the whole-step CUDA graph")
+    ap.add_argument("--regularisers", action="store_true",
+                    help="add the depth / normal smoothness terms of the real step (main_train_dimo.py:363-372); "
+                         "not part of the BASELINE metric, reported for completeness")
     return ap.parse_args()
 
 
@@ -199,7 +202,8 @@ def run_ours(args, wl):
     from dimo_b200.camera import orbit_minicam
 
     r, _ = build_model(wl, rank, dev)
-    ts = trainstep.TrainStep(r, lr=1e-5, world=world, graph=not args.no_graph, probe_steps=6, capacity_margin=1.12)
+    ts = trainstep.TrainStep(r, lr=1e-5, world=world, graph=not args.no_graph, probe_steps=6, capacity_margin=1.12,
+                             regularisers=args.regularisers)
     H, W = wl["H"], wl["W"]
     S = wl["bm"] * wl["bv"] * wl["bf"]
     cams_all = [orbit_minicam(v, wl["views"], W, H, device=dev) for v in range(wl["views"])]
@@ -369,6 +373,7 @@ def run_ours(args, wl):
                        if graph_used else ("eager launches" + (f" (graph capture failed: {ts.graph_error})" if ts.graph_error else "")),
                        "optimizer": "dimo_adam_step: one launch over the flat parameter/gradient buffers, zero_grad folded in",
                        "l2": "per-step working set (GT 64 MiB + splat/instance buffers > 200 MiB) exceeds the 126 MB L2; no explicit flush",
+                       "loss": "MSE + SSIM + mask MSE" + (" + depth/normal smoothness" if args.regularisers else ""),
                        "raster_MPix_per_s_fwd_bwd": value * H * W / 1e6},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": _lib.PROFILE.kernel_launches_per_step(prof_steps)}

@@ -40,6 +40,8 @@ _SIGS = {
     "dimo_lbs_bwd": (c_int, [c_int] * 4 + [c_vp] * 17),
     "dimo_ssim_fwd": (c_int, [c_int] * 5 + [c_vp] * 6 + [c_f32] * 3 + [c_vp]),
     "dimo_ssim_bwd": (c_int, [c_int] * 5 + [c_vp] * 3 + [c_f32] * 3 + [c_vp] * 4),
+    "dimo_smooth_fwd": (c_int, [c_int] * 4 + [c_vp] * 5 + [c_f32] * 4 + [c_vp]),
+    "dimo_smooth_bwd": (c_int, [c_int] * 4 + [c_vp] * 3 + [c_f32] * 4 + [c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
     "dimo_segment_sum": (c_int, [c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "dimo_sqdiff_sum": (c_int, [c_i64] + [c_vp] * 4 + [c_f32, c_vp]),
     "dimo_adam_step": (c_int, [c_i64] + [c_vp] * 4 + [c_int, c_vp, c_vp, c_f64, c_f64, c_f32, c_int, c_vp, c_vp]),
@@ -100,7 +102,7 @@ _OWN_LAUNCHES = {
     "dimo_raster_preprocess_bwd": 1, "dimo_knn": 1, "dimo_dist3nn": 1, "dimo_linear_fwd": 1,
     "dimo_linear_bwd_data": 1, "dimo_linear_tc": 1, "dimo_linear_wgrad_tc": 1, "dimo_linear_wgrad_tc_grouped": 1, "dimo_linear_bwd_weight": 1, "dimo_timenet_embed_fwd": 1,
     "dimo_timenet_embed_bwd": 1, "dimo_lbs_fwd": 1, "dimo_lbs_bwd": 1, "dimo_ssim_fwd": 1, "dimo_ssim_bwd": 1,
-    "dimo_sqdiff_sum": 1, "dimo_segment_sum": 1, "dimo_adam_step": 1, "dimo_transpose_grouped": 1,
+    "dimo_sqdiff_sum": 1, "dimo_smooth_fwd": 1, "dimo_smooth_bwd": 1, "dimo_segment_sum": 1, "dimo_adam_step": 1, "dimo_transpose_grouped": 1,
 }
 
 

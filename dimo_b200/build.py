@@ -32,6 +32,7 @@ SOURCES = {
     "mlp_tc.cu": [],
     "ssim.cu": [],
     "optim.cu": [],
+    "smooth.cu": [],
 }
 
 

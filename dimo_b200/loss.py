@@ -59,6 +59,60 @@ def fused_ssim(img1, img2, padding="same", train=True):
     return image_losses(img1, img2, need_ssim_grad=train)[0]
 
 
+class _Smoothness(torch.autograd.Function):
+    """l_smooth * edge_aware_smoothness(depth, rgb) + l_bilateral * bilateral_normal_smoothness(normal, rgb) summed over
+    `groups` equal groups of frames (the reference evaluates both per motion, main_train_dimo.py:363-372).
+    rgb [B,3,H,W], depth [B,1,H,W], normal [B,3,H,W]; differentiable in all three."""
+
+    @staticmethod
+    def forward(ctx, rgb, depth, normal, groups, l_smooth, l_bilateral, clamp01):
+        rgb = rgb.contiguous().float(); depth = depth.contiguous().float(); normal = normal.contiguous().float()
+        B, _, H, W = rgb.shape
+        per = B // groups
+        nx, ny = float(per * H * max(W - 1, 1)), float(per * max(H - 1, 1) * W)
+        w = (l_smooth / nx, l_smooth / ny, l_bilateral / (3.0 * nx), l_bilateral / (3.0 * ny))
+        sums = torch.empty(4, dtype=torch.float32, device=rgb.device)
+        loss = torch.zeros((), dtype=torch.float32, device=rgb.device)
+        _lib.call("dimo_smooth_fwd", B, H, W, int(clamp01), _lib.ptr(rgb), _lib.ptr(depth), _lib.ptr(normal),
+                  _lib.ptr(sums), _lib.ptr(loss), w[0], w[1], w[2], w[3], _lib.stream())
+        ctx.save_for_backward(rgb, depth, normal)
+        ctx.w, ctx.clamp01 = w, int(clamp01)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        rgb, depth, normal = ctx.saved_tensors
+        B, _, H, W = rgb.shape
+        w = ctx.w
+        g = g.contiguous().float()
+        d_rgb = torch.empty_like(rgb); d_depth = torch.empty_like(depth); d_normal = torch.empty_like(normal)
+        _lib.call("dimo_smooth_bwd", B, H, W, ctx.clamp01, _lib.ptr(rgb), _lib.ptr(depth), _lib.ptr(normal),
+                  w[0], w[1], w[2], w[3], _lib.ptr(g), _lib.ptr(d_rgb), 0, _lib.ptr(d_depth), _lib.ptr(d_normal),
+                  _lib.stream())
+        return d_rgb, d_depth, d_normal, None, None, None, None
+
+
+def smoothness_losses(rgb, depth, normal, groups=1, lambda_smooth=1.0, lambda_bilateral=1.0, clamp01=False):
+    """NCHW entry point of the two step regularisers; returns their weighted sum as a scalar tensor."""
+    return _Smoothness.apply(rgb, depth, normal, groups, float(lambda_smooth), float(lambda_bilateral), clamp01)
+
+
+def compute_edge_aware_smoothness_loss(depth, rgb):
+    """src/loss.py:64 signature: depth [batch,H,W,1], rgb [batch,H,W,3] (channel-last, as the reference calls it)."""
+    d = depth.permute(0, 3, 1, 2)
+    c = rgb.permute(0, 3, 1, 2)
+    n = torch.zeros_like(c)
+    return _Smoothness.apply(c, d, n, 1, 1.0, 0.0, False)
+
+
+def compute_bilateral_normal_smoothness_loss(normal, rgb):
+    """src/loss.py:87 signature: normal [batch,H,W,3], rgb [batch,H,W,3]."""
+    n = normal.permute(0, 3, 1, 2)
+    c = rgb.permute(0, 3, 1, 2)
+    d = torch.zeros_like(c[:, :1])
+    return _Smoothness.apply(c, d, n, 1, 0.0, 1.0, False)
+
+
 def l1_loss(a, b):
     return image_losses(a, b, need_ssim_grad=False)[1]
 

@@ -16,6 +16,7 @@ Two execution modes, same kernels, same results:
 import torch
 
 from . import _lib
+from . import loss as _loss
 from .dist import FlatGradReducer
 from .optim import FusedAdam
 from .renderer import Renderer
@@ -26,6 +27,8 @@ class StepLossWeights:
     lambda_mse = 5000.0
     lambda_ssim = 500.0
     lambda_mask = 500.0
+    lambda_smooth = 100.0        # edge-aware depth smoothness (add_depth, after depth_reg_start_iter), :49-51
+    lambda_bilateral = 0.05      # bilateral normal smoothness (add_normal, after normal_reg_start_iter), :53-55
 
 
 class _StepLoss(torch.autograd.Function):
@@ -84,7 +87,7 @@ class TrainStep:
     process group once per step (the only exchange on the path; frames are sharded by motion)."""
 
     def __init__(self, renderer: Renderer, lr=1e-4, world=1, stage="s2", graph=False, probe_steps=3,
-                 capacity_margin=1.25, optimizer="fused"):
+                 capacity_margin=1.25, optimizer="fused", regularisers=False):
         """lr: one float for every group, or {group name: lr} with the reference's group names
         (renderer/latent_gs_renderer.py:460-473).  optimizer: "fused" (dimo_adam_step, one launch incl. zero_grad) or
         "torch" (torch.optim.Adam(fused=True), kept for A/B runs)."""
@@ -110,6 +113,8 @@ class TrainStep:
         # TimeNet's weight gradients are accumulated by the kernels straight into the flat buffer
         g._timenet.direct_grads = True
         self.frame_w = None           # optional [S] device tensor: per-frame MSE weights (main_train_dimo.py:333-336)
+        # depth / normal smoothness terms of the real step (main_train_dimo.py:363-372); off in the north-star step
+        self.regularisers = bool(regularisers)
         # graph mode state
         self.use_graph = bool(graph)
         self.probe_steps = int(probe_steps)
@@ -144,6 +149,10 @@ class TrainStep:
         elif overflow_acc is not None:
             overflow_acc.copy_(torch.maximum(overflow_acc, st.count_overflow))
         loss = step_loss(out["image_raw"], out["alpha"], gt, mask, n_motions, frame_w=self.frame_w)
+        if self.regularisers:
+            loss = loss + _loss.smoothness_losses(out["image_raw"], out["depth"], out["normal"], groups=n_motions,
+                                                  lambda_smooth=StepLossWeights.lambda_smooth,
+                                                  lambda_bilateral=StepLossWeights.lambda_bilateral, clamp01=True)
         loss.backward()                                   # gradients accumulate straight into reducer.flat
         if self.world > 1:
             self._timed("py:allreduce_wait", self.reducer.reduce)

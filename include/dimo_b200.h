@@ -240,6 +240,25 @@ int dimo_segment_sum(int S, int U, int64_t n, const int32_t* seg, const float* i
 int dimo_sqdiff_sum(int64_t n, const float* a, const float* b, float* sum, float* loss_acc, float lw, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Step regularisers on the rendered maps: compute_edge_aware_smoothness_loss and
+ * compute_bilateral_normal_smoothness_loss, src/loss.py:64-107, as main_train_dimo.py:363-372 applies them.
+ *   rgb [B,3,H,W] (clamp01: clamped to [0,1] on load, gradient masked outside), depth [B,1,H,W], normal [B,3,H,W].
+ *   sums4 (zeroed by the callee) = { sum over x-pairs of |dd| e^-gi, same over y-pairs,
+ *                                    sum over x-pairs and channels of sqrt(1 + (|dn| e^-3gi)^2), same over y-pairs }
+ *   with gi = mean_c |rgb_p - rgb_q|; the reference's means divide by B*H*(W-1) / B*(H-1)*W (x3 for the normals).
+ *   wdx, wdy, wnx, wny: weight of each sum in the loss (the caller folds lambda and the normalisers in);
+ *   loss_acc (device scalar or NULL) += the weighted total.
+ * Backward: d_depth, d_normal are overwritten; d_rgb is overwritten or (accumulate_rgb != 0) added to -- the
+ * exp(-gi) factor depends on the rendered image, so the image receives a gradient too; g_dev = upstream gradient of
+ * the scalar loss (device scalar, NULL = 1).
+ * ------------------------------------------------------------------------------------------- */
+int dimo_smooth_fwd(int B, int H, int W, int clamp01, const float* rgb, const float* depth, const float* normal,
+                    float* sums4, float* loss_acc, float wdx, float wdy, float wnx, float wny, void* stream);
+int dimo_smooth_bwd(int B, int H, int W, int clamp01, const float* rgb, const float* depth, const float* normal,
+                    float wdx, float wdy, float wnx, float wny, const float* g_dev, float* d_rgb, int accumulate_rgb,
+                    float* d_depth, float* d_normal, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Optimizer: torch.optim.Adam(groups, lr=0.0, eps=1e-15) of GaussianModel.training_setup
  * (renderer/latent_gs_renderer.py:453-476), stepped + zero_grad'ed at main_train_dimo.py:416-417.
  *   params / grads / exp_avg / exp_avg_sq: flat fp32 buffers of n floats (n % 4 == 0) with identical layout;

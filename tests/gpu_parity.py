@@ -121,7 +121,7 @@ def compare_raster(o, c, verbose=True):
     return ints, flo, gr
 
 
-def run_step_pair(N=1500, M=32, W=64, H=64, device="cuda"):
+def run_step_pair(N=1500, M=32, W=64, H=64, device="cuda", regularisers=False):
     """One full deform -> raster -> loss step (4 frames: 2 motions x 1 view x 2 times) on the CUDA fast path and on the
     oracle, same seeded inputs.  Returns (loss_cuda, loss_oracle, grads_cuda, grads_oracle) for a few parameters."""
     from dimo_b200 import trainstep
@@ -138,7 +138,7 @@ def run_step_pair(N=1500, M=32, W=64, H=64, device="cuda"):
     leaves = {k: v.clone().requires_grad_(True) for k, v in sc.items()}
     op = [(Wt.clone().requires_grad_(True), b.clone().requires_grad_(True)) for Wt, b in params]
     dist, idx = oknn.knn(sc["_c_xyz"], sc["_xyz"], 4)
-    imgs, alphas = [], []
+    imgs, alphas, depths, normals = [], [], [], []
     for (m, v, t) in frames:
         cam = ocamera.orbit_cam(v, 4, W, H)
         dxyz, dquat = odeform.timenet_forward(op, leaves["_c_xyz"], t, leaves["_latent_codes"][m])
@@ -148,13 +148,18 @@ def run_step_pair(N=1500, M=32, W=64, H=64, device="cuda"):
                                 cam.world_view_transform, cam.full_proj_transform, cam.camera_center, cam.tanfovx,
                                 cam.tanfovy, W, H, torch.ones(3), shs=torch.cat([leaves["_features_dc"], leaves["_features_rest"]], 1))
         imgs.append(out["image"].clamp(0, 1)); alphas.append(out["alpha"])
+        depths.append(out["depth"]); normals.append(out["normal"])
     img = torch.stack(imgs); alp = torch.stack(alphas)
+    dep = torch.stack(depths); nrm = torch.stack(normals)
     lo = 0
     for f in range(4):
         lo = lo + lw.lambda_mse * oloss.mse_loss(img[f], gt[f])
     for m in range(2):
         sl = slice(2 * m, 2 * m + 2)
         lo = lo + lw.lambda_ssim * (1 - oloss.ssim(img[sl], gt[sl])) + lw.lambda_mask * oloss.mse_loss(alp[sl], mk[sl])
+        if regularisers:       # main_train_dimo.py:363-372
+            lo = lo + lw.lambda_smooth * oloss.edge_aware_smoothness(dep[sl], img[sl]) + \
+                lw.lambda_bilateral * oloss.bilateral_normal_smoothness(nrm[sl], img[sl])
     lo.backward()
 
     # ---- CUDA fast path (eager TrainStep, no optimizer update) ----
@@ -169,6 +174,11 @@ def run_step_pair(N=1500, M=32, W=64, H=64, device="cuda"):
     ts.g.find_knn(4)
     out = r.render_batch(prepared=prep, stage="s2", clamp=False)
     lc = trainstep.step_loss(out["image_raw"], out["alpha"], gt.to(device), mk.to(device), 2)
+    if regularisers:
+        from dimo_b200 import loss as dloss
+        lc = lc + dloss.smoothness_losses(out["image_raw"], out["depth"], out["normal"], groups=2,
+                                          lambda_smooth=lw.lambda_smooth, lambda_bilateral=lw.lambda_bilateral,
+                                          clamp01=True)
     lc.backward()
     torch.cuda.synchronize()
     gc = {"xyz": r.gaussians._xyz.grad, "opacity": r.gaussians._opacity.grad, "c_xyz": r.gaussians._c_xyz.grad,

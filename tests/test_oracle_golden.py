@@ -117,3 +117,20 @@ def test_ssim_l1_match_reference():
     assert abs(ol.ssim(a.detach(), a.detach()).item() - float(d["ssim_same"])) < 1e-6
     w1 = ol.gaussian_window_1d()
     assert torch.equal(w1[:, None].mm(w1[None, :]), T(d["window"]))
+
+
+def test_smoothness_regularisers_match_reference():
+    """edge-aware depth / bilateral normal smoothness (src/loss.py:64-107): values and gradients"""
+    d = load("smooth.npz")
+    depth = T(d["depth"]).requires_grad_(True); normal = T(d["normal"]).requires_grad_(True)
+    rgb = T(d["rgb"]).requires_grad_(True)
+    ld = ol.edge_aware_smoothness(depth, rgb)
+    ln = ol.bilateral_normal_smoothness(normal, rgb)
+    assert abs(ld.item() - float(d["loss_depth"])) < 1e-6
+    assert abs(ln.item() - float(d["loss_normal"])) < 1e-6
+    gd = torch.autograd.grad(ld, [depth, rgb], retain_graph=True)
+    gn = torch.autograd.grad(ln, [normal, rgb])
+    assert torch.allclose(gd[0], T(d["ddepth"]), rtol=1e-5, atol=1e-9)
+    assert torch.allclose(gd[1], T(d["drgb_depth"]), rtol=1e-5, atol=1e-9)
+    assert torch.allclose(gn[0], T(d["dnormal"]), rtol=1e-5, atol=1e-9)
+    assert torch.allclose(gn[1], T(d["drgb_normal"]), rtol=1e-5, atol=1e-9)

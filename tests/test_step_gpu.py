@@ -93,11 +93,13 @@ def test_trainstep_graph_matches_eager(cuda):
         assert abs(a - b) <= 2e-3 * abs(a), (losses[False], losses[True])
 
 
-def test_full_step_matches_oracle(cuda):
+@pytest.mark.parametrize("regularisers", [False, True])
+def test_full_step_matches_oracle(cuda, regularisers):
     """deform -> raster -> loss for 4 frames: loss and a sample of parameter gradients vs the CPU oracle
-    (autograd through the whole oracle chain)."""
+    (autograd through the whole oracle chain).  regularisers: + the depth / normal smoothness terms of the real step
+    (main_train_dimo.py:363-372), which also exercises the depth / normal gradient path of the rasteriser."""
     import gpu_parity as gp
-    lc, lo, gc, go = gp.run_step_pair()
+    lc, lo, gc, go = gp.run_step_pair(regularisers=regularisers)
     assert abs(lc - lo) <= 1e-4 * abs(lo), (lc, lo)
     for k in gc:
         # ReLU-kink flips (DESIGN.md section 2) can move MLP-side gradients by ~1/sqrt(rows); Gaussian-side ones are tight
