@@ -397,11 +397,11 @@ def algorithmic_bytes(name, wl, S, st):
     R = st.get("R") or 0
     BN = wl["N"] * S
     table = {
-        "dimo_raster_blend_fwd": 68 * R + 40 * P,                 # record gather + index, 10 output planes
+        "dimo_raster_blend_fwd": 68 * R + 40 * P,                 # record gather + instance word, 10 output planes
         # depth/normal carry no gradient in this step: 24 B/px in, 9 gradient fields (RMW) per (tile, splat)
         "dimo_raster_blend_bwd": 68 * R + 24 * P + 2 * 36 * R,
         "dimo_raster_preprocess": 56 * BN + 72 * BN,
-        "dimo_raster_bin": 8 * R + 2 * 16 * R + 4 * R,             # emit, 2 radix passes over (key, value), ranges
+        "dimo_raster_bin": 4 * R + 2 * 8 * R + 4 * R,              # emit packed words, 2 keys-only radix passes, ranges
         "dimo_raster_preprocess_bwd": 64 * BN + 44 * BN + 60 * BN,
         "dimo_ssim_fwd": 8 * 3 * P + 36 * P,
         "dimo_ssim_bwd": 60 * P + 12 * P,

@@ -22,8 +22,9 @@ _SIGS = {
     "dimo_raster_sort_temp_bytes": (c_sz, [c_i64]),
     "dimo_raster_preprocess": (c_int, [c_int] * 6 + [c_f32, c_vp, c_vp] + [c_vp, c_i64] * 6 + [c_vp] * 6 + [c_vp, c_sz, c_vp, c_vp]),
     "dimo_raster_bin": (c_int, [c_int] * 4 + [c_i64] + [c_vp] * 8 + [c_vp, c_sz, c_vp, c_vp, c_vp]),
-    "dimo_raster_blend_fwd": (c_int, [c_int] * 3 + [c_vp] * 11),
-    "dimo_raster_blend_bwd": (c_int, [c_int] * 4 + [c_vp] * 12),
+    "dimo_raster_packed_value_bits": (c_int, [c_int] * 4),
+    "dimo_raster_blend_fwd": (c_int, [c_int] * 5 + [c_vp] * 11),
+    "dimo_raster_blend_bwd": (c_int, [c_int] * 5 + [c_vp] * 12),
     "dimo_raster_preprocess_bwd": (c_int, [c_int] * 6 + [c_f32, c_vp, c_vp] + [c_vp, c_i64] * 4 + [c_vp] * 10),
     "dimo_knn": (c_int, [c_int] * 3 + [c_vp] * 5),
     "dimo_dist3nn": (c_int, [c_int, c_vp, c_vp, c_vp]),

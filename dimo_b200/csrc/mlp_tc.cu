@@ -478,8 +478,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(const __grid_co
 using namespace dimo;
 
 namespace dimo { extern int g_blend_gather_mode; extern int g_blend_bwd_chunk; }   // raster_blend.cu
+namespace dimo { extern int g_disable_packed_instances; }                           // raster_bin.cu
 
 extern "C" int dimo_tc_debug_set(int key, int value) {
+  if (key == 6) {
+    dimo::g_disable_packed_instances = value != 0;
+    return 0;
+  }
   if (key < 0 || key >= 5) return -2;
   if (key == 4) {
     if (value != 64 && value != 128) return -2;

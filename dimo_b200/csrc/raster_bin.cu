@@ -38,20 +38,21 @@ const char* get_error() { return g_err; }
 // read-back of the count) the unused tail carries sentinel keys (>= ntiles) which sort last and are skipped here.
 // Four slots per thread (one 128-bit load + the two neighbouring keys): 16 B in flight per thread instead of 4.
 __global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t R, uint32_t ntiles, const uint32_t* __restrict__ keys,
-                                                          uint2* __restrict__ ranges) {
+                                                          int shift, uint2* __restrict__ ranges) {
   const int64_t j0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (j0 >= R) return;
   constexpr uint32_t NONE = 0xFFFFFFFFu;      // never a valid tile id (ntiles < 2^31)
   uint32_t k[6];
-  k[0] = j0 > 0 ? keys[j0 - 1] : NONE;
+  // `shift` > 0: packed instances, the tile key is the word's upper part
+  k[0] = j0 > 0 ? keys[j0 - 1] >> shift : NONE;
   if (j0 + 4 <= R) {
     const uint4 v = *reinterpret_cast<const uint4*>(keys + j0);
-    k[1] = v.x; k[2] = v.y; k[3] = v.z; k[4] = v.w;
+    k[1] = v.x >> shift; k[2] = v.y >> shift; k[3] = v.z >> shift; k[4] = v.w >> shift;
   } else {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) k[1 + i] = j0 + i < R ? keys[j0 + i] : NONE;
+    for (int i = 0; i < 4; ++i) k[1 + i] = j0 + i < R ? keys[j0 + i] >> shift : NONE;
   }
-  k[5] = j0 + 4 < R ? keys[j0 + 4] : NONE;
+  k[5] = j0 + 4 < R ? keys[j0 + 4] >> shift : NONE;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const uint32_t tile = k[1 + i];
@@ -70,6 +71,8 @@ __global__ void overflow_check_kernel(const uint32_t* __restrict__ offsets, int6
     if ((int64_t)total > slots) flag[1] = 1;
   }
 }
+
+int g_disable_packed_instances = 0;     // dimo_tc_debug_set key 6: force the (key, value) pair format (tests, A/B)
 
 static inline int bits_for(int64_t n) {
   int bits = 1;
@@ -97,7 +100,7 @@ int preprocess_launch(int B, int N, int W, int H, int sh_degree, int sh_coeffs, 
                       const float* colors_precomp, int64_t colors_bstride, float* splats, int32_t* radii,
                       uint32_t* tiles_touched, uint64_t* depth_keys, uint32_t* iota, cudaStream_t st);
 int emit_keys_launch(int B, int N, int W, int H, int64_t R, const float* splats, const int32_t* radii,
-                     const uint32_t* perm, const uint32_t* offsets, uint32_t* tile_keys, uint32_t* vals,
+                     const uint32_t* perm, const uint32_t* offsets, uint32_t* tile_keys, uint32_t* vals, int vbits,
                      cudaStream_t st);
 }  // namespace dimo
 
@@ -123,6 +126,18 @@ size_t dimo_raster_scan_temp_bytes(int64_t BN) {
   cub::DeviceRadixSort::SortPairs(nullptr, sort, (const uint64_t*)nullptr, (uint64_t*)nullptr,
                                   (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)BN, 0, 64);
   return (scan > sort ? scan : sort) + 256;
+}
+
+// Packed instances: when the tile key (bits_for(B*tiles + 1) bits, one spare code for the capacity-mode sentinel)
+// and the index of a Gaussian within its frame (bits_for(N) bits) fit one 32-bit word, instances are single words
+// (key << vbits) | index and the tile sort is a keys-only radix sort over the key bits: half the bytes per pass.
+int dimo_raster_packed_value_bits(int B, int N, int W, int H) {
+  if (dimo::g_disable_packed_instances) return 0;
+  const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+  const int64_t ntiles = (int64_t)B * gx * gy;
+  if (B <= 0 || N <= 0 || ntiles <= 0) return 0;
+  const int vbits = bits_for(N), kbits = bits_for(ntiles + 1);
+  return vbits + kbits <= 32 ? vbits : 0;
 }
 
 size_t dimo_raster_sort_temp_bytes(int64_t R) {
@@ -185,23 +200,33 @@ int dimo_raster_bin(int B, int N, int W, int H, int64_t R, const float* splats, 
   const int64_t BN = (int64_t)B * N;
   DIMO_REQUIRE(R < ((int64_t)1 << 31), "instance count must fit int32");
   DIMO_REQUIRE(ntiles < ((int64_t)1 << 31) - 1, "B*tiles must fit int32");
-  DIMO_REQUIRE(((uintptr_t)keys_sorted & 15) == 0, "keys_sorted must be 16-byte aligned");
+  const int vbits = dimo_raster_packed_value_bits(B, N, W, H);
+  uint32_t* const first_unsorted = vbits > 0 ? vals_unsorted : keys_unsorted;   // buffer that carries the key bits
+  DIMO_REQUIRE(((uintptr_t)(vbits > 0 ? vals_sorted : keys_sorted) & 15) == 0, "sorted instance buffer must be 16-byte aligned");
   DIMO_CHECK_CUDA(cudaMemsetAsync(ranges, 0, sizeof(uint32_t) * 2 * ntiles, st));
   if (R == 0 || BN == 0) return 0;
   if (count_overflow != nullptr) {
     // capacity mode: R is a slot count chosen by the caller; unused slots keep the all-ones sentinel key
-    DIMO_CHECK_CUDA(cudaMemsetAsync(keys_unsorted, 0xFF, sizeof(uint32_t) * (size_t)R, st));
+    DIMO_CHECK_CUDA(cudaMemsetAsync(first_unsorted, 0xFF, sizeof(uint32_t) * (size_t)R, st));
     overflow_check_kernel<<<1, 32, 0, st>>>(offsets, BN, R, count_overflow);
     DIMO_CHECK_LAUNCH();
   }
-  int rc = emit_keys_launch(B, N, W, H, R, splats, radii, perm_sorted, offsets, keys_unsorted, vals_unsorted, st);
+  int rc = emit_keys_launch(B, N, W, H, R, splats, radii, perm_sorted, offsets, keys_unsorted, vals_unsorted, vbits, st);
   if (rc) return rc;
   size_t need = sort_temp_bytes;
   // one spare code above the last tile id so that the sentinel sorts behind every real key
-  DIMO_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(sort_temp, need, keys_unsorted, keys_sorted, vals_unsorted,
-                                                  vals_sorted, (int)R, 0, bits_for(ntiles + 1), st));
-  tile_ranges_kernel<<<ceil_div(R, 1024), 256, 0, st>>>(R, (uint32_t)ntiles, keys_sorted,
-                                                       reinterpret_cast<uint2*>(ranges));
+  const int kbits = bits_for(ntiles + 1);
+  if (vbits > 0) {
+    DIMO_CHECK_CUDA(cub::DeviceRadixSort::SortKeys(sort_temp, need, vals_unsorted, vals_sorted, (int)R, vbits,
+                                                   vbits + kbits, st));
+    tile_ranges_kernel<<<ceil_div(R, 1024), 256, 0, st>>>(R, (uint32_t)ntiles, vals_sorted, vbits,
+                                                         reinterpret_cast<uint2*>(ranges));
+  } else {
+    DIMO_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(sort_temp, need, keys_unsorted, keys_sorted, vals_unsorted,
+                                                    vals_sorted, (int)R, 0, kbits, st));
+    tile_ranges_kernel<<<ceil_div(R, 1024), 256, 0, st>>>(R, (uint32_t)ntiles, keys_sorted, 0,
+                                                         reinterpret_cast<uint2*>(ranges));
+  }
   DIMO_CHECK_LAUNCH();
   return 0;
 }

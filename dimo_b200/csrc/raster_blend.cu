@@ -116,7 +116,8 @@ static_assert(CHUNK == 2 * BLEND_THREADS, "stage_gather assigns two records per 
 
 template <int MODE>
 __global__ void __launch_bounds__(BLEND_THREADS) blend_fwd_kernel(
-    int W, int H, int gx, int tiles_per_frame, const float* __restrict__ cams, const float4* __restrict__ table,
+    int W, int H, int gx, int tiles_per_frame, uint32_t vmask, uint32_t frame_stride,
+    const float* __restrict__ cams, const float4* __restrict__ table,
     const uint32_t* __restrict__ vals_sorted, const uint2* __restrict__ ranges, float* __restrict__ out_color,
     float* __restrict__ out_depth, float* __restrict__ out_normal, float* __restrict__ out_alpha,
     float* __restrict__ final_T, int32_t* __restrict__ n_contrib) {
@@ -135,11 +136,14 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_fwd_kernel(
   const int n = (int)(rng.y - rng.x);
   const int nchunks = (n + CHUNK - 1) / CHUNK;
   const uint32_t* ids = vals_sorted + rng.x;
-  // record indices of list positions c*CHUNK + tid and + 64 (0 when past the end: never dereferenced)
+  // record indices of list positions c*CHUNK + tid and + 64 (0 when past the end: never dereferenced).  An instance
+  // word is the record index itself (vmask = all ones, frame_stride = 0) or, packed, (tile key | index within the
+  // frame): record = (word & vmask) + frame * N.
+  const uint32_t fbase = (uint32_t)b * frame_stride;
   auto load_ids = [&](int c, uint32_t& i0, uint32_t& i1) {
     const int p0 = c * CHUNK + tid;
-    i0 = p0 < n ? ids[p0] : 0u;
-    i1 = p0 + 64 < n ? ids[p0 + 64] : 0u;
+    i0 = p0 < n ? (ids[p0] & vmask) + fbase : 0u;
+    i1 = p0 + 64 < n ? (ids[p0 + 64] & vmask) + fbase : 0u;
   };
 
   if (tid == 0) {
@@ -290,7 +294,8 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 
 template <int MODE, bool DN, int CH>
 __global__ void __launch_bounds__(BLEND_THREADS) blend_bwd_kernel(
-    int W, int H, int gx, int tiles_per_frame, const float* __restrict__ cams, const float4* __restrict__ table,
+    int W, int H, int gx, int tiles_per_frame, uint32_t vmask, uint32_t frame_stride,
+    const float* __restrict__ cams, const float4* __restrict__ table,
     const uint32_t* __restrict__ vals_sorted, const uint2* __restrict__ ranges, const float* __restrict__ final_T,
     const int32_t* __restrict__ n_contrib,
     const float* __restrict__ dL_dcolor, const float* __restrict__ dL_ddepth, const float* __restrict__ dL_dnormal,
@@ -362,10 +367,11 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_bwd_kernel(
   if (nproc == 0) return;
   const int nchunks = (nproc + CH - 1) / CH;
   const uint32_t* ids = vals_sorted + rng.x;
+  const uint32_t fbase = (uint32_t)b * frame_stride;    // instance word -> record index, see blend_fwd_kernel
   auto load_ids = [&](int cc, uint32_t& i0, uint32_t& i1) {
     const int p0 = cc * CH + tid;
-    i0 = p0 < nproc ? ids[p0] : 0u;
-    i1 = (CH > BLEND_THREADS && p0 + 64 < nproc) ? ids[p0 + 64] : 0u;
+    i0 = p0 < nproc ? (ids[p0] & vmask) + fbase : 0u;
+    i1 = (CH > BLEND_THREADS && p0 + 64 < nproc) ? (ids[p0 + 64] & vmask) + fbase : 0u;
   };
 
   // chunk k of the descending walk is list chunk (nchunks-1-k); stage = k&1
@@ -516,22 +522,32 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_bwd_kernel(
 
 using namespace dimo;
 
-extern "C" int dimo_raster_blend_fwd(int B, int W, int H, const float* cams, const float* splats,
+namespace dimo {
+// instance-word decoding parameters for a launch set (see dimo_raster_packed_value_bits, raster_bin.cu)
+static inline void instance_decode(int value_bits, int N, uint32_t& vmask, uint32_t& frame_stride) {
+  vmask = value_bits > 0 ? ((1u << value_bits) - 1u) : 0xFFFFFFFFu;
+  frame_stride = value_bits > 0 ? (uint32_t)N : 0u;
+}
+}  // namespace dimo
+
+extern "C" int dimo_raster_blend_fwd(int B, int N, int W, int H, int value_bits, const float* cams, const float* splats,
                                      const uint32_t* vals_sorted, const uint32_t* ranges, float* out_color,
                                      float* out_depth, float* out_normal, float* out_alpha, float* final_T,
                                      int32_t* n_contrib, void* stream) {
   DIMO_REQUIRE(B >= 0 && W > 0 && H > 0, "bad sizes");
   if (B == 0) return 0;
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+  uint32_t vmask, fstride;
+  instance_decode(value_bits, N, vmask, fstride);
   auto kern = g_blend_gather_mode == 0 ? blend_fwd_kernel<0> : blend_fwd_kernel<1>;
   kern<<<B * gx * gy, BLEND_THREADS, 0, (cudaStream_t)stream>>>(
-      W, H, gx, gx * gy, cams, reinterpret_cast<const float4*>(splats), vals_sorted,
+      W, H, gx, gx * gy, vmask, fstride, cams, reinterpret_cast<const float4*>(splats), vals_sorted,
       reinterpret_cast<const uint2*>(ranges), out_color, out_depth, out_normal, out_alpha, final_T, n_contrib);
   DIMO_CHECK_LAUNCH();
   return 0;
 }
 
-extern "C" int dimo_raster_blend_bwd(int B, int N, int W, int H, const float* cams, const float* splats,
+extern "C" int dimo_raster_blend_bwd(int B, int N, int W, int H, int value_bits, const float* cams, const float* splats,
                                      const uint32_t* vals_sorted, const uint32_t* ranges, const float* final_T,
                                      const int32_t* n_contrib, const float* dL_dcolor, const float* dL_ddepth,
                                      const float* dL_dnormal, const float* dL_dalpha, float* dL_dsplats,
@@ -551,8 +567,10 @@ extern "C" int dimo_raster_blend_bwd(int B, int N, int W, int H, const float* ca
                         : (small ? blend_bwd_kernel<0, false, 64> : blend_bwd_kernel<0, false, 128>))
                   : (dn ? (small ? blend_bwd_kernel<1, true, 64> : blend_bwd_kernel<1, true, 128>)
                         : (small ? blend_bwd_kernel<1, false, 64> : blend_bwd_kernel<1, false, 128>));
+  uint32_t vmask, fstride;
+  instance_decode(value_bits, N, vmask, fstride);
   kern<<<B * gx * gy, BLEND_THREADS, 0, st>>>(
-      W, H, gx, gx * gy, cams, reinterpret_cast<const float4*>(splats), vals_sorted,
+      W, H, gx, gx * gy, vmask, fstride, cams, reinterpret_cast<const float4*>(splats), vals_sorted,
       reinterpret_cast<const uint2*>(ranges), final_T, n_contrib, dL_dcolor, dL_ddepth, dL_dnormal, dL_dalpha,
       dL_dsplats);
   DIMO_CHECK_LAUNCH();

@@ -449,10 +449,13 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
 // index)-sorted order (`perm`), and `offsets` is the inclusive scan of tile counts in that order.  Instances
 // are therefore emitted front-to-back, and a STABLE sort by the tile id alone (raster_bin.cu) yields exactly
 // the order of a full (tile | depth) 64-bit sort -- ties in depth keep ascending Gaussian index.
+// VBITS > 0 ("packed" instances): key and value share ONE 32-bit word, (key << VBITS) | (index within the frame),
+// written to `vals`; the tile sort then moves 4 instead of 8 bytes per instance and pass (raster_bin.cu).
+template <bool PACKED>
 __global__ void __launch_bounds__(256) emit_keys_kernel(
     int64_t BN, int N, int W, int H, const float4* __restrict__ splats, const int32_t* __restrict__ radii,
     const uint32_t* __restrict__ perm, const uint32_t* __restrict__ offsets, int64_t R,
-    uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ vals) {
+    uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ vals, int vbits) {
   // Warp-cooperative: a warp owns 32 consecutive splats of the sorted order and walks their concatenated output
   // slots 32 at a time, so the key/value stores are full 128-byte lines (one thread per splat writing its own
   // run gave 4-byte scattered stores).  The owner of a slot is found by a 5-step shuffle search over the
@@ -473,7 +476,9 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(
       int x0, y0, x1, y1;
       tile_rect(s0.x, s0.y, (float)rad, gx, gy, x0, y0, x1, y1);
       rect = (uint32_t)x0 | ((uint32_t)y0 << 10) | ((uint32_t)(x1 - x0) << 20);   // gx, gy <= 1023 (checked by the host)
-      fbase = (uint32_t)(idx / (uint32_t)N) * (uint32_t)(gx * gy);
+      const uint32_t frame = idx / (uint32_t)N;
+      fbase = frame * (uint32_t)(gx * gy);
+      if (PACKED) idx -= frame * (uint32_t)N;      // index within the frame
     }
   }
   // lanes past the end repeat the last valid inclusive offset (they own no slots)
@@ -503,8 +508,13 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(
       const uint32_t k = o - o_excl;
       const uint32_t w = o_rect >> 20, x0 = o_rect & 1023u, y0 = (o_rect >> 10) & 1023u;
       const uint32_t row = k / w;
-      tile_keys[slot] = o_fb + (y0 + row) * (uint32_t)gx + x0 + (k - row * w);
-      vals[slot] = o_idx;
+      const uint32_t key = o_fb + (y0 + row) * (uint32_t)gx + x0 + (k - row * w);
+      if (PACKED) {
+        vals[slot] = (key << vbits) | o_idx;
+      } else {
+        tile_keys[slot] = key;
+        vals[slot] = o_idx;
+      }
     }
   }
 }
@@ -570,13 +580,17 @@ int preprocess_launch(
 }
 
 int emit_keys_launch(int B, int N, int W, int H, int64_t R, const float* splats, const int32_t* radii,
-                     const uint32_t* perm, const uint32_t* offsets, uint32_t* tile_keys, uint32_t* vals,
+                     const uint32_t* perm, const uint32_t* offsets, uint32_t* tile_keys, uint32_t* vals, int vbits,
                      cudaStream_t st) {
   const int64_t BN = (int64_t)B * N;
   if (BN == 0 || R == 0) return 0;
   DIMO_REQUIRE((W + TILE - 1) / TILE <= 1023 && (H + TILE - 1) / TILE <= 1023, "image larger than 1023 tiles per side");
-  emit_keys_kernel<<<ceil_div(BN, 256), 256, 0, st>>>(BN, N, W, H, reinterpret_cast<const float4*>(splats), radii,
-                                                      perm, offsets, R, tile_keys, vals);
+  if (vbits > 0)
+    emit_keys_kernel<true><<<ceil_div(BN, 256), 256, 0, st>>>(BN, N, W, H, reinterpret_cast<const float4*>(splats),
+                                                              radii, perm, offsets, R, tile_keys, vals, vbits);
+  else
+    emit_keys_kernel<false><<<ceil_div(BN, 256), 256, 0, st>>>(BN, N, W, H, reinterpret_cast<const float4*>(splats),
+                                                               radii, perm, offsets, R, tile_keys, vals, 0);
   DIMO_CHECK_LAUNCH();
   return 0;
 }

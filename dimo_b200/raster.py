@@ -47,7 +47,26 @@ class RasterState:
     __slots__ = ("B", "N", "W", "H", "R", "count_overflow", "cams", "splats", "radii", "tiles_touched", "offsets", "perm",
                  "keys_sorted",
                  "vals_sorted", "ranges", "final_T", "n_contrib", "sh_degree", "sh_coeffs",
-                 "scale_modifier", "frame_src", "n_src")
+                 "scale_modifier", "frame_src", "n_src", "value_bits")
+
+    # The sorted instance list is either (keys_sorted, vals_sorted) = (frame*tiles + tile, index into B*N) or, packed
+    # (value_bits > 0, include/dimo_b200.h dimo_raster_packed_value_bits), single words in vals_sorted.  These two
+    # accessors give the unpacked view in both cases (tests / inspection; the kernels decode on the fly).
+    def tile_keys(self, count=None):
+        w = self.vals_sorted if count is None else self.vals_sorted[:count]
+        if self.value_bits > 0:
+            return (w.long() & 0xFFFFFFFF) >> self.value_bits
+        k = self.keys_sorted if count is None else self.keys_sorted[:count]
+        return k.long() & 0xFFFFFFFF
+
+    def record_ids(self, count=None):
+        w = self.vals_sorted if count is None else self.vals_sorted[:count]
+        w = w.long() & 0xFFFFFFFF
+        if self.value_bits > 0:
+            tiles = ((self.W + TILE - 1) // TILE) * ((self.H + TILE - 1) // TILE)
+            frame = torch.clamp((w >> self.value_bits) // tiles, max=self.B - 1)      # sentinel slots: clamped, unused
+            return (w & ((1 << self.value_bits) - 1)) + frame * self.N
+        return w
 
 
 def _forward_impl(cams, means3D, scales, rotations, opacities, shs, colors_precomp, B, N, W, H, sh_degree,
@@ -101,10 +120,12 @@ def _forward_impl(cams, means3D, scales, rotations, opacities, shs, colors_preco
         st.count_overflow = torch.zeros(2, **i32)
     gx, gy = (W + TILE - 1) // TILE, (H + TILE - 1) // TILE
     Ra = max(R, 1)
-    keys_u = torch.empty(Ra, **i32)
+    st.value_bits = int(L.dimo_raster_packed_value_bits(B, N, W, H))
+    packed = st.value_bits > 0
+    keys_u = None if packed else torch.empty(Ra, **i32)
     vals_u = torch.empty(Ra, **i32)
-    st.keys_sorted = torch.empty(Ra, **i32)          # frame*tiles + tile, sorted (sentinel in unused slots)
-    st.vals_sorted = torch.empty(Ra, **i32)
+    st.keys_sorted = None if packed else torch.empty(Ra, **i32)   # frame*tiles + tile, sorted (sentinel in unused slots)
+    st.vals_sorted = torch.empty(Ra, **i32)          # record indices, or packed (key | index-in-frame) words
     st.ranges = torch.empty(B * gx * gy, 2, **i32)
     sort_bytes = L.dimo_raster_sort_temp_bytes(Ra)
     sort_temp = torch.empty(sort_bytes, dtype=torch.uint8, device=dev)
@@ -119,7 +140,7 @@ def _forward_impl(cams, means3D, scales, rotations, opacities, shs, colors_preco
     alpha = torch.empty(B, 1, H, W, **f32)
     st.final_T = torch.empty(B, H, W, **f32)
     st.n_contrib = torch.empty(B, H, W, **i32)
-    _lib.call("dimo_raster_blend_fwd", B, W, H, _lib.ptr(cams), _lib.ptr(st.splats), _lib.ptr(st.vals_sorted),
+    _lib.call("dimo_raster_blend_fwd", B, N, W, H, st.value_bits, _lib.ptr(cams), _lib.ptr(st.splats), _lib.ptr(st.vals_sorted),
               _lib.ptr(st.ranges),
               _lib.ptr(color), _lib.ptr(depth), _lib.ptr(normal), _lib.ptr(alpha), _lib.ptr(st.final_T),
               _lib.ptr(st.n_contrib), s)
@@ -162,7 +183,7 @@ class _Rasterize(torch.autograd.Function):
         g_alpha = g_alpha.contiguous() if g_alpha is not None else zeros(B, 1, H, W)
         s = _lib.stream()
         dsplats = torch.empty(B * N, SPLAT_FLOATS, **f32)
-        _lib.call("dimo_raster_blend_bwd", B, N, W, H, _lib.ptr(st.cams), _lib.ptr(st.splats),
+        _lib.call("dimo_raster_blend_bwd", B, N, W, H, st.value_bits, _lib.ptr(st.cams), _lib.ptr(st.splats),
                   _lib.ptr(st.vals_sorted), _lib.ptr(st.ranges), _lib.ptr(st.final_T), _lib.ptr(st.n_contrib), _lib.ptr(g_color),
                   _lib.ptr(g_depth), _lib.ptr(g_normal), _lib.ptr(g_alpha), _lib.ptr(dsplats), s)
         d_means3D = torch.empty(B, N, 3, **f32)

@@ -60,6 +60,12 @@ int         dimo_device_info(int* out3_host);
 /* temp bytes for the scan over B*N counters / the radix sort of R (key,value) pairs */
 size_t dimo_raster_scan_temp_bytes(int64_t BN);
 size_t dimo_raster_sort_temp_bytes(int64_t R);
+/* Instance format of a launch set.  Returns value_bits > 0 when a tile key (B*tiles + 1 codes) and the index of a
+ * Gaussian within its frame (N codes) fit one 32-bit word: stage 2 then emits, sorts and returns SINGLE words
+ * (key << value_bits) | index in vals_sorted (keys_unsorted / keys_sorted are not touched and may be NULL) and the
+ * tile sort is keys-only -- half the bytes of a (key, value) pair sort.  0: separate 32-bit keys and B*N indices.
+ * Pass the same value to dimo_raster_blend_fwd / _bwd, which decode  record = (word & mask) + frame * N. */
+int dimo_raster_packed_value_bits(int B, int N, int W, int H);
 
 /* Stage 1: per-Gaussian projection + tile counting, depth sort of the B*N splats, inclusive scan of the tile
  * counts in (frame, depth, index) order.
@@ -106,7 +112,7 @@ int dimo_raster_bin(
  *   out_color [B,3,H,W], out_depth [B,1,H,W], out_normal [B,3,H,W], out_alpha [B,1,H,W],
  *   final_T [B,H,W] f32, n_contrib [B,H,W] i32. */
 int dimo_raster_blend_fwd(
-    int B, int W, int H, const float* cams, const float* splats, const uint32_t* vals_sorted,
+    int B, int N, int W, int H, int value_bits, const float* cams, const float* splats, const uint32_t* vals_sorted,
     const uint32_t* ranges, float* out_color, float* out_depth, float* out_normal, float* out_alpha,
     float* final_T, int32_t* n_contrib, void* stream);
 
@@ -114,7 +120,7 @@ int dimo_raster_blend_fwd(
  * dL_ddepth and dL_dnormal may BOTH be NULL (no loss term reads depth / normal, e.g. the MSE + SSIM + mask step):
  * the four channels are then compiled out of the pixel loop and of the warp reduction. */
 int dimo_raster_blend_bwd(
-    int B, int N, int W, int H, const float* cams, const float* splats, const uint32_t* vals_sorted,
+    int B, int N, int W, int H, int value_bits, const float* cams, const float* splats, const uint32_t* vals_sorted,
     const uint32_t* ranges, const float* final_T, const int32_t* n_contrib,
     const float* dL_dcolor, const float* dL_ddepth, const float* dL_dnormal, const float* dL_dalpha,
     float* dL_dsplats, void* stream);
@@ -177,8 +183,8 @@ int dimo_linear_wgrad_tc_grouped(int n, int R, const int* K, const int* No, cons
                                  const float* const* X, const int64_t* ldx, float* const* dW, float* const* db,
                                  void* stream);
 /* bring-up knobs (0: swap LBO/SBO, 1: single-pass TF32, 2: wgrad CTA target, 3: blend gather via 16-byte
- * cp.async instead of 64-byte bulk copies, 4: records per stage of the blend backward, 64 or 128); not part of the
- * stable ABI */
+ * cp.async instead of 64-byte bulk copies, 4: records per stage of the blend backward, 64 or 128, 6: 1 = never pack
+ * instances into single words); not part of the stable ABI */
 int dimo_tc_debug_set(int key, int value);
 
 /* TimeNet input embedding h0[R,104] = [posenc(x,10) | posenc(t,6) | latent]  (pos_enc.py:35-36,

@@ -87,11 +87,11 @@ def run_raster_pair(N, W, H, view=1, nviews=8, sh_degree=0, seed=0, scale_boost=
     st = state[0]
     # the library sorts 32-bit tile ids (emitted front-to-back); rebuild the reference-shaped 64-bit
     # (tile << 32 | depth bits) keys from the sorted tile ids and the sorted splats' depths for comparison
-    vals = st.vals_sorted[:st.R].long()
+    vals = st.record_ids(st.R)
     dbits = st.splats[vals, 10].contiguous().view(torch.int32).long() & 0xFFFFFFFF
-    keys64 = (st.keys_sorted[:st.R].long() << 32) | dbits
+    keys64 = (st.tile_keys(st.R) << 32) | dbits
     c = dict(image=color[0], depth=depth[0], normal=normal[0], alpha=alpha[0], radii=radii[0],
-             tiles_touched=st.tiles_touched, keys=keys64, ids=st.vals_sorted[:st.R],
+             tiles_touched=st.tiles_touched, keys=keys64, ids=vals,
              ranges=st.ranges, n_contrib=st.n_contrib[0], final_T=st.final_T[0], R=st.R,
              grads=dict(means3D=cl[0].grad, scales=cl[1].grad, rotations=cl[2].grad, opacities=cl[3].grad,
                         shs=cl[4].grad, means2D=cm2d.grad))

@@ -25,6 +25,27 @@ def test_raster_matches_oracle(cuda, N, W, H, deg, boost, use_dn):
         assert v < gp.GRAD_TOL, f"grad {k}: rel err {v:.3e}"
 
 
+def test_unpacked_instance_format(cuda):
+    """The instance list has two formats (include/dimo_b200.h, dimo_raster_packed_value_bits): single packed words
+    when tile key and in-frame index fit 32 bits -- every other test here -- and (key, value) pairs otherwise
+    (e.g. 500k Gaussians at 800x800 x 16 frames).  Force the pair format and check it against the oracle too."""
+    import gpu_parity as gp
+    from dimo_b200 import _lib
+    assert _lib.lib().dimo_raster_packed_value_bits(16, 100000, 512, 512) == 17      # the bench shape packs exactly
+    assert _lib.lib().dimo_raster_packed_value_bits(16, 500000, 800, 800) == 0
+    _lib.call("dimo_tc_debug_set", 6, 1)
+    try:
+        o, c = gp.run_raster_pair(3000, 128, 96, scale_boost=0.5)
+        ints, flo, gr = gp.compare_raster(o, c)
+    finally:
+        _lib.call("dimo_tc_debug_set", 6, 0)
+    assert all(v == 0 for v in ints.values()), f"integer outputs differ: {ints}"
+    for k in ("image", "depth", "normal", "alpha", "final_T"):
+        assert flo[k] < gp.PIX_TOL
+    for k, v in gr.items():
+        assert v < gp.GRAD_TOL
+
+
 def test_empty_scene(cuda):
     """all Gaussians behind the camera: image == background, no instances"""
     import math
@@ -142,7 +163,7 @@ def test_raster_properties_full_size(cuda):
     s = st[0]
     R = s.R
     assert R == int(s.offsets[-1]) and R == int(s.tiles_touched.sum())
-    keys = s.keys_sorted[:R].long()                    # frame*tiles + tile
+    keys = s.tile_keys(R)                              # frame*tiles + tile
     assert bool((keys[1:] >= keys[:-1]).all()), "tile keys not sorted"
     perm = s.perm.long()
     assert torch.equal(torch.sort(perm).values, torch.arange(2 * N, device="cuda")), "perm is not a permutation"
@@ -153,7 +174,7 @@ def test_raster_properties_full_size(cuda):
     tile_of_key = keys
     counts = torch.bincount(tile_of_key, minlength=rng.shape[0])
     assert torch.equal(counts, (rng[:, 1] - rng[:, 0]))
-    vals = s.vals_sorted[:R].long()
+    vals = s.record_ids(R)
     depth_rec = s.splats[vals, 10]                     # blend record: depth
     same_tile = tile_of_key[1:] == tile_of_key[:-1]
     assert bool((depth_rec[1:][same_tile] >= depth_rec[:-1][same_tile]).all()), "tile lists not depth sorted"

@@ -33,8 +33,9 @@ def test_capacity_mode_equals_exact(cuda):
         assert torch.equal(a, b)
     assert stc[0].count_overflow.tolist() == [R, 0]
     assert torch.equal(stc[0].ranges, st[0].ranges)
-    assert torch.equal(stc[0].keys_sorted[:R], st[0].keys_sorted[:R])
-    assert bool((stc[0].keys_sorted[R:].long() & 0xFFFFFFFF >= cams.shape[0] * 6 * 5).all()), "tail must hold sentinels"
+    assert torch.equal(stc[0].tile_keys()[:R], st[0].tile_keys()[:R])
+    assert torch.equal(stc[0].record_ids()[:R], st[0].record_ids()[:R])
+    assert bool((stc[0].tile_keys()[R:] >= cams.shape[0] * 6 * 5).all()), "tail must hold sentinels"
     # backward through the capped path
     leaves = [t.clone().requires_grad_(True) for t in (xyz, scales, rot, op, shs)]
     o1 = draster.rasterize_batch(cams, *leaves[:4], W, H, shs=leaves[4])
