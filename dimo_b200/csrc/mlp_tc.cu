@@ -27,7 +27,7 @@ constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // 64 KB
 constexpr int TC_SMEM_BYTES = 2 * TC_STAGE_BYTES + 1024;          // + alignment slack
 
 // debug knobs (dimo_tc_debug_set): 0 = swap LBO/SBO in the shared-memory descriptors, 1 = single-pass TF32 (no compensation)
-static int h_tc_knob[4] = {0, 0, 0, 0};
+static int h_tc_knob[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // [7]: ablation mask for timing experiments
 
 struct TcArgs {
   int R, K, No;
@@ -38,6 +38,7 @@ struct TcArgs {
   float* Y; int64_t ldy;
   int relu, accumulate;
   int swap_lbo_sbo, single_pass;
+  int ablate;      // timing experiments only (tools/linear_tc_bench.py): 1 = no global loads, 2 = no shared stores, 4 = no MMAs
 };
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -201,18 +202,26 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) linear_tc_kernel(TcArgs p) {
     }
   };
 
-  fetch(0);
+  if (!(p.ablate & 1)) fetch(0);
+  else {
+#pragma unroll
+    for (int it = 0; it < LIN_NA; ++it) va[it] = make_float4(1.f, 2.f, 3.f, 4.f);
+#pragma unroll
+    for (int it = 0; it < LIN_NB; ++it) vb[it] = make_float4(1.f, 2.f, 3.f, 4.f);
+  }
   for (int kt = 0; kt < nk; ++kt) {
     const int s = kt & 1;
     uint8_t* stage = smem + s * LIN_STAGE_BYTES;
     uint8_t* a_hi = stage, *a_lo = stage + LIN_A_BYTES, *b_hi = stage + 2 * LIN_A_BYTES,
              *b_lo = stage + 2 * LIN_A_BYTES + LIN_B_BYTES;
     if (kt >= 2) tc_mbar_wait(&mma_bar[s], (uint32_t)(((kt >> 1) - 1) & 1));   // MMAs of tile kt-2 have read this stage
+    if (!(p.ablate & 2)) {
 #pragma unroll
-    for (int it = 0; it < LIN_NA; ++it) split_store(a_hi, a_lo, canon_off_n(a_row[it], a_chunk[it], LIN_BK / 4), va[it]);
+      for (int it = 0; it < LIN_NA; ++it) split_store(a_hi, a_lo, canon_off_n(a_row[it], a_chunk[it], LIN_BK / 4), va[it]);
 #pragma unroll
-    for (int it = 0; it < LIN_NB; ++it) split_store(b_hi, b_lo, canon_off_n(b_row[it], b_chunk[it], LIN_BK / 4), vb[it]);
-    if (kt + 1 < nk) fetch(kt + 1);          // in flight during the barrier, the MMA issue and the next wait
+      for (int it = 0; it < LIN_NB; ++it) split_store(b_hi, b_lo, canon_off_n(b_row[it], b_chunk[it], LIN_BK / 4), vb[it]);
+    }
+    if (kt + 1 < nk && !(p.ablate & 1)) fetch(kt + 1);          // in flight during the barrier, the MMA issue and the next wait
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async-proxy (MMA) reads
     __syncthreads();
     if (tid == 0) {
@@ -224,6 +233,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) linear_tc_kernel(TcArgs p) {
         const uint32_t koff = (uint32_t)ks * 256u;     // 8 tf32 = two 16-byte chunks = two 128-byte core-matrix blocks
         const uint64_t dah = make_smem_desc(sa_hi + koff, lbo, sbo), dal = make_smem_desc(sa_lo + koff, lbo, sbo);
         const uint64_t dbh = make_smem_desc(sb_hi + koff, lbo, sbo), dbl = make_smem_desc(sb_lo + koff, lbo, sbo);
+        if (p.ablate & 4) continue;
         tc_mma(tmem_d, dah, dbh, idesc, (kt > 0 || ks > 0) ? 1u : 0u);
         if (!p.single_pass) {
           tc_mma(tmem_d, dah, dbl, idesc, 1u);
@@ -485,6 +495,10 @@ extern "C" int dimo_tc_debug_set(int key, int value) {
     dimo::g_disable_packed_instances = value != 0;
     return 0;
   }
+  if (key == 7) {
+    h_tc_knob[7] = value;
+    return 0;
+  }
   if (key < 0 || key >= 5) return -2;
   if (key == 4) {
     if (value != 64 && value != 128) return -2;
@@ -513,7 +527,7 @@ extern "C" int dimo_linear_tc(int R, int K, int No, const float* X, int64_t ldx,
   TcArgs p{};
   p.R = R; p.K = K; p.No = No; p.X = X; p.ldx = ldx; p.mask = mask; p.ldm = ldm; p.Wt = Wt; p.bias = bias;
   p.Y = Y; p.ldy = ldy; p.relu = relu; p.accumulate = accumulate;
-  p.swap_lbo_sbo = h_tc_knob[0]; p.single_pass = h_tc_knob[1];
+  p.swap_lbo_sbo = h_tc_knob[0]; p.single_pass = h_tc_knob[1]; p.ablate = h_tc_knob[7];
   dim3 grid(ceil_div(R, TC_BM), ceil_div(No, LIN_BN));
   linear_tc_kernel<<<grid, LIN_THREADS, LIN_SMEM_BYTES, (cudaStream_t)stream>>>(p);
   DIMO_CHECK_LAUNCH();

@@ -42,6 +42,11 @@ def main():
             for K in (64, 128, 256, 512, 1024):
                 print(f"single_pass={single} R={R} K={K} No=256: {bench(R, K, 256):.2f} us per launch")
     _lib.call("dimo_tc_debug_set", 1, 0)
+    # ablations (results are garbage, only the time matters): 1 = no global loads, 2 = no shared stores, 4 = no MMAs
+    for ab in (1, 2, 4, 3, 5, 6, 7):
+        _lib.call("dimo_tc_debug_set", 7, ab)
+        print(f"ablate={ab} R=4096 No=256: K=256 {bench(4096, 256, 256):.2f} us, K=1024 {bench(4096, 1024, 256):.2f} us per launch")
+    _lib.call("dimo_tc_debug_set", 7, 0)
     # an empty-ish reference: the same chain with a trivially small problem
     print(f"R=128 K=64 No=64: {bench(128, 64, 64):.2f} us per launch")
 
