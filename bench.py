@@ -41,8 +41,11 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-mode", default="prefetch", choices=["prefetch", "inline"],
                     help="prefetch: next step's ground truth on a copy stream; inline: copy on the compute stream")
-    ap.add_argument("--e2e-read", default="item", choices=["item", "async"],
-                    help="item: loss.item() every step (host sync); async: non_blocking D2H into pinned memory, one sync at the end")
+    ap.add_argument("--e2e-read", default="lagged", choices=["item", "lagged", "async"],
+                    help="how the host reads every step's loss.  item: loss.item() (the host blocks on the step it just "
+                         "enqueued); lagged: non-blocking D2H into pinned memory + the host waits for and reads the "
+                         "PREVIOUS step's value while the current step runs (what a training loop that logs the loss "
+                         "does); async: non-blocking D2H, one sync at the end")
     ap.add_argument("--cpu-frames", type=int, default=1, help="frames in the bounded CPU sample")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the whole-step CUDA graph")
     ap.add_argument("--regularisers", action="store_true",
@@ -224,6 +227,7 @@ def run_ours(args, wl):
     mk_buf = [torch.empty(S, 1, H, W, device=dev) for _ in range(2)]
     ready_ev, free_ev, staged = [None, None], [None, None], {}
     loss_host = torch.zeros(max(args.steps + args.warmup + 2, 8)).pin_memory()
+    loss_events = {}
 
     def stage(i):
         slot = i % 2
@@ -261,7 +265,16 @@ def run_ours(args, wl):
                 stage(i + 1)
             if args.e2e_read == "item":
                 return loss.item()      # device -> host read of the step's result, host waits for it
-            loss_host[i % loss_host.numel()].copy_(loss.detach(), non_blocking=True)
+            slot_l = i % loss_host.numel()
+            loss_host[slot_l].copy_(loss.detach(), non_blocking=True)
+            if args.e2e_read == "lagged":
+                ev = torch.cuda.Event()
+                ev.record()
+                prev = loss_events.pop(i - 1, None)
+                loss_events[i] = (ev, slot_l)
+                if prev is not None:    # the previous step's loss has landed (or we wait for it) -> host value
+                    prev[0].synchronize()
+                    return float(loss_host[prev[1]])
             return None
         return ts.run(cams, times, lat, gt_dev[i % pool], mk_dev[i % pool], wl["bm"])
 
@@ -280,6 +293,11 @@ def run_ours(args, wl):
         e0.record()
         for i in range(warmup, warmup + steps):
             one_step(i, e2e)
+        if e2e and loss_events:          # lagged reads: the last step's loss is read before the clock stops
+            for ev, slot_l in loss_events.values():
+                ev.synchronize()
+                float(loss_host[slot_l])
+            loss_events.clear()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)

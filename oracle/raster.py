@@ -109,9 +109,12 @@ def preprocess(means3D, scales, rotations, opacities, view, proj, campos, tanfov
     tytz = tvy / tvz
     tx = torch.clamp(txtz, -limx, limx) * tvz
     ty = torch.clamp(tytz, -limy, limy) * tvz
-    J00 = fx / tvz
+    # NB: `python_scalar / tensor` is evaluated by torch as tensor.reciprocal() * scalar (two roundings); the kernel
+    # performs ONE IEEE division, so the numerator is materialised as a tensor first.  (Found by the 1024x1024 test:
+    # 1 radius in 30 000 differed by one pixel through the cancellation in mid^2 - det.)
+    J00 = torch.full_like(tvz, fx) / tvz
     J02 = -(fx * tx) / (tvz * tvz)
-    J11 = fy / tvz
+    J11 = torch.full_like(tvz, fy) / tvz
     J12 = -(fy * ty) / (tvz * tvz)
     M0 = [J00 * V[k, 0] + J02 * V[k, 2] for k in range(3)]
     M1 = [J11 * V[k, 1] + J12 * V[k, 2] for k in range(3)]

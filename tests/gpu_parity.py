@@ -52,7 +52,7 @@ def weighted_loss(img, depth, normal, alpha, w, use_dn=True):
 
 
 def run_raster_pair(N, W, H, view=1, nviews=8, sh_degree=0, seed=0, scale_boost=0.0, bg=(1.0, 1.0, 1.0),
-                    device="cuda", use_dn=True):
+                    device="cuda", use_dn=True, backward=True):
     """Runs the oracle (CPU fp32 + autograd) and the CUDA path on identical inputs; returns both result dicts."""
     K = (sh_degree + 1) ** 2
     xyz, scales, rot, op, shs = scene_inputs(N, seed, K, scale_boost)
@@ -66,9 +66,11 @@ def run_raster_pair(N, W, H, view=1, nviews=8, sh_degree=0, seed=0, scale_boost=
     o = oraster.rasterize(leaves[0], leaves[1], leaves[2], leaves[3], ocam.world_view_transform,
                           ocam.full_proj_transform, ocam.camera_center, ocam.tanfovx, ocam.tanfovy, W, H, bg_t,
                           shs=leaves[4], sh_degree=sh_degree, means2D=m2d)
-    weighted_loss(o["image"], o["depth"], o["normal"], o["alpha"], w, use_dn).backward()
-    o["grads"] = dict(means3D=leaves[0].grad, scales=leaves[1].grad, rotations=leaves[2].grad,
-                      opacities=leaves[3].grad, shs=leaves[4].grad, means2D=m2d.grad)
+    o["grads"] = {}
+    if backward:
+        weighted_loss(o["image"], o["depth"], o["normal"], o["alpha"], w, use_dn).backward()
+        o["grads"] = dict(means3D=leaves[0].grad, scales=leaves[1].grad, rotations=leaves[2].grad,
+                          opacities=leaves[3].grad, shs=leaves[4].grad, means2D=m2d.grad)
 
     # ---- CUDA ----
     cam = orbit_minicam(view, nviews, W, H, device=device)
@@ -82,7 +84,8 @@ def run_raster_pair(N, W, H, view=1, nviews=8, sh_degree=0, seed=0, scale_boost=
     color, depth, normal, alpha, radii = draster.rasterize_batch(
         cams, cl[0], cl[1], cl[2], cl[3], W, H, shs=cl[4], sh_degree=sh_degree, means2D=cm2d, state_out=state)
     wd = {k: v.to(device) for k, v in w.items()}
-    weighted_loss(color[0], depth[0], normal[0], alpha[0], wd, use_dn).backward()
+    if backward:
+        weighted_loss(color[0], depth[0], normal[0], alpha[0], wd, use_dn).backward()
     torch.cuda.synchronize()
     st = state[0]
     # the library sorts 32-bit tile ids (emitted front-to-back); rebuild the reference-shaped 64-bit
@@ -94,7 +97,7 @@ def run_raster_pair(N, W, H, view=1, nviews=8, sh_degree=0, seed=0, scale_boost=
              tiles_touched=st.tiles_touched, keys=keys64, ids=vals,
              ranges=st.ranges, n_contrib=st.n_contrib[0], final_T=st.final_T[0], R=st.R,
              grads=dict(means3D=cl[0].grad, scales=cl[1].grad, rotations=cl[2].grad, opacities=cl[3].grad,
-                        shs=cl[4].grad, means2D=cm2d.grad))
+                        shs=cl[4].grad, means2D=cm2d.grad) if backward else {})
     return o, c
 
 

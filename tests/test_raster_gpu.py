@@ -142,6 +142,69 @@ def test_raster_full_size_c2_shape(cuda):
         assert v < 10 * gp.GRAD_TOL, f"grad {k}: rel err {v:.3e}"
 
 
+def test_raster_c4_inference_shape(cuda):
+    """BASELINE config-4 shape (4-D inference): 30k Gaussians rendered at 1024x1024, forward only, vs the oracle.
+    Same acceptance as the c2 test: integers bit-exact, pixels within 1e-4 except threshold flips."""
+    import gpu_parity as gp
+    o, c = gp.run_raster_pair(30000, 1024, 1024, view=17, nviews=120, backward=False)
+    ints, flo, _ = gp.compare_raster(o, c)
+    assert all(v == 0 for v in ints.values()), f"integer outputs differ: {ints}"
+    for k in ("image", "depth", "normal", "alpha"):
+        frac = gp.outlier_frac(c[k], o[k], gp.PIX_TOL)
+        assert frac <= 1e-4, f"{k}: {frac:.2e} of pixels outside 1e-4"
+        assert flo[k] <= 1.0 / 255.0 + 1e-4, f"{k}: max deviation {flo[k]:.3e}"
+    assert flo["n_contrib_mismatch_frac"] < 1e-3
+
+
+def test_raster_c5_stress_shape_properties(cuda):
+    """BASELINE config-5 shape: 500k Gaussians at 800x800 (50x50 tiles), 2 frames, forward + backward.  No oracle at
+    this size; size-independent properties instead: instance count = sum of tile counts, tile keys sorted, ranges
+    partition the list, per-tile depth order, alpha = 1 - final_T, determinism, finite gradients of the right shape,
+    and agreement between the packed and the (key, value) instance formats."""
+    import math
+    import gpu_parity as gp
+    from dimo_b200 import _lib, raster as draster
+    from dimo_b200.camera import orbit_minicam
+    N, W, H = 500000, 800, 800
+    xyz, scales, rot, op, shs = [t.cuda() for t in gp.scene_inputs(N)]
+    cams = []
+    for v in (1, 6):
+        cam = orbit_minicam(v, 8, W, H)
+        cams.append(draster.pack_cameras(cam.world_view_transform, cam.full_proj_transform, cam.camera_center,
+                                         math.tan(cam.FoVx / 2), math.tan(cam.FoVy / 2), torch.ones(3, device="cuda")))
+    cams = torch.cat(cams)
+    outs = {}
+    for fmt in ("packed", "pairs"):
+        _lib.call("dimo_tc_debug_set", 6, 0 if fmt == "packed" else 1)
+        try:
+            st = []
+            leaves = [t.clone().requires_grad_(True) for t in (xyz, scales, rot, op, shs)]
+            color, depth, normal, alpha, radii = draster.rasterize_batch(cams, *leaves[:4], W, H, shs=leaves[4], state_out=st)
+            (color.square().sum() + alpha.sum()).backward()
+        finally:
+            _lib.call("dimo_tc_debug_set", 6, 0)
+        s = st[0]
+        R = s.R
+        assert (s.value_bits > 0) == (fmt == "packed")
+        assert R == int(s.tiles_touched.long().sum())
+        keys = s.tile_keys(R)
+        assert bool((keys[1:] >= keys[:-1]).all()), "tile keys not sorted"
+        rng = s.ranges.long()
+        assert torch.equal(torch.bincount(keys, minlength=rng.shape[0]), rng[:, 1] - rng[:, 0])
+        ids = s.record_ids(R)
+        d = s.splats[ids, 10]
+        same = keys[1:] == keys[:-1]
+        assert bool((d[1:][same] >= d[:-1][same]).all()), "tile lists not depth sorted"
+        assert torch.allclose(alpha[:, 0], 1 - s.final_T, atol=1e-6)
+        for l, ref in zip(leaves, (xyz, scales, rot, op, shs)):
+            assert l.grad.shape == ref.shape and bool(torch.isfinite(l.grad).all())
+        outs[fmt] = (color.detach(), [l.grad.clone() for l in leaves], keys, ids)
+    assert torch.equal(outs["packed"][0], outs["pairs"][0]), "the two instance formats render different images"
+    assert torch.equal(outs["packed"][2], outs["pairs"][2]) and torch.equal(outs["packed"][3], outs["pairs"][3])
+    for a, b in zip(outs["packed"][1], outs["pairs"][1]):
+        assert gp.rel_err(a, b) < 1e-5          # atomics: summation order differs between runs
+
+
 def test_raster_properties_full_size(cuda):
     """size-independent properties at the bench size (100k Gaussians, 512x512, B=2), no oracle needed:
     ranges partition [0,R) in tile order, keys sorted, each tile's records depth-sorted, alpha = 1 - final_T,
