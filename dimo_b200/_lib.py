@@ -6,7 +6,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdimo_b200.so")
+# DIMO_LIB: load another build of the same ABI (instrumented / experimental builds during bring-up)
+LIB_PATH = os.environ.get("DIMO_LIB") or os.path.join(_HERE, "lib", "libdimo_b200.so")
 
 _lib = None
 
