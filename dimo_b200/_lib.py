@@ -29,6 +29,10 @@ _SIGS = {
     "dimo_raster_preprocess_bwd": (c_int, [c_int] * 6 + [c_f32, c_vp, c_vp] + [c_vp, c_i64] * 4 + [c_vp] * 10),
     "dimo_knn": (c_int, [c_int] * 3 + [c_vp] * 5),
     "dimo_dist3nn": (c_int, [c_int, c_vp, c_vp, c_vp]),
+    "dimo_fps": (c_int, [c_int] * 4 + [c_vp] * 4),
+    "dimo_ball_query": (c_int, [c_int] * 4 + [c_f32] + [c_vp] * 5),
+    "dimo_chamfer_fwd": (c_int, [c_int] * 2 + [c_vp] * 6 + [c_f32, c_vp]),
+    "dimo_chamfer_bwd": (c_int, [c_int] + [c_vp] * 4 + [c_f32] + [c_vp] * 3),
     "dimo_linear_fwd": (c_int, [c_int] * 3 + [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_int, c_vp]),
     "dimo_linear_bwd_data": (c_int, [c_int] * 3 + [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_vp]),
     "dimo_linear_bwd_weight": (c_int, [c_int] * 3 + [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
@@ -101,7 +105,8 @@ def stream():
 # hand-written kernels launched per C-ABI call (CUB scan/sort launches are listed separately)
 _OWN_LAUNCHES = {
     "dimo_raster_preprocess": 2, "dimo_raster_bin": 2, "dimo_raster_blend_fwd": 1, "dimo_raster_blend_bwd": 1,
-    "dimo_raster_preprocess_bwd": 1, "dimo_knn": 1, "dimo_dist3nn": 1, "dimo_linear_fwd": 1,
+    "dimo_raster_preprocess_bwd": 1, "dimo_knn": 1, "dimo_dist3nn": 1,
+    "dimo_fps": 1, "dimo_ball_query": 1, "dimo_chamfer_fwd": 1, "dimo_chamfer_bwd": 1, "dimo_linear_fwd": 1,
     "dimo_linear_bwd_data": 1, "dimo_linear_tc": 1, "dimo_linear_wgrad_tc": 1, "dimo_linear_wgrad_tc_grouped": 1, "dimo_linear_bwd_weight": 1, "dimo_timenet_embed_fwd": 1,
     "dimo_timenet_embed_bwd": 1, "dimo_lbs_fwd": 1, "dimo_lbs_bwd": 1, "dimo_ssim_fwd": 1, "dimo_ssim_bwd": 1,
     "dimo_sqdiff_sum": 1, "dimo_smooth_fwd": 1, "dimo_smooth_bwd": 1, "dimo_segment_sum": 1, "dimo_adam_step": 1, "dimo_transpose_grouped": 1,

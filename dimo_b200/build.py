@@ -27,6 +27,7 @@ SOURCES = {
     "raster_bin.cu": [],
     "raster_blend.cu": [],
     "knn.cu": ["-fmad=false"],
+    "points.cu": ["-fmad=false"],
     "deform.cu": [],
     "mlp.cu": [],
     "mlp_tc.cu": [],

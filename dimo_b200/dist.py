@@ -67,6 +67,13 @@ class FlatGradReducer:
         for p in self.early:
             self._hooks.append(p.register_post_accumulate_grad_hook(self._on_early_grad))
 
+    def detach(self):
+        """Removes the post-accumulate hooks (call before the parameter set is re-laid out, e.g. after densify / prune:
+        gaussian_model.GaussianModel._rebind builds a new reducer over the new tensors)."""
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
     def layout(self):
         return list(self.offsets), self.n
 

@@ -54,6 +54,9 @@ class FusedAdam:
             groups.append(gi)
         begins.append(n)
         self._seg_group = groups
+        # segments hold their group DICT: the reference pops groups from `param_groups` (main_train_dimo.py:489-493,
+        # the shared-radius group "r" at the start of stage s2), which must not shift the other segments' rates
+        self._seg_dict = [self.param_groups[g] for g in groups]
         self._seg_begin = (ctypes.c_int64 * len(begins))(*begins)
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
@@ -70,7 +73,7 @@ class FusedAdam:
     # ------------------------------------------------------------------------------------------
     def sync_lrs(self):
         """Uploads the groups' learning rates if they changed (call outside a graph capture / before a replay)."""
-        cur = tuple(self.param_groups[g]["lr"] for g in self._seg_group)
+        cur = tuple(float(d["lr"]) for d in self._seg_dict)
         if cur != self._lr_sent:
             k = self._lr_slot
             self._lr_slot = (k + 1) % len(self._lr_ring)
@@ -92,6 +95,26 @@ class FusedAdam:
                   _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), len(self._seg_group), self._seg_begin,
                   _lib.ptr(self._lr_dev), self.betas[0], self.betas[1], self.eps, int(self.fold_zero_grad),
                   _lib.ptr(self.state), _lib.stream())
+
+    # -- moment access for the surgery in gaussian_model.GaussianModel (densify / prune / reset_opacity) --------
+    def _span(self, p):
+        for q, (off, numel) in zip(self.reducer.params, self.reducer.offsets):
+            if q is p:
+                return off, numel
+        raise KeyError("parameter is not part of this optimizer's flat buffer")
+
+    def moments(self, p):
+        """(exp_avg, exp_avg_sq) views shaped like `p`."""
+        off, numel = self._span(p)
+        return self.exp_avg[off:off + numel].view_as(p), self.exp_avg_sq[off:off + numel].view_as(p)
+
+    def load_moments(self, by_id):
+        """by_id: {id(param): (exp_avg, exp_avg_sq)}; parameters that are not listed keep zero moments."""
+        for q, (off, numel) in zip(self.reducer.params, self.reducer.offsets):
+            mv = by_id.get(id(q))
+            if mv is not None:
+                self.exp_avg[off:off + numel].copy_(mv[0].reshape(-1))
+                self.exp_avg_sq[off:off + numel].copy_(mv[1].reshape(-1))
 
     def zero_grad(self, set_to_none=False):
         """No kernel when the clear is folded into step(); the reducer's bookkeeping is reset either way."""

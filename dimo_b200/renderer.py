@@ -1,16 +1,15 @@
-"""Host-side mirror of the reference renderer classes for the hot path
-(renderer/latent_gs_renderer.py: GaussianModel :248-415 [parameters + activations only], Renderer.render
-:1096-1293) on top of the libdimo_b200 kernels.
+"""Host-side mirror of the reference `Renderer` (renderer/latent_gs_renderer.py:973-1293; `GaussianModel` lives in
+gaussian_model.py) on top of the libdimo_b200 kernels.
 
 `Renderer.render(...)` keeps the reference signature and result dict (one frame per call);
 `Renderer.render_batch(...)` is the B200 fast path: all S frames of an optimisation step in ONE launch
 set -- TimeNet once per unique (motion, t) pair (its output is view-independent), LBS once per pair,
-rasterisation batched over all frames.
-
-Out of scope here: densify/prune, PLY/.pth I/O, optimizer surgery.
+rasterisation batched over all frames.  `initialize` / `initialize_ag` / `arap_loss_v2` / `reparameterize` complete
+the class surface main_train_dimo.py and main_test_dimo.py use.
 """
 import math
 
+import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -18,121 +17,88 @@ import torch.nn.functional as F
 from . import deform as _deform
 from . import knn as _knn
 from . import raster as _raster
+from . import regularisers as _reg
 from .camera import MiniCam  # noqa: F401  (re-export: the reference imports MiniCam from the renderer module)
-
-C0 = 0.28209479177387814
-
-
-def inverse_sigmoid(x):
-    return torch.log(x / (1 - x))
+from .gaussian_model import (BasicPointCloud, GaussianModel, RGB2SH, SH2RGB, C0, get_expon_lr_func,  # noqa: F401
+                             inverse_sigmoid)
 
 
-class GaussianModel:
-    """Parameters + activations of the reference GaussianModel, same attribute names."""
-
-    def __init__(self, sh_degree: int, num_latent_code: int = 1, latent_code_dim: int = 32, device="cuda"):
-        self.active_sh_degree = 0
-        self.max_sh_degree = sh_degree
-        self.num_latent_code = num_latent_code
-        self.latent_code_dim = latent_code_dim
-        self.device = device
-        e = torch.empty(0, device=device)
-        self._xyz = self._features_dc = self._features_rest = self._scaling = self._rotation = self._opacity = e
-        self._c_xyz = self._c_radius = self._r = e
-        self.max_radii2D = e
-        self.optimizer = None
-        self._latent_codes = nn.Parameter(torch.randn(num_latent_code, latent_code_dim, device=device))
-        self._timenet = _deform.TimeNet(latent_code_dim=latent_code_dim).to(device)
-        self.neighbor_dists = None
-        self.neighbor_indices = None
-
-    # -- construction from tensors (synthetic scenes, checkpoints) --------------------------------
-    def load_state(self, state: dict):
-        for k in ("_xyz", "_features_dc", "_features_rest", "_scaling", "_rotation", "_opacity", "_c_xyz", "_c_radius"):
-            setattr(self, k, nn.Parameter(state[k].to(self.device).float().contiguous()))
-        if "_latent_codes" in state:
-            self._latent_codes = nn.Parameter(state["_latent_codes"].to(self.device).float().contiguous())
-            self.num_latent_code = self._latent_codes.shape[0]
-        self._r = torch.empty(0, device=self.device)
-        self.max_radii2D = torch.zeros(self._xyz.shape[0], device=self.device)
-
-    # -- activations: renderer/latent_gs_renderer.py:257-265, 340-407 ---------------------------
-    @property
-    def get_scaling(self):
-        if len(self._r) == 0:
-            return torch.exp(self._scaling)
-        elif self._r.shape[0] != self._xyz.shape[0]:
-            return torch.exp(self._r.repeat(self._xyz.shape[0], 3))
-        elif self._r.shape[1] == 1:
-            return torch.exp(self._r.repeat(1, 3))
-        elif self._r.shape == self._xyz.shape:
-            return torch.exp(self._r)
-        raise ValueError("Shape of _r is not supported.")
-
-    @property
-    def get_rotation(self):
-        return F.normalize(self._rotation)
-
-    @property
-    def get_xyz(self):
-        return self._xyz
-
-    @property
-    def get_c_xyz(self):
-        return self._c_xyz
-
-    @property
-    def get_features(self):
-        return torch.cat((self._features_dc, self._features_rest), dim=1)
-
-    @property
-    def get_opacity(self):
-        return torch.sigmoid(self._opacity)
-
-    @property
-    def get_latent_codes(self):
-        return self._latent_codes
-
-    def get_c_radius(self, stage="s2"):
-        if stage < "s2":
-            return torch.exp(self._r.repeat(self._xyz.shape[0], 1))
-        return torch.exp(self._c_radius)
-
-    def parameters(self):
-        return [self._xyz, self._features_dc, self._features_rest, self._opacity, self._scaling, self._rotation,
-                self._c_xyz, self._c_radius, self._latent_codes] + list(self._timenet.parameters())
-
-    # reference group names and order: GaussianModel.training_setup, renderer/latent_gs_renderer.py:460-473
-    GROUP_NAMES = ("xyz", "f_dc", "f_rest", "opacity", "scaling", "rotation", "latent_code", "deform", "deform_rot",
-                   "c_xyz", "c_radius", "r")
-
-    def param_groups(self, lr=0.0):
-        """The twelve optimizer groups of training_setup.  lr: float (every group) or {name: lr} (missing -> 0.0,
-        the reference constructs Adam with lr=0.0 and per-group values)."""
-        mlp, mlp_rot = self._timenet.get_mlp_parameters()
-        tensors = {"xyz": [self._xyz], "f_dc": [self._features_dc], "f_rest": [self._features_rest],
-                   "opacity": [self._opacity], "scaling": [self._scaling], "rotation": [self._rotation],
-                   "latent_code": [self._latent_codes], "deform": list(mlp), "deform_rot": list(mlp_rot),
-                   "c_xyz": [self._c_xyz], "c_radius": [self._c_radius], "r": [self._r]}
-        get = (lambda n: float(lr.get(n, 0.0))) if isinstance(lr, dict) else (lambda n: float(lr))
-        return [{"params": [p for p in tensors[n] if isinstance(p, nn.Parameter)], "lr": get(n), "name": n}
-                for n in self.GROUP_NAMES]
-
-    def find_knn(self, k=4):
-        """main_train_dimo.py:502-509 (GUI.find_knn): once per optimisation step."""
-        self.neighbor_dists, self.neighbor_indices = _knn.knn(self._c_xyz, self._xyz, k)
+def _ball_points(n, radius):
+    """n points uniform in a ball, drawn from NumPy's global stream in the reference's order: phi, cos(theta), mu
+    (renderer/latent_gs_renderer.py:999-1007)."""
+    phis = np.random.random((n,)) * 2 * np.pi
+    costheta = np.random.random((n,)) * 2 - 1
+    thetas = np.arccos(costheta)
+    mu = np.random.random((n,))
+    r = radius * np.cbrt(mu)
+    return np.stack((r * np.sin(thetas) * np.cos(phis), r * np.sin(thetas) * np.sin(phis), r * np.cos(thetas)), axis=1)
 
 
 class Renderer:
     def __init__(self, sh_degree=3, white_background=True, radius=1, delta_t=1 / 32, num_latent_code=1,
-                 latent_code_dim=32, add_normal=False, device="cuda"):
+                 latent_code_dim=32, add_normal=False, device="cuda", vae_latent=False):
+        """vae_latent=True: the renderer/gaussian_gs_renderer.py twin (`_mu` / `_log_var` + reparameterisation)."""
         self.sh_degree = sh_degree
         self.white_background = white_background
         self.radius = radius
-        self.gaussians = GaussianModel(sh_degree, num_latent_code, latent_code_dim, device=device)
+        self.gaussians = GaussianModel(sh_degree, num_latent_code, latent_code_dim, device=device,
+                                       vae_latent=vae_latent)
         self.bg_color = torch.tensor([1, 1, 1] if white_background else [0, 0, 0], dtype=torch.float32, device=device)
         self.delta_t = delta_t
         self.add_normal = add_normal
+        self.vae_latent = bool(vae_latent)
+
+    # -- initialisation: :995-1058 -----------------------------------------------------------------
+    def initialize(self, input=None, num_pts=5000, num_cpts=512, radius=0.5, radius2=0.5, only_init_gaussians=False,
+                   dist3nn=None):
+        """Random Gaussians in a ball of `radius` and control points in a ball of `radius2` (NumPy global stream, same
+        draw order as the reference), or a given BasicPointCloud."""
+        if input is None:
+            xyz = _ball_points(num_pts, radius)
+            shs = np.random.random((num_pts, 3)) / 255.0
+            pcd = BasicPointCloud(points=xyz, colors=SH2RGB(shs), normals=np.zeros((num_pts, 3)))
+            cxyz = _ball_points(num_cpts, radius2)
+            cshs = np.random.random((num_cpts, 3)) / 255.0
+            pcd2 = BasicPointCloud(points=cxyz, colors=SH2RGB(cshs), normals=np.zeros((num_cpts, 3)))
+            self.gaussians.create_from_pcd(pcd, pcd2, 1, only_init_gaussians=only_init_gaussians, dist3nn=dist3nn)
+        elif isinstance(input, BasicPointCloud):
+            self.gaussians.create_from_pcd(input, input, 1, dist3nn=dist3nn)
+        else:
+            raise ValueError("Unsupported initialization type!!!")
+
+    def initialize_ag(self, c_xyz, c_radius, num_cpts=512, num_pts_per_cpt=200, init_ratio=1, dist3nn=None):
+        """Adaptive Gaussian initialisation (:1038-1058): the SAME ball of num_pts_per_cpt offsets, radius
+        mean(c_radius) * init_ratio, around every control point."""
+        offs = _ball_points(num_pts_per_cpt, c_radius.mean().item() * init_ratio)
+        xyz = torch.tensor(offs)[None].repeat(num_cpts, 1, 1).flatten(0, 1)
+        centres = c_xyz.cpu().data[:, None].repeat(1, num_pts_per_cpt, 1).flatten(0, 1)
+        xyz = (xyz + centres).numpy()
+        n = num_pts_per_cpt * num_cpts
+        shs = np.random.random((n, 3)) / 255.0
+        pcd = BasicPointCloud(points=xyz, colors=SH2RGB(shs), normals=np.zeros((n, 3)))
+        self.gaussians.create_from_pcd(pcd, pcd, 1, only_init_gaussians=True, dist3nn=dist3nn)
+
+    # -- latent codes ---------------------------------------------------------------------------------
+    def reparameterize(self, mu, log_var):
+        """gaussian_gs_renderer.py:1088-1098: z = mu + eps * exp(log_var / 2), eps ~ N(0, I)."""
+        std = torch.exp(0.5 * log_var)
+        return torch.randn_like(std) * std + mu
+
+    def latent_code(self, latent_index):
+        g = self.gaussians
+        if self.vae_latent:
+            return self.reparameterize(g._mu[latent_index], g._log_var[latent_index])
+        return g._latent_codes[latent_index]
+
+    # -- ARAP over T random time samples: :1081-1094 ----------------------------------------------------
+    def arap_loss_v2(self, delta_t=0.05, t_samp_num=8, stage="s1", latent_index=0):
+        g = self.gaussians
+        q_times = torch.rand(t_samp_num).to(g._xyz.device)
+        means3D = g._xyz if stage == "s1" else g._c_xyz                                  # [M,3]
+        lat = self.latent_code(latent_index)
+        deform, _ = g._timenet.forward_batched(means3D, q_times, lat[None, :].expand(t_samp_num, -1))
+        means3D_t = means3D[None].detach() + deform                                      # [T,M,3]
+        return _reg.arap_loss_points(means3D_t)
 
     # ------------------------------------------------------------------------------------------
     def prepare_step(self, cameras, times, latent_indices, bg_color=None, out=None):
@@ -182,7 +148,10 @@ class Renderer:
         g = self.gaussians
         prep = prepared if prepared is not None else self.prepare_step(cameras, times, latent_indices, bg_color)
         W, H = prep["W"], prep["H"]
-        latents = g._latent_codes.index_select(0, prep["li"])               # [U,L]
+        if self.vae_latent:                                                  # one reparameterised draw per pair
+            latents = self.reparameterize(g._mu.index_select(0, prep["li"]), g._log_var.index_select(0, prep["li"]))
+        else:
+            latents = g._latent_codes.index_select(0, prep["li"])           # [U,L]
         t_dev = prep["t"]
         if stage >= "s2":
             dxyz, dquat = g._timenet.forward_batched(g._c_xyz, t_dev, latents)   # [U,M,3],[U,M,4]
@@ -234,7 +203,7 @@ class Renderer:
         except Exception:
             pass
         t_dev = torch.tensor([float(time)], dtype=torch.float32).to(dev, non_blocking=True)
-        latents = g._latent_codes[latent_index][None]
+        latents = self.latent_code(latent_index)[None]
         if stage >= "s2":
             dxyz, dquat = g._timenet.forward_batched(g._c_xyz, t_dev, latents)
             cpts_t = g._c_xyz + dxyz[0]

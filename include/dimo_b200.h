@@ -150,6 +150,32 @@ int dimo_knn(int M, int N, int k, const float* ref, const float* query,
 int dimo_dist3nn(int N, const float* points, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Point-set ops of the key-point annealing and the step regularisers.  The
+ * reference reaches them through pip packages that are not part of its tree (pytorch3d, chamferdist:
+ * parity unpinned, semantics restated in csrc/points.cu).
+ * ------------------------------------------------------------------------------------------- */
+/* replaces pytorch3d.ops.sample_farthest_points(points[B,N,3], K=K)[1] (GUI.FPS, main_train_dimo.py:511-515,
+ * main_test_dimo.py:166-170): idx [B,K] i64, first pick = `start` (pytorch3d: 0), then repeatedly the point with
+ * the largest squared distance to the picked set (ties -> lower index).  min_dist_scratch [B,N] f32. */
+int dimo_fps(int B, int N, int K, int start, const float* points, float* min_dist_scratch, int64_t* idx,
+             void* stream);
+/* replaces pytorch3d.ops.ball_query(p1[B,P1,3], p2[B,P2,3], K=K, radius=radius) (utils/deform_utils.py:128):
+ * idx [B,P1,K] i64 = the first K points of p2 IN INDEX ORDER with squared distance < radius^2 (-1 padded),
+ * dists [B,P1,K] f32 = those squared distances (0 padded). */
+int dimo_ball_query(int B, int P1, int P2, int K, float radius, const float* p1, const float* p2,
+                    int64_t* idx, float* dists, void* stream);
+/* replaces chamferdist.ChamferDistance()(src[1,N,3], tgt[1,M,3]) (main_train_dimo.py:298-299; defaults: forward
+ * direction only, squared distances summed over the source points):
+ *   d2 [N] f32, nn [N] i32 = nearest target per source point; *sum += sum_i d2_i (may be NULL);
+ *   *loss_acc += lw * sum_i d2_i (may be NULL: the step's loss scalar, like dimo_ssim_fwd).
+ * bwd: d_src [N,3] = 2 * gw * g * (src_i - tgt_nn(i)) (g = *g_scalar on the device, NULL = 1);
+ *      d_tgt [M,3] (may be NULL; must be zeroed by the caller) accumulates the opposite sign. */
+int dimo_chamfer_fwd(int N, int M, const float* src, const float* tgt, float* d2, int32_t* nn, float* sum,
+                     float* loss_acc, float lw, void* stream);
+int dimo_chamfer_bwd(int N, const float* src, const float* tgt, const int32_t* nn, const float* g_scalar,
+                     float gw, float* d_src, float* d_tgt, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Deformation: positional encoding + TimeNet MLP (renderer/latent_gs_renderer.py:184-235,
  * src/pos_enc.py:6-54) and K-neighbour linear-blend skinning (:1191-1219).
  * ------------------------------------------------------------------------------------------- */
