@@ -63,7 +63,7 @@ class FusedAdam:
         self.state = torch.zeros(4, dtype=torch.int32, device=dev)     # [0] step count, [1] ticket
         # learning rates travel through a small ring of pinned staging buffers (asynchronous copies; a slot is
         # reused only after its previous copy has completed)
-        self._lr_ring = [torch.zeros(len(groups), dtype=torch.float32).pin_memory() for _ in range(4)]
+        self._lr_ring = None                                            # pinned, allocated on first use
         self._lr_events = [None] * 4
         self._lr_slot = 0
         self._lr_dev = torch.zeros(len(groups), dtype=torch.float32, device=dev)
@@ -75,6 +75,8 @@ class FusedAdam:
         """Uploads the groups' learning rates if they changed (call outside a graph capture / before a replay)."""
         cur = tuple(float(d["lr"]) for d in self._seg_dict)
         if cur != self._lr_sent:
+            if self._lr_ring is None:
+                self._lr_ring = [torch.zeros(len(cur), dtype=torch.float32).pin_memory() for _ in range(4)]
             k = self._lr_slot
             self._lr_slot = (k + 1) % len(self._lr_ring)
             if self._lr_events[k] is not None:

@@ -96,7 +96,7 @@ class Renderer:
         q_times = torch.rand(t_samp_num).to(g._xyz.device)
         means3D = g._xyz if stage == "s1" else g._c_xyz                                  # [M,3]
         lat = self.latent_code(latent_index)
-        deform, _ = g._timenet.forward_batched(means3D, q_times, lat[None, :].expand(t_samp_num, -1))
+        deform, _ = g._timenet.forward_batched(means3D, q_times, lat[None, :].expand(t_samp_num, -1).contiguous())
         means3D_t = means3D[None].detach() + deform                                      # [T,M,3]
         return _reg.arap_loss_points(means3D_t)
 

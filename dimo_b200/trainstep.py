@@ -95,19 +95,28 @@ class TrainStep:
         self.g = renderer.gaussians
         self.stage = stage
         self.world = world
-        self.params = [p for p in self.g.parameters() if p.numel() > 0]
         g = self.g
-        # per-Gaussian parameters: their gradients are final once the LBS backward has run, i.e. before the
-        # TimeNet backward -> bucket 0 of the flat buffer, all-reduced while the MLP backward executes
-        early = [g._xyz, g._features_dc, g._features_rest, g._opacity, g._scaling, g._rotation]
-        self.reducer = FlatGradReducer(self.params, early=early)
-        groups = g.param_groups(lr)
-        if optimizer == "fused":
-            self.opt = FusedAdam(groups, self.reducer, eps=1e-15)
+        if optimizer == "fused" and g.optimizer is not None and g.reducer is not None:
+            # GaussianModel.training_setup already built the flat buffers (reference flow: training_setup, then steps)
+            self.reducer, self.opt = g.reducer, g.optimizer
+            self.params = list(self.reducer.params)
         else:
-            self.opt = torch.optim.Adam([{"params": [p for p in gr["params"] if p.numel() > 0], "lr": gr["lr"],
-                                          "name": gr["name"]} for gr in groups if any(p.numel() for p in gr["params"])],
-                                        lr=0.0, eps=1e-15, fused=True, capturable=bool(graph))
+            self.params = [p for p in g.parameters() if p.numel() > 0]
+            # per-Gaussian parameters: their gradients are final once the LBS backward has run, i.e. before the
+            # TimeNet backward -> bucket 0 of the flat buffer, all-reduced while the MLP backward executes
+            early = [g._xyz, g._features_dc, g._features_rest, g._opacity, g._scaling, g._rotation]
+            self.reducer = FlatGradReducer(self.params, early=early)
+            groups = g.param_groups(lr)
+            if optimizer == "fused":
+                self.opt = FusedAdam(groups, self.reducer, eps=1e-15)
+                g.reducer, g._optimizer_kind = self.reducer, "fused"
+            else:
+                self.opt = torch.optim.Adam([{"params": [p for p in gr["params"] if p.numel() > 0], "lr": gr["lr"],
+                                              "name": gr["name"]} for gr in groups if any(p.numel() for p in gr["params"])],
+                                            lr=0.0, eps=1e-15, fused=True, capturable=bool(graph))
+                g.reducer, g._optimizer_kind = None, "torch"
+        # densify / prune / reset_opacity re-lay the flat buffers out (GaussianModel._rebind): follow them
+        g.on_relayout = self._on_relayout
         self.fused_opt = optimizer == "fused"
         g.optimizer = self.opt
         # TimeNet's weight gradients are accumulated by the kernels straight into the flat buffer
@@ -125,6 +134,21 @@ class TrainStep:
         self._max_R = 0
         self._static = None
         self.graph_error = None
+
+    def _on_relayout(self, model):
+        """The Gaussian count (or a parameter tensor) changed: new flat buffers, new instance counts -- a captured graph
+        is stale, so the next run() probes the instance count again and re-captures."""
+        if model.reducer is None:
+            raise RuntimeError("TrainStep follows re-layouts of the fused optimizer only (optimizer='torch' is an A/B "
+                               "vehicle with a fixed parameter set)")
+        self.reducer, self.opt = model.reducer, model.optimizer
+        self.params = list(self.reducer.params)
+        model._timenet.direct_grads = True
+        self.graph = None
+        self._static = None
+        self.capacity = None
+        self._seen = 0
+        self._max_R = 0
 
     def _timed(self, name, fn):
         if not _lib.PROFILE.enabled or torch.cuda.is_current_stream_capturing():

@@ -1,0 +1,187 @@
+"""-m gpu: a miniature of GUI.train_step / prepare_train_s1 / prepare_train_s2 (main_train_dimo.py:221-499) written the
+way the reference writes it -- one renderer.render() per (motion, view, frame), torch-level loss sums,
+loss.backward(); optimizer.step(); optimizer.zero_grad(), densification statistics from viewspace_points, FPS key-point
+annealing, densify_and_prune, the s1 -> s2 hand-over (copy key points, adaptive initialisation, training_setup, popped
+"r" group), find_knn, chamfer / ARAP / smoothness terms, save_ply + save_model and a reload -- against the dimo_b200
+class surface.  It checks that the surface composes on the GPU the way the reference drives it; the
+numerics of every piece are checked in the other test files."""
+import math
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _opt():
+    import model_scenario as ms
+    o = ms.train_args(position_lr_max_steps=500)
+    for k, v in dict(lambda_mse=5000.0, lambda_ssim=500.0, lambda_mask=500.0, lambda_smooth=100.0, lambda_bilateral=0.05,
+                     lambda_ga1=10.0, lambda_arap=10.0, num_cpts=64, FPS_iter=10, density_start_iter=2,
+                     density_end_iter=8, densification_interval=4, densify_grad_threshold=0.0002,
+                     densify_opacity_threshold_s1=0.01, densify_opacity_threshold_s2=0.01, init_ratio=1,
+                     batch_size=2, iters_s2=40).items():
+        setattr(o, k, v)
+    return o
+
+
+def test_reference_style_training_loop(cuda, tmp_path):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import dimo_b200
+    dimo_b200.install_shims()
+    import pytorch3d.ops as ops
+    from chamferdist import ChamferDistance
+    from dimo_b200.camera import orbit_camera
+    from dimo_b200.loss import (compute_bilateral_normal_smoothness_loss, compute_edge_aware_smoothness_loss, ssim)
+    from dimo_b200.renderer import MiniCam, Renderer
+    import torch.nn.functional as F
+
+    opt = _opt()
+    np.random.seed(0)
+    torch.manual_seed(0)
+    videos = ["walk", "jump"]
+    R = 64                                              # render resolution
+    fovy = math.radians(33.9)
+    azimuths = [0.0, 120.0, 240.0]
+    times = [i / 4 for i in range(4)]
+    gen = torch.Generator().manual_seed(1)
+    gt_img = {v: torch.rand(3, 4, 1, 3, R, R, generator=gen) for v in videos}
+    gt_msk = {v: (torch.rand(3, 4, 1, 1, R, R, generator=gen) > 0.4).float() for v in videos}
+    renderer = Renderer(sh_degree=0, num_latent_code=len(videos), latent_code_dim=32, add_normal=True)
+    g = renderer.gaussians
+    chamfer = ChamferDistance()
+    renderer.initialize(num_pts=opt.num_cpts, num_cpts=opt.num_cpts)          # main_train_dimo.py:143
+
+    def render_losses(stage, step, cpts_s1=None, regularise=False):
+        loss = 0
+        out = None
+        for latent_index, name in enumerate(videos):
+            imgs, gts, masks, gmasks, depths, normals = [], [], [], [], [], []
+            for vi in (0, 2):
+                for fi in (1, 3):
+                    pose = orbit_camera(0, azimuths[vi], 2)
+                    cam = MiniCam(pose, R, R, fovy, fovy, 0.01, 100)
+                    out = renderer.render(cam, time=times[fi], stage=stage, latent_index=latent_index)
+                    if cpts_s1 is not None:
+                        loss = loss + opt.lambda_ga1 * chamfer(out["cpts_t"][None, ...], cpts_s1[name][fi].detach()[None, ...])
+                    imgs.append(out["image"].unsqueeze(0)); masks.append(out["alpha"].unsqueeze(0))
+                    depths.append(out["depth"].unsqueeze(0)); normals.append(out["normal"].unsqueeze(0))
+                    gts.append(gt_img[name][vi][fi].cuda()); gmasks.append(gt_msk[name][vi][fi].cuda())
+            imgs, gts, masks, gmasks = torch.cat(imgs), torch.cat(gts), torch.cat(masks), torch.cat(gmasks)
+            depths, normals = torch.cat(depths), torch.cat(normals)
+            for i in range(imgs.shape[0]):
+                loss = loss + opt.lambda_mse * (1.0 if i == 0 else 0.5) * F.mse_loss(imgs[i], gts[i])
+            loss = loss + opt.lambda_ssim * (1 - ssim(imgs, gts))
+            loss = loss + opt.lambda_mask * F.mse_loss(masks, gmasks)
+            if regularise:
+                loss = loss + opt.lambda_smooth * compute_edge_aware_smoothness_loss(depths.permute(0, 2, 3, 1),
+                                                                                     imgs.permute(0, 2, 3, 1))
+                loss = loss + opt.lambda_bilateral * compute_bilateral_normal_smoothness_loss(normals.permute(0, 2, 3, 1),
+                                                                                              imgs.permute(0, 2, 3, 1))
+                arap, _conn = renderer.arap_loss_v2(stage=stage, latent_index=latent_index)
+                loss = loss + opt.lambda_arap * arap
+        return loss, out
+
+    # ------------------------------- stage s1 (prepare_train_s1, :455-470) -------------------------------
+    stage = "s1"
+    g.training_setup(opt)
+    g.active_sh_degree = g.max_sh_degree
+    optimizer = g.optimizer
+    for grp in optimizer.param_groups:
+        if grp["name"] in ("c_radius", "c_xyz"):
+            grp["lr"] = 0.0
+    sizes, losses = [], []
+    for step in range(0, 13):
+        if step % opt.FPS_iter == 0:                                           # GUI.FPS, :226-228, 511-515
+            _, idxs = ops.sample_farthest_points(points=g._xyz.unsqueeze(0), K=opt.num_cpts)
+            g.prune_points(idxs[0])
+            assert g._xyz.shape[0] == opt.num_cpts
+            assert g.optimizer is optimizer, "surgery must keep the optimizer object the training loop holds"
+        it = step + 1
+        g.update_learning_rate(it, stage)
+        loss, out = render_losses(stage, it, regularise=(it > 9))
+        loss.backward()
+        optimizer.step()
+        optimizer.zero_grad()
+        losses.append(float(loss))
+        if it % opt.FPS_iter >= opt.density_start_iter and it <= opt.density_end_iter:
+            vsp, vis, radii = out["viewspace_points"], out["visibility_filter"], out["radii"]
+            g.max_radii2D[vis] = torch.max(g.max_radii2D[vis], radii[vis])
+            g.add_densification_stats(vsp, vis)
+            if it % opt.densification_interval == 0:
+                g.densify_and_prune(opt.densify_grad_threshold, min_opacity=opt.densify_opacity_threshold_s1, extent=4,
+                                    max_screen_size=1)
+        sizes.append(g._xyz.shape[0])
+    assert all(math.isfinite(x) for x in losses), losses
+    assert max(sizes) > opt.num_cpts, f"densification never fired: {sizes}"
+    assert sizes[-1] == opt.num_cpts, sizes                                   # FPS at step 10 brought it back
+    assert len(set(losses)) == len(losses) and min(losses[1:9]) < losses[0]
+    assert g.optimizer is optimizer
+
+    # ------------------------------- hand-over (prepare_train_s2, :472-499) -------------------------------
+    stage = "s2"
+    with torch.no_grad():
+        g._c_xyz.copy_(g._xyz)
+        g._scaling.copy_(g._r.expand_as(g._xyz))
+        g._c_radius.copy_(g._r.expand_as(g._c_radius))
+    renderer.initialize_ag(g._c_xyz, g.get_c_radius(stage="s2"), num_cpts=g._c_xyz.shape[0], num_pts_per_cpt=20,
+                           init_ratio=opt.init_ratio)
+    assert g._xyz.shape[0] == 20 * opt.num_cpts and g._c_xyz.shape[0] == opt.num_cpts
+    g.training_setup(opt)
+    g.active_sh_degree = g.max_sh_degree
+    optimizer = g.optimizer
+    g._r = torch.tensor([], device="cuda")
+    r_id = 0
+    for grp in optimizer.param_groups:                                          # the reference's pop loop, verbatim
+        if grp["name"] == "r":
+            grp["lr"] = 0.0
+            optimizer.param_groups.pop(r_id)
+        r_id += 1
+    opt.position_lr_max_steps = opt.iters_s2
+    opt.position_lr_init, opt.position_lr_final = 0.0002, 0.000002
+    c_means3D = g._c_xyz
+    cpts_s1 = {name: [] for name in videos}
+    with torch.no_grad():
+        for li, name in enumerate(videos):                                     # :230-245 cached key-point trajectories
+            for t in times:
+                d, _ = g._timenet(c_means3D, t, g._latent_codes[li])
+                cpts_s1[name].append(c_means3D + d)
+    losses2 = []
+    for it in range(1, 7):
+        g.update_learning_rate(it, stage)
+        for grp in optimizer.param_groups:
+            if grp["name"] == "xyz":
+                grp["lr"] = 0.0002
+        g.find_knn(4)                                                           # GUI.find_knn, :502-509
+        loss, out = render_losses(stage, it, cpts_s1=cpts_s1, regularise=(it > 3))
+        loss.backward()
+        optimizer.step()
+        optimizer.zero_grad()
+        losses2.append(float(loss))
+        if it == 4:
+            g.prune(min_opacity=opt.densify_opacity_threshold_s2, extent=4, max_screen_size=1)
+            assert g.optimizer is optimizer
+    assert all(math.isfinite(x) for x in losses2), losses2
+    assert len(set(losses2)) == len(losses2)
+    assert float(g._c_xyz.grad.abs().max()) == 0.0 and g._c_xyz.grad.data_ptr() >= g.reducer.flat.data_ptr()
+
+    # ------------------------------- files (:419-423) and a reload -------------------------------
+    save = str(tmp_path / "s2")
+    g.save_ply(os.path.join(save, "point_cloud_6.ply"), os.path.join(save, "point_cloud_c_6.ply"))
+    g.save_model(save, step=6)
+    g.find_knn(4)
+    cam = MiniCam(orbit_camera(0, 30.0, 2), R, R, fovy, fovy, 0.01, 100)
+    with torch.no_grad():
+        ref_img = renderer.render(cam, time=0.5, stage="s2", latent_index=1)["image"].clone()
+    r2 = Renderer(sh_degree=0, num_latent_code=len(videos), latent_code_dim=32, add_normal=True)
+    g2 = r2.gaussians
+    g2.load_ply(os.path.join(save, "point_cloud_6.ply"), os.path.join(save, "point_cloud_c_6.ply"))
+    g2.load_model(save, step=6)
+    g2.find_knn(4)
+    with torch.no_grad():
+        img2 = r2.render(cam, time=0.5, stage="s2", latent_index=1)["image"]
+    assert torch.equal(img2, ref_img), "a saved + reloaded model must render bit-identically"
