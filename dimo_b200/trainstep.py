@@ -228,12 +228,28 @@ class TrainStep:
             if self._seen < self.probe_steps:              # eager probe steps: learn the instance count
                 self._seen += 1
                 return self._body(prep, gt, mask, n_motions, optimize)
+            gen = torch.cuda.default_generators[gt.device.index if gt.device.index is not None
+                                                else torch.cuda.current_device()]
+            try:
+                rng_backup = gen.clone_state()             # a failed capture leaves the generator in capture mode
+            except Exception:
+                rng_backup = None
             try:
                 self._capture(prep, gt, mask, n_motions, optimize)
             except Exception as e:                         # stay correct: fall back to eager and say so
+                import warnings
                 self.graph_error = f"{type(e).__name__}: {e}"
                 self.graph = None
+                self._static = None
                 torch.cuda.synchronize()
+                if rng_backup is not None:
+                    try:
+                        gen.graphsafe_set_state(rng_backup.graphsafe_get_state())
+                    except Exception:
+                        pass
+                warnings.warn("dimo_b200 TrainStep: CUDA-graph capture failed, running eagerly (" + self.graph_error +
+                              ").  A common cause: tensors of an earlier backward (a render() result, a loss) are "
+                              "still alive, so their AccumulateGrad nodes stay bound to the stream they were created on.")
                 return self._body(prep, gt, mask, n_motions, optimize)
         st = self._static
         self.r.prepare_step(cameras, times, latent_indices, out=st["prep"])
