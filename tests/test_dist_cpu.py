@@ -79,3 +79,92 @@ def test_flat_allreduce_two_ranks():
             assert torch.allclose(a, want)
         else:
             assert torch.allclose(a, l0[i] + l1[i])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# rank-identical densification (replicated Gaussians, per-rank statistics)
+# ---------------------------------------------------------------------------------------------------------------
+def _densify_model():
+    import types
+    from dimo_b200 import synthetic
+    from dimo_b200.gaussian_model import GaussianModel
+    import model_scenario as ms
+    torch.manual_seed(3)
+    g = GaussianModel(0, num_latent_code=2, device="cpu")
+    g.load_state(synthetic.make_scene(500, n_ctrl=16, n_motions=2, seed=4))
+    g.spatial_lr_scale = 1
+    g.training_setup(ms.train_args(), optimizer="torch")
+    gen = torch.Generator().manual_seed(1)
+    for _ in range(2):                                    # replicated parameters: identical (all-reduced) gradients
+        for grp in g.optimizer.param_groups:
+            for p in grp["params"]:
+                p.grad = 0.01 * torch.randn(p.shape, generator=gen)
+        g.optimizer.step()
+        g.optimizer.zero_grad()
+    with torch.no_grad():
+        g._scaling.data.copy_(torch.log(torch.rand(500, 3, generator=gen) * 0.08 + 0.005))
+    return g, types
+
+
+def _feed_stats(g, types, rank):
+    gen = torch.Generator().manual_seed(100 + rank)       # every rank saw other frames
+    n = g._xyz.shape[0]
+    for _ in range(3):
+        vs = types.SimpleNamespace(grad=0.03 * torch.randn(n, 3, generator=gen))
+        vis = torch.rand(n, generator=gen) > 0.4
+        radii = torch.randint(0, 3, (n,), generator=gen).float()
+        g.max_radii2D[vis] = torch.max(g.max_radii2D[vis], radii[vis])
+        g.add_densification_stats(vs, vis)
+
+
+def _densify_worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g, types = _densify_model()
+    _feed_stats(g, types, rank)
+    torch.manual_seed(77 + rank)                          # ranks' own streams differ: the split must not depend on them
+    g.densify_and_prune(0.02, min_opacity=0.1, extent=4, max_screen_size=1)
+    with torch.no_grad():
+        g._opacity.data[::9] = -8.0
+    g.max_radii2D[rank::5] = 3.0                          # rank-local screen-size statistics
+    g.prune(min_opacity=0.01, extent=4, max_screen_size=2)
+    st = g.optimizer.state[g._xyz]
+    q.put((rank, g._xyz.detach().numpy().copy(), g._scaling.detach().numpy().copy(), st["exp_avg"].numpy().copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_densify_and_prune_is_rank_identical():
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_densify_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, x0, s0, m0), (_, x1, s1, m1) = res
+    assert x0.shape == x1.shape and x0.shape[0] != 500
+    assert (x0 == x1).all() and (s0 == s1).all() and (m0 == m1).all(), "ranks diverged"
+    # ... and equal to ONE process that saw both ranks' frames (same split seed: rank 0's draw after seeding 77)
+    g, types = _densify_model()
+    _feed_stats(g, types, 0)
+    _feed_stats(g, types, 1)
+    torch.manual_seed(77)
+    seed = int(torch.randint(0, 2 ** 31 - 1, (1,), dtype=torch.int64))
+    g.split_generator = torch.Generator().manual_seed(seed)
+    g.densify_and_prune(0.02, min_opacity=0.1, extent=4, max_screen_size=1)
+    with torch.no_grad():
+        g._opacity.data[::9] = -8.0
+    g.max_radii2D[0::5] = 3.0
+    g.max_radii2D[1::5] = 3.0
+    g.prune(min_opacity=0.01, extent=4, max_screen_size=2)
+    assert g._xyz.shape[0] == x0.shape[0]
+    assert (g._xyz.detach().numpy() == x0).all()
