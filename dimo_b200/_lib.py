@@ -52,6 +52,7 @@ _SIGS = {
     "dimo_sqdiff_sum": (c_int, [c_i64] + [c_vp] * 4 + [c_f32, c_vp]),
     "dimo_adam_step": (c_int, [c_i64] + [c_vp] * 4 + [c_int, c_vp, c_vp, c_f64, c_f64, c_f32, c_int, c_vp, c_vp]),
     "dimo_transpose_grouped": (c_int, [c_int] + [c_vp] * 5),
+    "dimo_gt_fetch": (c_int, [c_int] * 6 + [c_vp] * 5),
 }
 
 
@@ -109,7 +110,7 @@ _OWN_LAUNCHES = {
     "dimo_fps": 1, "dimo_ball_query": 1, "dimo_chamfer_fwd": 1, "dimo_chamfer_bwd": 1, "dimo_linear_fwd": 1,
     "dimo_linear_bwd_data": 1, "dimo_linear_tc": 1, "dimo_linear_wgrad_tc": 1, "dimo_linear_wgrad_tc_grouped": 1, "dimo_linear_bwd_weight": 1, "dimo_timenet_embed_fwd": 1,
     "dimo_timenet_embed_bwd": 1, "dimo_lbs_fwd": 1, "dimo_lbs_bwd": 1, "dimo_ssim_fwd": 1, "dimo_ssim_bwd": 1,
-    "dimo_sqdiff_sum": 1, "dimo_smooth_fwd": 1, "dimo_smooth_bwd": 1, "dimo_segment_sum": 1, "dimo_adam_step": 1, "dimo_transpose_grouped": 1,
+    "dimo_sqdiff_sum": 1, "dimo_smooth_fwd": 1, "dimo_smooth_bwd": 1, "dimo_segment_sum": 1, "dimo_adam_step": 1, "dimo_transpose_grouped": 1, "dimo_gt_fetch": 1,
 }
 
 

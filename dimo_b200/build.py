@@ -34,6 +34,7 @@ SOURCES = {
     "ssim.cu": [],
     "optim.cu": [],
     "smooth.cu": [],
+    "gtcache.cu": [],
 }
 
 

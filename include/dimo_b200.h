@@ -308,6 +308,16 @@ int dimo_adam_step(int64_t n, float* params, float* grads, float* exp_avg, float
 int dimo_transpose_grouped(int n, const int* rows_host, const int* cols_host, const float* const* src_host,
                            float* const* dst_host, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Ground truth resident in HBM: one gather + convert + bilinear-resample launch per step instead
+ * of the reference's per-frame upload + F.interpolate(mode="bilinear", align_corners=False)
+ * (main_train_dimo.py:283-284, 305-313).
+ *   store [F,4,Hs,Ws] (u8: value / 255, or f32; channels R,G,B,mask), slots [S] i32 (device) = frame slots to fetch,
+ *   rgb [S,3,Ho,Wo] f32, mask [S,1,Ho,Wo] f32.
+ * ------------------------------------------------------------------------------------------- */
+int dimo_gt_fetch(int S, int Hs, int Ws, int Ho, int Wo, int store_is_u8, const void* store,
+                  const int32_t* slots, float* rgb, float* mask, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

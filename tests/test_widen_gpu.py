@@ -336,3 +336,46 @@ def test_keypoint_trajectory_loss(cuda):
     assert a.grad.abs().sum() > 0
     w = regularisers.keypoint_trajectory_loss(a, b, chamfer=False)
     assert abs(w.item() - 10000.0 * (a.detach() - b).abs().mean().item()) <= 1e-5 * w.item()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# ground truth resident in HBM
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.uint8, torch.float32])
+def test_gt_cache_fetch_matches_interpolate(cuda, dtype):
+    from dimo_b200.data import GroundTruthCache
+    from oracle import data as odata
+    gen = torch.Generator().manual_seed(6)
+    cache = GroundTruthCache(n_motions=2, n_views=3, n_frames=4, size=96, dtype=dtype)
+    host = torch.zeros(24, 4, 96, 96, dtype=dtype)
+    for m in range(2):
+        for v in range(3):
+            for f in range(4):
+                if dtype == torch.uint8:
+                    frame = torch.randint(0, 256, (4, 96, 96), generator=gen, dtype=torch.uint8)
+                    img, msk = frame[:3].float() / 255.0, frame[3:].float() / 255.0     # what the reference's loader returns
+                else:
+                    frame = torch.rand(4, 96, 96, generator=gen)
+                    img, msk = frame[:3], frame[3:]
+                host[cache.slot(m, v, f)] = frame
+                cache.put(m, v, f, img[None].cuda(), msk[None].cuda())
+    assert torch.equal(cache.store.cpu(), host)
+    triples = [(1, 2, 3), (0, 0, 0), (1, 0, 2), (0, 2, 1), (1, 2, 3)]
+    slots = [cache.slot(*t) for t in triples]
+    for res in (96, 48, 32, 128, 77):
+        rgb, mask = cache.fetch(triples, res)
+        want_rgb, want_mask = odata.fetch(host, slots, res)
+        assert rgb.shape == (5, 3, res, res) and mask.shape == (5, 1, res, res)
+        if res == 96:
+            assert torch.equal(rgb.cpu(), want_rgb) and torch.equal(mask.cpu(), want_mask)   # same size: exact copy
+        else:
+            # the source coordinate scale * (dst + 0.5) - 0.5 is an fp32 number of magnitude <= 96: its fraction (the
+            # tap weight) carries ~4e-6 of rounding, fused or not -- the same spread exists between torch's own CPU
+            # and CUDA kernels
+            assert float((rgb.cpu() - want_rgb).abs().max()) <= 2e-5
+            assert float((mask.cpu() - want_mask).abs().max()) <= 2e-5
+    with pytest.raises(IndexError):
+        cache.fetch([(2, 0, 0)])
+    if dtype == torch.uint8:
+        with pytest.raises(ValueError):
+            cache.put(0, 0, 0, torch.full((1, 3, 96, 96), 0.123).cuda(), torch.zeros(1, 1, 96, 96).cuda())
