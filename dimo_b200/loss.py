@@ -119,3 +119,14 @@ def l1_loss(a, b):
 
 def mse_loss(a, b):
     return image_losses(a, b, need_ssim_grad=False)[2]
+
+
+def compute_tv_norm(values, losstype="l2"):
+    """src/loss.py:109-129 (imported by main_train_dimo.py:28, never called): squared / absolute forward differences of
+    a channel-last [batch,H,W,C] tensor -> [batch,H-1,W-1,C].  Plain tensor arithmetic: not on any measured path."""
+    v00, v01, v10 = values[..., :-1, :-1, :], values[..., :-1, 1:, :], values[..., 1:, :-1, :]
+    if losstype == "l2":
+        return (v00 - v01) ** 2 + (v00 - v10) ** 2
+    if losstype == "l1":
+        return (v00 - v01).abs() + (v00 - v10).abs()
+    raise ValueError(f"losstype must be l2 or l1 but is {losstype}")
