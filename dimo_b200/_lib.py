@@ -33,6 +33,8 @@ _SIGS = {
     "dimo_ball_query": (c_int, [c_int] * 4 + [c_f32] + [c_vp] * 5),
     "dimo_chamfer_fwd": (c_int, [c_int] * 2 + [c_vp] * 6 + [c_f32, c_vp]),
     "dimo_chamfer_bwd": (c_int, [c_int] + [c_vp] * 4 + [c_f32] + [c_vp] * 3),
+    "dimo_arap_connectivity": (c_int, [c_int] * 3 + [c_f32] + [c_vp] * 4),
+    "dimo_arap_energy": (c_int, [c_int] * 3 + [c_vp] * 6),
     "dimo_linear_fwd": (c_int, [c_int] * 3 + [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_int, c_vp]),
     "dimo_linear_bwd_data": (c_int, [c_int] * 3 + [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_vp]),
     "dimo_linear_bwd_weight": (c_int, [c_int] * 3 + [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
@@ -107,7 +109,8 @@ def stream():
 _OWN_LAUNCHES = {
     "dimo_raster_preprocess": 2, "dimo_raster_bin": 2, "dimo_raster_blend_fwd": 1, "dimo_raster_blend_bwd": 1,
     "dimo_raster_preprocess_bwd": 1, "dimo_knn": 1, "dimo_dist3nn": 1,
-    "dimo_fps": 1, "dimo_ball_query": 1, "dimo_chamfer_fwd": 1, "dimo_chamfer_bwd": 1, "dimo_linear_fwd": 1,
+    "dimo_fps": 1, "dimo_ball_query": 1, "dimo_chamfer_fwd": 1, "dimo_chamfer_bwd": 1,
+    "dimo_arap_connectivity": 1, "dimo_arap_energy": 1, "dimo_linear_fwd": 1,
     "dimo_linear_bwd_data": 1, "dimo_linear_tc": 1, "dimo_linear_wgrad_tc": 1, "dimo_linear_wgrad_tc_grouped": 1, "dimo_linear_bwd_weight": 1, "dimo_timenet_embed_fwd": 1,
     "dimo_timenet_embed_bwd": 1, "dimo_lbs_fwd": 1, "dimo_lbs_bwd": 1, "dimo_ssim_fwd": 1, "dimo_ssim_bwd": 1,
     "dimo_sqdiff_sum": 1, "dimo_smooth_fwd": 1, "dimo_smooth_bwd": 1, "dimo_segment_sum": 1, "dimo_adam_step": 1, "dimo_transpose_grouped": 1, "dimo_gt_fetch": 1,

@@ -28,6 +28,7 @@ SOURCES = {
     "raster_blend.cu": [],
     "knn.cu": ["-fmad=false"],
     "points.cu": ["-fmad=false"],
+    "arap.cu": ["-fmad=false"],
     "deform.cu": [],
     "mlp.cu": [],
     "mlp_tc.cu": [],

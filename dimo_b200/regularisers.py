@@ -2,16 +2,23 @@
 (Renderer.arap_loss_v2 renderer/latent_gs_renderer.py:1081-1094 -> utils/deform_utils.py:115-150 connectivity,
 :152-232 rotation fit + energy) and the key-point trajectory term (main_train_dimo.py:295-302).
 
-Formulation here: a neighbour TABLE nbr [M,K] (-1 padded) instead of the reference's (ii, jj, nn) edge triplets --
-every per-vertex quantity (edge vectors, the 3x3 covariance, the fitted rotation, the energy) is then a dense
-[.., M, K, 3] expression with a mask, batched over all T-1 target frames at once (the reference loops over frames and
-scatters into zero matrices per frame).  M = 512, K = 10: a few dozen small launches per call; the ball query is the
-dimo_ball_query kernel.  Results equal the reference's: tests/golden/arap.npz is produced by executing
-utils/deform_utils.py.
+Formulation: a neighbour TABLE nbr [M,K] (-1 padded) instead of the reference's (ii, jj, nn) edge triplets -- every
+per-vertex quantity (edge vectors, the 3x3 covariance, the fitted rotation, the energy) is then local to one vertex
+and one target frame.
+
+Two implementations of the same arithmetic:
+  * CUDA tensors: TWO kernel launches, `dimo_arap_connectivity` + `dimo_arap_energy` (csrc/arap.cu over
+    csrc/arap_math.h: thread per vertex / per (frame, vertex), fp64 Jacobi rotation fit, gradient by atomics) --
+    the reference spends ~40 launches per call on M = 512 points, once per motion of the batch;
+  * any device, `fused=False`: dense [.., M, K, 3] torch expressions batched over all target frames (what the CPU
+    tests drive, and the A/B partner of the kernels on the GPU).
+Both equal the reference: tests/golden/arap.npz is produced by executing utils/deform_utils.py, and the kernels' source
+is checked against it through a host build (tests/test_arap_math_cpu.py).
 """
 import numpy as np
 import torch
 
+from . import _lib
 from . import points as _points
 
 
@@ -99,8 +106,80 @@ def arap_energy(nodes, nbr, weight=None, sample_num=512, sample_idx=None):
     return per_vertex.sum()
 
 
-def arap_loss_points(means3D_t, K=10, radius=0.1, ball_query=None):
-    """means3D_t [T,M,3] -> (error, (ii, jj, nn, nbr)) -- the tail of Renderer.arap_loss_v2 (:1090-1094)."""
+class Connectivity:
+    """Result of the fused connectivity kernel.  Unpacks like the reference's `(ii, jj, nn, _)` tuple
+    (`loss, conns = renderer.arap_loss_v2(...)`), but the edge triplets are only materialised when asked for: boolean
+    indexing needs the edge count on the host, and the training loop never looks at them."""
+
+    def __init__(self, nbr, count=None):
+        self.nbr, self.count = nbr, count
+
+    def triplets(self):
+        M, K = self.nbr.shape
+        valid = self.nbr >= 0
+        ii = torch.arange(M, device=self.nbr.device)[:, None].expand(M, K)[valid]
+        nn = torch.arange(K, device=self.nbr.device)[None, :].expand(M, K)[valid]
+        return ii, self.nbr[valid], nn
+
+    def __iter__(self):
+        ii, jj, nn = self.triplets()
+        return iter((ii, jj, nn, self.nbr))
+
+    def __len__(self):
+        return 4
+
+
+def connectivity_fused(points, K=10, radius=0.1):
+    """points [T,M,3] CUDA -> Connectivity (one launch, no host sync)."""
+    p = points.detach().contiguous().float()
+    T, M, _ = p.shape
+    nbr = torch.empty(M, K, dtype=torch.int64, device=p.device)
+    count = torch.empty(M, dtype=torch.int32, device=p.device)
+    _lib.call("dimo_arap_connectivity", T, M, int(K), float(radius), _lib.ptr(p), _lib.ptr(nbr), _lib.ptr(count),
+              _lib.stream())
+    return Connectivity(nbr, count)
+
+
+class _ArapEnergy(torch.autograd.Function):
+    """energy (scalar) of nodes [T,M,3] over a neighbour table; the kernel returns the gradient with the forward."""
+
+    @staticmethod
+    def forward(ctx, nodes, nbr, mult):
+        x = nodes.contiguous().float()
+        T, M, _ = x.shape
+        energy = torch.empty((), dtype=torch.float32, device=x.device)
+        grad = torch.empty_like(x)
+        _lib.call("dimo_arap_energy", T, M, nbr.shape[1], _lib.ptr(x), _lib.ptr(nbr), _lib.ptr(mult), _lib.ptr(energy),
+                  _lib.ptr(grad), _lib.stream())
+        ctx.save_for_backward(grad)
+        return energy
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None, None
+
+
+def arap_energy_fused(nodes, nbr, sample_num=512, sample_idx=None):
+    """CUDA counterpart of arap_energy (unit edge weights).  Vertex sampling with replacement becomes a per-vertex
+    multiplicity."""
+    M = nodes.shape[1]
+    if sample_idx is None and M > sample_num:
+        sample_idx = torch.from_numpy(np.random.choice(M, sample_num)).long()
+    mult = None
+    if sample_idx is not None:
+        mult = torch.bincount(sample_idx.to(nodes.device), minlength=M).float()
+    return _ArapEnergy.apply(nodes, nbr.contiguous(), mult)
+
+
+def arap_loss_points(means3D_t, K=10, radius=0.1, ball_query=None, fused=None):
+    """means3D_t [T,M,3] -> (error, (ii, jj, nn, nbr)) -- the tail of Renderer.arap_loss_v2 (:1090-1094).
+    fused: None = kernels on CUDA tensors (when no ball_query override is given), torch formulation otherwise."""
+    if fused is None:
+        fused = means3D_t.is_cuda and ball_query is None
+    if fused:
+        conn = connectivity_fused(means3D_t, K=K, radius=radius)
+        return arap_energy_fused(means3D_t, conn.nbr), conn
     ii, jj, nn, nbr = connectivity_v2(means3D_t.detach(), K=K, radius=radius, ball_query=ball_query)
     return arap_energy(means3D_t, nbr), (ii, jj, nn, nbr)
 

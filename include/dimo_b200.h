@@ -174,6 +174,19 @@ int dimo_chamfer_fwd(int N, int M, const float* src, const float* tgt, float* d2
                      float* loss_acc, float lw, void* stream);
 int dimo_chamfer_bwd(int N, const float* src, const float* tgt, const int32_t* nn, const float* g_scalar,
                      float gw, float* d_src, float* d_tgt, void* stream);
+/* ARAP term (Renderer.arap_loss_v2, renderer/latent_gs_renderer.py:1081-1094; utils/deform_utils.py:115-232).
+ *   nodes [T,M,3] f32: frame 0 is the source, frames 1..T-1 the targets.
+ * connectivity: nbr [M,K] i64 (-1 padded, ascending) = vertices inside the ball of `radius` around i in EVERY frame
+ *   (per frame the first K+1 hits in index order, the first one dropped -- cal_connectivity_from_points_v2), count [M]
+ *   i32 (may be NULL).  K <= 15.
+ * energy: *energy = sum_t sum_i mult_i sum_k |(p^t_i - p^t_j) - R^t_i (p^0_i - p^0_j)|^2 with R the Kabsch rotation of
+ *   the vertex's edge fan (cal_arap_error with unit edge weights); mult [M] f32 = how often vertex i is in the
+ *   reference's random vertex sample (NULL = 1 each); grad [T,M,3] (may be NULL) = d energy / d nodes with R held
+ *   constant.  Both outputs are overwritten. */
+int dimo_arap_connectivity(int T, int M, int K, float radius, const float* nodes, int64_t* nbr, int32_t* count,
+                           void* stream);
+int dimo_arap_energy(int T, int M, int K, const float* nodes, const int64_t* nbr, const float* mult, float* energy,
+                     float* grad, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Deformation: positional encoding + TimeNet MLP (renderer/latent_gs_renderer.py:184-235,

@@ -297,7 +297,7 @@ def test_arap_loss_v2_against_oracle(cuda):
     with torch.no_grad():                                      # a live deformation (the reference init is the identity)
         g._timenet.pts_layers[-1].weight.normal_(0, 0.004)
     torch.manual_seed(5)
-    err, (ii, jj, nn, nbr) = r.arap_loss_v2(stage="s2", latent_index=1)
+    err, (ii, jj, nn, nbr) = r.arap_loss_v2(stage="s2", latent_index=1)      # fused kernels (CUDA tensors)
     err.backward()
     assert len(ii) > 50 and math.isfinite(err.item()) and err.item() > 0
     # oracle: same time samples, TimeNet + connectivity + energy on the CPU
@@ -379,3 +379,40 @@ def test_gt_cache_fetch_matches_interpolate(cuda, dtype):
     if dtype == torch.uint8:
         with pytest.raises(ValueError):
             cache.put(0, 0, 0, torch.full((1, 3, 96, 96), 0.123).cuda(), torch.zeros(1, 1, 96, 96).cuda())
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# fused ARAP kernels vs the torch formulation (same device) and the host build of the same source
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("T,M,spread", [(8, 512, 0.45), (4, 96, 0.22), (2, 7, 0.05), (1, 30, 0.2), (3, 1500, 0.6)])
+def test_arap_kernels_match_torch_formulation(cuda, T, M, spread):
+    from dimo_b200 import regularisers as reg
+    g = torch.Generator().manual_seed(T * 1000 + M)
+    base = (torch.rand(M, 3, generator=g) - 0.5) * 2 * spread
+    nodes = torch.stack([base + 0.004 * t * torch.randn(M, 3, generator=g) for t in range(T)])
+    if T > 2:
+        nodes[-1] = nodes[0]                                   # identical frame: the "unchanged vertex" rule, R = I
+    a = nodes.cuda().requires_grad_(True)
+    b = nodes.cuda().requires_grad_(True)
+    np.random.seed(5)
+    e_f, conn = reg.arap_loss_points(a, fused=True)
+    if T == 1:                                                   # no target frame: zero energy, zero gradient
+        assert e_f.item() == 0.0
+        e_f.backward()
+        assert float(a.grad.abs().max()) == 0.0
+        return
+    np.random.seed(5)
+    e_t, (ii, jj, nn, nbr) = reg.arap_loss_points(b, fused=False)
+    assert torch.equal(conn.nbr, nbr), "neighbour tables differ"
+    assert torch.equal(conn.count.long(), (nbr >= 0).sum(1))
+    fi, fj, fn, _ = conn                                         # unpacks like the reference's tuple
+    assert torch.equal(fi, ii) and torch.equal(fj, jj) and torch.equal(fn, nn)
+    scale = max(e_t.item(), 1e-12)
+    assert abs(e_f.item() - e_t.item()) <= 3e-5 * scale, (e_f.item(), e_t.item())
+    if T > 1 and e_t.item() > 0:
+        (2.5 * e_f).backward()
+        (2.5 * e_t).backward()
+        gs = float(b.grad.abs().max())
+        assert float((a.grad - b.grad).abs().max()) <= 2e-4 * gs
+    if M > 512:
+        assert int(conn.count.sum()) > 0                       # the sampled branch (np.random.choice) was exercised
