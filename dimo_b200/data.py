@@ -41,8 +41,12 @@ class GroundTruthCache:
         if both.shape[-2:] != (self.size, self.size):
             raise ValueError(f"frame is {tuple(both.shape[-2:])}, cache holds {self.size}x{self.size}")
         if self.dtype == torch.uint8 and both.dtype != torch.uint8:
-            q = torch.round(both.float() * 255.0)
-            if not torch.equal(q / 255.0, both.float()):
+            scaled = both.float() * 255.0
+            q = torch.round(scaled)
+            # byte / 255 * 255 is within an ulp of the byte; anything further off is not an 8-bit sample.  (Not tested as
+            # q / 255 == frame: torch's CUDA tensor / scalar multiplies by the reciprocal, which is not IEEE division;
+            # the kernel's own (float)byte / 255.0f is, like NumPy's in utils/load_utils.py:70.)
+            if float((scaled - q).abs().max()) > 1e-3:
                 raise ValueError("float frame is not byte / 255: use a float32 cache for it")
             both = q.to(torch.uint8)
         self.store[self.slot(motion, view, frame)].copy_(both.to(self.dtype), non_blocking=True)
