@@ -15,6 +15,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import deform as _deform
+from . import flags as _flags
 from . import knn as _knn
 from . import raster as _raster
 from . import regularisers as _reg
@@ -192,9 +193,9 @@ class Renderer:
                compute_cov3D_python=False, convert_SHs_python=False, time=0.0, stage="s1", rot_as_res=True,
                xyz_detach=False, local_frame=True, direct_deform=False, vertices_deform=None, latent_index=0):
         """Reference signature and result dict (renderer/latent_gs_renderer.py:1096-1293), one frame."""
-        if compute_cov3D_python or convert_SHs_python or not local_frame:
-            raise NotImplementedError("dimo_b200 render(): python-side cov3D / SH conversion and local_frame=False "
-                                      "are off the reference's default path")
+        if compute_cov3D_python and stage >= "s2":
+            # the reference itself cannot do this: it leaves rotations = None and then calls quat_mul(rots3D, None) (:1209)
+            raise ValueError("compute_cov3D_python=True is only defined for stage 's1' (as in the reference)")
         g = self.gaussians
         dev = g._xyz.device
         screenspace_points = torch.zeros_like(g._xyz, requires_grad=True) + 0
@@ -207,8 +208,12 @@ class Renderer:
         if stage >= "s2":
             dxyz, dquat = g._timenet.forward_batched(g._c_xyz, t_dev, latents)
             cpts_t = g._c_xyz + dxyz[0]
-            means3D, rotations = _deform.lbs_deform(g._xyz, g._rotation, g._c_xyz, g._c_radius, dxyz[0], dquat[0],
-                                                    g.neighbor_indices, g.neighbor_dists)
+            if local_frame:
+                means3D, rotations = _deform.lbs_deform(g._xyz, g._rotation, g._c_xyz, g._c_radius, dxyz[0], dquat[0],
+                                                        g.neighbor_indices, g.neighbor_dists)
+            else:                                          # off-default flag: tensor expressions (flags.py)
+                means3D, rotations = _flags.lbs_global_frame(g._xyz, g._rotation, g.get_c_radius(stage), dxyz[0],
+                                                             dquat[0], g.neighbor_indices, g.neighbor_dists)
         elif stage == "s1":
             dxyz, dquat = g._timenet.forward_batched(g._xyz, t_dev, latents)
             cpts_t = g._xyz + dxyz[0]
@@ -224,9 +229,15 @@ class Renderer:
                                     math.tan(viewpoint_camera.FoVy * 0.5), bg)
         shs = colors = None
         if override_color is None:
-            shs = g.get_features
+            if convert_SHs_python:                         # off-default flag (:1227-1238): colours from the CANONICAL centres
+                colors = _flags.sh_colors(g.active_sh_degree, g.get_features, g.get_xyz, viewpoint_camera.camera_center)
+            else:
+                shs = g.get_features
         else:
             colors = override_color
+        # compute_cov3D_python (stage s1 only): the reference's precomputed covariance R (m s)^2 R^T from the canonical
+        # rotations is what the kernel builds from (scales, rotations, scale_modifier) -- in s1 `rotations` ARE the
+        # canonical ones, so the flag needs no separate path
         color, depth, normal, alpha, radii = _raster.rasterize_batch(
             cams, means3D, g.get_scaling, rotations, g.get_opacity, int(viewpoint_camera.image_width),
             int(viewpoint_camera.image_height), shs=shs, colors_precomp=colors, sh_degree=g.active_sh_degree,
