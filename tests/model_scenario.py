@@ -157,6 +157,23 @@ def run(renderer_cls, init_kwargs=None, setup_kwargs=None, schedule_fn=None):
     rec["geom/smallest_axis"] = _np(g2.get_smallest_axis())
     rec["geom/normal"] = _np(g2.get_normal(cam))
     rec["geom/rotmat"] = _np(g2.get_rotation_matrix())
+
+    # ---- end of stage s1 (main_train_dimo.py:199-201): key points pruned together with their Gaussians ----
+    np.random.seed(13)
+    torch.manual_seed(13)
+    r3 = renderer_cls(sh_degree=0, white_background=True, num_latent_code=2, latent_code_dim=32)
+    g3 = r3.gaussians
+    r3.initialize(num_pts=48, num_cpts=48, radius=0.5, radius2=0.5, **init_kwargs)
+    g3._c_radius = torch.nn.Parameter(g3._c_radius.detach().clone())
+    g3.training_setup(train_args(), **setup_kwargs)
+    for it in range(2):
+        fake_backward(g3, gen, scale=0.01)
+        g3.optimizer.step()
+        g3.optimizer.zero_grad()
+    with torch.no_grad():
+        g3._opacity.data[::4] = -7.0
+    g3.prune_s1_end(min_opacity=0.01, extent=4, max_screen_size=1)
+    snapshot(g3, rec, "s1_end")
     return rec
 
 
