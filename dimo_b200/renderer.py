@@ -11,12 +11,10 @@ import math
 
 import numpy as np
 import torch
-import torch.nn as nn
 import torch.nn.functional as F
 
 from . import deform as _deform
 from . import flags as _flags
-from . import knn as _knn
 from . import raster as _raster
 from . import regularisers as _reg
 from .camera import MiniCam  # noqa: F401  (re-export: the reference imports MiniCam from the renderer module)

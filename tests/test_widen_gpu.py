@@ -2,7 +2,6 @@
 through the C ABI, the GaussianModel life cycle on the fused optimizer (flat re-layout after densify / prune) against
 the same life on torch.optim.Adam, a training step that survives a change of N, and the pytorch3d / chamferdist
 shims at the reference's call sites."""
-import functools
 import math
 import os
 import sys

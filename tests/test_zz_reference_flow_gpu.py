@@ -7,7 +7,6 @@ class surface.  It checks that the surface composes on the GPU
 numerics of every piece are checked in the other test files."""
 import math
 import os
-import types
 
 import numpy as np
 import pytest
