@@ -135,8 +135,8 @@ def test_flat_relayout_follows_reference_surgery(host_fused):
         assert all(b % 4 == 0 for b in gf.optimizer._seg_begin)
     assert sizes[0] == 600 and sizes[1] != 600 and sizes[4] == 100
     assert int(gf.optimizer.state[0]) == 8
-    # densify_and_prune = clone + split (append, prune) + prune: each is one re-layout; prune, index prune, reset: one each
-    assert len(relayouts) >= 5
+    # densify_and_prune (append, append, prune, prune), prune, index prune, reset: ONE re-layout each
+    assert len(relayouts) == 4, relayouts
 
 
 def test_popped_group_keeps_other_rates(host_fused):
