@@ -5,8 +5,9 @@ ctypes; PyTorch only owns memory/streams/autograd plumbing.  There is no CPU fal
 here imports ``oracle``.
 
 ``install_shims()`` puts drop-in modules named exactly as the reference imports them
-(diff_gauss, diff_gaussian_rasterization, knn_cuda, simple_knn, fused_ssim) on sys.path, so
-main_train_dimo.py / main_test_dimo.py run unmodified.
+(diff_gauss, diff_gaussian_rasterization, knn_cuda, simple_knn, fused_ssim, plus the slices of pytorch3d,
+chamferdist and plyfile the path calls) on sys.path, so the reference's renderer / deform_utils modules import and
+run unmodified.
 """
 import os
 import sys
