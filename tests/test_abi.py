@@ -56,3 +56,38 @@ def test_no_cpu_fallback():
     from dimo_b200 import knn
     with pytest.raises(RuntimeError):
         knn.knn(torch.rand(8, 3), torch.rand(5, 3), 4)
+
+
+def test_shim_modules_expose_the_names_the_reference_imports():
+    """Every import statement of the reference that the shim directory serves resolves on a
+    machine without a GPU, and the new ops refuse CPU tensors like the rest of the product."""
+    import pytest
+    import torch
+    import dimo_b200
+    dimo_b200.install_shims()
+    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer        # noqa: F401
+    from diff_gauss import GaussianRasterizationSettings as S2, GaussianRasterizer as R2             # noqa: F401
+    from simple_knn._C import distCUDA2                                                               # noqa: F401
+    from knn_cuda import KNN                                                                          # noqa: F401
+    from fused_ssim import fused_ssim                                                                 # noqa: F401
+    from plyfile import PlyData, PlyElement                                                           # noqa: F401
+    from chamferdist import ChamferDistance
+    from pytorch3d.loss.mesh_laplacian_smoothing import cot_laplacian
+    from pytorch3d.ops import ball_query
+    from pytorch3d.io import load_ply                                                                 # noqa: F401
+    import pytorch3d.ops as ops
+    from pytorch3d.transforms import quaternion_to_matrix
+    assert S2._fields == GaussianRasterizationSettings._fields and len(S2._fields) == 12
+    q = torch.tensor([[0.5, -0.5, 0.5, 0.5], [2.0, 0.0, 0.0, 0.0]])
+    R = quaternion_to_matrix(q)
+    assert torch.allclose(R @ R.transpose(1, 2), torch.eye(3).expand(2, 3, 3), atol=1e-6)        # scale-free, like pytorch3d
+    assert torch.allclose(R[1], torch.eye(3))
+    pts = torch.rand(1, 20, 3)
+    for call in (lambda: ops.sample_farthest_points(points=pts, K=4), lambda: ball_query(pts, pts, K=3, radius=0.1),
+                 lambda: ChamferDistance()(pts, pts)):
+        with pytest.raises(RuntimeError):
+            call()                                                   # CUDA-only product: no silent CPU path
+    with pytest.raises(NotImplementedError):
+        cot_laplacian()
+    with pytest.raises(NotImplementedError):
+        ops.sample_farthest_points(points=pts, K=4, random_start_point=True)
