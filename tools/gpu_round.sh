@@ -12,6 +12,8 @@ echo "pytest exit $?" >> $OUT/${TAG}_pytest.log
 tail -3 $OUT/${TAG}_pytest.log
 timeout 400 python bench.py --steps 20 --warmup 3 > $OUT/${TAG}_bench.log 2> $OUT/${TAG}_bench.err
 tail -c 3000 $OUT/${TAG}_bench.log
+# rows widened from SURVEY 8f: CUDA-event medians (gt fetch GB/s, ARAP fused vs torch formulation, FPS, chamfer, densify)
+timeout 120 python tools/widen_bench.py > $OUT/${TAG}_widen_bench.jsonl 2> $OUT/${TAG}_widen_bench.err
 if [ "${SKIP_NCU:-0}" != "1" ]; then
   timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
       --log-file $OUT/${TAG}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-graph \
