@@ -20,7 +20,7 @@ if [ "${SKIP_NCU:-0}" != "1" ]; then
       > $OUT/${TAG}_launches_run.log 2>&1
   # skip the probe/warm-up steps, then capture one eager step's worth of our kernels
   timeout 400 ncu --set full --clock-control none --import-source on \
-      -k regex:"${NCU_KERNELS:-blend|ssim|preprocess|lbs_|emit_keys|adam}" --launch-skip ${NCU_SKIP:-40} -c ${NCU_COUNT:-14} \
+      -k regex:"${NCU_KERNELS:-blend|ssim|preprocess|lbs_|emit_keys|adam|gt_fetch|arap_|fps_kernel}" --launch-skip ${NCU_SKIP:-40} -c ${NCU_COUNT:-14} \
       -f -o $OUT/${TAG}_top python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-graph \
       > $OUT/${TAG}_ncu_run.log 2>&1
   ls -la $OUT | tail -12
