@@ -126,3 +126,49 @@ def test_rotation_fit_against_svd(host):
         assert abs(np.linalg.det(R) - 1) < 1e-9
         assert np.abs(R @ (a / np.linalg.norm(a)) - b / np.linalg.norm(b)).max() < 1e-7
     assert np.array_equal(fit(np.zeros((3, 3))), np.eye(3))
+
+
+def test_connectivity_host_build_vs_reference_shaped_oracle_random(host):
+    """Random clouds, densities from 'almost no neighbours' to 'more than K in the ball' (lists truncated at K + 1 hits),
+    T from 1 to 6: the kernels' connectivity source (host build) against the oracle written in the reference's own
+    shape (one_hot / any / all / topk, oracle/points.py::arap_connectivity_v2)."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.integers(1, 6), st.integers(12, 90), st.floats(0.08, 0.5), st.integers(0, 2 ** 31 - 1))
+    def check(T, M, spread, seed):
+        g = torch.Generator().manual_seed(seed)
+        base = (torch.rand(M, 3, generator=g) - 0.5) * 2 * spread
+        nodes = torch.stack([base + 0.01 * torch.randn(M, 3, generator=g) for _ in range(T)])
+        nbr, cnt = _connectivity(host, nodes.numpy())
+        ii, jj, _nn = opoints.arap_connectivity_v2(nodes)
+        want = sorted(zip(ii.tolist(), jj.tolist()))
+        got = sorted((i, int(j)) for i in range(M) for j in nbr[i] if j >= 0)
+        assert got == want
+        assert all(list(nbr[i][:cnt[i]]) == sorted(nbr[i][:cnt[i]]) and (nbr[i][cnt[i]:] == -1).all() for i in range(M))
+
+    check()
+
+
+def test_energy_host_build_vs_reference_shaped_oracle_random(host):
+    """Energy and gradient of the kernels' source against the oracle in the reference's shape (edge triplets, one SVD
+    per frame, torch.svd + reflection fix) on random clouds."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=25, deadline=None)
+    @given(st.integers(2, 5), st.integers(12, 70), st.floats(0.1, 0.3), st.integers(0, 2 ** 31 - 1))
+    def check(T, M, spread, seed):
+        g = torch.Generator().manual_seed(seed)
+        base = (torch.rand(M, 3, generator=g) - 0.5) * 2 * spread
+        nodes = torch.stack([base + 0.01 * t * torch.randn(M, 3, generator=g) for t in range(T)]).requires_grad_(True)
+        ii, jj, nn = opoints.arap_connectivity_v2(nodes.detach())
+        want = opoints.arap_error(nodes, ii, jj, nn)
+        nbr, _ = _connectivity(host, nodes.detach().numpy())
+        e, grad = _energy(host, nodes.detach().numpy(), nbr)
+        scale = max(want.item(), 1e-10)
+        assert abs(e - want.item()) <= 1e-4 * scale
+        if len(ii) and want.item() > 1e-8:
+            (gw,) = torch.autograd.grad(want, nodes)
+            assert np.abs(grad - gw.numpy()).max() <= 2e-3 * float(gw.abs().max())
+
+    check()
