@@ -134,7 +134,7 @@ def test_connectivity_host_build_vs_reference_shaped_oracle_random(host):
     shape (one_hot / any / all / topk, oracle/points.py::arap_connectivity_v2)."""
     from hypothesis import given, settings, strategies as st
 
-    @settings(max_examples=40, deadline=None)
+    @settings(max_examples=40, deadline=None, derandomize=True, database=None)
     @given(st.integers(1, 6), st.integers(12, 90), st.floats(0.08, 0.5), st.integers(0, 2 ** 31 - 1))
     def check(T, M, spread, seed):
         g = torch.Generator().manual_seed(seed)
@@ -155,7 +155,7 @@ def test_energy_host_build_vs_reference_shaped_oracle_random(host):
     per frame, torch.svd + reflection fix) on random clouds."""
     from hypothesis import given, settings, strategies as st
 
-    @settings(max_examples=25, deadline=None)
+    @settings(max_examples=25, deadline=None, derandomize=True, database=None)
     @given(st.integers(2, 5), st.integers(12, 70), st.floats(0.1, 0.3), st.integers(0, 2 ** 31 - 1))
     def check(T, M, spread, seed):
         g = torch.Generator().manual_seed(seed)

@@ -28,7 +28,7 @@ def tables(draw):
     return arr
 
 
-@settings(max_examples=60, deadline=None)
+@settings(max_examples=60, deadline=None, derandomize=True, database=None)
 @given(tables())
 def test_binary_little_endian_round_trip(arr):
     buf = io.BytesIO()
@@ -39,7 +39,7 @@ def test_binary_little_endian_round_trip(arr):
         assert np.array_equal(back[n], arr[n]), n
 
 
-@settings(max_examples=40, deadline=None)
+@settings(max_examples=40, deadline=None, derandomize=True, database=None)
 @given(tables())
 def test_big_endian_and_ascii_files_read_back(arr):
     header = ["ply", "format {} 1.0", "comment hypothesis", f"element vertex {arr.shape[0]}"]
