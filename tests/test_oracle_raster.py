@@ -120,3 +120,55 @@ def test_knn_oracle_basic():
     assert torch.allclose(d[0], torch.tensor([0.1, 0.1, 0.9, math.sqrt(0.81 + 4)]))
     pts = torch.tensor([[0., 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [5, 5, 5]])
     assert torch.allclose(oknn.dist3nn(pts)[0], torch.tensor(1.0))
+
+
+def test_ewa_covariance_against_the_true_projection():
+    """The screen-space covariance the oracle derives in closed form (J W Sigma W^T J^T + 0.3 I) against two derivations
+    that never touch that formula: (a) the numerical Jacobian of the exact world -> pixel mapping given by the
+    camera matrices, (b) the sample covariance of points drawn from the 3-D Gaussian and projected exactly."""
+    import numpy as np
+    W, H = 96, 64
+    cam = _cam(W, H, view=3)
+    g = torch.Generator().manual_seed(0)
+    n = 12
+    xyz = (torch.rand(n, 3, generator=g, dtype=torch.float64) - 0.5) * 0.6
+    scales = torch.rand(n, 3, generator=g, dtype=torch.float64) * 0.02 + 0.004
+    q = torch.nn.functional.normalize(torch.randn(n, 4, generator=g, dtype=torch.float64))
+    pre = orast.preprocess(xyz, scales, q, torch.ones(n, dtype=torch.float64), cam.world_view_transform.double(),
+                           cam.full_proj_transform.double(), cam.camera_center.double(), cam.tanfovx, cam.tanfovy, W, H,
+                           colors_precomp=torch.zeros(n, 3, dtype=torch.float64))
+    P = cam.full_proj_transform.double().numpy()
+
+    def pixel(p):                                     # exact mapping: row vector times full projection, NDC -> pixel
+        h = np.concatenate([p, np.ones_like(p[..., :1])], axis=-1) @ P
+        ndc = h[..., :2] / h[..., 3:4]
+        return ((ndc + 1.0) * np.array([W, H]) - 1.0) * 0.5
+
+    w, x, y, z = q.numpy().T
+    R = np.stack([np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)], -1),
+                  np.stack([2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)], -1),
+                  np.stack([2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)], -1)], 1)
+    S3 = R @ np.stack([np.diag(s ** 2) for s in scales.numpy()]) @ R.transpose(0, 2, 1)
+    cov = pre["cov2d"].numpy()
+    rng = np.random.default_rng(0)
+    for i in range(n):
+        p = xyz[i].numpy()
+        assert np.abs(pixel(p) - pre["xy"][i].numpy()).max() < 1e-5        # the oracle divides by (w + 1e-7)
+        eps = 1e-6
+        J = np.stack([(pixel(p + eps * e) - pixel(p - eps * e)) / (2 * eps) for e in np.eye(3)], axis=1)   # [2,3]
+        C = J @ S3[i] @ J.T
+        got = np.array([[cov[i, 0] - orast.DILATION, cov[i, 1]], [cov[i, 1], cov[i, 2] - orast.DILATION]])
+        assert np.abs(got - C).max() <= 1e-6 * np.abs(C).max(), i
+        samples = rng.multivariate_normal(p, S3[i], size=200_000)
+        Cs = np.cov(pixel(samples).T)
+        assert np.abs(Cs - C).max() <= 0.03 * np.abs(C).max(), i              # Monte Carlo + second-order terms
+    # conic = inverse of the dilated covariance; radius = ceil(3 sigma_max)
+    for i in range(n):
+        A = np.array([[cov[i, 0], cov[i, 1]], [cov[i, 1], cov[i, 2]]])
+        inv = np.linalg.inv(A)
+        assert np.allclose([inv[0, 0], inv[0, 1], inv[1, 1]], pre["conic"][i].numpy(), rtol=1e-9)
+        # published rule: lambda_max = mid + sqrt(max(0.1, mid^2 - det)) -- the floor widens nearly isotropic footprints
+        mid, det = 0.5 * (A[0, 0] + A[1, 1]), np.linalg.det(A)
+        lam = mid + np.sqrt(max(orast.LAMBDA_FLOOR, mid * mid - det))
+        assert lam >= np.linalg.eigvalsh(A).max() - 1e-12
+        assert int(pre["radii"][i]) == int(np.ceil(orast.RADIUS_SIGMAS * np.sqrt(lam)))
