@@ -71,13 +71,17 @@ def timenet_init(latent_dim=32, seed=0, dtype=torch.float32, final_scale=None):
     return [(W, b) for W, b in params]
 
 
-def timenet_forward(params, pts, t, latent, return_kink_distance=False):
+def timenet_forward(params, pts, t, latent, return_kink_distance=False, masks_in=None, masks_out=None):
     """TimeNet.forward, renderer/latent_gs_renderer.py:205-235, on flat rows.
 
     pts [R,3], t [R,1] (or python float), latent [R,L] (or [L]) -> (dxyz [R,3], dquat [R,4]).
     return_kink_distance: also return, per row, min |pre-activation| / max |pre-activation| over all ReLU
     inputs -- rows where it is ~1e-6 sit on a ReLU kink, where the gradient is discontinuous and two
     floating-point evaluations can legitimately disagree (used by the parity tests to mask such rows).
+    masks_out: a list that receives, per ReLU layer (deformnet.0..7, pts_layers.0, rot_layers.0), the tuple
+    (pre-activation z, z > 0).  masks_in: a list of ten boolean [R, 256] tensors -- the ReLU of layer i becomes
+    z * masks_in[i], i.e. the network is evaluated on the linear piece selected by a GIVEN activation pattern (the one
+    the CUDA forward chose); with the pattern fixed, the function is smooth and every row's gradient is comparable.
     """
     R = pts.shape[0]
     if not torch.is_tensor(t):
@@ -96,8 +100,15 @@ def timenet_forward(params, pts, t, latent, return_kink_distance=False):
             with torch.no_grad():
                 d = z.abs().min(dim=-1).values / z.abs().max().clamp_min(1e-30)
                 kink = d if kink is None else torch.minimum(kink, d)
+        if masks_out is not None:
+            masks_out.append((z.detach(), z.detach() > 0))
+        if masks_in is not None:
+            m = masks_in[len(used)]
+            used.append(1)
+            return z * m.to(z.dtype)
         return F.relu(z)
 
+    used = []
     for i in range(DEPTH):
         W, b = params[i]
         h = relu_layer(h, W, b)

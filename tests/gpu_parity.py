@@ -124,10 +124,41 @@ def compare_raster(o, c, verbose=True):
     return ints, flo, gr
 
 
-def run_step_pair(N=1500, M=32, W=64, H=64, device="cuda", regularisers=False):
+def l2_err(a, ref):
+    """||a - ref||_2 / ||ref||_2 over the whole tensor (second metric next to rel_err: insensitive to one large entry
+    setting the scale, sensitive to many small entries being wrong)."""
+    a = a.detach().double().cpu(); ref = ref.detach().double().cpu()
+    return ((a - ref).norm() / ref.norm().clamp_min(1e-30)).item()
+
+
+def entry_outlier_frac(a, ref, rtol=1e-4, atol_scale=1e-6):
+    """fraction of entries with |a - ref| > rtol * |ref| + atol_scale * max|ref| (per-entry relative error with an
+    absolute floor for the near-zero entries)"""
+    a = a.detach().double().cpu(); ref = ref.detach().double().cpu()
+    scale = max(ref.abs().max().item(), 1e-30)
+    return ((a - ref).abs() > rtol * ref.abs() + atol_scale * scale).double().mean().item()
+
+
+def cuda_relu_masks(capture):
+    """dimo_b200.deform.DEBUG_CAPTURE entry -> the ten activation patterns [R,256] (bool) in the oracle's ReLU order:
+    deformnet.0..7, pts_layers.0, rot_layers.0"""
+    cat, hp, hr, *acts = capture
+    E = cat.shape[1] - odeform.HIDDEN
+    trunk = acts[:odeform.SKIP_AFTER] + [cat[:, E:]] + acts[odeform.SKIP_AFTER:]
+    return [(t > 0).cpu() for t in trunk + [hp, hr]]
+
+
+def run_step_pair(N=1500, M=32, W=64, H=64, device="cuda", regularisers=False, force_masks=True):
     """One full deform -> raster -> loss step (4 frames: 2 motions x 1 view x 2 times) on the CUDA fast path and on the
-    oracle, same seeded inputs.  Returns (loss_cuda, loss_oracle, grads_cuda, grads_oracle) for a few parameters."""
-    from dimo_b200 import trainstep
+    oracle, same seeded inputs.  Returns (loss_cuda, loss_oracle, grads_cuda, grads_oracle, mask_stats): gradients of
+    EVERY parameter on the path (Gaussian attributes, control points, latents, all 24 TimeNet tensors).
+
+    force_masks: the oracle's TimeNet is evaluated on the activation pattern the CUDA forward chose (exported ReLU
+    masks), so a pre-activation that the two evaluations round to different sides of zero does not turn into a
+    whole-row gradient difference; mask_stats reports how many of the R*2560 signs differ between the oracle's own
+    pattern and the CUDA one and how far from zero (relative to the layer's scale) the oracle's pre-activation is at
+    those places -- a genuine kink flip has |z| ~ 1e-6 * scale, anything larger is a bug."""
+    from dimo_b200 import trainstep, deform as ddeform
     from dimo_b200.renderer import Renderer
     from oracle import loss as oloss, knn as oknn
     sc = synthetic.make_scene(N, n_ctrl=M, n_motions=2, seed=11)
@@ -137,21 +168,67 @@ def run_step_pair(N=1500, M=32, W=64, H=64, device="cuda", regularisers=False):
     gt = torch.rand(4, 3, H, W, generator=g); mk = torch.rand(4, 1, H, W, generator=g)
     lw = trainstep.StepLossWeights
 
+    # ---- CUDA fast path (eager TrainStep, no optimizer update) ----
+    r = Renderer(sh_degree=0, num_latent_code=2, add_normal=True, device=device)
+    r.gaussians.load_state(sc)
+    tn = r.gaussians._timenet
+    with torch.no_grad():
+        for p_pair, (Wt, b) in zip(zip(tn.flat_params()[0::2], tn.flat_params()[1::2]), params):
+            p_pair[0].copy_(Wt); p_pair[1].copy_(b)
+    ts = trainstep.TrainStep(r, lr=0.0)
+    cams = [orbit_minicam(v, 4, W, H, device=device) for (_, v, _) in frames]
+    prep = r.prepare_step(cams, [t for (_, _, t) in frames], [m for (m, _, _) in frames])
+    ts.g.find_knn(4)
+    ddeform.DEBUG_CAPTURE = []
+    try:
+        out = r.render_batch(prepared=prep, stage="s2", clamp=False)
+        capture = ddeform.DEBUG_CAPTURE[0]
+    finally:
+        ddeform.DEBUG_CAPTURE = None
+    lc = trainstep.step_loss(out["image_raw"], out["alpha"], gt.to(device), mk.to(device), 2)
+    if regularisers:
+        from dimo_b200 import loss as dloss
+        lc = lc + dloss.smoothness_losses(out["image_raw"], out["depth"], out["normal"], groups=2,
+                                          lambda_smooth=lw.lambda_smooth, lambda_bilateral=lw.lambda_bilateral,
+                                          clamp01=True)
+    lc.backward()
+    torch.cuda.synchronize()
+    G = r.gaussians
+    gc = {"xyz": G._xyz.grad, "features_dc": G._features_dc.grad, "opacity": G._opacity.grad,
+          "scaling": G._scaling.grad, "rotation": G._rotation.grad, "c_xyz": G._c_xyz.grad,
+          "c_radius": G._c_radius.grad, "latents": G._latent_codes.grad}
+    for li, (pw, pb) in enumerate(zip(tn.flat_params()[0::2], tn.flat_params()[1::2])):
+        gc[f"W{li}"] = pw.grad; gc[f"b{li}"] = pb.grad
+    gc = {k: v.detach().clone() for k, v in gc.items()}
+    masks = cuda_relu_masks(capture)                       # rows ordered [pair][control point]
+    pair_of_frame = prep["pair_of_frame"]
+
     # ---- oracle ----
     leaves = {k: v.clone().requires_grad_(True) for k, v in sc.items()}
     op = [(Wt.clone().requires_grad_(True), b.clone().requires_grad_(True)) for Wt, b in params]
     dist, idx = oknn.knn(sc["_c_xyz"], sc["_xyz"], 4)
     imgs, alphas, depths, normals = [], [], [], []
-    for (m, v, t) in frames:
+    n_signs = n_flip = 0
+    worst_flip = 0.0
+    for f, (m, v, t) in enumerate(frames):
         cam = ocamera.orbit_cam(v, 4, W, H)
-        dxyz, dquat = odeform.timenet_forward(op, leaves["_c_xyz"], t, leaves["_latent_codes"][m])
+        rows = slice(pair_of_frame[f] * M, (pair_of_frame[f] + 1) * M)
+        own = []
+        dxyz, dquat = odeform.timenet_forward(op, leaves["_c_xyz"], t, leaves["_latent_codes"][m],
+                                              masks_in=[mm[rows] for mm in masks] if force_masks else None,
+                                              masks_out=own)
+        for (z, pos), mm in zip(own, masks):
+            diff = pos != mm[rows]
+            n_signs += pos.numel(); n_flip += int(diff.sum())
+            if bool(diff.any()):
+                worst_flip = max(worst_flip, float(z[diff].abs().max() / z.abs().max()))
         means, rots = odeform.lbs_deform(leaves["_xyz"], leaves["_rotation"], leaves["_c_xyz"],
                                          torch.exp(leaves["_c_radius"]), dxyz, dquat, idx, dist)
-        out = oraster.rasterize(means, torch.exp(leaves["_scaling"]), rots, torch.sigmoid(leaves["_opacity"]),
-                                cam.world_view_transform, cam.full_proj_transform, cam.camera_center, cam.tanfovx,
-                                cam.tanfovy, W, H, torch.ones(3), shs=torch.cat([leaves["_features_dc"], leaves["_features_rest"]], 1))
-        imgs.append(out["image"].clamp(0, 1)); alphas.append(out["alpha"])
-        depths.append(out["depth"]); normals.append(out["normal"])
+        o = oraster.rasterize(means, torch.exp(leaves["_scaling"]), rots, torch.sigmoid(leaves["_opacity"]),
+                              cam.world_view_transform, cam.full_proj_transform, cam.camera_center, cam.tanfovx,
+                              cam.tanfovy, W, H, torch.ones(3), shs=torch.cat([leaves["_features_dc"], leaves["_features_rest"]], 1))
+        imgs.append(o["image"].clamp(0, 1)); alphas.append(o["alpha"])
+        depths.append(o["depth"]); normals.append(o["normal"])
     img = torch.stack(imgs); alp = torch.stack(alphas)
     dep = torch.stack(depths); nrm = torch.stack(normals)
     lo = 0
@@ -164,31 +241,13 @@ def run_step_pair(N=1500, M=32, W=64, H=64, device="cuda", regularisers=False):
             lo = lo + lw.lambda_smooth * oloss.edge_aware_smoothness(dep[sl], img[sl]) + \
                 lw.lambda_bilateral * oloss.bilateral_normal_smoothness(nrm[sl], img[sl])
     lo.backward()
-
-    # ---- CUDA fast path (eager TrainStep, no optimizer update) ----
-    r = Renderer(sh_degree=0, num_latent_code=2, add_normal=True, device=device)
-    r.gaussians.load_state(sc)
-    with torch.no_grad():
-        for p_pair, (Wt, b) in zip(zip(r.gaussians._timenet.flat_params()[0::2], r.gaussians._timenet.flat_params()[1::2]), params):
-            p_pair[0].copy_(Wt); p_pair[1].copy_(b)
-    ts = trainstep.TrainStep(r, lr=0.0)
-    cams = [orbit_minicam(v, 4, W, H, device=device) for (_, v, _) in frames]
-    prep = r.prepare_step(cams, [t for (_, _, t) in frames], [m for (m, _, _) in frames])
-    ts.g.find_knn(4)
-    out = r.render_batch(prepared=prep, stage="s2", clamp=False)
-    lc = trainstep.step_loss(out["image_raw"], out["alpha"], gt.to(device), mk.to(device), 2)
-    if regularisers:
-        from dimo_b200 import loss as dloss
-        lc = lc + dloss.smoothness_losses(out["image_raw"], out["depth"], out["normal"], groups=2,
-                                          lambda_smooth=lw.lambda_smooth, lambda_bilateral=lw.lambda_bilateral,
-                                          clamp01=True)
-    lc.backward()
-    torch.cuda.synchronize()
-    gc = {"xyz": r.gaussians._xyz.grad, "opacity": r.gaussians._opacity.grad, "c_xyz": r.gaussians._c_xyz.grad,
-          "latents": r.gaussians._latent_codes.grad, "W0": r.gaussians._timenet.deformnet[0].weight.grad}
-    go = {"xyz": leaves["_xyz"].grad, "opacity": leaves["_opacity"].grad, "c_xyz": leaves["_c_xyz"].grad,
-          "latents": leaves["_latent_codes"].grad, "W0": op[0][0].grad}
-    return float(lc), float(lo), gc, go
+    go = {"xyz": leaves["_xyz"].grad, "features_dc": leaves["_features_dc"].grad, "opacity": leaves["_opacity"].grad,
+          "scaling": leaves["_scaling"].grad, "rotation": leaves["_rotation"].grad, "c_xyz": leaves["_c_xyz"].grad,
+          "c_radius": leaves["_c_radius"].grad, "latents": leaves["_latent_codes"].grad}
+    for li, (Wt, b) in enumerate(op):
+        go[f"W{li}"] = Wt.grad; go[f"b{li}"] = b.grad
+    stats = {"signs": n_signs, "flips": n_flip, "worst_flip_rel_z": worst_flip}
+    return float(lc), float(lo), gc, go, stats
 
 
 def smoke():
@@ -197,6 +256,6 @@ def smoke():
     assert all(v == 0 for v in ints.values()), ints
     assert all(flo[k] < PIX_TOL for k in ("image", "depth", "normal", "alpha")), flo
     assert all(v < 5 * GRAD_TOL for v in gr.values()), gr
-    lc, lo, gc, go = run_step_pair()
-    print(f"full step: loss cuda {lc:.6f} oracle {lo:.6f}")
+    lc, lo, gc, go, stats = run_step_pair()
+    print(f"full step: loss cuda {lc:.6f} oracle {lo:.6f}; ReLU pattern {stats}")
     assert abs(lc - lo) <= 1e-4 * abs(lo), (lc, lo)

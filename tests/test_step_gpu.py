@@ -100,7 +100,7 @@ def test_full_step_matches_oracle(cuda, regularisers):
     (autograd through the whole oracle chain).  regularisers: + the depth / normal smoothness terms of the real step
     (main_train_dimo.py:363-372), which also exercises the depth / normal gradient path of the rasteriser."""
     import gpu_parity as gp
-    lc, lo, gc, go = gp.run_step_pair(regularisers=regularisers)
+    lc, lo, gc, go, stats = gp.run_step_pair(regularisers=regularisers)
     assert abs(lc - lo) <= 1e-4 * abs(lo), (lc, lo)
     for k in gc:
         # ReLU-kink flips (DESIGN.md section 2) can move MLP-side gradients by ~1/sqrt(rows); Gaussian-side ones are tight
