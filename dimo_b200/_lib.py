@@ -52,7 +52,7 @@ _SIGS = {
     "dimo_smooth_bwd": (c_int, [c_int] * 4 + [c_vp] * 3 + [c_f32] * 4 + [c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
     "dimo_segment_sum": (c_int, [c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "dimo_sqdiff_sum": (c_int, [c_i64] + [c_vp] * 4 + [c_f32, c_vp]),
-    "dimo_adam_step": (c_int, [c_i64] + [c_vp] * 4 + [c_int, c_vp, c_vp, c_f64, c_f64, c_f32, c_int, c_vp, c_vp]),
+    "dimo_adam_step": (c_int, [c_i64] + [c_vp] * 4 + [c_int, c_vp, c_vp, c_f64, c_f64, c_f32, c_int, c_vp, c_vp, c_vp]),
     "dimo_transpose_grouped": (c_int, [c_int] + [c_vp] * 5),
     "dimo_gt_fetch": (c_int, [c_int] * 6 + [c_vp] * 5),
 }

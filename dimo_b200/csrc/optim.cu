@@ -28,13 +28,18 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_kernel(int64_t n4, float4* 
                                                             float4* __restrict__ m, float4* __restrict__ v,
                                                             const float* __restrict__ seg_lr, AdamSegs segs,
                                                             double beta1d, double beta2d, float eps,
-                                                            int zero_grads, int* __restrict__ state) {
+                                                            int zero_grads, int* __restrict__ state,
+                                                            const float* __restrict__ skip_flag) {
   __shared__ int64_t s_begin[ADAM_MAX_SEGS + 1];
   __shared__ float s_lr[ADAM_MAX_SEGS];
   __shared__ float s_bc[2];
   for (int i = threadIdx.x; i <= segs.n; i += ADAM_THREADS) s_begin[i] = segs.begin[i];
   for (int i = threadIdx.x; i < segs.n; i += ADAM_THREADS) s_lr[i] = seg_lr[i];
   const int t = state[0] + 1;
+  // skip_flag (device float, may be NULL; lives OUTSIDE the buffers this kernel writes): non-zero = the step that
+  // produced these gradients dropped work (the rasteriser's instance capacity overflowed on some rank) -> no update,
+  // the step counter stays, the gradients are still cleared, state[3] counts the skipped steps
+  const bool skip = skip_flag != nullptr && skip_flag[0] != 0.f;
   if (threadIdx.x == 0) {
     // bias corrections in double, as torch.optim.Adam forms them on the host (1 - beta ** step): float(0.999) alone
     // is already 1.3e-5 (relative) away from 1 - 0.999 at step 1.  One thread per CTA, two pow() calls.
@@ -50,6 +55,10 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_kernel(int64_t n4, float4* 
     const int64_t e = i * 4;
     // segments are few and a thread walks the buffer monotonically: advance linearly
     while (seg + 1 < segs.n && e >= s_begin[seg + 1]) ++seg;
+    if (skip) {
+      if (zero_grads) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      continue;
+    }
     const float step_size = s_lr[seg] * inv_bc1;
     float4 P = p[i], G = g[i], M = m[i], V = v[i];
     float* pp = &P.x; float* gp = &G.x; float* mp = &M.x; float* vp = &V.x;
@@ -70,7 +79,7 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_kernel(int64_t n4, float4* 
     __threadfence();
     const int ticket = atomicAdd(&state[1], 1);
     if (ticket == (int)gridDim.x - 1) {
-      state[0] = t;
+      if (skip) state[3] += 1; else state[0] = t;
       state[1] = 0;
       __threadfence();
     }
@@ -116,7 +125,7 @@ using namespace dimo;
 
 extern "C" int dimo_adam_step(int64_t n, float* params, float* grads, float* exp_avg, float* exp_avg_sq, int nseg,
                               const int64_t* seg_begin_host, const float* seg_lr, double beta1, double beta2, float eps,
-                              int zero_grads, int* state, void* stream) {
+                              int zero_grads, int* state, const float* skip_flag, void* stream) {
   DIMO_REQUIRE(n >= 0 && (n & 3) == 0, "n must be a multiple of 4 (pad the flat buffer)");
   DIMO_REQUIRE(nseg >= 1 && nseg <= ADAM_MAX_SEGS, "1..64 learning-rate segments");
   if (n == 0) return 0;
@@ -136,7 +145,7 @@ extern "C" int dimo_adam_step(int64_t n, float* params, float* grads, float* exp
   const int grid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
   adam_kernel<<<grid, ADAM_THREADS, 0, (cudaStream_t)stream>>>(
       n4, reinterpret_cast<float4*>(params), reinterpret_cast<float4*>(grads), reinterpret_cast<float4*>(exp_avg),
-      reinterpret_cast<float4*>(exp_avg_sq), seg_lr, segs, beta1, beta2, eps, zero_grads, state);
+      reinterpret_cast<float4*>(exp_avg_sq), seg_lr, segs, beta1, beta2, eps, zero_grads, state, skip_flag);
   DIMO_CHECK_LAUNCH();
   return 0;
 }

@@ -16,6 +16,7 @@ into the communication buffer (no pack / unpack copies).  The buffer has two con
 import torch
 
 ALIGN = 4      # floats
+TAIL = 4       # status floats behind the gradients (see FlatGradReducer)
 
 
 def shard_motions(n_motions, world, rank):
@@ -48,7 +49,13 @@ class FlatGradReducer:
         if not self.early:
             self.n_early = 0
         self.n = o
+        # TAIL floats behind the gradients ride along in the late bucket's all-reduce: [0] = "instance capacity
+        # overflowed on this rank" (trainstep.TrainStep writes it every step; after the SUM it is the number of ranks
+        # that dropped work, identical everywhere, and gates the optimizer update on every rank alike)
         self.flat = None
+        self.flat_all = None
+        self.tail = None
+        self.dirty = False          # gradients accumulated since the optimizer last consumed them
         self._arrived = 0
         self._work = []
         self._hooks = []
@@ -58,7 +65,9 @@ class FlatGradReducer:
     # ------------------------------------------------------------------------------------------
     def attach(self):
         dev = self.params[0].device
-        self.flat = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        self.flat_all = torch.zeros(self.n + TAIL, dtype=torch.float32, device=dev)
+        self.flat = self.flat_all[:self.n]
+        self.tail = self.flat_all[self.n:]
         for p, (o, numel) in zip(self.params, self.offsets):
             v = self.flat[o:o + numel].view_as(p)
             if p.grad is not None:
@@ -87,6 +96,7 @@ class FlatGradReducer:
         self._work = []
 
     def _on_early_grad(self, _p):
+        self.dirty = True
         self._arrived += 1
         if self._arrived == len(self.early) and self._distributed():
             self._launch(0, self.n_early)
@@ -98,7 +108,7 @@ class FlatGradReducer:
     def _launch(self, lo, hi):
         import torch.distributed as dist
         if hi > lo:
-            self._work.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            self._work.append(dist.all_reduce(self.flat_all[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def reduce(self):
         """Call after backward.  Launches what is still outstanding and makes the current stream wait for all of it."""
@@ -107,7 +117,7 @@ class FlatGradReducer:
         early_done = self._arrived >= len(self.early) and len(self.early) > 0
         if not early_done:
             self._launch(0, self.n_early)
-        self._launch(self.n_early, self.n)
+        self._launch(self.n_early, self.n + TAIL)
         for w in self._work:
             w.wait()
         self._work = []

@@ -68,6 +68,9 @@ class FusedAdam:
         self._lr_slot = 0
         self._lr_dev = torch.zeros(len(groups), dtype=torch.float32, device=dev)
         self._lr_sent = None
+        # optional device float: non-zero -> dimo_adam_step discards the step's gradients (TrainStep points it at the
+        # all-reduced capacity-overflow word of the flat buffer's tail)
+        self.skip_flag = None
         self.sync_lrs()
 
     # ------------------------------------------------------------------------------------------
@@ -91,12 +94,13 @@ class FusedAdam:
             self._lr_sent = cur
 
     def step(self):
+        self.reducer.dirty = False
         if not torch.cuda.is_current_stream_capturing():
             self.sync_lrs()
         _lib.call("dimo_adam_step", self.flat.numel(), _lib.ptr(self.flat), _lib.ptr(self.reducer.flat),
                   _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), len(self._seg_group), self._seg_begin,
                   _lib.ptr(self._lr_dev), self.betas[0], self.betas[1], self.eps, int(self.fold_zero_grad),
-                  _lib.ptr(self.state), _lib.stream())
+                  _lib.ptr(self.state), _lib.ptr(self.skip_flag), _lib.stream())
 
     # -- moment access for the surgery in gaussian_model.GaussianModel (densify / prune / reset_opacity) --------
     def _span(self, p):
@@ -119,8 +123,13 @@ class FusedAdam:
                 self.exp_avg_sq[off:off + numel].copy_(mv[1].reshape(-1))
 
     def zero_grad(self, set_to_none=False):
-        """No kernel when the clear is folded into step(); the reducer's bookkeeping is reset either way."""
+        """No kernel when the clear is folded into step(); the reducer's bookkeeping is reset either way.  A backward
+        whose gradients no step() consumed (a skipped / probe step; seen through the reducer's post-accumulate hooks
+        on the per-Gaussian parameters) IS cleared, as torch.optim.Adam.zero_grad would."""
         if self.fold_zero_grad:
+            if getattr(self.reducer, "dirty", False):
+                self.reducer.zero()
+                self.reducer.dirty = False
             self.reducer.reset()
         else:
             self.reducer.zero()

@@ -12,7 +12,13 @@ Two execution modes, same kernels, same results:
   graph   the rasteriser runs in capacity mode (no read-back, overflow flag on the device) and the WHOLE step --
           forward, loss, backward, all-reduce, Adam -- is captured once in a CUDA graph and replayed; only the
           step's inputs (cameras, times, latent indices, ground truth) are copied into static buffers.
+          A replay whose instance count exceeded the captured capacity (on ANY rank) can never reach the parameters:
+          its overflow word is all-reduced with the gradients and makes dimo_adam_step discard the step; run() polls
+          that word every `poll_every` replays (asynchronous 16-byte read), warns, grows the capacity and re-captures.
 """
+import warnings
+
+
 import torch
 
 from . import _lib
@@ -87,7 +93,7 @@ class TrainStep:
     process group once per step (the only exchange on the path; frames are sharded by motion)."""
 
     def __init__(self, renderer: Renderer, lr=1e-4, world=1, stage="s2", graph=False, probe_steps=3,
-                 capacity_margin=1.25, optimizer="fused", regularisers=False):
+                 capacity_margin=1.25, optimizer="fused", regularisers=False, poll_every=16):
         """lr: one float for every group, or {group name: lr} with the reference's group names
         (renderer/latent_gs_renderer.py:460-473).  optimizer: "fused" (dimo_adam_step, one launch incl. zero_grad) or
         "torch" (torch.optim.Adam(fused=True), kept for A/B runs)."""
@@ -134,6 +140,16 @@ class TrainStep:
         self._max_R = 0
         self._static = None
         self.graph_error = None
+        self.poll_every = max(1, int(poll_every))
+        self._replays = 0
+        self._poll = None             # (event, pinned [4] floats) of the read in flight
+        self.skipped_steps = 0        # replays discarded because of an overflow (as far as polled)
+        self.recaptures = 0
+        self._bind_skip_flag()
+
+    def _bind_skip_flag(self):
+        if self.fused_opt:
+            self.opt.skip_flag = self.reducer.tail[0:1]
 
     def _on_relayout(self, model):
         """The Gaussian count (or a parameter tensor) changed: new flat buffers, new instance counts -- a captured graph
@@ -144,6 +160,8 @@ class TrainStep:
         self.reducer, self.opt = model.reducer, model.optimizer
         self.params = list(self.reducer.params)
         model._timenet.direct_grads = True
+        self._bind_skip_flag()
+        self._poll = None
         self.graph = None
         self._static = None
         self.capacity = None
@@ -172,6 +190,8 @@ class TrainStep:
             self._max_R = max(self._max_R, st.R)
         elif overflow_acc is not None:
             overflow_acc.copy_(torch.maximum(overflow_acc, st.count_overflow))
+            if self.fused_opt:       # this step's flag -> the all-reduced status word that gates the optimizer
+                self.reducer.tail[0:1].copy_(st.count_overflow[1:2])
         loss = step_loss(out["image_raw"], out["alpha"], gt, mask, n_motions, frame_w=self.frame_w)
         if self.regularisers:
             loss = loss + _loss.smoothness_losses(out["image_raw"], out["depth"], out["normal"], groups=n_motions,
@@ -209,6 +229,45 @@ class TrainStep:
             st["loss"] = self._body(st["prep"], st["gt"], st["mask"], n_motions, optimize, self.capacity, st["overflow"])
         self.graph = graph
 
+    def _poll_overflow(self):
+        """Every `poll_every` replays: read the (all-reduced, rank-identical) overflow word and this rank's largest
+        instance count without blocking, and act on the previous read once it has landed.  Returns True when an
+        overflow was seen and the captured graph was dropped (larger capacity, re-capture on the next run())."""
+        st = self._static
+        if self._replays % self.poll_every != 0:
+            return False
+        # the previous read was issued poll_every replays ago: waiting for it costs nothing, and acting at a fixed
+        # replay index keeps all ranks in lock-step (a re-capture issues extra collectives)
+        if self._poll is not None:
+            self._poll[0].synchronize()
+            host = self._poll[1]
+            self._poll = None
+            if float(host[0]) != 0.0:
+                n_bad, need = int(host[0]), int(host[1])
+                self.skipped_steps += 1
+                warnings.warn(f"dimo_b200 TrainStep: the rasteriser's instance capacity ({self.capacity}) overflowed on "
+                              f"{n_bad} rank(s) (largest count on this rank {need}); the optimizer discarded the "
+                              "affected steps.  Growing the capacity and re-capturing the graph.")
+                # every rank re-captures (the flag is identical everywhere); each grows by what IT saw, at least 25 %
+                self._max_R = max(self._max_R, need, int(self.capacity * 1.25 / self.capacity_margin))
+                self.graph = None
+                self._static = None
+                self.recaptures += 1
+                self.reducer.tail.zero_()
+                return True
+        if self._poll is None:
+            if "poll_host" not in st:
+                st["poll_host"] = torch.zeros(4, dtype=torch.float32).pin_memory()
+                st["poll_dev"] = torch.zeros(4, dtype=torch.float32, device=st["gt"].device)
+            flag = self.reducer.tail[0:1] if self.fused_opt else st["overflow"][1:2]
+            st["poll_dev"][0:1].copy_(flag)
+            st["poll_dev"][1:2].copy_(st["overflow"][0:1])
+            st["poll_host"].copy_(st["poll_dev"], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            self._poll = (ev, st["poll_host"])
+        return False
+
     def overflowed(self):
         """graph mode: (max instance count seen, capacity, overflow flag) -- one small device read."""
         if self._static is None:
@@ -225,7 +284,7 @@ class TrainStep:
             return self._body(prep, gt, mask, n_motions, optimize)
         if self.graph is None:
             prep = self.r.prepare_step(cameras, times, latent_indices)
-            if self._seen < self.probe_steps:              # eager probe steps: learn the instance count
+            if self._seen < self.probe_steps and self.recaptures == 0:    # eager probe steps: learn the instance count
                 self._seen += 1
                 return self._body(prep, gt, mask, n_motions, optimize)
             gen = torch.cuda.default_generators[gt.device.index if gt.device.index is not None
@@ -237,7 +296,6 @@ class TrainStep:
             try:
                 self._capture(prep, gt, mask, n_motions, optimize)
             except Exception as e:                         # stay correct: fall back to eager and say so
-                import warnings
                 self.graph_error = f"{type(e).__name__}: {e}"
                 self.graph = None
                 self._static = None
@@ -251,7 +309,11 @@ class TrainStep:
                               ").  A common cause: tensors of an earlier backward (a render() result, a loss) are "
                               "still alive, so their AccumulateGrad nodes stay bound to the stream they were created on.")
                 return self._body(prep, gt, mask, n_motions, optimize)
+        if self._poll_overflow():                          # capacity grown: this step runs eagerly, the next one re-captures
+            prep = self.r.prepare_step(cameras, times, latent_indices)
+            return self._body(prep, gt, mask, n_motions, optimize)
         st = self._static
+        self._replays += 1
         self.r.prepare_step(cameras, times, latent_indices, out=st["prep"])
         st["gt"].copy_(gt, non_blocking=True)
         st["mask"].copy_(mask, non_blocking=True)

@@ -310,11 +310,16 @@ int dimo_smooth_bwd(int B, int H, int W, int clamp01, const float* rgb, const fl
  *   nseg learning-rate segments: seg_begin_host [nseg+1] (host array, element offsets, multiples of 4, covering
  *   [0,n)), seg_lr [nseg] (DEVICE array, so learning-rate schedules work under CUDA-graph replay);
  *   state [4] i32 (device): [0] = number of updates applied so far (bias correction uses state[0]+1 and the
- *   kernel increments it), [1] scratch (must start 0);  zero_grads != 0: grads are cleared in the same pass.
+ *   kernel increments it), [1] scratch (must start 0), [3] number of skipped steps;  zero_grads != 0: grads are
+ *   cleared in the same pass.
+ *   skip_flag (device float, may be NULL, must not alias the four buffers): non-zero => this step's gradients are
+ *   discarded (cleared, no update, step count unchanged).  The training step points it at the all-reduced
+ *   "instance capacity overflowed" word, so a CUDA-graph replay whose rasteriser dropped instances on any rank never
+ *   reaches the parameters (dimo_raster_bin, count_overflow).
  * ------------------------------------------------------------------------------------------- */
 int dimo_adam_step(int64_t n, float* params, float* grads, float* exp_avg, float* exp_avg_sq, int nseg,
                    const int64_t* seg_begin_host, const float* seg_lr, double beta1, double beta2, float eps,
-                   int zero_grads, int* state, void* stream);
+                   int zero_grads, int* state, const float* skip_flag, void* stream);
 
 /* dst_k[c][r] = src_k[r][c] for n <= 16 row-major matrices in ONE launch (W^T operands of the tensor-core
  * data-gradient GEMMs); all four arguments are host arrays of length n. */

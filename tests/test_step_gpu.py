@@ -53,7 +53,14 @@ def test_capacity_mode_equals_exact(cuda):
     assert cnt == R and flag == 1
 
 
-def _make_step(graph):
+# Seven optimizer steps at lr 1e-4: Adam with eps = 1e-15 turns every gradient entry into a +-lr move, so the 1e-7
+# run-to-run spread of the atomically accumulated gradients (entries that are ~0) is amplified into +-lr differences in a
+# few parameters -> the two TRAINED trajectories agree to ~1e-3, while with frozen parameters (lr = 0) the graph replay
+# reproduces the eager loss to 1e-6.
+GRAPH_TOL = 2e-3
+
+
+def _make_step(graph, lr=1e-4):
     from dimo_b200 import synthetic, trainstep
     from dimo_b200.renderer import Renderer
     sc = synthetic.make_scene(4000, n_ctrl=64, n_motions=4, seed=3)
@@ -64,10 +71,11 @@ def _make_step(graph):
         tn = r.gaussians._timenet
         for lin in (tn.pts_layers[-1], tn.rot_layers[-1]):
             lin.weight.copy_(0.01 * torch.randn_like(lin.weight))
-    return trainstep.TrainStep(r, lr=1e-4, graph=graph, probe_steps=2)
+    return trainstep.TrainStep(r, lr=lr, graph=graph, probe_steps=2)
 
 
-def test_trainstep_graph_matches_eager(cuda):
+@pytest.mark.parametrize("lr,tol", [(1e-4, GRAPH_TOL), (0.0, 1e-6)])
+def test_trainstep_graph_matches_eager(cuda, lr, tol):
     from dimo_b200.camera import orbit_minicam
     W = H = 64
     cams_all = [orbit_minicam(v, 4, W, H) for v in range(4)]
@@ -76,7 +84,7 @@ def test_trainstep_graph_matches_eager(cuda):
     mks = [torch.rand(8, 1, H, W, generator=g).cuda() for _ in range(3)]
     losses = {}
     for mode in (False, True):
-        ts = _make_step(mode)
+        ts = _make_step(mode, lr)
         ls = []
         for i in range(7):
             frames = [(m, v, f) for m in ((i) % 4, (i + 1) % 4) for v in ((i) % 4, (i + 2) % 4) for f in (i % 5, (i + 3) % 5)]
@@ -91,18 +99,76 @@ def test_trainstep_graph_matches_eager(cuda):
             cnt, cap, flag = ts.overflowed()
             assert not flag and cnt <= cap
     for a, b in zip(losses[False], losses[True]):
-        assert abs(a - b) <= 2e-3 * abs(a), (losses[False], losses[True])
+        assert abs(a - b) <= tol * abs(a), (losses[False], losses[True])
 
 
 @pytest.mark.parametrize("regularisers", [False, True])
 def test_full_step_matches_oracle(cuda, regularisers):
-    """deform -> raster -> loss for 4 frames: loss and a sample of parameter gradients vs the CPU oracle
-    (autograd through the whole oracle chain).  regularisers: + the depth / normal smoothness terms of the real step
-    (main_train_dimo.py:363-372), which also exercises the depth / normal gradient path of the rasteriser."""
+    """deform -> raster -> loss for 4 frames: the loss and the gradient of EVERY parameter on the path (Gaussian
+    attributes, control points, radii, latent codes, all 24 TimeNet tensors) vs the CPU oracle (autograd through the
+    whole oracle chain), at the north-star tolerance 1e-4 in two norms: max|d| / max|ref| and ||d||_2 / ||ref||_2.
+    The oracle's TimeNet is evaluated on the activation pattern the CUDA forward chose (gpu_parity.run_step_pair): a
+    sign that differs between the two patterns must sit on the kink itself (|z| <= 1e-5 of the layer's scale).
+    regularisers: + the depth / normal smoothness terms of the real step (main_train_dimo.py:363-372), which also
+    exercises the depth / normal gradient path of the rasteriser."""
     import gpu_parity as gp
     lc, lo, gc, go, stats = gp.run_step_pair(regularisers=regularisers)
     assert abs(lc - lo) <= 1e-4 * abs(lo), (lc, lo)
+    assert stats["flips"] <= 1e-5 * stats["signs"] and stats["worst_flip_rel_z"] <= 1e-5, stats
+    assert len(gc) == 8 + 24
     for k in gc:
-        # ReLU-kink flips (DESIGN.md section 2) can move MLP-side gradients by ~1/sqrt(rows); Gaussian-side ones are tight
-        tol = 5e-2 if k in ("c_xyz", "latents", "W0") else 1e-3
-        assert gp.rel_err(gc[k], go[k]) < tol, f"{k}: {gp.rel_err(gc[k], go[k]):.2e}"
+        e_max, e_l2 = gp.rel_err(gc[k], go[k]), gp.l2_err(gc[k], go[k])
+        assert e_max < gp.GRAD_TOL and e_l2 < gp.GRAD_TOL, f"{k}: max-norm {e_max:.2e}, l2 {e_l2:.2e}"
+
+
+def test_full_step_own_activation_pattern(cuda):
+    """the same comparison with the oracle on its OWN ReLU pattern: identical unless a pre-activation straddles zero
+    (reported by the flip count); with zero flips the 1e-4 bound must hold here too."""
+    import gpu_parity as gp
+    lc, lo, gc, go, stats = gp.run_step_pair(force_masks=False)
+    if stats["flips"] == 0:
+        for k in gc:
+            assert gp.rel_err(gc[k], go[k]) < gp.GRAD_TOL, f"{k}: {gp.rel_err(gc[k], go[k]):.2e}"
+    else:
+        assert stats["worst_flip_rel_z"] <= 1e-5, stats
+
+
+def test_graph_overflow_is_gated_polled_and_recaptured(cuda):
+    """a replay whose instance count exceeds the captured capacity must not reach the parameters,
+    and the host must find out.  The capacity is forced below the true count: dimo_adam_step discards those steps
+    (parameters and step counter unchanged), the poll warns, grows the capacity and re-captures, and training resumes."""
+    import warnings
+    from dimo_b200.camera import orbit_minicam
+    W = H = 64
+    cams_all = [orbit_minicam(v, 4, W, H) for v in range(4)]
+    g = torch.Generator().manual_seed(1)
+    gt = torch.rand(8, 3, H, W, generator=g).cuda(); mk = torch.rand(8, 1, H, W, generator=g).cuda()
+    ts = _make_step(True)
+    ts.poll_every = 2
+    frames = [(m, v, f) for m in (0, 1) for v in (0, 2) for f in (0, 3)]
+    args = ([cams_all[v] for (_, v, _) in frames], [f / 5 for (_, _, f) in frames], [m for (m, _, _) in frames], gt, mk, 2)
+    for _ in range(3):                       # 2 probe steps + capture
+        ts.run(*args)
+    assert ts.graph is not None and ts.graph_error is None
+    true_R = ts._max_R
+    # sabotage: re-capture with half the capacity the scene needs
+    ts._max_R = true_R // 3
+    ts.graph = None; ts._static = None; ts.recaptures = 1
+    ts.run(*args)
+    assert ts.graph is not None and ts.capacity < true_R
+    p0 = ts.opt.flat.clone(); step0 = ts.opt.state.clone()
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        for _ in range(6):
+            ts.run(*args)
+    torch.cuda.synchronize()
+    assert any("overflowed" in str(w.message) for w in rec), "the poll must warn about the overflow"
+    assert ts.recaptures >= 2 and ts.capacity >= true_R, (ts.recaptures, ts.capacity, true_R)
+    st = ts.opt.state.tolist()
+    assert st[3] >= 1, "overflowed replays must be counted as skipped by the optimizer"
+    assert st[0] > int(step0[0]), "training must resume after the re-capture"
+    cnt, cap, flag = ts.overflowed()
+    assert not flag and cnt <= cap
+    # the discarded steps left no trace: a fresh run without the sabotage reaches the same parameters after the same
+    # number of APPLIED updates only if no corrupted gradient was ever applied -> check finiteness and movement
+    assert bool(torch.isfinite(ts.opt.flat).all()) and not torch.equal(ts.opt.flat, p0)

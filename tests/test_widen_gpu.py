@@ -296,7 +296,14 @@ def test_arap_loss_v2_against_oracle(cuda):
     with torch.no_grad():                                      # a live deformation (the reference init is the identity)
         g._timenet.pts_layers[-1].weight.normal_(0, 0.004)
     torch.manual_seed(5)
-    err, (ii, jj, nn, nbr) = r.arap_loss_v2(stage="s2", latent_index=1)      # fused kernels (CUDA tensors)
+    import gpu_parity as gp
+    from dimo_b200 import deform as ddeform
+    ddeform.DEBUG_CAPTURE = []
+    try:
+        err, (ii, jj, nn, nbr) = r.arap_loss_v2(stage="s2", latent_index=1)      # fused kernels (CUDA tensors)
+        cmasks = gp.cuda_relu_masks(ddeform.DEBUG_CAPTURE[0])                     # rows ordered [time sample][key point]
+    finally:
+        ddeform.DEBUG_CAPTURE = None
     err.backward()
     assert len(ii) > 50 and math.isfinite(err.item()) and err.item() > 0
     # oracle: same time samples, TimeNet + connectivity + energy on the CPU
@@ -306,7 +313,11 @@ def test_arap_loss_v2_against_oracle(cuda):
               [g._timenet.pts_layers[0], g._timenet.pts_layers[2], g._timenet.rot_layers[0], g._timenet.rot_layers[2]]]
     c = g._c_xyz.detach().cpu().clone().requires_grad_(True)
     lat = g._latent_codes.detach().cpu()[1]
-    frames = [c.detach() + odeform.timenet_forward(params, c, float(t), lat)[0] for t in q]
+    # the oracle's TimeNet runs on the activation pattern the CUDA forward chose (gpu_parity.run_step_pair explains why)
+    M = c.shape[0]
+    frames = [c.detach() + odeform.timenet_forward(params, c, float(t), lat,
+                                                   masks_in=[m[k * M:(k + 1) * M] for m in cmasks])[0]
+              for k, t in enumerate(q)]
     nodes = torch.stack(frames)
     oi, oj, on = opoints.arap_connectivity_v2(nodes.detach())
     # the GPU and CPU node positions differ by ~1e-7, so a pair sitting on the ball's surface may flip: allow 2 edges
@@ -318,9 +329,7 @@ def test_arap_loss_v2_against_oracle(cuda):
     want.backward()
     e = (g._c_xyz.grad.cpu() - c.grad).abs().flatten()
     scale = float(c.grad.abs().max())
-    # TimeNet's ReLU kinks: a row whose pre-activation sits within rounding of zero can take the
-    # other branch on the tensor-core path, which moves that row's gradient; the bulk must agree tightly
-    assert float(e.quantile(0.9)) <= 1e-4 * scale and float(e.max()) <= 5e-2 * scale
+    assert float(e.max()) <= 2e-4 * scale, float(e.max()) / scale        # (ARAP's fp64 Jacobi SVD vs torch.linalg.svd: 2e-4)
 
 
 def test_keypoint_trajectory_loss(cuda):

@@ -203,23 +203,59 @@ def test_c1_config_against_reference_fixture(cuda):
             p[0].copy_(W); p[1].copy_(b)
     xyz = scene["_xyz"].cuda().requires_grad_(True)
     lat = scene["_latent_codes"][0].cuda().requires_grad_(True)
-    dxyz, dquat = net(xyz, float(d["t"]), lat)                       # the reference's call form (pts, t, latent)
+    import gpu_parity as gp
+    from dimo_b200 import deform as ddeform
+    from oracle import deform as od
+    ddeform.DEBUG_CAPTURE = []
+    try:
+        dxyz, dquat = net(xyz, float(d["t"]), lat)                   # the reference's call form (pts, t, latent)
+        cmasks = gp.cuda_relu_masks(ddeform.DEBUG_CAPTURE[0])
+    finally:
+        ddeform.DEBUG_CAPTURE = None
     for got, key in ((dxyz, "dxyz"), (dquat, "dquat")):
         want = torch.from_numpy(d[key])
         assert float((got.detach().cpu() - want).abs().max()) <= 2e-5 * float(want.abs().max()), key
-    loss = (xyz + dxyz - torch.from_numpy(d["target"]).cuda()).abs().mean()
+    target = torch.from_numpy(d["target"])
+    loss = (xyz + dxyz - target.cuda()).abs().mean()
     assert abs(loss.item() - float(d["l1_points"])) <= 1e-5 * float(d["l1_points"])
     loss.backward()
+
+    # Rows whose ReLU pattern differs between the CUDA forward and the reference's (= the oracle's own, pinned to the
+    # fixture by tests/test_c1_cpu.py) sit on a kink; the fixture's loss weights are fixed, so instead of masking them
+    # the fixture is CORRECTED for exactly those rows: minus their contribution on the oracle's own pattern, plus their
+    # contribution on the CUDA pattern (both evaluated by the oracle).  Every row is then compared at 1e-4.
+    own = []
+    od.timenet_forward(params, scene["_xyz"], float(d["t"]), scene["_latent_codes"][0], masks_out=own)
+    differ = torch.zeros(1000, dtype=torch.bool)
+    for (z, pos), cm in zip(own, cmasks):
+        diff = pos != cm
+        if bool(diff.any()):
+            assert float(z[diff].abs().max() / z.abs().max()) <= 1e-5, "activation patterns differ away from a kink"
+        differ |= diff.any(dim=1)
+    D = differ.nonzero().flatten()
+    print(f"c1: {int(differ.sum())} of 1000 rows on a ReLU kink")
+    assert D.numel() <= 20
+
+    def contribution(masks):
+        px = scene["_xyz"][D].clone().requires_grad_(True)
+        pl = scene["_latent_codes"][0].clone().requires_grad_(True)
+        ps = [(W.clone().requires_grad_(True), b.clone().requires_grad_(True)) for W, b in params]
+        dx, _ = od.timenet_forward(ps, px, float(d["t"]), pl, masks_in=[m[D] for m in masks])
+        ((px + dx - target[D]).abs().sum() / 3000.0).backward()
+        full = torch.zeros(1000, 3); full[D] = px.grad
+        return {"d_xyz": full, "d_latent": pl.grad, "d_w0": ps[0][0].grad, "d_wp": ps[9][0].grad}
+
+    corr = None
+    if D.numel() > 0:
+        c_own, c_cuda = contribution([pos for _, pos in own]), contribution(cmasks)
+        corr = {k: c_cuda[k] - c_own[k] for k in c_own}
     for got, key in ((xyz.grad, "d_xyz"), (lat.grad, "d_latent"), (net.deformnet[0].weight.grad, "d_w0"),
                      (net.pts_layers[2].weight.grad, "d_wp")):
         want = torch.from_numpy(d[key])
-        err = (got.detach().cpu() - want).abs().flatten()
-        scale = float(want.abs().max())
-        # ~1 % of the 1000 rows sit within rounding of a ReLU kink and may take the other branch on the tensor-core
-        # path; one flipped unit reroutes ~1/16 of that row's signal, which shifts every summed gradient entry by
-        # ~0.1-0.3 % of the tensor's scale per flip (measured earlier: up to 2 % on single entries with ~8 flips in 1536 rows,
-        # DESIGN.md section 2).  Gross errors (a wrong term, a missing row, a factor) are O(1); the forward above is tight.
-        assert float(err.median()) <= 2e-2 * scale and float(err.max()) <= 3e-1 * scale, (key, float(err.max()), scale)
+        if corr is not None:
+            want = want + corr[key]
+        assert gp.rel_err(got, want) <= 1e-4, (key, gp.rel_err(got, want))
+        assert gp.l2_err(got, want) <= 1e-4, (key, gp.l2_err(got, want))
     a, b = torch.from_numpy(d["img_a"]).cuda(), torch.from_numpy(d["img_b"]).cuda()
     s, l1, _mse = dloss.image_losses(a, b, need_ssim_grad=False).tolist()
     assert abs(l1 - float(d["l1_images"])) <= 1e-6 and abs(s - float(d["ssim_images"])) <= 1e-5
