@@ -3,13 +3,16 @@
 
   python bench.py --gpus N --steps K --warmup W            # our arm (torchrun for N > 1)
   python bench.py --impl reference --gpus N --steps K ...  # the reference's algorithm on the host CPU (oracle port)
+  python bench.py --workload c2|c3|c4|c5                   # BASELINE.json configs[1..4]; c3 is the headline (default)
 
 One "step" = one optimisation step over S frames per GPU: find_knn -> TimeNet over the unique (motion,t)
-pairs -> LBS -> batched rasterisation -> {MSE, SSIM, mask-MSE} -> backward -> [all-reduce] -> Adam.
+pairs -> LBS -> batched rasterisation -> {MSE, SSIM, mask-MSE} -> backward -> [all-reduce] -> Adam
+(c4: forward only -- 4-D inference, S rendered frames per step).
 One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -19,13 +22,22 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+METRIC = "train frames/s (deform+raster+SSIM fwd+bwd)"
+METRIC_INFER = "render frames/s (deform+raster fwd, 4-D inference)"
+
 WORKLOADS = {
-    # name: (n_gaussians, n_ctrl, H, W, motions/step/GPU, views/step, frames/step, total motions/GPU, total frames, total views)
-    "c3": dict(N=100_000, M=512, H=512, W=512, bm=4, bv=2, bf=2, motions_per_gpu=16, frames=32, views=8,
+    # bm x bv x bf = motions x views x frames per step and GPU (main_train_dimo.py:266-270 with batch_size 2)
+    "c3": dict(mode="train", N=100_000, M=512, H=512, W=512, bm=4, bv=2, bf=2, motions_per_gpu=16, frames=32, views=8,
                desc="c3 shard: 100k synthetic Gaussians, 512 control points, 512x512, 16 motions x 32 frames per GPU"),
-    "c2": dict(N=30_000, M=512, H=512, W=512, bm=4, bv=2, bf=2, motions_per_gpu=51, frames=20, views=9,
+    "c2": dict(mode="train", N=30_000, M=512, H=512, W=512, bm=4, bv=2, bf=2, motions_per_gpu=51, frames=20, views=9,
                desc="c2 shape: 30k synthetic Gaussians, 512 control points, 512x512, 51 motions x 20 frames"),
-    "small": dict(N=5_000, M=128, H=128, W=128, bm=2, bv=2, bf=2, motions_per_gpu=4, frames=8, views=4,
+    "c4": dict(mode="inference", N=30_000, M=512, H=1024, W=1024, bm=1, bv=4, bf=4, motions_per_gpu=1, frames=32,
+               views=120,
+               desc="c4: 4-D inference, 30k synthetic Gaussians, orbit 120 views x 32 frames at 1024x1024, (view, frame) "
+                    "pairs sharded over the GPUs, forward only"),
+    "c5": dict(mode="train", N=500_000, M=512, H=800, W=800, bm=4, bv=2, bf=2, motions_per_gpu=32, frames=32, views=8,
+               desc="c5 shard: 500k-Gaussian stress, 32 of 256 motions per GPU, 800x800, KNN + SSIM on"),
+    "small": dict(mode="train", N=5_000, M=128, H=128, W=128, bm=2, bv=2, bf=2, motions_per_gpu=4, frames=8, views=4,
                   desc="small smoke workload"),
 }
 
@@ -37,10 +49,14 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--min-seconds", type=float, default=2.0,
+                    help="the timed region repeats the K-step block until it is at least this long (sustained clocks); "
+                         "the first block alone is reported as `burst`")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-mode", default="prefetch", choices=["prefetch", "inline"],
-                    help="prefetch: next step's ground truth on a copy stream; inline: copy on the compute stream")
+    ap.add_argument("--e2e-gt", default="u8", choices=["u8", "f32"],
+                    help="ground truth crossing PCIe every step: u8 = the 8-bit samples it was decoded from, converted on "
+                         "the device by dimo_gt_fetch (GroundTruthCache semantics); f32 = the reference's host floats")
     ap.add_argument("--e2e-read", default="lagged", choices=["item", "lagged", "async"],
                     help="how the host reads every step's loss.  item: loss.item() (the host blocks on the step it just "
                          "enqueued); lagged: non-blocking D2H into pinned memory + the host waits for and reads the "
@@ -52,6 +68,16 @@ def parse():
                     help="add the depth / normal smoothness terms of the real step (main_train_dimo.py:363-372); "
                          "not part of the BASELINE metric, reported for completeness")
     return ap.parse_args()
+
+
+def workload_config(wl):
+    """The `config` object of the JSON line: names the workload only, identical for both arms."""
+    S = wl["bm"] * wl["bv"] * wl["bf"]
+    return {"workload": wl["desc"], "mode": wl["mode"], "frames_per_step_per_gpu": S, "H": wl["H"], "W": wl["W"],
+            "gaussians": wl["N"], "control_points": wl["M"],
+            "loss": "MSE + SSIM + mask MSE" if wl["mode"] == "train" else "none (forward only)",
+            "l2": "inputs larger than L2: the per-step working set (ground truth + splat / instance / gradient buffers, "
+                  "> 250 MB at c3) exceeds the 126 MB L2, no explicit flush"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -79,14 +105,20 @@ def build_model(wl, rank, device, seed=0):
     return r, sc
 
 
-def step_schedule(wl, step):
+def step_schedule(wl, step, rank=0, world=1):
     """Deterministic stand-in for the reference's random.sample (main_train_dimo.py:266-270):
-    bm motions x bv views x bf frames, motion-major."""
+    bm motions x bv views x bf frames, motion-major.  Inference (c4): the (view, frame) grid is block-partitioned over
+    the ranks and walked bv x bf pairs at a time."""
+    if wl["mode"] == "inference":
+        vblocks, fblocks = wl["views"] // wl["bv"], wl["frames"] // wl["bf"]
+        per_rank = (vblocks * fblocks) // world
+        blk = rank * per_rank + step % max(per_rank, 1)
+        v0, f0 = (blk // fblocks) * wl["bv"], (blk % fblocks) * wl["bf"]
+        return [(0, v0 + i, f0 + j) for i in range(wl["bv"]) for j in range(wl["bf"])]
     ms = [(step * wl["bm"] + i) % wl["motions_per_gpu"] for i in range(wl["bm"])]
     vs = [(step * wl["bv"] + i) % wl["views"] for i in range(wl["bv"])]
     fs = [(step * wl["bf"] + i) % wl["frames"] for i in range(wl["bf"])]
-    frames = [(m, v, f) for m in ms for v in vs for f in fs]
-    return frames
+    return [(m, v, f) for m in ms for v in vs for f in fs]
 
 
 class ClockSampler(threading.Thread):
@@ -125,7 +157,8 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------------
 def cpu_baseline(wl, n_frames, threads=None):
     """Times the oracle (CPU restatement of the reference algorithm, autograd backward) on `n_frames` frames of the
-    same workload: deform (TimeNet+LBS) -> raster -> MSE+SSIM+mask loss -> backward.  Returns frames/s."""
+    same workload: deform (TimeNet+LBS) -> raster -> MSE+SSIM+mask loss -> backward (inference workloads: forward
+    only).  Returns frames/s."""
     import torch
     from dimo_b200 import synthetic
     from oracle import deform as od, raster as orast, camera as ocam, loss as oloss, knn as oknn
@@ -133,32 +166,43 @@ def cpu_baseline(wl, n_frames, threads=None):
     # adds contention (measured: 8 threads 40 s/frame, 128 threads 657 s/frame on the B200 host) -> cap at 16
     threads = threads or min(os.cpu_count(), 16)
     torch.set_num_threads(threads)
+    train = wl["mode"] == "train"
     sc = synthetic.make_scene(wl["N"], n_ctrl=wl["M"], n_motions=wl["motions_per_gpu"], seed=0)
     params = od.timenet_init(32, seed=0, final_scale=0.01)
-    leaves = {k: v.clone().requires_grad_(True) for k, v in sc.items()}
+    leaves = {k: v.clone().requires_grad_(train) for k, v in sc.items()}
     H, W = wl["H"], wl["W"]
     g = torch.Generator().manual_seed(5)
     t0 = time.perf_counter()
     dist, idx = oknn.knn(sc["_c_xyz"], sc["_xyz"], 4)
     done = 0
-    for (m, v, f) in step_schedule(wl, 0)[:n_frames]:
-        cam = ocam.orbit_cam(v, wl["views"], W, H)
-        t = f / wl["frames"]
-        dxyz, dquat = od.timenet_forward(params, leaves["_c_xyz"], t, leaves["_latent_codes"][m])
-        means, rots = od.lbs_deform(leaves["_xyz"], leaves["_rotation"], leaves["_c_xyz"],
-                                    torch.exp(leaves["_c_radius"]), dxyz, dquat, idx, dist)
-        out = orast.rasterize(means, torch.exp(leaves["_scaling"]), rots, torch.sigmoid(leaves["_opacity"]),
-                              cam.world_view_transform, cam.full_proj_transform, cam.camera_center, cam.tanfovx,
-                              cam.tanfovy, W, H, torch.ones(3),
-                              shs=torch.cat([leaves["_features_dc"], leaves["_features_rest"]], 1), sh_degree=0)
-        gt = torch.rand(1, 3, H, W, generator=g); mk = torch.rand(1, 1, H, W, generator=g)
-        img = out["image"].clamp(0, 1)[None]
-        loss = 5000.0 * oloss.mse_loss(img, gt) + 500.0 * (1 - oloss.ssim(img, gt)) + \
-            500.0 * oloss.mse_loss(out["alpha"][None], mk)
-        loss.backward()
-        done += 1
+    with torch.set_grad_enabled(train):
+        for (m, v, f) in step_schedule(wl, 0)[:n_frames]:
+            cam = ocam.orbit_cam(v, wl["views"], W, H)
+            t = f / wl["frames"]
+            dxyz, dquat = od.timenet_forward(params, leaves["_c_xyz"], t, leaves["_latent_codes"][m])
+            means, rots = od.lbs_deform(leaves["_xyz"], leaves["_rotation"], leaves["_c_xyz"],
+                                        torch.exp(leaves["_c_radius"]), dxyz, dquat, idx, dist)
+            out = orast.rasterize(means, torch.exp(leaves["_scaling"]), rots, torch.sigmoid(leaves["_opacity"]),
+                                  cam.world_view_transform, cam.full_proj_transform, cam.camera_center, cam.tanfovx,
+                                  cam.tanfovy, W, H, torch.ones(3),
+                                  shs=torch.cat([leaves["_features_dc"], leaves["_features_rest"]], 1), sh_degree=0)
+            img = out["image"].clamp(0, 1)[None]
+            if train:
+                gt = torch.rand(1, 3, H, W, generator=g); mk = torch.rand(1, 1, H, W, generator=g)
+                loss = 5000.0 * oloss.mse_loss(img, gt) + 500.0 * (1 - oloss.ssim(img, gt)) + \
+                    500.0 * oloss.mse_loss(out["alpha"][None], mk)
+                loss.backward()
+            done += 1
     dt = time.perf_counter() - t0
     return done / dt, dt, threads
+
+
+def cpu_sample_text(args, wl, dt=None):
+    what = "deform+raster+loss fwd+bwd" if wl["mode"] == "train" else "deform+raster fwd"
+    S = wl["bm"] * wl["bv"] * wl["bf"]
+    return f"{args.cpu_frames} frame(s) of the {args.workload} workload (of {S} per step)" + \
+        (f", {dt:.1f} s" if dt is not None else "") + f", {what}, oracle port (PyTorch CPU" + \
+        (" + autograd)" if wl["mode"] == "train" else ")")
 
 
 def run_reference(args, wl):
@@ -174,14 +218,13 @@ def run_reference(args, wl):
         if time.perf_counter() - t_start + dt > budget_s:
             break
     fps = sorted(v[0] for v in vals)[len(vals) // 2]
-    sample = f"{args.cpu_frames} frame(s) of the {args.workload} workload (of {wl['bm'] * wl['bv'] * wl['bf']} per step), " \
-             f"deform+raster+loss fwd+bwd, oracle port (PyTorch CPU + autograd)"
-    line = {"impl": "reference", "metric": "train frames/s (deform+raster+SSIM fwd+bwd)", "value": fps,
+    line = {"impl": "reference", "metric": METRIC if wl["mode"] == "train" else METRIC_INFER, "value": fps,
             "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 / fps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": {"workload": wl["desc"], "H": wl["H"], "W": wl["W"],
-                                                          "gaussians": wl["N"]},
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
+            "dtype": "f32", "data": "synthetic", "config": workload_config(wl),
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                             "sample": cpu_sample_text(args, wl) + f"; median of {len(vals)} sample(s); one 'step' of "
+                                                                   "this arm = that sample"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -204,65 +247,99 @@ def run_ours(args, wl):
     from dimo_b200 import _lib, trainstep
     from dimo_b200.camera import orbit_minicam
 
+    train = wl["mode"] == "train"
     r, _ = build_model(wl, rank, dev)
-    ts = trainstep.TrainStep(r, lr=1e-5, world=world, graph=not args.no_graph, probe_steps=6, capacity_margin=1.12,
-                             regularisers=args.regularisers)
+    if train:
+        ts = trainstep.TrainStep(r, lr=1e-5, world=world, graph=not args.no_graph, probe_steps=6, capacity_margin=1.12,
+                                 regularisers=args.regularisers)
+    else:
+        ts = trainstep.RenderStep(r, graph=not args.no_graph, probe_steps=6, capacity_margin=1.25)
     H, W = wl["H"], wl["W"]
     S = wl["bm"] * wl["bv"] * wl["bf"]
     cams_all = [orbit_minicam(v, wl["views"], W, H, device=dev) for v in range(wl["views"])]
 
-    # ground truth: U(0,1) images + masks for a pool of steps, in pinned host memory (e2e) and resident in HBM (value)
-    pool = min(4, args.steps + args.warmup)
-    g = torch.Generator().manual_seed(1234 + rank)
-    gt_host = [torch.rand(S, 3, H, W, generator=g).pin_memory() for _ in range(pool)]
-    mk_host = [torch.rand(S, 1, H, W, generator=g).pin_memory() for _ in range(pool)]
-    gt_dev = [t.to(dev) for t in gt_host]
-    mk_dev = [t.to(dev) for t in mk_host]
+    # Ground truth of a pool of steps: 8-bit samples (R, G, B, mask) like the decoded PNGs of the reference
+    # (utils/load_utils.py:56-83), in pinned host memory for e2e and, converted by dimo_gt_fetch, resident in HBM as the
+    # floats byte / 255 for `value`.
+    pool = 4
+    slots = torch.arange(S, dtype=torch.int32, device=dev)
+    gt_u8_host, gt_dev, mk_dev, gt_f32_host = [], [], [], []
+    if train:
+        g = torch.Generator().manual_seed(1234 + rank)
+        for _ in range(pool):
+            u8 = torch.randint(0, 256, (S, 4, H, W), dtype=torch.uint8, generator=g).pin_memory()
+            gt_u8_host.append(u8)
+            rgb = torch.empty(S, 3, H, W, device=dev); msk = torch.empty(S, 1, H, W, device=dev)
+            _lib.call("dimo_gt_fetch", S, H, W, H, W, 1, _lib.ptr(u8.to(dev)), _lib.ptr(slots), _lib.ptr(rgb),
+                      _lib.ptr(msk), _lib.stream())
+            gt_dev.append(rgb); mk_dev.append(msk)
+            if args.e2e_gt == "f32":
+                gt_f32_host.append((rgb.cpu().pin_memory(), msk.cpu().pin_memory()))
+        torch.cuda.synchronize()
 
-    # e2e: ground truth travels host(pinned) -> device EVERY step, on a copy stream, double-buffered, so the
-    # copy of step i+1 overlaps the compute of step i (the reference uploads per render on the default stream,
-    # main_train_dimo.py:283-284)
+    # e2e: the step's ground truth travels host(pinned) -> device EVERY step on a copy stream, double-buffered, issued
+    # after the previous step's launches so it overlaps that step's GPU work (the reference uploads per render on the
+    # default stream, main_train_dimo.py:283-284); u8: converted on the device by one dimo_gt_fetch launch.
     copy_stream = torch.cuda.Stream(device=dev)
-    gt_buf = [torch.empty(S, 3, H, W, device=dev) for _ in range(2)]
-    mk_buf = [torch.empty(S, 1, H, W, device=dev) for _ in range(2)]
+    if train:
+        stage_u8 = [torch.empty(S, 4, H, W, dtype=torch.uint8, device=dev) for _ in range(2)]
+        gt_buf = [torch.empty(S, 3, H, W, device=dev) for _ in range(2)]
+        mk_buf = [torch.empty(S, 1, H, W, device=dev) for _ in range(2)]
+    else:
+        img_u8_host = [torch.empty(S, 3, H, W, dtype=torch.uint8).pin_memory() for _ in range(2)]
     ready_ev, free_ev, staged = [None, None], [None, None], {}
-    loss_host = torch.zeros(max(args.steps + args.warmup + 2, 8)).pin_memory()
+    loss_host = torch.zeros(64).pin_memory()
     loss_events = {}
+    d2h_events = [None, None]
 
     def stage(i):
         slot = i % 2
         with torch.cuda.stream(copy_stream):
             if free_ev[slot] is not None:
                 copy_stream.wait_event(free_ev[slot])
-            gt_buf[slot].copy_(gt_host[i % pool], non_blocking=True)
-            mk_buf[slot].copy_(mk_host[i % pool], non_blocking=True)
+            if args.e2e_gt == "u8":
+                stage_u8[slot].copy_(gt_u8_host[i % pool], non_blocking=True)
+            else:
+                gt_buf[slot].copy_(gt_f32_host[i % pool][0], non_blocking=True)
+                mk_buf[slot].copy_(gt_f32_host[i % pool][1], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
         ready_ev[slot] = ev
         staged[i] = slot
 
     def one_step(i, e2e):
-        frames = step_schedule(wl, i)
+        frames = step_schedule(wl, i, rank, world)
         cams = [cams_all[v] for (_, v, _) in frames]
         times = [f / wl["frames"] for (_, _, f) in frames]
         lat = [m for (m, _, _) in frames]
+        if not train:
+            img = ts.run(cams, times, lat)
+            if e2e:
+                # what main_test_dimo.py:243-260 does per frame (.detach().cpu() -> uint8), batched: quantise on the
+                # device, one D2H copy of the step's S frames into pinned memory, host waits one step behind
+                slot = i % 2
+                if d2h_events[slot] is not None:
+                    d2h_events[slot].synchronize()
+                u8 = (img * 255.0).to(torch.uint8)
+                img_u8_host[slot].copy_(u8, non_blocking=True)
+                ev = torch.cuda.Event(); ev.record()
+                d2h_events[slot] = ev
+            return None
         if e2e:
-            if args.e2e_mode == "inline":
-                gt = gt_host[i % pool].to(dev, non_blocking=True)
-                mk = mk_host[i % pool].to(dev, non_blocking=True)
-                loss = ts.run(cams, times, lat, gt, mk, wl["bm"])
-            else:
-                if i not in staged:
-                    stage(i)
-                slot = staged.pop(i)
-                torch.cuda.current_stream().wait_event(ready_ev[slot])
-                loss = ts.run(cams, times, lat, gt_buf[slot], mk_buf[slot], wl["bm"])
-                ev = torch.cuda.Event()
-                ev.record()
-                free_ev[slot] = ev
-                # issued AFTER this step's work is enqueued: the copy engine then runs it under the step's
-                # remaining GPU work instead of in front of the step's own small uploads
-                stage(i + 1)
+            if i not in staged:
+                stage(i)
+            slot = staged.pop(i)
+            torch.cuda.current_stream().wait_event(ready_ev[slot])
+            if args.e2e_gt == "u8":
+                _lib.call("dimo_gt_fetch", S, H, W, H, W, 1, _lib.ptr(stage_u8[slot]), _lib.ptr(slots),
+                          _lib.ptr(gt_buf[slot]), _lib.ptr(mk_buf[slot]), _lib.stream())
+            loss = ts.run(cams, times, lat, gt_buf[slot], mk_buf[slot], wl["bm"])
+            ev = torch.cuda.Event()
+            ev.record()
+            free_ev[slot] = ev
+            # issued AFTER this step's work is enqueued: the copy engine then runs it under the step's
+            # remaining GPU work instead of in front of the step's own small uploads
+            stage(i + 1)
             if args.e2e_read == "item":
                 return loss.item()      # device -> host read of the step's result, host waits for it
             slot_l = i % loss_host.numel()
@@ -283,21 +360,29 @@ def run_ours(args, wl):
             dist.barrier()
         torch.cuda.synchronize()
 
+    counter = [0]
+
     def timed(e2e, steps, warmup, profile=False):
-        for i in range(warmup):
-            one_step(i, e2e)
+        """`warmup` untimed steps, then EXACTLY `steps` timed steps between barrier + synchronize, CUDA events on the
+        launching stream, max over ranks.  Returns ms."""
+        for _ in range(warmup):
+            one_step(counter[0], e2e); counter[0] += 1
         barrier()
         if profile:
             _lib.PROFILE.reset(enabled=True)
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(warmup, warmup + steps):
-            one_step(i, e2e)
+        for _ in range(steps):
+            one_step(counter[0], e2e); counter[0] += 1
         if e2e and loss_events:          # lagged reads: the last step's loss is read before the clock stops
             for ev, slot_l in loss_events.values():
                 ev.synchronize()
                 float(loss_host[slot_l])
             loss_events.clear()
+        if e2e and not train:
+            for ev in d2h_events:
+                if ev is not None:
+                    ev.synchronize()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -309,24 +394,37 @@ def run_ours(args, wl):
         return float(t.item())
 
     sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
     # graph mode needs probe steps (eager, to learn the instance capacity) + the capture itself before the timed region
     extra_warm = (ts.probe_steps + 1) if ts.use_graph else 0
-    ms = timed(False, args.steps, args.warmup + extra_warm, profile=False)
+    ms_burst = timed(False, args.steps, args.warmup + extra_warm)          # the first K-step block on a cool GPU
+    # sustained: repeat the K-step block back to back until the timed region lasts >= --min-seconds (one event pair
+    # around ALL of it); `value` is taken from this region, the single block above is reported as `burst`
+    blocks = max(1, int(math.ceil(args.min_seconds * 1000.0 / max(ms_burst, 1e-3))))
+    if sampler:
+        sampler.start()
+    ms = timed(False, args.steps * blocks, 0)
     clocks = sampler.stop() if sampler else None
-    frames_total = world * S * args.steps
-    value = frames_total / (ms / 1000.0)
+    timed_steps = args.steps * blocks
+    value = world * S * timed_steps / (ms / 1000.0)
 
     e2e = None
     if not args.no_e2e:
-        ms_e = timed(True, args.steps, 1)
+        staged.clear()
+        ms_e = timed(True, timed_steps, 2)
         cam_bytes = S * 40 * 4
-        e2e = {"value": world * S * args.steps / (ms_e / 1000.0), "unit": "frames/s",
-               "h2d_bytes_per_step": S * 4 * H * W * 4 + cam_bytes, "d2h_bytes_per_step": 4,
-               "mode": f"ground truth {args.e2e_mode}, loss read {args.e2e_read}"}
+        if train:
+            gt_bytes = S * 4 * H * W * (1 if args.e2e_gt == "u8" else 4)
+            e2e = {"value": world * S * timed_steps / (ms_e / 1000.0), "unit": "frames/s",
+                   "h2d_bytes_per_step": gt_bytes + cam_bytes, "d2h_bytes_per_step": 4,
+                   "mode": f"ground truth ({args.e2e_gt}) from pinned host memory every step on a copy stream "
+                           f"(double-buffered), loss read {args.e2e_read}", "timed_steps": timed_steps}
+        else:
+            e2e = {"value": world * S * timed_steps / (ms_e / 1000.0), "unit": "frames/s",
+                   "h2d_bytes_per_step": cam_bytes, "d2h_bytes_per_step": S * 3 * H * W,
+                   "mode": "cameras up, the step's S rendered frames down as uint8 (main_test_dimo.py:243-260), host one "
+                           "step behind", "timed_steps": timed_steps}
     count_seen, capacity, overflow = ts.overflowed()
-    graph_used = ts.use_graph and ts.graph is not None and ts.graph_error is None
+    graph_used = ts.use_graph and ts.graph is not None and getattr(ts, "graph_error", None) is None
 
     # per-kernel durations: the same step launched eagerly with CUDA events around every C-ABI call
     # (a captured graph cannot be timed per kernel); identical kernels, identical inputs
@@ -359,40 +457,58 @@ def run_ours(args, wl):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     roof = None
+    ms_k = lambda name: prof.get(name, {}).get("ms_per_step", 0.0)
     if prof:
         top = max(((k, v) for k, v in prof.items() if not k.startswith("py:")), key=lambda kv: kv[1]["ms"])
         name, rec = top
-        st = r_state_stats(_lib)
+        st = dict(_lib.PROFILE.extra)
         alg = algorithmic_bytes(name, wl, S, st)
         dur_s = rec["ms"] / rec["calls"] / 1000.0
+        km = kernel_metrics(args.workload, name)
         roof = {"kernel": name, "bound": "hbm", "achieved": alg / dur_s / 1e9 if alg else None, "peak": hbm_peak,
                 "unit": "GB/s", "frac": (alg / dur_s / 1e9 / hbm_peak) if alg else None,
-                "traffic": MEASURED_TRAFFIC.get((args.workload, name)),
+                "traffic": km.get("dram_bytes"), "traffic_source": km.get("source"),
                 "peak_source": peak_src, "avg_launch_ms": rec["ms"] / rec["calls"],
                 "share_of_step": rec["ms_per_step"] / (ms_prof / prof_steps),
                 "timed_in": f"eager profiled pass of {prof_steps} steps ({ms_prof / prof_steps:.3f} ms/step) right after the timed region",
-                "note": "blend kernels are FP32-FMA/MUFU-issue bound by design (DESIGN.md K5/K6); HBM fraction is reported as the contract asks",
+                # what actually binds the blend kernels: FP32 FMA + ALU + MUFU issue slots; from the
+                # committed `ncu --set full` capture of the shipped kernel
+                "issue": ({"bound": "fp32_issue", "pipe_fma_pct": km.get("pipe_fma"), "pipe_alu_pct": km.get("pipe_alu"),
+                           "pipe_xu_pct": km.get("pipe_xu"), "issue_active_pct": km.get("issue_active"),
+                           "source": km.get("source")} if km else None),
                 "breakdown_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
                 "instances_R_per_step": st.get("R"), "pairs_note": "R = tile instances of the last step"}
 
     cpu = None
     if not args.no_cpu_baseline:
         fps, dt, threads = cpu_baseline(wl, args.cpu_frames)
-        cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-               "sample": f"{args.cpu_frames} frame(s) of the same workload ({dt:.1f} s), oracle port of deform+raster+loss fwd+bwd"}
+        cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": cpu_sample_text(args, wl, dt)}
 
-    line = {"metric": "train frames/s (deform+raster+SSIM fwd+bwd)", "value": value, "unit": "frames/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+    t_fwd = ms_k("dimo_raster_preprocess") + ms_k("dimo_raster_bin") + ms_k("dimo_raster_blend_fwd")
+    t_bwd = ms_k("dimo_raster_blend_bwd") + ms_k("dimo_raster_preprocess_bwd")
+    mpix = S * H * W / 1e6
+    line = {"metric": METRIC if train else METRIC_INFER, "value": value, "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / timed_steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "frames_per_step_per_gpu": S, "H": H, "W": W, "gaussians": wl["N"],
-                       "parallelism": f"motion-sharded dp{world}, one flat NCCL all-reduce/step" if world > 1 else "single GPU",
-                       "execution": ("whole step replayed as one CUDA graph (rasteriser in capacity mode: "
-                                     f"{capacity} instance slots, max count seen {count_seen}, overflow={overflow})")
-                       if graph_used else ("eager launches" + (f" (graph capture failed: {ts.graph_error})" if ts.graph_error else "")),
-                       "optimizer": "dimo_adam_step: one launch over the flat parameter/gradient buffers, zero_grad folded in",
-                       "l2": "per-step working set (GT 64 MiB + splat/instance buffers > 200 MiB) exceeds the 126 MB L2; no explicit flush",
-                       "loss": "MSE + SSIM + mask MSE" + (" + depth/normal smoothness" if args.regularisers else ""),
-                       "raster_MPix_per_s_fwd_bwd": value * H * W / 1e6},
+            "config": workload_config(wl),
+            "timing": {"timed_steps": timed_steps, "timed_region_s": ms / 1000.0, "blocks_of_steps": blocks,
+                       "burst": {"steps": args.steps, "ms_per_step": ms_burst / args.steps,
+                                 "value": world * S * args.steps / (ms_burst / 1000.0)}},
+            "impl_detail": {
+                "parallelism": f"motion-sharded dp{world}, one flat NCCL all-reduce/step" if (world > 1 and train) else
+                               (f"(view, frame) pairs sharded over {world} GPUs, no collective" if world > 1 else "single GPU"),
+                "execution": ("whole step replayed as one CUDA graph (rasteriser in capacity mode: "
+                              f"{capacity} instance slots, max count seen {count_seen}, overflow={overflow})")
+                if graph_used else ("eager launches" + (f" (graph capture failed: {ts.graph_error})" if getattr(ts, "graph_error", None) else "")),
+                "optimizer": "dimo_adam_step: one launch over the flat parameter/gradient buffers, zero_grad folded in, "
+                             "gated on the all-reduced overflow word" if train else None,
+                "regularisers": bool(args.regularisers)},
+            "raster": {"MPix_per_s_step": value * H * W / 1e6,
+                       "MPix_per_s_fwd_kernels": mpix / (t_fwd / 1000.0) if t_fwd > 0 else None,
+                       "MPix_per_s_fwd_bwd_kernels": mpix / ((t_fwd + t_bwd) / 1000.0) if (t_fwd > 0 and t_bwd > 0) else None,
+                       "note": "step: whole-step throughput x pixels per frame; *_kernels: pixels of one step / summed "
+                               "durations of the rasteriser's own calls (preprocess + bin + blend_fwd [+ blend_bwd + "
+                               "preprocess_bwd]) in the eager profiled pass"},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": _lib.PROFILE.kernel_launches_per_step(prof_steps)}
     if overflow:
@@ -401,12 +517,13 @@ def run_ours(args, wl):
     finish()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
-MEASURED_TRAFFIC = {("c3", "dimo_raster_blend_bwd"): 341.182e6 + 15.485e6, ("c3", "dimo_raster_blend_fwd"): 280.712e6 + 132.389e6}
-
-
-def r_state_stats(_lib):
-    return dict(_lib.PROFILE.extra)
+def kernel_metrics(workload, name):
+    """dram bytes per launch and pipe utilisations of `name` from the committed ncu capture of the SHIPPED kernels
+    (profiles/r2_kernel_metrics.json, written by tools/ncu_metrics_json.py from an `ncu --set full` report)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r2_kernel_metrics.json"))).get(workload, {}).get(name, {})
+    except Exception:
+        return {}
 
 
 def algorithmic_bytes(name, wl, S, st):

@@ -321,3 +321,63 @@ class TrainStep:
             self.opt.sync_lrs()                            # learning-rate changes reach the replay through device memory
         self.graph.replay()
         return st["loss"]
+
+
+class RenderStep:
+    """Forward-only launch set for 4-D inference (main_test_dimo.py:199-365: find_knn once, then per (view, frame)
+    `render()` without backward): all S frames of a call go through ONE batched launch set; in graph mode the set is
+    captured once (rasteriser in capacity mode) and replayed.  Returns the clamped images [S,3,H,W]."""
+
+    def __init__(self, renderer: Renderer, stage="s2", graph=True, probe_steps=3, capacity_margin=1.25):
+        self.r, self.g, self.stage = renderer, renderer.gaussians, stage
+        self.use_graph, self.probe_steps, self.capacity_margin = bool(graph), int(probe_steps), float(capacity_margin)
+        self.graph, self._static, self.capacity = None, None, None
+        self._seen, self._max_R = 0, 0
+        if stage >= "s2":
+            with torch.no_grad():
+                self.g.find_knn(4)                 # once per run (main_test_dimo.py:213)
+
+    def _body(self, prep, capacity=None):
+        with torch.no_grad():
+            out = self.r.render_batch(prepared=prep, stage=self.stage, clamp=True, capacity=capacity,
+                                      with_visibility=False)
+        st = out["raster_state"]
+        if capacity is None:
+            self._max_R = max(self._max_R, st.R)
+        return out["image"], out["depth"], out["alpha"], st
+
+    def run(self, cameras, times, latent_indices):
+        if not self.use_graph:
+            return self._body(self.r.prepare_step(cameras, times, latent_indices))[0]
+        if self.graph is None:
+            prep = self.r.prepare_step(cameras, times, latent_indices)
+            if self._seen < self.probe_steps:
+                self._seen += 1
+                return self._body(prep)[0]
+            self.capacity = int(self._max_R * self.capacity_margin) + 1024
+            self._static = {"prep": {k: (v.clone() if torch.is_tensor(v) else v) for k, v in prep.items()},
+                            "overflow": torch.zeros(2, dtype=torch.int32, device=prep["cams"].device)}
+            stt = self._static
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self._body(stt["prep"], self.capacity)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                img, depth, alpha, st = self._body(stt["prep"], self.capacity)
+                stt["overflow"].copy_(torch.maximum(stt["overflow"], st.count_overflow))
+                stt["image"] = img
+            self.graph = graph
+        stt = self._static
+        self.r.prepare_step(cameras, times, latent_indices, out=stt["prep"])
+        self.graph.replay()
+        return stt["image"]
+
+    def overflowed(self):
+        if self._static is None:
+            return self._max_R, None, False
+        cnt, flag = self._static["overflow"].tolist()
+        return cnt, self.capacity, bool(flag)

@@ -12,7 +12,14 @@ BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"}
 
 
-FINAL_LOG = os.path.join(ROOT, "profiles", "r1p_bench.log")      # the bench line of the round's last GPU visit
+def _final_log():
+    """the bench line of the latest GPU visit that was committed under profiles/ (r2*_bench.log, else round 1's)"""
+    import glob
+    logs = sorted(glob.glob(os.path.join(ROOT, "profiles", "r2*_bench.log")), key=os.path.getmtime)
+    return logs[-1] if logs else os.path.join(ROOT, "profiles", "r1p_bench.log")
+
+
+FINAL_LOG = _final_log()
 
 
 def _last_committed_line():
