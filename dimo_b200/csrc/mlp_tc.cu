@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_tc_kernel(const __grid_co
 
 using namespace dimo;
 
-namespace dimo { extern int g_blend_gather_mode; extern int g_blend_bwd_chunk; }   // raster_blend.cu
+namespace dimo { extern int g_blend_gather_mode; extern int g_blend_bwd_chunk; extern int g_blend_fwd_chunk; }   // raster_blend.cu
 namespace dimo { extern int g_disable_packed_instances; }                           // raster_bin.cu
 
 extern "C" int dimo_tc_debug_set(int key, int value) {
@@ -497,6 +497,11 @@ extern "C" int dimo_tc_debug_set(int key, int value) {
   }
   if (key == 7) {
     h_tc_knob[7] = value;
+    return 0;
+  }
+  if (key == 5) {
+    if (value != 64 && value != 128) return -2;
+    dimo::g_blend_fwd_chunk = value;
     return 0;
   }
   if (key < 0 || key >= 5) return -2;

@@ -26,7 +26,6 @@ constexpr int CHUNK = 128;                      // blend records per smem stage
 constexpr int REC_F4 = DIMO_SPLAT_FLOATS / 4;   // float4 per record
 constexpr int PPT = 4;                          // pixels per thread
 constexpr int BLEND_THREADS = TILE_PIX / PPT;   // 64
-constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 
 // blend record layout (written by preprocess_fwd_kernel, raster_preprocess.cu):
@@ -40,6 +39,7 @@ int g_blend_gather_mode = 0;
 // Records per shared-memory stage of the backward kernel (dimo_tc_debug_set key 4): 128, or 64 = half the shared memory
 // per CTA (12.7 KB instead of 25.6 KB) -> occupancy is no longer shared-memory bound, at twice the barrier rounds.
 int g_blend_bwd_chunk = 64;
+int g_blend_fwd_chunk = 64;      // same for the forward kernel (dimo_tc_debug_set key 5)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -114,14 +114,32 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 static_assert(CHUNK == 2 * BLEND_THREADS, "stage_gather assigns two records per thread");
 
-template <int MODE>
-__global__ void __launch_bounds__(BLEND_THREADS) blend_fwd_kernel(
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));   // one MUFU.RCP (__fdividef expands to a denormal-guarded sequence)
+  return y;
+}
+
+// Forward.  DN = false: depth / normal are not produced (out_depth = out_normal = NULL; the MSE + SSIM + mask step has
+// no consumer for them): 3 instead of 7 accumulators per pixel, 24 instead of 40 output bytes per pixel.
+//
+// Inner loop, per record and warp:
+//   test    p_i for the thread's 4 pixels (2 FFMA each), ONE compare of max(p_i) against the record's conservative
+//           threshold, one vote -> records that cannot reach alpha >= 1/255 anywhere in the warp's 16 x 8 pixels cost
+//           ~25 instructions;
+//   blend   BRANCH-FREE over the 4 pixels: the accept / saturate decisions become predicates, the weight of a
+//           rejected pair is selected to 0 and the accumulators are updated unconditionally (x + c * 0 = x exactly), so
+//           the four dependent chains (EX2 -> alpha -> T) interleave instead of running one divergent region per pixel.
+// A pixel that saturates keeps its transmittance with the sign flipped: T < 0 can never pass the T >= 1e-4 test again,
+// so no per-pixel "alive" test is needed in the loop; final_T = |T|.
+template <int MODE, bool DN, int CH>
+__global__ void __launch_bounds__(BLEND_THREADS, DN ? 12 : 16) blend_fwd_kernel(
     int W, int H, int gx, int tiles_per_frame, uint32_t vmask, uint32_t frame_stride,
     const float* __restrict__ cams, const float4* __restrict__ table,
     const uint32_t* __restrict__ vals_sorted, const uint2* __restrict__ ranges, float* __restrict__ out_color,
     float* __restrict__ out_depth, float* __restrict__ out_normal, float* __restrict__ out_alpha,
     float* __restrict__ final_T, int32_t* __restrict__ n_contrib) {
-  __shared__ __align__(128) float4 sm[2][CHUNK * REC_F4];
+  __shared__ __align__(128) float4 sm[2][CH * REC_F4];
   __shared__ __align__(8) uint64_t bar[2];
 
   const int tile = blockIdx.x;
@@ -134,16 +152,16 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_fwd_kernel(
 
   const uint2 rng = ranges[tile];
   const int n = (int)(rng.y - rng.x);
-  const int nchunks = (n + CHUNK - 1) / CHUNK;
+  const int nchunks = (n + CH - 1) / CH;
   const uint32_t* ids = vals_sorted + rng.x;
-  // record indices of list positions c*CHUNK + tid and + 64 (0 when past the end: never dereferenced).  An instance
+  // record indices of list positions c*CH + tid and + 64 (0 when past the end: never dereferenced).  An instance
   // word is the record index itself (vmask = all ones, frame_stride = 0) or, packed, (tile key | index within the
   // frame): record = (word & vmask) + frame * N.
   const uint32_t fbase = (uint32_t)b * frame_stride;
   auto load_ids = [&](int c, uint32_t& i0, uint32_t& i1) {
-    const int p0 = c * CHUNK + tid;
+    const int p0 = c * CH + tid;
     i0 = p0 < n ? (ids[p0] & vmask) + fbase : 0u;
-    i1 = p0 + 64 < n ? (ids[p0 + 64] & vmask) + fbase : 0u;
+    i1 = (CH > BLEND_THREADS && p0 + 64 < n) ? (ids[p0 + 64] & vmask) + fbase : 0u;
   };
 
   if (tid == 0) {
@@ -155,66 +173,74 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_fwd_kernel(
   uint32_t nid0 = 0, nid1 = 0;   // indices of the next stage to be issued
   for (int c = 0; c < 2 && c < nchunks; ++c) {
     load_ids(c, nid0, nid1);
-    stage_gather<MODE>(&sm[c][0], table, nid0, nid1, min(CHUNK, n - c * CHUNK), tid, &bar[c]);
+    stage_gather<MODE>(&sm[c][0], table, nid0, nid1, min(CH, n - c * CH), tid, &bar[c]);
   }
   if (nchunks > 2) load_ids(2, nid0, nid1);
 
-  float T[PPT], Cr[PPT], Cg[PPT], Cb[PPT], D[PPT], Nx[PPT], Ny[PPT], Nz[PPT];
+  constexpr int NCH = DN ? 7 : 3;            // r, g, b [, depth, nx, ny, nz]
+  float T[PPT], A[NCH][PPT];
   int last[PPT];
-  unsigned alive = 0;
+  unsigned alive = 0;                        // bit i: pixel i is inside the image and not saturated
 #pragma unroll
   for (int i = 0; i < PPT; ++i) {
-    T[i] = 1.f; Cr[i] = Cg[i] = Cb[i] = D[i] = Nx[i] = Ny[i] = Nz[i] = 0.f; last[i] = 0;
-    if (px0 + i < W && pyi < H) alive |= 1u << i;
+    last[i] = 0;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) A[k][i] = 0.f;
+    const bool inside = px0 + i < W && pyi < H;
+    T[i] = inside ? 1.f : -1.f;              // outside the image: "saturated" from the start
+    if (inside) alive |= 1u << i;
   }
 
   int c = 0;
   for (; c < nchunks; ++c) {
     const int stage = c & 1;
     mbar_wait(&bar[stage], (c >> 1) & 1);
-    const int cnt = min(CHUNK, n - c * CHUNK);
-    // The loop is kept WARP-UNIFORM (votes decide every branch that is not a plain predicated region): a
-    // per-thread `continue`/`break` loop de-converges the warp for good -- the first version of this kernel ran
-    // at 1.65 active threads per instruction (profiles/r1_blend_v1_*.csv).
+    const int cnt = min(CH, n - c * CH);
+    // The loop is kept WARP-UNIFORM (votes decide every branch): a per-thread `continue`/`break` loop de-converges the
+    // warp for good -- the first version of this kernel ran at 1.65 active threads per instruction
+    // (profiles/r1_blend_v1_*.csv).
     if (__any_sync(0xffffffffu, alive != 0)) {
       const float4* s = &sm[stage][0];
-      const int base = c * CHUNK;
+      const int base = c * CH + 1;
       for (int j = 0; j < cnt; ++j) {
         const float4 a = s[j * REC_F4 + 0];   // x, y, a2, b2
         const float4 bq = s[j * REC_F4 + 1];  // c2, opacity, pthr2, r
         const float dy = a.y - pyf, dx0 = a.x - pxf0;
         const float by = a.w * dy, cy = bq.x * dy * dy;
         float p[PPT];
-        unsigned hit = 0;
 #pragma unroll
         for (int i = 0; i < PPT; ++i) {
           const float dx = dx0 - (float)i;
           p[i] = fmaf(fmaf(a.z, dx, by), dx, cy);
-          if (p[i] <= 0.f && p[i] >= bq.z) hit |= 1u << i;
         }
-        hit &= alive;
-        if (__any_sync(0xffffffffu, hit != 0)) {
-          const float4 cq = s[j * REC_F4 + 2];  // g, b, depth, nx
-          const float4 dq = s[j * REC_F4 + 3];  // ny, nz, gid, -
+        // pthr2 is conservative (0.7 % margin on alpha): below it no pixel can reach alpha >= 1/255
+        const float pmax = fmaxf(fmaxf(p[0], p[1]), fmaxf(p[2], p[3]));
+        if (!__any_sync(0xffffffffu, pmax >= bq.z && alive != 0)) continue;
+        const float4 cq = s[j * REC_F4 + 2];  // g, b, depth, nx
+        float4 dq = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (DN) dq = s[j * REC_F4 + 3];       // ny, nz, gid, -
+        const int idx = base + j;
+        bool died[PPT];
 #pragma unroll
-          for (int i = 0; i < PPT; ++i) {
-            if (hit & (1u << i)) {
-              const float alpha = fminf(ALPHA_MAX, bq.y * ex2_approx(p[i]));
-              if (alpha >= ALPHA_MIN) {
-                const float test_T = T[i] * (1.0f - alpha);
-                if (test_T < T_MIN) {
-                  alive &= ~(1u << i);
-                } else {
-                  const float w = alpha * T[i];
-                  Cr[i] = fmaf(bq.w, w, Cr[i]); Cg[i] = fmaf(cq.x, w, Cg[i]); Cb[i] = fmaf(cq.y, w, Cb[i]);
-                  D[i] = fmaf(cq.z, w, D[i]);
-                  Nx[i] = fmaf(cq.w, w, Nx[i]); Ny[i] = fmaf(dq.x, w, Ny[i]); Nz[i] = fmaf(dq.y, w, Nz[i]);
-                  T[i] = test_T;
-                  last[i] = base + j + 1;
-                }
-              }
-            }
+        for (int i = 0; i < PPT; ++i) {
+          const float alpha = fminf(ALPHA_MAX, bq.y * ex2_approx(p[i]));
+          const float test_T = T[i] * (1.0f - alpha);
+          const bool cand = (p[i] <= 0.f) & (alpha >= ALPHA_MIN);     // the pair passes the reference's two skips
+          const bool ok = cand & (test_T >= T_MIN);                   // ... and the pixel is not saturated by it
+          died[i] = cand & !ok & (T[i] > 0.f);
+          const float w = ok ? alpha * T[i] : 0.f;
+          A[0][i] = fmaf(bq.w, w, A[0][i]); A[1][i] = fmaf(cq.x, w, A[1][i]); A[2][i] = fmaf(cq.y, w, A[2][i]);
+          if (DN) {
+            A[3][i] = fmaf(cq.z, w, A[3][i]);
+            A[4][i] = fmaf(cq.w, w, A[4][i]); A[5][i] = fmaf(dq.x, w, A[5][i]); A[6][i] = fmaf(dq.y, w, A[6][i]);
           }
+          T[i] = ok ? test_T : T[i];
+          last[i] = ok ? idx : last[i];
+        }
+        if (__any_sync(0xffffffffu, died[0] | died[1] | died[2] | died[3])) {      // rare: a pixel saturated here
+#pragma unroll
+          for (int i = 0; i < PPT; ++i)
+            if (died[i]) { T[i] = -T[i]; alive &= ~(1u << i); }
           if (!__any_sync(0xffffffffu, alive != 0)) break;   // whole warp saturated
         }
       }
@@ -222,7 +248,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_fwd_kernel(
     const int num_alive = __syncthreads_count(alive != 0);
     if (num_alive == 0) break;
     if (c + 2 < nchunks) {
-      stage_gather<MODE>(&sm[stage][0], table, nid0, nid1, min(CHUNK, n - (c + 2) * CHUNK), tid, &bar[stage]);
+      stage_gather<MODE>(&sm[stage][0], table, nid0, nid1, min(CH, n - (c + 2) * CH), tid, &bar[stage]);
       if (c + 3 < nchunks) load_ids(c + 3, nid0, nid1);
     }
   }
@@ -230,25 +256,29 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_fwd_kernel(
   if (c < nchunks && c + 1 < nchunks) mbar_wait(&bar[(c + 1) & 1], ((c + 1) >> 1) & 1);
 
   if (pyi >= H || px0 >= W) return;
+#pragma unroll
+  for (int i = 0; i < PPT; ++i) T[i] = fabsf(T[i]);
   const float* bg = cams + (int64_t)b * DIMO_CAM_FLOATS + CAM_BG;
   const float bg0 = bg[0], bg1 = bg[1], bg2 = bg[2];
   const int64_t hw = (int64_t)H * W;
   const int64_t pix = (int64_t)pyi * W + px0;
   float* oc = out_color + (int64_t)b * 3 * hw + pix;
-  float* od = out_depth + (int64_t)b * hw + pix;
-  float* on = out_normal + (int64_t)b * 3 * hw + pix;
   float* oa = out_alpha + (int64_t)b * hw + pix;
   float* oT = final_T + (int64_t)b * hw + pix;
   int32_t* oN = n_contrib + (int64_t)b * hw + pix;
+  float* od = DN ? out_depth + (int64_t)b * hw + pix : nullptr;
+  float* on = DN ? out_normal + (int64_t)b * 3 * hw + pix : nullptr;
   if ((W & 3) == 0 && px0 + PPT <= W) {
     // W % 4 == 0 and px0 % 4 == 0: 16-byte aligned rows -> 128-bit stores
-    *reinterpret_cast<float4*>(oc) = make_float4(Cr[0] + T[0] * bg0, Cr[1] + T[1] * bg0, Cr[2] + T[2] * bg0, Cr[3] + T[3] * bg0);
-    *reinterpret_cast<float4*>(oc + hw) = make_float4(Cg[0] + T[0] * bg1, Cg[1] + T[1] * bg1, Cg[2] + T[2] * bg1, Cg[3] + T[3] * bg1);
-    *reinterpret_cast<float4*>(oc + 2 * hw) = make_float4(Cb[0] + T[0] * bg2, Cb[1] + T[1] * bg2, Cb[2] + T[2] * bg2, Cb[3] + T[3] * bg2);
-    *reinterpret_cast<float4*>(od) = make_float4(D[0], D[1], D[2], D[3]);
-    *reinterpret_cast<float4*>(on) = make_float4(Nx[0], Nx[1], Nx[2], Nx[3]);
-    *reinterpret_cast<float4*>(on + hw) = make_float4(Ny[0], Ny[1], Ny[2], Ny[3]);
-    *reinterpret_cast<float4*>(on + 2 * hw) = make_float4(Nz[0], Nz[1], Nz[2], Nz[3]);
+    *reinterpret_cast<float4*>(oc) = make_float4(A[0][0] + T[0] * bg0, A[0][1] + T[1] * bg0, A[0][2] + T[2] * bg0, A[0][3] + T[3] * bg0);
+    *reinterpret_cast<float4*>(oc + hw) = make_float4(A[1][0] + T[0] * bg1, A[1][1] + T[1] * bg1, A[1][2] + T[2] * bg1, A[1][3] + T[3] * bg1);
+    *reinterpret_cast<float4*>(oc + 2 * hw) = make_float4(A[2][0] + T[0] * bg2, A[2][1] + T[1] * bg2, A[2][2] + T[2] * bg2, A[2][3] + T[3] * bg2);
+    if (DN) {
+      *reinterpret_cast<float4*>(od) = make_float4(A[NCH - 4][0], A[NCH - 4][1], A[NCH - 4][2], A[NCH - 4][3]);
+      *reinterpret_cast<float4*>(on) = make_float4(A[NCH - 3][0], A[NCH - 3][1], A[NCH - 3][2], A[NCH - 3][3]);
+      *reinterpret_cast<float4*>(on + hw) = make_float4(A[NCH - 2][0], A[NCH - 2][1], A[NCH - 2][2], A[NCH - 2][3]);
+      *reinterpret_cast<float4*>(on + 2 * hw) = make_float4(A[NCH - 1][0], A[NCH - 1][1], A[NCH - 1][2], A[NCH - 1][3]);
+    }
     *reinterpret_cast<float4*>(oa) = make_float4(1.f - T[0], 1.f - T[1], 1.f - T[2], 1.f - T[3]);
     *reinterpret_cast<float4*>(oT) = make_float4(T[0], T[1], T[2], T[3]);
     *reinterpret_cast<int4*>(oN) = make_int4(last[0], last[1], last[2], last[3]);
@@ -256,9 +286,11 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_fwd_kernel(
 #pragma unroll
     for (int i = 0; i < PPT; ++i) {
       if (px0 + i < W) {
-        oc[i] = Cr[i] + T[i] * bg0; oc[hw + i] = Cg[i] + T[i] * bg1; oc[2 * hw + i] = Cb[i] + T[i] * bg2;
-        od[i] = D[i];
-        on[i] = Nx[i]; on[hw + i] = Ny[i]; on[2 * hw + i] = Nz[i];
+        oc[i] = A[0][i] + T[i] * bg0; oc[hw + i] = A[1][i] + T[i] * bg1; oc[2 * hw + i] = A[2][i] + T[i] * bg2;
+        if (DN) {
+          od[i] = A[NCH - 4][i];
+          on[i] = A[NCH - 3][i]; on[hw + i] = A[NCH - 2][i]; on[2 * hw + i] = A[NCH - 1][i];
+        }
         oa[i] = 1.f - T[i]; oT[i] = T[i]; oN[i] = last[i];
       }
     }
@@ -392,53 +424,49 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_bwd_kernel(
     const float4* s = &sm[stage][0];
     for (int j = cnt - 1; j >= 0; --j) {
       const int pos = cc * CH + j;
-      unsigned hit = 0;
+      // test: one compare of max(p_i) against the record's conservative threshold + "this thread still has
+      // contributors at or behind this list position", one vote (see blend_fwd_kernel)
+      const float4 a = s[j * REC_F4 + 0];
+      const float4 bq = s[j * REC_F4 + 1];
+      const float dy = a.y - pyf, dx0 = a.x - pxf0;
+      const float by = a.w * dy, cy = bq.x * dy * dy;
       float p[PPT];
-      float4 a, bq;
-      float dy = 0.f, dx0 = 0.f;
-      if (__any_sync(0xffffffffu, pos < lmax)) {
-        a = s[j * REC_F4 + 0];
-        bq = s[j * REC_F4 + 1];
-        dy = a.y - pyf; dx0 = a.x - pxf0;
-        const float by = a.w * dy, cy = bq.x * dy * dy;
 #pragma unroll
-        for (int i = 0; i < PPT; ++i) {
-          const float dx = dx0 - (float)i;
-          p[i] = fmaf(fmaf(a.z, dx, by), dx, cy);
-          if (pos < last[i] && p[i] <= 0.f && p[i] >= bq.z) hit |= 1u << i;
-        }
+      for (int i = 0; i < PPT; ++i) {
+        const float dx = dx0 - (float)i;
+        p[i] = fmaf(fmaf(a.z, dx, by), dx, cy);
       }
-      if (!__any_sync(0xffffffffu, hit != 0)) continue;
+      const float pmax = fmaxf(fmaxf(p[0], p[1]), fmaxf(p[2], p[3]));
+      if (!__any_sync(0xffffffffu, pmax >= bq.z && pos < lmax)) continue;
+      // blend: branch-free over the 4 pixels; a pair the forward pass skipped contributes exact zeros
       float vt = 0.f, vsx = 0.f, vsxx = 0.f, vr = 0.f, vg = 0.f, vb = 0.f;
       float vd = 0.f, vn0 = 0.f, vn1 = 0.f, vn2 = 0.f;
-      if (hit) {
-        const float4 cq = s[j * REC_F4 + 2];  // g, b, depth, nx
-        float4 dq = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (DN) dq = s[j * REC_F4 + 3];       // ny, nz, gid, -
+      const float4 cq = s[j * REC_F4 + 2];  // g, b, depth, nx
+      float4 dq = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (DN) dq = s[j * REC_F4 + 3];       // ny, nz, gid, -
 #pragma unroll
-        for (int i = 0; i < PPT; ++i) {
-          if (hit & (1u << i)) {
-            const float G = ex2_approx(p[i]);
-            const float alpha = fminf(ALPHA_MAX, bq.y * G);
-            if (alpha >= ALPHA_MIN) {
-              const float dx = dx0 - (float)i;
-              const float inv = __fdividef(1.0f, 1.0f - alpha);   // alpha <= 0.99: MUFU.RCP (1 ulp) is ample for the 1e-4 bound
-              T[i] = T[i] * inv;
-              const float w = alpha * T[i];
-              float dotf = gc0[i] * bq.w + gc1[i] * cq.x + gc2[i] * cq.y;
-              if (DN) dotf += gd[i] * cq.z + gn0[i] * cq.w + gn1[i] * dq.x + gn2[i] * dq.y;
-              const float dLa = T[i] * dotf - Qp[i] * inv;
-              Qp[i] = fmaf(dotf, w, Qp[i]);
-              const float tt = G * dLa;          // dL/dopacity contribution; dL/dp2 = tt * op * ln2
-              const float dxt = dx * tt;
-              vt += tt; vsx += dxt; vsxx = fmaf(dx, dxt, vsxx);
-              vr = fmaf(gc0[i], w, vr); vg = fmaf(gc1[i], w, vg); vb = fmaf(gc2[i], w, vb);
-              if (DN) {
-                vd = fmaf(gd[i], w, vd);
-                vn0 = fmaf(gn0[i], w, vn0); vn1 = fmaf(gn1[i], w, vn1); vn2 = fmaf(gn2[i], w, vn2);
-              }
-            }
-          }
+      for (int i = 0; i < PPT; ++i) {
+        const float G = ex2_approx(p[i]);
+        const float alpha = fminf(ALPHA_MAX, bq.y * G);
+        const bool valid = (pos < last[i]) & (p[i] <= 0.f) & (alpha >= ALPHA_MIN);
+        const float dx = dx0 - (float)i;
+        const float inv = rcp_approx(1.0f - alpha);       // alpha <= 0.99: MUFU.RCP (1 ulp) is ample for the 1e-4 bound
+        const float Tn = T[i] * inv;                      // transmittance in front of this record
+        const float w = alpha * Tn;
+        float dotf = gc0[i] * bq.w + gc1[i] * cq.x + gc2[i] * cq.y;
+        if (DN) dotf += gd[i] * cq.z + gn0[i] * cq.w + gn1[i] * dq.x + gn2[i] * dq.y;
+        const float dLa = Tn * dotf - Qp[i] * inv;
+        const float Qn = fmaf(dotf, w, Qp[i]);
+        const float tt = valid ? G * dLa : 0.f;           // dL/dopacity contribution; dL/dp2 = tt * op * ln2
+        const float wv = valid ? w : 0.f;
+        T[i] = valid ? Tn : T[i];
+        Qp[i] = valid ? Qn : Qp[i];
+        const float dxt = dx * tt;
+        vt += tt; vsx += dxt; vsxx = fmaf(dx, dxt, vsxx);
+        vr = fmaf(gc0[i], wv, vr); vg = fmaf(gc1[i], wv, vg); vb = fmaf(gc2[i], wv, vb);
+        if (DN) {
+          vd = fmaf(gd[i], wv, vd);
+          vn0 = fmaf(gn0[i], wv, vn0); vn1 = fmaf(gn1[i], wv, vn1); vn2 = fmaf(gn2[i], wv, vn2);
         }
       }
       const float vsy = dy * vt, vsxy = dy * vsx, vsyy = dy * vsy;
@@ -539,7 +567,14 @@ extern "C" int dimo_raster_blend_fwd(int B, int N, int W, int H, int value_bits,
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
   uint32_t vmask, fstride;
   instance_decode(value_bits, N, vmask, fstride);
-  auto kern = g_blend_gather_mode == 0 ? blend_fwd_kernel<0> : blend_fwd_kernel<1>;
+  DIMO_REQUIRE((out_depth == nullptr) == (out_normal == nullptr), "out_depth and out_normal: pass both or neither");
+  const bool dn = out_depth != nullptr;
+  const bool small = g_blend_fwd_chunk == 64;
+  auto kern = g_blend_gather_mode == 0
+                  ? (dn ? (small ? blend_fwd_kernel<0, true, 64> : blend_fwd_kernel<0, true, 128>)
+                        : (small ? blend_fwd_kernel<0, false, 64> : blend_fwd_kernel<0, false, 128>))
+                  : (dn ? (small ? blend_fwd_kernel<1, true, 64> : blend_fwd_kernel<1, true, 128>)
+                        : (small ? blend_fwd_kernel<1, false, 64> : blend_fwd_kernel<1, false, 128>));
   kern<<<B * gx * gy, BLEND_THREADS, 0, (cudaStream_t)stream>>>(
       W, H, gx, gx * gy, vmask, fstride, cams, reinterpret_cast<const float4*>(splats), vals_sorted,
       reinterpret_cast<const uint2*>(ranges), out_color, out_depth, out_normal, out_alpha, final_T, n_contrib);

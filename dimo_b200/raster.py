@@ -70,7 +70,7 @@ class RasterState:
 
 
 def _forward_impl(cams, means3D, scales, rotations, opacities, shs, colors_precomp, B, N, W, H, sh_degree,
-                  scale_modifier, capacity=None, frame_src=None, n_src=None):
+                  scale_modifier, capacity=None, frame_src=None, n_src=None, depth_normal=True):
     """capacity=None: exact mode -- the instance count R is read back from the device once (a host sync, like the
     upstream rasterisers) and buffers are sized to it.  capacity=int: sync-free mode for CUDA graphs -- buffers hold
     `capacity` instance slots, `st.count_overflow` (device i32[2]) receives the true count and an overflow flag."""
@@ -135,8 +135,10 @@ def _forward_impl(cams, means3D, scales, rotations, opacities, shs, colors_preco
               _lib.ptr(sort_temp), sort_bytes, _lib.ptr(st.ranges),
               _lib.ptr(st.count_overflow), s)
     color = torch.empty(B, 3, H, W, **f32)
-    depth = torch.empty(B, 1, H, W, **f32)
-    normal = torch.empty(B, 3, H, W, **f32)
+    # depth_normal=False: nobody reads depth / normal (the MSE + SSIM + mask step) -> the blend kernel's 3-channel
+    # variant (dimo_raster_blend_fwd with out_depth = out_normal = NULL)
+    depth = torch.empty(B, 1, H, W, **f32) if depth_normal else None
+    normal = torch.empty(B, 3, H, W, **f32) if depth_normal else None
     alpha = torch.empty(B, 1, H, W, **f32)
     st.final_T = torch.empty(B, H, W, **f32)
     st.n_contrib = torch.empty(B, H, W, **i32)
@@ -150,10 +152,10 @@ def _forward_impl(cams, means3D, scales, rotations, opacities, shs, colors_preco
 class _Rasterize(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, scales, rotations, opacities, shs, colors_precomp, cams, B, N, W, H,
-                sh_degree, scale_modifier, state_out, capacity, frame_src, n_src):
+                sh_degree, scale_modifier, state_out, capacity, frame_src, n_src, depth_normal=True):
         color, depth, normal, alpha, st = _forward_impl(cams, means3D, scales, rotations, opacities, shs,
                                                         colors_precomp, B, N, W, H, sh_degree, scale_modifier,
-                                                        capacity, frame_src, n_src)
+                                                        capacity, frame_src, n_src, depth_normal)
         ctx.st = st
         ctx.set_materialize_grads(False)     # unused outputs (depth / normal in the image-loss step) arrive as None
         ctx.save_for_backward(means3D, scales, rotations, shs)
@@ -227,14 +229,16 @@ class _Rasterize(torch.autograd.Function):
                 fit(d_scales, sh_sc, N * 3), fit(d_rot, sh_rot, N * 4, True), fit(d_op, sh_op, N),
                 fit(d_shs, sh_shs, N * st.sh_coeffs * 3) if use_sh else None,
                 fit(d_col, sh_col, N * 3) if not use_sh else None,
-                None, None, None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None, None, None)
 
 
 def rasterize_batch(cams, means3D, scales, rotations, opacities, W, H, shs=None, colors_precomp=None,
-                    sh_degree=0, scale_modifier=1.0, means2D=None, state_out=None, capacity=None, frame_src=None):
+                    sh_degree=0, scale_modifier=1.0, means2D=None, state_out=None, capacity=None, frame_src=None,
+                    depth_normal=True):
     """cams [B,40]; means3D [B,N,3] or [N,3]; scales [N,3]; rotations [B,N,4] or [N,4]; opacities [N,1]/[N];
     shs [N,K,3] xor colors_precomp [B?,N,3].  frame_src [B] int32 (device): means3D / rotations are [U,N,*] and
     frame b uses block frame_src[b] (frames that differ only in the view share one deformation).
+    depth_normal=False: depth and normal are not rendered (returned as None).
     Returns color [B,3,H,W], depth [B,1,H,W], normal [B,3,H,W], alpha [B,1,H,W], radii [B,N] int32."""
     if (shs is None) == (colors_precomp is None):
         raise ValueError("Please provide exactly one of either SHs or precomputed colors!")
@@ -249,4 +253,4 @@ def rasterize_batch(cams, means3D, scales, rotations, opacities, W, H, shs=None,
             raise ValueError("frame_src supports at most 1024 frames per launch set")
     return _Rasterize.apply(c(means3D), means2D, c(scales), c(rotations), c(opacities), c(shs), c(colors_precomp),
                             cams.contiguous(), B, N, int(W), int(H), int(sh_degree), float(scale_modifier), state_out,
-                            capacity, frame_src, n_src)
+                            capacity, frame_src, n_src, bool(depth_normal))

@@ -137,10 +137,11 @@ class Renderer:
 
     def render_batch(self, cameras=None, times=None, latent_indices=None, stage="s2", scaling_modifier=1.0,
                      bg_color=None, override_color=None, xyz_detach=False, clamp=True, prepared=None, capacity=None,
-                     with_visibility=True):
+                     with_visibility=True, depth_normal=True):
         """All S frames of a step in ONE launch set.  cameras: list of S MiniCam (same W,H); times: list of S floats;
         latent_indices: list of S ints -- or `prepared` = the result of prepare_step().  capacity: instance-slot
-        capacity for the sync-free rasteriser mode (None = exact mode with one host read-back).
+        capacity for the sync-free rasteriser mode (None = exact mode with one host read-back).  depth_normal=False:
+        depth / normal are not rendered (None in the result) -- for steps whose loss reads image + alpha only.
         Returns a dict of batched tensors: image [S,3,H,W] (clamped), image_raw, depth, normal, alpha, radii [S,N],
         visibility_filter, pts_t [U,N,3] (one block per unique (motion,t); frame f uses block pair_of_frame[f]),
         cpts_t [U,M,3] + `pair_of_frame`."""
@@ -181,7 +182,7 @@ class Renderer:
         color, depth, normal, alpha, radii = _raster.rasterize_batch(
             prep["cams"], means3D, g.get_scaling, rotations, g.get_opacity, W, H, shs=shs, colors_precomp=colors,
             sh_degree=g.active_sh_degree, scale_modifier=scaling_modifier, state_out=state, capacity=capacity,
-            frame_src=frame_src)
+            frame_src=frame_src, depth_normal=depth_normal)
         return {"image": color.clamp(0, 1) if clamp else None, "image_raw": color, "depth": depth, "normal": normal,
                 "alpha": alpha, "radii": radii, "visibility_filter": (radii > 0) if with_visibility else None,
                 "pts_t": means3D, "cpts_t": cpts_t, "pair_of_frame": prep["pair_of_frame"], "raster_state": state[0]}

@@ -184,7 +184,7 @@ class TrainStep:
             self.g.find_knn(4)
         # the loss kernel clamps the render to [0,1] on load (and masks the gradient), so skip the separate clamp pass
         out = self.r.render_batch(prepared=prep, stage=self.stage, clamp=False, capacity=capacity,
-                                  with_visibility=False)
+                                  with_visibility=False, depth_normal=self.regularisers)
         st = out["raster_state"]
         if capacity is None:
             self._max_R = max(self._max_R, st.R)
@@ -328,7 +328,10 @@ class RenderStep:
     `render()` without backward): all S frames of a call go through ONE batched launch set; in graph mode the set is
     captured once (rasteriser in capacity mode) and replayed.  Returns the clamped images [S,3,H,W]."""
 
-    def __init__(self, renderer: Renderer, stage="s2", graph=True, probe_steps=3, capacity_margin=1.25):
+    def __init__(self, renderer: Renderer, stage="s2", graph=True, probe_steps=3, capacity_margin=1.25,
+                 depth_normal=False):
+        """depth_normal=False: images (+ alpha) only, as the inference loops consume them (main_test_dimo.py:243-260)."""
+        self.depth_normal = bool(depth_normal)
         self.r, self.g, self.stage = renderer, renderer.gaussians, stage
         self.use_graph, self.probe_steps, self.capacity_margin = bool(graph), int(probe_steps), float(capacity_margin)
         self.graph, self._static, self.capacity = None, None, None
@@ -340,7 +343,7 @@ class RenderStep:
     def _body(self, prep, capacity=None):
         with torch.no_grad():
             out = self.r.render_batch(prepared=prep, stage=self.stage, clamp=True, capacity=capacity,
-                                      with_visibility=False)
+                                      with_visibility=False, depth_normal=self.depth_normal)
         st = out["raster_state"]
         if capacity is None:
             self._max_R = max(self._max_R, st.R)

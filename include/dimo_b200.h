@@ -222,7 +222,7 @@ int dimo_linear_wgrad_tc_grouped(int n, int R, const int* K, const int* No, cons
                                  const float* const* X, const int64_t* ldx, float* const* dW, float* const* db,
                                  void* stream);
 /* bring-up knobs (0: swap LBO/SBO, 1: single-pass TF32, 2: wgrad CTA target, 3: blend gather via 16-byte
- * cp.async instead of 64-byte bulk copies, 4: records per stage of the blend backward, 64 or 128, 6: 1 = never pack
+ * cp.async instead of 64-byte bulk copies, 4 / 5: records per stage of the blend backward / forward, 64 or 128, 6: 1 = never pack
  * instances into single words); not part of the stable ABI */
 int dimo_tc_debug_set(int key, int value);
 
