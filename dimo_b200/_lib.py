@@ -19,10 +19,9 @@ _SIGS = {
     "dimo_abi_version": (c_int, []),
     "dimo_last_error": (ctypes.c_char_p, []),
     "dimo_device_info": (c_int, [c_vp]),
-    "dimo_raster_scan_temp_bytes": (c_sz, [c_i64]),
-    "dimo_raster_sort_temp_bytes": (c_sz, [c_i64]),
-    "dimo_raster_preprocess": (c_int, [c_int] * 6 + [c_f32, c_vp, c_vp] + [c_vp, c_i64] * 6 + [c_vp] * 6 + [c_vp, c_sz, c_vp, c_vp]),
-    "dimo_raster_bin": (c_int, [c_int] * 4 + [c_i64] + [c_vp] * 8 + [c_vp, c_sz, c_vp, c_vp, c_vp]),
+    "dimo_raster_bin_temp_bytes": (c_sz, [c_int] * 4),
+    "dimo_raster_preprocess": (c_int, [c_int] * 6 + [c_f32, c_vp, c_vp] + [c_vp, c_i64] * 6 + [c_vp] * 7 + [c_vp, c_vp]),
+    "dimo_raster_bin": (c_int, [c_int] * 4 + [c_i64] + [c_vp] * 4 + [c_vp, c_sz, c_vp, c_vp, c_vp]),
     "dimo_raster_packed_value_bits": (c_int, [c_int] * 4),
     "dimo_raster_blend_fwd": (c_int, [c_int] * 5 + [c_vp] * 11),
     "dimo_raster_blend_bwd": (c_int, [c_int] * 5 + [c_vp] * 12),
@@ -76,7 +75,7 @@ def lib():
             if fn is not None:
                 fn.restype = res
                 fn.argtypes = args
-        if L.dimo_abi_version() != 1:
+        if L.dimo_abi_version() != 2:
             raise RuntimeError("libdimo_b200.so ABI version mismatch")
         # bring-up knobs for A/B runs, e.g. DIMO_KNOBS="3=1,2=148" (see dimo_tc_debug_set in include/dimo_b200.h)
         for kv in filter(None, os.environ.get("DIMO_KNOBS", "").split(",")):
@@ -105,9 +104,9 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-# hand-written kernels launched per C-ABI call (CUB scan/sort launches are listed separately)
+# hand-written kernels launched per C-ABI call
 _OWN_LAUNCHES = {
-    "dimo_raster_preprocess": 2, "dimo_raster_bin": 2, "dimo_raster_blend_fwd": 1, "dimo_raster_blend_bwd": 1,
+    "dimo_raster_preprocess": 2, "dimo_raster_bin": 4, "dimo_raster_blend_fwd": 1, "dimo_raster_blend_bwd": 1,
     "dimo_raster_preprocess_bwd": 1, "dimo_knn": 1, "dimo_dist3nn": 1,
     "dimo_fps": 1, "dimo_ball_query": 1, "dimo_chamfer_fwd": 1, "dimo_chamfer_bwd": 1,
     "dimo_arap_connectivity": 1, "dimo_arap_energy": 1, "dimo_linear_fwd": 1,

@@ -1,25 +1,35 @@
-// Binning stage of the tile rasteriser: inclusive scan of per-splat tile counts, key emission,
-// stable radix sort by tile id, per-tile ranges.
+// Binning stage of the tile rasteriser: depth order of the splats, per-tile instance lists, per-tile ranges.
 //
 // Upstream shape (diff_gauss / diff_gaussian_rasterization, call site
 // renderer/latent_gs_renderer.py:1256-1277): InclusiveSum -> duplicateWithKeys -> SortPairs over
 // 64-bit (tile | depth) keys (6 radix passes at 512^2 x 16 frames = 144 B per instance) -> identifyTileRanges.
 //
-// Here the same total order is produced with ~4.5x less traffic:
-//   1. the B*N splats are sorted ONCE by (frame, depth) -- 64-bit keys, but only B*N of them;
-//   2. tile counts are scanned in that order and instances are emitted front-to-back;
-//   3. the R instances are STABLE-sorted by the tile id alone: 32-bit keys, ceil(log2(B*tiles)) bits
-//      (14 bits = 2 passes at 512^2 x 16 frames, 32 B per instance).
-// A stable sort keeps the emission order inside a tile, i.e. ascending depth with ties in ascending Gaussian
-// index -- bit-for-bit the order of the 64-bit sort (tests compare against the oracle's stable 64-bit sort).
+// Here the same total order -- per tile: ascending view depth, ties in ascending Gaussian index -- comes from two
+// hand-written stages that never materialise a (tile | depth) key:
+//
+//   1. depth_sort_kernel   the N splats of every frame are sorted by their 32-bit depth bits (culled ones last) by
+//      ONE kernel: a thread-block CLUSTER of 8 CTAs per frame runs the four 8-bit passes of a stable LSD radix sort;
+//      digit counts are exchanged through distributed shared memory and the passes are separated by cluster barriers,
+//      so there are no per-pass launches, no global histograms and no look-back spinning.  Inside a warp, ranks
+//      come from match.any (lanes that hold the same digit) -- no shared-memory atomics.
+//   2. a STABLE COUNTING SORT of the instances by tile, one pass, exploiting that the depth order is frame-major
+//      (instances of frame b can only land in tiles of frame b):
+//        tile_hist_kernel      per chunk of consecutive splats: how many of them touch each tile -- a 2-D difference
+//                              array (4 shared-memory increments per splat) + prefix sums, no per-instance work;
+//        tile_chunk_scan / tile_base_scan   exclusive prefix over chunks per tile, then over tiles: every tile's
+//                              [begin, end) range and every chunk's first slot in every tile (+ overflow flag);
+//        tile_scatter_kernel   every warp walks the instances of its splats in depth order, 32 at a time, and
+//                              writes each one to its tile's next free slot (match.any ranks + per-warp cursors).
+//      HBM: 8 B read per splat (tile rectangle) twice + 4 B written per instance; the 2-pass radix sort it replaces
+//      wrote the unsorted instances, read them for the histogram and moved them twice (28 B per instance), plus a
+//      4 B sentinel fill and a 4 B read for the ranges.
 // The blend kernels gather the 64-byte blend records of a tile's list by index (`vals_sorted` -> record table
-// written by the preprocess kernel): the table (B*N records) is far smaller than the instance list and mostly
-// L2-resident, and only the part of a list in front of the saturation depth is ever fetched -- materialising all R
-// records in sorted order (the first version of this file) cost more than both sorts together.  Scan and sorts
-// are CUB device primitives compiled into this library (integer-only, HBM-bound).
+// written by the preprocess kernel).  Integer-only, bit-exact against the oracle's stable 64-bit sort.
 #include "common.cuh"
-#include <cub/cub.cuh>
+#include <cooperative_groups.h>
 #include <stdarg.h>
+
+namespace cg = cooperative_groups;
 
 namespace dimo {
 
@@ -32,46 +42,6 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
-// Per-tile [begin, end) ranges of the sorted instance list: every slot's key is compared with its neighbours.
-//
-// `R` is the number of SLOTS: with an exact instance count every slot is valid; in capacity mode (no host
-// read-back of the count) the unused tail carries sentinel keys (>= ntiles) which sort last and are skipped here.
-// Four slots per thread (one 128-bit load + the two neighbouring keys): 16 B in flight per thread instead of 4.
-__global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t R, uint32_t ntiles, const uint32_t* __restrict__ keys,
-                                                          int shift, uint2* __restrict__ ranges) {
-  const int64_t j0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (j0 >= R) return;
-  constexpr uint32_t NONE = 0xFFFFFFFFu;      // never a valid tile id (ntiles < 2^31)
-  uint32_t k[6];
-  // `shift` > 0: packed instances, the tile key is the word's upper part
-  k[0] = j0 > 0 ? keys[j0 - 1] >> shift : NONE;
-  if (j0 + 4 <= R) {
-    const uint4 v = *reinterpret_cast<const uint4*>(keys + j0);
-    k[1] = v.x >> shift; k[2] = v.y >> shift; k[3] = v.z >> shift; k[4] = v.w >> shift;
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) k[1 + i] = j0 + i < R ? keys[j0 + i] >> shift : NONE;
-  }
-  k[5] = j0 + 4 < R ? keys[j0 + 4] >> shift : NONE;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint32_t tile = k[1 + i];
-    if (tile >= ntiles) continue;             // sentinel slot (capacity mode) or past the end
-    if (k[i] != tile) ranges[tile].x = (uint32_t)(j0 + i);
-    if (k[2 + i] != tile) ranges[tile].y = (uint32_t)(j0 + i + 1);
-  }
-}
-
-// capacity mode: flags an instance count larger than the number of slots (the surplus instances were dropped)
-__global__ void overflow_check_kernel(const uint32_t* __restrict__ offsets, int64_t BN, int64_t slots,
-                                      int32_t* __restrict__ flag) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    const uint32_t total = offsets[BN - 1];
-    flag[0] = (int32_t)total;
-    if ((int64_t)total > slots) flag[1] = 1;
-  }
-}
-
 int g_disable_packed_instances = 0;     // dimo_tc_debug_set key 6: force the (key, value) pair format (tests, A/B)
 
 static inline int bits_for(int64_t n) {
@@ -80,12 +50,333 @@ static inline int bits_for(int64_t n) {
   return bits;
 }
 
-// gathers tile counts in depth-sorted order for the scan
-struct PermutedCount {
-  const uint32_t* counts;
-  const uint32_t* perm;
-  __host__ __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return counts[perm[i]]; }
+// ---------------------------------------------------------------------------------------------------------------
+// 1. per-frame depth sort
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int DS_CL = 8;              // CTAs per cluster = per frame
+constexpr int DS_THREADS = 512;
+constexpr int DS_WARPS = DS_THREADS / 32;
+constexpr int DS_BINS = 256;
+
+// keys0 [B*N] (input, depth bits); kB, kC, vB, vC [B*N] ping-pong buffers.  After the four passes vC holds, per
+// frame, the indices b*N + i in ascending (depth, i) order.
+__global__ void __cluster_dims__(DS_CL, 1, 1) __launch_bounds__(DS_THREADS)
+depth_sort_kernel(int N, const uint32_t* __restrict__ keys0, uint32_t* __restrict__ kB, uint32_t* __restrict__ kC,
+                  uint32_t* __restrict__ vB, uint32_t* __restrict__ vC) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = (int)cluster.block_rank();
+  const int b = blockIdx.x / DS_CL;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ uint32_t wc[DS_WARPS][DS_BINS];     // per-warp digit counts, then per-warp cursors
+  __shared__ uint32_t cta_tot[DS_BINS];          // this CTA's digit counts (read by the whole cluster)
+  __shared__ uint32_t scan[DS_BINS];
+  const int64_t fbase = (int64_t)b * N;
+  // contiguous ranges: CTA `crank` of the frame, warp `warp` of the CTA (multiples of 32 keep the loads aligned)
+  const int per_cta = ((N + DS_CL - 1) / DS_CL + 31) & ~31;
+  const int clo = min(N, crank * per_cta), chi = min(N, clo + per_cta);
+  const int per_warp = (((chi - clo) + DS_WARPS - 1) / DS_WARPS + 31) & ~31;
+  const int wlo = min(chi, clo + warp * per_warp), whi = min(chi, wlo + per_warp);
+  const uint32_t lt = (1u << lane) - 1u;
+
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 8 * pass;
+    const uint32_t* in_k = pass == 0 ? keys0 : ((pass & 1) ? kB : kC);
+    const uint32_t* in_v = (pass & 1) ? vB : vC;
+    uint32_t* out_k = (pass & 1) ? kC : kB;
+    uint32_t* out_v = (pass & 1) ? vC : vB;
+    for (int k = tid; k < DS_WARPS * DS_BINS; k += DS_THREADS) (&wc[0][0])[k] = 0;
+    __syncthreads();
+    // ---- count: one lane per distinct digit of the 32 keys adds the group's size to the warp's own counters ----
+    for (int i0 = wlo; i0 < whi; i0 += 32) {
+      const int i = i0 + lane;
+      const bool valid = i < whi;
+      const uint32_t key = valid ? in_k[fbase + i] : 0u;
+      const uint32_t d = valid ? ((key >> shift) & 255u) : (256u + (uint32_t)lane);   // idle lanes match nobody
+      const uint32_t peers = __match_any_sync(0xffffffffu, d);
+      if (valid && (peers & lt) == 0) wc[warp][d] += __popc(peers);
+      __syncwarp();
+    }
+    __syncthreads();
+    if (tid < DS_BINS) {                          // exclusive prefix over the CTA's warps, CTA total per digit
+      uint32_t run = 0;
+#pragma unroll
+      for (int w = 0; w < DS_WARPS; ++w) { const uint32_t c = wc[w][tid]; wc[w][tid] = run; run += c; }
+      cta_tot[tid] = run;
+    }
+    cluster.sync();                               // every CTA's totals are published
+    uint32_t lower = 0, all = 0;
+    if (tid < DS_BINS) {
+#pragma unroll
+      for (int c = 0; c < DS_CL; ++c) {
+        const uint32_t t = *cluster.map_shared_rank(&cta_tot[tid], c);
+        all += t;
+        if (c < crank) lower += t;
+      }
+      scan[tid] = all;
+    }
+    __syncthreads();
+    for (int off = 1; off < DS_BINS; off <<= 1) {  // inclusive Hillis-Steele scan over the 256 digit totals
+      uint32_t v = 0;
+      if (tid < DS_BINS && tid >= off) v = scan[tid - off];
+      __syncthreads();
+      if (tid < DS_BINS) scan[tid] += v;
+      __syncthreads();
+    }
+    if (tid < DS_BINS) {
+      const uint32_t base = scan[tid] - all + lower;   // keys with a smaller digit + same digit in earlier CTAs
+#pragma unroll
+      for (int w = 0; w < DS_WARPS; ++w) wc[w][tid] += base;
+    }
+    __syncthreads();
+    // ---- scatter: rank among the lanes with the same digit = position after the warp's cursor ----
+    for (int i0 = wlo; i0 < whi; i0 += 32) {
+      const int i = i0 + lane;
+      const bool valid = i < whi;
+      const uint32_t key = valid ? in_k[fbase + i] : 0u;
+      const uint32_t val = valid ? (pass == 0 ? (uint32_t)(fbase + i) : in_v[fbase + i]) : 0u;
+      const uint32_t d = valid ? ((key >> shift) & 255u) : (256u + (uint32_t)lane);
+      const uint32_t peers = __match_any_sync(0xffffffffu, d);
+      const uint32_t pos = valid ? wc[warp][d] + __popc(peers & lt) : 0u;
+      __syncwarp();
+      if (valid && (peers & lt) == 0) wc[warp][d] += __popc(peers);
+      __syncwarp();
+      if (valid) {
+        if (pass < 3) out_k[fbase + pos] = key;
+        out_v[fbase + pos] = val;
+      }
+    }
+    cluster.sync();   // the pass's writes are visible to the whole cluster; cta_tot may be overwritten again
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 2. stable counting sort of the instances by tile
+// ---------------------------------------------------------------------------------------------------------------
+// Chunk c of frame b = sorted positions [c * per_chunk, (c+1) * per_chunk) of that frame (same split in the
+// histogram and the scatter kernel).
+struct BinGeom {
+  int B, N, gx, gy, T, nchunk, per_chunk, wpc;   // T = gx * gy tiles per frame; wpc = warps per scatter CTA
 };
+
+// counts[(y, x)] over a (gy+1) x (gx+1) difference array: += the number of rectangles covering tile (x, y)
+__device__ __forceinline__ void diff_add(int* diff, int gw, uint2 r) {
+  const int x0 = r.x & 0xFFFF, y0 = r.x >> 16, x1 = r.y & 0xFFFF, y1 = r.y >> 16;
+  if (x1 <= x0 || y1 <= y0) return;
+  atomicAdd(&diff[y0 * gw + x0], 1);
+  atomicAdd(&diff[y0 * gw + x1], -1);
+  atomicAdd(&diff[y1 * gw + x0], -1);
+  atomicAdd(&diff[y1 * gw + x1], 1);
+}
+
+// in-place 2-D inclusive prefix of a (gy+1) x (gx+1) array by `nthr` cooperating threads (thread `t` of them);
+// the caller synchronises the group before and after and between the two phases through `sync`
+template <typename Sync>
+__device__ __forceinline__ void prefix2d(int* a, int gw, int gh, int t, int nthr, Sync sync) {
+  for (int y = t; y < gh; y += nthr) {
+    int run = 0;
+    for (int x = 0; x < gw; ++x) { run += a[y * gw + x]; a[y * gw + x] = run; }
+  }
+  sync();
+  for (int x = t; x < gw; x += nthr) {
+    int run = 0;
+    for (int y = 0; y < gh; ++y) { run += a[y * gw + x]; a[y * gw + x] = run; }
+  }
+  sync();
+}
+
+__global__ void __launch_bounds__(256) tile_hist_kernel(BinGeom g, const uint2* __restrict__ rects,
+                                                        const uint32_t* __restrict__ perm,
+                                                        uint32_t* __restrict__ hist) {
+  extern __shared__ int diff[];                  // (gy+1) x (gx+1)
+  const int chunk = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const int gw = g.gx + 1, gh = g.gy + 1;
+  for (int k = tid; k < gw * gh; k += blockDim.x) diff[k] = 0;
+  __syncthreads();
+  const int lo = min(g.N, chunk * g.per_chunk), hi = min(g.N, lo + g.per_chunk);
+  const int64_t fbase = (int64_t)b * g.N;
+  for (int i = lo + tid; i < hi; i += blockDim.x) diff_add(diff, gw, rects[perm[fbase + i]]);
+  __syncthreads();
+  prefix2d(diff, gw, gh, tid, (int)blockDim.x, [] { __syncthreads(); });
+  uint32_t* out = hist + ((int64_t)b * g.nchunk + chunk) * g.T;
+  for (int t = tid; t < g.T; t += blockDim.x) {
+    const int y = t / g.gx, x = t - y * g.gx;
+    out[t] = (uint32_t)diff[y * gw + x];
+  }
+}
+
+// hist[b][c][t] -> exclusive prefix over c (in place); tile_total[b*T + t] = sum over c
+__global__ void __launch_bounds__(256) tile_chunk_scan_kernel(BinGeom g, uint32_t* __restrict__ hist,
+                                                              uint32_t* __restrict__ tile_total) {
+  const int64_t bt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (bt >= (int64_t)g.B * g.T) return;
+  const int b = (int)(bt / g.T), t = (int)(bt - (int64_t)b * g.T);
+  uint32_t* col = hist + (int64_t)b * g.nchunk * g.T + t;
+  uint32_t run = 0;
+  for (int c = 0; c < g.nchunk; ++c) {
+    const uint32_t v = col[(int64_t)c * g.T];
+    col[(int64_t)c * g.T] = run;
+    run += v;
+  }
+  tile_total[bt] = run;
+}
+
+// exclusive scan over the B*T tile totals (frame-major, tile order) by ONE CTA: ranges[tile] = [begin, end), clamped
+// to `slots`; count_overflow (may be NULL): [0] = true instance count, [1] |= count > slots
+constexpr int TS_THREADS = 1024;
+__global__ void __launch_bounds__(TS_THREADS) tile_base_scan_kernel(int64_t n, int64_t slots,
+                                                                    const uint32_t* __restrict__ tile_total,
+                                                                    uint32_t* __restrict__ tile_base,
+                                                                    uint2* __restrict__ ranges,
+                                                                    int32_t* __restrict__ count_overflow) {
+  __shared__ uint32_t part[TS_THREADS];
+  const int tid = threadIdx.x;
+  const int64_t per = (n + TS_THREADS - 1) / TS_THREADS;
+  const int64_t lo = min(n, (int64_t)tid * per), hi = min(n, lo + per);
+  uint32_t sum = 0;
+  for (int64_t k = lo; k < hi; ++k) sum += tile_total[k];
+  part[tid] = sum;
+  __syncthreads();
+  for (int off = 1; off < TS_THREADS; off <<= 1) {
+    const uint32_t v = tid >= off ? part[tid - off] : 0u;
+    __syncthreads();
+    part[tid] += v;
+    __syncthreads();
+  }
+  uint32_t run = part[tid] - sum;
+  const uint32_t cap = (uint32_t)min(slots, (int64_t)0xFFFFFFFFll);
+  for (int64_t k = lo; k < hi; ++k) {
+    const uint32_t c = tile_total[k];
+    tile_base[k] = run;
+    ranges[k] = make_uint2(min(run, cap), min(run + c, cap));
+    run += c;
+  }
+  if (tid == TS_THREADS - 1 && count_overflow != nullptr) {
+    count_overflow[0] = (int32_t)part[tid];
+    if ((int64_t)part[tid] > slots) count_overflow[1] = 1;
+  }
+}
+
+// Every warp of a CTA owns a contiguous run of the chunk's splats (depth order) and walks their instances in order.
+//   cnt[w][(gy+1) x (gx+1)]: difference array -> per-tile count of warp w -> warp w's next free slot per tile.
+template <bool PACKED>
+__global__ void __launch_bounds__(256) tile_scatter_kernel(BinGeom g, int64_t slots, int vbits,
+                                                           const uint2* __restrict__ rects,
+                                                           const uint32_t* __restrict__ perm,
+                                                           const uint32_t* __restrict__ hist,
+                                                           const uint32_t* __restrict__ tile_base,
+                                                           uint32_t* __restrict__ keys_out,
+                                                           uint32_t* __restrict__ vals_out) {
+  extern __shared__ int cnt_all[];
+  const int chunk = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gw = g.gx + 1, gh = g.gy + 1, stride = gw * gh;
+  int* cnt = cnt_all + warp * stride;
+  for (int k = tid; k < g.wpc * stride; k += blockDim.x) cnt_all[k] = 0;
+  __syncthreads();
+  const int clo = min(g.N, chunk * g.per_chunk), chi = min(g.N, clo + g.per_chunk);
+  const int per_warp = (((chi - clo) + g.wpc - 1) / g.wpc + 31) & ~31;
+  const int wlo = min(chi, clo + warp * per_warp), whi = min(chi, wlo + per_warp);
+  const int64_t fbase = (int64_t)b * g.N;
+  // ---- per-warp tile counts ----
+  for (int i = wlo + lane; i < whi; i += 32) diff_add(cnt, gw, rects[perm[fbase + i]]);
+  __syncwarp();
+  prefix2d(cnt, gw, gh, lane, 32, [] { __syncwarp(); });
+  __syncthreads();
+  // ---- cursors: tile base + earlier chunks + earlier warps of this chunk ----
+  const uint32_t* hx = hist + ((int64_t)b * g.nchunk + chunk) * g.T;
+  const uint32_t* tb = tile_base + (int64_t)b * g.T;
+  for (int t = tid; t < g.T; t += blockDim.x) {
+    const int y = t / g.gx, x = t - y * g.gx;
+    uint32_t run = tb[t] + hx[t];
+    for (int w = 0; w < g.wpc; ++w) {
+      int* c = cnt_all + w * stride + y * gw + x;
+      const uint32_t v = (uint32_t)*c;
+      *c = (int)run;
+      run += v;
+    }
+  }
+  __syncthreads();
+  // ---- scatter: the warp's instance stream, 32 instances at a time, in depth order ----
+  const uint32_t lt = (1u << lane) - 1u;
+  const uint32_t key_base = (uint32_t)b * (uint32_t)g.T;
+  for (int g0 = wlo; g0 < whi; g0 += 32) {
+    const int i = g0 + lane;
+    uint32_t idx = 0, rx = 0, rw = 0, n_inst = 0;
+    if (i < whi) {
+      idx = perm[fbase + i];
+      const uint2 r = rects[idx];
+      const uint32_t x0 = r.x & 0xFFFF, y0 = r.x >> 16, x1 = r.y & 0xFFFF, y1 = r.y >> 16;
+      if (x1 > x0 && y1 > y0) {
+        rx = r.x; rw = x1 - x0; n_inst = rw * (y1 - y0);
+        if (PACKED) idx -= (uint32_t)fbase;          // index within the frame
+      }
+    }
+    uint32_t incl = n_inst;                          // inclusive scan of the lanes' instance counts
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    const uint32_t excl = incl - n_inst;
+    for (uint32_t o0 = 0; o0 < total; o0 += 32) {
+      const uint32_t o = o0 + lane;
+      int s = 0;                                     // owner of output o: the smallest lane with incl > o
+#pragma unroll
+      for (int step = 16; step >= 1; step >>= 1) {
+        const uint32_t v = __shfl_sync(0xffffffffu, incl, s + step - 1);
+        if (v <= o) s += step;
+      }
+      s = min(s, 31);
+      const uint32_t o_excl = __shfl_sync(0xffffffffu, excl, s);
+      const uint32_t o_rx = __shfl_sync(0xffffffffu, rx, s);
+      const uint32_t o_rw = __shfl_sync(0xffffffffu, rw, s);
+      const uint32_t o_idx = __shfl_sync(0xffffffffu, idx, s);
+      const bool act = o < total;
+      uint32_t tile = (uint32_t)g.T + (uint32_t)lane, cell = 0;   // idle lanes match nobody
+      if (act) {
+        const uint32_t k = o - o_excl;
+        const uint32_t row = k / o_rw, col = k - row * o_rw;
+        const uint32_t x = (o_rx & 0xFFFF) + col, y = (o_rx >> 16) + row;
+        tile = y * (uint32_t)g.gx + x;
+        cell = y * (uint32_t)gw + x;
+      }
+      const uint32_t peers = __match_any_sync(0xffffffffu, tile);
+      const uint32_t slot = act ? (uint32_t)cnt[cell] + __popc(peers & lt) : 0u;
+      __syncwarp();
+      if (act && (peers & lt) == 0) cnt[cell] += __popc(peers);
+      __syncwarp();
+      if (act && (int64_t)slot < slots) {
+        const uint32_t key = key_base + tile;
+        if (PACKED) {
+          vals_out[slot] = (key << vbits) | o_idx;
+        } else {
+          keys_out[slot] = key;
+          vals_out[slot] = o_idx;
+        }
+      }
+    }
+  }
+}
+
+
+// launch geometry of the counting sort for a launch set
+static inline BinGeom bin_geom(int B, int N, int W, int H) {
+  BinGeom g;
+  g.B = B; g.N = N;
+  g.gx = (W + TILE - 1) / TILE; g.gy = (H + TILE - 1) / TILE;
+  g.T = g.gx * g.gy;
+  int nchunk = (2 * 148 + B - 1) / (B > 0 ? B : 1);
+  nchunk = nchunk < 4 ? 4 : (nchunk > 128 ? 128 : nchunk);
+  const int by_size = (N + 255) / 256;                 // at least 256 splats per chunk
+  if (nchunk > by_size) nchunk = by_size < 1 ? 1 : by_size;
+  g.nchunk = nchunk;
+  g.per_chunk = (((N + nchunk - 1) / nchunk) + 31) & ~31;
+  const int64_t cell_bytes = (int64_t)(g.gx + 1) * (g.gy + 1) * 4;
+  int wpc = (int)(96 * 1024 / cell_bytes);
+  g.wpc = wpc > 8 ? 8 : wpc;                            // < 1: rejected by dimo_raster_bin
+  return g;
+}
 
 }  // namespace dimo
 
@@ -98,10 +389,8 @@ int preprocess_launch(int B, int N, int W, int H, int sh_degree, int sh_coeffs, 
                       int64_t scales_bstride, const float* rotations, int64_t rotations_bstride,
                       const float* opacities, int64_t opacities_bstride, const float* shs, int64_t shs_bstride,
                       const float* colors_precomp, int64_t colors_bstride, float* splats, int32_t* radii,
-                      uint32_t* tiles_touched, uint64_t* depth_keys, uint32_t* iota, cudaStream_t st);
-int emit_keys_launch(int B, int N, int W, int H, int64_t R, const float* splats, const int32_t* radii,
-                     const uint32_t* perm, const uint32_t* offsets, uint32_t* tile_keys, uint32_t* vals, int vbits,
-                     cudaStream_t st);
+                      uint32_t* tiles_touched, uint32_t* rects, uint32_t* depth_keys,
+                      unsigned long long* total_count, cudaStream_t st);
 }  // namespace dimo
 
 extern "C" {
@@ -120,17 +409,15 @@ int dimo_device_info(int* out3_host) {
   return 0;
 }
 
-size_t dimo_raster_scan_temp_bytes(int64_t BN) {
-  size_t scan = 0, sort = 0;
-  cub::DeviceScan::InclusiveSum(nullptr, scan, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)BN);
-  cub::DeviceRadixSort::SortPairs(nullptr, sort, (const uint64_t*)nullptr, (uint64_t*)nullptr,
-                                  (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)BN, 0, 64);
-  return (scan > sort ? scan : sort) + 256;
+/* bytes of the counting sort's scratch (per-chunk tile histograms, tile totals and bases) */
+size_t dimo_raster_bin_temp_bytes(int B, int N, int W, int H) {
+  if (B <= 0 || N <= 0 || W <= 0 || H <= 0) return 256;
+  const BinGeom g = bin_geom(B, N, W, H);
+  return ((size_t)B * g.nchunk * g.T + 2 * (size_t)B * g.T) * sizeof(uint32_t) + 256;
 }
 
-// Packed instances: when the tile key (bits_for(B*tiles + 1) bits, one spare code for the capacity-mode sentinel)
-// and the index of a Gaussian within its frame (bits_for(N) bits) fit one 32-bit word, instances are single words
-// (key << vbits) | index and the tile sort is a keys-only radix sort over the key bits: half the bytes per pass.
+// Packed instances: when the tile key (bits_for(B*tiles + 1) bits) and the index of a Gaussian within its frame
+// (bits_for(N) bits) fit one 32-bit word, instances are single words (key << vbits) | index: half the bytes.
 int dimo_raster_packed_value_bits(int B, int N, int W, int H) {
   if (dimo::g_disable_packed_instances) return 0;
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
@@ -140,21 +427,14 @@ int dimo_raster_packed_value_bits(int B, int N, int W, int H) {
   return vbits + kbits <= 32 ? vbits : 0;
 }
 
-size_t dimo_raster_sort_temp_bytes(int64_t R) {
-  size_t bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
-                                  (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)R, 0, 32);
-  return bytes + 256;
-}
-
 int dimo_raster_preprocess(int B, int N, int W, int H, int sh_degree, int sh_coeffs, float scale_modifier,
                            const float* cams, const int32_t* frame_src, const float* means3D,
                            int64_t means3D_bstride, const float* scales,
                            int64_t scales_bstride, const float* rotations, int64_t rotations_bstride,
                            const float* opacities, int64_t opacities_bstride, const float* shs,
                            int64_t shs_bstride, const float* colors_precomp, int64_t colors_bstride,
-                           float* splats, int32_t* radii, uint32_t* tiles_touched, uint32_t* offsets,
-                           uint64_t* depth_keys, uint32_t* perm, void* scan_temp, size_t scan_temp_bytes,
+                           float* splats, int32_t* radii, uint32_t* tiles_touched, uint32_t* rects,
+                           uint32_t* sort_scratch, uint32_t* perm, uint64_t* total_count,
                            int64_t* R_host, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t BN = (int64_t)B * N;
@@ -163,70 +443,77 @@ int dimo_raster_preprocess(int B, int N, int W, int H, int sh_degree, int sh_coe
   DIMO_REQUIRE(sh_degree >= 0 && sh_degree <= 3, "sh_degree must be 0..3");
   DIMO_REQUIRE((shs != nullptr) != (colors_precomp != nullptr), "exactly one of shs / colors_precomp");
   DIMO_REQUIRE(shs == nullptr || sh_coeffs >= (sh_degree + 1) * (sh_degree + 1), "sh_coeffs < (deg+1)^2");
+  DIMO_REQUIRE((W + TILE - 1) / TILE <= 1023 && (H + TILE - 1) / TILE <= 1023, "image larger than 1023 tiles per side");
   if (BN == 0) {
     if (R_host) *R_host = 0;
     return 0;
   }
-  // depth_keys: [2*BN] (unsorted | sorted), perm: [2*BN] (iota | sorted permutation = perm + BN)
+  DIMO_CHECK_CUDA(cudaMemsetAsync(total_count, 0, sizeof(uint64_t), st));
+  // sort_scratch: [3*BN] u32 = depth keys | ping | pong; perm: [2*BN] u32 = ping | pong (result = perm + BN)
   int rc = preprocess_launch(B, N, W, H, sh_degree, sh_coeffs, scale_modifier, cams, frame_src, means3D,
-                             means3D_bstride, scales,
-                             scales_bstride, rotations, rotations_bstride, opacities, opacities_bstride, shs,
-                             shs_bstride, colors_precomp, colors_bstride, splats, radii, tiles_touched, depth_keys,
-                             perm, st);
+                             means3D_bstride, scales, scales_bstride, rotations, rotations_bstride, opacities,
+                             opacities_bstride, shs, shs_bstride, colors_precomp, colors_bstride, splats, radii,
+                             tiles_touched, rects, sort_scratch, reinterpret_cast<unsigned long long*>(total_count),
+                             st);
   if (rc) return rc;
-  size_t need = scan_temp_bytes;
-  DIMO_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(scan_temp, need, depth_keys, depth_keys + BN, perm, perm + BN,
-                                                  (int)BN, 0, 32 + bits_for(B), st));
-  need = scan_temp_bytes;
-  cub::TransformInputIterator<uint32_t, PermutedCount, cub::CountingInputIterator<uint32_t>> counts_sorted(
-      cub::CountingInputIterator<uint32_t>(0), PermutedCount{tiles_touched, perm + BN});
-  DIMO_CHECK_CUDA(cub::DeviceScan::InclusiveSum(scan_temp, need, counts_sorted, offsets, (int)BN, st));
+  depth_sort_kernel<<<B * DS_CL, DS_THREADS, 0, st>>>(N, sort_scratch, sort_scratch + BN, sort_scratch + 2 * BN, perm,
+                                                     perm + BN);
+  DIMO_CHECK_LAUNCH();
   if (R_host) {
-    uint32_t last = 0;
-    DIMO_CHECK_CUDA(cudaMemcpyAsync(&last, offsets + (BN - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    unsigned long long total = 0;
+    DIMO_CHECK_CUDA(cudaMemcpyAsync(&total, total_count, sizeof(total), cudaMemcpyDeviceToHost, st));
     DIMO_CHECK_CUDA(cudaStreamSynchronize(st));
-    *R_host = (int64_t)last;
+    *R_host = (int64_t)total;
   }
   return 0;
 }
 
-int dimo_raster_bin(int B, int N, int W, int H, int64_t R, const float* splats, const int32_t* radii,
-                    const uint32_t* perm_sorted, const uint32_t* offsets, uint32_t* keys_unsorted,
-                    uint32_t* vals_unsorted, uint32_t* keys_sorted, uint32_t* vals_sorted, void* sort_temp,
-                    size_t sort_temp_bytes, uint32_t* ranges, int32_t* count_overflow, void* stream) {
+int dimo_raster_bin(int B, int N, int W, int H, int64_t R, const uint32_t* rects, const uint32_t* perm_sorted,
+                    uint32_t* keys_sorted, uint32_t* vals_sorted, void* temp, size_t temp_bytes, uint32_t* ranges,
+                    int32_t* count_overflow, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
   const int64_t ntiles = (int64_t)B * gx * gy;
   const int64_t BN = (int64_t)B * N;
   DIMO_REQUIRE(R < ((int64_t)1 << 31), "instance count must fit int32");
   DIMO_REQUIRE(ntiles < ((int64_t)1 << 31) - 1, "B*tiles must fit int32");
+  DIMO_REQUIRE(gx <= 1023 && gy <= 1023, "image larger than 1023 tiles per side");
+  if (BN == 0 || ntiles == 0) {
+    if (ntiles > 0) DIMO_CHECK_CUDA(cudaMemsetAsync(ranges, 0, sizeof(uint32_t) * 2 * ntiles, st));
+    return 0;
+  }
+  const BinGeom g = bin_geom(B, N, W, H);
+  DIMO_REQUIRE(g.wpc >= 1, "image too large for the tile counting sort (more than ~24k tiles per frame)");
+  DIMO_REQUIRE(temp_bytes >= dimo_raster_bin_temp_bytes(B, N, W, H), "dimo_raster_bin: temp buffer too small");
   const int vbits = dimo_raster_packed_value_bits(B, N, W, H);
-  uint32_t* const first_unsorted = vbits > 0 ? vals_unsorted : keys_unsorted;   // buffer that carries the key bits
-  DIMO_REQUIRE(((uintptr_t)(vbits > 0 ? vals_sorted : keys_sorted) & 15) == 0, "sorted instance buffer must be 16-byte aligned");
-  DIMO_CHECK_CUDA(cudaMemsetAsync(ranges, 0, sizeof(uint32_t) * 2 * ntiles, st));
-  if (R == 0 || BN == 0) return 0;
-  if (count_overflow != nullptr) {
-    // capacity mode: R is a slot count chosen by the caller; unused slots keep the all-ones sentinel key
-    DIMO_CHECK_CUDA(cudaMemsetAsync(first_unsorted, 0xFF, sizeof(uint32_t) * (size_t)R, st));
-    overflow_check_kernel<<<1, 32, 0, st>>>(offsets, BN, R, count_overflow);
-    DIMO_CHECK_LAUNCH();
+  DIMO_REQUIRE(vbits > 0 || keys_sorted != nullptr, "keys_sorted required for the (key, value) instance format");
+  uint32_t* hist = reinterpret_cast<uint32_t*>(temp);
+  uint32_t* tile_total = hist + (size_t)B * g.nchunk * g.T;
+  uint32_t* tile_base = tile_total + (size_t)B * g.T;
+  const size_t cells = (size_t)(g.gx + 1) * (g.gy + 1) * sizeof(int);
+  static bool attr_set = false;
+  if (!attr_set) {
+    DIMO_CHECK_CUDA(cudaFuncSetAttribute(tile_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    DIMO_CHECK_CUDA(cudaFuncSetAttribute(tile_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    DIMO_CHECK_CUDA(cudaFuncSetAttribute(tile_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
   }
-  int rc = emit_keys_launch(B, N, W, H, R, splats, radii, perm_sorted, offsets, keys_unsorted, vals_unsorted, vbits, st);
-  if (rc) return rc;
-  size_t need = sort_temp_bytes;
-  // one spare code above the last tile id so that the sentinel sorts behind every real key
-  const int kbits = bits_for(ntiles + 1);
-  if (vbits > 0) {
-    DIMO_CHECK_CUDA(cub::DeviceRadixSort::SortKeys(sort_temp, need, vals_unsorted, vals_sorted, (int)R, vbits,
-                                                   vbits + kbits, st));
-    tile_ranges_kernel<<<ceil_div(R, 1024), 256, 0, st>>>(R, (uint32_t)ntiles, vals_sorted, vbits,
-                                                         reinterpret_cast<uint2*>(ranges));
-  } else {
-    DIMO_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(sort_temp, need, keys_unsorted, keys_sorted, vals_unsorted,
-                                                    vals_sorted, (int)R, 0, kbits, st));
-    tile_ranges_kernel<<<ceil_div(R, 1024), 256, 0, st>>>(R, (uint32_t)ntiles, keys_sorted, 0,
-                                                         reinterpret_cast<uint2*>(ranges));
-  }
+  const uint2* r2 = reinterpret_cast<const uint2*>(rects);
+  dim3 grid(g.nchunk, B);
+  tile_hist_kernel<<<grid, 256, cells, st>>>(g, r2, perm_sorted, hist);
+  DIMO_CHECK_LAUNCH();
+  tile_chunk_scan_kernel<<<ceil_div(ntiles, 256), 256, 0, st>>>(g, hist, tile_total);
+  DIMO_CHECK_LAUNCH();
+  tile_base_scan_kernel<<<1, TS_THREADS, 0, st>>>(ntiles, R, tile_total, tile_base, reinterpret_cast<uint2*>(ranges),
+                                                  count_overflow);
+  DIMO_CHECK_LAUNCH();
+  if (R == 0) return 0;
+  if (vbits > 0)
+    tile_scatter_kernel<true><<<grid, g.wpc * 32, g.wpc * cells, st>>>(g, R, vbits, r2, perm_sorted, hist, tile_base,
+                                                                      keys_sorted, vals_sorted);
+  else
+    tile_scatter_kernel<false><<<grid, g.wpc * 32, g.wpc * cells, st>>>(g, R, 0, r2, perm_sorted, hist, tile_base,
+                                                                       keys_sorted, vals_sorted);
   DIMO_CHECK_LAUNCH();
   return 0;
 }

@@ -130,8 +130,9 @@ __device__ __forceinline__ float rcp_approx(float x) {
 //   blend   BRANCH-FREE over the 4 pixels: the accept / saturate decisions become predicates, the weight of a
 //           rejected pair is selected to 0 and the accumulators are updated unconditionally (x + c * 0 = x exactly), so
 //           the four dependent chains (EX2 -> alpha -> T) interleave instead of running one divergent region per pixel.
-// A pixel that saturates keeps its transmittance with the sign flipped: T < 0 can never pass the T >= 1e-4 test again,
-// so no per-pixel "alive" test is needed in the loop; final_T = |T|.
+// A pixel that saturates (or lies outside the image) gets its own alpha threshold raised from 1/255 to 2: no pair can be
+// accepted for it any more, so the loop needs no per-pixel "alive" test (the ALU pipe -- compares, selects, min -- is
+// the binding one here: 8 ALU + 7 FMA-pipe + 1 MUFU instruction per pixel and record).
 template <int MODE, bool DN, int CH>
 __global__ void __launch_bounds__(BLEND_THREADS, DN ? 12 : 16) blend_fwd_kernel(
     int W, int H, int gx, int tiles_per_frame, uint32_t vmask, uint32_t frame_stride,
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, DN ? 12 : 16) blend_fwd_kernel(
   if (nchunks > 2) load_ids(2, nid0, nid1);
 
   constexpr int NCH = DN ? 7 : 3;            // r, g, b [, depth, nx, ny, nz]
-  float T[PPT], A[NCH][PPT];
+  float T[PPT], A[NCH][PPT], amin[PPT];
   int last[PPT];
   unsigned alive = 0;                        // bit i: pixel i is inside the image and not saturated
 #pragma unroll
@@ -187,7 +188,8 @@ __global__ void __launch_bounds__(BLEND_THREADS, DN ? 12 : 16) blend_fwd_kernel(
 #pragma unroll
     for (int k = 0; k < NCH; ++k) A[k][i] = 0.f;
     const bool inside = px0 + i < W && pyi < H;
-    T[i] = inside ? 1.f : -1.f;              // outside the image: "saturated" from the start
+    T[i] = 1.f;
+    amin[i] = inside ? ALPHA_MIN : 2.0f;     // outside the image: "saturated" from the start
     if (inside) alive |= 1u << i;
   }
 
@@ -225,9 +227,9 @@ __global__ void __launch_bounds__(BLEND_THREADS, DN ? 12 : 16) blend_fwd_kernel(
         for (int i = 0; i < PPT; ++i) {
           const float alpha = fminf(ALPHA_MAX, bq.y * ex2_approx(p[i]));
           const float test_T = T[i] * (1.0f - alpha);
-          const bool cand = (p[i] <= 0.f) & (alpha >= ALPHA_MIN);     // the pair passes the reference's two skips
+          const bool cand = (p[i] <= 0.f) & (alpha >= amin[i]);       // the pair passes the reference's two skips
           const bool ok = cand & (test_T >= T_MIN);                   // ... and the pixel is not saturated by it
-          died[i] = cand & !ok & (T[i] > 0.f);
+          died[i] = cand & !ok;
           const float w = ok ? alpha * T[i] : 0.f;
           A[0][i] = fmaf(bq.w, w, A[0][i]); A[1][i] = fmaf(cq.x, w, A[1][i]); A[2][i] = fmaf(cq.y, w, A[2][i]);
           if (DN) {
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, DN ? 12 : 16) blend_fwd_kernel(
         if (__any_sync(0xffffffffu, died[0] | died[1] | died[2] | died[3])) {      // rare: a pixel saturated here
 #pragma unroll
           for (int i = 0; i < PPT; ++i)
-            if (died[i]) { T[i] = -T[i]; alive &= ~(1u << i); }
+            if (died[i]) { amin[i] = 2.0f; alive &= ~(1u << i); }
           if (!__any_sync(0xffffffffu, alive != 0)) break;   // whole warp saturated
         }
       }
@@ -256,8 +258,6 @@ __global__ void __launch_bounds__(BLEND_THREADS, DN ? 12 : 16) blend_fwd_kernel(
   if (c < nchunks && c + 1 < nchunks) mbar_wait(&bar[(c + 1) & 1], ((c + 1) >> 1) & 1);
 
   if (pyi >= H || px0 >= W) return;
-#pragma unroll
-  for (int i = 0; i < PPT; ++i) T[i] = fabsf(T[i]);
   const float* bg = cams + (int64_t)b * DIMO_CAM_FLOATS + CAM_BG;
   const float bg0 = bg[0], bg1 = bg[1], bg2 = bg[2];
   const int64_t hw = (int64_t)H * W;

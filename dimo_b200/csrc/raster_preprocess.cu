@@ -196,9 +196,15 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
     const float* __restrict__ shs, int64_t shs_bs,
     const float* __restrict__ colors, int64_t col_bs,
     float4* __restrict__ splats, int32_t* __restrict__ radii, uint32_t* __restrict__ tiles_touched,
-    uint64_t* __restrict__ depth_keys) {
+    uint2* __restrict__ rects, uint32_t* __restrict__ depth_keys, unsigned long long* __restrict__ total_count) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)B * N) return;
+  // the CTA's tile-instance count is summed (warp shuffles + one shared atomic per warp) and added to the launch
+  // set's total with one global atomic per CTA: the instance count R without a scan over the B*N counters
+  __shared__ unsigned int s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  unsigned int my_tiles = 0;
+  if (idx < (int64_t)B * N) {
   const int b = (int)(idx / N);
   const int i = (int)(idx - (int64_t)b * N);
   const float* cam = cams + (int64_t)b * DIMO_CAM_FLOATS;
@@ -225,11 +231,11 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
   if (!visible) {
     radii[idx] = 0;
     tiles_touched[idx] = 0;
-    depth_keys[idx] = ~0ull;                 // culled splats sort to the end and emit nothing
+    rects[idx] = make_uint2(0u, 0u);
+    depth_keys[idx] = 0xFFFFFFFFu;           // culled splats sort to the end of their frame and emit nothing
     const float4 zz = make_float4(0.f, 0.f, 0.f, 0.f);
     out[0] = zz; out[1] = zz; out[2] = zz; out[3] = zz;
-    return;
-  }
+  } else {
 
   float rgb[3];
   if (colors != nullptr) {
@@ -264,7 +270,9 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
 
   radii[idx] = (int)g.radius_f;
   tiles_touched[idx] = (uint32_t)ntiles;
-  depth_keys[idx] = ((uint64_t)b << 32) | (uint64_t)__float_as_uint(g.tvz);   // view depth > 0.2: bits order as uints
+  my_tiles = (unsigned int)ntiles;
+  rects[idx] = make_uint2((uint32_t)x0 | ((uint32_t)y0 << 16), (uint32_t)x1 | ((uint32_t)y1 << 16));   // [x0,x1) x [y0,y1), tiles
+  depth_keys[idx] = __float_as_uint(g.tvz);   // view depth > 0.2: the bits order as unsigned integers
   // blend record (include/dimo_b200.h; consumed as-is by raster_blend.cu, gathered by index):
   //   x, y, a2, b2 | c2, opacity, pthr2, r | g, b, depth, nx | ny, nz, own index, 0
   // the conic is pre-multiplied into log2 units (alpha = opacity * 2^(a2 dx^2 + b2 dx dy + c2 dy^2));
@@ -275,6 +283,13 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
   out[1] = make_float4((-0.5f * LOG2E) * g.conic_c, op, pthr2, rgb[0]);
   out[2] = make_float4(rgb[1], rgb[2], g.tvz, nx);
   out[3] = make_float4(ny, nz, __uint_as_float((uint32_t)idx), 0.f);
+  }   // visible
+  }   // idx < B*N
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) my_tiles += __shfl_xor_sync(0xffffffffu, my_tiles, o);
+  if ((threadIdx.x & 31) == 0 && my_tiles) atomicAdd(&s_cnt, my_tiles);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_cnt) atomicAdd(total_count, (unsigned long long)s_cnt);
 }
 
 __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
@@ -444,86 +459,6 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
   dL_dop[idx] = g_op;
 }
 
-// Emits, for every visible splat, one (frame*tiles + tile) key and its B*N index per covered tile.
-// Upstream shape: "duplicateWithKeys", with one change: thread i handles the i-th splat of the (frame, depth,
-// index)-sorted order (`perm`), and `offsets` is the inclusive scan of tile counts in that order.  Instances
-// are therefore emitted front-to-back, and a STABLE sort by the tile id alone (raster_bin.cu) yields exactly
-// the order of a full (tile | depth) 64-bit sort -- ties in depth keep ascending Gaussian index.
-// VBITS > 0 ("packed" instances): key and value share ONE 32-bit word, (key << VBITS) | (index within the frame),
-// written to `vals`; the tile sort then moves 4 instead of 8 bytes per instance and pass (raster_bin.cu).
-template <bool PACKED>
-__global__ void __launch_bounds__(256) emit_keys_kernel(
-    int64_t BN, int N, int W, int H, const float4* __restrict__ splats, const int32_t* __restrict__ radii,
-    const uint32_t* __restrict__ perm, const uint32_t* __restrict__ offsets, int64_t R,
-    uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ vals, int vbits) {
-  // Warp-cooperative: a warp owns 32 consecutive splats of the sorted order and walks their concatenated output
-  // slots 32 at a time, so the key/value stores are full 128-byte lines (one thread per splat writing its own
-  // run gave 4-byte scattered stores).  The owner of a slot is found by a 5-step shuffle search over the
-  // lanes' inclusive offsets.
-  const int lane = threadIdx.x & 31;
-  const int64_t first = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) - lane;   // this warp's first splat
-  if (first >= BN) return;
-  const int64_t i = first + lane;
-  const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
-  const uint32_t base = first == 0 ? 0u : offsets[first - 1];
-  uint32_t incl = 0, idx = 0, rect = 0, fbase = 0;
-  if (i < BN) {
-    incl = offsets[i] - base;
-    idx = perm[i];
-    const int rad = radii[idx];
-    if (rad > 0) {
-      const float4 s0 = splats[4 * (int64_t)idx + 0];
-      int x0, y0, x1, y1;
-      tile_rect(s0.x, s0.y, (float)rad, gx, gy, x0, y0, x1, y1);
-      rect = (uint32_t)x0 | ((uint32_t)y0 << 10) | ((uint32_t)(x1 - x0) << 20);   // gx, gy <= 1023 (checked by the host)
-      const uint32_t frame = idx / (uint32_t)N;
-      fbase = frame * (uint32_t)(gx * gy);
-      if (PACKED) idx -= frame * (uint32_t)N;      // index within the frame
-    }
-  }
-  // lanes past the end repeat the last valid inclusive offset (they own no slots)
-  {
-    const int last_valid = (int)min((int64_t)31, BN - 1 - first);
-    const uint32_t tail = __shfl_sync(0xffffffffu, incl, last_valid);
-    if (i >= BN) incl = tail;
-  }
-  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-  const uint32_t excl = __shfl_up_sync(0xffffffffu, incl, 1);
-  const uint32_t excl0 = lane == 0 ? 0u : excl;
-  for (uint32_t o0 = 0; o0 < total; o0 += 32) {
-    const uint32_t o = o0 + lane;
-    int s = 0;   // smallest lane with incl > o
-#pragma unroll
-    for (int step = 16; step >= 1; step >>= 1) {
-      const uint32_t v = __shfl_sync(0xffffffffu, incl, s + step - 1);
-      if (v <= o) s += step;
-    }
-    s = min(s, 31);
-    const uint32_t o_excl = __shfl_sync(0xffffffffu, excl0, s);
-    const uint32_t o_rect = __shfl_sync(0xffffffffu, rect, s);
-    const uint32_t o_fb = __shfl_sync(0xffffffffu, fbase, s);
-    const uint32_t o_idx = __shfl_sync(0xffffffffu, idx, s);
-    const int64_t slot = (int64_t)base + o;
-    if (o < total && slot < R) {
-      const uint32_t k = o - o_excl;
-      const uint32_t w = o_rect >> 20, x0 = o_rect & 1023u, y0 = (o_rect >> 10) & 1023u;
-      const uint32_t row = k / w;
-      const uint32_t key = o_fb + (y0 + row) * (uint32_t)gx + x0 + (k - row * w);
-      if (PACKED) {
-        vals[slot] = (key << vbits) | o_idx;
-      } else {
-        tile_keys[slot] = key;
-        vals[slot] = o_idx;
-      }
-    }
-  }
-}
-
-__global__ void __launch_bounds__(256) iota_kernel(int64_t n, uint32_t* __restrict__ out) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = (uint32_t)i;
-}
-
 // out[u, :] = sum over rows s with seg[s] == u of in[s, :]  (seg == NULL: every row belongs to segment 0), rows
 // added in ascending s (deterministic).  Folds the per-frame gradients of the rasteriser backward onto the inputs
 // they came from: a (motion, t) deformation shared by several views, or a parameter shared by all frames.
@@ -566,31 +501,15 @@ int preprocess_launch(
     const float* means3D, int64_t means3D_bstride, const float* scales, int64_t scales_bstride,
     const float* rotations, int64_t rotations_bstride, const float* opacities, int64_t opacities_bstride,
     const float* shs, int64_t shs_bstride, const float* colors_precomp, int64_t colors_bstride,
-    float* splats, int32_t* radii, uint32_t* tiles_touched, uint64_t* depth_keys, uint32_t* iota,
-    cudaStream_t st) {
+    float* splats, int32_t* radii, uint32_t* tiles_touched, uint32_t* rects, uint32_t* depth_keys,
+    unsigned long long* total_count, cudaStream_t st) {
   const int64_t BN = (int64_t)B * N;
   if (BN == 0) return 0;
-  iota_kernel<<<ceil_div(BN, 256), 256, 0, st>>>(BN, iota);
   preprocess_fwd_kernel<<<ceil_div(BN, 256), 256, 0, st>>>(
       B, N, W, H, sh_degree, sh_coeffs, scale_modifier, cams, frame_src, means3D, means3D_bstride, scales,
       scales_bstride, rotations, rotations_bstride, opacities, opacities_bstride, shs, shs_bstride, colors_precomp,
-      colors_bstride, reinterpret_cast<float4*>(splats), radii, tiles_touched, depth_keys);
-  DIMO_CHECK_LAUNCH();
-  return 0;
-}
-
-int emit_keys_launch(int B, int N, int W, int H, int64_t R, const float* splats, const int32_t* radii,
-                     const uint32_t* perm, const uint32_t* offsets, uint32_t* tile_keys, uint32_t* vals, int vbits,
-                     cudaStream_t st) {
-  const int64_t BN = (int64_t)B * N;
-  if (BN == 0 || R == 0) return 0;
-  DIMO_REQUIRE((W + TILE - 1) / TILE <= 1023 && (H + TILE - 1) / TILE <= 1023, "image larger than 1023 tiles per side");
-  if (vbits > 0)
-    emit_keys_kernel<true><<<ceil_div(BN, 256), 256, 0, st>>>(BN, N, W, H, reinterpret_cast<const float4*>(splats),
-                                                              radii, perm, offsets, R, tile_keys, vals, vbits);
-  else
-    emit_keys_kernel<false><<<ceil_div(BN, 256), 256, 0, st>>>(BN, N, W, H, reinterpret_cast<const float4*>(splats),
-                                                               radii, perm, offsets, R, tile_keys, vals, 0);
+      colors_bstride, reinterpret_cast<float4*>(splats), radii, tiles_touched, reinterpret_cast<uint2*>(rects),
+      depth_keys, total_count);
   DIMO_CHECK_LAUNCH();
   return 0;
 }

@@ -1,7 +1,7 @@
 """Host side of the tile rasteriser: torch owns the memory, libdimo_b200 does the work.
 
 `rasterize_batch` renders B frames that share the image size in one set of kernel launches
-(preprocess -> scan -> key emission -> radix sort -> pack -> blend) and is differentiable through
+(preprocess -> per-frame depth sort -> counting sort by tile -> blend) and is differentiable through
 `_Rasterize` (blend backward -> preprocess backward).  The single-frame reference API
 (diff_gauss / diff_gaussian_rasterization GaussianRasterizer, renderer/latent_gs_renderer.py:1147,
 1256-1277) is B=1 of the same path (dimo_b200/shims).
@@ -44,7 +44,7 @@ def _bstride(t, B, per_frame_numel, blocks=None):
 
 class RasterState:
     """Buffers kept from forward for backward / inspection (all torch-owned)."""
-    __slots__ = ("B", "N", "W", "H", "R", "count_overflow", "cams", "splats", "radii", "tiles_touched", "offsets", "perm",
+    __slots__ = ("B", "N", "W", "H", "R", "count_overflow", "cams", "splats", "radii", "tiles_touched", "rects", "perm",
                  "keys_sorted",
                  "vals_sorted", "ranges", "final_T", "n_contrib", "sh_degree", "sh_coeffs",
                  "scale_modifier", "frame_src", "n_src", "value_bits")
@@ -89,13 +89,12 @@ def _forward_impl(cams, means3D, scales, rotations, opacities, shs, colors_preco
     st.splats = torch.empty(BN, SPLAT_FLOATS, **f32)
     st.radii = torch.empty(BN, **i32)
     st.tiles_touched = torch.empty(BN, **i32)
-    st.offsets = torch.empty(BN, **i32)
+    st.rects = torch.empty(BN, 2, **i32)
     L = _lib.lib()
-    depth_keys = torch.empty(2 * BN, dtype=torch.int64, device=dev)
+    sort_scratch = torch.empty(3 * BN, **i32)
     perm2 = torch.empty(2 * BN, **i32)
     st.perm = perm2[BN:]
-    scan_bytes = L.dimo_raster_scan_temp_bytes(BN)
-    scan_temp = torch.empty(scan_bytes, dtype=torch.uint8, device=dev)
+    total = torch.empty(1, dtype=torch.int64, device=dev)
     R_host = ctypes.c_int64(0)
     s = _lib.stream()
     _lib.call("dimo_raster_preprocess", B, N, W, H, st.sh_degree, st.sh_coeffs, st.scale_modifier, _lib.ptr(cams),
@@ -106,8 +105,8 @@ def _forward_impl(cams, means3D, scales, rotations, opacities, shs, colors_preco
               _lib.ptr(opacities), _bstride(opacities, B, N),
               _lib.ptr(shs), _bstride(shs, B, N * st.sh_coeffs * 3),
               _lib.ptr(colors_precomp), _bstride(colors_precomp, B, N * 3),
-              _lib.ptr(st.splats), _lib.ptr(st.radii), _lib.ptr(st.tiles_touched), _lib.ptr(st.offsets),
-              _lib.ptr(depth_keys), _lib.ptr(perm2), _lib.ptr(scan_temp), scan_bytes,
+              _lib.ptr(st.splats), _lib.ptr(st.radii), _lib.ptr(st.tiles_touched), _lib.ptr(st.rects),
+              _lib.ptr(sort_scratch), _lib.ptr(perm2), _lib.ptr(total),
               ctypes.addressof(R_host) if capacity is None else None, s)
     if capacity is None:
         R = int(R_host.value)
@@ -122,17 +121,13 @@ def _forward_impl(cams, means3D, scales, rotations, opacities, shs, colors_preco
     Ra = max(R, 1)
     st.value_bits = int(L.dimo_raster_packed_value_bits(B, N, W, H))
     packed = st.value_bits > 0
-    keys_u = None if packed else torch.empty(Ra, **i32)
-    vals_u = torch.empty(Ra, **i32)
-    st.keys_sorted = None if packed else torch.empty(Ra, **i32)   # frame*tiles + tile, sorted (sentinel in unused slots)
+    st.keys_sorted = None if packed else torch.empty(Ra, **i32)   # frame*tiles + tile, tile-major
     st.vals_sorted = torch.empty(Ra, **i32)          # record indices, or packed (key | index-in-frame) words
     st.ranges = torch.empty(B * gx * gy, 2, **i32)
-    sort_bytes = L.dimo_raster_sort_temp_bytes(Ra)
-    sort_temp = torch.empty(sort_bytes, dtype=torch.uint8, device=dev)
-    _lib.call("dimo_raster_bin", B, N, W, H, R, _lib.ptr(st.splats), _lib.ptr(st.radii), _lib.ptr(st.perm),
-              _lib.ptr(st.offsets),
-              _lib.ptr(keys_u), _lib.ptr(vals_u), _lib.ptr(st.keys_sorted), _lib.ptr(st.vals_sorted),
-              _lib.ptr(sort_temp), sort_bytes, _lib.ptr(st.ranges),
+    bin_bytes = L.dimo_raster_bin_temp_bytes(B, N, W, H)
+    bin_temp = torch.empty(bin_bytes, dtype=torch.uint8, device=dev)
+    _lib.call("dimo_raster_bin", B, N, W, H, R, _lib.ptr(st.rects), _lib.ptr(st.perm),
+              _lib.ptr(st.keys_sorted), _lib.ptr(st.vals_sorted), _lib.ptr(bin_temp), bin_bytes, _lib.ptr(st.ranges),
               _lib.ptr(st.count_overflow), s)
     color = torch.empty(B, 3, H, W, **f32)
     # depth_normal=False: nobody reads depth / normal (the MSE + SSIM + mask step) -> the blend kernel's 3-channel

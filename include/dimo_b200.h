@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DIMO_ABI_VERSION 1
+#define DIMO_ABI_VERSION 2
 
 /* Per-frame camera block, DIMO_CAM_FLOATS floats on the device:
  *   [0:16)  viewmatrix   (world_view_transform, row-vector convention)   renderer/latent_gs_renderer.py:960
@@ -57,23 +57,23 @@ int         dimo_device_info(int* out3_host);
  * .GaussianRasterizer, :1163,1268-1277).  Batched over B frames that share W,H.
  * ------------------------------------------------------------------------------------------- */
 
-/* temp bytes for the scan over B*N counters / the radix sort of R (key,value) pairs */
-size_t dimo_raster_scan_temp_bytes(int64_t BN);
-size_t dimo_raster_sort_temp_bytes(int64_t R);
+/* bytes of stage 2's scratch buffer (per-chunk tile histograms, tile totals, tile bases) */
+size_t dimo_raster_bin_temp_bytes(int B, int N, int W, int H);
 /* Instance format of a launch set.  Returns value_bits > 0 when a tile key (B*tiles + 1 codes) and the index of a
- * Gaussian within its frame (N codes) fit one 32-bit word: stage 2 then emits, sorts and returns SINGLE words
- * (key << value_bits) | index in vals_sorted (keys_unsorted / keys_sorted are not touched and may be NULL) and the
- * tile sort is keys-only -- half the bytes of a (key, value) pair sort.  0: separate 32-bit keys and B*N indices.
+ * Gaussian within its frame (N codes) fit one 32-bit word: stage 2 then writes SINGLE words
+ * (key << value_bits) | index into vals_sorted (keys_sorted is not touched and may be NULL).  0: separate 32-bit keys
+ * and B*N indices.
  * Pass the same value to dimo_raster_blend_fwd / _bwd, which decode  record = (word & mask) + frame * N. */
 int dimo_raster_packed_value_bits(int B, int N, int W, int H);
 
-/* Stage 1: per-Gaussian projection + tile counting, depth sort of the B*N splats, inclusive scan of the tile
- * counts in (frame, depth, index) order.
- *   splats [B*N,16] f32, radii [B*N] i32, tiles_touched [B*N] u32 (Gaussian order),
- *   depth_keys [2*B*N] u64 scratch (unsorted | sorted), perm [2*B*N] u32 scratch: perm + B*N is the sorted
- *   permutation (input of stage 2), offsets [B*N] u32 = inclusive scan in sorted order.
+/* Stage 1: per-Gaussian projection + tile rectangles, total instance count, per-frame depth sort of the splats
+ * (one thread-block cluster per frame; hand-written stable LSD radix sort on the 32-bit depth bits).
+ *   splats [B*N,16] f32, radii [B*N] i32, tiles_touched [B*N] u32, rects [B*N,2] u32 (x0 | y0 << 16, x1 | y1 << 16:
+ *   the tile rectangle [x0,x1) x [y0,y1) of every splat; empty for culled ones), all in Gaussian order;
+ *   sort_scratch [3*B*N] u32, perm [2*B*N] u32 scratch: perm + B*N is, per frame, the splat indices b*N + i in
+ *   ascending (view depth, i) order, culled splats last (input of stage 2);
+ *   total_count [1] u64 (device): number of tile instances R of the launch set.
  *   shs [N,sh_coeffs,3] (or NULL) / colors_precomp [N,3] (or NULL): exactly one non-NULL.
- *   temp: dimo_raster_scan_temp_bytes(B*N) bytes.
  *   R_host: if non-NULL the stream is synchronised and the total instance count is stored there.
  *   frame_src [B] i32 (device, or NULL = identity): frame b reads means3D / rotations block frame_src[b] -- the
  *   deformation depends on (motion, t) only, so the frames of a step that differ in the view alone share one
@@ -87,24 +87,24 @@ int dimo_raster_preprocess(
     const float* opacities, int64_t opacities_bstride,
     const float* shs, int64_t shs_bstride,
     const float* colors_precomp, int64_t colors_bstride,
-    float* splats, int32_t* radii, uint32_t* tiles_touched, uint32_t* offsets,
-    uint64_t* depth_keys, uint32_t* perm,
-    void* scan_temp, size_t scan_temp_bytes,
+    float* splats, int32_t* radii, uint32_t* tiles_touched, uint32_t* rects,
+    uint32_t* sort_scratch, uint32_t* perm, uint64_t* total_count,
     int64_t* R_host, void* stream);
 
-/* Stage 2: emit (frame*tiles + tile) keys front-to-back, stable-sort by tile, per-tile ranges.
- *   perm_sorted [B*N] u32 (= perm + B*N of stage 1), keys_* [R] u32, vals_* [R] u32 (index into the B*N splat
- *   records), ranges [B*tiles,2] u32; temp: dimo_raster_sort_temp_bytes(R) bytes.
+/* Stage 2: per-tile instance lists in depth order (stable counting sort by tile) + per-tile ranges.
+ *   rects, perm_sorted (= perm + B*N) from stage 1; vals_sorted [R] u32 (index into the B*N splat records, or packed
+ *   words), keys_sorted [R] u32 (frame*tiles + tile; only in the unpacked format), ranges [B*tiles,2] u32 = [begin,
+ *   end) of every tile's list; temp: dimo_raster_bin_temp_bytes() bytes.
  *   R is the number of instance SLOTS.  count_overflow == NULL: R is the exact count read back from stage 1.
  *   count_overflow != NULL (i32[2], device, [1] zeroed by the caller once): "capacity mode" for sync-free /
- *   CUDA-graph use -- R is a capacity, unused slots carry a sentinel key that sorts last, [0] receives the true
- *   count and [1] is set to 1 if it exceeded R (the surplus instances were dropped: the caller must re-run with a
- *   larger capacity). */
+ *   CUDA-graph use -- R is a capacity, [0] receives the true count and [1] is set to 1 if it exceeded R (instances
+ *   whose slot lies beyond R were dropped and the ranges are clamped to R: the caller must re-run with a larger
+ *   capacity). */
 int dimo_raster_bin(
     int B, int N, int W, int H, int64_t R,
-    const float* splats, const int32_t* radii, const uint32_t* perm_sorted, const uint32_t* offsets,
-    uint32_t* keys_unsorted, uint32_t* vals_unsorted, uint32_t* keys_sorted, uint32_t* vals_sorted,
-    void* sort_temp, size_t sort_temp_bytes,
+    const uint32_t* rects, const uint32_t* perm_sorted,
+    uint32_t* keys_sorted, uint32_t* vals_sorted,
+    void* temp, size_t temp_bytes,
     uint32_t* ranges, int32_t* count_overflow, void* stream);
 
 /* Stage 3: per-tile front-to-back blend; tile t walks vals_sorted[ranges[t].x .. ranges[t].y) and gathers the

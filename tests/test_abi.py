@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(L, s), f"{s} declared in include/dimo_b200.h but not exported"
     L.dimo_abi_version.restype = ctypes.c_int
-    assert L.dimo_abi_version() == 1
+    assert L.dimo_abi_version() == 2
 
 
 def test_binding_table_matches_header():

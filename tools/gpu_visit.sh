@@ -23,3 +23,8 @@ if [ "$NCU" != "none" ]; then
      -f -o $OUT/${TAG}_ncu python bench.py --steps 2 --warmup 1 --min-seconds 0 --no-cpu-baseline --no-e2e --no-graph "$@" > $OUT/${TAG}_ncu_run.log 2>&1
   ls -la $OUT/${TAG}_ncu.ncu-rep
 fi
+if [ "${LAUNCH_LIST:-0}" = "1" ]; then
+  timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $OUT/${TAG}_launches.csv \
+     python bench.py --steps 2 --warmup 1 --min-seconds 0 --no-cpu-baseline --no-e2e --no-graph "$@" > $OUT/${TAG}_launches_run.log 2>&1
+  python tools/launch_summary.py $OUT/${TAG}_launches.csv | head -45
+fi
