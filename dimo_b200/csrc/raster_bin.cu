@@ -50,13 +50,27 @@ static inline int bits_for(int64_t n) {
   return bits;
 }
 
+// Lanes that hold the same `key` (its low `nbits` bits) among the lanes with `valid`: one ballot per bit.  (The
+// hardware MATCH.ANY serialises on a slow unit -- ~900 cycles per use with 16 resident warps, profiles/r2e -- while
+// ballots issue at full rate.)  Lanes with !valid get an empty set.
+__device__ __forceinline__ uint32_t warp_match(uint32_t key, int nbits, bool valid) {
+  uint32_t peers = __ballot_sync(0xffffffffu, valid);
+  for (int bit = 0; bit < nbits; ++bit) {
+    const bool p = (key >> bit) & 1u;
+    const uint32_t b = __ballot_sync(0xffffffffu, p);
+    peers &= p ? b : ~b;
+  }
+  return valid ? peers : 0u;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // 1. per-frame depth sort
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int DS_CL = 8;              // CTAs per cluster = per frame
-constexpr int DS_THREADS = 512;
+constexpr int DS_THREADS = 1024;
 constexpr int DS_WARPS = DS_THREADS / 32;
 constexpr int DS_BINS = 256;
+constexpr int DS_BATCH = 8;           // keys in flight per lane (independent loads)
 
 // keys0 [B*N] (input, depth bits); kB, kC, vB, vC [B*N] ping-pong buffers.  After the four passes vC holds, per
 // frame, the indices b*N + i in ascending (depth, i) order.
@@ -87,14 +101,22 @@ depth_sort_kernel(int N, const uint32_t* __restrict__ keys0, uint32_t* __restric
     for (int k = tid; k < DS_WARPS * DS_BINS; k += DS_THREADS) (&wc[0][0])[k] = 0;
     __syncthreads();
     // ---- count: one lane per distinct digit of the 32 keys adds the group's size to the warp's own counters ----
-    for (int i0 = wlo; i0 < whi; i0 += 32) {
-      const int i = i0 + lane;
-      const bool valid = i < whi;
-      const uint32_t key = valid ? in_k[fbase + i] : 0u;
-      const uint32_t d = valid ? ((key >> shift) & 255u) : (256u + (uint32_t)lane);   // idle lanes match nobody
-      const uint32_t peers = __match_any_sync(0xffffffffu, d);
-      if (valid && (peers & lt) == 0) wc[warp][d] += __popc(peers);
-      __syncwarp();
+    for (int i0 = wlo; i0 < whi; i0 += 32 * DS_BATCH) {
+      uint32_t key[DS_BATCH];
+#pragma unroll
+      for (int u = 0; u < DS_BATCH; ++u) {
+        const int i = i0 + 32 * u + lane;
+        key[u] = i < whi ? in_k[fbase + i] : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < DS_BATCH; ++u) {
+        if (i0 + 32 * u >= whi) break;                   // warp-uniform
+        const bool valid = i0 + 32 * u + lane < whi;
+        const uint32_t d = (key[u] >> shift) & 255u;
+        const uint32_t peers = warp_match(d, 8, valid);
+        if (valid && (peers & lt) == 0) wc[warp][d] += __popc(peers);
+        __syncwarp();
+      }
     }
     __syncthreads();
     if (tid < DS_BINS) {                          // exclusive prefix over the CTA's warps, CTA total per digit
@@ -129,20 +151,28 @@ depth_sort_kernel(int N, const uint32_t* __restrict__ keys0, uint32_t* __restric
     }
     __syncthreads();
     // ---- scatter: rank among the lanes with the same digit = position after the warp's cursor ----
-    for (int i0 = wlo; i0 < whi; i0 += 32) {
-      const int i = i0 + lane;
-      const bool valid = i < whi;
-      const uint32_t key = valid ? in_k[fbase + i] : 0u;
-      const uint32_t val = valid ? (pass == 0 ? (uint32_t)(fbase + i) : in_v[fbase + i]) : 0u;
-      const uint32_t d = valid ? ((key >> shift) & 255u) : (256u + (uint32_t)lane);
-      const uint32_t peers = __match_any_sync(0xffffffffu, d);
-      const uint32_t pos = valid ? wc[warp][d] + __popc(peers & lt) : 0u;
-      __syncwarp();
-      if (valid && (peers & lt) == 0) wc[warp][d] += __popc(peers);
-      __syncwarp();
-      if (valid) {
-        if (pass < 3) out_k[fbase + pos] = key;
-        out_v[fbase + pos] = val;
+    for (int i0 = wlo; i0 < whi; i0 += 32 * DS_BATCH) {
+      uint32_t key[DS_BATCH], val[DS_BATCH];
+#pragma unroll
+      for (int u = 0; u < DS_BATCH; ++u) {
+        const int i = i0 + 32 * u + lane;
+        key[u] = i < whi ? in_k[fbase + i] : 0u;
+        val[u] = i < whi ? (pass == 0 ? (uint32_t)(fbase + i) : in_v[fbase + i]) : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < DS_BATCH; ++u) {
+        if (i0 + 32 * u >= whi) break;
+        const bool valid = i0 + 32 * u + lane < whi;
+        const uint32_t d = (key[u] >> shift) & 255u;
+        const uint32_t peers = warp_match(d, 8, valid);
+        const uint32_t pos = valid ? wc[warp][d] + __popc(peers & lt) : 0u;
+        __syncwarp();
+        if (valid && (peers & lt) == 0) wc[warp][d] += __popc(peers);
+        __syncwarp();
+        if (valid) {
+          if (pass < 3) out_k[fbase + pos] = key[u];
+          out_v[fbase + pos] = val[u];
+        }
       }
     }
     cluster.sync();   // the pass's writes are visible to the whole cluster; cta_tot may be overwritten again
@@ -184,9 +214,10 @@ __device__ __forceinline__ void prefix2d(int* a, int gw, int gh, int t, int nthr
   sync();
 }
 
+// also writes the rectangles in sorted order (rects_sorted [B*N]) so that the scatter kernel reads them coalesced
 __global__ void __launch_bounds__(256) tile_hist_kernel(BinGeom g, const uint2* __restrict__ rects,
                                                         const uint32_t* __restrict__ perm,
-                                                        uint32_t* __restrict__ hist) {
+                                                        uint32_t* __restrict__ hist, uint2* __restrict__ rects_sorted) {
   extern __shared__ int diff[];                  // (gy+1) x (gx+1)
   const int chunk = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   const int gw = g.gx + 1, gh = g.gy + 1;
@@ -194,7 +225,11 @@ __global__ void __launch_bounds__(256) tile_hist_kernel(BinGeom g, const uint2* 
   __syncthreads();
   const int lo = min(g.N, chunk * g.per_chunk), hi = min(g.N, lo + g.per_chunk);
   const int64_t fbase = (int64_t)b * g.N;
-  for (int i = lo + tid; i < hi; i += blockDim.x) diff_add(diff, gw, rects[perm[fbase + i]]);
+  for (int i = lo + tid; i < hi; i += blockDim.x) {
+    const uint2 r = rects[perm[fbase + i]];
+    rects_sorted[fbase + i] = r;
+    diff_add(diff, gw, r);
+  }
   __syncthreads();
   prefix2d(diff, gw, gh, tid, (int)blockDim.x, [] { __syncthreads(); });
   uint32_t* out = hist + ((int64_t)b * g.nchunk + chunk) * g.T;
@@ -212,47 +247,75 @@ __global__ void __launch_bounds__(256) tile_chunk_scan_kernel(BinGeom g, uint32_
   const int b = (int)(bt / g.T), t = (int)(bt - (int64_t)b * g.T);
   uint32_t* col = hist + (int64_t)b * g.nchunk * g.T + t;
   uint32_t run = 0;
-  for (int c = 0; c < g.nchunk; ++c) {
-    const uint32_t v = col[(int64_t)c * g.T];
-    col[(int64_t)c * g.T] = run;
-    run += v;
+  for (int c0 = 0; c0 < g.nchunk; c0 += 8) {        // 8 independent loads in flight
+    uint32_t v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = c0 + u < g.nchunk ? col[(int64_t)(c0 + u) * g.T] : 0u;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (c0 + u < g.nchunk) col[(int64_t)(c0 + u) * g.T] = run;
+      run += v[u];
+    }
   }
   tile_total[bt] = run;
 }
 
-// exclusive scan over the B*T tile totals (frame-major, tile order) by ONE CTA: ranges[tile] = [begin, end), clamped
-// to `slots`; count_overflow (may be NULL): [0] = true instance count, [1] |= count > slots
+// exclusive scan over the B*T tile totals (frame-major, tile order) by ONE CTA, 4096 tiles per round (one 128-bit
+// load per thread): ranges[tile] = [begin, end), clamped to `slots`; count_overflow (may be NULL): [0] = true
+// instance count, [1] |= count > slots
 constexpr int TS_THREADS = 1024;
 __global__ void __launch_bounds__(TS_THREADS) tile_base_scan_kernel(int64_t n, int64_t slots,
                                                                     const uint32_t* __restrict__ tile_total,
                                                                     uint32_t* __restrict__ tile_base,
                                                                     uint2* __restrict__ ranges,
                                                                     int32_t* __restrict__ count_overflow) {
-  __shared__ uint32_t part[TS_THREADS];
-  const int tid = threadIdx.x;
-  const int64_t per = (n + TS_THREADS - 1) / TS_THREADS;
-  const int64_t lo = min(n, (int64_t)tid * per), hi = min(n, lo + per);
-  uint32_t sum = 0;
-  for (int64_t k = lo; k < hi; ++k) sum += tile_total[k];
-  part[tid] = sum;
-  __syncthreads();
-  for (int off = 1; off < TS_THREADS; off <<= 1) {
-    const uint32_t v = tid >= off ? part[tid - off] : 0u;
-    __syncthreads();
-    part[tid] += v;
-    __syncthreads();
-  }
-  uint32_t run = part[tid] - sum;
+  __shared__ uint32_t wsum[32];
+  __shared__ uint32_t carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t cap = (uint32_t)min(slots, (int64_t)0xFFFFFFFFll);
-  for (int64_t k = lo; k < hi; ++k) {
-    const uint32_t c = tile_total[k];
-    tile_base[k] = run;
-    ranges[k] = make_uint2(min(run, cap), min(run + c, cap));
-    run += c;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < n; base += 4 * TS_THREADS) {
+    const int64_t k0 = base + 4 * (int64_t)tid;
+    uint32_t c[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) c[u] = k0 + u < n ? tile_total[k0 + u] : 0u;
+    const uint32_t mine = c[0] + c[1] + c[2] + c[3];
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = wsum[lane], wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += v;
+      }
+      wsum[lane] = wi - w;                           // exclusive prefix of the warp sums
+    }
+    __syncthreads();
+    const uint32_t carry = carry_s;
+    uint32_t run = carry + wsum[warp] + incl - mine;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (k0 + u < n) {
+        tile_base[k0 + u] = run;
+        ranges[k0 + u] = make_uint2(min(run, cap), min(run + c[u], cap));
+      }
+      run += c[u];
+    }
+    __syncthreads();
+    if (tid == TS_THREADS - 1) carry_s = run;        // the round's total
+    __syncthreads();
   }
-  if (tid == TS_THREADS - 1 && count_overflow != nullptr) {
-    count_overflow[0] = (int32_t)part[tid];
-    if ((int64_t)part[tid] > slots) count_overflow[1] = 1;
+  if (tid == 0 && count_overflow != nullptr) {
+    count_overflow[0] = (int32_t)carry_s;
+    if ((int64_t)carry_s > slots) count_overflow[1] = 1;
   }
 }
 
@@ -260,10 +323,10 @@ __global__ void __launch_bounds__(TS_THREADS) tile_base_scan_kernel(int64_t n, i
 //   cnt[w][(gy+1) x (gx+1)]: difference array -> per-tile count of warp w -> warp w's next free slot per tile.
 template <bool PACKED>
 __global__ void __launch_bounds__(256) tile_scatter_kernel(BinGeom g, int64_t slots, int vbits,
-                                                           const uint2* __restrict__ rects,
+                                                           const uint2* __restrict__ rects_sorted,
                                                            const uint32_t* __restrict__ perm,
                                                            const uint32_t* __restrict__ hist,
-                                                           const uint32_t* __restrict__ tile_base,
+                                                           const uint32_t* __restrict__ tile_base, int tile_bits,
                                                            uint32_t* __restrict__ keys_out,
                                                            uint32_t* __restrict__ vals_out) {
   extern __shared__ int cnt_all[];
@@ -278,7 +341,7 @@ __global__ void __launch_bounds__(256) tile_scatter_kernel(BinGeom g, int64_t sl
   const int wlo = min(chi, clo + warp * per_warp), whi = min(chi, wlo + per_warp);
   const int64_t fbase = (int64_t)b * g.N;
   // ---- per-warp tile counts ----
-  for (int i = wlo + lane; i < whi; i += 32) diff_add(cnt, gw, rects[perm[fbase + i]]);
+  for (int i = wlo + lane; i < whi; i += 32) diff_add(cnt, gw, rects_sorted[fbase + i]);
   __syncwarp();
   prefix2d(cnt, gw, gh, lane, 32, [] { __syncwarp(); });
   __syncthreads();
@@ -299,12 +362,15 @@ __global__ void __launch_bounds__(256) tile_scatter_kernel(BinGeom g, int64_t sl
   // ---- scatter: the warp's instance stream, 32 instances at a time, in depth order ----
   const uint32_t lt = (1u << lane) - 1u;
   const uint32_t key_base = (uint32_t)b * (uint32_t)g.T;
+  uint32_t nidx = 0;                                 // next group's splat (prefetched while this group is walked)
+  uint2 nrect = make_uint2(0u, 0u);
+  if (wlo + lane < whi) { nidx = perm[fbase + wlo + lane]; nrect = rects_sorted[fbase + wlo + lane]; }
   for (int g0 = wlo; g0 < whi; g0 += 32) {
     const int i = g0 + lane;
-    uint32_t idx = 0, rx = 0, rw = 0, n_inst = 0;
+    uint32_t idx = nidx, rx = 0, rw = 0, n_inst = 0;
+    const uint2 r = nrect;
+    if (i + 32 < whi) { nidx = perm[fbase + i + 32]; nrect = rects_sorted[fbase + i + 32]; }
     if (i < whi) {
-      idx = perm[fbase + i];
-      const uint2 r = rects[idx];
       const uint32_t x0 = r.x & 0xFFFF, y0 = r.x >> 16, x1 = r.y & 0xFFFF, y1 = r.y >> 16;
       if (x1 > x0 && y1 > y0) {
         rx = r.x; rw = x1 - x0; n_inst = rw * (y1 - y0);
@@ -333,7 +399,7 @@ __global__ void __launch_bounds__(256) tile_scatter_kernel(BinGeom g, int64_t sl
       const uint32_t o_rw = __shfl_sync(0xffffffffu, rw, s);
       const uint32_t o_idx = __shfl_sync(0xffffffffu, idx, s);
       const bool act = o < total;
-      uint32_t tile = (uint32_t)g.T + (uint32_t)lane, cell = 0;   // idle lanes match nobody
+      uint32_t tile = 0, cell = 0;
       if (act) {
         const uint32_t k = o - o_excl;
         const uint32_t row = k / o_rw, col = k - row * o_rw;
@@ -341,7 +407,7 @@ __global__ void __launch_bounds__(256) tile_scatter_kernel(BinGeom g, int64_t sl
         tile = y * (uint32_t)g.gx + x;
         cell = y * (uint32_t)gw + x;
       }
-      const uint32_t peers = __match_any_sync(0xffffffffu, tile);
+      const uint32_t peers = warp_match(tile, tile_bits, act);
       const uint32_t slot = act ? (uint32_t)cnt[cell] + __popc(peers & lt) : 0u;
       __syncwarp();
       if (act && (peers & lt) == 0) cnt[cell] += __popc(peers);
@@ -366,7 +432,7 @@ static inline BinGeom bin_geom(int B, int N, int W, int H) {
   g.B = B; g.N = N;
   g.gx = (W + TILE - 1) / TILE; g.gy = (H + TILE - 1) / TILE;
   g.T = g.gx * g.gy;
-  int nchunk = (2 * 148 + B - 1) / (B > 0 ? B : 1);
+  int nchunk = (6 * 148 + B - 1) / (B > 0 ? B : 1);    // ~6 resident scatter CTAs per SM
   nchunk = nchunk < 4 ? 4 : (nchunk > 128 ? 128 : nchunk);
   const int by_size = (N + 255) / 256;                 // at least 256 splats per chunk
   if (nchunk > by_size) nchunk = by_size < 1 ? 1 : by_size;
@@ -413,7 +479,7 @@ int dimo_device_info(int* out3_host) {
 size_t dimo_raster_bin_temp_bytes(int B, int N, int W, int H) {
   if (B <= 0 || N <= 0 || W <= 0 || H <= 0) return 256;
   const BinGeom g = bin_geom(B, N, W, H);
-  return ((size_t)B * g.nchunk * g.T + 2 * (size_t)B * g.T) * sizeof(uint32_t) + 256;
+  return ((size_t)B * g.nchunk * g.T + 2 * (size_t)B * g.T + 2 + 2 * (size_t)B * N) * sizeof(uint32_t) + 256;
 }
 
 // Packed instances: when the tile key (bits_for(B*tiles + 1) bits) and the index of a Gaussian within its frame
@@ -490,6 +556,9 @@ int dimo_raster_bin(int B, int N, int W, int H, int64_t R, const uint32_t* rects
   uint32_t* hist = reinterpret_cast<uint32_t*>(temp);
   uint32_t* tile_total = hist + (size_t)B * g.nchunk * g.T;
   uint32_t* tile_base = tile_total + (size_t)B * g.T;
+  const size_t words = ((size_t)B * g.nchunk * g.T + 2 * (size_t)B * g.T + 1) & ~(size_t)1;   // keep uint2 alignment
+  DIMO_REQUIRE((reinterpret_cast<uintptr_t>(temp) & 7) == 0, "dimo_raster_bin: temp must be 8-byte aligned");
+  uint2* rects_sorted = reinterpret_cast<uint2*>(hist + words);
   const size_t cells = (size_t)(g.gx + 1) * (g.gy + 1) * sizeof(int);
   static bool attr_set = false;
   if (!attr_set) {
@@ -500,7 +569,7 @@ int dimo_raster_bin(int B, int N, int W, int H, int64_t R, const uint32_t* rects
   }
   const uint2* r2 = reinterpret_cast<const uint2*>(rects);
   dim3 grid(g.nchunk, B);
-  tile_hist_kernel<<<grid, 256, cells, st>>>(g, r2, perm_sorted, hist);
+  tile_hist_kernel<<<grid, 256, cells, st>>>(g, r2, perm_sorted, hist, rects_sorted);
   DIMO_CHECK_LAUNCH();
   tile_chunk_scan_kernel<<<ceil_div(ntiles, 256), 256, 0, st>>>(g, hist, tile_total);
   DIMO_CHECK_LAUNCH();
@@ -509,11 +578,11 @@ int dimo_raster_bin(int B, int N, int W, int H, int64_t R, const uint32_t* rects
   DIMO_CHECK_LAUNCH();
   if (R == 0) return 0;
   if (vbits > 0)
-    tile_scatter_kernel<true><<<grid, g.wpc * 32, g.wpc * cells, st>>>(g, R, vbits, r2, perm_sorted, hist, tile_base,
-                                                                      keys_sorted, vals_sorted);
+    tile_scatter_kernel<true><<<grid, g.wpc * 32, g.wpc * cells, st>>>(g, R, vbits, rects_sorted, perm_sorted, hist,
+                                                                      tile_base, bits_for(g.T), keys_sorted, vals_sorted);
   else
-    tile_scatter_kernel<false><<<grid, g.wpc * 32, g.wpc * cells, st>>>(g, R, 0, r2, perm_sorted, hist, tile_base,
-                                                                       keys_sorted, vals_sorted);
+    tile_scatter_kernel<false><<<grid, g.wpc * 32, g.wpc * cells, st>>>(g, R, 0, rects_sorted, perm_sorted, hist,
+                                                                       tile_base, bits_for(g.T), keys_sorted, vals_sorted);
   DIMO_CHECK_LAUNCH();
   return 0;
 }
