@@ -100,7 +100,7 @@ depth_sort_kernel(int N, const uint32_t* __restrict__ keys0, uint32_t* __restric
     uint32_t* out_v = (pass & 1) ? vC : vB;
     for (int k = tid; k < DS_WARPS * DS_BINS; k += DS_THREADS) (&wc[0][0])[k] = 0;
     __syncthreads();
-    // ---- count: one lane per distinct digit of the 32 keys adds the group's size to the warp's own counters ----
+    // ---- count: native shared-memory integer atomics on the warp's own counters (ranks are not needed yet) ----
     for (int i0 = wlo; i0 < whi; i0 += 32 * DS_BATCH) {
       uint32_t key[DS_BATCH];
 #pragma unroll
@@ -109,14 +109,8 @@ depth_sort_kernel(int N, const uint32_t* __restrict__ keys0, uint32_t* __restric
         key[u] = i < whi ? in_k[fbase + i] : 0u;
       }
 #pragma unroll
-      for (int u = 0; u < DS_BATCH; ++u) {
-        if (i0 + 32 * u >= whi) break;                   // warp-uniform
-        const bool valid = i0 + 32 * u + lane < whi;
-        const uint32_t d = (key[u] >> shift) & 255u;
-        const uint32_t peers = warp_match(d, 8, valid);
-        if (valid && (peers & lt) == 0) wc[warp][d] += __popc(peers);
-        __syncwarp();
-      }
+      for (int u = 0; u < DS_BATCH; ++u)
+        if (i0 + 32 * u + lane < whi) atomicAdd(&wc[warp][(key[u] >> shift) & 255u], 1u);
     }
     __syncthreads();
     if (tid < DS_BINS) {                          // exclusive prefix over the CTA's warps, CTA total per digit
