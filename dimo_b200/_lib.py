@@ -41,6 +41,10 @@ _SIGS = {
     "dimo_linear_wgrad_tc": (c_int, [c_int] * 3 + [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "dimo_linear_wgrad_tc_grouped": (c_int, [c_int, c_int] + [c_vp] * 10 + [c_vp]),
     "dimo_tc_debug_set": (c_int, [c_int, c_int]),
+    "dimo_timenet_workspace_bytes": (c_sz, [c_int] * 3),
+    "dimo_timenet_layout": (c_int, [c_int] * 3 + [c_vp]),
+    "dimo_timenet_fwd": (c_int, [c_int] * 3 + [c_vp] * 6 + [c_sz] + [c_vp] * 3),
+    "dimo_timenet_bwd": (c_int, [c_int] * 3 + [c_vp] * 2 + [c_sz] + [c_vp] * 7),
     "dimo_timenet_embed_fwd": (c_int, [c_int] * 3 + [c_vp] * 4 + [c_i64, c_vp]),
     "dimo_timenet_embed_bwd": (c_int, [c_int] * 3 + [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "dimo_lbs_fwd": (c_int, [c_int] * 4 + [c_vp] * 11),
@@ -112,6 +116,7 @@ _OWN_LAUNCHES = {
     "dimo_arap_connectivity": 1, "dimo_arap_energy": 1, "dimo_linear_fwd": 1,
     "dimo_linear_bwd_data": 1, "dimo_linear_tc": 1, "dimo_linear_wgrad_tc": 1, "dimo_linear_wgrad_tc_grouped": 1, "dimo_linear_bwd_weight": 1, "dimo_timenet_embed_fwd": 1,
     "dimo_timenet_embed_bwd": 1, "dimo_lbs_fwd": 1, "dimo_lbs_bwd": 1, "dimo_ssim_fwd": 1, "dimo_ssim_bwd": 1,
+    "dimo_timenet_fwd": 15, "dimo_timenet_bwd": 19,
     "dimo_sqdiff_sum": 1, "dimo_smooth_fwd": 1, "dimo_smooth_bwd": 1, "dimo_segment_sum": 1, "dimo_adam_step": 1, "dimo_transpose_grouped": 1, "dimo_gt_fetch": 1,
 }
 

@@ -32,6 +32,7 @@ SOURCES = {
     "deform.cu": [],
     "mlp.cu": [],
     "mlp_tc.cu": [],
+    "timenet_tc.cu": [],
     "ssim.cu": [],
     "optim.cu": [],
     "smooth.cu": [],

@@ -1,0 +1,781 @@
+// TimeNet (renderer/latent_gs_renderer.py:184-235) as a chain of TMA-fed tcgen05 GEMMs on PRE-SPLIT operands.
+//
+// 3xTF32:  x = hi + lo (hi = tf32(x), lo = tf32(x - hi));  X W^T ~= Xhi Whi^T + Xhi Wlo^T + Xlo Whi^T, FP32 accumulate in
+// TMEM (the 1e-4 parity bound rules out plain TF32 / BF16).  Round 1 split the operands INSIDE every GEMM
+// (LDG -> cvt -> STS per K tile: 2.45 us per tile, load / convert / MMA phases serialised).  Here every operand lives in
+// global memory already split and already in the shared-memory image the tensor core reads (canonical K-major core
+// matrices), so a K tile is moved by ONE bulk asynchronous copy per operand (cp.async.bulk -> mbarrier complete_tx) and
+// the kernel is a producer warp / MMA-issuer warp / epilogue warps pipeline with no conversion work on the critical
+// path:
+//   * weights are packed once per optimizer step (tn_pack_kernel: forward tiles W, data-gradient tiles W^T);
+//   * every GEMM's epilogue (TMEM -> registers: bias, ReLU or ReLU-mask) writes its result three ways: split tiles
+//     that are the NEXT layer's A operand, TRANSPOSED split tiles that are the weight-gradient GEMM's operand (reduction
+//     index = row index contiguous), and plain fp32 where a SIMT consumer needs it (3- / 4-wide heads, embedding);
+//   * the weight gradients of all ten 256-wide layers run as ONE grouped launch over (layer, tile, row split).
+//
+// Tile formats ("plane" = tf32 values in 32-bit words; a split tile is the hi plane followed by the lo plane):
+//   operand tile   [rows x 32 k]  offset(row, q) = ((row >> 3) * 8 + q) * 128 + (row & 7) * 16 bytes, q = 16-byte chunk
+//                  (UMMA canonical K-major, no swizzle: LBO = 128 B between k chunks, SBO = 1024 B between 8-row groups)
+//   activations    A[rb][kt]      rb = 128-row block, kt = 32-column block of the activation matrix; 2 x 16 KB
+//   weights        B[kt]          rows = output features of the GEMM (padded to a multiple of 16), 2 x rows*128 B
+//   transposed     T[rt][plane][fb]  rt = 32-row block, fb = 128-feature block; tile rows = features, k = row index
+#include "common.cuh"
+
+namespace dimo {
+
+constexpr int TN_BM = 128;                 // rows per CTA
+constexpr int TN_KT = 32;                  // k per stage
+constexpr int TN_PLANE_A = TN_BM * TN_KT * 4;          // 16 KB
+constexpr int TN_STAGE_A = 2 * TN_PLANE_A;             // 32 KB  (hi | lo)
+constexpr int TN_MAXN = 256;
+constexpr int TN_STAGE_B = 2 * TN_MAXN * TN_KT * 4;    // 64 KB
+constexpr int TN_STAGE = TN_STAGE_A + TN_STAGE_B;      // 96 KB
+constexpr int TN_SMEM = 2 * TN_STAGE + 1024;
+constexpr int TN_THREADS = 192;            // warps 0-3 epilogue, 4 producer, 5 MMA issuer
+constexpr int TN_FB_BYTES = 128 * TN_KT * 4;           // 16 KB: one 128-feature block of a transposed tile plane
+
+__device__ __forceinline__ uint32_t tn_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t tn_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void tn_split4(const float4 v, uint4& hi, uint4& lo) {
+  hi = make_uint4(tn_tf32(v.x), tn_tf32(v.y), tn_tf32(v.z), tn_tf32(v.w));
+  lo = make_uint4(tn_tf32(v.x - __uint_as_float(hi.x)), tn_tf32(v.y - __uint_as_float(hi.y)),
+                  tn_tf32(v.z - __uint_as_float(hi.z)), tn_tf32(v.w - __uint_as_float(hi.w)));
+}
+__device__ __forceinline__ void tn_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tn_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tn_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tn_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tn_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tn_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tn_mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(tn_smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tn_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   tn_smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(tn_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ uint64_t tn_desc(uint32_t saddr) {     // LBO 128 B, SBO 1024 B, no swizzle, version 1
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((128u >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((1024u >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+__device__ __forceinline__ uint32_t tn_idesc(int M, int N) {      // kind::tf32, FP32 accumulate, both operands K-major
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tn_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tn_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tn_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tn_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
+      "%24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// byte offset of (row, 16-byte chunk q) inside an operand tile plane
+__device__ __host__ __forceinline__ uint32_t tn_off(int row, int q) { return (uint32_t)((((row >> 3) * 8 + q) << 7) + ((row & 7) << 4)); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// weight packing: W [No, ld] (row-major) -> operand tiles
+// ---------------------------------------------------------------------------------------------------------------
+struct PackJob {
+  const float* W; int ld;
+  int rows;          // valid tile rows
+  int rows_pad;      // tile rows (multiple of 16)
+  int kk;            // valid reduction length
+  int nkt;           // 32-wide k tiles
+  int transposed;    // 0: tile(row n, k) = W[n][col0 + k];  1: tile(row c, k) = W[k][col0 + c]
+  int col0;
+  uint8_t* dst;      // nkt split tiles of 2 * rows_pad * 128 bytes
+  int chunk0;        // first global chunk id of this job (prefix over jobs)
+};
+constexpr int TN_MAX_PACK = 32;
+struct PackArgs { int n; int total_chunks; PackJob job[TN_MAX_PACK]; };
+
+__global__ void __launch_bounds__(256) tn_pack_kernel(const __grid_constant__ PackArgs a) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= a.total_chunks) return;
+  int j = 0;
+  while (j + 1 < a.n && g >= a.job[j + 1].chunk0) ++j;
+  const PackJob& p = a.job[j];
+  const int c = g - p.chunk0;                       // chunk index: (kt, row, q)
+  const int q = c & 7, row = (c >> 3) % p.rows_pad, kt = (c >> 3) / p.rows_pad;
+  float v[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int k = kt * TN_KT + q * 4 + e;
+    float x = 0.f;
+    if (row < p.rows && k < p.kk) x = p.transposed ? p.W[(int64_t)k * p.ld + p.col0 + row] : p.W[(int64_t)row * p.ld + p.col0 + k];
+    v[e] = x;
+  }
+  uint4 hi, lo;
+  tn_split4(make_float4(v[0], v[1], v[2], v[3]), hi, lo);
+  const size_t plane = (size_t)p.rows_pad * 128;
+  uint8_t* t = p.dst + (size_t)kt * 2 * plane + tn_off(row, q);
+  *reinterpret_cast<uint4*>(t) = hi;
+  *reinterpret_cast<uint4*>(t + plane) = lo;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// plain fp32 [R, ld] (cols valid columns, optional ReLU mask from a second plain matrix) -> split tiles + transposed tiles
+// ---------------------------------------------------------------------------------------------------------------
+struct TilesArgs {
+  int R, Rp, cols, nkt;
+  const float* X; int64_t ldx;
+  const float* mask; int64_t ldm;      // optional: X(r,c) *= [mask(r,c) > 0]
+  uint8_t* out; int out_nkt, out_kt0;  // A[rb][kt] (NULL: skip)
+  uint8_t* outT; int t_nfb, t_f0;      // T[rt][plane][fb] (NULL: skip); feature offset of column 0
+};
+
+__global__ void __launch_bounds__(256) tn_tiles_kernel(const TilesArgs p) {
+  // one thread per (row, 16-byte chunk); consecutive threads take consecutive rows (coalesced tile stores)
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nq = p.nkt * 8;
+  if (g >= (int64_t)p.Rp * nq) return;
+  const int r = (int)(g % p.Rp), qq = (int)(g / p.Rp);
+  float v[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int c = qq * 4 + e;
+    float x = 0.f;
+    if (r < p.R && c < p.cols) {
+      x = p.X[(int64_t)r * p.ldx + c];
+      if (p.mask != nullptr && !(p.mask[(int64_t)r * p.ldm + c] > 0.f)) x = 0.f;
+    }
+    v[e] = x;
+  }
+  uint4 hi, lo;
+  tn_split4(make_float4(v[0], v[1], v[2], v[3]), hi, lo);
+  const int rb = r >> 7, rl = r & 127, kt = qq >> 3, q = qq & 7;
+  if (p.out != nullptr) {
+    uint8_t* t = p.out + ((size_t)rb * p.out_nkt + p.out_kt0 + kt) * TN_STAGE_A + tn_off(rl, q);
+    *reinterpret_cast<uint4*>(t) = hi;
+    *reinterpret_cast<uint4*>(t + TN_PLANE_A) = lo;
+  }
+  if (p.outT != nullptr) {
+    const int rt = r >> 5, rq = (r & 31) >> 2, re = r & 3;
+    const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w}, l[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int f = p.t_f0 + qq * 4 + e, fb = f >> 7, fl = f & 127;
+      uint8_t* t = p.outT + (((size_t)rt * 2) * p.t_nfb + fb) * TN_FB_BYTES + tn_off(fl, rq) + re * 4;
+      *reinterpret_cast<uint32_t*>(t) = h[e];
+      *reinterpret_cast<uint32_t*>(t + (size_t)p.t_nfb * TN_FB_BYTES) = l[e];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// GEMM  D[128 rows, N] = sum over segments  A_seg[rows, k] * B_seg[N, k]^T
+// ---------------------------------------------------------------------------------------------------------------
+struct TnSeg { const uint8_t* a; int a_nkt, a_kt0; const uint8_t* b; int nkt; };
+struct TnGemmArgs {
+  int R, N;                 // valid rows; output columns (multiple of 16, <= 256)
+  int nseg; TnSeg seg[2];
+  const float* bias; int relu;
+  const uint8_t* mask; int mask_nkt, mask_kt0;     // ReLU mask source: split tiles A[rb][kt] of the activation whose sign gates column block kt
+  uint8_t* out; int out_nkt, out_kt0;              // split tiles of the result (next GEMM's A), or NULL
+  uint8_t* outT; int t_nfb, t_f0;                  // transposed split tiles (weight-gradient operand), or NULL
+  float* plain; int64_t ldp; int plain_cols, plain_acc;   // fp32 row-major copy of the first plain_cols columns, or NULL
+};
+
+__global__ void __launch_bounds__(TN_THREADS, 1) tn_gemm_kernel(const __grid_constant__ TnGemmArgs p) {
+  extern __shared__ uint8_t tn_smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2], done_bar;
+  __shared__ uint32_t tmem_slot;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tn_smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rb = blockIdx.x;
+  const uint32_t planeB = (uint32_t)p.N * 128u;
+
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tn_smem_u32(&tmem_slot)),
+                 "r"((uint32_t)TN_MAXN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    tn_mbar_init(&full_bar[0], 1); tn_mbar_init(&full_bar[1], 1);
+    tn_mbar_init(&empty_bar[0], 1); tn_mbar_init(&empty_bar[1], 1);
+    tn_mbar_init(&done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = tmem_slot;
+
+  if (warp == 4) {
+    // ===== producer: one bulk copy per operand and stage =====
+    if (lane == 0) {
+      int it = 0;
+      for (int sg = 0; sg < p.nseg; ++sg) {
+        const TnSeg& s = p.seg[sg];
+        for (int kt = 0; kt < s.nkt; ++kt, ++it) {
+          const int st = it & 1;
+          if (it >= 2) tn_mbar_wait(&empty_bar[st], (uint32_t)(((it >> 1) - 1) & 1));
+          uint8_t* sa = smem + st * TN_STAGE;
+          uint8_t* sb = sa + TN_STAGE_A;
+          tn_mbar_expect_tx(&full_bar[st], TN_STAGE_A + 2 * planeB);
+          tn_bulk_g2s(sa, s.a + ((size_t)rb * s.a_nkt + s.a_kt0 + kt) * TN_STAGE_A, TN_STAGE_A, &full_bar[st]);
+          tn_bulk_g2s(sb, s.b + (size_t)kt * 2 * planeB, 2 * planeB, &full_bar[st]);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = tn_idesc(TN_BM, p.N);
+      int total = 0;
+      for (int sg = 0; sg < p.nseg; ++sg) total += p.seg[sg].nkt;
+      for (int it = 0; it < total; ++it) {
+        const int st = it & 1;
+        tn_mbar_wait(&full_bar[st], (uint32_t)((it >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = tn_smem_u32(smem + st * TN_STAGE), sb = sa + TN_STAGE_A;
+#pragma unroll
+        for (int ks = 0; ks < TN_KT / 8; ++ks) {
+          const uint32_t koff = (uint32_t)ks * 256u;
+          const uint64_t dah = tn_desc(sa + koff), dal = tn_desc(sa + TN_PLANE_A + koff);
+          const uint64_t dbh = tn_desc(sb + koff), dbl = tn_desc(sb + planeB + koff);
+          tn_mma(tmem_d, dah, dbh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+          tn_mma(tmem_d, dah, dbl, idesc, 1u);
+          tn_mma(tmem_d, dal, dbh, idesc, 1u);
+        }
+        tn_commit(&empty_bar[st]);
+      }
+      tn_commit(&done_bar);
+    }
+  } else {
+    // ===== epilogue: warp w owns TMEM lanes / tile rows [32 w, 32 w + 32) =====
+    tn_mbar_wait(&done_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int rl = warp * 32 + lane;
+    const int gr = rb * TN_BM + rl;
+    const bool valid = gr < p.R;
+    const int rt = rb * 4 + warp;                 // this warp's 32 rows are one r tile of the transposed layout
+    for (int c = 0; c < p.N / 32 + ((p.N & 31) ? 1 : 0); ++c) {
+      uint32_t v[32];
+      tn_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
+      const int n0 = c * 32;
+      float y[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float t = __uint_as_float(v[j]);
+        if (p.bias != nullptr && n0 + j < p.N) t += p.bias[n0 + j];
+        if (p.relu) t = fmaxf(t, 0.f);
+        y[j] = (valid && n0 + j < p.N) ? t : 0.f;
+      }
+      if (p.mask != nullptr) {
+        const uint8_t* mt = p.mask + ((size_t)rb * p.mask_nkt + p.mask_kt0 + c) * TN_STAGE_A;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 mh = *reinterpret_cast<const float4*>(mt + tn_off(rl, q));
+          const float4 ml = *reinterpret_cast<const float4*>(mt + TN_PLANE_A + tn_off(rl, q));
+          if (!(mh.x > 0.f || ml.x > 0.f)) y[4 * q + 0] = 0.f;
+          if (!(mh.y > 0.f || ml.y > 0.f)) y[4 * q + 1] = 0.f;
+          if (!(mh.z > 0.f || ml.z > 0.f)) y[4 * q + 2] = 0.f;
+          if (!(mh.w > 0.f || ml.w > 0.f)) y[4 * q + 3] = 0.f;
+        }
+      }
+      if (p.out != nullptr) {
+        uint8_t* t = p.out + ((size_t)rb * p.out_nkt + p.out_kt0 + c) * TN_STAGE_A;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          uint4 hi, lo;
+          tn_split4(make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]), hi, lo);
+          *reinterpret_cast<uint4*>(t + tn_off(rl, q)) = hi;
+          *reinterpret_cast<uint4*>(t + TN_PLANE_A + tn_off(rl, q)) = lo;
+        }
+      }
+      if (p.outT != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int f = p.t_f0 + n0 + j, fb = f >> 7, fl = f & 127;
+          const uint32_t hi = tn_tf32(y[j]), lo = tn_tf32(y[j] - __uint_as_float(hi));
+          uint8_t* t = p.outT + (((size_t)rt * 2) * p.t_nfb + fb) * TN_FB_BYTES + tn_off(fl, lane >> 2) + (lane & 3) * 4;
+          *reinterpret_cast<uint32_t*>(t) = hi;
+          *reinterpret_cast<uint32_t*>(t + (size_t)p.t_nfb * TN_FB_BYTES) = lo;
+        }
+      }
+      if (p.plain != nullptr && valid) {
+        float* row = p.plain + (int64_t)gr * p.ldp + n0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n0 + j < p.plain_cols) row[j] = y[j] + (p.plain_acc ? row[j] : 0.f);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 5) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)TN_MAXN) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// grouped weight gradient  dW[n, col0 + j] += sum_r dYm[r, n] * X[r, f0 + j]   (+ db[n] += sum_r dYm[r, n])
+// A = dYm^T tiles (128-feature block a_fb), B = X^T tiles (feature blocks [b_fb0, b_fb0 + b_nfb_use)), reduction over the
+// row index in 32-row stages [rt0, rt1)
+// ---------------------------------------------------------------------------------------------------------------
+struct TnWJob {
+  const uint8_t* aT; int a_nfb, a_fb;
+  const uint8_t* bT; int b_nfb, b_fb0, b_use;      // N = 128 * b_use (1 or 2)
+  float* dW; int ldw, col0, ncols, nrows;          // output rows n < nrows, columns j < ncols
+  float* db;                                       // NULL unless this job also owns the bias gradient of its n block
+};
+constexpr int TN_MAX_WJOBS = 32;
+struct TnWTable { int n, splits, per, nrt; TnWJob job[TN_MAX_WJOBS]; };    // CTA = (job, row split)
+
+__global__ void __launch_bounds__(TN_THREADS, 1) tn_wgrad_kernel(const __grid_constant__ TnWTable tab) {
+  extern __shared__ uint8_t tn_smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2], done_bar;
+  __shared__ uint32_t tmem_slot;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tn_smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const TnWJob& p = tab.job[blockIdx.x / tab.splits];
+  const int split = blockIdx.x % tab.splits;
+  const int rt0 = split * tab.per, rt1 = min(tab.nrt, rt0 + tab.per);
+  const int N = 128 * p.b_use;
+  const uint32_t planeB = (uint32_t)N * 128u;
+  const int nst = max(0, rt1 - rt0);
+
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tn_smem_u32(&tmem_slot)),
+                 "r"((uint32_t)TN_MAXN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    tn_mbar_init(&full_bar[0], 1); tn_mbar_init(&full_bar[1], 1);
+    tn_mbar_init(&empty_bar[0], 1 + 128); tn_mbar_init(&empty_bar[1], 1 + 128);   // MMA commit + the 128 bias-gradient readers
+    tn_mbar_init(&done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int it = 0; it < nst; ++it) {
+        const int st = it & 1;
+        if (it >= 2) tn_mbar_wait(&empty_bar[st], (uint32_t)(((it >> 1) - 1) & 1));
+        uint8_t* sa = smem + st * TN_STAGE;
+        uint8_t* sb = sa + TN_STAGE_A;
+        const size_t rt = (size_t)(rt0 + it);
+        tn_mbar_expect_tx(&full_bar[st], TN_STAGE_A + 2 * planeB);
+        tn_bulk_g2s(sa, p.aT + ((rt * 2 + 0) * p.a_nfb + p.a_fb) * TN_FB_BYTES, TN_FB_BYTES, &full_bar[st]);
+        tn_bulk_g2s(sa + TN_PLANE_A, p.aT + ((rt * 2 + 1) * p.a_nfb + p.a_fb) * TN_FB_BYTES, TN_FB_BYTES, &full_bar[st]);
+        tn_bulk_g2s(sb, p.bT + ((rt * 2 + 0) * p.b_nfb + p.b_fb0) * TN_FB_BYTES, planeB, &full_bar[st]);
+        tn_bulk_g2s(sb + planeB, p.bT + ((rt * 2 + 1) * p.b_nfb + p.b_fb0) * TN_FB_BYTES, planeB, &full_bar[st]);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      const uint32_t idesc = tn_idesc(TN_BM, N);
+      for (int it = 0; it < nst; ++it) {
+        const int st = it & 1;
+        tn_mbar_wait(&full_bar[st], (uint32_t)((it >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = tn_smem_u32(smem + st * TN_STAGE), sb = sa + TN_STAGE_A;
+#pragma unroll
+        for (int ks = 0; ks < TN_KT / 8; ++ks) {
+          const uint32_t koff = (uint32_t)ks * 256u;
+          const uint64_t dah = tn_desc(sa + koff), dal = tn_desc(sa + TN_PLANE_A + koff);
+          const uint64_t dbh = tn_desc(sb + koff), dbl = tn_desc(sb + planeB + koff);
+          tn_mma(tmem_d, dah, dbh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+          tn_mma(tmem_d, dah, dbl, idesc, 1u);
+          tn_mma(tmem_d, dal, dbh, idesc, 1u);
+        }
+        tn_commit(&empty_bar[st]);
+      }
+      tn_commit(&done_bar);
+    }
+  } else {
+    // epilogue warps: thread = output row n (feature of dY); bias gradient = row sums of the A tiles as they pass by
+    const int nl = warp * 32 + lane;
+    float dbacc = 0.f;
+    for (int it = 0; it < nst; ++it) {
+      const int st = it & 1;
+      tn_mbar_wait(&full_bar[st], (uint32_t)((it >> 1) & 1));
+      if (p.db != nullptr) {
+        const uint8_t* sa = smem + st * TN_STAGE;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 h = *reinterpret_cast<const float4*>(sa + tn_off(nl, q));
+          const float4 l = *reinterpret_cast<const float4*>(sa + TN_PLANE_A + tn_off(nl, q));
+          dbacc += (h.x + l.x) + (h.y + l.y) + (h.z + l.z) + (h.w + l.w);
+        }
+      }
+      tn_mbar_arrive(&empty_bar[st]);
+    }
+    tn_mbar_wait(&done_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int n = p.a_fb * 128 + nl;
+    if (nst > 0) {
+      for (int c = 0; c < N / 32; ++c) {
+        uint32_t v[32];
+        tn_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
+        if (n < p.nrows) {
+          float* wrow = p.dW + (int64_t)n * p.ldw + p.col0 + c * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (c * 32 + j + 3 < p.ncols) {
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(wrow + j), "f"(__uint_as_float(v[j])),
+                           "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                           : "memory");
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (c * 32 + j + e < p.ncols) atomicAdd(wrow + j + e, __uint_as_float(v[j + e]));
+            }
+          }
+        }
+      }
+      if (p.db != nullptr && n < p.nrows) atomicAdd(p.db + n, dbacc);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 5) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)TN_MAXN) : "memory");
+  }
+}
+
+}  // namespace dimo
+
+using namespace dimo;
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side: workspace layout + launch sequences
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int HID = 256, NL = 12;             // layers: deformnet.0..7, pts.0, pts.2, rot.0, rot.2
+struct TnLayout {
+  int R, Rp, nrb, nrt, E, Ep;                 // E = embedding width (104), Ep = padded to 128
+  size_t w_fwd[NL], w_bwd[NL], w_bwd5b;       // packed weight tiles (byte offsets)
+  size_t h0, catT, cat_plain;                 // embedding: split tiles (4 kt), transposed [rt][2][3 fb], plain [R, E]
+  size_t y[10], yT[10];                       // outputs of layers 0..7, 8 (hp), 10 (hr): split tiles (8 kt) / transposed (2 fb)
+  size_t hp_plain, hr_plain;                  // plain [R, 256] inputs of the SIMT head layers
+  size_t g[10], gT[10];                       // masked upstream gradients of the same ten outputs: split tiles / transposed
+  size_t dhp_plain, dhr_plain, dcat_plain;    // plain scratch of the backward pass
+  size_t total;
+};
+
+inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+TnLayout tn_layout(int R, int L) {
+  TnLayout o{};
+  o.R = R; o.Rp = (R + 127) / 128 * 128; o.nrb = o.Rp / 128; o.nrt = o.Rp / 32;
+  o.E = 72 + L; o.Ep = 128;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t r = off; off = al256(off + bytes); return r; };
+  const size_t wtile = 2 * (size_t)HID * 128;                 // split weight tile, 256 rows
+  const int fwd_kt[NL] = {4, 8, 8, 8, 8, 12, 8, 8, 8, 0, 8, 0};
+  for (int l = 0; l < NL; ++l) o.w_fwd[l] = fwd_kt[l] ? take(fwd_kt[l] * wtile) : 0;
+  for (int l = 0; l < NL; ++l) {
+    if (l == 9 || l == 11) { o.w_bwd[l] = 0; continue; }
+    const size_t rows_pad = l == 0 ? 128 : HID;              // output columns of the data-gradient GEMM
+    o.w_bwd[l] = take(8 * 2 * rows_pad * 128);
+  }
+  o.w_bwd5b = take(8 * 2 * (size_t)128 * 128);
+  o.h0 = take((size_t)o.nrb * 4 * TN_STAGE_A);
+  o.catT = take((size_t)o.nrt * 2 * 3 * TN_FB_BYTES);
+  o.cat_plain = take((size_t)R * o.E * 4);
+  for (int i = 0; i < 10; ++i) {
+    o.y[i] = take((size_t)o.nrb * 8 * TN_STAGE_A);
+    o.yT[i] = i == 4 ? 0 : take((size_t)o.nrt * 2 * 2 * TN_FB_BYTES);       // layer 4's output lives in catT (fb 1, 2)
+    o.g[i] = take((size_t)o.nrb * 8 * TN_STAGE_A);
+    o.gT[i] = take((size_t)o.nrt * 2 * 2 * TN_FB_BYTES);
+  }
+  o.hp_plain = take((size_t)R * HID * 4); o.hr_plain = take((size_t)R * HID * 4);
+  o.dhp_plain = take((size_t)R * HID * 4); o.dhr_plain = take((size_t)R * HID * 4);
+  o.dcat_plain = take((size_t)R * o.E * 4);
+  o.total = off;
+  return o;
+}
+
+int tn_set_attrs() {
+  static bool done = false;
+  if (!done) {
+    DIMO_CHECK_CUDA(cudaFuncSetAttribute(tn_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM));
+    DIMO_CHECK_CUDA(cudaFuncSetAttribute(tn_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM));
+    done = true;
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int dimo_linear_fwd(int R, int K, int No, const float* X, int64_t ldx, const float* Wt, const float* bias,
+                               float* Y, int64_t ldy, int relu, void* stream);
+extern "C" int dimo_linear_bwd_data(int R, int K, int No, const float* dY, int64_t lddy, const float* Y, int64_t ldy,
+                                    const float* Wt, float* dX, int64_t lddx, int accumulate, void* stream);
+extern "C" int dimo_linear_bwd_weight(int R, int K, int No, const float* dY, int64_t lddy, const float* Y, int64_t ldy,
+                                      const float* X, int64_t ldx, float* dW, float* db, void* stream);
+extern "C" int dimo_timenet_embed_fwd(int G, int rows_per_group, int L, const float* pts, const float* times,
+                                      const float* latents, float* h0, int64_t ldh, void* stream);
+extern "C" int dimo_timenet_embed_bwd(int G, int rows_per_group, int L, const float* h0, const float* dh0, int64_t ldh,
+                                      float* dpts, float* dlatents, void* stream);
+
+extern "C" size_t dimo_timenet_workspace_bytes(int G, int M, int L) {
+  if (G <= 0 || M <= 0) return 256;
+  return tn_layout(G * M, L).total;
+}
+
+/* byte offsets of the stored activations inside the workspace (tests / debugging): out[0] = padded rows, out[1] = offset
+ * of the embedding's split tiles (4 k tiles), out[2..11] = split tiles (8 k tiles) of the outputs of deformnet.0..7,
+ * pts_layers.0, rot_layers.0 */
+extern "C" int dimo_timenet_layout(int G, int M, int L, int64_t* out12_host) {
+  const TnLayout o = tn_layout(G * M, L);
+  out12_host[0] = o.Rp; out12_host[1] = (int64_t)o.h0;
+  for (int i = 0; i < 10; ++i) out12_host[2 + i] = (int64_t)o.y[i];
+  return 0;
+}
+
+// index of a layer's output among the ten stored activations (0..7 trunk, 8 = pts_layers.0, 9 = rot_layers.0)
+static inline int tn_slot(int layer) { return layer <= 7 ? layer : (layer == 8 ? 8 : 9); }
+
+extern "C" int dimo_timenet_fwd(int G, int M, int L, const float* pts, const float* times, const float* latents,
+                                const float* const* W_host, const float* const* b_host, void* workspace,
+                                size_t workspace_bytes, float* dxyz, float* dquat, void* stream) {
+  const int R = G * M;
+  if (R == 0) return 0;
+  DIMO_REQUIRE(L >= 0 && 72 + L <= 128 && (72 + L) % 4 == 0, "TimeNet: embedding width must be a multiple of 4 and <= 128");
+  const TnLayout o = tn_layout(R, L);
+  DIMO_REQUIRE(workspace_bytes >= o.total, "TimeNet workspace too small (dimo_timenet_workspace_bytes)");
+  DIMO_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "TimeNet workspace must be 256-byte aligned");
+  if (tn_set_attrs()) return -1;
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  const int E = o.E;
+
+  // ---- pack the weights: forward tiles W and data-gradient tiles W^T, one launch ----
+  {
+    PackArgs a{};
+    int n = 0, chunks = 0;
+    auto add = [&](const float* W, int ld, int rows, int rows_pad, int kk, int nkt, int transposed, int col0, uint8_t* dst) {
+      PackJob& j = a.job[n++];
+      j.W = W; j.ld = ld; j.rows = rows; j.rows_pad = rows_pad; j.kk = kk; j.nkt = nkt; j.transposed = transposed;
+      j.col0 = col0; j.dst = dst; j.chunk0 = chunks;
+      chunks += nkt * rows_pad * 8;
+    };
+    add(W_host[0], E, HID, HID, E, 4, 0, 0, ws + o.w_fwd[0]);
+    for (int l = 1; l <= 8; ++l) {
+      if (l == 5) {                       // K order of layer 5: [out of layer 4 (256) | embedding (E)]
+        add(W_host[5], E + HID, HID, HID, HID, 8, 0, E, ws + o.w_fwd[5]);
+        add(W_host[5], E + HID, HID, HID, E, 4, 0, 0, ws + o.w_fwd[5] + 8 * 2 * (size_t)HID * 128);
+      } else {
+        add(W_host[l], HID, HID, HID, HID, 8, 0, 0, ws + o.w_fwd[l]);
+      }
+    }
+    add(W_host[10], HID, HID, HID, HID, 8, 0, 0, ws + o.w_fwd[10]);
+    // data gradient: tile rows = input features, reduction over the layer's 256 outputs
+    add(W_host[0], E, E, 128, HID, 8, 1, 0, ws + o.w_bwd[0]);
+    for (int l = 1; l <= 8; ++l) {
+      if (l == 5) {
+        add(W_host[5], E + HID, HID, HID, HID, 8, 1, E, ws + o.w_bwd[5]);
+        add(W_host[5], E + HID, E, 128, HID, 8, 1, 0, ws + o.w_bwd5b);
+      } else {
+        add(W_host[l], HID, HID, HID, HID, 8, 1, 0, ws + o.w_bwd[l]);
+      }
+    }
+    add(W_host[10], HID, HID, HID, HID, 8, 1, 0, ws + o.w_bwd[10]);
+    a.n = n; a.total_chunks = chunks;
+    tn_pack_kernel<<<ceil_div(chunks, 256), 256, 0, st>>>(a);
+    DIMO_CHECK_LAUNCH();
+  }
+  // ---- embedding (plain) -> split tiles + transposed tiles (feature block 0 of catT) ----
+  float* cat_plain = reinterpret_cast<float*>(ws + o.cat_plain);
+  int rc = dimo_timenet_embed_fwd(G, M, L, pts, times, latents, cat_plain, E, stream);
+  if (rc) return rc;
+  {
+    TilesArgs t{};
+    t.R = R; t.Rp = o.Rp; t.cols = E; t.nkt = 4; t.X = cat_plain; t.ldx = E;
+    t.out = ws + o.h0; t.out_nkt = 4; t.out_kt0 = 0; t.outT = ws + o.catT; t.t_nfb = 3; t.t_f0 = 0;
+    tn_tiles_kernel<<<ceil_div((int64_t)o.Rp * 32, 256), 256, 0, st>>>(t);
+    DIMO_CHECK_LAUNCH();
+  }
+  // ---- the ten 256-wide layers ----
+  auto gemm = [&](TnGemmArgs& g) {
+    tn_gemm_kernel<<<o.nrb, TN_THREADS, TN_SMEM, st>>>(g);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  };
+  const int order[10] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 10};
+  for (int oi = 0; oi < 10; ++oi) {
+    const int l = order[oi], slot = tn_slot(l);
+    TnGemmArgs g{};
+    g.R = R; g.N = HID; g.bias = b_host[l]; g.relu = 1;
+    if (l == 0) {
+      g.nseg = 1; g.seg[0] = TnSeg{ws + o.h0, 4, 0, ws + o.w_fwd[0], 4};
+    } else if (l == 5) {
+      g.nseg = 2;
+      g.seg[0] = TnSeg{ws + o.y[4], 8, 0, ws + o.w_fwd[5], 8};
+      g.seg[1] = TnSeg{ws + o.h0, 4, 0, ws + o.w_fwd[5] + 8 * 2 * (size_t)HID * 128, 4};
+    } else {
+      const int src = l == 10 ? 7 : l - 1;        // rot_layers.0 reads the trunk output like pts_layers.0
+      g.nseg = 1; g.seg[0] = TnSeg{ws + o.y[tn_slot(src)], 8, 0, ws + o.w_fwd[l], 8};
+    }
+    g.out = ws + o.y[slot]; g.out_nkt = 8; g.out_kt0 = 0;
+    if (l == 4) { g.outT = ws + o.catT; g.t_nfb = 3; g.t_f0 = 128; }
+    else if (l == 8 || l == 10) { g.outT = nullptr; }                 // hp / hr feed only the SIMT heads
+    else { g.outT = ws + o.yT[slot]; g.t_nfb = 2; g.t_f0 = 0; }
+    if (l == 8) { g.plain = reinterpret_cast<float*>(ws + o.hp_plain); g.ldp = HID; g.plain_cols = HID; }
+    if (l == 10) { g.plain = reinterpret_cast<float*>(ws + o.hr_plain); g.ldp = HID; g.plain_cols = HID; }
+    if (gemm(g)) { dimo::set_error("tn_gemm_kernel launch failed (layer %d)", l); return -1; }
+  }
+  // ---- 3- and 4-wide heads (FP32 SIMT) ----
+  rc = dimo_linear_fwd(R, HID, 3, reinterpret_cast<float*>(ws + o.hp_plain), HID, W_host[9], b_host[9], dxyz, 3, 0, stream);
+  if (rc) return rc;
+  return dimo_linear_fwd(R, HID, 4, reinterpret_cast<float*>(ws + o.hr_plain), HID, W_host[11], b_host[11], dquat, 4, 0, stream);
+}
+
+extern "C" int dimo_timenet_bwd(int G, int M, int L, const float* const* W_host, void* workspace, size_t workspace_bytes,
+                                const float* g_dxyz, const float* g_dquat, float* const* dW_host, float* const* db_host,
+                                float* dpts, float* dlatents, void* stream) {
+  const int R = G * M;
+  if (R == 0) return 0;
+  const TnLayout o = tn_layout(R, L);
+  DIMO_REQUIRE(workspace_bytes >= o.total, "TimeNet workspace too small (dimo_timenet_workspace_bytes)");
+  if (tn_set_attrs()) return -1;
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  const int E = o.E;
+  float* hp = reinterpret_cast<float*>(ws + o.hp_plain);
+  float* hr = reinterpret_cast<float*>(ws + o.hr_plain);
+  float* dhp = reinterpret_cast<float*>(ws + o.dhp_plain);
+  float* dhr = reinterpret_cast<float*>(ws + o.dhr_plain);
+  float* dcat = reinterpret_cast<float*>(ws + o.dcat_plain);
+  // ---- heads (FP32 SIMT): weight gradients, data gradients -> masked split tiles ----
+  int rc = dimo_linear_bwd_weight(R, HID, 3, g_dxyz, 3, nullptr, 0, hp, HID, dW_host[9], db_host[9], stream);
+  if (rc) return rc;
+  rc = dimo_linear_bwd_weight(R, HID, 4, g_dquat, 4, nullptr, 0, hr, HID, dW_host[11], db_host[11], stream);
+  if (rc) return rc;
+  rc = dimo_linear_bwd_data(R, HID, 3, g_dxyz, 3, nullptr, 0, W_host[9], dhp, HID, 0, stream);
+  if (rc) return rc;
+  rc = dimo_linear_bwd_data(R, HID, 4, g_dquat, 4, nullptr, 0, W_host[11], dhr, HID, 0, stream);
+  if (rc) return rc;
+  for (int h = 0; h < 2; ++h) {
+    TilesArgs t{};
+    t.R = R; t.Rp = o.Rp; t.cols = HID; t.nkt = 8; t.X = h ? dhr : dhp; t.ldx = HID; t.mask = h ? hr : hp; t.ldm = HID;
+    t.out = ws + o.g[8 + h]; t.out_nkt = 8; t.out_kt0 = 0; t.outT = ws + o.gT[8 + h]; t.t_nfb = 2; t.t_f0 = 0;
+    tn_tiles_kernel<<<ceil_div((int64_t)o.Rp * 64, 256), 256, 0, st>>>(t);
+    DIMO_CHECK_LAUNCH();
+  }
+  auto gemm = [&](TnGemmArgs& g) {
+    tn_gemm_kernel<<<o.nrb, TN_THREADS, TN_SMEM, st>>>(g);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  };
+  // ---- d(out of layer 7) = dhp_m W8 + dhr_m W10, masked by the sign of layer 7's output ----
+  {
+    TnGemmArgs g{};
+    g.R = R; g.N = HID; g.nseg = 2;
+    g.seg[0] = TnSeg{ws + o.g[8], 8, 0, ws + o.w_bwd[8], 8};
+    g.seg[1] = TnSeg{ws + o.g[9], 8, 0, ws + o.w_bwd[10], 8};
+    g.mask = ws + o.y[7]; g.mask_nkt = 8; g.mask_kt0 = 0;
+    g.out = ws + o.g[7]; g.out_nkt = 8; g.outT = ws + o.gT[7]; g.t_nfb = 2;
+    if (gemm(g)) { dimo::set_error("tn_gemm_kernel launch failed (heads data gradient)"); return -1; }
+  }
+  // ---- trunk, layers 7 .. 1: d(out of layer l-1) = dY_l W_l masked ----
+  for (int l = 7; l >= 1; --l) {
+    TnGemmArgs g{};
+    g.R = R; g.N = HID; g.nseg = 1;
+    g.seg[0] = TnSeg{ws + o.g[l], 8, 0, ws + o.w_bwd[l], 8};
+    g.mask = ws + o.y[l - 1]; g.mask_nkt = 8; g.mask_kt0 = 0;
+    g.out = ws + o.g[l - 1]; g.out_nkt = 8; g.outT = ws + o.gT[l - 1]; g.t_nfb = 2;
+    if (gemm(g)) { dimo::set_error("tn_gemm_kernel launch failed (data gradient, layer %d)", l); return -1; }
+    if (l == 5) {                     // the embedding part of layer 5's input: plain, no mask
+      TnGemmArgs e{};
+      e.R = R; e.N = 128; e.nseg = 1;
+      e.seg[0] = TnSeg{ws + o.g[5], 8, 0, ws + o.w_bwd5b, 8};
+      e.plain = dcat; e.ldp = E; e.plain_cols = E; e.plain_acc = 0;
+      if (gemm(e)) { dimo::set_error("tn_gemm_kernel launch failed (data gradient, layer 5 embedding part)"); return -1; }
+    }
+  }
+  {                                   // layer 0: d(embedding) += dY_0 W_0
+    TnGemmArgs e{};
+    e.R = R; e.N = 128; e.nseg = 1;
+    e.seg[0] = TnSeg{ws + o.g[0], 8, 0, ws + o.w_bwd[0], 8};
+    e.plain = dcat; e.ldp = E; e.plain_cols = E; e.plain_acc = 1;
+    if (gemm(e)) { dimo::set_error("tn_gemm_kernel launch failed (data gradient, layer 0)"); return -1; }
+  }
+  if (dpts != nullptr || dlatents != nullptr) {
+    rc = dimo_timenet_embed_bwd(G, M, L, reinterpret_cast<float*>(ws + o.cat_plain), dcat, E, dpts, dlatents, stream);
+    if (rc) return rc;
+  }
+  // ---- weight gradients of the ten 256-wide layers: one grouped launch over (job, row split) ----
+  {
+    TnWTable tab{};
+    int n = 0;
+    tab.splits = o.nrt >= 64 ? 8 : (o.nrt >= 16 ? 4 : (o.nrt >= 4 ? 2 : 1));
+    tab.per = (o.nrt + tab.splits - 1) / tab.splits;
+    tab.nrt = o.nrt;
+    auto add = [&](const uint8_t* aT, int a_fb, const uint8_t* bT, int b_nfb, int b_fb0, int b_use, float* dW, int ldw,
+                   int col0, int ncols, float* db) {
+      TnWJob& j = tab.job[n++];
+      j.aT = aT; j.a_nfb = 2; j.a_fb = a_fb; j.bT = bT; j.b_nfb = b_nfb; j.b_fb0 = b_fb0; j.b_use = b_use;
+      j.dW = dW; j.ldw = ldw; j.col0 = col0; j.ncols = ncols; j.nrows = HID; j.db = db;
+    };
+    const int order[10] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 10};
+    for (int oi = 0; oi < 10; ++oi) {
+      const int l = order[oi], slot = tn_slot(l);
+      for (int nb = 0; nb < 2; ++nb) {
+        const uint8_t* aT = ws + o.gT[slot];
+        if (l == 0) {
+          add(aT, nb, ws + o.catT, 3, 0, 1, dW_host[0], E, 0, E, db_host[0]);
+        } else if (l == 5) {
+          add(aT, nb, ws + o.catT, 3, 0, 1, dW_host[5], E + HID, 0, E, db_host[5]);
+          add(aT, nb, ws + o.catT, 3, 1, 2, dW_host[5], E + HID, E, HID, nullptr);
+        } else {
+          const int src = l == 10 ? 7 : l - 1;
+          const uint8_t* bT = src == 4 ? ws + o.catT : ws + o.yT[tn_slot(src)];
+          add(aT, nb, bT, src == 4 ? 3 : 2, src == 4 ? 1 : 0, 2, dW_host[l], HID, 0, HID, db_host[l]);
+        }
+      }
+    }
+    tab.n = n;
+    tn_wgrad_kernel<<<n * tab.splits, TN_THREADS, TN_SMEM, st>>>(tab);
+    DIMO_CHECK_LAUNCH();
+  }
+  return 0;
+}

@@ -21,6 +21,80 @@ PTS_FREQS, TIME_FREQS, HIDDEN, DEPTH, SKIP_AFTER = 10, 6, 256, 8, 4
 USE_TC = os.environ.get("DIMO_TC", "1") != "0"
 TC_FWD = TC_DGRAD = TC_WGRAD = True      # per-operation switches (bring-up / A-B tests); all on by default
 DEBUG_CAPTURE = None                      # list -> forward activations are cloned into it (bring-up only)
+# DIMO_TIMENET=layers: round 1's per-layer kernels (operands split inside every GEMM); default: dimo_timenet_fwd / _bwd,
+# one C-ABI call per direction over pre-split, TMA-fed operands (csrc/timenet_tc.cu)
+USE_CHAIN = os.environ.get("DIMO_TIMENET", "chain") != "layers"
+
+
+def _untile(ws, off, rows_pad, nkt):
+    """split tiles A[rb][kt] (csrc/timenet_tc.cu) -> plain fp32 [rows_pad, 32 * nkt] (hi + lo); tests / debugging"""
+    nrb = rows_pad // 128
+    t = ws[off:off + nrb * nkt * 32768].view(torch.float32).view(nrb, nkt, 2, 16, 8, 8, 4)   # rb, kt, plane, row group, q, row, e
+    t = t.sum(dim=2)
+    return t.permute(0, 2, 4, 1, 3, 5).reshape(nrb * 128, nkt * 32)
+
+
+class _TimeNetChainFn(torch.autograd.Function):
+    """Same contract as _TimeNetFn; forward and backward are one C-ABI call each (dimo_timenet_fwd / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, pts, times, latents, sink, *params):
+        ctx.sink = sink
+        dev = pts.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        pts = pts.contiguous().float(); times = times.contiguous().float(); latents = latents.contiguous().float()
+        params = [p.contiguous().float() for p in params]
+        Ws, bs = params[0::2], params[1::2]
+        M, G, L = pts.shape[0], times.shape[0], latents.shape[1]
+        lib = _lib.lib()
+        nbytes = int(lib.dimo_timenet_workspace_bytes(G, M, L))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        dxyz = torch.empty(G, M, 3, **f32)
+        dquat = torch.empty(G, M, 4, **f32)
+        wp = (ctypes.c_void_p * 12)(*[w.data_ptr() for w in Ws])
+        bp = (ctypes.c_void_p * 12)(*[b.data_ptr() for b in bs])
+        _lib.call("dimo_timenet_fwd", G, M, L, _lib.ptr(pts), _lib.ptr(times), _lib.ptr(latents), wp, bp, _lib.ptr(ws),
+                  nbytes, _lib.ptr(dxyz), _lib.ptr(dquat), _lib.stream())
+        ctx.save_for_backward(ws, *Ws)
+        ctx.dims = (M, G, L, nbytes)
+        if DEBUG_CAPTURE is not None:
+            lay = (ctypes.c_int64 * 12)()
+            lib.dimo_timenet_layout(G, M, L, lay)
+            R, E = G * M, 72 + L
+            acts = [_untile(ws, int(lay[2 + i]), int(lay[0]), 8)[:R].clone() for i in range(10)]
+            h0 = _untile(ws, int(lay[1]), int(lay[0]), 4)[:R, :E]
+            cat = torch.cat([h0, acts[SKIP_AFTER]], dim=1)
+            DEBUG_CAPTURE.append([cat, acts[8], acts[9]] + [a for i, a in enumerate(acts[:DEPTH]) if i != SKIP_AFTER])
+        return dxyz, dquat
+
+    @staticmethod
+    def backward(ctx, g_dxyz, g_dquat):
+        M, G, L, nbytes = ctx.dims
+        ws, *Ws = ctx.saved_tensors
+        dev = ws.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        g_dxyz = (g_dxyz if g_dxyz is not None else torch.zeros(G, M, 3, **f32)).contiguous().float()
+        g_dquat = (g_dquat if g_dquat is not None else torch.zeros(G, M, 4, **f32)).contiguous().float()
+        sink = ctx.sink
+        if sink is not None:
+            dWs, dbs = list(sink[0::2]), list(sink[1::2])
+        else:
+            dWs = [torch.zeros_like(W) for W in Ws]
+            dbs = [torch.zeros(W.shape[0], **f32) for W in Ws]
+        need_pts, need_lat = ctx.needs_input_grad[0], ctx.needs_input_grad[2]
+        dpts = torch.zeros(M, 3, **f32) if need_pts else None
+        dlat = torch.zeros(G, L, **f32) if need_lat else None
+        wp = (ctypes.c_void_p * 12)(*[w.data_ptr() for w in Ws])
+        dwp = (ctypes.c_void_p * 12)(*[w.data_ptr() for w in dWs])
+        dbp = (ctypes.c_void_p * 12)(*[b.data_ptr() for b in dbs])
+        _lib.call("dimo_timenet_bwd", G, M, L, wp, _lib.ptr(ws), nbytes, _lib.ptr(g_dxyz), _lib.ptr(g_dquat), dwp, dbp,
+                  _lib.ptr(dpts), _lib.ptr(dlat), _lib.stream())
+        if sink is not None:
+            return (dpts, None, dlat, None, *([None] * (2 * len(Ws))))
+        grads = []
+        for W, b in zip(dWs, dbs):
+            grads += [W, b]
+        return (dpts, None, dlat, None, *grads)
 
 
 def _linear_fwd(R, K, No, X, ldx, W, b, Y, ldy, relu, s):
@@ -251,6 +325,9 @@ class TimeNet(nn.Module):
             sink = [p.grad for p in ps]
             if any(g is None or not g.is_contiguous() for g in sink):
                 raise RuntimeError("TimeNet.direct_grads needs every parameter's .grad preallocated (FlatGradReducer)")
+        L = latents.shape[1]
+        if USE_TC and USE_CHAIN and (72 + L) % 4 == 0 and 72 + L <= 128:
+            return _TimeNetChainFn.apply(pts, times, latents, sink, *ps)
         return _TimeNetFn.apply(pts, times, latents, sink, *ps)
 
     def forward(self, pts, t, latent_code, nobatch=False, t_apply=False):

@@ -221,6 +221,27 @@ int dimo_linear_wgrad_tc_grouped(int n, int R, const int* K, const int* No, cons
                                  const int64_t* lddy, const float* const* mask, const int64_t* ldm,
                                  const float* const* X, const int64_t* ldx, float* const* dW, float* const* db,
                                  void* stream);
+/* ---------------------------------------------------------------------------------------------
+ * TimeNet as ONE call per direction (renderer/latent_gs_renderer.py:205-235: pos-enc + 12 F.linear; autograd backward):
+ * TMA-fed tcgen05 GEMMs on operands that are stored pre-split (3xTF32 hi / lo) in the tensor core's shared-memory
+ * layout (csrc/timenet_tc.cu).  G (motion, t) groups x M points = R rows; L = latent width (72 + L <= 128).
+ *   W_host / b_host / dW_host / db_host: HOST arrays of 12 DEVICE pointers in the order deformnet.0..7, pts_layers.0,
+ *   pts_layers.2, rot_layers.0, rot_layers.2 (weights [out, in] row-major).
+ *   workspace: dimo_timenet_workspace_bytes(G, M, L) bytes, 256-byte aligned; written by _fwd (packed weights, every
+ *   activation as split tiles + transposed split tiles) and consumed by _bwd -- keep it alive in between.
+ *   _fwd: dxyz [R,3], dquat [R,4].
+ *   _bwd: g_dxyz / g_dquat upstream gradients; dW / db are ACCUMULATED into (caller zeroes; they may be views of the
+ *   flat gradient buffer); dpts [M,3] / dlatents [G,L] (may be NULL) are accumulated into as well (caller zeroes).
+ * ------------------------------------------------------------------------------------------- */
+size_t dimo_timenet_workspace_bytes(int G, int M, int L);
+int dimo_timenet_layout(int G, int M, int L, int64_t* out12_host);
+int dimo_timenet_fwd(int G, int M, int L, const float* pts, const float* times, const float* latents,
+                     const float* const* W_host, const float* const* b_host, void* workspace, size_t workspace_bytes,
+                     float* dxyz, float* dquat, void* stream);
+int dimo_timenet_bwd(int G, int M, int L, const float* const* W_host, void* workspace, size_t workspace_bytes,
+                     const float* g_dxyz, const float* g_dquat, float* const* dW_host, float* const* db_host,
+                     float* dpts, float* dlatents, void* stream);
+
 /* bring-up knobs (0: swap LBO/SBO, 1: single-pass TF32, 2: wgrad CTA target, 3: blend gather via 16-byte
  * cp.async instead of 64-byte bulk copies, 4 / 5: records per stage of the blend backward / forward, 64 or 128, 6: 1 = never pack
  * instances into single words); not part of the stable ABI */
