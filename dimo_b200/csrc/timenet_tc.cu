@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(256) tn_tiles_kernel(const TilesArgs p) {
 // ---------------------------------------------------------------------------------------------------------------
 struct TnSeg { const uint8_t* a; int a_nkt, a_kt0; const uint8_t* b; int nkt; };
 struct TnGemmArgs {
-  int R, N;                 // valid rows; output columns (multiple of 16, <= 256)
+  int R, N;                 // valid rows; output columns: 128 or 256 (the weight tiles hold N rows)
   int nseg; TnSeg seg[2];
   const float* bias; int relu;
   const uint8_t* mask; int mask_nkt, mask_kt0;     // ReLU mask source: split tiles A[rb][kt] of the activation whose sign gates column block kt
@@ -216,24 +216,34 @@ struct TnGemmArgs {
   float* plain; int64_t ldp; int plain_cols, plain_acc;   // fp32 row-major copy of the first plain_cols columns, or NULL
 };
 
-__global__ void __launch_bounds__(TN_THREADS, 1) tn_gemm_kernel(const __grid_constant__ TnGemmArgs p) {
+// One CTA = 128 rows x 128 output columns (grid.y = N / 128).  10 warps: 0-7 epilogue (warp w: TMEM lanes 32 (w & 3),
+// columns 64 (w >> 2) + [0, 64)), 8 producer, 9 MMA issuer; three 64 KB stages.
+constexpr int TG_NB = 128;
+constexpr int TG_STAGE_B = 2 * TG_NB * TN_KT * 4;           // 32 KB
+constexpr int TG_STAGE = TN_STAGE_A + TG_STAGE_B;           // 64 KB
+constexpr int TG_STAGES = 3;
+constexpr int TG_SMEM = TG_STAGES * TG_STAGE + 1024;
+constexpr int TG_THREADS = 320;
+
+__global__ void __launch_bounds__(TG_THREADS, 1) tn_gemm_kernel(const __grid_constant__ TnGemmArgs p) {
   extern __shared__ uint8_t tn_smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2], done_bar;
+  __shared__ __align__(8) uint64_t full_bar[TG_STAGES], empty_bar[TG_STAGES], done_bar;
   __shared__ uint32_t tmem_slot;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tn_smem_raw) + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int rb = blockIdx.x;
-  const uint32_t planeB = (uint32_t)p.N * 128u;
+  const int rb = blockIdx.x, cb = blockIdx.y;
+  const uint32_t planeB_full = (uint32_t)p.N * 128u;          // bytes of one plane of a packed weight tile (all N rows)
+  constexpr uint32_t planeB = TG_NB * 128u;                   // this CTA's 128 rows of it
 
-  if (warp == 5) {
+  if (warp == 9) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tn_smem_u32(&tmem_slot)),
-                 "r"((uint32_t)TN_MAXN)
+                 "r"((uint32_t)TG_NB)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
-    tn_mbar_init(&full_bar[0], 1); tn_mbar_init(&full_bar[1], 1);
-    tn_mbar_init(&empty_bar[0], 1); tn_mbar_init(&empty_bar[1], 1);
+#pragma unroll
+    for (int s = 0; s < TG_STAGES; ++s) { tn_mbar_init(&full_bar[s], 1); tn_mbar_init(&empty_bar[s], 1); }
     tn_mbar_init(&done_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -242,34 +252,36 @@ __global__ void __launch_bounds__(TN_THREADS, 1) tn_gemm_kernel(const __grid_con
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = tmem_slot;
 
-  if (warp == 4) {
-    // ===== producer: one bulk copy per operand and stage =====
+  if (warp == 8) {
+    // ===== producer: three bulk copies per stage (A split tile, B hi rows, B lo rows) =====
     if (lane == 0) {
       int it = 0;
       for (int sg = 0; sg < p.nseg; ++sg) {
         const TnSeg& s = p.seg[sg];
         for (int kt = 0; kt < s.nkt; ++kt, ++it) {
-          const int st = it & 1;
-          if (it >= 2) tn_mbar_wait(&empty_bar[st], (uint32_t)(((it >> 1) - 1) & 1));
-          uint8_t* sa = smem + st * TN_STAGE;
+          const int st = it % TG_STAGES, round = it / TG_STAGES;
+          if (round > 0) tn_mbar_wait(&empty_bar[st], (uint32_t)((round - 1) & 1));
+          uint8_t* sa = smem + st * TG_STAGE;
           uint8_t* sb = sa + TN_STAGE_A;
+          const uint8_t* bt = s.b + (size_t)kt * 2 * planeB_full + (size_t)cb * planeB;
           tn_mbar_expect_tx(&full_bar[st], TN_STAGE_A + 2 * planeB);
           tn_bulk_g2s(sa, s.a + ((size_t)rb * s.a_nkt + s.a_kt0 + kt) * TN_STAGE_A, TN_STAGE_A, &full_bar[st]);
-          tn_bulk_g2s(sb, s.b + (size_t)kt * 2 * planeB, 2 * planeB, &full_bar[st]);
+          tn_bulk_g2s(sb, bt, planeB, &full_bar[st]);
+          tn_bulk_g2s(sb + planeB, bt + planeB_full, planeB, &full_bar[st]);
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      const uint32_t idesc = tn_idesc(TN_BM, p.N);
+      const uint32_t idesc = tn_idesc(TN_BM, TG_NB);
       int total = 0;
       for (int sg = 0; sg < p.nseg; ++sg) total += p.seg[sg].nkt;
       for (int it = 0; it < total; ++it) {
-        const int st = it & 1;
-        tn_mbar_wait(&full_bar[st], (uint32_t)((it >> 1) & 1));
+        const int st = it % TG_STAGES, round = it / TG_STAGES;
+        tn_mbar_wait(&full_bar[st], (uint32_t)(round & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = tn_smem_u32(smem + st * TN_STAGE), sb = sa + TN_STAGE_A;
+        const uint32_t sa = tn_smem_u32(smem + st * TG_STAGE), sb = sa + TN_STAGE_A;
 #pragma unroll
         for (int ks = 0; ks < TN_KT / 8; ++ks) {
           const uint32_t koff = (uint32_t)ks * 256u;
@@ -284,55 +296,76 @@ __global__ void __launch_bounds__(TN_THREADS, 1) tn_gemm_kernel(const __grid_con
       tn_commit(&done_bar);
     }
   } else {
-    // ===== epilogue: warp w owns TMEM lanes / tile rows [32 w, 32 w + 32) =====
+    // ===== epilogue =====
     tn_mbar_wait(&done_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int rl = warp * 32 + lane;
+    const int lg = warp & 3;                       // TMEM lane group = tile rows [32 lg, 32 lg + 32)
+    const int rl = lg * 32 + lane;
     const int gr = rb * TN_BM + rl;
     const bool valid = gr < p.R;
-    const int rt = rb * 4 + warp;                 // this warp's 32 rows are one r tile of the transposed layout
-    for (int c = 0; c < p.N / 32 + ((p.N & 31) ? 1 : 0); ++c) {
+    const int rt = rb * 4 + lg;                    // these 32 rows are one r tile of the transposed layout
+    const uint32_t row_off = tn_off(rl, 0);        // (row, chunk q) -> row_off + 128 q
+    const uint32_t t_lane = (uint32_t)((lane >> 2) * 128 + (lane & 3) * 4);
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      const int lc0 = (warp >> 2) * 64 + c * 32;   // column within the CTA's 128
+      const int n0 = cb * TG_NB + lc0;             // column of the GEMM's N
       uint32_t v[32];
-      tn_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
-      const int n0 = c * 32;
+      tn_ld32(tmem_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)lc0, v);
       float y[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float t = __uint_as_float(v[j]);
-        if (p.bias != nullptr && n0 + j < p.N) t += p.bias[n0 + j];
-        if (p.relu) t = fmaxf(t, 0.f);
-        y[j] = (valid && n0 + j < p.N) ? t : 0.f;
-      }
-      if (p.mask != nullptr) {
-        const uint8_t* mt = p.mask + ((size_t)rb * p.mask_nkt + p.mask_kt0 + c) * TN_STAGE_A;
+      if (p.bias != nullptr) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const float4 mh = *reinterpret_cast<const float4*>(mt + tn_off(rl, q));
-          const float4 ml = *reinterpret_cast<const float4*>(mt + TN_PLANE_A + tn_off(rl, q));
+          const float4 bb = b4[q];
+          y[4 * q] = __uint_as_float(v[4 * q]) + bb.x; y[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + bb.y;
+          y[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + bb.z; y[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + bb.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(v[j]);
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
+      }
+      if (!valid) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) y[j] = 0.f;
+      }
+      const int kt_out = n0 >> 5;                  // this chunk is k tile kt_out of the result / of the mask source
+      if (p.mask != nullptr) {
+        const uint8_t* mt = p.mask + ((size_t)rb * p.mask_nkt + p.mask_kt0 + kt_out) * TN_STAGE_A + row_off;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 mh = *reinterpret_cast<const float4*>(mt + 128 * q);
+          const float4 ml = *reinterpret_cast<const float4*>(mt + TN_PLANE_A + 128 * q);
           if (!(mh.x > 0.f || ml.x > 0.f)) y[4 * q + 0] = 0.f;
           if (!(mh.y > 0.f || ml.y > 0.f)) y[4 * q + 1] = 0.f;
           if (!(mh.z > 0.f || ml.z > 0.f)) y[4 * q + 2] = 0.f;
           if (!(mh.w > 0.f || ml.w > 0.f)) y[4 * q + 3] = 0.f;
         }
       }
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { hi[j] = tn_tf32(y[j]); lo[j] = tn_tf32(y[j] - __uint_as_float(hi[j])); }
       if (p.out != nullptr) {
-        uint8_t* t = p.out + ((size_t)rb * p.out_nkt + p.out_kt0 + c) * TN_STAGE_A;
+        uint8_t* t = p.out + ((size_t)rb * p.out_nkt + p.out_kt0 + kt_out) * TN_STAGE_A + row_off;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          uint4 hi, lo;
-          tn_split4(make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]), hi, lo);
-          *reinterpret_cast<uint4*>(t + tn_off(rl, q)) = hi;
-          *reinterpret_cast<uint4*>(t + TN_PLANE_A + tn_off(rl, q)) = lo;
+          *reinterpret_cast<uint4*>(t + 128 * q) = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+          *reinterpret_cast<uint4*>(t + TN_PLANE_A + 128 * q) = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
         }
       }
       if (p.outT != nullptr) {
+        // feature f = t_f0 + n0 + j with (t_f0 + n0) a multiple of 32: one feature block, consecutive tile rows
+        const int f0 = p.t_f0 + n0, fb = f0 >> 7, fl0 = f0 & 127;
+        uint8_t* t = p.outT + (((size_t)rt * 2) * p.t_nfb + fb) * TN_FB_BYTES + (size_t)(fl0 >> 3) * 1024 + t_lane;
+        const size_t lo_off = (size_t)p.t_nfb * TN_FB_BYTES;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const int f = p.t_f0 + n0 + j, fb = f >> 7, fl = f & 127;
-          const uint32_t hi = tn_tf32(y[j]), lo = tn_tf32(y[j] - __uint_as_float(hi));
-          uint8_t* t = p.outT + (((size_t)rt * 2) * p.t_nfb + fb) * TN_FB_BYTES + tn_off(fl, lane >> 2) + (lane & 3) * 4;
-          *reinterpret_cast<uint32_t*>(t) = hi;
-          *reinterpret_cast<uint32_t*>(t + (size_t)p.t_nfb * TN_FB_BYTES) = lo;
+          *reinterpret_cast<uint32_t*>(t + (j >> 3) * 1024 + (j & 7) * 16) = hi[j];
+          *reinterpret_cast<uint32_t*>(t + lo_off + (j >> 3) * 1024 + (j & 7) * 16) = lo[j];
         }
       }
       if (p.plain != nullptr && valid) {
@@ -345,8 +378,8 @@ __global__ void __launch_bounds__(TN_THREADS, 1) tn_gemm_kernel(const __grid_con
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 5) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)TN_MAXN) : "memory");
+  if (warp == 9) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)TG_NB) : "memory");
   }
 }
 
@@ -538,7 +571,7 @@ TnLayout tn_layout(int R, int L) {
 int tn_set_attrs() {
   static bool done = false;
   if (!done) {
-    DIMO_CHECK_CUDA(cudaFuncSetAttribute(tn_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM));
+    DIMO_CHECK_CUDA(cudaFuncSetAttribute(tn_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
     DIMO_CHECK_CUDA(cudaFuncSetAttribute(tn_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM));
     done = true;
   }
@@ -638,7 +671,7 @@ extern "C" int dimo_timenet_fwd(int G, int M, int L, const float* pts, const flo
   }
   // ---- the ten 256-wide layers ----
   auto gemm = [&](TnGemmArgs& g) {
-    tn_gemm_kernel<<<o.nrb, TN_THREADS, TN_SMEM, st>>>(g);
+    tn_gemm_kernel<<<dim3(o.nrb, g.N / TG_NB), TG_THREADS, TG_SMEM, st>>>(g);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
   };
   const int order[10] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 10};
@@ -703,7 +736,7 @@ extern "C" int dimo_timenet_bwd(int G, int M, int L, const float* const* W_host,
     DIMO_CHECK_LAUNCH();
   }
   auto gemm = [&](TnGemmArgs& g) {
-    tn_gemm_kernel<<<o.nrb, TN_THREADS, TN_SMEM, st>>>(g);
+    tn_gemm_kernel<<<dim3(o.nrb, g.N / TG_NB), TG_THREADS, TG_SMEM, st>>>(g);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
   };
   // ---- d(out of layer 7) = dhp_m W8 + dhr_m W10, masked by the sign of layer 7's output ----
