@@ -52,6 +52,30 @@ __global__ void __launch_bounds__(256) gt_fetch_kernel(int S, int Hs, int Ws, in
   }
 }
 
+// Equal sizes (no resampling), 8-bit store: pure gather + convert.  One thread = 16 consecutive samples of one plane:
+// one 128-bit load, four 128-bit stores (the generic kernel moves one sample per thread with 1-byte loads: 7.5 % of
+// the HBM peak, profiles/r1q_widen_bench.jsonl).
+__global__ void __launch_bounds__(256) gt_convert_u8_kernel(int S, int64_t plane16, const uint8_t* __restrict__ store,
+                                                            const int32_t* __restrict__ slots, float* __restrict__ rgb,
+                                                            float* __restrict__ mask) {
+  const int64_t total = (int64_t)S * 4 * plane16;       // plane16 = H * W / 16
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = e % plane16;
+    const int c = (int)((e / plane16) % 4);
+    const int s = (int)(e / (4 * plane16));
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(store + ((int64_t)slots[s] * 4 + c) * plane16 * 16) + v);
+    float* dst = c < 3 ? rgb + ((int64_t)s * 3 + c) * plane16 * 16 : mask + (int64_t)s * plane16 * 16;
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float4 o;
+      o.x = (float)(w[k] & 0xFF) / 255.0f; o.y = (float)((w[k] >> 8) & 0xFF) / 255.0f;
+      o.z = (float)((w[k] >> 16) & 0xFF) / 255.0f; o.w = (float)(w[k] >> 24) / 255.0f;
+      reinterpret_cast<float4*>(dst)[v * 4 + k] = o;
+    }
+  }
+}
+
 }  // namespace dimo
 
 using namespace dimo;
@@ -64,6 +88,15 @@ extern "C" int dimo_gt_fetch(int S, int Hs, int Ws, int Ho, int Wo, int store_is
   const int64_t total = (int64_t)S * 4 * Ho * Wo;
   const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   cudaStream_t st = (cudaStream_t)stream;
+  const int64_t plane = (int64_t)Hs * Ws;
+  if (store_is_u8 && Hs == Ho && Ws == Wo && (plane & 15) == 0 && ((uintptr_t)store & 15) == 0 &&
+      ((uintptr_t)rgb & 15) == 0 && ((uintptr_t)mask & 15) == 0) {
+    const int64_t items = (int64_t)S * 4 * (plane / 16);
+    const int g2 = (int)((items + 255) / 256 < 148 * 16 ? (items + 255) / 256 : 148 * 16);
+    gt_convert_u8_kernel<<<g2, 256, 0, st>>>(S, plane / 16, (const uint8_t*)store, slots, rgb, mask);
+    DIMO_CHECK_LAUNCH();
+    return 0;
+  }
   if (store_is_u8)
     gt_fetch_kernel<uint8_t><<<grid, 256, 0, st>>>(S, Hs, Ws, Ho, Wo, sy, sx, (const uint8_t*)store, slots, rgb, mask);
   else

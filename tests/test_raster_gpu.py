@@ -295,3 +295,42 @@ def test_raster_properties_full_size(cuda):
     out = draster.rasterize_batch(cams, leaves[0], leaves[1], leaves[2], leaves[3], W, H, shs=leaves[4])
     (out[0].sum() * 0.0).backward()
     assert all(float(l.grad.abs().max()) == 0.0 for l in leaves)
+
+
+def test_shim_precomputed_covariance_and_extra_attrs(cuda):
+    """diff_gauss call forms off the DIMO default path: cov3Ds_precomp (strip_symmetric layout of
+    renderer/latent_gs_renderer.py:61-66) must render what (scales, rotations) render, and extra_attrs come back
+    alpha-blended like colours."""
+    import math
+    import dimo_b200; dimo_b200.install_shims()
+    import gpu_parity as gp
+    from diff_gauss import GaussianRasterizationSettings, GaussianRasterizer
+    from dimo_b200.camera import orbit_minicam
+    N, W, H = 1500, 80, 64
+    xyz, scales, rot, op, shs = [t.cuda() for t in gp.scene_inputs(N, scale_boost=0.4)]
+    cam = orbit_minicam(2, 8, W, H)
+    rs = GaussianRasterizationSettings(image_height=H, image_width=W, tanfovx=math.tan(cam.FoVx / 2),
+                                       tanfovy=math.tan(cam.FoVy / 2), bg=torch.ones(3, device="cuda"), scale_modifier=1.0,
+                                       viewmatrix=cam.world_view_transform, projmatrix=cam.full_proj_transform, sh_degree=0,
+                                       campos=cam.camera_center, prefiltered=False, debug=False)
+    rast = GaussianRasterizer(raster_settings=rs)
+    m2d = torch.zeros(N, 3, device="cuda")
+    base = rast(means3D=xyz, means2D=m2d, shs=shs, colors_precomp=None, opacities=op, scales=scales, rotations=rot,
+                cov3Ds_precomp=None, extra_attrs=None)
+    # Sigma = R diag(s^2) R^T, strip_symmetric
+    q = rot
+    r_, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r_ * z), 2 * (x * z + r_ * y),
+                     2 * (x * y + r_ * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r_ * x),
+                     2 * (x * z - r_ * y), 2 * (y * z + r_ * x), 1 - 2 * (x * x + y * y)], -1).reshape(N, 3, 3)
+    L = R * scales[:, None, :]
+    S = L @ L.transpose(1, 2)
+    cov6 = torch.stack([S[:, 0, 0], S[:, 0, 1], S[:, 0, 2], S[:, 1, 1], S[:, 1, 2], S[:, 2, 2]], -1).requires_grad_(True)
+    attrs = torch.rand(N, 4, device="cuda")
+    out = rast(means3D=xyz, means2D=m2d, shs=shs, colors_precomp=None, opacities=op, scales=None, rotations=None,
+               cov3Ds_precomp=cov6, extra_attrs=attrs)
+    for a, b in zip(out[:2] + out[3:4], base[:2] + base[3:4]):          # image, depth, alpha
+        assert gp.outlier_frac(a, b, 1e-3) <= 2e-3, "covariance path deviates from the scale/rotation path"
+    assert tuple(out[5].shape) == (4, H, W) and float(out[5].max()) <= 1.0 + 1e-5 and float(out[5].min()) >= 0.0
+    out[0].sum().backward()
+    assert cov6.grad is not None and bool(torch.isfinite(cov6.grad).all()) and float(cov6.grad.abs().max()) > 0

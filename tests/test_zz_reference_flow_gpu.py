@@ -259,3 +259,40 @@ def test_c1_config_against_reference_fixture(cuda):
     a, b = torch.from_numpy(d["img_a"]).cuda(), torch.from_numpy(d["img_b"]).cuda()
     s, l1, _mse = dloss.image_losses(a, b, need_ssim_grad=False).tolist()
     assert abs(l1 - float(d["l1_images"])) <= 1e-6 and abs(s - float(d["ssim_images"])) <= 1e-5
+
+
+def test_render_glue_against_reference_fixture(cuda):
+    """B1 glue pinned end to end: `dimo_b200.renderer.Renderer.render` on the GPU against tests/golden/render.npz, which
+    is the REFERENCE's own `Renderer.render` (renderer/latent_gs_renderer.py:1096-1293: TimeNet, LBS block, activations,
+    MiniCam, SH features / override_color, result dict) executed on the CPU with the oracle rasteriser in place of
+    diff_gauss (tests/golden/make_golden_render.py) -- stage s1, s2, s2 with local_frame=False, override_color.
+    Every result key and every recorded gradient (incl. viewspace_points.grad) within 1e-4; integers exact."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import gpu_parity as gp
+    import render_scenario
+    from dimo_b200 import knn as dknn
+    from dimo_b200.camera import MiniCam, orbit_camera
+    from dimo_b200.renderer import Renderer
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "render.npz"))
+    fovy = np.deg2rad(33.9)
+
+    def make_cam(view):
+        return MiniCam(orbit_camera(-10.0 + 7 * view, 40.0 * view, 2.0), render_scenario.W, render_scenario.H, fovy, fovy,
+                       0.01, 100)
+
+    r = render_scenario.build(Renderer, "cuda")
+    rec = render_scenario.run(r, make_cam, lambda c, x: dknn.knn(c, x, 4), "cuda")
+    assert set(rec) == set(gold.files)
+    for key in gold.files:
+        want, got = gold[key], rec[key]
+        assert want.shape == got.shape, key
+        if want.dtype.kind in "biu":
+            assert np.array_equal(want, got), key
+        elif want.size:
+            w, g_ = torch.from_numpy(want), torch.from_numpy(got)
+            if key.split("/")[1] in ("image", "depth", "normal", "alpha"):
+                # threshold flips between two exp implementations: see test_raster_full_size_c2_shape
+                assert gp.outlier_frac(g_, w, 1e-4) <= 1e-3 and gp.rel_err(g_, w) <= 1.0 / 255.0 + 1e-4, key
+            else:
+                assert gp.rel_err(g_, w) <= 1e-4, (key, gp.rel_err(g_, w))
