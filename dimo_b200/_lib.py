@@ -20,12 +20,12 @@ _SIGS = {
     "dimo_last_error": (ctypes.c_char_p, []),
     "dimo_device_info": (c_int, [c_vp]),
     "dimo_raster_bin_temp_bytes": (c_sz, [c_int] * 4),
-    "dimo_raster_preprocess": (c_int, [c_int] * 6 + [c_f32, c_vp, c_vp] + [c_vp, c_i64] * 6 + [c_vp] * 7 + [c_vp, c_vp]),
+    "dimo_raster_preprocess": (c_int, [c_int] * 6 + [c_f32, c_int, c_vp, c_vp] + [c_vp, c_i64] * 6 + [c_vp] * 7 + [c_vp, c_vp]),
     "dimo_raster_bin": (c_int, [c_int] * 4 + [c_i64] + [c_vp] * 4 + [c_vp, c_sz, c_vp, c_vp, c_vp]),
     "dimo_raster_packed_value_bits": (c_int, [c_int] * 4),
     "dimo_raster_blend_fwd": (c_int, [c_int] * 5 + [c_vp] * 11),
     "dimo_raster_blend_bwd": (c_int, [c_int] * 5 + [c_vp] * 12),
-    "dimo_raster_preprocess_bwd": (c_int, [c_int] * 6 + [c_f32, c_vp, c_vp] + [c_vp, c_i64] * 4 + [c_vp] * 10),
+    "dimo_raster_preprocess_bwd": (c_int, [c_int] * 6 + [c_f32, c_int, c_vp, c_vp] + [c_vp, c_i64] * 5 + [c_vp] * 10),
     "dimo_knn": (c_int, [c_int] * 3 + [c_vp] * 5),
     "dimo_dist3nn": (c_int, [c_int, c_vp, c_vp, c_vp]),
     "dimo_fps": (c_int, [c_int] * 4 + [c_vp] * 4),
@@ -41,6 +41,9 @@ _SIGS = {
     "dimo_linear_wgrad_tc": (c_int, [c_int] * 3 + [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "dimo_linear_wgrad_tc_grouped": (c_int, [c_int, c_int] + [c_vp] * 10 + [c_vp]),
     "dimo_tc_debug_set": (c_int, [c_int, c_int]),
+    "dimo_set_deterministic": (c_int, [c_int]),
+    "dimo_get_deterministic": (c_int, []),
+    "dimo_fixed_to_float": (c_int, [c_i64, c_vp, c_vp, c_int, c_vp]),
     "dimo_timenet_workspace_bytes": (c_sz, [c_int] * 3),
     "dimo_timenet_layout": (c_int, [c_int] * 3 + [c_vp]),
     "dimo_timenet_fwd": (c_int, [c_int] * 3 + [c_vp] * 6 + [c_sz] + [c_vp] * 3),
@@ -86,8 +89,37 @@ def lib():
             k, v = kv.split("=")
             if L.dimo_tc_debug_set(int(k), int(v)) != 0:
                 raise RuntimeError(f"bad DIMO_KNOBS entry {kv!r}")
+        if os.environ.get("DIMO_DETERMINISTIC", "0") not in ("", "0"):
+            L.dimo_set_deterministic(1)
         _lib = L
     return _lib
+
+
+def deterministic():
+    """True when gradient accumulation runs in the order-independent fixed-point mode (DIMO_DETERMINISTIC=1 or
+    set_deterministic(True)); the host side then hands int64 accumulation buffers to the backward kernels."""
+    return bool(lib().dimo_get_deterministic())
+
+
+def set_deterministic(on):
+    lib().dimo_set_deterministic(1 if on else 0)
+
+
+def acc_zeros(shape, device):
+    """accumulation target for a backward kernel: fp32 zeros, or int64 zeros in deterministic mode"""
+    return torch.zeros(shape, dtype=torch.int64 if deterministic() else torch.float32, device=device)
+
+
+def acc_result(buf, into=None):
+    """fp32 view of an accumulation target (deterministic mode: one dimo_fixed_to_float launch); `into`: add to it"""
+    if buf.dtype != torch.int64:
+        if into is None:
+            return buf
+        into.add_(buf)
+        return into
+    out = into if into is not None else torch.empty(buf.shape, dtype=torch.float32, device=buf.device)
+    call("dimo_fixed_to_float", buf.numel(), ptr(buf), ptr(out), 1 if into is not None else 0, stream())
+    return out
 
 
 def check(rc):
@@ -116,7 +148,7 @@ _OWN_LAUNCHES = {
     "dimo_arap_connectivity": 1, "dimo_arap_energy": 1, "dimo_linear_fwd": 1,
     "dimo_linear_bwd_data": 1, "dimo_linear_tc": 1, "dimo_linear_wgrad_tc": 1, "dimo_linear_wgrad_tc_grouped": 1, "dimo_linear_bwd_weight": 1, "dimo_timenet_embed_fwd": 1,
     "dimo_timenet_embed_bwd": 1, "dimo_lbs_fwd": 1, "dimo_lbs_bwd": 1, "dimo_ssim_fwd": 1, "dimo_ssim_bwd": 1,
-    "dimo_timenet_fwd": 15, "dimo_timenet_bwd": 19,
+    "dimo_timenet_fwd": 15, "dimo_timenet_bwd": 19, "dimo_fixed_to_float": 1,
     "dimo_sqdiff_sum": 1, "dimo_smooth_fwd": 1, "dimo_smooth_bwd": 1, "dimo_segment_sum": 1, "dimo_adam_step": 1, "dimo_transpose_grouped": 1, "dimo_gt_fetch": 1,
 }
 

@@ -47,4 +47,19 @@ void set_error(const char* fmt, ...);
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// Deterministic accumulation (dimo_set_deterministic): every accumulation target that several CTAs add into is then an
+// INT64 buffer of the same element count; addends are rounded to multiples of 1 / DET_SCALE and summed with native 64-bit
+// integer reductions, which are associative -- the result does not depend on the order the CTAs arrive in.  Range
+// +-3.4e10, resolution 3.7e-9 per addend.  dimo_fixed_to_float converts back.
+constexpr float DET_SCALE = 268435456.0f;          // 2^28
+float det_scale();                                  // 0 = off (fp32 atomics), DET_SCALE = on   (raster_bin.cu)
+#ifdef __CUDACC__
+__device__ __forceinline__ void acc_add(float* base, int64_t idx, float v, float det) {
+  if (det != 0.f)
+    atomicAdd(reinterpret_cast<unsigned long long*>(base) + idx, (unsigned long long)__float2ll_rn(v * det));
+  else
+    atomicAdd(base + idx, v);
+}
+#endif
+
 }  // namespace dimo

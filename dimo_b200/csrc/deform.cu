@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) lbs_bwd_kernel(
     const float* __restrict__ c_radius_raw, const float* __restrict__ dxyz, const float* __restrict__ dquat,
     const float* __restrict__ g_means3D, const float4* __restrict__ g_rotations, float* __restrict__ dxyz_c,
     float* __restrict__ drot_c, float* __restrict__ dc_xyz, float* __restrict__ dc_radius_raw,
-    float* __restrict__ ddxyz, float* __restrict__ ddquat) {
+    float* __restrict__ ddxyz, float* __restrict__ ddquat, float det) {
   extern __shared__ float tab[];   // [M][CT] when use_smem
   const int b = blockIdx.y;
   if (use_smem) {
@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(256) lbs_bwd_kernel(
   const float* dq_b = dquat + (int64_t)b * M * 4;
   float* ddx_b = ddxyz + (int64_t)b * M * 3;
   float* ddq_b = ddquat + (int64_t)b * M * 4;
+  const int64_t ox = (int64_t)b * M * 3, oq = (int64_t)b * M * 4;      // element offsets of this block (deterministic mode)
 
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
     float w[K], e[K], rad[K];
@@ -158,10 +159,10 @@ __global__ void __launch_bounds__(256) lbs_bwd_kernel(
     const float gc_x = -g0 * qb.x + g1 * qb.r + g2 * qb.z - g3 * qb.y;
     const float gc_y = -g0 * qb.y - g1 * qb.z + g2 * qb.r + g3 * qb.x;
     const float gc_z = -g0 * qb.z + g1 * qb.y - g2 * qb.x + g3 * qb.r;
-    atomicAdd(&drot_c[4 * (int64_t)i + 0], gc_r);
-    atomicAdd(&drot_c[4 * (int64_t)i + 1], gc_x);
-    atomicAdd(&drot_c[4 * (int64_t)i + 2], gc_y);
-    atomicAdd(&drot_c[4 * (int64_t)i + 3], gc_z);
+    acc_add(drot_c, 4 * (int64_t)i + 0, gc_r, det);
+    acc_add(drot_c, 4 * (int64_t)i + 1, gc_x, det);
+    acc_add(drot_c, 4 * (int64_t)i + 2, gc_y, det);
+    acc_add(drot_c, 4 * (int64_t)i + 3, gc_z, det);
 
     float gwn[K];
     float gxyz[3] = {0.f, 0.f, 0.f};
@@ -212,16 +213,17 @@ __global__ void __launch_bounds__(256) lbs_bwd_kernel(
         atomicAdd(tj + 3, gdq0); atomicAdd(tj + 4, gdq1); atomicAdd(tj + 5, gdq2); atomicAdd(tj + 6, gdq3);
         atomicAdd(tj + 7, wn * (gx - rtg[0])); atomicAdd(tj + 8, wn * (gy - rtg[1])); atomicAdd(tj + 9, wn * (gz - rtg[2]));
       } else {
-        atomicAdd(ddx_b + 3 * j + 0, wn * gx); atomicAdd(ddx_b + 3 * j + 1, wn * gy); atomicAdd(ddx_b + 3 * j + 2, wn * gz);
-        atomicAdd(ddq_b + 4 * j + 0, gdq0); atomicAdd(ddq_b + 4 * j + 1, gdq1);
-        atomicAdd(ddq_b + 4 * j + 2, gdq2); atomicAdd(ddq_b + 4 * j + 3, gdq3);
-        atomicAdd(dc_xyz + 3 * j + 0, wn * (gx - rtg[0])); atomicAdd(dc_xyz + 3 * j + 1, wn * (gy - rtg[1]));
-        atomicAdd(dc_xyz + 3 * j + 2, wn * (gz - rtg[2]));
+        acc_add(ddxyz, ox + 3 * j + 0, wn * gx, det); acc_add(ddxyz, ox + 3 * j + 1, wn * gy, det);
+        acc_add(ddxyz, ox + 3 * j + 2, wn * gz, det);
+        acc_add(ddquat, oq + 4 * j + 0, gdq0, det); acc_add(ddquat, oq + 4 * j + 1, gdq1, det);
+        acc_add(ddquat, oq + 4 * j + 2, gdq2, det); acc_add(ddquat, oq + 4 * j + 3, gdq3, det);
+        acc_add(dc_xyz, 3 * j + 0, wn * (gx - rtg[0]), det); acc_add(dc_xyz, 3 * j + 1, wn * (gy - rtg[1]), det);
+        acc_add(dc_xyz, 3 * j + 2, wn * (gz - rtg[2]), det);
       }
     }
-    atomicAdd(&dxyz_c[3 * (int64_t)i + 0], gxyz[0]);
-    atomicAdd(&dxyz_c[3 * (int64_t)i + 1], gxyz[1]);
-    atomicAdd(&dxyz_c[3 * (int64_t)i + 2], gxyz[2]);
+    acc_add(dxyz_c, 3 * (int64_t)i + 0, gxyz[0], det);
+    acc_add(dxyz_c, 3 * (int64_t)i + 1, gxyz[1], det);
+    acc_add(dxyz_c, 3 * (int64_t)i + 2, gxyz[2], det);
     // weights: wn = w / S ; w = exp(-d^2 / (2 r^2)) + eps ; r = exp(raw)
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -229,7 +231,7 @@ __global__ void __launch_bounds__(256) lbs_bwd_kernel(
       const float d = dist[(int64_t)i * K + k];
       const float graw = gw * e[k] * (d * d) / (rad[k] * rad[k]);   // dw/dr * r = e * d^2 / r^2
       if (use_smem) atomicAdd(tab + nb[k] * CT + 10, graw);
-      else atomicAdd(dc_radius_raw + nb[k], graw);
+      else acc_add(dc_radius_raw, nb[k], graw, det);
     }
   }
   if (use_smem) {
@@ -280,7 +282,8 @@ extern "C" int dimo_lbs_bwd(int B, int N, int M, int K, const float* xyz, const 
   if (B == 0 || N == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = (size_t)M * CT * sizeof(float);
-  const int use_smem = smem <= 160 * 1024 ? 1 : 0;
+  const float det = dimo::det_scale();          // deterministic mode: every output is an int64 buffer, no shared staging
+  const int use_smem = (smem <= 160 * 1024 && det == 0.f) ? 1 : 0;
   // few, fat CTAs per frame so each shared-memory table is flushed once: ~2 waves over 148 SMs in total
   int per_frame = max(1, min(ceil_div(N, 256), ceil_div(296, B)));
   dim3 grid(per_frame, B);
@@ -291,7 +294,7 @@ extern "C" int dimo_lbs_bwd(int B, int N, int M, int K, const float* xyz, const 
       DIMO_CHECK_CUDA(cudaFuncSetAttribute(lbs_bwd_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     lbs_bwd_kernel<KK><<<grid, 256, use_smem ? smem : 0, st>>>(                                                    \
         N, M, use_smem, xyz, rot, idx, dist, c_xyz, c_radius_raw, dxyz, dquat, dL_dmeans3D,                        \
-        reinterpret_cast<const float4*>(dL_drotations), dxyz_c, drot_c, dc_xyz, dc_radius_raw, ddxyz, ddquat);     \
+        reinterpret_cast<const float4*>(dL_drotations), dxyz_c, drot_c, dc_xyz, dc_radius_raw, ddxyz, ddquat, det); \
   } break;
     DIMO_LBS_CASE(1) DIMO_LBS_CASE(2) DIMO_LBS_CASE(3) DIMO_LBS_CASE(4)
     DIMO_LBS_CASE(5) DIMO_LBS_CASE(6) DIMO_LBS_CASE(7) DIMO_LBS_CASE(8)

@@ -29,6 +29,7 @@ struct GemmArgs {
   int relu;                                // epilogue ReLU
   int mode;                                // 0: C = v ; 1: C += v ; 2: atomicAdd(C, v)
   int l_per_split;                         // reduction range per blockIdx.z
+  float det;                               // mode 2 / rowsum: deterministic fixed-point accumulation (common.cuh)
 };
 
 // A_LC: A's contiguous dimension is l (else i).  B_LC: B's contiguous dimension is l (else j).
@@ -125,9 +126,9 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs p) {
       float* c = p.C + gi * p.sCi + gj;
       if (p.mode == 0) *c = val;
       else if (p.mode == 1) *c += val;
-      else atomicAdd(c, val);
+      else acc_add(p.C, (int64_t)gi * p.sCi + gj, val, p.det);
     }
-    if (do_rowsum && tx == 0) atomicAdd(p.rowsum + gi, rsum[u]);
+    if (do_rowsum && tx == 0) acc_add(p.rowsum, gi, rsum[u], p.det);
   }
 }
 
@@ -171,7 +172,7 @@ constexpr int EMB_ROWS_PER_WARP = 4;
 
 __global__ void __launch_bounds__(256) embed_bwd_kernel(int G, int Mrows, int L, const float* __restrict__ h0,
                                                         const float* __restrict__ dh0, int64_t ldh,
-                                                        float* __restrict__ dpts, float* __restrict__ dlatents) {
+                                                        float* __restrict__ dpts, float* __restrict__ dlatents, float det) {
   extern __shared__ float slat[];   // [L] partial sums of this block
   const int g = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(int G, int Mrows, int L,
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) gp[d] += __shfl_xor_sync(0xffffffffu, gp[d], o);
       }
-      if (lane < 3) atomicAdd(&dpts[3 * m + lane], lane == 0 ? gp[0] : (lane == 1 ? gp[1] : gp[2]));
+      if (lane < 3) acc_add(dpts, 3 * (int64_t)m + lane, lane == 0 ? gp[0] : (lane == 1 ? gp[1] : gp[2]), det);
     }
     if (dlatents != nullptr) {
 #pragma unroll
@@ -218,11 +219,14 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(int G, int Mrows, int L,
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int l = lane + 32 * q;
-      if (l < L) atomicAdd(&slat[l], lat_acc[q]);
+      if (l < L) {
+        if (det != 0.f) acc_add(dlatents, (int64_t)g * L + l, lat_acc[q], det);     // order-independent: no staging
+        else atomicAdd(&slat[l], lat_acc[q]);
+      }
     }
   }
   __syncthreads();
-  if (dlatents != nullptr)
+  if (dlatents != nullptr && det == 0.f)
     for (int l = threadIdx.x; l < L; l += blockDim.x) atomicAdd(&dlatents[(int64_t)g * L + l], slat[l]);
 }
 
@@ -269,7 +273,7 @@ extern "C" int dimo_linear_bwd_weight(int R, int K, int No, const float* dY, int
   p.A = dY; p.sAi = 1; p.sAl = lddy;
   p.mask = Y; p.sMi = 1; p.sMl = ldy;
   p.Bm = X; p.sBl = ldx; p.sBj = 1;
-  p.C = dW; p.sCi = K; p.rowsum = db; p.mode = 2;
+  p.C = dW; p.sCi = K; p.rowsum = db; p.mode = 2; p.det = dimo::det_scale();
   // split the long reduction over rows so the grid fills the machine (~2 waves of 148 SMs)
   const int tiles = ceil_div(No, BM) * ceil_div(K, BN);
   int splits = max(1, min(ceil_div(R, 4 * BK), ceil_div(296, tiles)));
@@ -296,8 +300,8 @@ extern "C" int dimo_timenet_embed_bwd(int G, int rows_per_group, int L, const fl
   if (G == 0 || rows_per_group == 0) return 0;
   DIMO_REQUIRE(L <= 128, "latent dimension must be <= 128");
   dim3 grid(ceil_div(rows_per_group, 8 * EMB_ROWS_PER_WARP), G);
-  embed_bwd_kernel<<<grid, 256, sizeof(float) * (size_t)max(L, 1), (cudaStream_t)stream>>>(G, rows_per_group, L, h0,
-                                                                                          dh0, ldh, dpts, dlatents);
+  embed_bwd_kernel<<<grid, 256, sizeof(float) * (size_t)max(L, 1), (cudaStream_t)stream>>>(
+      G, rows_per_group, L, h0, dh0, ldh, dpts, dlatents, dimo::det_scale());
   DIMO_CHECK_LAUNCH();
   return 0;
 }

@@ -42,6 +42,17 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
+static float g_det_scale = 0.f;
+float det_scale() { return g_det_scale; }
+
+__global__ void __launch_bounds__(256) fixed_to_float_kernel(int64_t n, const long long* __restrict__ src,
+                                                             float* __restrict__ dst, int accumulate, double inv) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = (float)((double)src[i] * inv);
+  dst[i] = accumulate ? dst[i] + v : v;
+}
+
 int g_disable_packed_instances = 0;     // dimo_tc_debug_set key 6: force the (key, value) pair format (tests, A/B)
 
 static inline int bits_for(int64_t n) {
@@ -443,7 +454,7 @@ static inline BinGeom bin_geom(int B, int N, int W, int H) {
 using namespace dimo;
 
 namespace dimo {
-int preprocess_launch(int B, int N, int W, int H, int sh_degree, int sh_coeffs, float scale_modifier,
+int preprocess_launch(int B, int N, int W, int H, int sh_degree, int sh_coeffs, float scale_modifier, int act_flags,
                       const float* cams, const int32_t* frame_src, const float* means3D, int64_t means3D_bstride,
                       const float* scales,
                       int64_t scales_bstride, const float* rotations, int64_t rotations_bstride,
@@ -456,6 +467,20 @@ int preprocess_launch(int B, int N, int W, int H, int sh_degree, int sh_coeffs, 
 extern "C" {
 
 int dimo_abi_version(void) { return DIMO_ABI_VERSION; }
+
+int dimo_set_deterministic(int on) {
+  dimo::g_det_scale = on ? DET_SCALE : 0.f;
+  return 0;
+}
+int dimo_get_deterministic(void) { return dimo::g_det_scale != 0.f; }
+
+int dimo_fixed_to_float(int64_t n, const void* src_i64, float* dst, int accumulate, void* stream) {
+  if (n <= 0) return 0;
+  fixed_to_float_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      n, reinterpret_cast<const long long*>(src_i64), dst, accumulate, 1.0 / (double)DET_SCALE);
+  DIMO_CHECK_LAUNCH();
+  return 0;
+}
 const char* dimo_last_error(void) { return dimo::get_error(); }
 
 int dimo_device_info(int* out3_host) {
@@ -488,7 +513,7 @@ int dimo_raster_packed_value_bits(int B, int N, int W, int H) {
 }
 
 int dimo_raster_preprocess(int B, int N, int W, int H, int sh_degree, int sh_coeffs, float scale_modifier,
-                           const float* cams, const int32_t* frame_src, const float* means3D,
+                           int act_flags, const float* cams, const int32_t* frame_src, const float* means3D,
                            int64_t means3D_bstride, const float* scales,
                            int64_t scales_bstride, const float* rotations, int64_t rotations_bstride,
                            const float* opacities, int64_t opacities_bstride, const float* shs,
@@ -510,7 +535,7 @@ int dimo_raster_preprocess(int B, int N, int W, int H, int sh_degree, int sh_coe
   }
   DIMO_CHECK_CUDA(cudaMemsetAsync(total_count, 0, sizeof(uint64_t), st));
   // sort_scratch: [3*BN] u32 = depth keys | ping | pong; perm: [2*BN] u32 = ping | pong (result = perm + BN)
-  int rc = preprocess_launch(B, N, W, H, sh_degree, sh_coeffs, scale_modifier, cams, frame_src, means3D,
+  int rc = preprocess_launch(B, N, W, H, sh_degree, sh_coeffs, scale_modifier, act_flags, cams, frame_src, means3D,
                              means3D_bstride, scales, scales_bstride, rotations, rotations_bstride, opacities,
                              opacities_bstride, shs, shs_bstride, colors_precomp, colors_bstride, splats, radii,
                              tiles_touched, rects, sort_scratch, reinterpret_cast<unsigned long long*>(total_count),

@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_bwd_kernel(
     const uint32_t* __restrict__ vals_sorted, const uint2* __restrict__ ranges, const float* __restrict__ final_T,
     const int32_t* __restrict__ n_contrib,
     const float* __restrict__ dL_dcolor, const float* __restrict__ dL_ddepth, const float* __restrict__ dL_dnormal,
-    const float* __restrict__ dL_dalpha, float* __restrict__ dL_dsplats) {
+    const float* __restrict__ dL_dalpha, float* __restrict__ dL_dsplats, float det) {
   constexpr int NG = BwdFields<DN>::NG;
   __shared__ __align__(128) float4 sm[2][CH * REC_F4];
   __shared__ float acc[2][CH * NG];          // [warp][record][field]
@@ -527,13 +527,26 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_bwd_kernel(
         const float op = bq.y, k = op * LN2;
         const float St = f[0], Sx = f[1], Sy = f[2], Sxx = f[3], Sxy = f[4], Syy = f[5];
         float* out = dL_dsplats + (int64_t)gid * DIMO_SPLAT_FLOATS;
-        red_add_v4(out, k * (2.f * a.z * Sx + a.w * Sy), k * (2.f * bq.x * Sy + a.w * Sx), -0.5f * op * Sxx, -op * Sxy);
-        red_add_v4(out + 4, -0.5f * op * Syy, St, f[6], f[7]);
-        if (DN) {
-          red_add_v4(out + 8, f[8], f[9], f[10], f[11]);
-          atomicAdd(out + 12, f[12]);
+        const float o0 = k * (2.f * a.z * Sx + a.w * Sy), o1 = k * (2.f * bq.x * Sy + a.w * Sx), o2 = -0.5f * op * Sxx,
+                    o3 = -op * Sxy, o4 = -0.5f * op * Syy;
+        if (det != 0.f) {          // deterministic mode: 64-bit fixed-point reductions into an int64 record table
+          const int64_t e0 = (int64_t)gid * DIMO_SPLAT_FLOATS;
+          const float o[9] = {o0, o1, o2, o3, o4, St, f[6], f[7], f[8]};
+#pragma unroll
+          for (int q = 0; q < 9; ++q) acc_add(dL_dsplats, e0 + q, o[q], det);
+          if (DN) {
+#pragma unroll
+            for (int q = 9; q < NG; ++q) acc_add(dL_dsplats, e0 + q, f[q], det);
+          }
         } else {
-          atomicAdd(out + 8, f[8]);
+          red_add_v4(out, o0, o1, o2, o3);
+          red_add_v4(out + 4, o4, St, f[6], f[7]);
+          if (DN) {
+            red_add_v4(out + 8, f[8], f[9], f[10], f[11]);
+            atomicAdd(out + 12, f[12]);
+          } else {
+            atomicAdd(out + 8, f[8]);
+          }
         }
       }
     }
@@ -590,7 +603,8 @@ extern "C" int dimo_raster_blend_bwd(int B, int N, int W, int H, int value_bits,
   DIMO_REQUIRE(B >= 0 && W > 0 && H > 0, "bad sizes");
   cudaStream_t st = (cudaStream_t)stream;
   if (B == 0 || N == 0) return 0;
-  DIMO_CHECK_CUDA(cudaMemsetAsync(dL_dsplats, 0, sizeof(float) * DIMO_SPLAT_FLOATS * (size_t)B * N, st));
+  const float det = dimo::det_scale();        // deterministic mode: dL_dsplats is an int64 table of the same shape
+  DIMO_CHECK_CUDA(cudaMemsetAsync(dL_dsplats, 0, (det != 0.f ? 8 : 4) * DIMO_SPLAT_FLOATS * (size_t)B * N, st));
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
   // no gradient for depth AND normal (NULL): the four channels are compiled out of the pixel loop and the reduction
   DIMO_REQUIRE((dL_ddepth == nullptr) == (dL_dnormal == nullptr), "dL_ddepth and dL_dnormal: pass both or neither");
@@ -607,7 +621,7 @@ extern "C" int dimo_raster_blend_bwd(int B, int N, int W, int H, int value_bits,
   kern<<<B * gx * gy, BLEND_THREADS, 0, st>>>(
       W, H, gx, gx * gy, vmask, fstride, cams, reinterpret_cast<const float4*>(splats), vals_sorted,
       reinterpret_cast<const uint2*>(ranges), final_T, n_contrib, dL_dcolor, dL_ddepth, dL_dnormal, dL_dalpha,
-      dL_dsplats);
+      dL_dsplats, det);
   DIMO_CHECK_LAUNCH();
   return 0;
 }

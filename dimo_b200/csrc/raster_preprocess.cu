@@ -186,8 +186,13 @@ __device__ __forceinline__ void sh_basis_grad(int deg, float x, float y, float z
   }
 }
 
+// act_flags: bit 0 = `scales` holds log-scales (the model's raw _scaling; exp applied here), bit 1 = `opacities` holds
+// logits (raw _opacity; sigmoid applied here) -- GaussianModel.get_scaling / get_opacity
+// (renderer/latent_gs_renderer.py:257-265, 340-355) folded into the projection pass and its backward.
+constexpr int ACT_EXP_SCALE = 1, ACT_SIGMOID_OPACITY = 2;
+
 __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
-    int B, int N, int W, int H, int sh_degree, int sh_coeffs, float scale_modifier,
+    int B, int N, int W, int H, int sh_degree, int sh_coeffs, float scale_modifier, int act_flags,
     const float* __restrict__ cams, const int32_t* __restrict__ frame_src,
     const float* __restrict__ means3D, int64_t means3D_bs,
     const float* __restrict__ scales, int64_t scales_bs,
@@ -213,7 +218,8 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
   const float* pm = means3D + bsrc * means3D_bs + 3 * (int64_t)i;
   const float px = pm[0], py = pm[1], pz = pm[2];
   const float* ps = scales + b * scales_bs + 3 * (int64_t)i;
-  const float sc[3] = {ps[0], ps[1], ps[2]};
+  float sc[3] = {ps[0], ps[1], ps[2]};
+  if (act_flags & ACT_EXP_SCALE) { sc[0] = expf(sc[0]); sc[1] = expf(sc[1]); sc[2] = expf(sc[2]); }
   const float4 q4 = *reinterpret_cast<const float4*>(rotations + bsrc * rot_bs + 4 * (int64_t)i);
   const float q[4] = {q4.x, q4.y, q4.z, q4.w};
 
@@ -266,7 +272,8 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
   const float nx = dot3(nw0, nw1, nw2, V[0], V[4], V[8]);
   const float ny = dot3(nw0, nw1, nw2, V[1], V[5], V[9]);
   const float nz = dot3(nw0, nw1, nw2, V[2], V[6], V[10]);
-  const float op = opacities[b * op_bs + i];
+  float op = opacities[b * op_bs + i];
+  if (act_flags & ACT_SIGMOID_OPACITY) op = 1.0f / (1.0f + expf(-op));
 
   radii[idx] = (int)g.radius_f;
   tiles_touched[idx] = (uint32_t)ntiles;
@@ -293,7 +300,8 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(
 }
 
 __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
-    int B, int N, int W, int H, int sh_degree, int sh_coeffs, float scale_modifier,
+    int B, int N, int W, int H, int sh_degree, int sh_coeffs, float scale_modifier, int act_flags,
+    const float* __restrict__ opacities, int64_t op_bs,
     const float* __restrict__ cams, const int32_t* __restrict__ frame_src,
     const float* __restrict__ means3D, int64_t means3D_bs,
     const float* __restrict__ scales, int64_t scales_bs,
@@ -327,7 +335,8 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
   const float* pm = means3D + bsrc * means3D_bs + 3 * (int64_t)i;
   const float px = pm[0], py = pm[1], pz = pm[2];
   const float* ps = scales + b * scales_bs + 3 * (int64_t)i;
-  const float sc[3] = {ps[0], ps[1], ps[2]};
+  float sc[3] = {ps[0], ps[1], ps[2]};
+  if (act_flags & ACT_EXP_SCALE) { sc[0] = expf(sc[0]); sc[1] = expf(sc[1]); sc[2] = expf(sc[2]); }
   const float4 q4 = *reinterpret_cast<const float4*>(rotations + bsrc * rot_bs + 4 * (int64_t)i);
   const float q[4] = {q4.x, q4.y, q4.z, q4.w};
   Geo g;
@@ -452,11 +461,19 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
 
   dL_dmeans3D[3 * idx + 0] = dmean[0]; dL_dmeans3D[3 * idx + 1] = dmean[1]; dL_dmeans3D[3 * idx + 2] = dmean[2];
   dL_dmeans2D[3 * idx + 0] = g_ndcx; dL_dmeans2D[3 * idx + 1] = g_ndcy; dL_dmeans2D[3 * idx + 2] = 0.f;
-  dL_dscales[3 * idx + 0] = dscale[0] * scale_modifier;
-  dL_dscales[3 * idx + 1] = dscale[1] * scale_modifier;
-  dL_dscales[3 * idx + 2] = dscale[2] * scale_modifier;
+  // d exp(x) = exp(x): the gradient lands on the log-scales when the activation is folded in
+  const float e0 = (act_flags & ACT_EXP_SCALE) ? sc[0] : 1.0f, e1 = (act_flags & ACT_EXP_SCALE) ? sc[1] : 1.0f,
+              e2 = (act_flags & ACT_EXP_SCALE) ? sc[2] : 1.0f;
+  dL_dscales[3 * idx + 0] = dscale[0] * scale_modifier * e0;
+  dL_dscales[3 * idx + 1] = dscale[1] * scale_modifier * e1;
+  dL_dscales[3 * idx + 2] = dscale[2] * scale_modifier * e2;
   dL_drot[idx] = dq;
-  dL_dop[idx] = g_op;
+  float g_opacity = g_op;
+  if (act_flags & ACT_SIGMOID_OPACITY) {            // d sigmoid(x) = s (1 - s)
+    const float sg = 1.0f / (1.0f + expf(-opacities[b * op_bs + i]));
+    g_opacity = g_op * sg * (1.0f - sg);
+  }
+  dL_dop[idx] = g_opacity;
 }
 
 // out[u, :] = sum over rows s with seg[s] == u of in[s, :]  (seg == NULL: every row belongs to segment 0), rows
@@ -496,7 +513,7 @@ __global__ void __launch_bounds__(256) segment_sum_kernel(int S, int64_t n, cons
 namespace dimo {
 
 int preprocess_launch(
-    int B, int N, int W, int H, int sh_degree, int sh_coeffs, float scale_modifier, const float* cams,
+    int B, int N, int W, int H, int sh_degree, int sh_coeffs, float scale_modifier, int act_flags, const float* cams,
     const int32_t* frame_src,
     const float* means3D, int64_t means3D_bstride, const float* scales, int64_t scales_bstride,
     const float* rotations, int64_t rotations_bstride, const float* opacities, int64_t opacities_bstride,
@@ -506,7 +523,7 @@ int preprocess_launch(
   const int64_t BN = (int64_t)B * N;
   if (BN == 0) return 0;
   preprocess_fwd_kernel<<<ceil_div(BN, 256), 256, 0, st>>>(
-      B, N, W, H, sh_degree, sh_coeffs, scale_modifier, cams, frame_src, means3D, means3D_bstride, scales,
+      B, N, W, H, sh_degree, sh_coeffs, scale_modifier, act_flags, cams, frame_src, means3D, means3D_bstride, scales,
       scales_bstride, rotations, rotations_bstride, opacities, opacities_bstride, shs, shs_bstride, colors_precomp,
       colors_bstride, reinterpret_cast<float4*>(splats), radii, tiles_touched, reinterpret_cast<uint2*>(rects),
       depth_keys, total_count);
@@ -519,10 +536,11 @@ int preprocess_launch(
 using namespace dimo;
 
 extern "C" int dimo_raster_preprocess_bwd(
-    int B, int N, int W, int H, int sh_degree, int sh_coeffs, float scale_modifier, const float* cams,
+    int B, int N, int W, int H, int sh_degree, int sh_coeffs, float scale_modifier, int act_flags, const float* cams,
     const int32_t* frame_src,
     const float* means3D, int64_t means3D_bstride, const float* scales, int64_t scales_bstride,
-    const float* rotations, int64_t rotations_bstride, const float* shs, int64_t shs_bstride,
+    const float* rotations, int64_t rotations_bstride, const float* opacities, int64_t opacities_bstride,
+    const float* shs, int64_t shs_bstride,
     const int32_t* radii, const float* dL_dsplats, float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dscales,
     float* dL_drotations, float* dL_dopacities, float* dL_dshs, float* dL_dcolors, void* stream) {
   const int64_t BN = (int64_t)B * N;
@@ -530,8 +548,9 @@ extern "C" int dimo_raster_preprocess_bwd(
   DIMO_REQUIRE(sh_degree >= 0 && sh_degree <= 3, "sh_degree must be 0..3");
   DIMO_REQUIRE((dL_dshs != nullptr) != (dL_dcolors != nullptr), "exactly one of dL_dshs / dL_dcolors");
   DIMO_REQUIRE(dL_dcolors != nullptr || shs != nullptr, "shs required when colours come from SH");
+  DIMO_REQUIRE(!(act_flags & ACT_SIGMOID_OPACITY) || opacities != nullptr, "opacities (logits) required when the sigmoid is folded in");
   preprocess_bwd_kernel<<<ceil_div(BN, 256), 256, 0, (cudaStream_t)stream>>>(
-      B, N, W, H, sh_degree, sh_coeffs, scale_modifier, cams, frame_src, means3D, means3D_bstride, scales,
+      B, N, W, H, sh_degree, sh_coeffs, scale_modifier, act_flags, opacities, opacities_bstride, cams, frame_src, means3D, means3D_bstride, scales,
       scales_bstride, rotations, rotations_bstride, shs, shs_bstride, radii, reinterpret_cast<const float4*>(dL_dsplats),
       dL_dmeans3D, dL_dmeans2D, dL_dscales, reinterpret_cast<float4*>(dL_drotations), dL_dopacities, dL_dshs,
       dL_dcolors);

@@ -395,7 +395,7 @@ struct TnWJob {
   float* db;                                       // NULL unless this job also owns the bias gradient of its n block
 };
 constexpr int TN_MAX_WJOBS = 32;
-struct TnWTable { int n, splits, per, nrt; TnWJob job[TN_MAX_WJOBS]; };    // CTA = (job, row split)
+struct TnWTable { int n, splits, per, nrt; float det; TnWJob job[TN_MAX_WJOBS]; };    // CTA = (job, row split)
 
 __global__ void __launch_bounds__(TN_THREADS, 1) tn_wgrad_kernel(const __grid_constant__ TnWTable tab) {
   extern __shared__ uint8_t tn_smem_raw[];
@@ -492,7 +492,12 @@ __global__ void __launch_bounds__(TN_THREADS, 1) tn_wgrad_kernel(const __grid_co
           float* wrow = p.dW + (int64_t)n * p.ldw + p.col0 + c * 32;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            if (c * 32 + j + 3 < p.ncols) {
+            if (tab.det != 0.f) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (c * 32 + j + e < p.ncols)
+                  acc_add(p.dW, (int64_t)n * p.ldw + p.col0 + c * 32 + j + e, __uint_as_float(v[j + e]), tab.det);
+            } else if (c * 32 + j + 3 < p.ncols) {
               asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(wrow + j), "f"(__uint_as_float(v[j])),
                            "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
                            : "memory");
@@ -504,7 +509,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) tn_wgrad_kernel(const __grid_co
           }
         }
       }
-      if (p.db != nullptr && n < p.nrows) atomicAdd(p.db + n, dbacc);
+      if (p.db != nullptr && n < p.nrows) acc_add(p.db, n, dbacc, tab.det);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -783,6 +788,7 @@ extern "C" int dimo_timenet_bwd(int G, int M, int L, const float* const* W_host,
     tab.splits = o.nrt >= 64 ? 8 : (o.nrt >= 16 ? 4 : (o.nrt >= 4 ? 2 : 1));
     tab.per = (o.nrt + tab.splits - 1) / tab.splits;
     tab.nrt = o.nrt;
+    tab.det = dimo::det_scale();
     auto add = [&](const uint8_t* aT, int a_fb, const uint8_t* bT, int b_nfb, int b_fb0, int b_use, float* dW, int ldw,
                    int col0, int ncols, float* db) {
       TnWJob& j = tab.job[n++];

@@ -76,21 +76,29 @@ class _TimeNetChainFn(torch.autograd.Function):
         g_dxyz = (g_dxyz if g_dxyz is not None else torch.zeros(G, M, 3, **f32)).contiguous().float()
         g_dquat = (g_dquat if g_dquat is not None else torch.zeros(G, M, 4, **f32)).contiguous().float()
         sink = ctx.sink
-        if sink is not None:
+        det = _lib.deterministic()
+        if sink is not None and not det:
             dWs, dbs = list(sink[0::2]), list(sink[1::2])
-        else:
-            dWs = [torch.zeros_like(W) for W in Ws]
-            dbs = [torch.zeros(W.shape[0], **f32) for W in Ws]
+        else:                             # fresh accumulators (int64 in deterministic mode), folded into the sink below
+            dWs = [_lib.acc_zeros(W.shape, dev) for W in Ws]
+            dbs = [_lib.acc_zeros((W.shape[0],), dev) for W in Ws]
         need_pts, need_lat = ctx.needs_input_grad[0], ctx.needs_input_grad[2]
-        dpts = torch.zeros(M, 3, **f32) if need_pts else None
-        dlat = torch.zeros(G, L, **f32) if need_lat else None
+        dpts = _lib.acc_zeros((M, 3), dev) if need_pts else None
+        dlat = _lib.acc_zeros((G, L), dev) if need_lat else None
         wp = (ctypes.c_void_p * 12)(*[w.data_ptr() for w in Ws])
         dwp = (ctypes.c_void_p * 12)(*[w.data_ptr() for w in dWs])
         dbp = (ctypes.c_void_p * 12)(*[b.data_ptr() for b in dbs])
         _lib.call("dimo_timenet_bwd", G, M, L, wp, _lib.ptr(ws), nbytes, _lib.ptr(g_dxyz), _lib.ptr(g_dquat), dwp, dbp,
                   _lib.ptr(dpts), _lib.ptr(dlat), _lib.stream())
+        dpts = _lib.acc_result(dpts) if dpts is not None else None
+        dlat = _lib.acc_result(dlat) if dlat is not None else None
         if sink is not None:
+            if det:
+                for acc, dst in zip(dWs + dbs, list(sink[0::2]) + list(sink[1::2])):
+                    _lib.acc_result(acc, into=dst)
             return (dpts, None, dlat, None, *([None] * (2 * len(Ws))))
+        dWs = [_lib.acc_result(a) for a in dWs]
+        dbs = [_lib.acc_result(a) for a in dbs]
         grads = []
         for W, b in zip(dWs, dbs):
             grads += [W, b]
@@ -376,7 +384,7 @@ class _LBSFn(torch.autograd.Function):
         xyz, rot, c_xyz, c_radius_raw, dxyz, dquat, idx, dist = ctx.saved_tensors
         G, M = dxyz.shape[0], c_xyz.shape[0]
         N, K = idx.shape
-        z = lambda t: torch.zeros_like(t)
+        z = lambda t: _lib.acc_zeros(t.shape, t.device)          # int64 accumulators in deterministic mode
         d_xyz, d_rot, d_cxyz, d_crad, d_dxyz, d_dquat = z(xyz), z(rot), z(c_xyz), z(c_radius_raw), z(dxyz), z(dquat)
         g_means3D = g_means3D.contiguous().float() if g_means3D is not None else torch.zeros(G, N, 3, device=xyz.device)
         g_rot = g_rot.contiguous().float() if g_rot is not None else torch.zeros(G, N, 4, device=xyz.device)
@@ -384,6 +392,7 @@ class _LBSFn(torch.autograd.Function):
                   _lib.ptr(c_xyz), _lib.ptr(c_radius_raw), _lib.ptr(dxyz), _lib.ptr(dquat), _lib.ptr(g_means3D),
                   _lib.ptr(g_rot), _lib.ptr(d_xyz), _lib.ptr(d_rot), _lib.ptr(d_cxyz), _lib.ptr(d_crad),
                   _lib.ptr(d_dxyz), _lib.ptr(d_dquat), _lib.stream())
+        d_xyz, d_rot, d_cxyz, d_crad, d_dxyz, d_dquat = map(_lib.acc_result, (d_xyz, d_rot, d_cxyz, d_crad, d_dxyz, d_dquat))
         return d_xyz, d_rot, d_cxyz, d_crad, d_dxyz, d_dquat, None, None
 
 

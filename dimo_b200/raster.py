@@ -47,7 +47,7 @@ class RasterState:
     __slots__ = ("B", "N", "W", "H", "R", "count_overflow", "cams", "splats", "radii", "tiles_touched", "rects", "perm",
                  "keys_sorted",
                  "vals_sorted", "ranges", "final_T", "n_contrib", "sh_degree", "sh_coeffs",
-                 "scale_modifier", "frame_src", "n_src", "value_bits")
+                 "scale_modifier", "frame_src", "n_src", "value_bits", "act_flags")
 
     # The sorted instance list is either (keys_sorted, vals_sorted) = (frame*tiles + tile, index into B*N) or, packed
     # (value_bits > 0, include/dimo_b200.h dimo_raster_packed_value_bits), single words in vals_sorted.  These two
@@ -70,7 +70,7 @@ class RasterState:
 
 
 def _forward_impl(cams, means3D, scales, rotations, opacities, shs, colors_precomp, B, N, W, H, sh_degree,
-                  scale_modifier, capacity=None, frame_src=None, n_src=None, depth_normal=True):
+                  scale_modifier, capacity=None, frame_src=None, n_src=None, depth_normal=True, act_flags=0):
     """capacity=None: exact mode -- the instance count R is read back from the device once (a host sync, like the
     upstream rasterisers) and buffers are sized to it.  capacity=int: sync-free mode for CUDA graphs -- buffers hold
     `capacity` instance slots, `st.count_overflow` (device i32[2]) receives the true count and an overflow flag."""
@@ -85,6 +85,7 @@ def _forward_impl(cams, means3D, scales, rotations, opacities, shs, colors_preco
     st.sh_coeffs = 0 if shs is None else int(shs.shape[-2])
     st.scale_modifier = float(scale_modifier)
     st.frame_src, st.n_src = frame_src, n_src
+    st.act_flags = int(act_flags)
     BN = B * N
     st.splats = torch.empty(BN, SPLAT_FLOATS, **f32)
     st.radii = torch.empty(BN, **i32)
@@ -97,7 +98,7 @@ def _forward_impl(cams, means3D, scales, rotations, opacities, shs, colors_preco
     total = torch.empty(1, dtype=torch.int64, device=dev)
     R_host = ctypes.c_int64(0)
     s = _lib.stream()
-    _lib.call("dimo_raster_preprocess", B, N, W, H, st.sh_degree, st.sh_coeffs, st.scale_modifier, _lib.ptr(cams),
+    _lib.call("dimo_raster_preprocess", B, N, W, H, st.sh_degree, st.sh_coeffs, st.scale_modifier, st.act_flags, _lib.ptr(cams),
               _lib.ptr(frame_src),
               _lib.ptr(means3D), _bstride(means3D, B, N * 3, n_src),
               _lib.ptr(scales), _bstride(scales, B, N * 3),
@@ -147,13 +148,13 @@ def _forward_impl(cams, means3D, scales, rotations, opacities, shs, colors_preco
 class _Rasterize(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, scales, rotations, opacities, shs, colors_precomp, cams, B, N, W, H,
-                sh_degree, scale_modifier, state_out, capacity, frame_src, n_src, depth_normal=True):
+                sh_degree, scale_modifier, state_out, capacity, frame_src, n_src, depth_normal=True, act_flags=0):
         color, depth, normal, alpha, st = _forward_impl(cams, means3D, scales, rotations, opacities, shs,
                                                         colors_precomp, B, N, W, H, sh_degree, scale_modifier,
-                                                        capacity, frame_src, n_src, depth_normal)
+                                                        capacity, frame_src, n_src, depth_normal, act_flags)
         ctx.st = st
         ctx.set_materialize_grads(False)     # unused outputs (depth / normal in the image-loss step) arrive as None
-        ctx.save_for_backward(means3D, scales, rotations, shs)
+        ctx.save_for_backward(means3D, scales, rotations, shs, opacities)
         ctx.shapes = (means3D.shape, None if means2D is None else means2D.shape, scales.shape, rotations.shape,
                       opacities.shape, None if shs is None else shs.shape,
                       None if colors_precomp is None else colors_precomp.shape)
@@ -166,7 +167,7 @@ class _Rasterize(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_color, g_depth, g_normal, g_alpha, _g_radii):
         st = ctx.st
-        means3D, scales, rotations, shs = ctx.saved_tensors
+        means3D, scales, rotations, shs, opacities = ctx.saved_tensors
         B, N, W, H = st.B, st.N, st.W, st.H
         dev = means3D.device
         f32 = dict(dtype=torch.float32, device=dev)
@@ -179,10 +180,12 @@ class _Rasterize(torch.autograd.Function):
             g_normal = g_normal.contiguous() if g_normal is not None else zeros(B, 3, H, W)
         g_alpha = g_alpha.contiguous() if g_alpha is not None else zeros(B, 1, H, W)
         s = _lib.stream()
-        dsplats = torch.empty(B * N, SPLAT_FLOATS, **f32)
+        # deterministic mode: the kernel accumulates into an int64 record table (zeroed by the call like the fp32 one)
+        dsplats = torch.empty(B * N, SPLAT_FLOATS, dtype=torch.int64 if _lib.deterministic() else torch.float32, device=dev)
         _lib.call("dimo_raster_blend_bwd", B, N, W, H, st.value_bits, _lib.ptr(st.cams), _lib.ptr(st.splats),
                   _lib.ptr(st.vals_sorted), _lib.ptr(st.ranges), _lib.ptr(st.final_T), _lib.ptr(st.n_contrib), _lib.ptr(g_color),
                   _lib.ptr(g_depth), _lib.ptr(g_normal), _lib.ptr(g_alpha), _lib.ptr(dsplats), s)
+        dsplats = _lib.acc_result(dsplats)
         d_means3D = torch.empty(B, N, 3, **f32)
         d_means2D = torch.empty(B, N, 3, **f32)
         d_scales = torch.empty(B, N, 3, **f32)
@@ -191,11 +194,12 @@ class _Rasterize(torch.autograd.Function):
         use_sh = shs is not None
         d_shs = torch.empty(B, N, st.sh_coeffs, 3, **f32) if use_sh else None
         d_col = None if use_sh else torch.empty(B, N, 3, **f32)
-        _lib.call("dimo_raster_preprocess_bwd", B, N, W, H, st.sh_degree, st.sh_coeffs, st.scale_modifier,
+        _lib.call("dimo_raster_preprocess_bwd", B, N, W, H, st.sh_degree, st.sh_coeffs, st.scale_modifier, st.act_flags,
                   _lib.ptr(st.cams), _lib.ptr(st.frame_src),
                   _lib.ptr(means3D), _bstride(means3D, B, N * 3, st.n_src),
                   _lib.ptr(scales), _bstride(scales, B, N * 3),
                   _lib.ptr(rotations), _bstride(rotations, B, N * 4, st.n_src),
+                  _lib.ptr(opacities), _bstride(opacities, B, N),
                   _lib.ptr(shs), _bstride(shs, B, N * st.sh_coeffs * 3) if use_sh else 0,
                   _lib.ptr(st.radii), _lib.ptr(dsplats), _lib.ptr(d_means3D), _lib.ptr(d_means2D),
                   _lib.ptr(d_scales), _lib.ptr(d_rot), _lib.ptr(d_op), _lib.ptr(d_shs), _lib.ptr(d_col), s)
@@ -224,16 +228,18 @@ class _Rasterize(torch.autograd.Function):
                 fit(d_scales, sh_sc, N * 3), fit(d_rot, sh_rot, N * 4, True), fit(d_op, sh_op, N),
                 fit(d_shs, sh_shs, N * st.sh_coeffs * 3) if use_sh else None,
                 fit(d_col, sh_col, N * 3) if not use_sh else None,
-                None, None, None, None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None, None, None, None)
 
 
 def rasterize_batch(cams, means3D, scales, rotations, opacities, W, H, shs=None, colors_precomp=None,
                     sh_degree=0, scale_modifier=1.0, means2D=None, state_out=None, capacity=None, frame_src=None,
-                    depth_normal=True):
+                    depth_normal=True, raw_activations=False):
     """cams [B,40]; means3D [B,N,3] or [N,3]; scales [N,3]; rotations [B,N,4] or [N,4]; opacities [N,1]/[N];
     shs [N,K,3] xor colors_precomp [B?,N,3].  frame_src [B] int32 (device): means3D / rotations are [U,N,*] and
     frame b uses block frame_src[b] (frames that differ only in the view share one deformation).
     depth_normal=False: depth and normal are not rendered (returned as None).
+    raw_activations=True: `scales` are log-scales and `opacities` logits (the model's raw _scaling / _opacity); exp and
+    sigmoid run inside the projection kernels and the gradients come back w.r.t. the raw parameters.
     Returns color [B,3,H,W], depth [B,1,H,W], normal [B,3,H,W], alpha [B,1,H,W], radii [B,N] int32."""
     if (shs is None) == (colors_precomp is None):
         raise ValueError("Please provide exactly one of either SHs or precomputed colors!")
@@ -248,4 +254,4 @@ def rasterize_batch(cams, means3D, scales, rotations, opacities, W, H, shs=None,
             raise ValueError("frame_src supports at most 1024 frames per launch set")
     return _Rasterize.apply(c(means3D), means2D, c(scales), c(rotations), c(opacities), c(shs), c(colors_precomp),
                             cams.contiguous(), B, N, int(W), int(H), int(sh_degree), float(scale_modifier), state_out,
-                            capacity, frame_src, n_src, bool(depth_normal))
+                            capacity, frame_src, n_src, bool(depth_normal), 3 if raw_activations else 0)

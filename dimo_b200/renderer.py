@@ -179,10 +179,11 @@ class Renderer:
         else:
             colors = override_color
         state = []
+        # exp / sigmoid of the raw _scaling / _opacity run inside the projection kernels (A4 folded in)
         color, depth, normal, alpha, radii = _raster.rasterize_batch(
-            prep["cams"], means3D, g.get_scaling, rotations, g.get_opacity, W, H, shs=shs, colors_precomp=colors,
+            prep["cams"], means3D, g._scaling, rotations, g._opacity, W, H, shs=shs, colors_precomp=colors,
             sh_degree=g.active_sh_degree, scale_modifier=scaling_modifier, state_out=state, capacity=capacity,
-            frame_src=frame_src, depth_normal=depth_normal)
+            frame_src=frame_src, depth_normal=depth_normal, raw_activations=True)
         return {"image": color.clamp(0, 1) if clamp else None, "image_raw": color, "depth": depth, "normal": normal,
                 "alpha": alpha, "radii": radii, "visibility_filter": (radii > 0) if with_visibility else None,
                 "pts_t": means3D, "cpts_t": cpts_t, "pair_of_frame": prep["pair_of_frame"], "raster_state": state[0]}

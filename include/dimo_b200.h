@@ -77,9 +77,12 @@ int dimo_raster_packed_value_bits(int B, int N, int W, int H);
  *   R_host: if non-NULL the stream is synchronised and the total instance count is stored there.
  *   frame_src [B] i32 (device, or NULL = identity): frame b reads means3D / rotations block frame_src[b] -- the
  *   deformation depends on (motion, t) only, so the frames of a step that differ in the view alone share one
- *   block (renderer/latent_gs_renderer.py:1191-1219 is recomputed per render upstream). */
+ *   block (renderer/latent_gs_renderer.py:1191-1219 is recomputed per render upstream).
+ *   act_flags: bit 0 = `scales` are the model's raw log-scales (exp applied in the kernel), bit 1 = `opacities` are
+ *   logits (sigmoid applied in the kernel): GaussianModel.get_scaling / get_opacity (:257-265, 340-355) folded in;
+ *   the backward then returns gradients w.r.t. the raw parameters. */
 int dimo_raster_preprocess(
-    int B, int N, int W, int H, int sh_degree, int sh_coeffs, float scale_modifier,
+    int B, int N, int W, int H, int sh_degree, int sh_coeffs, float scale_modifier, int act_flags,
     const float* cams, const int32_t* frame_src,
     const float* means3D, int64_t means3D_bstride,
     const float* scales, int64_t scales_bstride,
@@ -129,11 +132,12 @@ int dimo_raster_blend_bwd(
  *   dL_dmeans3D [B,N,3], dL_dmeans2D [B,N,3] (NDC units, z=0), dL_dscales [B,N,3],
  *   dL_drotations [B,N,4], dL_dopacities [B,N], dL_dshs [B,N,sh_coeffs,3] or dL_dcolors [B,N,3]. */
 int dimo_raster_preprocess_bwd(
-    int B, int N, int W, int H, int sh_degree, int sh_coeffs, float scale_modifier,
+    int B, int N, int W, int H, int sh_degree, int sh_coeffs, float scale_modifier, int act_flags,
     const float* cams, const int32_t* frame_src,
     const float* means3D, int64_t means3D_bstride,
     const float* scales, int64_t scales_bstride,
     const float* rotations, int64_t rotations_bstride,
+    const float* opacities, int64_t opacities_bstride,
     const float* shs, int64_t shs_bstride,
     const int32_t* radii, const float* dL_dsplats,
     float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dscales, float* dL_drotations,
@@ -241,6 +245,20 @@ int dimo_timenet_fwd(int G, int M, int L, const float* pts, const float* times, 
 int dimo_timenet_bwd(int G, int M, int L, const float* const* W_host, void* workspace, size_t workspace_bytes,
                      const float* g_dxyz, const float* g_dquat, float* const* dW_host, float* const* db_host,
                      float* dpts, float* dlatents, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Deterministic gradient accumulation (hard part 4).  Off (default): gradients that several CTAs
+ * add into are summed with fp32 atomics / vector reductions -- run-to-run differences of ~1e-7 of the tensor scale.
+ * On: every such accumulation target of dimo_raster_blend_bwd (dL_dsplats), dimo_lbs_bwd (its six outputs),
+ * dimo_timenet_bwd (dW / db / dpts / dlatents), dimo_timenet_embed_bwd and dimo_linear_bwd_weight must be an INT64
+ * buffer with the same element count (zeroed by the caller); addends are rounded to multiples of 2^-28 and summed with
+ * native 64-bit integer reductions (associative: bit-identical results in any arrival order; range +-3.4e10).
+ * dimo_fixed_to_float converts such a buffer to fp32 (dst = or += src * 2^-28).  The scalar loss sums keep fp32
+ * atomics (they feed no gradient).
+ * ------------------------------------------------------------------------------------------- */
+int dimo_set_deterministic(int on);
+int dimo_get_deterministic(void);
+int dimo_fixed_to_float(int64_t n, const void* src_i64, float* dst, int accumulate, void* stream);
 
 /* bring-up knobs (0: swap LBO/SBO, 1: single-pass TF32, 2: wgrad CTA target, 3: blend gather via 16-byte
  * cp.async instead of 64-byte bulk copies, 4 / 5: records per stage of the blend backward / forward, 64 or 128, 6: 1 = never pack
