@@ -38,7 +38,7 @@ def build(renderer_cls, device, init_kwargs=None):
         g._timenet.pts_layers[-1].weight.copy_(0.02 * torch.randn(3, 256, generator=gen))
         g._timenet.rot_layers[-1].weight.copy_(0.02 * torch.randn(4, 256, generator=gen))
         g._opacity.copy_(torch.randn(g._opacity.shape, generator=gen))
-        g._scaling.add_(0.9 + 0.2 * torch.randn(g._scaling.shape, generator=gen))
+        g._scaling.add_((0.9 + 0.2 * torch.randn(g._scaling.shape, generator=gen)).to(g._scaling.device))
         g._features_dc.copy_(torch.randn(g._features_dc.shape, generator=gen))
         g._rotation.copy_(torch.randn(g._rotation.shape, generator=gen))
         g._latent_codes.copy_(torch.randn(g._latent_codes.shape, generator=gen))
