@@ -238,7 +238,7 @@ def rasterize_batch(cams, means3D, scales, rotations, opacities, W, H, shs=None,
     shs [N,K,3] xor colors_precomp [B?,N,3].  frame_src [B] int32 (device): means3D / rotations are [U,N,*] and
     frame b uses block frame_src[b] (frames that differ only in the view share one deformation).
     depth_normal=False: depth and normal are not rendered (returned as None).
-    raw_activations=True: `scales` are log-scales and `opacities` logits (the model's raw _scaling / _opacity); exp and
+    raw_activations=True (or a bit mask: 1 = scales, 2 = opacities): `scales` are log-scales and `opacities` logits (the model's raw _scaling / _opacity); exp and
     sigmoid run inside the projection kernels and the gradients come back w.r.t. the raw parameters.
     Returns color [B,3,H,W], depth [B,1,H,W], normal [B,3,H,W], alpha [B,1,H,W], radii [B,N] int32."""
     if (shs is None) == (colors_precomp is None):
@@ -254,4 +254,5 @@ def rasterize_batch(cams, means3D, scales, rotations, opacities, W, H, shs=None,
             raise ValueError("frame_src supports at most 1024 frames per launch set")
     return _Rasterize.apply(c(means3D), means2D, c(scales), c(rotations), c(opacities), c(shs), c(colors_precomp),
                             cams.contiguous(), B, N, int(W), int(H), int(sh_degree), float(scale_modifier), state_out,
-                            capacity, frame_src, n_src, bool(depth_normal), 3 if raw_activations else 0)
+                            capacity, frame_src, n_src, bool(depth_normal),
+                            (3 if raw_activations is True else int(raw_activations or 0)))

@@ -179,11 +179,13 @@ class Renderer:
         else:
             colors = override_color
         state = []
-        # exp / sigmoid of the raw _scaling / _opacity run inside the projection kernels (A4 folded in)
+        # exp / sigmoid of the raw _scaling / _opacity run inside the projection kernels (A4 folded in); while the shared
+        # radius `_r` of stage s1 is alive the scales come from it (get_scaling, :340-350) through torch
+        own_scales = len(g._r) == 0
         color, depth, normal, alpha, radii = _raster.rasterize_batch(
-            prep["cams"], means3D, g._scaling, rotations, g._opacity, W, H, shs=shs, colors_precomp=colors,
-            sh_degree=g.active_sh_degree, scale_modifier=scaling_modifier, state_out=state, capacity=capacity,
-            frame_src=frame_src, depth_normal=depth_normal, raw_activations=True)
+            prep["cams"], means3D, g._scaling if own_scales else g.get_scaling, rotations, g._opacity, W, H, shs=shs,
+            colors_precomp=colors, sh_degree=g.active_sh_degree, scale_modifier=scaling_modifier, state_out=state,
+            capacity=capacity, frame_src=frame_src, depth_normal=depth_normal, raw_activations=(1 if own_scales else 0) | 2)
         return {"image": color.clamp(0, 1) if clamp else None, "image_raw": color, "depth": depth, "normal": normal,
                 "alpha": alpha, "radii": radii, "visibility_filter": (radii > 0) if with_visibility else None,
                 "pts_t": means3D, "cpts_t": cpts_t, "pair_of_frame": prep["pair_of_frame"], "raster_state": state[0]}

@@ -64,7 +64,8 @@ def main():
                                 fovy, fovy, 0.01, 100)
 
     r = render_scenario.build(renderer.Renderer, "cpu")
-    rec = render_scenario.run(r, make_cam, lambda c, x: oknn.knn(c, x, 4), "cpu")
+    rec = render_scenario.run(r, make_cam, lambda c, x: oknn.knn(c, x, 4), "cpu")     # (the reference reaches distCUDA2
+    # through its simple_knn import, which reference_modules() serves with the oracle)
     np.savez_compressed(os.path.join(HERE, "render.npz"), **rec)
     print("render.npz:", len(rec), "arrays", {k: float(np.abs(v).max()) for k, v in rec.items() if k.endswith("/image")})
 
