@@ -148,7 +148,7 @@ _OWN_LAUNCHES = {
     "dimo_arap_connectivity": 1, "dimo_arap_energy": 1, "dimo_linear_fwd": 1,
     "dimo_linear_bwd_data": 1, "dimo_linear_tc": 1, "dimo_linear_wgrad_tc": 1, "dimo_linear_wgrad_tc_grouped": 1, "dimo_linear_bwd_weight": 1, "dimo_timenet_embed_fwd": 1,
     "dimo_timenet_embed_bwd": 1, "dimo_lbs_fwd": 1, "dimo_lbs_bwd": 1, "dimo_ssim_fwd": 1, "dimo_ssim_bwd": 1,
-    "dimo_timenet_fwd": 15, "dimo_timenet_bwd": 19, "dimo_fixed_to_float": 1,
+    "dimo_timenet_fwd": 14, "dimo_timenet_bwd": 14, "dimo_fixed_to_float": 1,
     "dimo_sqdiff_sum": 1, "dimo_smooth_fwd": 1, "dimo_smooth_bwd": 1, "dimo_segment_sum": 1, "dimo_adam_step": 1, "dimo_transpose_grouped": 1, "dimo_gt_fetch": 1,
 }
 

@@ -114,6 +114,42 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 static_assert(CHUNK == 2 * BLEND_THREADS, "stage_gather assigns two records per thread");
 
+// Packed FP32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: one issue slot for two lanes' worth of fp32 math).  The blend
+// loops are issue-bound (smsp__issue_active ~80 %, profiles/r2c_*), and every thread runs the same arithmetic on four
+// pixels, so the FMA-pipe instructions are issued on pixel PAIRS; compares, selects and MUFU stay scalar.
+struct f2 { float x, y; };
+__device__ __forceinline__ unsigned long long f2_pack(f2 a) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+  return r;
+}
+__device__ __forceinline__ f2 f2_unpack(unsigned long long v) {
+  f2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ f2 f2_bcast(float a) { return f2{a, a}; }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)), "l"(f2_pack(c)));
+  return f2_unpack(d);
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+  return f2_unpack(d);
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+  return f2_unpack(d);
+}
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) {
+  unsigned long long d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+  return f2_unpack(d);
+}
+
 __device__ __forceinline__ float rcp_approx(float x) {
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));   // one MUFU.RCP (__fdividef expands to a denormal-guarded sequence)
@@ -209,12 +245,14 @@ __global__ void __launch_bounds__(BLEND_THREADS, DN ? 12 : 16) blend_fwd_kernel(
         const float4 bq = s[j * REC_F4 + 1];  // c2, opacity, pthr2, r
         const float dy = a.y - pyf, dx0 = a.x - pxf0;
         const float by = a.w * dy, cy = bq.x * dy * dy;
-        float p[PPT];
+        // pixels (0,1) and (2,3) as packed pairs
+        f2 pp[2];
 #pragma unroll
-        for (int i = 0; i < PPT; ++i) {
-          const float dx = dx0 - (float)i;
-          p[i] = fmaf(fmaf(a.z, dx, by), dx, cy);
+        for (int h = 0; h < 2; ++h) {
+          const f2 dx = sub2(f2_bcast(dx0), f2{(float)(2 * h), (float)(2 * h + 1)});
+          pp[h] = fma2(fma2(f2_bcast(a.z), dx, f2_bcast(by)), dx, f2_bcast(cy));
         }
+        const float p[PPT] = {pp[0].x, pp[0].y, pp[1].x, pp[1].y};
         // pthr2 is conservative (0.7 % margin on alpha): below it no pixel can reach alpha >= 1/255
         const float pmax = fmaxf(fmaxf(p[0], p[1]), fmaxf(p[2], p[3]));
         if (!__any_sync(0xffffffffu, pmax >= bq.z && alive != 0)) continue;
@@ -224,20 +262,29 @@ __global__ void __launch_bounds__(BLEND_THREADS, DN ? 12 : 16) blend_fwd_kernel(
         const int idx = base + j;
         bool died[PPT];
 #pragma unroll
-        for (int i = 0; i < PPT; ++i) {
-          const float alpha = fminf(ALPHA_MAX, bq.y * ex2_approx(p[i]));
-          const float test_T = T[i] * (1.0f - alpha);
-          const bool cand = (p[i] <= 0.f) & (alpha >= amin[i]);       // the pair passes the reference's two skips
-          const bool ok = cand & (test_T >= T_MIN);                   // ... and the pixel is not saturated by it
-          died[i] = cand & !ok;
-          const float w = ok ? alpha * T[i] : 0.f;
-          A[0][i] = fmaf(bq.w, w, A[0][i]); A[1][i] = fmaf(cq.x, w, A[1][i]); A[2][i] = fmaf(cq.y, w, A[2][i]);
+        for (int h = 0; h < 2; ++h) {
+          const int i0 = 2 * h, i1 = 2 * h + 1;
+          const f2 og = mul2(f2_bcast(bq.y), f2{ex2_approx(p[i0]), ex2_approx(p[i1])});
+          const f2 alpha = f2{fminf(ALPHA_MAX, og.x), fminf(ALPHA_MAX, og.y)};
+          const f2 Tp = f2{T[i0], T[i1]};
+          const f2 test_T = mul2(Tp, sub2(f2_bcast(1.0f), alpha));
+          const f2 wa = mul2(alpha, Tp);
+          const bool cand0 = (p[i0] <= 0.f) & (alpha.x >= amin[i0]), cand1 = (p[i1] <= 0.f) & (alpha.y >= amin[i1]);
+          const bool ok0 = cand0 & (test_T.x >= T_MIN), ok1 = cand1 & (test_T.y >= T_MIN);
+          died[i0] = cand0 & !ok0; died[i1] = cand1 & !ok1;
+          const f2 w = f2{ok0 ? wa.x : 0.f, ok1 ? wa.y : 0.f};
+          f2 acc;
+          acc = fma2(f2_bcast(bq.w), w, f2{A[0][i0], A[0][i1]}); A[0][i0] = acc.x; A[0][i1] = acc.y;
+          acc = fma2(f2_bcast(cq.x), w, f2{A[1][i0], A[1][i1]}); A[1][i0] = acc.x; A[1][i1] = acc.y;
+          acc = fma2(f2_bcast(cq.y), w, f2{A[2][i0], A[2][i1]}); A[2][i0] = acc.x; A[2][i1] = acc.y;
           if (DN) {
-            A[3][i] = fmaf(cq.z, w, A[3][i]);
-            A[4][i] = fmaf(cq.w, w, A[4][i]); A[5][i] = fmaf(dq.x, w, A[5][i]); A[6][i] = fmaf(dq.y, w, A[6][i]);
+            acc = fma2(f2_bcast(cq.z), w, f2{A[3][i0], A[3][i1]}); A[3][i0] = acc.x; A[3][i1] = acc.y;
+            acc = fma2(f2_bcast(cq.w), w, f2{A[4][i0], A[4][i1]}); A[4][i0] = acc.x; A[4][i1] = acc.y;
+            acc = fma2(f2_bcast(dq.x), w, f2{A[5][i0], A[5][i1]}); A[5][i0] = acc.x; A[5][i1] = acc.y;
+            acc = fma2(f2_bcast(dq.y), w, f2{A[6][i0], A[6][i1]}); A[6][i0] = acc.x; A[6][i1] = acc.y;
           }
-          T[i] = ok ? test_T : T[i];
-          last[i] = ok ? idx : last[i];
+          T[i0] = ok0 ? test_T.x : T[i0]; T[i1] = ok1 ? test_T.y : T[i1];
+          last[i0] = ok0 ? idx : last[i0]; last[i1] = ok1 ? idx : last[i1];
         }
         if (__any_sync(0xffffffffu, died[0] | died[1] | died[2] | died[3])) {      // rare: a pixel saturated here
 #pragma unroll
@@ -430,45 +477,59 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_bwd_kernel(
       const float4 bq = s[j * REC_F4 + 1];
       const float dy = a.y - pyf, dx0 = a.x - pxf0;
       const float by = a.w * dy, cy = bq.x * dy * dy;
-      float p[PPT];
+      f2 dxp[2], pp[2];                 // pixels (0,1) and (2,3) as packed pairs (FFMA2 / FMUL2 / FADD2)
 #pragma unroll
-      for (int i = 0; i < PPT; ++i) {
-        const float dx = dx0 - (float)i;
-        p[i] = fmaf(fmaf(a.z, dx, by), dx, cy);
+      for (int h = 0; h < 2; ++h) {
+        dxp[h] = sub2(f2_bcast(dx0), f2{(float)(2 * h), (float)(2 * h + 1)});
+        pp[h] = fma2(fma2(f2_bcast(a.z), dxp[h], f2_bcast(by)), dxp[h], f2_bcast(cy));
       }
+      const float p[PPT] = {pp[0].x, pp[0].y, pp[1].x, pp[1].y};
       const float pmax = fmaxf(fmaxf(p[0], p[1]), fmaxf(p[2], p[3]));
       if (!__any_sync(0xffffffffu, pmax >= bq.z && pos < lmax)) continue;
       // blend: branch-free over the 4 pixels; a pair the forward pass skipped contributes exact zeros
-      float vt = 0.f, vsx = 0.f, vsxx = 0.f, vr = 0.f, vg = 0.f, vb = 0.f;
-      float vd = 0.f, vn0 = 0.f, vn1 = 0.f, vn2 = 0.f;
       const float4 cq = s[j * REC_F4 + 2];  // g, b, depth, nx
       float4 dq = make_float4(0.f, 0.f, 0.f, 0.f);
       if (DN) dq = s[j * REC_F4 + 3];       // ny, nz, gid, -
+      f2 vt2 = f2_bcast(0.f), vsx2 = f2_bcast(0.f), vsxx2 = f2_bcast(0.f), vr2 = f2_bcast(0.f), vg2 = f2_bcast(0.f),
+         vb2 = f2_bcast(0.f), vd2 = f2_bcast(0.f), vn02 = f2_bcast(0.f), vn12 = f2_bcast(0.f), vn22 = f2_bcast(0.f);
 #pragma unroll
-      for (int i = 0; i < PPT; ++i) {
-        const float G = ex2_approx(p[i]);
-        const float alpha = fminf(ALPHA_MAX, bq.y * G);
-        const bool valid = (pos < last[i]) & (p[i] <= 0.f) & (alpha >= ALPHA_MIN);
-        const float dx = dx0 - (float)i;
-        const float inv = rcp_approx(1.0f - alpha);       // alpha <= 0.99: MUFU.RCP (1 ulp) is ample for the 1e-4 bound
-        const float Tn = T[i] * inv;                      // transmittance in front of this record
-        const float w = alpha * Tn;
-        float dotf = gc0[i] * bq.w + gc1[i] * cq.x + gc2[i] * cq.y;
-        if (DN) dotf += gd[i] * cq.z + gn0[i] * cq.w + gn1[i] * dq.x + gn2[i] * dq.y;
-        const float dLa = Tn * dotf - Qp[i] * inv;
-        const float Qn = fmaf(dotf, w, Qp[i]);
-        const float tt = valid ? G * dLa : 0.f;           // dL/dopacity contribution; dL/dp2 = tt * op * ln2
-        const float wv = valid ? w : 0.f;
-        T[i] = valid ? Tn : T[i];
-        Qp[i] = valid ? Qn : Qp[i];
-        const float dxt = dx * tt;
-        vt += tt; vsx += dxt; vsxx = fmaf(dx, dxt, vsxx);
-        vr = fmaf(gc0[i], wv, vr); vg = fmaf(gc1[i], wv, vg); vb = fmaf(gc2[i], wv, vb);
+      for (int h = 0; h < 2; ++h) {
+        const int i0 = 2 * h, i1 = 2 * h + 1;
+        const f2 G = f2{ex2_approx(p[i0]), ex2_approx(p[i1])};
+        const f2 og = mul2(f2_bcast(bq.y), G);
+        const f2 alpha = f2{fminf(ALPHA_MAX, og.x), fminf(ALPHA_MAX, og.y)};
+        const bool valid0 = (pos < last[i0]) & (p[i0] <= 0.f) & (alpha.x >= ALPHA_MIN);
+        const bool valid1 = (pos < last[i1]) & (p[i1] <= 0.f) & (alpha.y >= ALPHA_MIN);
+        const f2 om = sub2(f2_bcast(1.0f), alpha);
+        const f2 inv = f2{rcp_approx(om.x), rcp_approx(om.y)};      // alpha <= 0.99: MUFU.RCP (1 ulp) is ample for the 1e-4 bound
+        const f2 Tp = f2{T[i0], T[i1]}, Qq = f2{Qp[i0], Qp[i1]};
+        const f2 Tn = mul2(Tp, inv);                                // transmittance in front of this record
+        const f2 w = mul2(alpha, Tn);
+        const f2 g0 = f2{gc0[i0], gc0[i1]}, g1 = f2{gc1[i0], gc1[i1]}, g2 = f2{gc2[i0], gc2[i1]};
+        f2 dotf = fma2(g2, f2_bcast(cq.y), fma2(g1, f2_bcast(cq.x), mul2(g0, f2_bcast(bq.w))));
+        f2 gdp = f2_bcast(0.f), gn0p = gdp, gn1p = gdp, gn2p = gdp;
         if (DN) {
-          vd = fmaf(gd[i], wv, vd);
-          vn0 = fmaf(gn0[i], wv, vn0); vn1 = fmaf(gn1[i], wv, vn1); vn2 = fmaf(gn2[i], wv, vn2);
+          gdp = f2{gd[i0], gd[i1]}; gn0p = f2{gn0[i0], gn0[i1]}; gn1p = f2{gn1[i0], gn1[i1]}; gn2p = f2{gn2[i0], gn2[i1]};
+          dotf = fma2(gn2p, f2_bcast(dq.y), fma2(gn1p, f2_bcast(dq.x), fma2(gn0p, f2_bcast(cq.w), fma2(gdp, f2_bcast(cq.z), dotf))));
+        }
+        const f2 dLa = sub2(mul2(Tn, dotf), mul2(Qq, inv));
+        const f2 Qn = fma2(dotf, w, Qq);
+        const f2 tg = mul2(G, dLa);                                 // dL/dopacity contribution; dL/dp2 = tt * op * ln2
+        const f2 tt = f2{valid0 ? tg.x : 0.f, valid1 ? tg.y : 0.f};
+        const f2 wv = f2{valid0 ? w.x : 0.f, valid1 ? w.y : 0.f};
+        T[i0] = valid0 ? Tn.x : T[i0]; T[i1] = valid1 ? Tn.y : T[i1];
+        Qp[i0] = valid0 ? Qn.x : Qp[i0]; Qp[i1] = valid1 ? Qn.y : Qp[i1];
+        const f2 dxt = mul2(dxp[h], tt);
+        vt2 = add2(vt2, tt); vsx2 = add2(vsx2, dxt); vsxx2 = fma2(dxp[h], dxt, vsxx2);
+        vr2 = fma2(g0, wv, vr2); vg2 = fma2(g1, wv, vg2); vb2 = fma2(g2, wv, vb2);
+        if (DN) {
+          vd2 = fma2(gdp, wv, vd2);
+          vn02 = fma2(gn0p, wv, vn02); vn12 = fma2(gn1p, wv, vn12); vn22 = fma2(gn2p, wv, vn22);
         }
       }
+      const float vt = vt2.x + vt2.y, vsx = vsx2.x + vsx2.y, vsxx = vsxx2.x + vsxx2.y;
+      const float vr = vr2.x + vr2.y, vg = vg2.x + vg2.y, vb = vb2.x + vb2.y;
+      const float vd = vd2.x + vd2.y, vn0 = vn02.x + vn02.y, vn1 = vn12.x + vn12.y, vn2 = vn22.x + vn22.y;
       const float vsy = dy * vt, vsxy = dy * vsx, vsyy = dy * vsy;
       float* const row = my_acc + j * NG;
       if (!DN) {

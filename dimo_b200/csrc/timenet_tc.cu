@@ -203,6 +203,116 @@ __global__ void __launch_bounds__(256) tn_tiles_kernel(const TilesArgs p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// the 3- and 4-wide output layers (pts_layers.2, rot_layers.2) in FP32 SIMT: one launch per direction
+// ---------------------------------------------------------------------------------------------------------------
+// forward: one warp per row; dxyz[r, :] = hp[r, :] W9^T + b9, dquat[r, :] = hr[r, :] W11^T + b11
+__global__ void __launch_bounds__(256) tn_heads_fwd_kernel(int R, const float* __restrict__ hp, const float* __restrict__ hr,
+                                                           const float* __restrict__ W9, const float* __restrict__ b9,
+                                                           const float* __restrict__ W11, const float* __restrict__ b11,
+                                                           float* __restrict__ dxyz, float* __restrict__ dquat) {
+  __shared__ float w[7][256];
+  for (int e = threadIdx.x; e < 7 * 256; e += blockDim.x) w[e >> 8][e & 255] = (e >> 8) < 3 ? W9[e] : W11[e - 3 * 256];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= R) return;
+  float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int c = half * 128 + lane * 4;
+    const float4 a = *reinterpret_cast<const float4*>(hp + r * 256 + c);
+    const float4 b = *reinterpret_cast<const float4*>(hr + r * 256 + c);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) acc[j] += a.x * w[j][c] + a.y * w[j][c + 1] + a.z * w[j][c + 2] + a.w * w[j][c + 3];
+#pragma unroll
+    for (int j = 3; j < 7; ++j) acc[j] += b.x * w[j][c] + b.y * w[j][c + 1] + b.z * w[j][c + 2] + b.w * w[j][c + 3];
+  }
+#pragma unroll
+  for (int j = 0; j < 7; ++j)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+  if (lane < 3) dxyz[r * 3 + lane] = (lane == 0 ? acc[0] : lane == 1 ? acc[1] : acc[2]) + b9[lane];
+  else if (lane < 7) dquat[r * 4 + (lane - 3)] = (lane == 3 ? acc[3] : lane == 4 ? acc[4] : lane == 5 ? acc[5] : acc[6]) + b11[lane - 3];
+}
+
+// backward: CTA = (128-row block, head).  dH = (g W) * [H > 0] -> split tiles + transposed tiles (the first data-
+// gradient GEMM's A operand / the weight-gradient operand); dW[j, c] += sum_r g[r, j] H[r, c]; db[j] += sum_r g[r, j]
+__global__ void __launch_bounds__(256) tn_heads_bwd_kernel(int R, int Rp, const float* __restrict__ g_dxyz,
+                                                           const float* __restrict__ g_dquat, const float* __restrict__ hp,
+                                                           const float* __restrict__ hr, const float* __restrict__ W9,
+                                                           const float* __restrict__ W11, uint8_t* __restrict__ out_p,
+                                                           uint8_t* __restrict__ outT_p, uint8_t* __restrict__ out_r,
+                                                           uint8_t* __restrict__ outT_r, float* __restrict__ dW9,
+                                                           float* __restrict__ db9, float* __restrict__ dW11,
+                                                           float* __restrict__ db11, float det) {
+  const int rb = blockIdx.x, head = blockIdx.y, tid = threadIdx.x;
+  const int No = head ? 4 : 3;
+  const float* g = head ? g_dquat : g_dxyz;
+  const float* H = head ? hr : hp;
+  const float* W = head ? W11 : W9;
+  uint8_t* out = head ? out_r : out_p;
+  uint8_t* outT = head ? outT_r : outT_p;
+  float* dW = head ? dW11 : dW9;
+  float* db = head ? db11 : db9;
+  __shared__ float sg[128][4];
+  __shared__ float sw[4][256];
+  for (int e = tid; e < 128 * 4; e += 256) {
+    const int r = rb * 128 + (e >> 2), j = e & 3;
+    sg[e >> 2][j] = (r < R && j < No) ? g[(int64_t)r * No + j] : 0.f;
+  }
+  for (int e = tid; e < 4 * 256; e += 256) sw[e >> 8][e & 255] = (e >> 8) < No ? W[e] : 0.f;
+  __syncthreads();
+  // ---- masked data gradient -> tiles: item = (row, 16-byte chunk), consecutive threads take consecutive rows ----
+  for (int it = tid; it < 128 * 64; it += 256) {
+    const int rl = it & 127, qq = it >> 7;              // qq: chunk of 4 columns, 0..63
+    const int r = rb * 128 + rl;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r < R) {
+      const float4 h = *reinterpret_cast<const float4*>(H + (int64_t)r * 256 + qq * 4);
+      const float hv[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = qq * 4 + e;
+        const float d = sg[rl][0] * sw[0][c] + sg[rl][1] * sw[1][c] + sg[rl][2] * sw[2][c] + sg[rl][3] * sw[3][c];
+        v[e] = hv[e] > 0.f ? d : 0.f;
+      }
+    }
+    uint4 hi, lo;
+    tn_split4(make_float4(v[0], v[1], v[2], v[3]), hi, lo);
+    const int kt = qq >> 3, q = qq & 7;
+    uint8_t* t = out + ((size_t)rb * 8 + kt) * TN_STAGE_A + tn_off(rl, q);
+    *reinterpret_cast<uint4*>(t) = hi;
+    *reinterpret_cast<uint4*>(t + TN_PLANE_A) = lo;
+    const int rt = r >> 5, rq = (r & 31) >> 2, re = r & 3;
+    const uint32_t hh[4] = {hi.x, hi.y, hi.z, hi.w}, ll[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int f = qq * 4 + e, fb = f >> 7, fl = f & 127;
+      uint8_t* tt = outT + (((size_t)rt * 2) * 2 + fb) * TN_FB_BYTES + tn_off(fl, rq) + re * 4;
+      *reinterpret_cast<uint32_t*>(tt) = hh[e];
+      *reinterpret_cast<uint32_t*>(tt + (size_t)2 * TN_FB_BYTES) = ll[e];
+    }
+  }
+  // ---- weight / bias gradient of the head: thread = column c ----
+  {
+    const int c = tid;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int rows = min(128, R - rb * 128);
+    for (int rl = 0; rl < rows; ++rl) {
+      const float h = H[(int64_t)(rb * 128 + rl) * 256 + c];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = fmaf(sg[rl][j], h, acc[j]);
+    }
+    for (int j = 0; j < No; ++j) acc_add(dW, (int64_t)j * 256 + c, acc[j], det);
+    if (tid < No) {
+      float s = 0.f;
+      for (int rl = 0; rl < rows; ++rl) s += sg[rl][tid];
+      acc_add(db, tid, s, det);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // GEMM  D[128 rows, N] = sum over segments  A_seg[rows, k] * B_seg[N, k]^T
 // ---------------------------------------------------------------------------------------------------------------
 struct TnSeg { const uint8_t* a; int a_nkt, a_kt0; const uint8_t* b; int nkt; };
@@ -702,10 +812,12 @@ extern "C" int dimo_timenet_fwd(int G, int M, int L, const float* pts, const flo
     if (l == 10) { g.plain = reinterpret_cast<float*>(ws + o.hr_plain); g.ldp = HID; g.plain_cols = HID; }
     if (gemm(g)) { dimo::set_error("tn_gemm_kernel launch failed (layer %d)", l); return -1; }
   }
-  // ---- 3- and 4-wide heads (FP32 SIMT) ----
-  rc = dimo_linear_fwd(R, HID, 3, reinterpret_cast<float*>(ws + o.hp_plain), HID, W_host[9], b_host[9], dxyz, 3, 0, stream);
-  if (rc) return rc;
-  return dimo_linear_fwd(R, HID, 4, reinterpret_cast<float*>(ws + o.hr_plain), HID, W_host[11], b_host[11], dquat, 4, 0, stream);
+  // ---- 3- and 4-wide heads (FP32 SIMT, one launch) ----
+  tn_heads_fwd_kernel<<<ceil_div(R, 8), 256, 0, st>>>(R, reinterpret_cast<float*>(ws + o.hp_plain),
+                                                      reinterpret_cast<float*>(ws + o.hr_plain), W_host[9], b_host[9],
+                                                      W_host[11], b_host[11], dxyz, dquat);
+  DIMO_CHECK_LAUNCH();
+  return 0;
 }
 
 extern "C" int dimo_timenet_bwd(int G, int M, int L, const float* const* W_host, void* workspace, size_t workspace_bytes,
@@ -724,22 +836,12 @@ extern "C" int dimo_timenet_bwd(int G, int M, int L, const float* const* W_host,
   float* dhp = reinterpret_cast<float*>(ws + o.dhp_plain);
   float* dhr = reinterpret_cast<float*>(ws + o.dhr_plain);
   float* dcat = reinterpret_cast<float*>(ws + o.dcat_plain);
-  // ---- heads (FP32 SIMT): weight gradients, data gradients -> masked split tiles ----
-  int rc = dimo_linear_bwd_weight(R, HID, 3, g_dxyz, 3, nullptr, 0, hp, HID, dW_host[9], db_host[9], stream);
-  if (rc) return rc;
-  rc = dimo_linear_bwd_weight(R, HID, 4, g_dquat, 4, nullptr, 0, hr, HID, dW_host[11], db_host[11], stream);
-  if (rc) return rc;
-  rc = dimo_linear_bwd_data(R, HID, 3, g_dxyz, 3, nullptr, 0, W_host[9], dhp, HID, 0, stream);
-  if (rc) return rc;
-  rc = dimo_linear_bwd_data(R, HID, 4, g_dquat, 4, nullptr, 0, W_host[11], dhr, HID, 0, stream);
-  if (rc) return rc;
-  for (int h = 0; h < 2; ++h) {
-    TilesArgs t{};
-    t.R = R; t.Rp = o.Rp; t.cols = HID; t.nkt = 8; t.X = h ? dhr : dhp; t.ldx = HID; t.mask = h ? hr : hp; t.ldm = HID;
-    t.out = ws + o.g[8 + h]; t.out_nkt = 8; t.out_kt0 = 0; t.outT = ws + o.gT[8 + h]; t.t_nfb = 2; t.t_f0 = 0;
-    tn_tiles_kernel<<<ceil_div((int64_t)o.Rp * 64, 256), 256, 0, st>>>(t);
-    DIMO_CHECK_LAUNCH();
-  }
+  // ---- heads (FP32 SIMT, one launch): weight / bias gradients + masked data gradients as split tiles ----
+  tn_heads_bwd_kernel<<<dim3(o.nrb, 2), 256, 0, st>>>(R, o.Rp, g_dxyz, g_dquat, hp, hr, W_host[9], W_host[11], ws + o.g[8],
+                                                      ws + o.gT[8], ws + o.g[9], ws + o.gT[9], dW_host[9], db_host[9],
+                                                      dW_host[11], db_host[11], dimo::det_scale());
+  DIMO_CHECK_LAUNCH();
+  int rc = 0;
   auto gemm = [&](TnGemmArgs& g) {
     tn_gemm_kernel<<<dim3(o.nrb, g.N / TG_NB), TG_THREADS, TG_SMEM, st>>>(g);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
