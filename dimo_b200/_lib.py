@@ -41,6 +41,7 @@ _SIGS = {
     "dimo_linear_wgrad_tc": (c_int, [c_int] * 3 + [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "dimo_linear_wgrad_tc_grouped": (c_int, [c_int, c_int] + [c_vp] * 10 + [c_vp]),
     "dimo_tc_debug_set": (c_int, [c_int, c_int]),
+    "dimo_debug_max_sort_clusters": (c_int, []),
     "dimo_set_deterministic": (c_int, [c_int]),
     "dimo_get_deterministic": (c_int, []),
     "dimo_fixed_to_float": (c_int, [c_i64, c_vp, c_vp, c_int, c_vp]),

@@ -54,6 +54,42 @@ static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b)
 constexpr float DET_SCALE = 268435456.0f;          // 2^28
 float det_scale();                                  // 0 = off (fp32 atomics), DET_SCALE = on   (raster_bin.cu)
 #ifdef __CUDACC__
+// Packed FP32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: one issue slot for two lanes' worth of fp32 math).  The blend
+// loops are issue-bound (smsp__issue_active ~80 %, profiles/r2c_*), and every thread runs the same arithmetic on four
+// pixels, so the FMA-pipe instructions are issued on pixel PAIRS; compares, selects and MUFU stay scalar.
+struct f2 { float x, y; };
+__device__ __forceinline__ unsigned long long f2_pack(f2 a) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+  return r;
+}
+__device__ __forceinline__ f2 f2_unpack(unsigned long long v) {
+  f2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ f2 f2_bcast(float a) { return f2{a, a}; }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)), "l"(f2_pack(c)));
+  return f2_unpack(d);
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+  return f2_unpack(d);
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+  return f2_unpack(d);
+}
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) {
+  unsigned long long d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+  return f2_unpack(d);
+}
+
 __device__ __forceinline__ void acc_add(float* base, int64_t idx, float v, float det) {
   if (det != 0.f)
     atomicAdd(reinterpret_cast<unsigned long long*>(base) + idx, (unsigned long long)__float2ll_rn(v * det));

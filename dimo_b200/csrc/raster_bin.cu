@@ -74,6 +74,24 @@ __device__ __forceinline__ uint32_t warp_match(uint32_t key, int nbits, bool val
   return valid ? peers : 0u;
 }
 
+// The same, but only over the bits in which the valid lanes' keys differ at all (one REDUX.OR finds them): the 32
+// instances of a scatter window come from a few neighbouring splats, so their tile ids share most of their bits.
+__device__ __forceinline__ uint32_t warp_match_sparse(uint32_t key, bool valid) {
+  const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+  if (vmask == 0u) return 0u;
+  const uint32_t ref = __shfl_sync(0xffffffffu, key, __ffs(vmask) - 1);
+  uint32_t diff = __reduce_or_sync(0xffffffffu, valid ? (key ^ ref) : 0u);
+  uint32_t peers = vmask;
+  while (diff) {                                   // warp-uniform
+    const int bit = __ffs(diff) - 1;
+    diff &= diff - 1;
+    const bool p = (key >> bit) & 1u;
+    const uint32_t b = __ballot_sync(0xffffffffu, p);
+    peers &= p ? b : ~b;
+  }
+  return valid ? peers : 0u;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // 1. per-frame depth sort
 // ---------------------------------------------------------------------------------------------------------------
@@ -412,7 +430,7 @@ __global__ void __launch_bounds__(256) tile_scatter_kernel(BinGeom g, int64_t sl
         tile = y * (uint32_t)g.gx + x;
         cell = y * (uint32_t)gw + x;
       }
-      const uint32_t peers = warp_match(tile, tile_bits, act);
+      const uint32_t peers = warp_match_sparse(tile, act);
       const uint32_t slot = act ? (uint32_t)cnt[cell] + __popc(peers & lt) : 0u;
       __syncwarp();
       if (act && (peers & lt) == 0) cnt[cell] += __popc(peers);
@@ -467,6 +485,19 @@ int preprocess_launch(int B, int N, int W, int H, int sh_degree, int sh_coeffs, 
 extern "C" {
 
 int dimo_abi_version(void) { return DIMO_ABI_VERSION; }
+
+/* debugging: how many depth-sort clusters (8 CTAs x 1024 threads) the device can hold at once */
+int dimo_debug_max_sort_clusters(void) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(DS_CL * 64); cfg.blockDim = dim3(DS_THREADS); cfg.dynamicSmemBytes = 0;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = DS_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int n = -1;
+  if (cudaOccupancyMaxActiveClusters(&n, depth_sort_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return -1; }
+  return n;
+}
 
 int dimo_set_deterministic(int on) {
   dimo::g_det_scale = on ? DET_SCALE : 0.f;

@@ -114,42 +114,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 static_assert(CHUNK == 2 * BLEND_THREADS, "stage_gather assigns two records per thread");
 
-// Packed FP32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: one issue slot for two lanes' worth of fp32 math).  The blend
-// loops are issue-bound (smsp__issue_active ~80 %, profiles/r2c_*), and every thread runs the same arithmetic on four
-// pixels, so the FMA-pipe instructions are issued on pixel PAIRS; compares, selects and MUFU stay scalar.
-struct f2 { float x, y; };
-__device__ __forceinline__ unsigned long long f2_pack(f2 a) {
-  unsigned long long r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
-  return r;
-}
-__device__ __forceinline__ f2 f2_unpack(unsigned long long v) {
-  f2 r;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
-  return r;
-}
-__device__ __forceinline__ f2 f2_bcast(float a) { return f2{a, a}; }
-__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
-  unsigned long long d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)), "l"(f2_pack(c)));
-  return f2_unpack(d);
-}
-__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
-  unsigned long long d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)));
-  return f2_unpack(d);
-}
-__device__ __forceinline__ f2 add2(f2 a, f2 b) {
-  unsigned long long d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)));
-  return f2_unpack(d);
-}
-__device__ __forceinline__ f2 sub2(f2 a, f2 b) {
-  unsigned long long d;
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)));
-  return f2_unpack(d);
-}
-
 __device__ __forceinline__ float rcp_approx(float x) {
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));   // one MUFU.RCP (__fdividef expands to a denormal-guarded sequence)

@@ -45,9 +45,12 @@ __global__ void __launch_bounds__(SS_THREADS) ssim_fwd_kernel(int H, int W, cons
                                                               const float* __restrict__ mse_frame_w,
                                                               float* __restrict__ loss_acc, float lw_ssim, float lw_l1,
                                                               float lw_mse) {
-  __shared__ float s1[SS_HH][SS_HW + 1];
-  __shared__ float s2[SS_HH][SS_HW + 1];
-  __shared__ float hz[5][SS_HH][SS_TW + 1];
+  // both images interleaved as (a, b) pairs; the five moments as (mu1, mu2), (E[a^2], E[b^2]) pairs + E[ab]: the
+  // filter taps are issued as packed FFMA2 on the pairs (3 issue slots per tap and output instead of 5-7)
+  __shared__ float2 s12[SS_HH][SS_HW + 1];
+  __shared__ float2 hzm[SS_HH][SS_TW + 1];
+  __shared__ float2 hzq[SS_HH][SS_TW + 1];
+  __shared__ float hzx[SS_HH][SS_TW + 1];
   __shared__ float red[4];
   const int plane = blockIdx.z;
   const int x0 = blockIdx.x * SS_TW, y0 = blockIdx.y * SS_TH;
@@ -62,26 +65,32 @@ __global__ void __launch_bounds__(SS_THREADS) ssim_fwd_kernel(int H, int W, cons
     float a = 0.f, b = 0.f;
     if (gy >= 0 && gy < H && gx >= 0 && gx < W) { a = p1[(int64_t)gy * W + gx]; b = p2[(int64_t)gy * W + gx]; }
     if (clamp01) a = fminf(fmaxf(a, 0.f), 1.f);
-    s1[ly][lx] = a; s2[ly][lx] = b;
+    s12[ly][lx] = make_float2(a, b);
   }
   __syncthreads();
-  // horizontal pass: item = (row, group of 4 columns); consecutive threads take consecutive rows (bank-conflict free)
+  // horizontal pass: item = (row, group of 4 columns); consecutive threads take consecutive rows
   for (int e = tid; e < SS_HH * SS_G; e += SS_THREADS) {
     const int row = e % SS_HH, g = e / SS_HH;
-    float a[14], b[14];
+    f2 ab[14], sq[14];
+    float x[14];
 #pragma unroll
-    for (int k = 0; k < 14; ++k) { a[k] = s1[row][4 * g + k]; b[k] = s2[row][4 * g + k]; }
+    for (int k = 0; k < 14; ++k) {
+      const float2 v = s12[row][4 * g + k];
+      ab[k] = f2{v.x, v.y};
+      sq[k] = mul2(ab[k], ab[k]);
+      x[k] = v.x * v.y;
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float m1 = 0.f, m2 = 0.f, q1 = 0.f, q2 = 0.f, q12 = 0.f;
+      f2 m = f2_bcast(0.f), q = f2_bcast(0.f);
+      float q12 = 0.f;
 #pragma unroll
       for (int k = 0; k < 11; ++k) {
-        const float w = SS_W[k], av = a[j + k], bv = b[j + k];
-        const float wa = w * av, wb = w * bv;
-        m1 += wa; m2 += wb; q1 = fmaf(wa, av, q1); q2 = fmaf(wb, bv, q2); q12 = fmaf(wa, bv, q12);
+        const f2 w = f2_bcast(SS_W[k]);
+        m = fma2(w, ab[j + k], m); q = fma2(w, sq[j + k], q); q12 = fmaf(SS_W[k], x[j + k], q12);
       }
       const int c = 4 * g + j;
-      hz[0][row][c] = m1; hz[1][row][c] = m2; hz[2][row][c] = q1; hz[3][row][c] = q2; hz[4][row][c] = q12;
+      hzm[row][c] = make_float2(m.x, m.y); hzq[row][c] = make_float2(q.x, q.y); hzx[row][c] = q12;
     }
   }
   __syncthreads();
@@ -89,17 +98,24 @@ __global__ void __launch_bounds__(SS_THREADS) ssim_fwd_kernel(int H, int W, cons
   const int col = tid & 31, rg = tid >> 5;
   float v_ssim = 0.f, v_l1 = 0.f, v_mse = 0.f;
   float mom[5][4];
+  {
+    f2 wm[14], wq[14];
+    float wx[14];
 #pragma unroll
-  for (int q = 0; q < 5; ++q) {
-    float win[14];
-#pragma unroll
-    for (int k = 0; k < 14; ++k) win[k] = hz[q][4 * rg + k][col];
+    for (int k = 0; k < 14; ++k) {
+      const float2 a = hzm[4 * rg + k][col], b = hzq[4 * rg + k][col];
+      wm[k] = f2{a.x, a.y}; wq[k] = f2{b.x, b.y}; wx[k] = hzx[4 * rg + k][col];
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float acc = 0.f;
+      f2 m = f2_bcast(0.f), q = f2_bcast(0.f);
+      float q12 = 0.f;
 #pragma unroll
-      for (int k = 0; k < 11; ++k) acc = fmaf(SS_W[k], win[j + k], acc);
-      mom[q][j] = acc;
+      for (int k = 0; k < 11; ++k) {
+        const f2 w = f2_bcast(SS_W[k]);
+        m = fma2(w, wm[j + k], m); q = fma2(w, wq[j + k], q); q12 = fmaf(SS_W[k], wx[j + k], q12);
+      }
+      mom[0][j] = m.x; mom[1][j] = m.y; mom[2][j] = q.x; mom[3][j] = q.y; mom[4][j] = q12;
     }
   }
   const int gx = x0 + col;
@@ -114,7 +130,8 @@ __global__ void __launch_bounds__(SS_THREADS) ssim_fwd_kernel(int H, int W, cons
       const float den1 = mu1s + mu2s + SSIM_C1, den2 = sg1 + sg2 + SSIM_C2;
       const float inv = 1.f / (den1 * den2);
       v_ssim += num1 * num2 * inv;
-      const float a = s1[ly + SS_R][col + SS_R], b = s2[ly + SS_R][col + SS_R];
+      const float2 abc = s12[ly + SS_R][col + SS_R];
+      const float a = abc.x, b = abc.y;
       v_l1 += fabsf(a - b);
       v_mse += (a - b) * (a - b);
       if (dm != nullptr) {
@@ -179,8 +196,10 @@ __global__ void __launch_bounds__(SS_THREADS) ssim_bwd_kernel(int H, int W, cons
                                                               int64_t plane_count, int clamp01, int C,
                                                               const float* __restrict__ mse_frame_w,
                                                               const float* __restrict__ g_dev) {
-  __shared__ float sm[3][SS_HH][SS_HW + 1];
-  __shared__ float hz[3][SS_HH][SS_TW + 1];
+  __shared__ float2 sm01[SS_HH][SS_HW + 1];      // maps 0, 1 as pairs (packed FFMA2 taps), map 2 scalar
+  __shared__ float sm2[SS_HH][SS_HW + 1];
+  __shared__ float2 hz01[SS_HH][SS_TW + 1];
+  __shared__ float hz2[SS_HH][SS_TW + 1];
   const int plane = blockIdx.z;
   const int x0 = blockIdx.x * SS_TW, y0 = blockIdx.y * SS_TH;
   const int tid = threadIdx.x;
@@ -197,38 +216,44 @@ __global__ void __launch_bounds__(SS_THREADS) ssim_bwd_kernel(int H, int W, cons
       const int sy = y0 + yy - SS_R, sx = x0 + xx - SS_R;
       const bool ok = sy >= 0 && sy < H && sx >= 0 && sx < W;
       const int64_t o = plane * hw + (int64_t)sy * W + sx;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) sm[c][yy][xx] = ok ? dm[c * plane_count * hw + o] : 0.f;
+      sm01[yy][xx] = ok ? make_float2(dm[o], dm[plane_count * hw + o]) : make_float2(0.f, 0.f);
+      sm2[yy][xx] = ok ? dm[2 * plane_count * hw + o] : 0.f;
     }
     __syncthreads();
     for (int e = tid; e < SS_HH * SS_G; e += SS_THREADS) {
       const int row = e % SS_HH, g = e / SS_HH;
+      f2 w01[14];
+      float w2[14];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        float win[14];
+      for (int k = 0; k < 14; ++k) {
+        const float2 v = sm01[row][4 * g + k];
+        w01[k] = f2{v.x, v.y}; w2[k] = sm2[row][4 * g + k];
+      }
 #pragma unroll
-        for (int k = 0; k < 14; ++k) win[k] = sm[c][row][4 * g + k];
+      for (int j = 0; j < 4; ++j) {
+        f2 acc = f2_bcast(0.f);
+        float acc2 = 0.f;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float acc = 0.f;
-#pragma unroll
-          for (int k = 0; k < 11; ++k) acc = fmaf(SS_W[k], win[j + k], acc);
-          hz[c][row][4 * g + j] = acc;
-        }
+        for (int k = 0; k < 11; ++k) { acc = fma2(f2_bcast(SS_W[k]), w01[j + k], acc); acc2 = fmaf(SS_W[k], w2[j + k], acc2); }
+        hz01[row][4 * g + j] = make_float2(acc.x, acc.y); hz2[row][4 * g + j] = acc2;
       }
     }
     __syncthreads();
+    {
+      f2 w01[14];
+      float w2[14];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      float win[14];
-#pragma unroll
-      for (int k = 0; k < 14; ++k) win[k] = hz[c][4 * rg + k][col];
+      for (int k = 0; k < 14; ++k) {
+        const float2 v = hz01[4 * rg + k][col];
+        w01[k] = f2{v.x, v.y}; w2[k] = hz2[4 * rg + k][col];
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float acc = 0.f;
+        f2 acc = f2_bcast(0.f);
+        float acc2 = 0.f;
 #pragma unroll
-        for (int k = 0; k < 11; ++k) acc = fmaf(SS_W[k], win[j + k], acc);
-        conv[c][j] = acc;
+        for (int k = 0; k < 11; ++k) { acc = fma2(f2_bcast(SS_W[k]), w01[j + k], acc); acc2 = fmaf(SS_W[k], w2[j + k], acc2); }
+        conv[0][j] = acc.x; conv[1][j] = acc.y; conv[2][j] = acc2;
       }
     }
   }

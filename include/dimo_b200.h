@@ -256,6 +256,7 @@ int dimo_timenet_bwd(int G, int M, int L, const float* const* W_host, void* work
  * dimo_fixed_to_float converts such a buffer to fp32 (dst = or += src * 2^-28).  The scalar loss sums keep fp32
  * atomics (they feed no gradient).
  * ------------------------------------------------------------------------------------------- */
+int dimo_debug_max_sort_clusters(void);   /* debugging: co-resident depth-sort clusters */
 int dimo_set_deterministic(int on);
 int dimo_get_deterministic(void);
 int dimo_fixed_to_float(int64_t n, const void* src_i64, float* dst, int accumulate, void* stream);

@@ -8,6 +8,7 @@ import gpu_parity as gp
 from dimo_b200 import _lib, raster as draster
 from dimo_b200.camera import orbit_minicam
 
+print('max co-resident depth-sort clusters:', _lib.lib().dimo_debug_max_sort_clusters())
 N, W, H = 100000, 512, 512
 xyz, scales, rot, op, shs = [t.cuda() for t in gp.scene_inputs(N)]
 for B in (1, 2, 4, 8, 16):
