@@ -96,19 +96,22 @@ __device__ __forceinline__ uint32_t warp_match_sparse(uint32_t key, bool valid) 
 // 1. per-frame depth sort
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int DS_CL = 8;              // CTAs per cluster = per frame
-constexpr int DS_THREADS = 1024;
-constexpr int DS_WARPS = DS_THREADS / 32;
 constexpr int DS_BINS = 256;
 constexpr int DS_BATCH = 8;           // keys in flight per lane (independent loads)
 
 // keys0 [B*N] (input, depth bits); kB, kC, vB, vC [B*N] ping-pong buffers.  After the four passes vC holds, per
 // frame, the indices b*N + i in ascending (depth, i) order.
-__global__ void __cluster_dims__(DS_CL, 1, 1) __launch_bounds__(DS_THREADS)
+// DS_THREADS = 1024: one CTA per SM, at most 15 clusters in flight on a B200 (measured, dimo_debug_max_sort_clusters);
+// 512: two CTAs per SM -- chosen when more frames than that have to be sorted at once, so that no frame waits for a
+// second wave.
+template <int DS_THREADS>
+__global__ void __cluster_dims__(DS_CL, 1, 1) __launch_bounds__(DS_THREADS, DS_THREADS == 1024 ? 1 : 2)
 depth_sort_kernel(int N, const uint32_t* __restrict__ keys0, uint32_t* __restrict__ kB, uint32_t* __restrict__ kC,
                   uint32_t* __restrict__ vB, uint32_t* __restrict__ vC) {
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = (int)cluster.block_rank();
   const int b = blockIdx.x / DS_CL;
+  constexpr int DS_WARPS = DS_THREADS / 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   __shared__ uint32_t wc[DS_WARPS][DS_BINS];     // per-warp digit counts, then per-warp cursors
   __shared__ uint32_t cta_tot[DS_BINS];          // this CTA's digit counts (read by the whole cluster)
@@ -430,7 +433,7 @@ __global__ void __launch_bounds__(256) tile_scatter_kernel(BinGeom g, int64_t sl
         tile = y * (uint32_t)g.gx + x;
         cell = y * (uint32_t)gw + x;
       }
-      const uint32_t peers = warp_match_sparse(tile, act);
+      const uint32_t peers = warp_match(tile, tile_bits, act);    // (a loop over only the differing bits was slower: r2m)
       const uint32_t slot = act ? (uint32_t)cnt[cell] + __popc(peers & lt) : 0u;
       __syncwarp();
       if (act && (peers & lt) == 0) cnt[cell] += __popc(peers);
@@ -489,13 +492,13 @@ int dimo_abi_version(void) { return DIMO_ABI_VERSION; }
 /* debugging: how many depth-sort clusters (8 CTAs x 1024 threads) the device can hold at once */
 int dimo_debug_max_sort_clusters(void) {
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(DS_CL * 64); cfg.blockDim = dim3(DS_THREADS); cfg.dynamicSmemBytes = 0;
+  cfg.gridDim = dim3(DS_CL * 64); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = 0;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = DS_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   int n = -1;
-  if (cudaOccupancyMaxActiveClusters(&n, depth_sort_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return -1; }
+  if (cudaOccupancyMaxActiveClusters(&n, depth_sort_kernel<1024>, &cfg) != cudaSuccess) { cudaGetLastError(); return -1; }
   return n;
 }
 
@@ -572,7 +575,11 @@ int dimo_raster_preprocess(int B, int N, int W, int H, int sh_degree, int sh_coe
                              tiles_touched, rects, sort_scratch, reinterpret_cast<unsigned long long*>(total_count),
                              st);
   if (rc) return rc;
-  depth_sort_kernel<<<B * DS_CL, DS_THREADS, 0, st>>>(N, sort_scratch, sort_scratch + BN, sort_scratch + 2 * BN, perm,
+  if (B <= 15)
+    depth_sort_kernel<1024><<<B * DS_CL, 1024, 0, st>>>(N, sort_scratch, sort_scratch + BN, sort_scratch + 2 * BN, perm,
+                                                       perm + BN);
+  else
+    depth_sort_kernel<512><<<B * DS_CL, 512, 0, st>>>(N, sort_scratch, sort_scratch + BN, sort_scratch + 2 * BN, perm,
                                                      perm + BN);
   DIMO_CHECK_LAUNCH();
   if (R_host) {

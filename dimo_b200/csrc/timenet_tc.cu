@@ -298,10 +298,17 @@ __global__ void __launch_bounds__(256) tn_heads_bwd_kernel(int R, int Rp, const 
     const int c = tid;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     const int rows = min(128, R - rb * 128);
-    for (int rl = 0; rl < rows; ++rl) {
-      const float h = H[(int64_t)(rb * 128 + rl) * 256 + c];
+    for (int r0 = 0; r0 < rows; r0 += 16) {           // 16 independent loads in flight
+      float h[16];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j] = fmaf(sg[rl][j], h, acc[j]);
+      for (int u = 0; u < 16; ++u) h[u] = r0 + u < rows ? H[(int64_t)(rb * 128 + r0 + u) * 256 + c] : 0.f;
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        if (r0 + u < rows) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[j] = fmaf(sg[r0 + u][j], h[u], acc[j]);
+        }
+      }
     }
     for (int j = 0; j < No; ++j) acc_add(dW, (int64_t)j * 256 + c, acc[j], det);
     if (tid < No) {
