@@ -414,15 +414,49 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tn_gemm_kernel(const __grid_con
     }
   } else {
     // ===== epilogue =====
-    tn_mbar_wait(&done_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int lg = warp & 3;                       // TMEM lane group = tile rows [32 lg, 32 lg + 32)
     const int rl = lg * 32 + lane;
     const int gr = rb * TN_BM + rl;
     const bool valid = gr < p.R;
-    const int rt = rb * 4 + lg;                    // these 32 rows are one r tile of the transposed layout
     const uint32_t row_off = tn_off(rl, 0);        // (row, chunk q) -> row_off + 128 q
     const uint32_t t_lane = (uint32_t)((lane >> 2) * 128 + (lane & 3) * 4);
+    // everything that does not depend on the accumulator is fetched while the MMAs run: bias, ReLU-mask bits
+    float bias_r[2][32];
+    uint32_t mbits[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int n0 = cb * TG_NB + (warp >> 2) * 64 + c * 32;
+      if (p.bias != nullptr) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 bb = b4[q];
+          bias_r[c][4 * q] = bb.x; bias_r[c][4 * q + 1] = bb.y; bias_r[c][4 * q + 2] = bb.z; bias_r[c][4 * q + 3] = bb.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) bias_r[c][j] = 0.f;
+      }
+      if (p.mask != nullptr) {
+        const uint8_t* mt = p.mask + ((size_t)rb * p.mask_nkt + p.mask_kt0 + (n0 >> 5)) * TN_STAGE_A + row_off;
+        uint32_t bits = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 mh = *reinterpret_cast<const float4*>(mt + 128 * q);
+          const float4 ml = *reinterpret_cast<const float4*>(mt + TN_PLANE_A + 128 * q);
+          bits |= (uint32_t)(mh.x > 0.f || ml.x > 0.f) << (4 * q);
+          bits |= (uint32_t)(mh.y > 0.f || ml.y > 0.f) << (4 * q + 1);
+          bits |= (uint32_t)(mh.z > 0.f || ml.z > 0.f) << (4 * q + 2);
+          bits |= (uint32_t)(mh.w > 0.f || ml.w > 0.f) << (4 * q + 3);
+        }
+        mbits[c] = bits;
+      }
+    }
+    tn_mbar_wait(&done_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // transposed tiles are staged in the (now idle) operand stages as the exact 16 KB images T[rt = 4 rb + lg][plane]
+    // [fb] they occupy in global memory and leave with one bulk store each (below)
+    uint8_t* stageT = smem + (size_t)lg * 2 * TN_FB_BYTES;
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
       const int lc0 = (warp >> 2) * 64 + c * 32;   // column within the CTA's 128
@@ -430,39 +464,14 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tn_gemm_kernel(const __grid_con
       uint32_t v[32];
       tn_ld32(tmem_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)lc0, v);
       float y[32];
-      if (p.bias != nullptr) {
-        const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 bb = b4[q];
-          y[4 * q] = __uint_as_float(v[4 * q]) + bb.x; y[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + bb.y;
-          y[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + bb.z; y[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + bb.w;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(v[j]);
+      for (int j = 0; j < 32; ++j) {
+        float t = __uint_as_float(v[j]) + (c == 0 ? bias_r[0][j] : bias_r[1][j]);
+        if (p.relu) t = fmaxf(t, 0.f);
+        const bool keep = valid && (((c == 0 ? mbits[0] : mbits[1]) >> j) & 1u);
+        y[j] = keep ? t : 0.f;
       }
-      if (p.relu) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
-      }
-      if (!valid) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) y[j] = 0.f;
-      }
-      const int kt_out = n0 >> 5;                  // this chunk is k tile kt_out of the result / of the mask source
-      if (p.mask != nullptr) {
-        const uint8_t* mt = p.mask + ((size_t)rb * p.mask_nkt + p.mask_kt0 + kt_out) * TN_STAGE_A + row_off;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 mh = *reinterpret_cast<const float4*>(mt + 128 * q);
-          const float4 ml = *reinterpret_cast<const float4*>(mt + TN_PLANE_A + 128 * q);
-          if (!(mh.x > 0.f || ml.x > 0.f)) y[4 * q + 0] = 0.f;
-          if (!(mh.y > 0.f || ml.y > 0.f)) y[4 * q + 1] = 0.f;
-          if (!(mh.z > 0.f || ml.z > 0.f)) y[4 * q + 2] = 0.f;
-          if (!(mh.w > 0.f || ml.w > 0.f)) y[4 * q + 3] = 0.f;
-        }
-      }
+      const int kt_out = n0 >> 5;                  // this chunk is k tile kt_out of the result
       uint32_t hi[32], lo[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) { hi[j] = tn_tf32(y[j]); lo[j] = tn_tf32(y[j] - __uint_as_float(hi[j])); }
@@ -475,14 +484,12 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tn_gemm_kernel(const __grid_con
         }
       }
       if (p.outT != nullptr) {
-        // feature f = t_f0 + n0 + j with (t_f0 + n0) a multiple of 32: one feature block, consecutive tile rows
-        const int f0 = p.t_f0 + n0, fb = f0 >> 7, fl0 = f0 & 127;
-        uint8_t* t = p.outT + (((size_t)rt * 2) * p.t_nfb + fb) * TN_FB_BYTES + (size_t)(fl0 >> 3) * 1024 + t_lane;
-        const size_t lo_off = (size_t)p.t_nfb * TN_FB_BYTES;
+        // feature f = t_f0 + n0 + j: the CTA's 128 columns are ONE feature block (t_f0 is a multiple of 128)
+        uint8_t* t = stageT + (size_t)(lc0 >> 3) * 1024 + t_lane;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           *reinterpret_cast<uint32_t*>(t + (j >> 3) * 1024 + (j & 7) * 16) = hi[j];
-          *reinterpret_cast<uint32_t*>(t + lo_off + (j >> 3) * 1024 + (j & 7) * 16) = lo[j];
+          *reinterpret_cast<uint32_t*>(t + TN_FB_BYTES + (j >> 3) * 1024 + (j & 7) * 16) = lo[j];
         }
       }
       if (p.plain != nullptr && valid) {
@@ -492,6 +499,25 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tn_gemm_kernel(const __grid_con
           if (n0 + j < p.plain_cols) row[j] = y[j] + (p.plain_acc ? row[j] : 0.f);
       }
     }
+    if (p.outT != nullptr) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged images -> bulk-copy engine
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (p.outT != nullptr && tid == 0) {
+    // eight bulk stores: (4 r tiles) x (hi, lo plane), 16 KB each, contiguous on both sides
+    const int fb = (p.t_f0 + cb * TG_NB) >> 7;
+#pragma unroll
+    for (int g4 = 0; g4 < 4; ++g4)
+#pragma unroll
+      for (int pl = 0; pl < 2; ++pl) {
+        const uint8_t* src = smem + (size_t)(g4 * 2 + pl) * TN_FB_BYTES;
+        uint8_t* dst = p.outT + ((((size_t)(rb * 4 + g4)) * 2 + pl) * p.t_nfb + fb) * TN_FB_BYTES;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(tn_smem_u32(src)),
+                     "r"((uint32_t)TN_FB_BYTES)
+                     : "memory");
+      }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // shared memory may be released after the reads
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
