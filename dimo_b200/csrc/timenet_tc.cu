@@ -32,7 +32,12 @@ constexpr int TN_STAGE_B = 2 * TN_MAXN * TN_KT * 4;    // 64 KB
 constexpr int TN_STAGE = TN_STAGE_A + TN_STAGE_B;      // 96 KB
 constexpr int TN_SMEM = 2 * TN_STAGE + 1024;
 constexpr int TN_THREADS = 192;            // warps 0-3 epilogue, 4 producer, 5 MMA issuer
-constexpr int TN_FB_BYTES = 128 * TN_KT * 4;           // 16 KB: one 128-feature block of a transposed tile plane
+// Transposed tiles: same canonical K-major layout but with the k chunks 144 B apart instead of 128 (16 B of padding per
+// core matrix).  Their writers are warps whose 32 lanes hold 32 consecutive k (= row) indices of ONE tile row: with a
+// 128 B chunk stride the eight chunks of a warp store fall on the same four shared-memory banks (8-way conflict);
+// 144 B = 36 words shifts every chunk by four banks -> conflict-free.  The tensor core does not care (LBO is free).
+constexpr int TT_LBO = 144, TT_SBO = 8 * TT_LBO;       // 1152
+constexpr int TN_FB_BYTES = 16 * TT_SBO;               // 18 KB: one 128-feature block of a transposed tile plane
 
 __device__ __forceinline__ uint32_t tn_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t tn_tf32(float x) {
@@ -72,14 +77,16 @@ __device__ __forceinline__ void tn_bulk_g2s(void* dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(tn_smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ uint64_t tn_desc(uint32_t saddr) {     // LBO 128 B, SBO 1024 B, no swizzle, version 1
+__device__ __forceinline__ uint64_t tn_desc_ls(uint32_t saddr, uint32_t lbo, uint32_t sbo) {   // no swizzle, version 1
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((128u >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((1024u >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
   return d;
 }
+__device__ __forceinline__ uint64_t tn_desc(uint32_t saddr) { return tn_desc_ls(saddr, 128u, 1024u); }
+__device__ __forceinline__ uint64_t tn_desc_t(uint32_t saddr) { return tn_desc_ls(saddr, TT_LBO, TT_SBO); }
 __device__ __forceinline__ uint32_t tn_idesc(int M, int N) {      // kind::tf32, FP32 accumulate, both operands K-major
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
@@ -109,6 +116,9 @@ __device__ __forceinline__ void tn_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __host__ __forceinline__ uint32_t tn_off_t(int row, int q) {   // the same inside a transposed tile plane
+  return (uint32_t)((row >> 3) * TT_SBO + q * TT_LBO + ((row & 7) << 4));
+}
 // byte offset of (row, 16-byte chunk q) inside an operand tile plane
 __device__ __host__ __forceinline__ uint32_t tn_off(int row, int q) { return (uint32_t)((((row >> 3) * 8 + q) << 7) + ((row & 7) << 4)); }
 
@@ -195,7 +205,7 @@ __global__ void __launch_bounds__(256) tn_tiles_kernel(const TilesArgs p) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int f = p.t_f0 + qq * 4 + e, fb = f >> 7, fl = f & 127;
-      uint8_t* t = p.outT + (((size_t)rt * 2) * p.t_nfb + fb) * TN_FB_BYTES + tn_off(fl, rq) + re * 4;
+      uint8_t* t = p.outT + (((size_t)rt * 2) * p.t_nfb + fb) * TN_FB_BYTES + tn_off_t(fl, rq) + re * 4;
       *reinterpret_cast<uint32_t*>(t) = h[e];
       *reinterpret_cast<uint32_t*>(t + (size_t)p.t_nfb * TN_FB_BYTES) = l[e];
     }
@@ -288,7 +298,7 @@ __global__ void __launch_bounds__(256) tn_heads_bwd_kernel(int R, int Rp, const 
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int f = qq * 4 + e, fb = f >> 7, fl = f & 127;
-      uint8_t* tt = outT + (((size_t)rt * 2) * 2 + fb) * TN_FB_BYTES + tn_off(fl, rq) + re * 4;
+      uint8_t* tt = outT + (((size_t)rt * 2) * 2 + fb) * TN_FB_BYTES + tn_off_t(fl, rq) + re * 4;
       *reinterpret_cast<uint32_t*>(tt) = hh[e];
       *reinterpret_cast<uint32_t*>(tt + (size_t)2 * TN_FB_BYTES) = ll[e];
     }
@@ -419,7 +429,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tn_gemm_kernel(const __grid_con
     const int gr = rb * TN_BM + rl;
     const bool valid = gr < p.R;
     const uint32_t row_off = tn_off(rl, 0);        // (row, chunk q) -> row_off + 128 q
-    const uint32_t t_lane = (uint32_t)((lane >> 2) * 128 + (lane & 3) * 4);
+    const uint32_t t_lane = (uint32_t)((lane >> 2) * TT_LBO + (lane & 3) * 4);
     // everything that does not depend on the accumulator is fetched while the MMAs run: bias, ReLU-mask bits
     float bias_r[2][32];
     uint32_t mbits[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
@@ -485,11 +495,11 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tn_gemm_kernel(const __grid_con
       }
       if (p.outT != nullptr) {
         // feature f = t_f0 + n0 + j: the CTA's 128 columns are ONE feature block (t_f0 is a multiple of 128)
-        uint8_t* t = stageT + (size_t)(lc0 >> 3) * 1024 + t_lane;
+        uint8_t* t = stageT + (size_t)(lc0 >> 3) * TT_SBO + t_lane;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          *reinterpret_cast<uint32_t*>(t + (j >> 3) * 1024 + (j & 7) * 16) = hi[j];
-          *reinterpret_cast<uint32_t*>(t + TN_FB_BYTES + (j >> 3) * 1024 + (j & 7) * 16) = lo[j];
+          *reinterpret_cast<uint32_t*>(t + (j >> 3) * TT_SBO + (j & 7) * 16) = hi[j];
+          *reinterpret_cast<uint32_t*>(t + TN_FB_BYTES + (j >> 3) * TT_SBO + (j & 7) * 16) = lo[j];
         }
       }
       if (p.plain != nullptr && valid) {
@@ -538,6 +548,8 @@ struct TnWJob {
   float* db;                                       // NULL unless this job also owns the bias gradient of its n block
 };
 constexpr int TN_MAX_WJOBS = 32;
+constexpr int TW_STAGE = 2 * TN_FB_BYTES + 4 * TN_FB_BYTES;      // A (hi, lo) + B (hi, lo) x up to 2 feature blocks = 108 KB
+constexpr int TW_SMEM = 2 * TW_STAGE + 1024;
 struct TnWTable { int n, splits, per, nrt; float det; TnWJob job[TN_MAX_WJOBS]; };    // CTA = (job, row split)
 
 __global__ void __launch_bounds__(TN_THREADS, 1) tn_wgrad_kernel(const __grid_constant__ TnWTable tab) {
@@ -550,7 +562,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) tn_wgrad_kernel(const __grid_co
   const int split = blockIdx.x % tab.splits;
   const int rt0 = split * tab.per, rt1 = min(tab.nrt, rt0 + tab.per);
   const int N = 128 * p.b_use;
-  const uint32_t planeB = (uint32_t)N * 128u;
+  const uint32_t planeB = (uint32_t)p.b_use * TN_FB_BYTES;    // transposed tiles: 18 KB per 128 features and plane
   const int nst = max(0, rt1 - rt0);
 
   if (warp == 5) {
@@ -575,12 +587,12 @@ __global__ void __launch_bounds__(TN_THREADS, 1) tn_wgrad_kernel(const __grid_co
       for (int it = 0; it < nst; ++it) {
         const int st = it & 1;
         if (it >= 2) tn_mbar_wait(&empty_bar[st], (uint32_t)(((it >> 1) - 1) & 1));
-        uint8_t* sa = smem + st * TN_STAGE;
-        uint8_t* sb = sa + TN_STAGE_A;
+        uint8_t* sa = smem + st * TW_STAGE;
+        uint8_t* sb = sa + 2 * TN_FB_BYTES;
         const size_t rt = (size_t)(rt0 + it);
-        tn_mbar_expect_tx(&full_bar[st], TN_STAGE_A + 2 * planeB);
+        tn_mbar_expect_tx(&full_bar[st], 2 * TN_FB_BYTES + 2 * planeB);
         tn_bulk_g2s(sa, p.aT + ((rt * 2 + 0) * p.a_nfb + p.a_fb) * TN_FB_BYTES, TN_FB_BYTES, &full_bar[st]);
-        tn_bulk_g2s(sa + TN_PLANE_A, p.aT + ((rt * 2 + 1) * p.a_nfb + p.a_fb) * TN_FB_BYTES, TN_FB_BYTES, &full_bar[st]);
+        tn_bulk_g2s(sa + TN_FB_BYTES, p.aT + ((rt * 2 + 1) * p.a_nfb + p.a_fb) * TN_FB_BYTES, TN_FB_BYTES, &full_bar[st]);
         tn_bulk_g2s(sb, p.bT + ((rt * 2 + 0) * p.b_nfb + p.b_fb0) * TN_FB_BYTES, planeB, &full_bar[st]);
         tn_bulk_g2s(sb + planeB, p.bT + ((rt * 2 + 1) * p.b_nfb + p.b_fb0) * TN_FB_BYTES, planeB, &full_bar[st]);
       }
@@ -592,12 +604,12 @@ __global__ void __launch_bounds__(TN_THREADS, 1) tn_wgrad_kernel(const __grid_co
         const int st = it & 1;
         tn_mbar_wait(&full_bar[st], (uint32_t)((it >> 1) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = tn_smem_u32(smem + st * TN_STAGE), sb = sa + TN_STAGE_A;
+        const uint32_t sa = tn_smem_u32(smem + st * TW_STAGE), sb = sa + 2 * TN_FB_BYTES;
 #pragma unroll
         for (int ks = 0; ks < TN_KT / 8; ++ks) {
-          const uint32_t koff = (uint32_t)ks * 256u;
-          const uint64_t dah = tn_desc(sa + koff), dal = tn_desc(sa + TN_PLANE_A + koff);
-          const uint64_t dbh = tn_desc(sb + koff), dbl = tn_desc(sb + planeB + koff);
+          const uint32_t koff = (uint32_t)ks * 2u * TT_LBO;
+          const uint64_t dah = tn_desc_t(sa + koff), dal = tn_desc_t(sa + TN_FB_BYTES + koff);
+          const uint64_t dbh = tn_desc_t(sb + koff), dbl = tn_desc_t(sb + planeB + koff);
           tn_mma(tmem_d, dah, dbh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
           tn_mma(tmem_d, dah, dbl, idesc, 1u);
           tn_mma(tmem_d, dal, dbh, idesc, 1u);
@@ -614,11 +626,11 @@ __global__ void __launch_bounds__(TN_THREADS, 1) tn_wgrad_kernel(const __grid_co
       const int st = it & 1;
       tn_mbar_wait(&full_bar[st], (uint32_t)((it >> 1) & 1));
       if (p.db != nullptr) {
-        const uint8_t* sa = smem + st * TN_STAGE;
+        const uint8_t* sa = smem + st * TW_STAGE;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const float4 h = *reinterpret_cast<const float4*>(sa + tn_off(nl, q));
-          const float4 l = *reinterpret_cast<const float4*>(sa + TN_PLANE_A + tn_off(nl, q));
+          const float4 h = *reinterpret_cast<const float4*>(sa + tn_off_t(nl, q));
+          const float4 l = *reinterpret_cast<const float4*>(sa + TN_FB_BYTES + tn_off_t(nl, q));
           dbacc += (h.x + l.x) + (h.y + l.y) + (h.z + l.z) + (h.w + l.w);
         }
       }
@@ -720,7 +732,7 @@ int tn_set_attrs() {
   static bool done = false;
   if (!done) {
     DIMO_CHECK_CUDA(cudaFuncSetAttribute(tn_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
-    DIMO_CHECK_CUDA(cudaFuncSetAttribute(tn_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM));
+    DIMO_CHECK_CUDA(cudaFuncSetAttribute(tn_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM));
     done = true;
   }
   return 0;
@@ -948,7 +960,7 @@ extern "C" int dimo_timenet_bwd(int G, int M, int L, const float* const* W_host,
       }
     }
     tab.n = n;
-    tn_wgrad_kernel<<<n * tab.splits, TN_THREADS, TN_SMEM, st>>>(tab);
+    tn_wgrad_kernel<<<n * tab.splits, TN_THREADS, TW_SMEM, st>>>(tab);
     DIMO_CHECK_LAUNCH();
   }
   return 0;
