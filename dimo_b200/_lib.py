@@ -47,6 +47,7 @@ _SIGS = {
     "dimo_fixed_to_float": (c_int, [c_i64, c_vp, c_vp, c_int, c_vp]),
     "dimo_timenet_workspace_bytes": (c_sz, [c_int] * 3),
     "dimo_timenet_layout": (c_int, [c_int] * 3 + [c_vp]),
+    "dimo_timenet_debug_stamps": (c_int, [c_vp]),
     "dimo_timenet_fwd": (c_int, [c_int] * 3 + [c_vp] * 6 + [c_sz] + [c_vp] * 3),
     "dimo_timenet_bwd": (c_int, [c_int] * 3 + [c_vp] * 2 + [c_sz] + [c_vp] * 7),
     "dimo_timenet_embed_fwd": (c_int, [c_int] * 3 + [c_vp] * 4 + [c_i64, c_vp]),

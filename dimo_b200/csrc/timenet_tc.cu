@@ -341,7 +341,16 @@ struct TnGemmArgs {
   uint8_t* out; int out_nkt, out_kt0;              // split tiles of the result (next GEMM's A), or NULL
   uint8_t* outT; int t_nfb, t_f0;                  // transposed split tiles (weight-gradient operand), or NULL
   float* plain; int64_t ldp; int plain_cols, plain_acc;   // fp32 row-major copy of the first plain_cols columns, or NULL
+  unsigned long long* dbg;                         // bring-up: [cta][8] %globaltimer stamps (dimo_timenet_debug_stamps), or NULL
 };
+
+__device__ __forceinline__ void tn_stamp(unsigned long long* dbg, int slot) {
+  if (dbg != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    dbg[(blockIdx.y * gridDim.x + blockIdx.x) * 8 + slot] = t;
+  }
+}
 
 // One CTA = 128 rows x 128 output columns (grid.y = N / 128).  10 warps: 0-7 epilogue (warp w: TMEM lanes 32 (w & 3),
 // columns 64 (w >> 2) + [0, 64)), 8 producer, 9 MMA issuer; three 64 KB stages.
@@ -359,6 +368,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tn_gemm_kernel(const __grid_con
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tn_smem_raw) + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rb = blockIdx.x, cb = blockIdx.y;
+  if (tid == 0) tn_stamp(p.dbg, 0);
   const uint32_t planeB_full = (uint32_t)p.N * 128u;          // bytes of one plane of a packed weight tile (all N rows)
   constexpr uint32_t planeB = TG_NB * 128u;                   // this CTA's 128 rows of it
 
@@ -378,6 +388,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tn_gemm_kernel(const __grid_con
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = tmem_slot;
+  if (tid == 0) tn_stamp(p.dbg, 1);
 
   if (warp == 8) {
     // ===== producer: three bulk copies per stage (A split tile, B hi rows, B lo rows) =====
@@ -407,6 +418,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tn_gemm_kernel(const __grid_con
       for (int it = 0; it < total; ++it) {
         const int st = it % TG_STAGES, round = it / TG_STAGES;
         tn_mbar_wait(&full_bar[st], (uint32_t)(round & 1));
+        if (it == 0) tn_stamp(p.dbg, 2);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sa = tn_smem_u32(smem + st * TG_STAGE), sb = sa + TN_STAGE_A;
 #pragma unroll
@@ -421,6 +433,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tn_gemm_kernel(const __grid_con
         tn_commit(&empty_bar[st]);
       }
       tn_commit(&done_bar);
+      tn_stamp(p.dbg, 3);
     }
   } else {
     // ===== epilogue =====
@@ -462,7 +475,9 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tn_gemm_kernel(const __grid_con
         mbits[c] = bits;
       }
     }
+    if (tid == 0) tn_stamp(p.dbg, 4);
     tn_mbar_wait(&done_bar, 0);
+    if (tid == 0) tn_stamp(p.dbg, 5);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     // transposed tiles are staged in the (now idle) operand stages as the exact 16 KB images T[rt = 4 rb + lg][plane]
     // [fb] they occupy in global memory and leave with one bulk store each (below)
@@ -510,6 +525,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tn_gemm_kernel(const __grid_con
       }
     }
     if (p.outT != nullptr) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged images -> bulk-copy engine
+    if (tid == 0) tn_stamp(p.dbg, 6);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -531,6 +547,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tn_gemm_kernel(const __grid_con
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (tid == 0) tn_stamp(p.dbg, 7);
   if (warp == 9) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)TG_NB) : "memory");
   }
@@ -751,6 +768,15 @@ extern "C" int dimo_timenet_embed_fwd(int G, int rows_per_group, int L, const fl
 extern "C" int dimo_timenet_embed_bwd(int G, int rows_per_group, int L, const float* h0, const float* dh0, int64_t ldh,
                                       float* dpts, float* dlatents, void* stream);
 
+static unsigned long long* g_tn_dbg = nullptr;
+static int g_tn_dbg_launch = 0;
+/* bring-up: device buffer of 32 x 64 x 8 u64; the following tn_gemm launches stamp [launch % 32][cta][8] with %globaltimer (NULL: off) */
+extern "C" int dimo_timenet_debug_stamps(void* dev_buf) {
+  g_tn_dbg = reinterpret_cast<unsigned long long*>(dev_buf);
+  g_tn_dbg_launch = 0;
+  return 0;
+}
+
 extern "C" size_t dimo_timenet_workspace_bytes(int G, int M, int L) {
   if (G <= 0 || M <= 0) return 256;
   return tn_layout(G * M, L).total;
@@ -831,6 +857,7 @@ extern "C" int dimo_timenet_fwd(int G, int M, int L, const float* pts, const flo
   }
   // ---- the ten 256-wide layers ----
   auto gemm = [&](TnGemmArgs& g) {
+    g.dbg = g_tn_dbg != nullptr ? g_tn_dbg + (size_t)(g_tn_dbg_launch++ % 32) * 64 * 8 : nullptr;
     tn_gemm_kernel<<<dim3(o.nrb, g.N / TG_NB), TG_THREADS, TG_SMEM, st>>>(g);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
   };
@@ -888,6 +915,7 @@ extern "C" int dimo_timenet_bwd(int G, int M, int L, const float* const* W_host,
   DIMO_CHECK_LAUNCH();
   int rc = 0;
   auto gemm = [&](TnGemmArgs& g) {
+    g.dbg = g_tn_dbg != nullptr ? g_tn_dbg + (size_t)(g_tn_dbg_launch++ % 32) * 64 * 8 : nullptr;
     tn_gemm_kernel<<<dim3(o.nrb, g.N / TG_NB), TG_THREADS, TG_SMEM, st>>>(g);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
   };
