@@ -215,8 +215,15 @@ __global__ void __launch_bounds__(256) tn_tiles_kernel(const TilesArgs p) {
 // ---------------------------------------------------------------------------------------------------------------
 // the 3- and 4-wide output layers (pts_layers.2, rot_layers.2) in FP32 SIMT: one launch per direction
 // ---------------------------------------------------------------------------------------------------------------
-// forward: one warp per row; dxyz[r, :] = hp[r, :] W9^T + b9, dquat[r, :] = hr[r, :] W11^T + b11
-__global__ void __launch_bounds__(256) tn_heads_fwd_kernel(int R, const float* __restrict__ hp, const float* __restrict__ hr,
+// value (hi + lo) of 4 consecutive columns 4 qq .. 4 qq + 3 of row r of an activation stored as split tiles A[rb][kt]
+__device__ __forceinline__ float4 tn_tile_load4(const uint8_t* __restrict__ tiles, int nkt, int r, int qq) {
+  const uint8_t* t = tiles + ((size_t)(r >> 7) * nkt + (qq >> 3)) * TN_STAGE_A + tn_off(r & 127, qq & 7);
+  const float4 h = *reinterpret_cast<const float4*>(t), l = *reinterpret_cast<const float4*>(t + TN_PLANE_A);
+  return make_float4(h.x + l.x, h.y + l.y, h.z + l.z, h.w + l.w);
+}
+
+// forward: one warp per row; dxyz[r, :] = hp[r, :] W9^T + b9, dquat[r, :] = hr[r, :] W11^T + b11 (hp / hr: split tiles)
+__global__ void __launch_bounds__(256) tn_heads_fwd_kernel(int R, const uint8_t* __restrict__ hp, const uint8_t* __restrict__ hr,
                                                            const float* __restrict__ W9, const float* __restrict__ b9,
                                                            const float* __restrict__ W11, const float* __restrict__ b11,
                                                            float* __restrict__ dxyz, float* __restrict__ dquat) {
@@ -230,8 +237,8 @@ __global__ void __launch_bounds__(256) tn_heads_fwd_kernel(int R, const float* _
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     const int c = half * 128 + lane * 4;
-    const float4 a = *reinterpret_cast<const float4*>(hp + r * 256 + c);
-    const float4 b = *reinterpret_cast<const float4*>(hr + r * 256 + c);
+    const float4 a = tn_tile_load4(hp, 8, (int)r, c >> 2);
+    const float4 b = tn_tile_load4(hr, 8, (int)r, c >> 2);
 #pragma unroll
     for (int j = 0; j < 3; ++j) acc[j] += a.x * w[j][c] + a.y * w[j][c + 1] + a.z * w[j][c + 2] + a.w * w[j][c + 3];
 #pragma unroll
@@ -248,8 +255,8 @@ __global__ void __launch_bounds__(256) tn_heads_fwd_kernel(int R, const float* _
 // backward: CTA = (128-row block, head).  dH = (g W) * [H > 0] -> split tiles + transposed tiles (the first data-
 // gradient GEMM's A operand / the weight-gradient operand); dW[j, c] += sum_r g[r, j] H[r, c]; db[j] += sum_r g[r, j]
 __global__ void __launch_bounds__(256) tn_heads_bwd_kernel(int R, int Rp, const float* __restrict__ g_dxyz,
-                                                           const float* __restrict__ g_dquat, const float* __restrict__ hp,
-                                                           const float* __restrict__ hr, const float* __restrict__ W9,
+                                                           const float* __restrict__ g_dquat, const uint8_t* __restrict__ hp,
+                                                           const uint8_t* __restrict__ hr, const float* __restrict__ W9,
                                                            const float* __restrict__ W11, uint8_t* __restrict__ out_p,
                                                            uint8_t* __restrict__ outT_p, uint8_t* __restrict__ out_r,
                                                            uint8_t* __restrict__ outT_r, float* __restrict__ dW9,
@@ -258,7 +265,7 @@ __global__ void __launch_bounds__(256) tn_heads_bwd_kernel(int R, int Rp, const 
   const int rb = blockIdx.x, head = blockIdx.y, tid = threadIdx.x;
   const int No = head ? 4 : 3;
   const float* g = head ? g_dquat : g_dxyz;
-  const float* H = head ? hr : hp;
+  const uint8_t* H = head ? hr : hp;                 // split tiles of the head's hidden activation
   const float* W = head ? W11 : W9;
   uint8_t* out = head ? out_r : out_p;
   uint8_t* outT = head ? outT_r : outT_p;
@@ -278,7 +285,7 @@ __global__ void __launch_bounds__(256) tn_heads_bwd_kernel(int R, int Rp, const 
     const int r = rb * 128 + rl;
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     if (r < R) {
-      const float4 h = *reinterpret_cast<const float4*>(H + (int64_t)r * 256 + qq * 4);
+      const float4 h = tn_tile_load4(H, 8, r, qq);
       const float hv[4] = {h.x, h.y, h.z, h.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -311,7 +318,13 @@ __global__ void __launch_bounds__(256) tn_heads_bwd_kernel(int R, int Rp, const 
     for (int r0 = 0; r0 < rows; r0 += 16) {           // 16 independent loads in flight
       float h[16];
 #pragma unroll
-      for (int u = 0; u < 16; ++u) h[u] = r0 + u < rows ? H[(int64_t)(rb * 128 + r0 + u) * 256 + c] : 0.f;
+      for (int u = 0; u < 16; ++u) {
+        h[u] = 0.f;
+        if (r0 + u < rows) {
+          const uint8_t* t = H + ((size_t)rb * 8 + (c >> 5)) * TN_STAGE_A + tn_off(r0 + u, (c & 31) >> 2) + (c & 3) * 4;
+          h[u] = *reinterpret_cast<const float*>(t) + *reinterpret_cast<const float*>(t + TN_PLANE_A);
+        }
+      }
 #pragma unroll
       for (int u = 0; u < 16; ++u) {
         if (r0 + u < rows) {
@@ -352,14 +365,21 @@ __device__ __forceinline__ void tn_stamp(unsigned long long* dbg, int slot) {
   }
 }
 
-// One CTA = 128 rows x 128 output columns (grid.y = N / 128).  10 warps: 0-7 epilogue (warp w: TMEM lanes 32 (w & 3),
-// columns 64 (w >> 2) + [0, 64)), 8 producer, 9 MMA issuer; three 64 KB stages.
-constexpr int TG_NB = 128;
-constexpr int TG_STAGE_B = 2 * TG_NB * TN_KT * 4;           // 32 KB
-constexpr int TG_STAGE = TN_STAGE_A + TG_STAGE_B;           // 64 KB
-constexpr int TG_STAGES = 3;
+// One CTA = 128 rows x 64 output columns (grid.y = N / 64: 128 CTAs for a 4096 x 256 layer -- one wave of the 148 SMs).
+// 10 warps: 0-7 epilogue (warp w: TMEM lanes 32 (w & 3), columns 32 (w >> 2) + [0, 32)), 8 producer, 9 MMA issuer; four
+// 48 KB stages.  Phase times of a K = 256 layer (tools/tn_stamps.py): first stage lands at 1.8 us, MMAs done at ~5 us.
+constexpr int TG_NB = 64;
+constexpr int TG_STAGE_B = 2 * TG_NB * TN_KT * 4;           // 16 KB
+constexpr int TG_STAGE = TN_STAGE_A + TG_STAGE_B;           // 48 KB
+constexpr int TG_STAGES = 4;
 constexpr int TG_SMEM = TG_STAGES * TG_STAGE + 1024;
 constexpr int TG_THREADS = 320;
+constexpr int TG_TSTAGE = 2 * (TG_NB / 8) * TT_SBO;         // transposed staging per lane group: (hi, lo) x 64 tile rows = 18 KB
+constexpr int TG_PLAIN_OFF = 4 * TG_TSTAGE;                 // plain staging [128][TG_NB + 1] floats behind it
+
+__device__ __forceinline__ void tn_named_bar(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
 
 __global__ void __launch_bounds__(TG_THREADS, 1) tn_gemm_kernel(const __grid_constant__ TnGemmArgs p) {
   extern __shared__ uint8_t tn_smem_raw[];
@@ -370,7 +390,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tn_gemm_kernel(const __grid_con
   const int rb = blockIdx.x, cb = blockIdx.y;
   if (tid == 0) tn_stamp(p.dbg, 0);
   const uint32_t planeB_full = (uint32_t)p.N * 128u;          // bytes of one plane of a packed weight tile (all N rows)
-  constexpr uint32_t planeB = TG_NB * 128u;                   // this CTA's 128 rows of it
+  constexpr uint32_t planeB = TG_NB * 128u;                   // this CTA's 64 rows of it
 
   if (warp == 9) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tn_smem_u32(&tmem_slot)),
@@ -436,114 +456,114 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tn_gemm_kernel(const __grid_con
       tn_stamp(p.dbg, 3);
     }
   } else {
-    // ===== epilogue =====
+    // ===== epilogue: one 32-column chunk per warp =====
     const int lg = warp & 3;                       // TMEM lane group = tile rows [32 lg, 32 lg + 32)
     const int rl = lg * 32 + lane;
     const int gr = rb * TN_BM + rl;
     const bool valid = gr < p.R;
+    const int lc0 = (warp >> 2) * 32;              // column within the CTA's 64
+    const int n0 = cb * TG_NB + lc0;               // column of the GEMM's N
     const uint32_t row_off = tn_off(rl, 0);        // (row, chunk q) -> row_off + 128 q
-    const uint32_t t_lane = (uint32_t)((lane >> 2) * TT_LBO + (lane & 3) * 4);
     // everything that does not depend on the accumulator is fetched while the MMAs run: bias, ReLU-mask bits
-    float bias_r[2][32];
-    uint32_t mbits[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+    float bias_r[32];
+    uint32_t mbits = 0xFFFFFFFFu;
+    if (p.bias != nullptr) {
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const int n0 = cb * TG_NB + (warp >> 2) * 64 + c * 32;
-      if (p.bias != nullptr) {
-        const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 bb = b4[q];
-          bias_r[c][4 * q] = bb.x; bias_r[c][4 * q + 1] = bb.y; bias_r[c][4 * q + 2] = bb.z; bias_r[c][4 * q + 3] = bb.w;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) bias_r[c][j] = 0.f;
+      for (int q = 0; q < 8; ++q) {
+        const float4 bb = b4[q];
+        bias_r[4 * q] = bb.x; bias_r[4 * q + 1] = bb.y; bias_r[4 * q + 2] = bb.z; bias_r[4 * q + 3] = bb.w;
       }
-      if (p.mask != nullptr) {
-        const uint8_t* mt = p.mask + ((size_t)rb * p.mask_nkt + p.mask_kt0 + (n0 >> 5)) * TN_STAGE_A + row_off;
-        uint32_t bits = 0;
+    } else {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 mh = *reinterpret_cast<const float4*>(mt + 128 * q);
-          const float4 ml = *reinterpret_cast<const float4*>(mt + TN_PLANE_A + 128 * q);
-          bits |= (uint32_t)(mh.x > 0.f || ml.x > 0.f) << (4 * q);
-          bits |= (uint32_t)(mh.y > 0.f || ml.y > 0.f) << (4 * q + 1);
-          bits |= (uint32_t)(mh.z > 0.f || ml.z > 0.f) << (4 * q + 2);
-          bits |= (uint32_t)(mh.w > 0.f || ml.w > 0.f) << (4 * q + 3);
-        }
-        mbits[c] = bits;
+      for (int j = 0; j < 32; ++j) bias_r[j] = 0.f;
+    }
+    if (p.mask != nullptr) {
+      const uint8_t* mt = p.mask + ((size_t)rb * p.mask_nkt + p.mask_kt0 + (n0 >> 5)) * TN_STAGE_A + row_off;
+      uint32_t bits = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 mh = *reinterpret_cast<const float4*>(mt + 128 * q);
+        const float4 ml = *reinterpret_cast<const float4*>(mt + TN_PLANE_A + 128 * q);
+        bits |= (uint32_t)(mh.x > 0.f || ml.x > 0.f) << (4 * q);
+        bits |= (uint32_t)(mh.y > 0.f || ml.y > 0.f) << (4 * q + 1);
+        bits |= (uint32_t)(mh.z > 0.f || ml.z > 0.f) << (4 * q + 2);
+        bits |= (uint32_t)(mh.w > 0.f || ml.w > 0.f) << (4 * q + 3);
       }
+      mbits = bits;
     }
     if (tid == 0) tn_stamp(p.dbg, 4);
     tn_mbar_wait(&done_bar, 0);
     if (tid == 0) tn_stamp(p.dbg, 5);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // transposed tiles are staged in the (now idle) operand stages as the exact 16 KB images T[rt = 4 rb + lg][plane]
-    // [fb] they occupy in global memory and leave with one bulk store each (below)
-    uint8_t* stageT = smem + (size_t)lg * 2 * TN_FB_BYTES;
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      const int lc0 = (warp >> 2) * 64 + c * 32;   // column within the CTA's 128
-      const int n0 = cb * TG_NB + lc0;             // column of the GEMM's N
-      uint32_t v[32];
-      tn_ld32(tmem_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)lc0, v);
-      float y[32];
+    uint32_t v[32];
+    tn_ld32(tmem_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)lc0, v);
+    float y[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float t = __uint_as_float(v[j]) + bias_r[j];
+      if (p.relu) t = fmaxf(t, 0.f);
+      y[j] = (valid && ((mbits >> j) & 1u)) ? t : 0.f;
+    }
+    uint32_t hi[32], lo[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { hi[j] = tn_tf32(y[j]); lo[j] = tn_tf32(y[j] - __uint_as_float(hi[j])); }
+    if (p.outT != nullptr) {
+      // transposed tiles: staged in the (now idle) operand stages as the exact image of this CTA's part of
+      // T[rt = 4 rb + lg][plane][fb] -- 64 consecutive tile rows = 9 KB, contiguous in global memory -- and written by one
+      // bulk store per (lane group, plane) as soon as the group's two warps are through
+      uint8_t* t = smem + (size_t)lg * TG_TSTAGE + (size_t)(lc0 >> 3) * TT_SBO + (lane >> 2) * TT_LBO + (lane & 3) * 4;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        float t = __uint_as_float(v[j]) + (c == 0 ? bias_r[0][j] : bias_r[1][j]);
-        if (p.relu) t = fmaxf(t, 0.f);
-        const bool keep = valid && (((c == 0 ? mbits[0] : mbits[1]) >> j) & 1u);
-        y[j] = keep ? t : 0.f;
+        *reinterpret_cast<uint32_t*>(t + (j >> 3) * TT_SBO + (j & 7) * 16) = hi[j];
+        *reinterpret_cast<uint32_t*>(t + TG_TSTAGE / 2 + (j >> 3) * TT_SBO + (j & 7) * 16) = lo[j];
       }
-      const int kt_out = n0 >> 5;                  // this chunk is k tile kt_out of the result
-      uint32_t hi[32], lo[32];
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // staged image -> bulk-copy engine
+      tn_named_bar(1 + lg, 64);
+      if (warp < 4 && lane == 0) {
+        const int f0 = p.t_f0 + cb * TG_NB, fb = f0 >> 7, fl0 = f0 & 127;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) { hi[j] = tn_tf32(y[j]); lo[j] = tn_tf32(y[j] - __uint_as_float(hi[j])); }
-      if (p.out != nullptr) {
-        uint8_t* t = p.out + ((size_t)rb * p.out_nkt + p.out_kt0 + kt_out) * TN_STAGE_A + row_off;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          *reinterpret_cast<uint4*>(t + 128 * q) = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-          *reinterpret_cast<uint4*>(t + TN_PLANE_A + 128 * q) = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+        for (int pl = 0; pl < 2; ++pl) {
+          const uint8_t* src = smem + (size_t)lg * TG_TSTAGE + (size_t)pl * (TG_TSTAGE / 2);
+          uint8_t* dst = p.outT + ((((size_t)(rb * 4 + lg)) * 2 + pl) * p.t_nfb + fb) * TN_FB_BYTES + (size_t)(fl0 >> 3) * TT_SBO;
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(tn_smem_u32(src)),
+                       "r"((uint32_t)(TG_TSTAGE / 2))
+                       : "memory");
         }
-      }
-      if (p.outT != nullptr) {
-        // feature f = t_f0 + n0 + j: the CTA's 128 columns are ONE feature block (t_f0 is a multiple of 128)
-        uint8_t* t = stageT + (size_t)(lc0 >> 3) * TT_SBO + t_lane;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          *reinterpret_cast<uint32_t*>(t + (j >> 3) * TT_SBO + (j & 7) * 16) = hi[j];
-          *reinterpret_cast<uint32_t*>(t + TN_FB_BYTES + (j >> 3) * TT_SBO + (j & 7) * 16) = lo[j];
-        }
-      }
-      if (p.plain != nullptr && valid) {
-        float* row = p.plain + (int64_t)gr * p.ldp + n0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (n0 + j < p.plain_cols) row[j] = y[j] + (p.plain_acc ? row[j] : 0.f);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     }
-    if (p.outT != nullptr) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged images -> bulk-copy engine
-    if (tid == 0) tn_stamp(p.dbg, 6);
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (p.outT != nullptr && tid == 0) {
-    // eight bulk stores: (4 r tiles) x (hi, lo plane), 16 KB each, contiguous on both sides
-    const int fb = (p.t_f0 + cb * TG_NB) >> 7;
+    if (p.out != nullptr) {
+      uint8_t* t = p.out + ((size_t)rb * p.out_nkt + p.out_kt0 + (n0 >> 5)) * TN_STAGE_A + row_off;
 #pragma unroll
-    for (int g4 = 0; g4 < 4; ++g4)
-#pragma unroll
-      for (int pl = 0; pl < 2; ++pl) {
-        const uint8_t* src = smem + (size_t)(g4 * 2 + pl) * TN_FB_BYTES;
-        uint8_t* dst = p.outT + ((((size_t)(rb * 4 + g4)) * 2 + pl) * p.t_nfb + fb) * TN_FB_BYTES;
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(tn_smem_u32(src)),
-                     "r"((uint32_t)TN_FB_BYTES)
-                     : "memory");
+      for (int q = 0; q < 8; ++q) {
+        *reinterpret_cast<uint4*>(t + 128 * q) = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+        *reinterpret_cast<uint4*>(t + TN_PLANE_A + 128 * q) = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
       }
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // shared memory may be released after the reads
+    }
+    if (p.plain != nullptr) {
+      // fp32 row-major copy: through shared memory so that the global accesses are row-contiguous
+      float* sp = reinterpret_cast<float*>(smem + TG_PLAIN_OFF);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sp[rl * (TG_NB + 1) + lc0 + j] = y[j];
+      tn_named_bar(5, 256);
+      for (int r = warp; r < TN_BM; r += 8) {
+        const int g2 = rb * TN_BM + r;
+        if (g2 >= p.R) break;
+#pragma unroll
+        for (int h = 0; h < TG_NB / 32; ++h) {
+          const int col = cb * TG_NB + h * 32 + lane;
+          if (col < p.plain_cols) {
+            float* dst = p.plain + (int64_t)g2 * p.ldp + col;
+            const float val = sp[r * (TG_NB + 1) + h * 32 + lane];
+            *dst = p.plain_acc ? *dst + val : val;
+          }
+        }
+      }
+    }
+    if (p.outT != nullptr && warp < 4 && lane == 0)
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // shared memory may be released after the reads
+    if (tid == 0) tn_stamp(p.dbg, 6);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -770,7 +790,7 @@ extern "C" int dimo_timenet_embed_bwd(int G, int rows_per_group, int L, const fl
 
 static unsigned long long* g_tn_dbg = nullptr;
 static int g_tn_dbg_launch = 0;
-/* bring-up: device buffer of 32 x 64 x 8 u64; the following tn_gemm launches stamp [launch % 32][cta][8] with %globaltimer (NULL: off) */
+/* bring-up: device buffer of 32 x 128 x 8 u64; the following tn_gemm launches stamp [launch % 32][cta][8] with %globaltimer (NULL: off) */
 extern "C" int dimo_timenet_debug_stamps(void* dev_buf) {
   g_tn_dbg = reinterpret_cast<unsigned long long*>(dev_buf);
   g_tn_dbg_launch = 0;
@@ -857,7 +877,7 @@ extern "C" int dimo_timenet_fwd(int G, int M, int L, const float* pts, const flo
   }
   // ---- the ten 256-wide layers ----
   auto gemm = [&](TnGemmArgs& g) {
-    g.dbg = g_tn_dbg != nullptr ? g_tn_dbg + (size_t)(g_tn_dbg_launch++ % 32) * 64 * 8 : nullptr;
+    g.dbg = g_tn_dbg != nullptr ? g_tn_dbg + (size_t)(g_tn_dbg_launch++ % 32) * 128 * 8 : nullptr;
     tn_gemm_kernel<<<dim3(o.nrb, g.N / TG_NB), TG_THREADS, TG_SMEM, st>>>(g);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
   };
@@ -880,14 +900,11 @@ extern "C" int dimo_timenet_fwd(int G, int M, int L, const float* pts, const flo
     if (l == 4) { g.outT = ws + o.catT; g.t_nfb = 3; g.t_f0 = 128; }
     else if (l == 8 || l == 10) { g.outT = nullptr; }                 // hp / hr feed only the SIMT heads
     else { g.outT = ws + o.yT[slot]; g.t_nfb = 2; g.t_f0 = 0; }
-    if (l == 8) { g.plain = reinterpret_cast<float*>(ws + o.hp_plain); g.ldp = HID; g.plain_cols = HID; }
-    if (l == 10) { g.plain = reinterpret_cast<float*>(ws + o.hr_plain); g.ldp = HID; g.plain_cols = HID; }
     if (gemm(g)) { dimo::set_error("tn_gemm_kernel launch failed (layer %d)", l); return -1; }
   }
   // ---- 3- and 4-wide heads (FP32 SIMT, one launch) ----
-  tn_heads_fwd_kernel<<<ceil_div(R, 8), 256, 0, st>>>(R, reinterpret_cast<float*>(ws + o.hp_plain),
-                                                      reinterpret_cast<float*>(ws + o.hr_plain), W_host[9], b_host[9],
-                                                      W_host[11], b_host[11], dxyz, dquat);
+  tn_heads_fwd_kernel<<<ceil_div(R, 8), 256, 0, st>>>(R, ws + o.y[8], ws + o.y[9], W_host[9], b_host[9], W_host[11],
+                                                      b_host[11], dxyz, dquat);
   DIMO_CHECK_LAUNCH();
   return 0;
 }
@@ -903,19 +920,15 @@ extern "C" int dimo_timenet_bwd(int G, int M, int L, const float* const* W_host,
   cudaStream_t st = (cudaStream_t)stream;
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   const int E = o.E;
-  float* hp = reinterpret_cast<float*>(ws + o.hp_plain);
-  float* hr = reinterpret_cast<float*>(ws + o.hr_plain);
-  float* dhp = reinterpret_cast<float*>(ws + o.dhp_plain);
-  float* dhr = reinterpret_cast<float*>(ws + o.dhr_plain);
   float* dcat = reinterpret_cast<float*>(ws + o.dcat_plain);
   // ---- heads (FP32 SIMT, one launch): weight / bias gradients + masked data gradients as split tiles ----
-  tn_heads_bwd_kernel<<<dim3(o.nrb, 2), 256, 0, st>>>(R, o.Rp, g_dxyz, g_dquat, hp, hr, W_host[9], W_host[11], ws + o.g[8],
+  tn_heads_bwd_kernel<<<dim3(o.nrb, 2), 256, 0, st>>>(R, o.Rp, g_dxyz, g_dquat, ws + o.y[8], ws + o.y[9], W_host[9], W_host[11], ws + o.g[8],
                                                       ws + o.gT[8], ws + o.g[9], ws + o.gT[9], dW_host[9], db_host[9],
                                                       dW_host[11], db_host[11], dimo::det_scale());
   DIMO_CHECK_LAUNCH();
   int rc = 0;
   auto gemm = [&](TnGemmArgs& g) {
-    g.dbg = g_tn_dbg != nullptr ? g_tn_dbg + (size_t)(g_tn_dbg_launch++ % 32) * 64 * 8 : nullptr;
+    g.dbg = g_tn_dbg != nullptr ? g_tn_dbg + (size_t)(g_tn_dbg_launch++ % 32) * 128 * 8 : nullptr;
     tn_gemm_kernel<<<dim3(o.nrb, g.N / TG_NB), TG_THREADS, TG_SMEM, st>>>(g);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
   };

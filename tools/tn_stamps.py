@@ -8,7 +8,7 @@ torch.manual_seed(0)
 G, M, L = 8, 512, 32
 net = TimeNet(latent_code_dim=L).cuda()
 pts = torch.rand(M, 3, device="cuda") - 0.5; times = torch.rand(G, device="cuda"); lat = torch.randn(G, L, device="cuda")
-buf = torch.zeros(32 * 64 * 8, dtype=torch.int64, device="cuda")
+buf = torch.zeros(32 * 128 * 8, dtype=torch.int64, device="cuda")
 with torch.no_grad():
     for _ in range(3):
         net.forward_batched(pts, times, lat)
@@ -17,7 +17,7 @@ with torch.no_grad():
     net.forward_batched(pts, times, lat)
     torch.cuda.synchronize()
     _lib.lib().dimo_timenet_debug_stamps(None)
-T = buf.view(32, 64, 8).cpu().double()
+T = buf.view(32, 128, 8).cpu().double()
 names = ["start", "setup", "stage0", "mma issued", "prefetch", "acc ready", "epi done", "stores read"]
 base = T[0, :, 0].min()
 for l in range(10):
