@@ -366,22 +366,22 @@ __device__ __forceinline__ void tn_stamp(unsigned long long* dbg, int slot) {
 }
 
 // One CTA = 128 rows x 64 output columns (grid.y = N / 64: 128 CTAs for a 4096 x 256 layer -- one wave of the 148 SMs).
-// 10 warps: 0-7 epilogue (warp w: TMEM lanes 32 (w & 3), columns 32 (w >> 2) + [0, 32)), 8 producer, 9 MMA issuer; four
-// 48 KB stages.  Phase times of a K = 256 layer (tools/tn_stamps.py): first stage lands at 1.8 us, MMAs done at ~5 us.
+// 10 warps: 0-7 epilogue (warp w: TMEM lanes 32 (w & 3), columns 32 (w >> 2) + [0, 32)), 8 producer, 9 MMA issuer; two
+// 48 KB stages, two CTAs per SM.  Phase times of a K = 256 layer (tools/tn_stamps.py): first stage lands at 1.8 us, MMAs done at ~5 us.
 constexpr int TG_NB = 64;
 constexpr int TG_STAGE_B = 2 * TG_NB * TN_KT * 4;           // 16 KB
 constexpr int TG_STAGE = TN_STAGE_A + TG_STAGE_B;           // 48 KB
-constexpr int TG_STAGES = 4;
-constexpr int TG_SMEM = TG_STAGES * TG_STAGE + 1024;
+constexpr int TG_STAGES = 2;                                // 97 KB per CTA: two CTAs per SM, so that one CTA's epilogue
+constexpr int TG_SMEM = TG_STAGES * TG_STAGE + 1024;        // overlaps the other's MMAs and 256-CTA grids (8192 rows) are one wave
 constexpr int TG_THREADS = 320;
 constexpr int TG_TSTAGE = 2 * (TG_NB / 8) * TT_SBO;         // transposed staging per lane group: (hi, lo) x 64 tile rows = 18 KB
-constexpr int TG_PLAIN_OFF = 4 * TG_TSTAGE;                 // plain staging [128][TG_NB + 1] floats behind it
+static_assert(4 * TG_TSTAGE <= TG_STAGES * TG_STAGE && 128 * (TG_NB + 1) * 4 <= TG_STAGES * TG_STAGE, "epilogue staging");
 
 __device__ __forceinline__ void tn_named_bar(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
-__global__ void __launch_bounds__(TG_THREADS, 1) tn_gemm_kernel(const __grid_constant__ TnGemmArgs p) {
+__global__ void __launch_bounds__(TG_THREADS, 2) tn_gemm_kernel(const __grid_constant__ TnGemmArgs p) {
   extern __shared__ uint8_t tn_smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[TG_STAGES], empty_bar[TG_STAGES], done_bar;
   __shared__ uint32_t tmem_slot;
@@ -498,26 +498,36 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tn_gemm_kernel(const __grid_con
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     uint32_t v[32];
     tn_ld32(tmem_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)lc0, v);
-    float y[32];
+    // per group of four columns: bias / ReLU / mask, split into (hi, lo), and every store that wants the values
+    uint8_t* tT = smem + (size_t)lg * TG_TSTAGE + (size_t)(lc0 >> 3) * TT_SBO + (lane >> 2) * TT_LBO + (lane & 3) * 4;
+    uint8_t* tO = p.out != nullptr ? p.out + ((size_t)rb * p.out_nkt + p.out_kt0 + (n0 >> 5)) * TN_STAGE_A + row_off : nullptr;
+    float* sp = reinterpret_cast<float*>(smem) + rl * (TG_NB + 1) + lc0;   // plain staging (jobs without transposed output)
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float t = __uint_as_float(v[j]) + bias_r[j];
-      if (p.relu) t = fmaxf(t, 0.f);
-      y[j] = (valid && ((mbits >> j) & 1u)) ? t : 0.f;
+    for (int q = 0; q < 8; ++q) {
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = 4 * q + e;
+        float t = __uint_as_float(v[j]) + bias_r[j];
+        if (p.relu) t = fmaxf(t, 0.f);
+        const float y = (valid && ((mbits >> j) & 1u)) ? t : 0.f;
+        hi[e] = tn_tf32(y);
+        lo[e] = tn_tf32(y - __uint_as_float(hi[e]));
+        if (p.outT != nullptr) {
+          *reinterpret_cast<uint32_t*>(tT + (j >> 3) * TT_SBO + (j & 7) * 16) = hi[e];
+          *reinterpret_cast<uint32_t*>(tT + TG_TSTAGE / 2 + (j >> 3) * TT_SBO + (j & 7) * 16) = lo[e];
+        }
+        if (p.plain != nullptr) sp[j] = y;
+      }
+      if (tO != nullptr) {
+        *reinterpret_cast<uint4*>(tO + 128 * q) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(tO + TN_PLANE_A + 128 * q) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
     }
-    uint32_t hi[32], lo[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) { hi[j] = tn_tf32(y[j]); lo[j] = tn_tf32(y[j] - __uint_as_float(hi[j])); }
     if (p.outT != nullptr) {
       // transposed tiles: staged in the (now idle) operand stages as the exact image of this CTA's part of
       // T[rt = 4 rb + lg][plane][fb] -- 64 consecutive tile rows = 9 KB, contiguous in global memory -- and written by one
       // bulk store per (lane group, plane) as soon as the group's two warps are through
-      uint8_t* t = smem + (size_t)lg * TG_TSTAGE + (size_t)(lc0 >> 3) * TT_SBO + (lane >> 2) * TT_LBO + (lane & 3) * 4;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        *reinterpret_cast<uint32_t*>(t + (j >> 3) * TT_SBO + (j & 7) * 16) = hi[j];
-        *reinterpret_cast<uint32_t*>(t + TG_TSTAGE / 2 + (j >> 3) * TT_SBO + (j & 7) * 16) = lo[j];
-      }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // staged image -> bulk-copy engine
       tn_named_bar(1 + lg, 64);
       if (warp < 4 && lane == 0) {
@@ -532,20 +542,9 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tn_gemm_kernel(const __grid_con
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
-    }
-    if (p.out != nullptr) {
-      uint8_t* t = p.out + ((size_t)rb * p.out_nkt + p.out_kt0 + (n0 >> 5)) * TN_STAGE_A + row_off;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        *reinterpret_cast<uint4*>(t + 128 * q) = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-        *reinterpret_cast<uint4*>(t + TN_PLANE_A + 128 * q) = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
-      }
-    }
-    if (p.plain != nullptr) {
+    } else if (p.plain != nullptr) {
       // fp32 row-major copy: through shared memory so that the global accesses are row-contiguous
-      float* sp = reinterpret_cast<float*>(smem + TG_PLAIN_OFF);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) sp[rl * (TG_NB + 1) + lc0 + j] = y[j];
+      const float* sr = reinterpret_cast<const float*>(smem);
       tn_named_bar(5, 256);
       for (int r = warp; r < TN_BM; r += 8) {
         const int g2 = rb * TN_BM + r;
@@ -555,7 +554,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tn_gemm_kernel(const __grid_con
           const int col = cb * TG_NB + h * 32 + lane;
           if (col < p.plain_cols) {
             float* dst = p.plain + (int64_t)g2 * p.ldp + col;
-            const float val = sp[r * (TG_NB + 1) + h * 32 + lane];
+            const float val = sr[r * (TG_NB + 1) + h * 32 + lane];
             *dst = p.plain_acc ? *dst + val : val;
           }
         }
