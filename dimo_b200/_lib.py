@@ -25,7 +25,7 @@ _SIGS = {
     "dimo_raster_packed_value_bits": (c_int, [c_int] * 4),
     "dimo_raster_blend_fwd": (c_int, [c_int] * 5 + [c_vp] * 11),
     "dimo_raster_blend_bwd": (c_int, [c_int] * 5 + [c_vp] * 12),
-    "dimo_raster_preprocess_bwd": (c_int, [c_int] * 6 + [c_f32, c_int, c_vp, c_vp] + [c_vp, c_i64] * 5 + [c_vp] * 10),
+    "dimo_raster_preprocess_bwd": (c_int, [c_int] * 6 + [c_f32, c_int, c_vp, c_vp] + [c_vp, c_i64] * 5 + [c_vp] * 9 + [c_int, c_vp]),
     "dimo_knn": (c_int, [c_int] * 3 + [c_vp] * 5),
     "dimo_dist3nn": (c_int, [c_int, c_vp, c_vp, c_vp]),
     "dimo_fps": (c_int, [c_int] * 4 + [c_vp] * 4),

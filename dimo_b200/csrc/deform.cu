@@ -8,7 +8,10 @@
 // xyz 12 + rot 16 + idx 32 + dist 16 B per Gaussian once per block column and writes 28 B per
 // (frame, Gaussian); the M x 11-float control tables stay in L1/L2.
 //
-// Backward: see lbs_bwd_frames_kernel (default) and lbs_bwd_kernel (deterministic mode, 64-bit fixed-point REDs).
+// Backward accumulates control-point gradients in a shared-memory table (M x 11 floats) per CTA and
+// flushes once, instead of N*K*11 contended global atomics on 512 addresses.  (Measured alternative, round 2: one thread
+// per Gaussian x 4 frames with frame-invariant work hoisted and 128-bit REDs straight to global memory -- 339 us against
+// 164 us for this kernel at 16 x 100k x K=4: the L2 serialises the ~3000 adds per control-point address.)
 #include "common.cuh"
 
 namespace dimo {
@@ -247,139 +250,6 @@ __global__ void __launch_bounds__(256) lbs_bwd_kernel(
   }
 }
 
-// Backward, default (non-deterministic) path: thread = one Gaussian x a group of FB frames.  Everything that does not
-// depend on the frame (skinning weights, neighbour offsets, the canonical rotation) is computed once; the canonical
-// gradients (dxyz_c, drot_c), the control-point position gradient and the radius gradient are summed over the thread's
-// frames in registers, so global reductions per (Gaussian, frame) drop from 51 scalar atomics (44 of them CAS loops on a
-// shared-memory table in the first version: ncu profiles/r2r, 164 us) to K x (one 128-bit RED + 3 scalar) + ~23 / FB.
-template <int K, int FB>
-__global__ void __launch_bounds__(128) lbs_bwd_frames_kernel(
-    int B, int N, int M, const float* __restrict__ xyz, const float* __restrict__ rot, const int64_t* __restrict__ idx,
-    const float* __restrict__ dist, const float* __restrict__ c_xyz, const float* __restrict__ c_radius_raw,
-    const float* __restrict__ dxyz, const float* __restrict__ dquat, const float* __restrict__ g_means3D,
-    const float4* __restrict__ g_rotations, float* __restrict__ dxyz_c, float* __restrict__ drot_c,
-    float* __restrict__ dc_xyz, float* __restrict__ dc_radius_raw, float* __restrict__ ddxyz, float* __restrict__ ddquat,
-    int ddquat_vec) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N) return;
-  const int b0 = blockIdx.y * FB, b1 = min(B, b0 + FB);
-  float w[K], e[K], rad[K], wn[K];
-  int nb[K];
-  const float S = lbs_weights<K>(dist + (int64_t)i * K, idx + (int64_t)i * K, c_radius_raw, w, e, rad, nb);
-  const float px = xyz[3 * (int64_t)i], py = xyz[3 * (int64_t)i + 1], pz = xyz[3 * (int64_t)i + 2];
-  float c[K][3], v[K][3];
-#pragma unroll
-  for (int k = 0; k < K; ++k) {
-    wn[k] = w[k] / S;
-    c[k][0] = c_xyz[3 * nb[k]]; c[k][1] = c_xyz[3 * nb[k] + 1]; c[k][2] = c_xyz[3 * nb[k] + 2];
-    v[k][0] = px - c[k][0]; v[k][1] = py - c[k][1]; v[k][2] = pz - c[k][2];
-  }
-  const float4 rc4 = *reinterpret_cast<const float4*>(rot + 4 * (int64_t)i);
-  const Quat rc = {rc4.x, rc4.y, rc4.z, rc4.w};
-  float gxyz[3] = {0.f, 0.f, 0.f}, gcan[4] = {0.f, 0.f, 0.f, 0.f};
-  float gcx[K][3], gw_acc[K];
-  float dot_acc = 0.f;
-#pragma unroll
-  for (int k = 0; k < K; ++k) { gcx[k][0] = gcx[k][1] = gcx[k][2] = 0.f; gw_acc[k] = 0.f; }
-
-  for (int b = b0; b < b1; ++b) {
-    const float* dx_b = dxyz + (int64_t)b * M * 3;
-    const float* dq_b = dquat + (int64_t)b * M * 4;
-    const int64_t o = (int64_t)b * N + i;
-    const float gx = g_means3D[3 * o], gy = g_means3D[3 * o + 1], gz = g_means3D[3 * o + 2];
-    const float4 gr4 = g_rotations[o];
-    // blended quaternion and the normalised product, recomputed for the normalisation backward
-    Quat qb = {0.f, 0.f, 0.f, 0.f};
-    float4 dqv[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      dqv[k] = *reinterpret_cast<const float4*>(dq_b + 4 * (int64_t)nb[k]);
-      qb.r += wn[k] * dqv[k].x; qb.x += wn[k] * dqv[k].y; qb.y += wn[k] * dqv[k].z; qb.z += wn[k] * dqv[k].w;
-    }
-    const Quat u = quat_mul(qb, rc);
-    const float un_raw = sqrtf(u.r * u.r + u.x * u.x + u.y * u.y + u.z * u.z);
-    const float un = fmaxf(un_raw, NORM_EPS);
-    const float y0 = u.r / un, y1 = u.x / un, y2 = u.y / un, y3 = u.z / un;
-    float g0 = gr4.x, g1 = gr4.y, g2 = gr4.z, g3 = gr4.w;
-    if (un_raw > NORM_EPS) {
-      const float dotyg = y0 * g0 + y1 * g1 + y2 * g2 + y3 * g3;
-      g0 = (g0 - y0 * dotyg) / un; g1 = (g1 - y1 * dotyg) / un; g2 = (g2 - y2 * dotyg) / un; g3 = (g3 - y3 * dotyg) / un;
-    } else {
-      g0 /= un; g1 /= un; g2 /= un; g3 /= un;
-    }
-    // u = qb (x) rc
-    const float gq_r = g0 * rc.r + g1 * rc.x + g2 * rc.y + g3 * rc.z;
-    const float gq_x = -g0 * rc.x + g1 * rc.r - g2 * rc.z + g3 * rc.y;
-    const float gq_y = -g0 * rc.y + g1 * rc.z + g2 * rc.r - g3 * rc.x;
-    const float gq_z = -g0 * rc.z - g1 * rc.y + g2 * rc.x + g3 * rc.r;
-    gcan[0] += g0 * qb.r + g1 * qb.x + g2 * qb.y + g3 * qb.z;
-    gcan[1] += -g0 * qb.x + g1 * qb.r + g2 * qb.z - g3 * qb.y;
-    gcan[2] += -g0 * qb.y - g1 * qb.z + g2 * qb.r + g3 * qb.x;
-    gcan[3] += -g0 * qb.z + g1 * qb.y - g2 * qb.x + g3 * qb.r;
-    float dotw = 0.f;
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const int j = nb[k];
-      const float4 dq = dqv[k];
-      const float nrm = sqrtf(dq.x * dq.x + dq.y * dq.y + dq.z * dq.z + dq.w * dq.w);
-      const Quat qn = {dq.x / nrm, dq.y / nrm, dq.z / nrm, dq.w / nrm};
-      float R[3][3];
-      rot_from_unit(qn, R);
-      const float tx = R[0][0] * v[k][0] + R[0][1] * v[k][1] + R[0][2] * v[k][2] + c[k][0] + dx_b[3 * j];
-      const float ty = R[1][0] * v[k][0] + R[1][1] * v[k][1] + R[1][2] * v[k][2] + c[k][1] + dx_b[3 * j + 1];
-      const float tz = R[2][0] * v[k][0] + R[2][1] * v[k][1] + R[2][2] * v[k][2] + c[k][2] + dx_b[3 * j + 2];
-      const float gwn = gx * tx + gy * ty + gz * tz + gq_r * dq.x + gq_x * dq.y + gq_y * dq.z + gq_z * dq.w;
-      gw_acc[k] += gwn;
-      dotw += gwn * wn[k];
-      // R^T g
-      const float rtg[3] = {R[0][0] * gx + R[1][0] * gy + R[2][0] * gz, R[0][1] * gx + R[1][1] * gy + R[2][1] * gz,
-                            R[0][2] * gx + R[1][2] * gy + R[2][2] * gz};
-      gxyz[0] += wn[k] * rtg[0]; gxyz[1] += wn[k] * rtg[1]; gxyz[2] += wn[k] * rtg[2];
-      gcx[k][0] += wn[k] * (gx - rtg[0]); gcx[k][1] += wn[k] * (gy - rtg[1]); gcx[k][2] += wn[k] * (gz - rtg[2]);
-      // dL/dR = wn * g v^T  ->  unit quaternion  ->  raw dquat (through normalisation)
-      const float gvec[3] = {gx, gy, gz};
-      float dR[3][3];
-#pragma unroll
-      for (int a = 0; a < 3; ++a)
-#pragma unroll
-        for (int cc = 0; cc < 3; ++cc) dR[a][cc] = wn[k] * gvec[a] * v[k][cc];
-      const float r = qn.r, x = qn.x, y = qn.y, z = qn.z;
-      const float gn0 = 2.f * (-z * dR[0][1] + y * dR[0][2] + z * dR[1][0] - x * dR[1][2] - y * dR[2][0] + x * dR[2][1]);
-      const float gn1 = 2.f * (y * dR[0][1] + z * dR[0][2] + y * dR[1][0] - 2.f * x * dR[1][1] - r * dR[1][2] + z * dR[2][0] +
-                               r * dR[2][1] - 2.f * x * dR[2][2]);
-      const float gn2 = 2.f * (-2.f * y * dR[0][0] + x * dR[0][1] + r * dR[0][2] + x * dR[1][0] + z * dR[1][2] - r * dR[2][0] +
-                               z * dR[2][1] - 2.f * y * dR[2][2]);
-      const float gn3 = 2.f * (-2.f * z * dR[0][0] - r * dR[0][1] + x * dR[0][2] + r * dR[1][0] - 2.f * z * dR[1][1] +
-                               y * dR[1][2] + x * dR[2][0] + y * dR[2][1]);
-      const float dotn = r * gn0 + x * gn1 + y * gn2 + z * gn3;
-      const float4 gdq = make_float4((gn0 - r * dotn) / nrm + wn[k] * gq_r, (gn1 - x * dotn) / nrm + wn[k] * gq_x,
-                                     (gn2 - y * dotn) / nrm + wn[k] * gq_y, (gn3 - z * dotn) / nrm + wn[k] * gq_z);
-      float* dq_out = ddquat + ((int64_t)b * M + j) * 4;
-      if (ddquat_vec) {
-        atomicAdd(reinterpret_cast<float4*>(dq_out), gdq);          // one 128-bit RED
-      } else {
-        atomicAdd(dq_out, gdq.x); atomicAdd(dq_out + 1, gdq.y); atomicAdd(dq_out + 2, gdq.z); atomicAdd(dq_out + 3, gdq.w);
-      }
-      float* dx_out = ddxyz + ((int64_t)b * M + j) * 3;
-      atomicAdd(dx_out, wn[k] * gx); atomicAdd(dx_out + 1, wn[k] * gy); atomicAdd(dx_out + 2, wn[k] * gz);
-    }
-    dot_acc += dotw;
-  }
-  atomicAdd(dxyz_c + 3 * (int64_t)i, gxyz[0]); atomicAdd(dxyz_c + 3 * (int64_t)i + 1, gxyz[1]);
-  atomicAdd(dxyz_c + 3 * (int64_t)i + 2, gxyz[2]);
-  atomicAdd(drot_c + 4 * (int64_t)i, gcan[0]); atomicAdd(drot_c + 4 * (int64_t)i + 1, gcan[1]);
-  atomicAdd(drot_c + 4 * (int64_t)i + 2, gcan[2]); atomicAdd(drot_c + 4 * (int64_t)i + 3, gcan[3]);
-  // weights: wn = w / S ; w = exp(-d^2 / (2 r^2)) + eps ; r = exp(raw)
-#pragma unroll
-  for (int k = 0; k < K; ++k) {
-    atomicAdd(dc_xyz + 3 * nb[k], gcx[k][0]); atomicAdd(dc_xyz + 3 * nb[k] + 1, gcx[k][1]);
-    atomicAdd(dc_xyz + 3 * nb[k] + 2, gcx[k][2]);
-    const float gw = (gw_acc[k] - dot_acc) / S;
-    const float d = dist[(int64_t)i * K + k];
-    atomicAdd(dc_radius_raw + nb[k], gw * e[k] * (d * d) / (rad[k] * rad[k]));   // dw/dr * r = e * d^2 / r^2
-  }
-}
-
 }  // namespace dimo
 
 using namespace dimo;
@@ -413,33 +283,19 @@ extern "C" int dimo_lbs_bwd(int B, int N, int M, int K, const float* xyz, const 
   DIMO_REQUIRE(K >= 1 && K <= LBS_MAXK, "K must be 1..8");
   if (B == 0 || N == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  const float det = dimo::det_scale();          // deterministic mode: every output is an int64 buffer, scalar 64-bit REDs
-  if (det == 0.f) {
-    constexpr int FB = 4;                       // frames per thread
-    const int ddquat_vec = ((uintptr_t)ddquat & 15) == 0;
-    dim3 grid(ceil_div(N, 128), ceil_div(B, FB));
-    switch (K) {
-#define DIMO_LBS_CASE(KK)                                                                                          \
-  case KK:                                                                                                         \
-    lbs_bwd_frames_kernel<KK, FB><<<grid, 128, 0, st>>>(                                                           \
-        B, N, M, xyz, rot, idx, dist, c_xyz, c_radius_raw, dxyz, dquat, dL_dmeans3D,                               \
-        reinterpret_cast<const float4*>(dL_drotations), dxyz_c, drot_c, dc_xyz, dc_radius_raw, ddxyz, ddquat,      \
-        ddquat_vec);                                                                                               \
-    break;
-      DIMO_LBS_CASE(1) DIMO_LBS_CASE(2) DIMO_LBS_CASE(3) DIMO_LBS_CASE(4)
-      DIMO_LBS_CASE(5) DIMO_LBS_CASE(6) DIMO_LBS_CASE(7) DIMO_LBS_CASE(8)
-#undef DIMO_LBS_CASE
-    }
-    DIMO_CHECK_LAUNCH();
-    return 0;
-  }
-  int per_frame = max(1, min(ceil_div(N, 256), ceil_div(1184, B)));
+  const size_t smem = (size_t)M * CT * sizeof(float);
+  const float det = dimo::det_scale();          // deterministic mode: every output is an int64 buffer, no shared staging
+  const int use_smem = (smem <= 160 * 1024 && det == 0.f) ? 1 : 0;
+  // few, fat CTAs per frame so each shared-memory table is flushed once: ~2 waves over 148 SMs in total
+  int per_frame = max(1, min(ceil_div(N, 256), ceil_div(296, B)));
   dim3 grid(per_frame, B);
   switch (K) {
 #define DIMO_LBS_CASE(KK)                                                                                          \
   case KK: {                                                                                                       \
-    lbs_bwd_kernel<KK><<<grid, 256, 0, st>>>(                                                                      \
-        N, M, 0, xyz, rot, idx, dist, c_xyz, c_radius_raw, dxyz, dquat, dL_dmeans3D,                               \
+    if (use_smem && smem > 48 * 1024)                                                                              \
+      DIMO_CHECK_CUDA(cudaFuncSetAttribute(lbs_bwd_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    lbs_bwd_kernel<KK><<<grid, 256, use_smem ? smem : 0, st>>>(                                                    \
+        N, M, use_smem, xyz, rot, idx, dist, c_xyz, c_radius_raw, dxyz, dquat, dL_dmeans3D,                        \
         reinterpret_cast<const float4*>(dL_drotations), dxyz_c, drot_c, dc_xyz, dc_radius_raw, ddxyz, ddquat, det); \
   } break;
     DIMO_LBS_CASE(1) DIMO_LBS_CASE(2) DIMO_LBS_CASE(3) DIMO_LBS_CASE(4)

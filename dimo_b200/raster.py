@@ -186,13 +186,18 @@ class _Rasterize(torch.autograd.Function):
                   _lib.ptr(st.vals_sorted), _lib.ptr(st.ranges), _lib.ptr(st.final_T), _lib.ptr(st.n_contrib), _lib.ptr(g_color),
                   _lib.ptr(g_depth), _lib.ptr(g_normal), _lib.ptr(g_alpha), _lib.ptr(dsplats), s)
         dsplats = _lib.acc_result(dsplats)
-        d_means3D = torch.empty(B, N, 3, **f32)
-        d_means2D = torch.empty(B, N, 3, **f32)
-        d_scales = torch.empty(B, N, 3, **f32)
-        d_rot = torch.empty(B, N, 4, **f32)
-        d_op = torch.empty(B, N, **f32)
         use_sh = shs is not None
-        d_shs = torch.empty(B, N, st.sh_coeffs, 3, **f32) if use_sh else None
+        # parameters shared by all frames (the training step: one set of scales / opacities / SHs): their gradients are
+        # summed over the frames inside the kernel -> [N, *] outputs, no per-frame tensors and no dimo_segment_sum
+        shared = (B > 1 and use_sh and _bstride(scales, B, N * 3) == 0 and _bstride(opacities, B, N) == 0
+                  and _bstride(shs, B, N * st.sh_coeffs * 3) == 0)
+        lead = (N,) if shared else (B, N)
+        d_means3D = torch.empty(B, N, 3, **f32)
+        d_means2D = torch.empty(B, N, 3, **f32) if ctx.needs_input_grad[1] else None
+        d_scales = torch.empty(*lead, 3, **f32)
+        d_rot = torch.empty(B, N, 4, **f32)
+        d_op = torch.empty(*lead, **f32)
+        d_shs = torch.empty(*lead, st.sh_coeffs, 3, **f32) if use_sh else None
         d_col = None if use_sh else torch.empty(B, N, 3, **f32)
         _lib.call("dimo_raster_preprocess_bwd", B, N, W, H, st.sh_degree, st.sh_coeffs, st.scale_modifier, st.act_flags,
                   _lib.ptr(st.cams), _lib.ptr(st.frame_src),
@@ -202,7 +207,8 @@ class _Rasterize(torch.autograd.Function):
                   _lib.ptr(opacities), _bstride(opacities, B, N),
                   _lib.ptr(shs), _bstride(shs, B, N * st.sh_coeffs * 3) if use_sh else 0,
                   _lib.ptr(st.radii), _lib.ptr(dsplats), _lib.ptr(d_means3D), _lib.ptr(d_means2D),
-                  _lib.ptr(d_scales), _lib.ptr(d_rot), _lib.ptr(d_op), _lib.ptr(d_shs), _lib.ptr(d_col), s)
+                  _lib.ptr(d_scales), _lib.ptr(d_rot), _lib.ptr(d_op), _lib.ptr(d_shs), _lib.ptr(d_col),
+                  1 if shared else 0, s)
         sh_m3, sh_m2, sh_sc, sh_rot, sh_op, sh_shs, sh_col = ctx.shapes
 
         def fit(g, shape, per_frame, mapped=False):
@@ -210,6 +216,8 @@ class _Rasterize(torch.autograd.Function):
             frames of each block when it was addressed through frame_src (one dimo_segment_sum launch either way)"""
             if shape is None or g is None:
                 return None
+            if g.numel() == per_frame:         # already summed over the frames by the kernel
+                return g.reshape(shape)
             numel = 1
             for d in shape:
                 numel *= d

@@ -129,8 +129,12 @@ int dimo_raster_blend_bwd(
     float* dL_dsplats, void* stream);
 
 /* Backward of stage 1: per-frame gradients (dense, no atomics):
- *   dL_dmeans3D [B,N,3], dL_dmeans2D [B,N,3] (NDC units, z=0), dL_dscales [B,N,3],
- *   dL_drotations [B,N,4], dL_dopacities [B,N], dL_dshs [B,N,sh_coeffs,3] or dL_dcolors [B,N,3]. */
+ *   dL_dmeans3D [B,N,3], dL_dmeans2D [B,N,3] (NDC units, z=0; may be NULL: not written), dL_dscales [B,N,3],
+ *   dL_drotations [B,N,4], dL_dopacities [B,N], dL_dshs [B,N,sh_coeffs,3] or dL_dcolors [B,N,3].
+ * reduce_shared != 0 (the training step: scales, opacities and shs shared by all frames, i.e. batch strides 0, SH
+ * colours): dL_dscales [N,3], dL_dopacities [N] and dL_dshs [N,sh_coeffs,3] are the SUMS over the B frames, formed in
+ * registers / shared memory in a fixed order (deterministic) instead of being written per frame and folded by
+ * dimo_segment_sum afterwards. */
 int dimo_raster_preprocess_bwd(
     int B, int N, int W, int H, int sh_degree, int sh_coeffs, float scale_modifier, int act_flags,
     const float* cams, const int32_t* frame_src,
@@ -141,7 +145,7 @@ int dimo_raster_preprocess_bwd(
     const float* shs, int64_t shs_bstride,
     const int32_t* radii, const float* dL_dsplats,
     float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dscales, float* dL_drotations,
-    float* dL_dopacities, float* dL_dshs, float* dL_dcolors, void* stream);
+    float* dL_dopacities, float* dL_dshs, float* dL_dcolors, int reduce_shared, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Nearest neighbours (replaces knn_cuda.KNN(k, transpose_mode=True), main_train_dimo.py:505-506,
