@@ -107,6 +107,18 @@ def set_deterministic(on):
     lib().dimo_set_deterministic(1 if on else 0)
 
 
+def grad_sink(p):
+    """The tensor a backward kernel may accumulate (+=) the gradient of parameter `p` into, or None: p.grad when it is a
+    preallocated contiguous fp32 buffer (the views of dist.FlatGradReducer's flat buffer) and the accumulation is fp32
+    (deterministic mode sums in int64 buffers).  Saves the zero-filled temporary and autograd's AccumulateGrad add."""
+    if p is None or not p.requires_grad or not p.is_leaf or deterministic():
+        return None
+    g = p.grad
+    if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.shape != p.shape or not g.is_cuda:
+        return None
+    return g
+
+
 def acc_zeros(shape, device):
     """accumulation target for a backward kernel: fp32 zeros, or int64 zeros in deterministic mode"""
     return torch.zeros(shape, dtype=torch.int64 if deterministic() else torch.float32, device=device)

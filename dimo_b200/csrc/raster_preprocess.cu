@@ -519,7 +519,7 @@ __global__ void __launch_bounds__(32 * FW) preprocess_bwd_shared_kernel(
     const float* __restrict__ rotations, int64_t rot_bs, const float* __restrict__ shs,
     const int32_t* __restrict__ radii, const float4* __restrict__ dL_dsplats,
     float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dmeans2D, float* __restrict__ dL_dscales,
-    float4* __restrict__ dL_drot, float* __restrict__ dL_dop, float* __restrict__ dL_dshs) {
+    float4* __restrict__ dL_drot, float* __restrict__ dL_dop, float* __restrict__ dL_dshs, int accumulate) {
   constexpr int K = (DEG + 1) * (DEG + 1);
   constexpr int V = 4 + 3 * K;                       // dscale (3), dop (1), dsh (3 K)
   __shared__ float red[FW][V][33];
@@ -561,8 +561,8 @@ __global__ void __launch_bounds__(32 * FW) preprocess_bwd_shared_kernel(
     float t = 0.f;
 #pragma unroll
     for (int f = 0; f < FW; ++f) t += red[f][v][il];
-    if (v < 3) dL_dscales[3 * (int64_t)(i0 + il) + v] = t;
-    else dL_dop[i0 + il] = t;
+    float* o = v < 3 ? dL_dscales + 3 * (int64_t)(i0 + il) + v : dL_dop + i0 + il;
+    *o = accumulate ? *o + t : t;
   }
   // SH gradients [N, sh_coeffs, 3]: the CTA's 32 Gaussians are one contiguous block; inactive bands are zero
   const int per = sh_coeffs * 3;
@@ -573,7 +573,9 @@ __global__ void __launch_bounds__(32 * FW) preprocess_bwd_shared_kernel(
 #pragma unroll
       for (int f = 0; f < FW; ++f) t += red[f][4 + v][il];
     }
-    dL_dshs[(int64_t)i0 * per + e] = t;
+    float* o = dL_dshs + (int64_t)i0 * per + e;
+    if (!accumulate) *o = t;
+    else if (v < 3 * K) *o += t;
   }
 }
 
@@ -659,7 +661,8 @@ extern "C" int dimo_raster_preprocess_bwd(
     preprocess_bwd_shared_kernel<D, FW><<<grid, 32 * FW, 0, st>>>(                                                   \
         B, N, W, H, sh_coeffs, scale_modifier, act_flags, opacities, cams, frame_src, means3D, means3D_bstride, scales, \
         rotations, rotations_bstride, shs, radii, reinterpret_cast<const float4*>(dL_dsplats), dL_dmeans3D,          \
-        dL_dmeans2D, dL_dscales, reinterpret_cast<float4*>(dL_drotations), dL_dopacities, dL_dshs);                  \
+        dL_dmeans2D, dL_dscales, reinterpret_cast<float4*>(dL_drotations), dL_dopacities, dL_dshs,                   \
+        reduce_shared == 2);                                                                                         \
     break;
     switch (sh_degree) { DIMO_PRE_BWD_CASE(0) DIMO_PRE_BWD_CASE(1) DIMO_PRE_BWD_CASE(2) DIMO_PRE_BWD_CASE(3) }
 #undef DIMO_PRE_BWD_CASE

@@ -38,8 +38,9 @@ class _TimeNetChainFn(torch.autograd.Function):
     """Same contract as _TimeNetFn; forward and backward are one C-ABI call each (dimo_timenet_fwd / _bwd)."""
 
     @staticmethod
-    def forward(ctx, pts, times, latents, sink, *params):
+    def forward(ctx, pts, times, latents, sink, pts_sink, *params):
         ctx.sink = sink
+        ctx.pts_sink = pts_sink            # (tensor, on_done) or None: d(pts) is accumulated into it
         dev = pts.device
         f32 = dict(dtype=torch.float32, device=dev)
         pts = pts.contiguous().float(); times = times.contiguous().float(); latents = latents.contiguous().float()
@@ -83,26 +84,32 @@ class _TimeNetChainFn(torch.autograd.Function):
             dWs = [_lib.acc_zeros(W.shape, dev) for W in Ws]
             dbs = [_lib.acc_zeros((W.shape[0],), dev) for W in Ws]
         need_pts, need_lat = ctx.needs_input_grad[0], ctx.needs_input_grad[2]
-        dpts = _lib.acc_zeros((M, 3), dev) if need_pts else None
+        pts_sink = ctx.pts_sink if (ctx.pts_sink is not None and need_pts and not det) else None
+        dpts = pts_sink[0] if pts_sink else (_lib.acc_zeros((M, 3), dev) if need_pts else None)
         dlat = _lib.acc_zeros((G, L), dev) if need_lat else None
         wp = (ctypes.c_void_p * 12)(*[w.data_ptr() for w in Ws])
         dwp = (ctypes.c_void_p * 12)(*[w.data_ptr() for w in dWs])
         dbp = (ctypes.c_void_p * 12)(*[b.data_ptr() for b in dbs])
         _lib.call("dimo_timenet_bwd", G, M, L, wp, _lib.ptr(ws), nbytes, _lib.ptr(g_dxyz), _lib.ptr(g_dquat), dwp, dbp,
                   _lib.ptr(dpts), _lib.ptr(dlat), _lib.stream())
-        dpts = _lib.acc_result(dpts) if dpts is not None else None
+        if pts_sink:
+            dpts = None
+            if pts_sink[1] is not None:
+                pts_sink[1]()
+        else:
+            dpts = _lib.acc_result(dpts) if dpts is not None else None
         dlat = _lib.acc_result(dlat) if dlat is not None else None
         if sink is not None:
             if det:
                 for acc, dst in zip(dWs + dbs, list(sink[0::2]) + list(sink[1::2])):
                     _lib.acc_result(acc, into=dst)
-            return (dpts, None, dlat, None, *([None] * (2 * len(Ws))))
+            return (dpts, None, dlat, None, None, *([None] * (2 * len(Ws))))
         dWs = [_lib.acc_result(a) for a in dWs]
         dbs = [_lib.acc_result(a) for a in dbs]
         grads = []
         for W, b in zip(dWs, dbs):
             grads += [W, b]
-        return (dpts, None, dlat, None, *grads)
+        return (dpts, None, dlat, None, None, *grads)
 
 
 def _linear_fwd(R, K, No, X, ldx, W, b, Y, ldy, relu, s):
@@ -325,8 +332,10 @@ class TimeNet(nn.Module):
             ps += [l.weight, l.bias]
         return ps
 
-    def forward_batched(self, pts, times, latents):
-        """pts [M,3]; times [G]; latents [G,L] -> dxyz [G,M,3], dquat [G,M,4] (one launch set for all G)."""
+    def forward_batched(self, pts, times, latents, pts_direct=None):
+        """pts [M,3]; times [G]; latents [G,L] -> dxyz [G,M,3], dquat [G,M,4] (one launch set for all G).
+        pts_direct: None, or a callback: with direct_grads on and `pts` a parameter with a preallocated .grad, d(pts) is
+        accumulated straight into it and pts_direct([pts]) is called afterwards."""
         ps = self.flat_params()
         sink = None
         if self.direct_grads and torch.is_grad_enabled():
@@ -335,7 +344,11 @@ class TimeNet(nn.Module):
                 raise RuntimeError("TimeNet.direct_grads needs every parameter's .grad preallocated (FlatGradReducer)")
         L = latents.shape[1]
         if USE_TC and USE_CHAIN and (72 + L) % 4 == 0 and 72 + L <= 128:
-            return _TimeNetChainFn.apply(pts, times, latents, sink, *ps)
+            pts_sink = None
+            if sink is not None and pts_direct is not None and _lib.grad_sink(pts) is not None and pts.dtype == torch.float32 \
+                    and pts.is_contiguous():
+                pts_sink = (pts.grad, lambda: pts_direct([pts]))
+            return _TimeNetChainFn.apply(pts, times, latents, sink, pts_sink, *ps)
         return _TimeNetFn.apply(pts, times, latents, sink, *ps)
 
     def forward(self, pts, t, latent_code, nobatch=False, t_apply=False):
@@ -360,11 +373,13 @@ class TimeNet(nn.Module):
 
 
 class _LBSFn(torch.autograd.Function):
-    """(xyz [N,3], rot [N,4], c_xyz [M,3], c_radius_raw [M,1], dxyz [G,M,3], dquat [G,M,4], idx, dist)
-    -> means3D [G,N,3], rotations [G,N,4] (normalised).  renderer/latent_gs_renderer.py:1191-1219."""
+    """(xyz [N,3], rot [N,4], c_xyz [M,3], c_radius_raw [M,1], dxyz [G,M,3], dquat [G,M,4], idx, dist, sink)
+    -> means3D [G,N,3], rotations [G,N,4] (normalised).  renderer/latent_gs_renderer.py:1191-1219.
+    `sink`: None, or (grad_xyz, grad_rot, grad_c_xyz, grad_c_radius, on_done): tensors (or None) the backward kernel
+    accumulates into directly instead of fresh zero buffers (autograd then sees no gradient for those inputs)."""
 
     @staticmethod
-    def forward(ctx, xyz, rot, c_xyz, c_radius_raw, dxyz, dquat, idx, dist):
+    def forward(ctx, xyz, rot, c_xyz, c_radius_raw, dxyz, dquat, idx, dist, sink=None):
         c = lambda t: t.contiguous().float()
         xyz, rot, c_xyz, c_radius_raw, dxyz, dquat, dist = map(c, (xyz, rot, c_xyz, c_radius_raw, dxyz, dquat, dist))
         idx = idx.contiguous()
@@ -377,6 +392,7 @@ class _LBSFn(torch.autograd.Function):
                   _lib.ptr(c_xyz), _lib.ptr(c_radius_raw), _lib.ptr(dxyz), _lib.ptr(dquat), _lib.ptr(means3D),
                   _lib.ptr(rotations), _lib.stream())
         ctx.save_for_backward(xyz, rot, c_xyz, c_radius_raw, dxyz, dquat, idx, dist)
+        ctx.sink = sink
         return means3D, rotations
 
     @staticmethod
@@ -384,22 +400,68 @@ class _LBSFn(torch.autograd.Function):
         xyz, rot, c_xyz, c_radius_raw, dxyz, dquat, idx, dist = ctx.saved_tensors
         G, M = dxyz.shape[0], c_xyz.shape[0]
         N, K = idx.shape
+        dev = xyz.device
+        sink = ctx.sink if (ctx.sink is not None and not _lib.deterministic()) else (None, None, None, None, None)
         z = lambda t: _lib.acc_zeros(t.shape, t.device)          # int64 accumulators in deterministic mode
-        d_xyz, d_rot, d_cxyz, d_crad, d_dxyz, d_dquat = z(xyz), z(rot), z(c_xyz), z(c_radius_raw), z(dxyz), z(dquat)
-        g_means3D = g_means3D.contiguous().float() if g_means3D is not None else torch.zeros(G, N, 3, device=xyz.device)
-        g_rot = g_rot.contiguous().float() if g_rot is not None else torch.zeros(G, N, 4, device=xyz.device)
+        outs = [sk if sk is not None else z(t) for sk, t in zip(sink[:4], (xyz, rot, c_xyz, c_radius_raw))]
+        # the two per-frame outputs share one zero fill
+        both = _lib.acc_zeros((G * M * 7,), dev)
+        d_dxyz, d_dquat = both[G * M * 4:].view(G, M, 3), both[:G * M * 4].view(G, M, 4)
+        g_means3D = g_means3D.contiguous().float() if g_means3D is not None else torch.zeros(G, N, 3, device=dev)
+        g_rot = g_rot.contiguous().float() if g_rot is not None else torch.zeros(G, N, 4, device=dev)
         _lib.call("dimo_lbs_bwd", G, N, M, K, _lib.ptr(xyz), _lib.ptr(rot), _lib.ptr(idx), _lib.ptr(dist),
                   _lib.ptr(c_xyz), _lib.ptr(c_radius_raw), _lib.ptr(dxyz), _lib.ptr(dquat), _lib.ptr(g_means3D),
-                  _lib.ptr(g_rot), _lib.ptr(d_xyz), _lib.ptr(d_rot), _lib.ptr(d_cxyz), _lib.ptr(d_crad),
+                  _lib.ptr(g_rot), _lib.ptr(outs[0]), _lib.ptr(outs[1]), _lib.ptr(outs[2]), _lib.ptr(outs[3]),
                   _lib.ptr(d_dxyz), _lib.ptr(d_dquat), _lib.stream())
-        d_xyz, d_rot, d_cxyz, d_crad, d_dxyz, d_dquat = map(_lib.acc_result, (d_xyz, d_rot, d_cxyz, d_crad, d_dxyz, d_dquat))
-        return d_xyz, d_rot, d_cxyz, d_crad, d_dxyz, d_dquat, None, None
+        res = [None if sk is not None else _lib.acc_result(o) for sk, o in zip(sink[:4], outs)]
+        if both.dtype == torch.int64:
+            d_dxyz, d_dquat = _lib.acc_result(d_dxyz.contiguous()), _lib.acc_result(d_dquat.contiguous())
+        if sink[4] is not None:
+            sink[4]()
+        return res[0], res[1], res[2], res[3], d_dxyz, d_dquat, None, None, None
 
 
-def lbs_deform(xyz, rot, c_xyz, c_radius_raw, dxyz, dquat, neighbor_indices, neighbor_dists):
-    """Batched stage-s2 skinning; dxyz/dquat may be [M,*] (one frame) or [G,M,*]."""
+class _GatherRowsFn(torch.autograd.Function):
+    """table.index_select(0, index) whose backward adds the row gradients straight into `sink` (table.grad): one
+    index_add launch instead of zeros + index_add + AccumulateGrad add."""
+
+    @staticmethod
+    def forward(ctx, table, index, sink, on_done):
+        ctx.save_for_backward(index)
+        ctx.sink, ctx.on_done = sink, on_done
+        return table.index_select(0, index)
+
+    @staticmethod
+    def backward(ctx, g):
+        (index,) = ctx.saved_tensors
+        ctx.sink.index_add_(0, index, g)
+        if ctx.on_done is not None:
+            ctx.on_done()
+        return None, None, None, None
+
+
+def gather_rows(table, index, on_done=None):
+    """table[index] (rows); gradients go straight into table.grad when it is preallocated (_lib.grad_sink)."""
+    sink = _lib.grad_sink(table) if torch.is_grad_enabled() else None
+    if sink is None:
+        return table.index_select(0, index)
+    return _GatherRowsFn.apply(table, index, sink, on_done)
+
+
+def lbs_deform(xyz, rot, c_xyz, c_radius_raw, dxyz, dquat, neighbor_indices, neighbor_dists, direct_grads=False,
+               on_done=None):
+    """Batched stage-s2 skinning; dxyz/dquat may be [M,*] (one frame) or [G,M,*].  direct_grads: the backward kernel
+    accumulates the gradients of the four parameters into their preallocated .grad (see _lib.grad_sink) and then calls
+    on_done(list of those parameters)."""
     single = dxyz.dim() == 2
     if single:
         dxyz, dquat = dxyz[None], dquat[None]
-    m, r = _LBSFn.apply(xyz, rot, c_xyz, c_radius_raw, dxyz, dquat, neighbor_indices, neighbor_dists)
+    sink = None
+    if direct_grads and torch.is_grad_enabled():
+        ps = (xyz, rot, c_xyz, c_radius_raw)
+        sk = [_lib.grad_sink(p) for p in ps]
+        if any(t is not None for t in sk):
+            done = [p for p, t in zip(ps, sk) if t is not None]
+            sink = (*sk, (lambda: on_done(done)) if on_done is not None else None)
+    m, r = _LBSFn.apply(xyz, rot, c_xyz, c_radius_raw, dxyz, dquat, neighbor_indices, neighbor_dists, sink)
     return (m[0], r[0]) if single else (m, r)

@@ -95,6 +95,16 @@ class FlatGradReducer:
         self._arrived = 0
         self._work = []
 
+    def direct_written(self, params):
+        """An op accumulated the (final) gradients of `params` straight into their .grad views -- no AccumulateGrad node
+        ran for them, so no post-accumulate hook fires: the same bookkeeping, called by the op's backward."""
+        early = {id(q) for q in self.early}
+        for p in params:
+            if id(p) in early:
+                self._on_early_grad(p)
+            else:
+                self.dirty = True
+
     def _on_early_grad(self, _p):
         self.dirty = True
         self._arrived += 1

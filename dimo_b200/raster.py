@@ -148,11 +148,13 @@ def _forward_impl(cams, means3D, scales, rotations, opacities, shs, colors_preco
 class _Rasterize(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, scales, rotations, opacities, shs, colors_precomp, cams, B, N, W, H,
-                sh_degree, scale_modifier, state_out, capacity, frame_src, n_src, depth_normal=True, act_flags=0):
+                sh_degree, scale_modifier, state_out, capacity, frame_src, n_src, depth_normal=True, act_flags=0,
+                grad_sink=None):
         color, depth, normal, alpha, st = _forward_impl(cams, means3D, scales, rotations, opacities, shs,
                                                         colors_precomp, B, N, W, H, sh_degree, scale_modifier,
                                                         capacity, frame_src, n_src, depth_normal, act_flags)
         ctx.st = st
+        ctx.grad_sink = grad_sink
         ctx.set_materialize_grads(False)     # unused outputs (depth / normal in the image-loss step) arrive as None
         ctx.save_for_backward(means3D, scales, rotations, shs, opacities)
         ctx.shapes = (means3D.shape, None if means2D is None else means2D.shape, scales.shape, rotations.shape,
@@ -192,12 +194,16 @@ class _Rasterize(torch.autograd.Function):
         shared = (B > 1 and use_sh and _bstride(scales, B, N * 3) == 0 and _bstride(opacities, B, N) == 0
                   and _bstride(shs, B, N * st.sh_coeffs * 3) == 0)
         lead = (N,) if shared else (B, N)
+        # grad_sink = (scales.grad, opacities.grad, shs.grad, on_done): the kernel adds the frame sums straight into the
+        # parameters' gradient buffers (all three or none)
+        sink = ctx.grad_sink if (shared and ctx.grad_sink is not None and not _lib.deterministic()
+                                 and all(t is not None for t in ctx.grad_sink[:3])) else None
         d_means3D = torch.empty(B, N, 3, **f32)
         d_means2D = torch.empty(B, N, 3, **f32) if ctx.needs_input_grad[1] else None
-        d_scales = torch.empty(*lead, 3, **f32)
+        d_scales = sink[0] if sink else torch.empty(*lead, 3, **f32)
         d_rot = torch.empty(B, N, 4, **f32)
-        d_op = torch.empty(*lead, **f32)
-        d_shs = torch.empty(*lead, st.sh_coeffs, 3, **f32) if use_sh else None
+        d_op = sink[1] if sink else torch.empty(*lead, **f32)
+        d_shs = sink[2] if sink else (torch.empty(*lead, st.sh_coeffs, 3, **f32) if use_sh else None)
         d_col = None if use_sh else torch.empty(B, N, 3, **f32)
         _lib.call("dimo_raster_preprocess_bwd", B, N, W, H, st.sh_degree, st.sh_coeffs, st.scale_modifier, st.act_flags,
                   _lib.ptr(st.cams), _lib.ptr(st.frame_src),
@@ -208,7 +214,11 @@ class _Rasterize(torch.autograd.Function):
                   _lib.ptr(shs), _bstride(shs, B, N * st.sh_coeffs * 3) if use_sh else 0,
                   _lib.ptr(st.radii), _lib.ptr(dsplats), _lib.ptr(d_means3D), _lib.ptr(d_means2D),
                   _lib.ptr(d_scales), _lib.ptr(d_rot), _lib.ptr(d_op), _lib.ptr(d_shs), _lib.ptr(d_col),
-                  1 if shared else 0, s)
+                  (2 if sink else 1) if shared else 0, s)
+        if sink:
+            d_scales = d_op = d_shs = None
+            if sink[3] is not None:
+                sink[3]()
         sh_m3, sh_m2, sh_sc, sh_rot, sh_op, sh_shs, sh_col = ctx.shapes
 
         def fit(g, shape, per_frame, mapped=False):
@@ -236,18 +246,20 @@ class _Rasterize(torch.autograd.Function):
                 fit(d_scales, sh_sc, N * 3), fit(d_rot, sh_rot, N * 4, True), fit(d_op, sh_op, N),
                 fit(d_shs, sh_shs, N * st.sh_coeffs * 3) if use_sh else None,
                 fit(d_col, sh_col, N * 3) if not use_sh else None,
-                None, None, None, None, None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None, None, None, None, None)
 
 
 def rasterize_batch(cams, means3D, scales, rotations, opacities, W, H, shs=None, colors_precomp=None,
                     sh_degree=0, scale_modifier=1.0, means2D=None, state_out=None, capacity=None, frame_src=None,
-                    depth_normal=True, raw_activations=False):
+                    depth_normal=True, raw_activations=False, direct_grads=False, on_done=None):
     """cams [B,40]; means3D [B,N,3] or [N,3]; scales [N,3]; rotations [B,N,4] or [N,4]; opacities [N,1]/[N];
     shs [N,K,3] xor colors_precomp [B?,N,3].  frame_src [B] int32 (device): means3D / rotations are [U,N,*] and
     frame b uses block frame_src[b] (frames that differ only in the view share one deformation).
     depth_normal=False: depth and normal are not rendered (returned as None).
     raw_activations=True (or a bit mask: 1 = scales, 2 = opacities): `scales` are log-scales and `opacities` logits (the model's raw _scaling / _opacity); exp and
     sigmoid run inside the projection kernels and the gradients come back w.r.t. the raw parameters.
+    direct_grads: when scales, opacities and shs are leaf parameters shared by all frames whose .grad is preallocated
+    (_lib.grad_sink), the backward adds their gradients straight into it and calls on_done([the three parameters]).
     Returns color [B,3,H,W], depth [B,1,H,W], normal [B,3,H,W], alpha [B,1,H,W], radii [B,N] int32."""
     if (shs is None) == (colors_precomp is None):
         raise ValueError("Please provide exactly one of either SHs or precomputed colors!")
@@ -260,7 +272,13 @@ def rasterize_batch(cams, means3D, scales, rotations, opacities, W, H, shs=None,
         n_src = int(means3D.shape[0])
         if B > 1024:
             raise ValueError("frame_src supports at most 1024 frames per launch set")
+    sink = None
+    if direct_grads and torch.is_grad_enabled() and shs is not None:
+        ps = (scales, opacities, shs)
+        sk = [_lib.grad_sink(p) if (p.dtype == torch.float32 and p.is_contiguous()) else None for p in ps]
+        if all(t is not None for t in sk):
+            sink = (*sk, (lambda: on_done(list(ps))) if on_done is not None else None)
     return _Rasterize.apply(c(means3D), means2D, c(scales), c(rotations), c(opacities), c(shs), c(colors_precomp),
                             cams.contiguous(), B, N, int(W), int(H), int(sh_degree), float(scale_modifier), state_out,
                             capacity, frame_src, n_src, bool(depth_normal),
-                            (3 if raw_activations is True else int(raw_activations or 0)))
+                            (3 if raw_activations is True else int(raw_activations or 0)), sink)

@@ -100,44 +100,106 @@ class Renderer:
         return _reg.arap_loss_points(means3D_t)
 
     # ------------------------------------------------------------------------------------------
+    def _camera_row(self, c):
+        """35 host floats of one camera (view 16 | full projection 16 | centre 3), cached on the camera object: cameras
+        are reused step after step, so the device->host read happens once per camera, not once per step."""
+        row = getattr(c, "_dimo_row", None)
+        if row is None:
+            row = torch.cat([c.world_view_transform.reshape(-1).float().cpu(), c.full_proj_transform.reshape(-1).float().cpu(),
+                             c.camera_center.reshape(-1).float().cpu()]).numpy().copy()
+            try:
+                c._dimo_row = row
+            except Exception:
+                pass
+        return row
+
     def prepare_step(self, cameras, times, latent_indices, bg_color=None, out=None):
-        """Host-side packing of one step's frame list into device tensors (no kernels of ours, no host sync):
-        cams [S,40], t [U], li [U] i64, pf [S] i64 where U = unique (motion, t) pairs (the deformation is
-        view-independent) and pf maps frame -> pair.  `out`: an earlier result whose tensors are
+        """Host-side packing of one step's frame list: cams [S,40], t [U], li [U] i64, pf [S] i64, pf32 [S] i32 where
+        U = unique (motion, t) pairs (the deformation is view-independent) and pf maps frame -> pair.
+        Everything is laid out in ONE pinned host buffer and reaches the device with one asynchronous copy (no kernels,
+        no host sync); the returned tensors are views of the device buffer.  `out`: an earlier result whose buffer is
         overwritten in place (static buffers for CUDA-graph replay; U and S must not change)."""
         dev = self.gaussians._xyz.device
         pairs, pair_of_frame = {}, []
         for t, li in zip(times, latent_indices):
             pair_of_frame.append(pairs.setdefault((int(li), float(t)), len(pairs)))
         keys = list(pairs.keys())
+        S, U = len(cameras), len(keys)
         bg = self.bg_color if bg_color is None else bg_color
-        V = torch.stack([c.world_view_transform for c in cameras]).reshape(-1, 16).float()
-        P = torch.stack([c.full_proj_transform for c in cameras]).reshape(-1, 16).float()
-        C = torch.stack([c.camera_center for c in cameras]).float()
-        S = len(cameras)
-        host = torch.empty(S, 3, dtype=torch.float32)                  # tanfovx, tanfovy, pair index
+        if bg is self.bg_color:
+            cache = getattr(self, "_bg_host", None)
+            if cache is None or cache[0] is not bg:
+                cache = (bg, bg.detach().float().cpu().reshape(3).numpy().copy())
+                self._bg_host = cache
+            bg_host = cache[1]
+        else:
+            bg_host = bg.detach().float().cpu().reshape(3).numpy()
+        o_t, o_li, o_pf, o_pf32, nbytes = self._prep_layout(S, U)
+        ring = getattr(self, "_prep_ring", None)
+        if ring is None or ring["nbytes"] != nbytes:
+            ring = {"nbytes": nbytes, "slot": 0, "host": [torch.zeros(nbytes, dtype=torch.uint8).pin_memory()
+                                                          if torch.cuda.is_available() and dev.type == "cuda"
+                                                          else torch.zeros(nbytes, dtype=torch.uint8) for _ in range(4)],
+                    "events": [None] * 4}
+            self._prep_ring = ring
+        k = ring["slot"]
+        ring["slot"] = (k + 1) % 4
+        if ring["events"][k] is not None:                # the copy that last used this staging slot has to be done
+            ring["events"][k].synchronize()
+        hb = ring["host"][k]
+        hn = hb.numpy()
+        cams_h = hn[:o_t].view(np.float32).reshape(S, 40)
         for i, c in enumerate(cameras):
-            host[i, 0] = math.tan(c.FoVx * 0.5); host[i, 1] = math.tan(c.FoVy * 0.5)
-        host[:, 2] = torch.tensor(pair_of_frame, dtype=torch.float32)
-        small = host.to(dev, non_blocking=True)
-        bgd = bg.to(dev).float().reshape(1, 3).expand(S, 3)
-        cams = torch.cat([V, P, C, small[:, 0:2], bgd], dim=1)
-        th = torch.tensor([[k[1], float(k[0])] for k in keys], dtype=torch.float32).to(dev, non_blocking=True)
-        prep = {"cams": cams, "t": th[:, 0].contiguous(), "li": th[:, 1].long(), "pf": small[:, 2].long(),
-                "pf32": small[:, 2].int(),
-                "S": S, "U": len(keys), "W": int(cameras[0].image_width), "H": int(cameras[0].image_height),
-                "pair_of_frame": pair_of_frame, "expand": pair_of_frame != list(range(S))}
+            cams_h[i, :35] = self._camera_row(c)
+            cams_h[i, 35] = math.tan(c.FoVx * 0.5); cams_h[i, 36] = math.tan(c.FoVy * 0.5)
+            cams_h[i, 37:40] = bg_host
+        hn[o_t:o_t + U * 4].view(np.float32)[:] = [k_[1] for k_ in keys]
+        hn[o_li:o_pf].view(np.int64)[:] = [k_[0] for k_ in keys]
+        hn[o_pf:o_pf32].view(np.int64)[:] = pair_of_frame
+        hn[o_pf32:nbytes].view(np.int32)[:] = pair_of_frame
         if out is not None:
-            assert out["S"] == prep["S"] and out["U"] == prep["U"] and out["expand"] == prep["expand"]
-            for k in ("cams", "t", "li", "pf", "pf32"):
-                out[k].copy_(prep[k])
+            assert out["S"] == S and out["U"] == U and out["expand"] == (pair_of_frame != list(range(S)))
+            buf = out["_buf"]
+        else:
+            buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        buf.copy_(hb, non_blocking=True)
+        if dev.type == "cuda":
+            ev = torch.cuda.Event()
+            ev.record()
+            ring["events"][k] = ev
+        if out is not None:
             out["pair_of_frame"] = pair_of_frame
             return out
+        prep = {"S": S, "U": U, "W": int(cameras[0].image_width), "H": int(cameras[0].image_height),
+                "pair_of_frame": pair_of_frame, "expand": pair_of_frame != list(range(S))}
+        return self._prep_views(prep, buf)
+
+    @staticmethod
+    def _prep_layout(S, U):
+        """byte layout (8-byte aligned sections): cams f32 [S,40] | t f32 [U] (+pad) | li i64 [U] | pf i64 [S] | pf32 i32 [S]"""
+        o_t = S * 40 * 4
+        o_li = o_t + (U * 4 + 7) // 8 * 8
+        o_pf = o_li + U * 8
+        o_pf32 = o_pf + S * 8
+        return o_t, o_li, o_pf, o_pf32, o_pf32 + S * 4
+
+    @classmethod
+    def _prep_views(cls, prep, buf):
+        S, U = prep["S"], prep["U"]
+        o_t, o_li, o_pf, o_pf32, nbytes = cls._prep_layout(S, U)
+        prep.update({"_buf": buf, "cams": buf[:o_t].view(torch.float32).view(S, 40),
+                     "t": buf[o_t:o_t + U * 4].view(torch.float32), "li": buf[o_li:o_pf].view(torch.int64),
+                     "pf": buf[o_pf:o_pf32].view(torch.int64), "pf32": buf[o_pf32:nbytes].view(torch.int32)})
         return prep
+
+    @classmethod
+    def clone_prep(cls, prep):
+        """Deep copy of a prepare_step() result (own device buffer): the static inputs of a captured graph."""
+        return cls._prep_views({k: v for k, v in prep.items() if not torch.is_tensor(v)}, prep["_buf"].clone())
 
     def render_batch(self, cameras=None, times=None, latent_indices=None, stage="s2", scaling_modifier=1.0,
                      bg_color=None, override_color=None, xyz_detach=False, clamp=True, prepared=None, capacity=None,
-                     with_visibility=True, depth_normal=True):
+                     with_visibility=True, depth_normal=True, with_cpts=True):
         """All S frames of a step in ONE launch set.  cameras: list of S MiniCam (same W,H); times: list of S floats;
         latent_indices: list of S ints -- or `prepared` = the result of prepare_step().  capacity: instance-slot
         capacity for the sync-free rasteriser mode (None = exact mode with one host read-back).  depth_normal=False:
@@ -148,16 +210,24 @@ class Renderer:
         g = self.gaussians
         prep = prepared if prepared is not None else self.prepare_step(cameras, times, latent_indices, bg_color)
         W, H = prep["W"], prep["H"]
+        # direct_grads (set by trainstep.TrainStep): backward kernels add parameter gradients straight into the flat
+        # gradient buffer's views (_lib.grad_sink) and tell the reducer, instead of zero-filled temporaries + one
+        # AccumulateGrad add per parameter (~20 small launches per step)
+        direct = bool(getattr(self, "direct_grads", False)) and torch.is_grad_enabled()
+        reducer = getattr(g, "reducer", None)
+        done = (reducer.direct_written if reducer is not None else (lambda ps: None)) if direct else None
         if self.vae_latent:                                                  # one reparameterised draw per pair
             latents = self.reparameterize(g._mu.index_select(0, prep["li"]), g._log_var.index_select(0, prep["li"]))
+        elif direct:
+            latents = _deform.gather_rows(g._latent_codes, prep["li"], lambda: done([g._latent_codes]))
         else:
             latents = g._latent_codes.index_select(0, prep["li"])           # [U,L]
         t_dev = prep["t"]
         if stage >= "s2":
-            dxyz, dquat = g._timenet.forward_batched(g._c_xyz, t_dev, latents)   # [U,M,3],[U,M,4]
-            cpts_t = g._c_xyz[None] + dxyz
+            dxyz, dquat = g._timenet.forward_batched(g._c_xyz, t_dev, latents, pts_direct=done)   # [U,M,3],[U,M,4]
+            cpts_t = g._c_xyz[None] + dxyz if with_cpts else None
             means3D_u, rot_u = _deform.lbs_deform(g._xyz, g._rotation, g._c_xyz, g._c_radius, dxyz, dquat,
-                                                  g.neighbor_indices, g.neighbor_dists)
+                                                  g.neighbor_indices, g.neighbor_dists, direct_grads=direct, on_done=done)
         elif stage == "s1":
             dxyz, dquat = g._timenet.forward_batched(g._xyz, t_dev, latents)
             cpts_t = g._xyz[None] + dxyz
@@ -185,7 +255,8 @@ class Renderer:
         color, depth, normal, alpha, radii = _raster.rasterize_batch(
             prep["cams"], means3D, g._scaling if own_scales else g.get_scaling, rotations, g._opacity, W, H, shs=shs,
             colors_precomp=colors, sh_degree=g.active_sh_degree, scale_modifier=scaling_modifier, state_out=state,
-            capacity=capacity, frame_src=frame_src, depth_normal=depth_normal, raw_activations=(1 if own_scales else 0) | 2)
+            capacity=capacity, frame_src=frame_src, depth_normal=depth_normal, raw_activations=(1 if own_scales else 0) | 2,
+            direct_grads=direct, on_done=done)
         return {"image": color.clamp(0, 1) if clamp else None, "image_raw": color, "depth": depth, "normal": normal,
                 "alpha": alpha, "radii": radii, "visibility_filter": (radii > 0) if with_visibility else None,
                 "pts_t": means3D, "cpts_t": cpts_t, "pair_of_frame": prep["pair_of_frame"], "raster_state": state[0]}

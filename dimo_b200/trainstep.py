@@ -127,6 +127,8 @@ class TrainStep:
         g.optimizer = self.opt
         # TimeNet's weight gradients are accumulated by the kernels straight into the flat buffer
         g._timenet.direct_grads = True
+        # ... and so are the gradients of the Gaussian / control-point / latent parameters (renderer.render_batch)
+        renderer.direct_grads = self.fused_opt
         self.frame_w = None           # optional [S] device tensor: per-frame MSE weights (main_train_dimo.py:333-336)
         # depth / normal smoothness terms of the real step (main_train_dimo.py:363-372); off in the north-star step
         self.regularisers = bool(regularisers)
@@ -184,7 +186,7 @@ class TrainStep:
             self.g.find_knn(4)
         # the loss kernel clamps the render to [0,1] on load (and masks the gradient), so skip the separate clamp pass
         out = self.r.render_batch(prepared=prep, stage=self.stage, clamp=False, capacity=capacity,
-                                  with_visibility=False, depth_normal=self.regularisers)
+                                  with_visibility=False, depth_normal=self.regularisers, with_cpts=False)
         st = out["raster_state"]
         if capacity is None:
             self._max_R = max(self._max_R, st.R)
@@ -212,7 +214,7 @@ class TrainStep:
     def _capture(self, prep, gt, mask, n_motions, optimize):
         dev = gt.device
         self.capacity = int(self._max_R * self.capacity_margin) + 1024
-        self._static = {"prep": {k: (v.clone() if torch.is_tensor(v) else v) for k, v in prep.items()},
+        self._static = {"prep": self.r.clone_prep(prep),
                         "gt": gt.clone(), "mask": mask.clone(),
                         "overflow": torch.zeros(2, dtype=torch.int32, device=dev), "n_motions": n_motions,
                         "optimize": optimize}
@@ -343,7 +345,7 @@ class RenderStep:
     def _body(self, prep, capacity=None):
         with torch.no_grad():
             out = self.r.render_batch(prepared=prep, stage=self.stage, clamp=True, capacity=capacity,
-                                      with_visibility=False, depth_normal=self.depth_normal)
+                                      with_visibility=False, depth_normal=self.depth_normal, with_cpts=False)
         st = out["raster_state"]
         if capacity is None:
             self._max_R = max(self._max_R, st.R)
@@ -358,7 +360,7 @@ class RenderStep:
                 self._seen += 1
                 return self._body(prep)[0]
             self.capacity = int(self._max_R * self.capacity_margin) + 1024
-            self._static = {"prep": {k: (v.clone() if torch.is_tensor(v) else v) for k, v in prep.items()},
+            self._static = {"prep": self.r.clone_prep(prep),
                             "overflow": torch.zeros(2, dtype=torch.int32, device=prep["cams"].device)}
             stt = self._static
             side = torch.cuda.Stream()

@@ -134,7 +134,8 @@ int dimo_raster_blend_bwd(
  * reduce_shared != 0 (the training step: scales, opacities and shs shared by all frames, i.e. batch strides 0, SH
  * colours): dL_dscales [N,3], dL_dopacities [N] and dL_dshs [N,sh_coeffs,3] are the SUMS over the B frames, formed in
  * registers / shared memory in a fixed order (deterministic) instead of being written per frame and folded by
- * dimo_segment_sum afterwards. */
+ * dimo_segment_sum afterwards.  reduce_shared == 2: the three sums are ADDED to what the buffers hold (the caller's
+ * gradient buffers) instead of overwriting them. */
 int dimo_raster_preprocess_bwd(
     int B, int N, int W, int H, int sh_degree, int sh_coeffs, float scale_modifier, int act_flags,
     const float* cams, const int32_t* frame_src,
