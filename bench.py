@@ -54,6 +54,7 @@ def parse():
                          "the first block alone is reported as `burst`")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="diagnostics: do not poll nvidia-smi during the timed region")
     ap.add_argument("--e2e-gt", default="u8", choices=["u8", "f32"],
                     help="ground truth crossing PCIe every step: u8 = the 8-bit samples it was decoded from, converted on "
                          "the device by dimo_gt_fetch (GroundTruthCache semantics); f32 = the reference's host floats")
@@ -361,6 +362,7 @@ def run_ours(args, wl):
         torch.cuda.synchronize()
 
     counter = [0]
+    host_ms = [0.0]
 
     def timed(e2e, steps, warmup, profile=False):
         """`warmup` untimed steps, then EXACTLY `steps` timed steps between barrier + synchronize, CUDA events on the
@@ -372,8 +374,10 @@ def run_ours(args, wl):
             _lib.PROFILE.reset(enabled=True)
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
+        t_host = time.perf_counter()
         for _ in range(steps):
             one_step(counter[0], e2e); counter[0] += 1
+        host_ms[0] = (time.perf_counter() - t_host) * 1000.0 / max(steps, 1)     # host time to ISSUE one step
         if e2e and loss_events:          # lagged reads: the last step's loss is read before the clock stops
             for ev, slot_l in loss_events.values():
                 ev.synchronize()
@@ -393,7 +397,7 @@ def run_ours(args, wl):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local) if (rank == 0 and not args.no_clocks) else None
     # graph mode needs probe steps (eager, to learn the instance capacity) + the capture itself before the timed region
     extra_warm = (ts.probe_steps + 1) if ts.use_graph else 0
     ms_burst = timed(False, args.steps, args.warmup + extra_warm)          # the first K-step block on a cool GPU
@@ -403,6 +407,7 @@ def run_ours(args, wl):
     if sampler:
         sampler.start()
     ms = timed(False, args.steps * blocks, 0)
+    host_issue_ms = host_ms[0]
     clocks = sampler.stop() if sampler else None
     timed_steps = args.steps * blocks
     value = world * S * timed_steps / (ms / 1000.0)
@@ -492,6 +497,7 @@ def run_ours(args, wl):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(wl),
             "timing": {"timed_steps": timed_steps, "timed_region_s": ms / 1000.0, "blocks_of_steps": blocks,
+                       "host_issue_ms_per_step": host_issue_ms,
                        "burst": {"steps": args.steps, "ms_per_step": ms_burst / args.steps,
                                  "value": world * S * args.steps / (ms_burst / 1000.0)}},
             "impl_detail": {

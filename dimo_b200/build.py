@@ -24,6 +24,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
 # radii / tile rectangles / sort keys / neighbour indices).
 SOURCES = {
     "raster_preprocess.cu": ["-fmad=false"],
+    "raster_preprocess_bwd.cu": [],
     "raster_bin.cu": [],
     "raster_blend.cu": [],
     "knn.cu": ["-fmad=false"],

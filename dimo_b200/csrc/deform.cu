@@ -8,7 +8,7 @@
 // xyz 12 + rot 16 + idx 32 + dist 16 B per Gaussian once per block column and writes 28 B per
 // (frame, Gaussian); the M x 11-float control tables stay in L1/L2.
 //
-// Backward accumulates control-point gradients in a shared-memory table (M x 11 floats) per CTA and
+// Backward accumulates control-point gradients in a shared-memory table (M x 8 floats) per CTA and
 // flushes once, instead of N*K*11 contended global atomics on 512 addresses.  (Measured alternative, round 2: one thread
 // per Gaussian x 4 frames with frame-invariant work hoisted and 128-bit REDs straight to global memory -- 339 us against
 // 164 us for this kernel at 16 x 100k x K=4: the L2 serialises the ~3000 adds per control-point address.)
@@ -98,8 +98,9 @@ __global__ void __launch_bounds__(256) lbs_fwd_kernel(
   rotations[o] = make_float4(u.r / un, u.x / un, u.y / un, u.z / un);
 }
 
-// control-table gradient slots: [0:3) ddxyz  [3:7) ddquat  [7:10) dc_xyz  [10] dc_radius_raw
-constexpr int CT = 11;
+// control-table gradient slots: [0:3) ddxyz  [3:7) ddquat  [7] dc_radius_raw.  The control-point position gradient needs
+// no slots of its own: sum_i wn (g - R^T g) = (I - R^T) sum_i wn g = (I - R_bj^T) ddxyz_bj, formed when the table is flushed.
+constexpr int CT = 9;        // 8 used + 1 pad: an odd row stride spreads the rows over the shared-memory banks
 
 template <int K>
 __global__ void __launch_bounds__(256) lbs_bwd_kernel(
@@ -213,7 +214,6 @@ __global__ void __launch_bounds__(256) lbs_bwd_kernel(
         float* tj = tab + j * CT;
         atomicAdd(tj + 0, wn * gx); atomicAdd(tj + 1, wn * gy); atomicAdd(tj + 2, wn * gz);
         atomicAdd(tj + 3, gdq0); atomicAdd(tj + 4, gdq1); atomicAdd(tj + 5, gdq2); atomicAdd(tj + 6, gdq3);
-        atomicAdd(tj + 7, wn * (gx - rtg[0])); atomicAdd(tj + 8, wn * (gy - rtg[1])); atomicAdd(tj + 9, wn * (gz - rtg[2]));
       } else {
         acc_add(ddxyz, ox + 3 * j + 0, wn * gx, det); acc_add(ddxyz, ox + 3 * j + 1, wn * gy, det);
         acc_add(ddxyz, ox + 3 * j + 2, wn * gz, det);
@@ -232,20 +232,30 @@ __global__ void __launch_bounds__(256) lbs_bwd_kernel(
       const float gw = (gwn[k] - dotw) / S;
       const float d = dist[(int64_t)i * K + k];
       const float graw = gw * e[k] * (d * d) / (rad[k] * rad[k]);   // dw/dr * r = e * d^2 / r^2
-      if (use_smem) atomicAdd(tab + nb[k] * CT + 10, graw);
+      if (use_smem) atomicAdd(tab + nb[k] * CT + 7, graw);
       else acc_add(dc_radius_raw, nb[k], graw, det);
     }
   }
   if (use_smem) {
     __syncthreads();
-    for (int e2 = threadIdx.x; e2 < M * CT; e2 += blockDim.x) {
-      const float val = tab[e2];
-      if (val == 0.f) continue;
-      const int j = e2 / CT, q = e2 - j * CT;
-      if (q < 3) atomicAdd(ddx_b + 3 * j + q, val);
-      else if (q < 7) atomicAdd(ddq_b + 4 * j + (q - 3), val);
-      else if (q < 10) atomicAdd(dc_xyz + 3 * j + (q - 7), val);
-      else atomicAdd(dc_radius_raw + j, val);
+    for (int j = threadIdx.x; j < M; j += blockDim.x) {
+      const float* tj = tab + j * CT;
+      const float sx = tj[0], sy = tj[1], sz = tj[2];
+      if (sx != 0.f || sy != 0.f || sz != 0.f) {
+        atomicAdd(ddx_b + 3 * j, sx); atomicAdd(ddx_b + 3 * j + 1, sy); atomicAdd(ddx_b + 3 * j + 2, sz);
+        const float4 dq = *reinterpret_cast<const float4*>(dq_b + 4 * (int64_t)j);
+        const float nrm = sqrtf(dq.x * dq.x + dq.y * dq.y + dq.z * dq.z + dq.w * dq.w);
+        const Quat qn = {dq.x / nrm, dq.y / nrm, dq.z / nrm, dq.w / nrm};
+        float R[3][3];
+        rot_from_unit(qn, R);
+        atomicAdd(dc_xyz + 3 * j, sx - (R[0][0] * sx + R[1][0] * sy + R[2][0] * sz));
+        atomicAdd(dc_xyz + 3 * j + 1, sy - (R[0][1] * sx + R[1][1] * sy + R[2][1] * sz));
+        atomicAdd(dc_xyz + 3 * j + 2, sz - (R[0][2] * sx + R[1][2] * sy + R[2][2] * sz));
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (tj[3 + q] != 0.f) atomicAdd(ddq_b + 4 * j + q, tj[3 + q]);
+      if (tj[7] != 0.f) atomicAdd(dc_radius_raw + j, tj[7]);
     }
   }
 }

@@ -8,6 +8,7 @@ rasterisation batched over all frames.  `initialize` / `initialize_ag` / `arap_l
 the class surface main_train_dimo.py and main_test_dimo.py use.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -137,8 +138,8 @@ class Renderer:
         o_t, o_li, o_pf, o_pf32, nbytes = self._prep_layout(S, U)
         ring = getattr(self, "_prep_ring", None)
         if ring is None or ring["nbytes"] != nbytes:
-            ring = {"nbytes": nbytes, "slot": 0, "host": [torch.zeros(nbytes, dtype=torch.uint8).pin_memory()
-                                                          if torch.cuda.is_available() and dev.type == "cuda"
+            pin = torch.cuda.is_available() and dev.type == "cuda" and not os.environ.get("DIMO_PREP_PAGEABLE")
+            ring = {"nbytes": nbytes, "slot": 0, "host": [torch.zeros(nbytes, dtype=torch.uint8).pin_memory() if pin
                                                           else torch.zeros(nbytes, dtype=torch.uint8) for _ in range(4)],
                     "events": [None] * 4}
             self._prep_ring = ring
