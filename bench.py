@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="diagnostics: do not poll nvidia-smi during the timed region")
+    ap.add_argument("--step-events", action="store_true",
+                    help="diagnostics: one CUDA event per step in the timed region, per-step statistics on stderr")
     ap.add_argument("--e2e-gt", default="u8", choices=["u8", "f32"],
                     help="ground truth crossing PCIe every step: u8 = the 8-bit samples it was decoded from, converted on "
                          "the device by dimo_gt_fetch (GroundTruthCache semantics); f32 = the reference's host floats")
@@ -375,8 +377,11 @@ def run_ours(args, wl):
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
         t_host = time.perf_counter()
+        marks = []
         for _ in range(steps):
             one_step(counter[0], e2e); counter[0] += 1
+            if args.step_events:
+                ev = torch.cuda.Event(enable_timing=True); ev.record(); marks.append((ev, time.perf_counter()))
         host_ms[0] = (time.perf_counter() - t_host) * 1000.0 / max(steps, 1)     # host time to ISSUE one step
         if e2e and loss_events:          # lagged reads: the last step's loss is read before the clock stops
             for ev, slot_l in loss_events.values():
@@ -390,6 +395,12 @@ def run_ours(args, wl):
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
+        if args.step_events and len(marks) > 2:
+            d = sorted(marks[k][0].elapsed_time(marks[k + 1][0]) for k in range(len(marks) - 1))
+            h = sorted((marks[k + 1][1] - marks[k][1]) * 1000.0 for k in range(len(marks) - 1))
+            q = lambda a, f: a[min(len(a) - 1, int(f * len(a)))]
+            print(f"[step-events] n={len(d)} gpu ms/step p10 {q(d, .1):.3f} p50 {q(d, .5):.3f} p90 {q(d, .9):.3f} max {d[-1]:.3f} | "
+                  f"host ms/step p10 {q(h, .1):.3f} p50 {q(h, .5):.3f} p90 {q(h, .9):.3f} max {h[-1]:.3f}", file=sys.stderr)
         if profile:
             _lib.PROFILE.enabled = False
         t = torch.tensor([ms], device=dev)
