@@ -125,36 +125,84 @@ def step_schedule(wl, step, rank=0, world=1):
 
 
 class ClockSampler(threading.Thread):
+    """SM clock, power draw and throttle reasons sampled DURING the timed region: NVML every 20 ms when the binding is
+    importable (nvidia_ml_py), else one nvidia-smi query per ~0.1 s."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
     def __init__(self, index=0):
         super().__init__(daemon=True)
         self.index = index
-        self.samples, self.reasons = [], set()
+        self.samples, self.power, self.reasons = [], [], set()
         self.max_mhz = None
+        self.source = None
         self._halt = threading.Event()
 
-    def run(self):
-        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+    def _run_nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        # NVML enumerates physical GPUs: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        idx = self.index
+        try:
+            ids = [int(x) for x in vis.split(",") if x.strip() != ""]
+            if ids:
+                idx = ids[self.index]
+        except ValueError:
+            pass
+        h = nv.nvmlDeviceGetHandleByIndex(idx)
+        self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        self.source = "nvml"
+        while not self._halt.is_set():
+            self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            try:
+                self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for n, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._halt.wait(0.02)
+
+    def _run_smi(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        self.source = "nvidia-smi"
         while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
                                       str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
                 f = [x.strip() for x in out.split(",")]
                 self.samples.append(float(f[0])); self.max_mhz = float(f[1])
-                for n, v in zip(names, f[2:]):
+                try:
+                    self.power.append(float(f[2]))
+                except ValueError:
+                    pass
+                for n, v in zip(self.NAMES, f[3:]):
                     if v.lower().startswith("active"):
                         self.reasons.add(n)
             except Exception:
                 pass
             self._halt.wait(0.05)
 
+    def run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            if not self._halt.is_set():
+                self._run_smi()
+
     def stop(self):
         self._halt.set()
         self.join(timeout=2)
-        s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+        s, pw = sorted(self.samples), sorted(self.power)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_mhz_min": s[0] if s else None, "sm_max_mhz": self.max_mhz,
+                "power_w": pw[len(pw) // 2] if pw else None, "power_w_max": pw[-1] if pw else None,
+                "reasons": sorted(self.reasons), "samples": len(s), "source": self.source}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -396,7 +444,12 @@ def run_ours(args, wl):
         barrier()
         ms = e0.elapsed_time(e1)
         if args.step_events and len(marks) > 2:
-            d = sorted(marks[k][0].elapsed_time(marks[k + 1][0]) for k in range(len(marks) - 1))
+            series = [marks[k][0].elapsed_time(marks[k + 1][0]) for k in range(len(marks) - 1)]
+            n10 = max(1, len(series) // 10)
+            print("[step-events] mean gpu ms/step per tenth of the region: " +
+                  " ".join(f"{sum(series[k:k + n10]) / len(series[k:k + n10]):.3f}" for k in range(0, len(series), n10)),
+                  file=sys.stderr)
+            d = sorted(series)
             h = sorted((marks[k + 1][1] - marks[k][1]) * 1000.0 for k in range(len(marks) - 1))
             q = lambda a, f: a[min(len(a) - 1, int(f * len(a)))]
             print(f"[step-events] n={len(d)} gpu ms/step p10 {q(d, .1):.3f} p50 {q(d, .5):.3f} p90 {q(d, .9):.3f} max {d[-1]:.3f} | "
