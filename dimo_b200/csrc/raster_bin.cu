@@ -18,8 +18,8 @@
 //                              array (4 shared-memory increments per splat) + prefix sums, no per-instance work;
 //        tile_chunk_scan / tile_base_scan   exclusive prefix over chunks per tile, then over tiles: every tile's
 //                              [begin, end) range and every chunk's first slot in every tile (+ overflow flag);
-//        tile_scatter_kernel   every warp walks the instances of its splats in depth order, 32 at a time, and
-//                              writes each one to its tile's next free slot (match.any ranks + per-warp cursors).
+//        tile_scatter_kernel   every warp walks its splats in depth order; the lanes take the tiles of one splat's
+//                              rectangle and write each instance to its tile's next free slot (per-warp cursors).
 //      HBM: 8 B read per splat (tile rectangle) twice + 4 B written per instance; the 2-pass radix sort it replaces
 //      wrote the unsorted instances, read them for the histogram and moved them twice (28 B per instance), plus a
 //      4 B sentinel fill and a 4 B read for the ranges.
@@ -385,68 +385,58 @@ __global__ void __launch_bounds__(256) tile_scatter_kernel(BinGeom g, int64_t sl
     }
   }
   __syncthreads();
-  // ---- scatter: the warp's instance stream, 32 instances at a time, in depth order ----
-  const uint32_t lt = (1u << lane) - 1u;
+  // ---- scatter: the warp's splats one after the other in depth order; the lanes take the tiles of the current
+  // splat's rectangle (distinct cells, so the cursor update needs no atomics and no lane matching), and the per-tile
+  // order is the order in which the splats are visited.  (An earlier version packed the instance stream into full
+  // 32-lane windows and recovered the per-tile ranks with ballot matching: 230 instructions per window, profiles/r2u;
+  // this loop needs ~35 per non-empty splat, i.e. less than half per instance at ~10 tiles per splat.) ----
   const uint32_t key_base = (uint32_t)b * (uint32_t)g.T;
   uint32_t nidx = 0;                                 // next group's splat (prefetched while this group is walked)
   uint2 nrect = make_uint2(0u, 0u);
   if (wlo + lane < whi) { nidx = perm[fbase + wlo + lane]; nrect = rects_sorted[fbase + wlo + lane]; }
   for (int g0 = wlo; g0 < whi; g0 += 32) {
     const int i = g0 + lane;
-    uint32_t idx = nidx, rx = 0, rw = 0, n_inst = 0;
+    uint32_t idx = nidx, rx = 0, rwh = 0;
     const uint2 r = nrect;
     if (i + 32 < whi) { nidx = perm[fbase + i + 32]; nrect = rects_sorted[fbase + i + 32]; }
     if (i < whi) {
       const uint32_t x0 = r.x & 0xFFFF, y0 = r.x >> 16, x1 = r.y & 0xFFFF, y1 = r.y >> 16;
       if (x1 > x0 && y1 > y0) {
-        rx = r.x; rw = x1 - x0; n_inst = rw * (y1 - y0);
+        rx = r.x; rwh = (x1 - x0) | ((y1 - y0) << 16);
         if (PACKED) idx -= (uint32_t)fbase;          // index within the frame
       }
     }
-    uint32_t incl = n_inst;                          // inclusive scan of the lanes' instance counts
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-    const uint32_t excl = incl - n_inst;
-    for (uint32_t o0 = 0; o0 < total; o0 += 32) {
-      const uint32_t o = o0 + lane;
-      int s = 0;                                     // owner of output o: the smallest lane with incl > o
-#pragma unroll
-      for (int step = 16; step >= 1; step >>= 1) {
-        const uint32_t v = __shfl_sync(0xffffffffu, incl, s + step - 1);
-        if (v <= o) s += step;
-      }
-      s = min(s, 31);
-      const uint32_t o_excl = __shfl_sync(0xffffffffu, excl, s);
-      const uint32_t o_rx = __shfl_sync(0xffffffffu, rx, s);
-      const uint32_t o_rw = __shfl_sync(0xffffffffu, rw, s);
-      const uint32_t o_idx = __shfl_sync(0xffffffffu, idx, s);
-      const bool act = o < total;
-      uint32_t tile = 0, cell = 0;
-      if (act) {
-        const uint32_t k = o - o_excl;
-        const uint32_t row = k / o_rw, col = k - row * o_rw;
-        const uint32_t x = (o_rx & 0xFFFF) + col, y = (o_rx >> 16) + row;
-        tile = y * (uint32_t)g.gx + x;
-        cell = y * (uint32_t)gw + x;
-      }
-      const uint32_t peers = warp_match(tile, tile_bits, act);    // (a loop over only the differing bits was slower: r2m)
-      const uint32_t slot = act ? (uint32_t)cnt[cell] + __popc(peers & lt) : 0u;
-      __syncwarp();
-      if (act && (peers & lt) == 0) cnt[cell] += __popc(peers);
-      __syncwarp();
-      if (act && (int64_t)slot < slots) {
-        const uint32_t key = key_base + tile;
-        if (PACKED) {
-          vals_out[slot] = (key << vbits) | o_idx;
-        } else {
-          keys_out[slot] = key;
-          vals_out[slot] = o_idx;
+    uint32_t todo = __ballot_sync(0xffffffffu, rwh != 0u);
+    while (todo) {                                   // warp-uniform: the non-empty splats of the group, in order
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint32_t s_rx = __shfl_sync(0xffffffffu, rx, src);
+      const uint32_t s_wh = __shfl_sync(0xffffffffu, rwh, src);
+      const uint32_t s_idx = __shfl_sync(0xffffffffu, idx, src);
+      const uint32_t w = s_wh & 0xFFFF, n = w * (s_wh >> 16);
+      const uint32_t bx = s_rx & 0xFFFF, by = s_rx >> 16;
+      // k -> (row, col) = (k / w, k % w): (k + 0.5) * (1 / w) truncates to the exact quotient while n <= 4096
+      // (|error| <= 4096 * 2^-22 < 0.5 / 64 <= distance of (k + 0.5) / w to the next integer); bigger rectangles divide
+      const bool small = n <= 4096u && w <= 64u;
+      const float inv_w = 1.0f / (float)w;
+      for (uint32_t k = lane; k < n; k += 32) {
+        const uint32_t row = small ? (uint32_t)(((float)k + 0.5f) * inv_w) : k / w;
+        const uint32_t col = k - row * w;
+        const uint32_t x = bx + col, y = by + row;
+        const uint32_t cell = y * (uint32_t)gw + x;
+        const uint32_t slot = (uint32_t)cnt[cell];
+        cnt[cell] = (int)(slot + 1u);
+        if ((int64_t)slot < slots) {
+          const uint32_t key = key_base + y * (uint32_t)g.gx + x;
+          if (PACKED) {
+            vals_out[slot] = (key << vbits) | s_idx;
+          } else {
+            keys_out[slot] = key;
+            vals_out[slot] = s_idx;
+          }
         }
       }
+      __syncwarp();                                  // the next splat reads the cursors this one advanced
     }
   }
 }
