@@ -394,40 +394,45 @@ __global__ void __launch_bounds__(256) tile_scatter_kernel(BinGeom g, int64_t sl
   uint32_t nidx = 0;                                 // next group's splat (prefetched while this group is walked)
   uint2 nrect = make_uint2(0u, 0u);
   if (wlo + lane < whi) { nidx = perm[fbase + wlo + lane]; nrect = rects_sorted[fbase + wlo + lane]; }
+  const uint32_t cap = (uint32_t)(slots < (int64_t)0xFFFFFFFFll ? slots : (int64_t)0xFFFFFFFFll);
   for (int g0 = wlo; g0 < whi; g0 += 32) {
     const int i = g0 + lane;
-    uint32_t idx = nidx, rx = 0, rwh = 0;
+    // per lane, for its own splat: origin (x0 | y0 << 16), width | count << 9, 1 / width -- shuffled to the whole warp
+    // when the splat's turn comes (width <= 511 tiles, count < 2^23: images up to 8176 pixels wide)
+    uint32_t idx = nidx, rx = 0, wn = 0;
+    float inv_w = 0.f;
     const uint2 r = nrect;
     if (i + 32 < whi) { nidx = perm[fbase + i + 32]; nrect = rects_sorted[fbase + i + 32]; }
     if (i < whi) {
       const uint32_t x0 = r.x & 0xFFFF, y0 = r.x >> 16, x1 = r.y & 0xFFFF, y1 = r.y >> 16;
       if (x1 > x0 && y1 > y0) {
-        rx = r.x; rwh = (x1 - x0) | ((y1 - y0) << 16);
+        rx = r.x; wn = (x1 - x0) | (((x1 - x0) * (y1 - y0)) << 9);
+        inv_w = 1.0f / (float)(x1 - x0);
         if (PACKED) idx -= (uint32_t)fbase;          // index within the frame
       }
     }
-    uint32_t todo = __ballot_sync(0xffffffffu, rwh != 0u);
+    uint32_t todo = __ballot_sync(0xffffffffu, wn != 0u);
     while (todo) {                                   // warp-uniform: the non-empty splats of the group, in order
       const int src = __ffs(todo) - 1;
       todo &= todo - 1;
       const uint32_t s_rx = __shfl_sync(0xffffffffu, rx, src);
-      const uint32_t s_wh = __shfl_sync(0xffffffffu, rwh, src);
+      const uint32_t s_wn = __shfl_sync(0xffffffffu, wn, src);
       const uint32_t s_idx = __shfl_sync(0xffffffffu, idx, src);
-      const uint32_t w = s_wh & 0xFFFF, n = w * (s_wh >> 16);
+      const float s_inv = __shfl_sync(0xffffffffu, inv_w, src);
+      const uint32_t w = s_wn & 511u, n = s_wn >> 9;
       const uint32_t bx = s_rx & 0xFFFF, by = s_rx >> 16;
+      const uint32_t cell0 = by * (uint32_t)gw + bx, key0 = key_base + by * (uint32_t)g.gx + bx;
       // k -> (row, col) = (k / w, k % w): (k + 0.5) * (1 / w) truncates to the exact quotient while n <= 4096
       // (|error| <= 4096 * 2^-22 < 0.5 / 64 <= distance of (k + 0.5) / w to the next integer); bigger rectangles divide
-      const bool small = n <= 4096u && w <= 64u;
-      const float inv_w = 1.0f / (float)w;
+      const bool small = n <= 4096u && w <= 64u;     // warp-uniform
       for (uint32_t k = lane; k < n; k += 32) {
-        const uint32_t row = small ? (uint32_t)(((float)k + 0.5f) * inv_w) : k / w;
+        const uint32_t row = small ? (uint32_t)(((float)k + 0.5f) * s_inv) : k / w;
         const uint32_t col = k - row * w;
-        const uint32_t x = bx + col, y = by + row;
-        const uint32_t cell = y * (uint32_t)gw + x;
+        const uint32_t cell = cell0 + row * (uint32_t)gw + col;
         const uint32_t slot = (uint32_t)cnt[cell];
         cnt[cell] = (int)(slot + 1u);
-        if ((int64_t)slot < slots) {
-          const uint32_t key = key_base + y * (uint32_t)g.gx + x;
+        if (slot < cap) {
+          const uint32_t key = key0 + row * (uint32_t)g.gx + col;
           if (PACKED) {
             vals_out[slot] = (key << vbits) | s_idx;
           } else {
@@ -448,7 +453,9 @@ static inline BinGeom bin_geom(int B, int N, int W, int H) {
   g.B = B; g.N = N;
   g.gx = (W + TILE - 1) / TILE; g.gy = (H + TILE - 1) / TILE;
   g.T = g.gx * g.gy;
-  int nchunk = (6 * 148 + B - 1) / (B > 0 ? B : 1);    // ~6 resident scatter CTAs per SM
+  int nchunk = (6 * 148) / (B > 0 ? B : 1);            // <= 6 resident scatter CTAs per SM: rounded DOWN, so that the
+                                                       // B x nchunk CTAs are one wave (rounding up left 8 CTAs of a
+                                                       // 896-CTA grid for a second wave that doubled the kernel's time)
   nchunk = nchunk < 4 ? 4 : (nchunk > 128 ? 128 : nchunk);
   const int by_size = (N + 255) / 256;                 // at least 256 splats per chunk
   if (nchunk > by_size) nchunk = by_size < 1 ? 1 : by_size;
