@@ -552,6 +552,8 @@ def run_ours(args, wl):
         top = max(((k, v) for k, v in prof.items() if not k.startswith("py:")), key=lambda kv: kv[1]["ms"])
         name, rec = top
         st = dict(_lib.PROFILE.extra)
+        st["walked"] = work_last["walked_instances"]       # the profiled pass runs on the model as the timed region left it
+        st["R"] = work_last["instances"]
         alg = algorithmic_bytes(name, wl, S, st)
         dur_s = rec["ms"] / rec["calls"] / 1000.0
         km = kernel_metrics(args.workload, name)
@@ -567,7 +569,9 @@ def run_ours(args, wl):
                            "pipe_xu_pct": km.get("pipe_xu"), "issue_active_pct": km.get("issue_active"),
                            "source": km.get("source")} if km else None),
                 "breakdown_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
-                "instances_R_per_step": st.get("R"), "pairs_note": "R = tile instances of the last step"}
+                "instances_R_per_step": st.get("R"), "walked_instances_per_step": st.get("walked"),
+                "pairs_note": "R = tile instances built per step, walked = instances the blend kernels read before every "
+                              "pixel of the tile has its last contributor; both of the model state after the timed region"}
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -623,17 +627,26 @@ def kernel_metrics(workload, name):
 
 
 def algorithmic_bytes(name, wl, S, st):
-    """Algorithmic HBM bytes per launch (DESIGN.md 'Kernels')."""
+    """Algorithmic HBM bytes per launch (DESIGN.md 'Kernels').  R = tile instances built by the binning
+    stage, Wk = the instances the blend kernels actually walk (a tile stops at its deepest last contributor), both of
+    the model's state when the per-kernel pass ran; P = pixels, BN = frames x Gaussians."""
     P = wl["H"] * wl["W"] * S
     R = st.get("R") or 0
+    Wk = st.get("walked") or R
     BN = wl["N"] * S
     table = {
-        "dimo_raster_blend_fwd": 68 * R + 40 * P,                 # record gather + instance word, 10 output planes
-        # depth/normal carry no gradient in this step: 24 B/px in, 9 gradient fields (RMW) per (tile, splat)
-        "dimo_raster_blend_bwd": 68 * R + 24 * P + 2 * 36 * R,
-        "dimo_raster_preprocess": 56 * BN + 72 * BN,
-        "dimo_raster_bin": 4 * R + 2 * 8 * R + 4 * R,              # emit packed words, 2 keys-only radix passes, ranges
-        "dimo_raster_preprocess_bwd": 64 * BN + 44 * BN + 60 * BN,
+        # per walked instance: 4 B list word + 64 B blend record; per pixel: colour 12 + alpha 4 + final_T 4 + n_contrib 4
+        "dimo_raster_blend_fwd": 68 * Wk + 24 * P,
+        # per walked instance: the same 68 B in + 36 B of gradient fields reduced into the record table; per pixel 24 B in
+        "dimo_raster_blend_bwd": 68 * Wk + 36 * Wk + 24 * P,
+        # in: means3D 12 + scales 12 + rotation 16 + opacity 4 + SH 12; out: record 64 + radius 4 + count 4 + rect 8 + key 4
+        "dimo_raster_preprocess": 56 * BN + 84 * BN,
+        # depth sort: 4 passes x (key + index, read + write) = 64 B per splat; histogram 8 B; scatter 12 B per splat
+        # + one 4 B list word per instance
+        "dimo_raster_bin": (64 + 8 + 12) * BN + 4 * R,
+        # in: gradient record 64 + the forward's inputs 56 + radius 4; out: d(means3D) 12 + d(rotation) 16 per (frame,
+        # Gaussian); the shared parameters' gradients leave as [N, *] sums
+        "dimo_raster_preprocess_bwd": 124 * BN + 28 * BN,
         "dimo_ssim_fwd": 8 * 3 * P + 36 * P,
         "dimo_ssim_bwd": 60 * P + 12 * P,
         "dimo_adam_step": 32 * st.get("n_params", 0),

@@ -19,7 +19,7 @@ class _ImageLoss(torch.autograd.Function):
         B, C, H, W = img1.shape
         dev = img1.device
         sums = torch.empty(3, dtype=torch.float32, device=dev)
-        keep = bool(need_ssim_grad) and img1.requires_grad
+        keep = bool(need_ssim_grad) and ctx.needs_input_grad[0]      # (img1 itself may be a no-grad copy by now)
         dm = torch.empty(3, B, C, H, W, dtype=torch.float32, device=dev) if keep else None
         _lib.call("dimo_ssim_fwd", B, C, H, W, int(clamp01), _lib.ptr(img1), _lib.ptr(img2), _lib.ptr(sums), _lib.ptr(dm),
                   None, None, 0.0, 0.0, 0.0, _lib.stream())
