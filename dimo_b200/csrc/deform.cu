@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(256) lbs_fwd_kernel(
 constexpr int CT = 9;        // 8 used + 1 pad: an odd row stride spreads the rows over the shared-memory banks
 
 template <int K>
-__global__ void __launch_bounds__(256) lbs_bwd_kernel(
+__global__ void __launch_bounds__(256, 3) lbs_bwd_kernel(
     int N, int M, int use_smem, const float* __restrict__ xyz, const float* __restrict__ rot,
     const int64_t* __restrict__ idx, const float* __restrict__ dist, const float* __restrict__ c_xyz,
     const float* __restrict__ c_radius_raw, const float* __restrict__ dxyz, const float* __restrict__ dquat,
@@ -296,8 +296,8 @@ extern "C" int dimo_lbs_bwd(int B, int N, int M, int K, const float* xyz, const 
   const size_t smem = (size_t)M * CT * sizeof(float);
   const float det = dimo::det_scale();          // deterministic mode: every output is an int64 buffer, no shared staging
   const int use_smem = (smem <= 160 * 1024 && det == 0.f) ? 1 : 0;
-  // few, fat CTAs per frame so each shared-memory table is flushed once: ~2 waves over 148 SMs in total
-  int per_frame = max(1, min(ceil_div(N, 256), ceil_div(296, B)));
+  // few, fat CTAs per frame so each shared-memory table is flushed once: one wave of 3 CTAs per SM (85 registers)
+  int per_frame = max(1, min(ceil_div(N, 256), (3 * 148) / B > 0 ? (3 * 148) / B : 1));   // 3 CTAs per SM, one wave
   dim3 grid(per_frame, B);
   switch (K) {
 #define DIMO_LBS_CASE(KK)                                                                                          \

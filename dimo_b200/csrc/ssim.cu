@@ -66,7 +66,7 @@ __device__ __forceinline__ void ss_load14(const float* __restrict__ row, bool ro
 }
 
 template <bool VEC>
-__global__ void __launch_bounds__(SS_THREADS, 3) ssim_fwd_kernel(int H, int W, const float* __restrict__ img1,
+__global__ void __launch_bounds__(SS_THREADS, 4) ssim_fwd_kernel(int H, int W, const float* __restrict__ img1,
                                                                  const float* __restrict__ img2,
                                                                  float* __restrict__ sums, float* __restrict__ dm,
                                                                  int64_t plane_count, int clamp01, int C,

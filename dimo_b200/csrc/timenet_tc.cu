@@ -252,8 +252,11 @@ __global__ void __launch_bounds__(256) tn_heads_fwd_kernel(int R, const uint8_t*
   else if (lane < 7) dquat[r * 4 + (lane - 3)] = (lane == 3 ? acc[3] : lane == 4 ? acc[4] : lane == 5 ? acc[5] : acc[6]) + b11[lane - 3];
 }
 
-// backward: CTA = (128-row block, head).  dH = (g W) * [H > 0] -> split tiles + transposed tiles (the first data-
-// gradient GEMM's A operand / the weight-gradient operand); dW[j, c] += sum_r g[r, j] H[r, c]; db[j] += sum_r g[r, j]
+// backward: CTA = (32-row block, head) -- 4 x the CTAs of a 128-row split: the kernel is latency-bound (strided tile
+// reads, scattered transposed stores) and 128 CTAs left most of the GPU idle.  dH = (g W) * [H > 0] -> split tiles +
+// transposed tiles (the first data-gradient GEMM's A operand / the weight-gradient operand);
+// dW[j, c] += sum_r g[r, j] H[r, c]; db[j] += sum_r g[r, j]
+constexpr int HB_ROWS = 32;
 __global__ void __launch_bounds__(256) tn_heads_bwd_kernel(int R, int Rp, const float* __restrict__ g_dxyz,
                                                            const float* __restrict__ g_dquat, const uint8_t* __restrict__ hp,
                                                            const uint8_t* __restrict__ hr, const float* __restrict__ W9,
@@ -262,7 +265,9 @@ __global__ void __launch_bounds__(256) tn_heads_bwd_kernel(int R, int Rp, const 
                                                            uint8_t* __restrict__ outT_r, float* __restrict__ dW9,
                                                            float* __restrict__ db9, float* __restrict__ dW11,
                                                            float* __restrict__ db11, float det) {
-  const int rb = blockIdx.x, head = blockIdx.y, tid = threadIdx.x;
+  const int head = blockIdx.y, tid = threadIdx.x;
+  const int row0 = blockIdx.x * HB_ROWS;             // first row of this CTA (never straddles a 128-row tile)
+  const int rb = row0 >> 7, rl0 = row0 & 127;
   const int No = head ? 4 : 3;
   const float* g = head ? g_dquat : g_dxyz;
   const uint8_t* H = head ? hr : hp;                 // split tiles of the head's hidden activation
@@ -271,18 +276,19 @@ __global__ void __launch_bounds__(256) tn_heads_bwd_kernel(int R, int Rp, const 
   uint8_t* outT = head ? outT_r : outT_p;
   float* dW = head ? dW11 : dW9;
   float* db = head ? db11 : db9;
-  __shared__ float sg[128][4];
+  __shared__ float sg[HB_ROWS][4];
   __shared__ float sw[4][256];
-  for (int e = tid; e < 128 * 4; e += 256) {
-    const int r = rb * 128 + (e >> 2), j = e & 3;
+  for (int e = tid; e < HB_ROWS * 4; e += 256) {
+    const int r = row0 + (e >> 2), j = e & 3;
     sg[e >> 2][j] = (r < R && j < No) ? g[(int64_t)r * No + j] : 0.f;
   }
   for (int e = tid; e < 4 * 256; e += 256) sw[e >> 8][e & 255] = (e >> 8) < No ? W[e] : 0.f;
   __syncthreads();
   // ---- masked data gradient -> tiles: item = (row, 16-byte chunk), consecutive threads take consecutive rows ----
-  for (int it = tid; it < 128 * 64; it += 256) {
-    const int rl = it & 127, qq = it >> 7;              // qq: chunk of 4 columns, 0..63
-    const int r = rb * 128 + rl;
+  for (int it = tid; it < HB_ROWS * 64; it += 256) {
+    const int rr = it & (HB_ROWS - 1), qq = it / HB_ROWS;    // qq: chunk of 4 columns, 0..63
+    const int rl = rl0 + rr;
+    const int r = row0 + rr;
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     if (r < R) {
       const float4 h = tn_tile_load4(H, 8, r, qq);
@@ -290,7 +296,7 @@ __global__ void __launch_bounds__(256) tn_heads_bwd_kernel(int R, int Rp, const 
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int c = qq * 4 + e;
-        const float d = sg[rl][0] * sw[0][c] + sg[rl][1] * sw[1][c] + sg[rl][2] * sw[2][c] + sg[rl][3] * sw[3][c];
+        const float d = sg[rr][0] * sw[0][c] + sg[rr][1] * sw[1][c] + sg[rr][2] * sw[2][c] + sg[rr][3] * sw[3][c];
         v[e] = hv[e] > 0.f ? d : 0.f;
       }
     }
@@ -314,14 +320,14 @@ __global__ void __launch_bounds__(256) tn_heads_bwd_kernel(int R, int Rp, const 
   {
     const int c = tid;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    const int rows = min(128, R - rb * 128);
+    const int rows = max(0, min(HB_ROWS, R - row0));
     for (int r0 = 0; r0 < rows; r0 += 16) {           // 16 independent loads in flight
       float h[16];
 #pragma unroll
       for (int u = 0; u < 16; ++u) {
         h[u] = 0.f;
         if (r0 + u < rows) {
-          const uint8_t* t = H + ((size_t)rb * 8 + (c >> 5)) * TN_STAGE_A + tn_off(r0 + u, (c & 31) >> 2) + (c & 3) * 4;
+          const uint8_t* t = H + ((size_t)rb * 8 + (c >> 5)) * TN_STAGE_A + tn_off(rl0 + r0 + u, (c & 31) >> 2) + (c & 3) * 4;
           h[u] = *reinterpret_cast<const float*>(t) + *reinterpret_cast<const float*>(t + TN_PLANE_A);
         }
       }
@@ -333,11 +339,13 @@ __global__ void __launch_bounds__(256) tn_heads_bwd_kernel(int R, int Rp, const 
         }
       }
     }
-    for (int j = 0; j < No; ++j) acc_add(dW, (int64_t)j * 256 + c, acc[j], det);
-    if (tid < No) {
-      float s = 0.f;
-      for (int rl = 0; rl < rows; ++rl) s += sg[rl][tid];
-      acc_add(db, tid, s, det);
+    if (rows > 0) {
+      for (int j = 0; j < No; ++j) acc_add(dW, (int64_t)j * 256 + c, acc[j], det);
+      if (tid < No) {
+        float s = 0.f;
+        for (int rr = 0; rr < rows; ++rr) s += sg[rr][tid];
+        acc_add(db, tid, s, det);
+      }
     }
   }
 }
@@ -921,7 +929,7 @@ extern "C" int dimo_timenet_bwd(int G, int M, int L, const float* const* W_host,
   const int E = o.E;
   float* dcat = reinterpret_cast<float*>(ws + o.dcat_plain);
   // ---- heads (FP32 SIMT, one launch): weight / bias gradients + masked data gradients as split tiles ----
-  tn_heads_bwd_kernel<<<dim3(o.nrb, 2), 256, 0, st>>>(R, o.Rp, g_dxyz, g_dquat, ws + o.y[8], ws + o.y[9], W_host[9], W_host[11], ws + o.g[8],
+  tn_heads_bwd_kernel<<<dim3(o.Rp / HB_ROWS, 2), 256, 0, st>>>(R, o.Rp, g_dxyz, g_dquat, ws + o.y[8], ws + o.y[9], W_host[9], W_host[11], ws + o.g[8],
                                                       ws + o.gT[8], ws + o.g[9], ws + o.gT[9], dW_host[9], db_host[9],
                                                       dW_host[11], db_host[11], dimo::det_scale());
   DIMO_CHECK_LAUNCH();
