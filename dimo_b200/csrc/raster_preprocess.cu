@@ -13,7 +13,7 @@
 namespace dimo {
 
 
-__global__ void __launch_bounds__(256) preprocess_fwd_kernel(
+__global__ void __launch_bounds__(256, 4) preprocess_fwd_kernel(
     int B, int N, int W, int H, int sh_degree, int sh_coeffs, float scale_modifier, int act_flags,
     const float* __restrict__ cams, const int32_t* __restrict__ frame_src,
     const float* __restrict__ means3D, int64_t means3D_bs,
