@@ -373,23 +373,32 @@ __device__ __forceinline__ void tn_stamp(unsigned long long* dbg, int slot) {
   }
 }
 
-// One CTA = 128 rows x 64 output columns (grid.y = N / 64: 128 CTAs for a 4096 x 256 layer -- one wave of the 148 SMs).
-// 10 warps: 0-7 epilogue (warp w: TMEM lanes 32 (w & 3), columns 32 (w >> 2) + [0, 32)), 8 producer, 9 MMA issuer; two
-// 48 KB stages, two CTAs per SM.  Phase times of a K = 256 layer (tools/tn_stamps.py): first stage lands at 1.8 us, MMAs done at ~5 us.
-constexpr int TG_NB = 64;
-constexpr int TG_STAGE_B = 2 * TG_NB * TN_KT * 4;           // 16 KB
-constexpr int TG_STAGE = TN_STAGE_A + TG_STAGE_B;           // 48 KB
-constexpr int TG_STAGES = 2;                                // 97 KB per CTA: two CTAs per SM, so that one CTA's epilogue
-constexpr int TG_SMEM = TG_STAGES * TG_STAGE + 1024;        // overlaps the other's MMAs and 256-CTA grids (8192 rows) are one wave
+// One CTA = 128 rows x NB output columns (grid.y = N / NB).  10 warps: 0-7 epilogue (warp w: TMEM lanes 32 (w & 3),
+// 32-column chunks (w >> 2), (w >> 2) + 2, ...), 8 producer, 9 MMA issuer.  The layers are bound by the L2 -> shared
+// memory operand traffic (every operand is a (hi, lo) pair: 8 B per element), so the tile shape follows the row count:
+//   NB =  64: two 48 KB stages, two CTAs per SM -- 128 CTAs for a 4096-row layer (one wave), 100 MB per 8192-row layer;
+//   NB = 128: three 64 KB stages, one CTA per SM -- 128 CTAs for an 8192-row layer, 67 MB (the A tiles are re-read by
+//             two column blocks instead of four).
+// Phase times of a K = 256 layer (tools/tn_stamps.py, NB = 64): first stage lands at 1.8 us, MMAs done at ~6 us.
 constexpr int TG_THREADS = 320;
-constexpr int TG_TSTAGE = 2 * (TG_NB / 8) * TT_SBO;         // transposed staging per lane group: (hi, lo) x 64 tile rows = 18 KB
-static_assert(4 * TG_TSTAGE <= TG_STAGES * TG_STAGE && 128 * (TG_NB + 1) * 4 <= TG_STAGES * TG_STAGE, "epilogue staging");
+template <int NB>
+struct TgCfg {
+  static constexpr int STAGE_B = 2 * NB * TN_KT * 4;               // 16 / 32 KB
+  static constexpr int STAGE = TN_STAGE_A + STAGE_B;               // 48 / 64 KB
+  static constexpr int STAGES = NB == 64 ? 2 : 3;
+  static constexpr int SMEM = STAGES * STAGE + 1024;
+  static constexpr int TSTAGE = 2 * (NB / 8) * TT_SBO;             // transposed staging per lane group: (hi, lo) x NB tile rows
+  static_assert(4 * TSTAGE <= STAGES * STAGE && 128 * (NB + 1) * 4 <= STAGES * STAGE, "epilogue staging");
+};
 
 __device__ __forceinline__ void tn_named_bar(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
-__global__ void __launch_bounds__(TG_THREADS, 2) tn_gemm_kernel(const __grid_constant__ TnGemmArgs p) {
+template <int NB>
+__global__ void __launch_bounds__(TG_THREADS, NB == 64 ? 2 : 1) tn_gemm_kernel(const __grid_constant__ TnGemmArgs p) {
+  using C = TgCfg<NB>;
+  constexpr int TG_STAGES = C::STAGES, TG_STAGE = C::STAGE, TG_TSTAGE = C::TSTAGE;
   extern __shared__ uint8_t tn_smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[TG_STAGES], empty_bar[TG_STAGES], done_bar;
   __shared__ uint32_t tmem_slot;
@@ -398,11 +407,11 @@ __global__ void __launch_bounds__(TG_THREADS, 2) tn_gemm_kernel(const __grid_con
   const int rb = blockIdx.x, cb = blockIdx.y;
   if (tid == 0) tn_stamp(p.dbg, 0);
   const uint32_t planeB_full = (uint32_t)p.N * 128u;          // bytes of one plane of a packed weight tile (all N rows)
-  constexpr uint32_t planeB = TG_NB * 128u;                   // this CTA's 64 rows of it
+  constexpr uint32_t planeB = NB * 128u;                      // this CTA's NB rows of it
 
   if (warp == 9) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tn_smem_u32(&tmem_slot)),
-                 "r"((uint32_t)TG_NB)
+                 "r"((uint32_t)NB)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -440,7 +449,7 @@ __global__ void __launch_bounds__(TG_THREADS, 2) tn_gemm_kernel(const __grid_con
   } else if (warp == 9) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      const uint32_t idesc = tn_idesc(TN_BM, TG_NB);
+      const uint32_t idesc = tn_idesc(TN_BM, NB);
       int total = 0;
       for (int sg = 0; sg < p.nseg; ++sg) total += p.seg[sg].nkt;
       for (int it = 0; it < total; ++it) {
@@ -464,82 +473,88 @@ __global__ void __launch_bounds__(TG_THREADS, 2) tn_gemm_kernel(const __grid_con
       tn_stamp(p.dbg, 3);
     }
   } else {
-    // ===== epilogue: one 32-column chunk per warp =====
+    // ===== epilogue: 32-column chunks (w >> 2), (w >> 2) + 2, ... of the lane group's 32 rows =====
     const int lg = warp & 3;                       // TMEM lane group = tile rows [32 lg, 32 lg + 32)
     const int rl = lg * 32 + lane;
     const int gr = rb * TN_BM + rl;
     const bool valid = gr < p.R;
-    const int lc0 = (warp >> 2) * 32;              // column within the CTA's 64
-    const int n0 = cb * TG_NB + lc0;               // column of the GEMM's N
     const uint32_t row_off = tn_off(rl, 0);        // (row, chunk q) -> row_off + 128 q
-    // everything that does not depend on the accumulator is fetched while the MMAs run: bias, ReLU-mask bits
-    float bias_r[32];
-    uint32_t mbits = 0xFFFFFFFFu;
-    if (p.bias != nullptr) {
-      const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 bb = b4[q];
-        bias_r[4 * q] = bb.x; bias_r[4 * q + 1] = bb.y; bias_r[4 * q + 2] = bb.z; bias_r[4 * q + 3] = bb.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) bias_r[j] = 0.f;
-    }
-    if (p.mask != nullptr) {
-      const uint8_t* mt = p.mask + ((size_t)rb * p.mask_nkt + p.mask_kt0 + (n0 >> 5)) * TN_STAGE_A + row_off;
-      uint32_t bits = 0;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 mh = *reinterpret_cast<const float4*>(mt + 128 * q);
-        const float4 ml = *reinterpret_cast<const float4*>(mt + TN_PLANE_A + 128 * q);
-        bits |= (uint32_t)(mh.x > 0.f || ml.x > 0.f) << (4 * q);
-        bits |= (uint32_t)(mh.y > 0.f || ml.y > 0.f) << (4 * q + 1);
-        bits |= (uint32_t)(mh.z > 0.f || ml.z > 0.f) << (4 * q + 2);
-        bits |= (uint32_t)(mh.w > 0.f || ml.w > 0.f) << (4 * q + 3);
-      }
-      mbits = bits;
-    }
     if (tid == 0) tn_stamp(p.dbg, 4);
-    tn_mbar_wait(&done_bar, 0);
-    if (tid == 0) tn_stamp(p.dbg, 5);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    uint32_t v[32];
-    tn_ld32(tmem_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)lc0, v);
-    // per group of four columns: bias / ReLU / mask, split into (hi, lo), and every store that wants the values
-    uint8_t* tT = smem + (size_t)lg * TG_TSTAGE + (size_t)(lc0 >> 3) * TT_SBO + (lane >> 2) * TT_LBO + (lane & 3) * 4;
-    uint8_t* tO = p.out != nullptr ? p.out + ((size_t)rb * p.out_nkt + p.out_kt0 + (n0 >> 5)) * TN_STAGE_A + row_off : nullptr;
-    float* sp = reinterpret_cast<float*>(smem) + rl * (TG_NB + 1) + lc0;   // plain staging (jobs without transposed output)
+    bool waited = false;
+    for (int ch = warp >> 2; ch < NB / 32; ch += 2) {
+      const int lc0 = ch * 32;                     // column within the CTA's NB
+      const int n0 = cb * NB + lc0;                // column of the GEMM's N
+      // everything that does not depend on the accumulator is fetched first (for the first chunk: while the MMAs run)
+      float bias_r[32];
+      uint32_t mbits = 0xFFFFFFFFu;
+      if (p.bias != nullptr) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      uint32_t hi[4], lo[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int j = 4 * q + e;
-        float t = __uint_as_float(v[j]) + bias_r[j];
-        if (p.relu) t = fmaxf(t, 0.f);
-        const float y = (valid && ((mbits >> j) & 1u)) ? t : 0.f;
-        hi[e] = tn_tf32(y);
-        lo[e] = tn_tf32(y - __uint_as_float(hi[e]));
-        if (p.outT != nullptr) {
-          *reinterpret_cast<uint32_t*>(tT + (j >> 3) * TT_SBO + (j & 7) * 16) = hi[e];
-          *reinterpret_cast<uint32_t*>(tT + TG_TSTAGE / 2 + (j >> 3) * TT_SBO + (j & 7) * 16) = lo[e];
+        for (int q = 0; q < 8; ++q) {
+          const float4 bb = b4[q];
+          bias_r[4 * q] = bb.x; bias_r[4 * q + 1] = bb.y; bias_r[4 * q + 2] = bb.z; bias_r[4 * q + 3] = bb.w;
         }
-        if (p.plain != nullptr) sp[j] = y;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) bias_r[j] = 0.f;
       }
-      if (tO != nullptr) {
-        *reinterpret_cast<uint4*>(tO + 128 * q) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(tO + TN_PLANE_A + 128 * q) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      if (p.mask != nullptr) {
+        const uint8_t* mt = p.mask + ((size_t)rb * p.mask_nkt + p.mask_kt0 + (n0 >> 5)) * TN_STAGE_A + row_off;
+        uint32_t bits = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 mh = *reinterpret_cast<const float4*>(mt + 128 * q);
+          const float4 ml = *reinterpret_cast<const float4*>(mt + TN_PLANE_A + 128 * q);
+          bits |= (uint32_t)(mh.x > 0.f || ml.x > 0.f) << (4 * q);
+          bits |= (uint32_t)(mh.y > 0.f || ml.y > 0.f) << (4 * q + 1);
+          bits |= (uint32_t)(mh.z > 0.f || ml.z > 0.f) << (4 * q + 2);
+          bits |= (uint32_t)(mh.w > 0.f || ml.w > 0.f) << (4 * q + 3);
+        }
+        mbits = bits;
+      }
+      if (!waited) {
+        tn_mbar_wait(&done_bar, 0);
+        if (tid == 0) tn_stamp(p.dbg, 5);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        waited = true;
+      }
+      uint32_t v[32];
+      tn_ld32(tmem_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)lc0, v);
+      // per group of four columns: bias / ReLU / mask, split into (hi, lo), and every store that wants the values
+      uint8_t* tT = smem + (size_t)lg * TG_TSTAGE + (size_t)(lc0 >> 3) * TT_SBO + (lane >> 2) * TT_LBO + (lane & 3) * 4;
+      uint8_t* tO = p.out != nullptr ? p.out + ((size_t)rb * p.out_nkt + p.out_kt0 + (n0 >> 5)) * TN_STAGE_A + row_off : nullptr;
+      float* sp = reinterpret_cast<float*>(smem) + rl * (NB + 1) + lc0;   // plain staging (jobs without transposed output)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = 4 * q + e;
+          float t = __uint_as_float(v[j]) + bias_r[j];
+          if (p.relu) t = fmaxf(t, 0.f);
+          const float y = (valid && ((mbits >> j) & 1u)) ? t : 0.f;
+          hi[e] = tn_tf32(y);
+          lo[e] = tn_tf32(y - __uint_as_float(hi[e]));
+          if (p.outT != nullptr) {
+            *reinterpret_cast<uint32_t*>(tT + (j >> 3) * TT_SBO + (j & 7) * 16) = hi[e];
+            *reinterpret_cast<uint32_t*>(tT + TG_TSTAGE / 2 + (j >> 3) * TT_SBO + (j & 7) * 16) = lo[e];
+          }
+          if (p.plain != nullptr) sp[j] = y;
+        }
+        if (tO != nullptr) {
+          *reinterpret_cast<uint4*>(tO + 128 * q) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(tO + TN_PLANE_A + 128 * q) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
       }
     }
     if (p.outT != nullptr) {
       // transposed tiles: staged in the (now idle) operand stages as the exact image of this CTA's part of
-      // T[rt = 4 rb + lg][plane][fb] -- 64 consecutive tile rows = 9 KB, contiguous in global memory -- and written by one
+      // T[rt = 4 rb + lg][plane][fb] -- NB consecutive tile rows, contiguous in global memory -- and written by one
       // bulk store per (lane group, plane) as soon as the group's two warps are through
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // staged image -> bulk-copy engine
       tn_named_bar(1 + lg, 64);
       if (warp < 4 && lane == 0) {
-        const int f0 = p.t_f0 + cb * TG_NB, fb = f0 >> 7, fl0 = f0 & 127;
+        const int f0 = p.t_f0 + cb * NB, fb = f0 >> 7, fl0 = f0 & 127;
 #pragma unroll
         for (int pl = 0; pl < 2; ++pl) {
           const uint8_t* src = smem + (size_t)lg * TG_TSTAGE + (size_t)pl * (TG_TSTAGE / 2);
@@ -558,11 +573,11 @@ __global__ void __launch_bounds__(TG_THREADS, 2) tn_gemm_kernel(const __grid_con
         const int g2 = rb * TN_BM + r;
         if (g2 >= p.R) break;
 #pragma unroll
-        for (int h = 0; h < TG_NB / 32; ++h) {
-          const int col = cb * TG_NB + h * 32 + lane;
+        for (int h = 0; h < NB / 32; ++h) {
+          const int col = cb * NB + h * 32 + lane;
           if (col < p.plain_cols) {
             float* dst = p.plain + (int64_t)g2 * p.ldp + col;
-            const float val = sr[r * (TG_NB + 1) + h * 32 + lane];
+            const float val = sr[r * (NB + 1) + h * 32 + lane];
             *dst = p.plain_acc ? *dst + val : val;
           }
         }
@@ -576,8 +591,19 @@ __global__ void __launch_bounds__(TG_THREADS, 2) tn_gemm_kernel(const __grid_con
   __syncthreads();
   if (tid == 0) tn_stamp(p.dbg, 7);
   if (warp == 9) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)TG_NB) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)NB) : "memory");
   }
+}
+
+// tile width by row count: see the comment above tn_gemm_kernel
+static inline int tn_pick_nb(int nrb, int N) { return (nrb >= 64 && N % 128 == 0) ? 128 : 64; }
+
+static int tn_launch_gemm(const TnGemmArgs& g, int nrb, cudaStream_t st) {
+  if (tn_pick_nb(nrb, g.N) == 128)
+    tn_gemm_kernel<128><<<dim3(nrb, g.N / 128), TG_THREADS, TgCfg<128>::SMEM, st>>>(g);
+  else
+    tn_gemm_kernel<64><<<dim3(nrb, g.N / 64), TG_THREADS, TgCfg<64>::SMEM, st>>>(g);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -775,7 +801,8 @@ TnLayout tn_layout(int R, int L) {
 int tn_set_attrs() {
   static bool done = false;
   if (!done) {
-    DIMO_CHECK_CUDA(cudaFuncSetAttribute(tn_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
+    DIMO_CHECK_CUDA(cudaFuncSetAttribute(tn_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TgCfg<64>::SMEM));
+    DIMO_CHECK_CUDA(cudaFuncSetAttribute(tn_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TgCfg<128>::SMEM));
     DIMO_CHECK_CUDA(cudaFuncSetAttribute(tn_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM));
     done = true;
   }
@@ -885,8 +912,7 @@ extern "C" int dimo_timenet_fwd(int G, int M, int L, const float* pts, const flo
   // ---- the ten 256-wide layers ----
   auto gemm = [&](TnGemmArgs& g) {
     g.dbg = g_tn_dbg != nullptr ? g_tn_dbg + (size_t)(g_tn_dbg_launch++ % 32) * 128 * 8 : nullptr;
-    tn_gemm_kernel<<<dim3(o.nrb, g.N / TG_NB), TG_THREADS, TG_SMEM, st>>>(g);
-    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+    return tn_launch_gemm(g, o.nrb, st);
   };
   const int order[10] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 10};
   for (int oi = 0; oi < 10; ++oi) {
@@ -936,8 +962,7 @@ extern "C" int dimo_timenet_bwd(int G, int M, int L, const float* const* W_host,
   int rc = 0;
   auto gemm = [&](TnGemmArgs& g) {
     g.dbg = g_tn_dbg != nullptr ? g_tn_dbg + (size_t)(g_tn_dbg_launch++ % 32) * 128 * 8 : nullptr;
-    tn_gemm_kernel<<<dim3(o.nrb, g.N / TG_NB), TG_THREADS, TG_SMEM, st>>>(g);
-    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+    return tn_launch_gemm(g, o.nrb, st);
   };
   // ---- d(out of layer 7) = dhp_m W8 + dhr_m W10, masked by the sign of layer 7's output ----
   {

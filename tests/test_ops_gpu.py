@@ -59,7 +59,7 @@ def _timenet_pair(M, G, L=32, seed=0, final_scale=0.01):
     return net, params, pts, times, lat
 
 
-@pytest.mark.parametrize("M,G", [(512, 3), (100, 1), (33, 5), (512, 8)])
+@pytest.mark.parametrize("M,G", [(512, 3), (100, 1), (33, 5), (512, 8), (512, 16), (515, 16)])   # >= 8192 rows: the 128-wide GEMM tiles
 def test_timenet_fwd_bwd(cuda, M, G):
     """TimeNet forward + every gradient vs the oracle, on EVERY row.  The ReLU patterns of the two forward passes are
     exported and compared: a row takes part in the gradient comparison when all of its 2560 signs agree (its loss

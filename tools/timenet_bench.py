@@ -13,7 +13,7 @@ from dimo_b200.deform import TimeNet  # noqa: E402
 
 def main():
     torch.manual_seed(0)
-    G, M, L = 8, 512, 32
+    G, M, L = int(os.environ.get("TN_G", "8")), 512, 32
     net = TimeNet(latent_code_dim=L).cuda()
     with torch.no_grad():
         for lin in (net.pts_layers[-1], net.rot_layers[-1]):

@@ -5,7 +5,7 @@ import torch
 from dimo_b200 import _lib
 from dimo_b200.deform import TimeNet
 torch.manual_seed(0)
-G, M, L = 8, 512, 32
+G, M, L = int(os.environ.get("TN_G", "8")), 512, 32
 net = TimeNet(latent_code_dim=L).cuda()
 pts = torch.rand(M, 3, device="cuda") - 0.5; times = torch.rand(G, device="cuda"); lat = torch.randn(G, L, device="cuda")
 buf = torch.zeros(32 * 128 * 8, dtype=torch.int64, device="cuda")
