@@ -466,7 +466,8 @@ def run_ours(args, wl):
         the clock runs, so a step late in the region is not the same work as the first one): one untimed render."""
         frames = step_schedule(wl, 0, rank, world)
         with torch.no_grad():
-            r.gaussians.find_knn(4)
+            if getattr(r.gaussians, "neighbor_indices", None) is None:
+                r.gaussians.find_knn(4)        # (never replace a table a captured graph may be reading)
             out = r.render_batch([cams_all[v] for (_, v, _) in frames], [f / wl["frames"] for (_, _, f) in frames],
                                  [m for (m, _, _) in frames], stage="s2", with_visibility=False, depth_normal=False,
                                  with_cpts=False)

@@ -360,8 +360,12 @@ class RenderStep:
                 self._seen += 1
                 return self._body(prep)[0]
             self.capacity = int(self._max_R * self.capacity_margin) + 1024
+            g = self.r.gaussians
             self._static = {"prep": self.r.clone_prep(prep),
-                            "overflow": torch.zeros(2, dtype=torch.int32, device=prep["cams"].device)}
+                            "overflow": torch.zeros(2, dtype=torch.int32, device=prep["cams"].device),
+                            # the captured launches read the model's KNN table by address: keep it alive even if the
+                            # model is given a new one (the graph then renders with the table it was captured with)
+                            "knn": (getattr(g, "neighbor_indices", None), getattr(g, "neighbor_dists", None))}
             stt = self._static
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
