@@ -334,3 +334,54 @@ def test_shim_precomputed_covariance_and_extra_attrs(cuda):
     assert tuple(out[5].shape) == (4, H, W) and float(out[5].max()) <= 1.0 + 1e-5 and float(out[5].min()) >= 0.0
     out[0].sum().backward()
     assert cov6.grad is not None and bool(torch.isfinite(cov6.grad).all()) and float(cov6.grad.abs().max()) > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("deg", [0, 1, 2, 3])
+def test_shared_parameter_gradients_summed_in_kernel(cuda, deg):
+    """Scales / opacities / SHs shared by all frames: the projection backward sums their gradients over the frames
+    inside the kernel (reduce_shared).  Must equal the per-frame path (the same inputs materialised per frame, whose
+    gradients autograd sums) for every SH degree and with the exp / sigmoid activations folded in, and the += variant
+    must add to what the gradient buffers already hold (direct_grads)."""
+    import math
+    import gpu_parity as gp
+    from dimo_b200 import raster as draster
+    from dimo_b200.camera import orbit_minicam
+    N, W, H, B = 1500, 80, 64, 5
+    K = (deg + 1) ** 2
+    xyz, scales, rot, op, shs = [t.cuda() for t in gp.scene_inputs(N, sh_coeffs=16, scale_boost=0.3)]
+    log_s, logit_o = torch.log(scales), torch.log(op / (1 - op))
+    cams = []
+    for v in range(B):
+        cam = orbit_minicam(v, B, W, H)
+        cams.append(draster.pack_cameras(cam.world_view_transform, cam.full_proj_transform, cam.camera_center,
+                                         math.tan(cam.FoVx / 2), math.tan(cam.FoVy / 2), torch.ones(3, device="cuda")))
+    cams = torch.cat(cams)
+    wc = torch.rand(B, 3, H, W, device="cuda"); wa = torch.rand(B, 1, H, W, device="cuda")
+
+    def run(mode):
+        ls, lo, lsh = [t.clone().requires_grad_(True) for t in (log_s, logit_o, shs)]
+        if mode == "per_frame":               # batched copies: the kernel writes per-frame gradients, autograd sums
+            out = draster.rasterize_batch(cams, xyz, ls[None].expand(B, -1, -1).contiguous(), rot,
+                                          lo[None].expand(B, -1, -1).contiguous(), W, H,
+                                          shs=lsh[None].expand(B, -1, -1, -1).contiguous(), sh_degree=deg,
+                                          raw_activations=True)
+        else:
+            if mode == "sink":                # preallocated gradient buffers holding earlier contributions
+                for t in (ls, lo, lsh):
+                    t.grad = torch.full_like(t, 0.25)
+            out = draster.rasterize_batch(cams, xyz, ls, rot, lo, W, H, shs=lsh, sh_degree=deg, raw_activations=True,
+                                          direct_grads=(mode == "sink"))
+        ((out[0] * wc).sum() + (out[3] * wa).sum()).backward()
+        return out, [ls.grad, lo.grad, lsh.grad]
+
+    out_p, g_p = run("per_frame")
+    out_s, g_s = run("shared")
+    out_k, g_k = run("sink")
+    for a, b in zip(out_p, out_s):
+        if a is not None:
+            assert torch.equal(a, b)
+    for a, b, c in zip(g_p, g_s, g_k):
+        assert gp.rel_err(b, a) < 1e-5 and gp.l2_err(b, a) < 1e-5
+        assert gp.rel_err(c - 0.25, a) < 1e-5
+    assert float(g_s[2][:, K:].abs().max() if K < 16 else 0.0) == 0.0        # inactive SH bands get exact zeros
