@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, DN ? 12 : 16) blend_fwd_kernel(
   const int tid = threadIdx.x;
   const int px0 = tx * TILE + (tid & 3) * PPT, pyi = ty * TILE + (tid >> 2);
   const float pxf0 = (float)px0, pyf = (float)pyi;
+  const f2 pxp[2] = {f2{pxf0, pxf0 + 1.0f}, f2{pxf0 + 2.0f, pxf0 + 3.0f}};     // x of the thread's four pixels
 
   const uint2 rng = ranges[tile];
   const int n = (int)(rng.y - rng.x);
@@ -207,13 +208,14 @@ __global__ void __launch_bounds__(BLEND_THREADS, DN ? 12 : 16) blend_fwd_kernel(
       for (int j = 0; j < cnt; ++j) {
         const float4 a = s[j * REC_F4 + 0];   // x, y, a2, b2
         const float4 bq = s[j * REC_F4 + 1];  // c2, opacity, pthr2, r
-        const float dy = a.y - pyf, dx0 = a.x - pxf0;
+        const float dy = a.y - pyf;
         const float by = a.w * dy, cy = bq.x * dy * dy;
-        // pixels (0,1) and (2,3) as packed pairs
+        // pixels (0,1) and (2,3) as packed pairs; their x coordinates live in two register pairs for the whole kernel
+        // (offsets built from immediates cost four uniform-register moves per visited record)
         f2 pp[2];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const f2 dx = sub2(f2_bcast(dx0), f2{(float)(2 * h), (float)(2 * h + 1)});
+          const f2 dx = sub2(f2_bcast(a.x), pxp[h]);
           pp[h] = fma2(fma2(f2_bcast(a.z), dx, f2_bcast(by)), dx, f2_bcast(cy));
         }
         const float p[PPT] = {pp[0].x, pp[0].y, pp[1].x, pp[1].y};
@@ -357,6 +359,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_bwd_kernel(
   const int lane = tid & 31, warp = tid >> 5;
   const int px0 = tx * TILE + (tid & 3) * PPT, pyi = ty * TILE + (tid >> 2);
   const float pxf0 = (float)px0, pyf = (float)pyi;
+  const f2 pxp[2] = {f2{pxf0, pxf0 + 1.0f}, f2{pxf0 + 2.0f, pxf0 + 3.0f}};     // x of the thread's four pixels
   const uint2 rng = ranges[tile];
   if (rng.y <= rng.x) return;
 
@@ -439,12 +442,12 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_bwd_kernel(
       // contributors at or behind this list position", one vote (see blend_fwd_kernel)
       const float4 a = s[j * REC_F4 + 0];
       const float4 bq = s[j * REC_F4 + 1];
-      const float dy = a.y - pyf, dx0 = a.x - pxf0;
+      const float dy = a.y - pyf;
       const float by = a.w * dy, cy = bq.x * dy * dy;
       f2 dxp[2], pp[2];                 // pixels (0,1) and (2,3) as packed pairs (FFMA2 / FMUL2 / FADD2)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        dxp[h] = sub2(f2_bcast(dx0), f2{(float)(2 * h), (float)(2 * h + 1)});
+        dxp[h] = sub2(f2_bcast(a.x), pxp[h]);
         pp[h] = fma2(fma2(f2_bcast(a.z), dxp[h], f2_bcast(by)), dxp[h], f2_bcast(cy));
       }
       const float p[PPT] = {pp[0].x, pp[0].y, pp[1].x, pp[1].y};
