@@ -190,13 +190,11 @@ class Renderer:
 
     def render_batch(self, cameras=None, times=None, latent_indices=None, stage="s2", scaling_modifier=1.0,
                      bg_color=None, override_color=None, xyz_detach=False, clamp=True, prepared=None, capacity=None,
-                     with_visibility=True, depth_normal=True, with_cpts=True, before_lbs=None):
+                     with_visibility=True, depth_normal=True, with_cpts=True):
         """All S frames of a step in ONE launch set.  cameras: list of S MiniCam (same W,H); times: list of S floats;
         latent_indices: list of S ints -- or `prepared` = the result of prepare_step().  capacity: instance-slot
         capacity for the sync-free rasteriser mode (None = exact mode with one host read-back).  depth_normal=False:
         depth / normal are not rendered (None in the result) -- for steps whose loss reads image + alpha only.
-        before_lbs: optional callable run after the TimeNet launches and before the skinning launch (trainstep.TrainStep
-        uses it to join the side stream that computes the KNN table while the TimeNet runs).
         Returns a dict of batched tensors: image [S,3,H,W] (clamped), image_raw, depth, normal, alpha, radii [S,N],
         visibility_filter, pts_t [U,N,3] (one block per unique (motion,t); frame f uses block pair_of_frame[f]),
         cpts_t [U,M,3] + `pair_of_frame`."""
@@ -219,8 +217,6 @@ class Renderer:
         if stage >= "s2":
             dxyz, dquat = g._timenet.forward_batched(g._c_xyz, t_dev, latents, pts_direct=done)   # [U,M,3],[U,M,4]
             cpts_t = g._c_xyz[None] + dxyz if with_cpts else None
-            if before_lbs is not None:      # e.g. join the stream on which the step's KNN ran beside the TimeNet
-                before_lbs()
             means3D_u, rot_u = _deform.lbs_deform(g._xyz, g._rotation, g._c_xyz, g._c_radius, dxyz, dquat,
                                                   g.neighbor_indices, g.neighbor_dists, direct_grads=direct, on_done=done)
         elif stage == "s1":

@@ -145,7 +145,6 @@ class TrainStep:
         self.poll_every = max(1, int(poll_every))
         self._replays = 0
         self._poll = None             # (event, pinned [4] floats) of the read in flight
-        self._knn_stream = None       # side stream of the per-step KNN (created on first use)
         self.skipped_steps = 0        # replays discarded because of an overflow (as far as polled)
         self.recaptures = 0
         self._bind_skip_flag()
@@ -183,23 +182,11 @@ class TrainStep:
 
     # ------------------------------------------------------------------------------------------
     def _body(self, prep, gt, mask, n_motions, optimize=True, capacity=None, overflow_acc=None):
-        join = None
         if self.stage >= "s2":
-            # the KNN table (Gaussian -> 4 nearest control points) only feeds the skinning, and the TimeNet chain that
-            # runs before it is latency-bound on at most 128 CTAs: compute the table on a side stream beside it
-            cur = torch.cuda.current_stream()
-            if self._knn_stream is None:
-                self._knn_stream = torch.cuda.Stream(device=self.g._xyz.device)
-            side = self._knn_stream
-            side.wait_stream(cur)
-            with torch.cuda.stream(side):
-                self.g.find_knn(4)
-            # (the table is allocated on the side stream and consumed on this one: no record_stream needed -- it stays
-            # referenced until the next find_knn replaces it, and that runs after side.wait_stream(cur) above)
-            join = lambda: cur.wait_stream(side)
+            self.g.find_knn(4)
         # the loss kernel clamps the render to [0,1] on load (and masks the gradient), so skip the separate clamp pass
         out = self.r.render_batch(prepared=prep, stage=self.stage, clamp=False, capacity=capacity,
-                                  with_visibility=False, depth_normal=self.regularisers, with_cpts=False, before_lbs=join)
+                                  with_visibility=False, depth_normal=self.regularisers, with_cpts=False)
         st = out["raster_state"]
         if capacity is None:
             self._max_R = max(self._max_R, st.R)
