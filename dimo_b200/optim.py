@@ -140,8 +140,54 @@ class FusedAdam:
                 "lrs": [g["lr"] for g in self.param_groups], "names": [g["name"] for g in self.param_groups]}
 
     def load_state_dict(self, sd):
+        """Accepts this class's own layout (state_dict above) and torch.optim.Adam's ({"state", "param_groups"}: a
+        checkpoint written by the reference, `capture()` at renderer/latent_gs_renderer.py:296-315, or by the
+        optimizer='torch' path).  torch keeps one step counter per parameter, this optimizer one for all: the largest
+        is taken (they are equal whenever every parameter received a gradient in every step, as on this path)."""
+        if "state" in sd and "param_groups" in sd:
+            by_name = {g.get("name", k): g for k, g in enumerate(sd["param_groups"])}
+            mom, step = {}, 0
+            for k, g in enumerate(self.param_groups):
+                tg = by_name.get(g["name"], sd["param_groups"][k] if k < len(sd["param_groups"]) else None)
+                if tg is None:
+                    continue
+                g["lr"] = float(tg.get("lr", g["lr"]))
+                live = [p for p in g["params"] if p.numel() > 0]
+                for p, idx in zip(live, tg["params"]):
+                    st = sd["state"].get(idx)
+                    if st is None:
+                        continue
+                    if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                        raise ValueError(f"optimizer state of group '{g['name']}' has shape {tuple(st['exp_avg'].shape)}, "
+                                         f"the parameter {tuple(p.shape)}")
+                    mom[id(p)] = (st["exp_avg"].to(self.flat.device, torch.float32),
+                                  st["exp_avg_sq"].to(self.flat.device, torch.float32))
+                    step = max(step, int(float(st["step"])))
+            self.exp_avg.zero_(); self.exp_avg_sq.zero_()
+            self.load_moments(mom)
+            self.state.zero_(); self.state[0] = step
+            self.sync_lrs()
+            return
         self.exp_avg.copy_(sd["exp_avg"]); self.exp_avg_sq.copy_(sd["exp_avg_sq"])
         self.state.zero_(); self.state[0] = int(sd["step"])
         for g, lr in zip(self.param_groups, sd["lrs"]):
             g["lr"] = float(lr)
         self.sync_lrs()
+
+    def torch_state_dict(self):
+        """The same state in torch.optim.Adam's layout (interchangeable checkpoints): parameters numbered group by
+        group, every parameter with the global step."""
+        state, groups, k = {}, [], 0
+        step = torch.tensor(float(int(self.state[0].item())))
+        for g in self.param_groups:
+            ids = []
+            for p in g["params"]:
+                if p.numel() == 0:
+                    continue
+                m, v = self.moments(p)
+                state[k] = {"step": step.clone(), "exp_avg": m.clone(), "exp_avg_sq": v.clone()}
+                ids.append(k); k += 1
+            groups.append({"lr": g["lr"], "name": g["name"], "betas": tuple(self.betas), "eps": self.eps, "weight_decay": 0,
+                           "amsgrad": False, "maximize": False, "foreach": None, "capturable": False,
+                           "differentiable": False, "fused": None, "decoupled_weight_decay": False, "params": ids})
+        return {"state": state, "param_groups": groups}

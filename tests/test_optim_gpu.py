@@ -186,3 +186,45 @@ def test_timenet_direct_grads_equal_autograd(cuda):
     import gpu_parity as gp
     for x, y in zip(a, b):
         assert gp.rel_err(y, x) < 1e-5
+
+
+@pytest.mark.gpu
+def test_fused_adam_restores_torch_format_checkpoint(cuda):
+    """A torch.optim.Adam state_dict (what the reference's capture() stores, renderer/latent_gs_renderer.py:296-315) is
+    restored into the flat moments, training continues as torch would, and torch_state_dict() round-trips it."""
+    from dimo_b200.dist import FlatGradReducer
+    from dimo_b200.optim import FusedAdam
+    shapes = [(40, 3), (40, 1), (9,), (5, 16)]
+    names, lrs = ["xyz", "opacity", "c_radius", "timenet"], [1.6e-4, 5e-2, 1e-3, 8e-4]
+    init, g = _make(shapes, 5)
+    grads = [[torch.randn(s, generator=g) for s in shapes] for _ in range(6)]
+    # reference run: torch.optim.Adam for 6 steps, checkpoint after 3
+    tp = [torch.nn.Parameter(t.clone().cuda()) for t in init]
+    topt = torch.optim.Adam([{"params": [p], "lr": lr, "name": n} for p, lr, n in zip(tp, lrs, names)], lr=0.0, eps=1e-15)
+    ckpt = None
+    for k in range(6):
+        for p, gr in zip(tp, grads[k]):
+            p.grad = gr.cuda()
+        topt.step()
+        if k == 2:
+            import copy
+            ckpt = (copy.deepcopy(topt.state_dict()), [p.detach().clone() for p in tp])
+    # fused optimizer restored from the torch checkpoint, three more steps
+    fp = [torch.nn.Parameter(t.clone()) for t in ckpt[1]]
+    red = FlatGradReducer(fp)
+    fopt = FusedAdam([{"params": [p], "lr": 0.0, "name": n} for p, n in zip(fp, names)], red, eps=1e-15)
+    fopt.load_state_dict(ckpt[0])
+    assert [gg["lr"] for gg in fopt.param_groups] == lrs and int(fopt.state[0]) == 3
+    for k in range(3, 6):
+        for p, gr in zip(fp, grads[k]):
+            p.grad.copy_(gr)
+        fopt.step(); fopt.zero_grad()
+    for a, b in zip(fp, tp):
+        assert torch.allclose(a.detach(), b.detach(), rtol=2e-6, atol=1e-7)
+    # and back: the torch layout of the fused state loads into a fresh torch optimizer
+    sd = fopt.torch_state_dict()
+    t2 = torch.optim.Adam([{"params": [p], "lr": lr, "name": n} for p, lr, n in zip(tp, lrs, names)], lr=0.0, eps=1e-15)
+    t2.load_state_dict(sd)
+    for i, p in enumerate(tp):
+        assert torch.allclose(t2.state[p]["exp_avg"], topt.state[p]["exp_avg"], rtol=1e-5, atol=1e-9)
+        assert int(t2.state[p]["step"]) == 6
