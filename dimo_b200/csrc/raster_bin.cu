@@ -74,24 +74,6 @@ __device__ __forceinline__ uint32_t warp_match(uint32_t key, int nbits, bool val
   return valid ? peers : 0u;
 }
 
-// The same, but only over the bits in which the valid lanes' keys differ at all (one REDUX.OR finds them): the 32
-// instances of a scatter window come from a few neighbouring splats, so their tile ids share most of their bits.
-__device__ __forceinline__ uint32_t warp_match_sparse(uint32_t key, bool valid) {
-  const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
-  if (vmask == 0u) return 0u;
-  const uint32_t ref = __shfl_sync(0xffffffffu, key, __ffs(vmask) - 1);
-  uint32_t diff = __reduce_or_sync(0xffffffffu, valid ? (key ^ ref) : 0u);
-  uint32_t peers = vmask;
-  while (diff) {                                   // warp-uniform
-    const int bit = __ffs(diff) - 1;
-    diff &= diff - 1;
-    const bool p = (key >> bit) & 1u;
-    const uint32_t b = __ballot_sync(0xffffffffu, p);
-    peers &= p ? b : ~b;
-  }
-  return valid ? peers : 0u;
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // 1. per-frame depth sort
 // ---------------------------------------------------------------------------------------------------------------
