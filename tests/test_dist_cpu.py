@@ -168,3 +168,56 @@ def test_densify_and_prune_is_rank_identical():
     g.prune(min_opacity=0.01, extent=4, max_screen_size=2)
     assert g._xyz.shape[0] == x0.shape[0]
     assert (g._xyz.detach().numpy() == x0).all()
+
+
+def _worker_direct(rank, world, port, q):
+    """Gradient sinks (trainstep direct_grads): 'kernels' write the gradients straight into the .grad views, no
+    AccumulateGrad node runs, the op reports through direct_written().  The early bucket must be launched exactly when
+    its last parameter has been reported, the overflow word of the tail must ride in the late bucket, and the result
+    must equal the sum over ranks."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    shapes = [(50, 3), (50, 4), (9, 3), (4, 8)]
+    params = [torch.nn.Parameter(torch.zeros(s)) for s in shapes]
+    red = FlatGradReducer(params, early=params[:2])
+    g = torch.Generator().manual_seed(20 + rank)
+    local = [torch.randn(s, generator=g) for s in shapes]
+    launched = []
+    orig = red._launch
+    red._launch = lambda lo, hi: (launched.append((lo, hi)), orig(lo, hi))[1]
+    with torch.no_grad():
+        params[0].grad.add_(local[0])                 # "LBS backward": first early parameter
+        red.direct_written([params[0]])
+        assert launched == [] and red.dirty
+        params[2].grad.add_(local[2])                 # a late parameter in between
+        red.direct_written([params[2]])
+        assert launched == []
+        params[1].grad.add_(local[1])                 # last early parameter -> bucket 0 goes out now
+        red.direct_written([params[1]])
+        assert launched == [(0, red.n_early)]
+        params[3].grad.add_(local[3])
+        red.direct_written([params[3]])
+        red.tail[0] = float(rank == 1)                # "this rank overflowed"
+    red.reduce()
+    assert launched[-1] == (red.n_early, red.n + 4) and len(launched) == 2
+    q.put((rank, [p.grad.numpy().copy() for p in params], [l.numpy().copy() for l in local], float(red.tail[0])))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_direct_written_bookkeeping_two_ranks():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_direct, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, g0, l0, t0), (_, g1, l1, t1) = res
+    assert t0 == t1 == 1.0                            # number of ranks that overflowed, identical everywhere
+    for a, b, x, y in zip(g0, g1, l0, l1):
+        assert (a == b).all() and torch.allclose(torch.tensor(a), torch.tensor(x) + torch.tensor(y))

@@ -44,3 +44,27 @@ def test_one_pair_per_frame_needs_no_expansion():
     cams = [orbit_minicam(v, 4, 32, 32, device="cpu") for v in range(3)]
     prep = r.prepare_step(cams, [0.0, 0.5, 0.75], [0, 0, 1])
     assert prep["U"] == 3 and prep["expand"] is False
+
+
+def test_clone_prep_owns_its_buffer():
+    """the static inputs of a captured graph: a deep copy whose tensors are views of ONE own buffer, refreshed in place
+    by prepare_step(out=...)"""
+    import torch
+    from dimo_b200.camera import orbit_minicam
+    from dimo_b200.renderer import Renderer
+    r = Renderer(sh_degree=0, num_latent_code=4, device="cpu")
+    r.gaussians._xyz = torch.zeros(4, 3)
+    cams = [orbit_minicam(v, 3, 32, 32, device="cpu") for v in range(3)]
+    prep = r.prepare_step(cams, [0.0, 0.5, 0.5], [0, 1, 1])
+    st = Renderer.clone_prep(prep)
+    assert st["_buf"].data_ptr() != prep["_buf"].data_ptr()
+    for k in ("cams", "t", "li", "pf", "pf32"):
+        assert torch.equal(st[k], prep[k])
+        lo, hi = st["_buf"].data_ptr(), st["_buf"].data_ptr() + st["_buf"].numel()
+        assert lo <= st[k].data_ptr() < hi                       # a view of the clone's own buffer
+    keep = st["cams"]
+    r.prepare_step(cams[::-1], [0.25, 0.25, 0.75], [2, 2, 3], out=st)
+    assert keep.data_ptr() == st["cams"].data_ptr()
+    assert st["li"].tolist() == [2, 3] and st["pf"].tolist() == [0, 0, 1]
+    assert torch.allclose(st["t"], torch.tensor([0.25, 0.75]))
+    assert torch.equal(prep["li"], torch.tensor([0, 1]))         # the original is untouched
