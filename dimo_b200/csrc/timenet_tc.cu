@@ -19,7 +19,11 @@
 //   activations    A[rb][kt]      rb = 128-row block, kt = 32-column block of the activation matrix; 2 x 16 KB
 //   weights        B[kt]          rows = output features of the GEMM (padded to a multiple of 16), 2 x rows*128 B
 //   transposed     T[rt][plane][fb]  rt = 32-row block, fb = 128-feature block; tile rows = features, k = row index
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace dimo {
 
@@ -395,42 +399,22 @@ __device__ __forceinline__ void tn_named_bar(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
+// The three warp roles of ONE layer (shared by the single-layer kernel and the chain kernel).  `it_base`: k tiles this
+// CTA has pushed through its stage ring before this layer (mbarrier phases continue across layers); `done_parity`:
+// parity of the layers this CTA has finished.
 template <int NB>
-__global__ void __launch_bounds__(TG_THREADS, NB == 64 ? 2 : 1) tn_gemm_kernel(const __grid_constant__ TnGemmArgs p) {
+__device__ __forceinline__ void tn_layer_roles(const TnGemmArgs& p, uint8_t* smem, uint64_t* full_bar, uint64_t* empty_bar,
+                                               uint64_t& done_bar, uint32_t tmem_d, int it_base, uint32_t done_parity,
+                                               int rb, int cb) {
   using C = TgCfg<NB>;
   constexpr int TG_STAGES = C::STAGES, TG_STAGE = C::STAGE, TG_TSTAGE = C::TSTAGE;
-  extern __shared__ uint8_t tn_smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[TG_STAGES], empty_bar[TG_STAGES], done_bar;
-  __shared__ uint32_t tmem_slot;
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tn_smem_raw) + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int rb = blockIdx.x, cb = blockIdx.y;
-  if (tid == 0) tn_stamp(p.dbg, 0);
   const uint32_t planeB_full = (uint32_t)p.N * 128u;          // bytes of one plane of a packed weight tile (all N rows)
   constexpr uint32_t planeB = NB * 128u;                      // this CTA's NB rows of it
-
-  if (warp == 9) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tn_smem_u32(&tmem_slot)),
-                 "r"((uint32_t)NB)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < TG_STAGES; ++s) { tn_mbar_init(&full_bar[s], 1); tn_mbar_init(&empty_bar[s], 1); }
-    tn_mbar_init(&done_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_d = tmem_slot;
-  if (tid == 0) tn_stamp(p.dbg, 1);
-
   if (warp == 8) {
     // ===== producer: three bulk copies per stage (A split tile, B hi rows, B lo rows) =====
     if (lane == 0) {
-      int it = 0;
+      int it = it_base;
       for (int sg = 0; sg < p.nseg; ++sg) {
         const TnSeg& s = p.seg[sg];
         for (int kt = 0; kt < s.nkt; ++kt, ++it) {
@@ -452,10 +436,11 @@ __global__ void __launch_bounds__(TG_THREADS, NB == 64 ? 2 : 1) tn_gemm_kernel(c
       const uint32_t idesc = tn_idesc(TN_BM, NB);
       int total = 0;
       for (int sg = 0; sg < p.nseg; ++sg) total += p.seg[sg].nkt;
-      for (int it = 0; it < total; ++it) {
+      for (int k = 0; k < total; ++k) {
+        const int it = it_base + k;
         const int st = it % TG_STAGES, round = it / TG_STAGES;
         tn_mbar_wait(&full_bar[st], (uint32_t)(round & 1));
-        if (it == 0) tn_stamp(p.dbg, 2);
+        if (k == 0) tn_stamp(p.dbg, 2);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sa = tn_smem_u32(smem + st * TG_STAGE), sb = sa + TN_STAGE_A;
 #pragma unroll
@@ -463,7 +448,7 @@ __global__ void __launch_bounds__(TG_THREADS, NB == 64 ? 2 : 1) tn_gemm_kernel(c
           const uint32_t koff = (uint32_t)ks * 256u;
           const uint64_t dah = tn_desc(sa + koff), dal = tn_desc(sa + TN_PLANE_A + koff);
           const uint64_t dbh = tn_desc(sb + koff), dbl = tn_desc(sb + planeB + koff);
-          tn_mma(tmem_d, dah, dbh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+          tn_mma(tmem_d, dah, dbh, idesc, (k > 0 || ks > 0) ? 1u : 0u);
           tn_mma(tmem_d, dah, dbl, idesc, 1u);
           tn_mma(tmem_d, dal, dbh, idesc, 1u);
         }
@@ -513,7 +498,7 @@ __global__ void __launch_bounds__(TG_THREADS, NB == 64 ? 2 : 1) tn_gemm_kernel(c
         mbits = bits;
       }
       if (!waited) {
-        tn_mbar_wait(&done_bar, 0);
+        tn_mbar_wait(&done_bar, done_parity);
         if (tid == 0) tn_stamp(p.dbg, 5);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         waited = true;
@@ -587,9 +572,102 @@ __global__ void __launch_bounds__(TG_THREADS, NB == 64 ? 2 : 1) tn_gemm_kernel(c
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // shared memory may be released after the reads
     if (tid == 0) tn_stamp(p.dbg, 6);
   }
+}
+
+template <int NB>
+__global__ void __launch_bounds__(TG_THREADS, NB == 64 ? 2 : 1) tn_gemm_kernel(const __grid_constant__ TnGemmArgs p) {
+  using C = TgCfg<NB>;
+  constexpr int TG_STAGES = C::STAGES, TG_STAGE = C::STAGE, TG_TSTAGE = C::TSTAGE;
+  extern __shared__ uint8_t tn_smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[TG_STAGES], empty_bar[TG_STAGES], done_bar;
+  __shared__ uint32_t tmem_slot;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tn_smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rb = blockIdx.x, cb = blockIdx.y;
+  if (tid == 0) tn_stamp(p.dbg, 0);
+  const uint32_t planeB_full = (uint32_t)p.N * 128u;          // bytes of one plane of a packed weight tile (all N rows)
+  constexpr uint32_t planeB = NB * 128u;                      // this CTA's NB rows of it
+
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tn_smem_u32(&tmem_slot)),
+                 "r"((uint32_t)NB)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < TG_STAGES; ++s) { tn_mbar_init(&full_bar[s], 1); tn_mbar_init(&empty_bar[s], 1); }
+    tn_mbar_init(&done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = tmem_slot;
+  if (tid == 0) tn_stamp(p.dbg, 1);
+
+  tn_layer_roles<NB>(p, smem, full_bar, empty_bar, done_bar, tmem_d, 0, 0u, rb, cb);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (tid == 0) tn_stamp(p.dbg, 7);
+  if (warp == 9) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)NB) : "memory");
+  }
+}
+
+// The whole chain of layers in ONE launch.  Rows are independent, so the only dependency between layer l and l + 1
+// is inside a 128-row block: the four CTAs that own its four 64-column slabs.  They form a thread-block cluster
+// (1 x 4 x 1); a layer's output tiles go to global memory as before (the backward needs them anyway) and a CLUSTER
+// barrier -- not a kernel boundary -- separates the layers: ~1 us instead of the ~5 us of launch gap, prologue and
+// teardown per layer.  Generic-proxy stores are fenced into the async proxy before the barrier because the next layer
+// reads them with bulk copies.
+struct TnChainArgs { int nlayers; TnGemmArgs layer[10]; };
+
+__global__ void __cluster_dims__(1, 4, 1) __launch_bounds__(TG_THREADS, 2) tn_chain_kernel(const __grid_constant__ TnChainArgs c) {
+  constexpr int NB = 64;
+  using C = TgCfg<NB>;
+  constexpr int TG_STAGES = C::STAGES;
+  extern __shared__ uint8_t tn_smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[TG_STAGES], empty_bar[TG_STAGES], done_bar;
+  __shared__ uint32_t tmem_slot;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tn_smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int rb = blockIdx.x, cb = blockIdx.y;
+  cg::cluster_group cluster = cg::this_cluster();
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tn_smem_u32(&tmem_slot)),
+                 "r"((uint32_t)NB)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < TG_STAGES; ++s) { tn_mbar_init(&full_bar[s], 1); tn_mbar_init(&empty_bar[s], 1); }
+    tn_mbar_init(&done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = tmem_slot;
+  int it_base = 0;
+  uint32_t n_done = 0;
+  for (int L = 0; L < c.nlayers; ++L) {
+    const TnGemmArgs& p = c.layer[L];
+    if (cb * NB < p.N) {                                   // (128-column layers use two of the four CTAs)
+      tn_layer_roles<NB>(p, smem, full_bar, empty_bar, done_bar, tmem_d, it_base, n_done & 1u, rb, cb);
+      for (int sg = 0; sg < p.nseg; ++sg) it_base += p.seg[sg].nkt;
+      ++n_done;
+    }
+    if (L + 1 < c.nlayers) {
+      asm volatile("fence.proxy.async;" ::: "memory");     // this thread's global stores -> visible to bulk copies
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      cluster.sync();                                      // release / acquire at cluster scope
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
   if (warp == 9) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)NB) : "memory");
   }
@@ -803,6 +881,7 @@ int tn_set_attrs() {
   if (!done) {
     DIMO_CHECK_CUDA(cudaFuncSetAttribute(tn_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TgCfg<64>::SMEM));
     DIMO_CHECK_CUDA(cudaFuncSetAttribute(tn_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TgCfg<128>::SMEM));
+    DIMO_CHECK_CUDA(cudaFuncSetAttribute(tn_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TgCfg<64>::SMEM));
     DIMO_CHECK_CUDA(cudaFuncSetAttribute(tn_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM));
     done = true;
   }
@@ -821,6 +900,13 @@ extern "C" int dimo_timenet_embed_fwd(int G, int rows_per_group, int L, const fl
                                       const float* latents, float* h0, int64_t ldh, void* stream);
 extern "C" int dimo_timenet_embed_bwd(int G, int rows_per_group, int L, const float* h0, const float* dh0, int64_t ldh,
                                       float* dpts, float* dlatents, void* stream);
+
+// all layers of one direction in one cluster launch (tn_chain_kernel) when the 64-column tiles are in use and nobody
+// asked for per-layer phase stamps; DIMO_TN_CHAIN=0 falls back to one launch per layer
+static bool tn_use_chain(int nrb) {
+  static const bool on = [] { const char* e = getenv("DIMO_TN_CHAIN"); return !(e != nullptr && e[0] == '0'); }();
+  return on && tn_pick_nb(nrb, 256) == 64;
+}
 
 static unsigned long long* g_tn_dbg = nullptr;
 static int g_tn_dbg_launch = 0;
@@ -910,7 +996,10 @@ extern "C" int dimo_timenet_fwd(int G, int M, int L, const float* pts, const flo
     DIMO_CHECK_LAUNCH();
   }
   // ---- the ten 256-wide layers ----
+  const bool chained = tn_use_chain(o.nrb) && g_tn_dbg == nullptr;
+  TnChainArgs chain{};
   auto gemm = [&](TnGemmArgs& g) {
+    if (chained) { g.dbg = nullptr; chain.layer[chain.nlayers++] = g; return 0; }
     g.dbg = g_tn_dbg != nullptr ? g_tn_dbg + (size_t)(g_tn_dbg_launch++ % 32) * 128 * 8 : nullptr;
     return tn_launch_gemm(g, o.nrb, st);
   };
@@ -934,6 +1023,10 @@ extern "C" int dimo_timenet_fwd(int G, int M, int L, const float* pts, const flo
     else if (l == 8 || l == 10) { g.outT = nullptr; }                 // hp / hr feed only the SIMT heads
     else { g.outT = ws + o.yT[slot]; g.t_nfb = 2; g.t_f0 = 0; }
     if (gemm(g)) { dimo::set_error("tn_gemm_kernel launch failed (layer %d)", l); return -1; }
+  }
+  if (chained) {
+    tn_chain_kernel<<<dim3(o.nrb, 4), TG_THREADS, TgCfg<64>::SMEM, st>>>(chain);
+    DIMO_CHECK_LAUNCH();
   }
   // ---- 3- and 4-wide heads (FP32 SIMT, one launch) ----
   tn_heads_fwd_kernel<<<ceil_div(R, 8), 256, 0, st>>>(R, ws + o.y[8], ws + o.y[9], W_host[9], b_host[9], W_host[11],
@@ -960,7 +1053,10 @@ extern "C" int dimo_timenet_bwd(int G, int M, int L, const float* const* W_host,
                                                       dW_host[11], db_host[11], dimo::det_scale());
   DIMO_CHECK_LAUNCH();
   int rc = 0;
+  const bool chained = tn_use_chain(o.nrb) && g_tn_dbg == nullptr;
+  TnChainArgs chain{};
   auto gemm = [&](TnGemmArgs& g) {
+    if (chained) { g.dbg = nullptr; chain.layer[chain.nlayers++] = g; return 0; }
     g.dbg = g_tn_dbg != nullptr ? g_tn_dbg + (size_t)(g_tn_dbg_launch++ % 32) * 128 * 8 : nullptr;
     return tn_launch_gemm(g, o.nrb, st);
   };
@@ -996,6 +1092,10 @@ extern "C" int dimo_timenet_bwd(int G, int M, int L, const float* const* W_host,
     e.seg[0] = TnSeg{ws + o.g[0], 8, 0, ws + o.w_bwd[0], 8};
     e.plain = dcat; e.ldp = E; e.plain_cols = E; e.plain_acc = 1;
     if (gemm(e)) { dimo::set_error("tn_gemm_kernel launch failed (data gradient, layer 0)"); return -1; }
+  }
+  if (chained) {
+    tn_chain_kernel<<<dim3(o.nrb, 4), TG_THREADS, TgCfg<64>::SMEM, st>>>(chain);
+    DIMO_CHECK_LAUNCH();
   }
   if (dpts != nullptr || dlatents != nullptr) {
     rc = dimo_timenet_embed_bwd(G, M, L, reinterpret_cast<float*>(ws + o.cat_plain), dcat, E, dpts, dlatents, stream);
