@@ -48,6 +48,7 @@ _SIGS = {
     "dimo_timenet_workspace_bytes": (c_sz, [c_int] * 3),
     "dimo_timenet_layout": (c_int, [c_int] * 3 + [c_vp]),
     "dimo_timenet_debug_stamps": (c_int, [c_vp]),
+    "dimo_timenet_last_launches": (c_int, []),
     "dimo_timenet_fwd": (c_int, [c_int] * 3 + [c_vp] * 6 + [c_sz] + [c_vp] * 3),
     "dimo_timenet_bwd": (c_int, [c_int] * 3 + [c_vp] * 2 + [c_sz] + [c_vp] * 7),
     "dimo_timenet_embed_fwd": (c_int, [c_int] * 3 + [c_vp] * 4 + [c_i64, c_vp]),
@@ -162,7 +163,8 @@ _OWN_LAUNCHES = {
     "dimo_arap_connectivity": 1, "dimo_arap_energy": 1, "dimo_linear_fwd": 1,
     "dimo_linear_bwd_data": 1, "dimo_linear_tc": 1, "dimo_linear_wgrad_tc": 1, "dimo_linear_wgrad_tc_grouped": 1, "dimo_linear_bwd_weight": 1, "dimo_timenet_embed_fwd": 1,
     "dimo_timenet_embed_bwd": 1, "dimo_lbs_fwd": 1, "dimo_lbs_bwd": 1, "dimo_ssim_fwd": 1, "dimo_ssim_bwd": 1,
-    "dimo_timenet_fwd": 14, "dimo_timenet_bwd": 14, "dimo_fixed_to_float": 1,
+    "dimo_timenet_fwd": None, "dimo_timenet_bwd": None,      # asked from the library after the call (chained or per layer)
+    "dimo_fixed_to_float": 1,
     "dimo_sqdiff_sum": 1, "dimo_smooth_fwd": 1, "dimo_smooth_bwd": 1, "dimo_segment_sum": 1, "dimo_adam_step": 1, "dimo_transpose_grouped": 1, "dimo_gt_fetch": 1,
 }
 
@@ -177,6 +179,7 @@ class _Profile:
         self.enabled = enabled
         self.events = []          # (name, start, end)
         self.counts = {}
+        self.dyn_launches = 0     # launches of calls whose count depends on the shape (asked from the library)
         self.extra = getattr(self, "extra", {})
 
     def summary(self):
@@ -189,7 +192,7 @@ class _Profile:
         return out
 
     def kernel_launches_per_step(self, steps):
-        n = sum(_OWN_LAUNCHES.get(k, 0) * v for k, v in self.counts.items())
+        n = sum((_OWN_LAUNCHES.get(k, 0) or 0) * v for k, v in self.counts.items()) + self.dyn_launches
         return n // max(steps, 1)
 
 
@@ -209,6 +212,8 @@ def call(name, *args):
         e1.record()
         PROFILE.events.append((name, e0, e1))
         PROFILE.counts[name] = PROFILE.counts.get(name, 0) + 1
+        if name in _OWN_LAUNCHES and _OWN_LAUNCHES[name] is None:
+            PROFILE.dyn_launches += int(lib().dimo_timenet_last_launches())
     else:
         check(fn(*args))
     if SYNC_EVERY_CALL:

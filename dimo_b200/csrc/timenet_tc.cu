@@ -908,6 +908,11 @@ static bool tn_use_chain(int nrb) {
   return on && tn_pick_nb(nrb, 256) == 64;
 }
 
+static int g_tn_last_launches = 0;
+/* kernel launches issued by the most recent dimo_timenet_fwd / dimo_timenet_bwd call of this process (5 / 4 with the
+ * chained GEMMs, 14 / 13 with one launch per layer): bench.py's gpu_launches counts with it */
+extern "C" int dimo_timenet_last_launches(void) { return g_tn_last_launches; }
+
 static unsigned long long* g_tn_dbg = nullptr;
 static int g_tn_dbg_launch = 0;
 /* bring-up: device buffer of 32 x 128 x 8 u64; the following tn_gemm launches stamp [launch % 32][cta][8] with %globaltimer (NULL: off) */
@@ -1028,6 +1033,7 @@ extern "C" int dimo_timenet_fwd(int G, int M, int L, const float* pts, const flo
     tn_chain_kernel<<<dim3(o.nrb, 4), TG_THREADS, TgCfg<64>::SMEM, st>>>(chain);
     DIMO_CHECK_LAUNCH();
   }
+  g_tn_last_launches = 4 + (chained ? 1 : 10);      // pack, embed, tiles, GEMMs, heads
   // ---- 3- and 4-wide heads (FP32 SIMT, one launch) ----
   tn_heads_fwd_kernel<<<ceil_div(R, 8), 256, 0, st>>>(R, ws + o.y[8], ws + o.y[9], W_host[9], b_host[9], W_host[11],
                                                       b_host[11], dxyz, dquat);
@@ -1097,6 +1103,7 @@ extern "C" int dimo_timenet_bwd(int G, int M, int L, const float* const* W_host,
     tn_chain_kernel<<<dim3(o.nrb, 4), TG_THREADS, TgCfg<64>::SMEM, st>>>(chain);
     DIMO_CHECK_LAUNCH();
   }
+  g_tn_last_launches = 2 + (chained ? 1 : 10) + ((dpts != nullptr || dlatents != nullptr) ? 1 : 0);   // heads, GEMMs, wgrad, embed
   if (dpts != nullptr || dlatents != nullptr) {
     rc = dimo_timenet_embed_bwd(G, M, L, reinterpret_cast<float*>(ws + o.cat_plain), dcat, E, dpts, dlatents, stream);
     if (rc) return rc;

@@ -244,6 +244,7 @@ int dimo_linear_wgrad_tc_grouped(int n, int R, const int* K, const int* No, cons
  * ------------------------------------------------------------------------------------------- */
 size_t dimo_timenet_workspace_bytes(int G, int M, int L);
 int dimo_timenet_layout(int G, int M, int L, int64_t* out12_host);
+int dimo_timenet_last_launches(void);           /* kernel launches of the latest dimo_timenet_fwd / _bwd call (5 / 4 chained, 14 / 13 per layer) */
 int dimo_timenet_debug_stamps(void* dev_buf);   /* bring-up: 64 x 8 u64 of per-CTA phase time stamps, NULL = off */
 int dimo_timenet_fwd(int G, int M, int L, const float* pts, const float* times, const float* latents,
                      const float* const* W_host, const float* const* b_host, void* workspace, size_t workspace_bytes,
