@@ -39,6 +39,18 @@ def test_sm100a_sass_and_tma_present():
     assert "sm_100a" in out or "SM100" in out.upper()
     assert "UBLKCP" in out, "blend kernel lost its bulk-TMA staging"
     assert "SYNCS" in out, "mbarrier instructions missing"
+    # the mnemonics B200_PROFILING.md lists as proof of the Blackwell paths, plus the ones this design relies on
+    for mnem, what in (("UBLKCP.S.G", "bulk TMA global -> shared (blend records, TimeNet operands)"),
+                       ("UBLKCP.G.S", "bulk TMA shared -> global (TimeNet transposed tiles)"),
+                       ("UTCHMMA", "tcgen05.mma kind::tf32 (TimeNet GEMMs, weight gradient)"),
+                       ("LDTM", "tcgen05.ld: accumulators read back from TMEM"),
+                       ("UTCBAR", "tcgen05.commit -> mbarrier"),
+                       ("UCGABAR", "cluster barriers (depth sort, chained TimeNet layers)"),
+                       ("FFMA2", "packed fp32 pairs in the blend / SSIM inner loops"),
+                       ("REDG.E.ADD.F32x4", "128-bit global reductions of the blend backward"),
+                       ("FENCE.VIEW.ASYNC", "generic -> async proxy fences in front of bulk copies")):
+        assert mnem in out, f"SASS lost {mnem}: {what}"
+    assert "MATCH.ANY" not in out, "MATCH.ANY is ~900 cycles per use on B200 (profiles r2e): use the ballot matcher"
 
 
 def test_product_never_imports_oracle():
